@@ -1,0 +1,167 @@
+/* libhpvg — C ABI of the B200-native HP-VAE-GAN hot path.
+ *
+ * The reference (SakiRinn/mindspore-hp-vae-gan) has no FFI of its own: its operator surface is MindSpore
+ * `nn.Cell`s and one `Primitive` (src/tools/trilinear.py:171-254).  This header is the boundary a maintainer binds
+ * instead of the MindSpore library ops listed in SURVEY.md §2.2 — through `ops.Custom(func_type="aot")` (the
+ * `Hpvg*` entry points at the bottom have exactly that signature) or through ctypes (everything else).
+ * INTEGRATION.md shows both bindings.
+ *
+ * Conventions
+ *   - every pointer named d_* / "device" is a CUDA device pointer owned by the caller; the library never frees it.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Nothing synchronises inside.
+ *   - return value: 0 on success, negative HPVG_E_* on failure; hpvg_last_error() gives a thread-local message.
+ *   - "cl" tensors are channels-last bf16: (N, T, H, W, Cpitch); "ncdhw" tensors are fp32 (N, C, T, H, W) — the
+ *     layout of the reference's Tensors.  2-D (N, C, H, W) data is the T == 1 case.
+ */
+#ifndef HPVG_H_
+#define HPVG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPVG_OK 0
+#define HPVG_E_CUDA (-1)
+#define HPVG_E_ARG (-2)
+#define HPVG_E_UNSUPPORTED (-3)
+
+/* conv kernel variants / epilogues (values mirror csrc/conv3d_umma.h) */
+#define HPVG_CONV_64_64 0 /* Cin 64 -> Cout 64                                   */
+#define HPVG_CONV_64_16 1 /* Cin 64 -> Cout <= 4 real (tail convs 64->3, 64->1)  */
+#define HPVG_CONV_8_64 2  /* Cin <= 8 (zero padded to 8) -> Cout 64 (head convs) */
+#define HPVG_ACT_NONE 0
+#define HPVG_ACT_LRELU 1 /* LeakyReLU(0.2): mindspore.nn.LeakyReLU default, networks_3d.py:20 */
+#define HPVG_ACT_TANH 2
+#define HPVG_OUT_BF16_CL 0
+#define HPVG_OUT_F32_NCDHW 1
+#define HPVG_OUT_F32_RAW 2
+
+/* ---------------------------------------------------------------- runtime (ctypes route; MindSpore owns these itself) */
+int hpvg_version(void);
+const char* hpvg_last_error(void);
+int hpvg_device_count(void);
+int hpvg_init(int device);
+int hpvg_sm_count(void);
+int hpvg_malloc(void** d_ptr, size_t bytes);
+int hpvg_free(void* d_ptr);
+int hpvg_host_alloc(void** h_ptr, size_t bytes); /* pinned */
+int hpvg_host_free(void* h_ptr);
+int hpvg_memset(void* d_ptr, int value, size_t bytes, void* stream);
+int hpvg_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);
+int hpvg_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
+int hpvg_d2d(void* d_dst, const void* d_src, size_t bytes, void* stream);
+int hpvg_stream_create(void** stream);
+int hpvg_stream_destroy(void* stream);
+int hpvg_stream_sync(void* stream);
+int hpvg_device_sync(void);
+int hpvg_event_create(void** event);
+int hpvg_event_destroy(void* event);
+int hpvg_event_record(void* event, void* stream);
+int hpvg_event_sync(void* event);
+int hpvg_event_elapsed_ms(void* start, void* stop, float* ms);
+/* CUDA-graph capture of everything enqueued on `stream` between begin and end */
+int hpvg_graph_begin(void* stream);
+int hpvg_graph_end(void* stream, void** graph_exec);
+int hpvg_graph_launch(void* graph_exec, void* stream);
+int hpvg_graph_destroy(void* graph_exec);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long hpvg_launch_count(void);
+
+/* ---------------------------------------------------------------- layout changes at the API edge */
+/* fp32 (N,C,T,H,W) -> bf16 (N,T,H,W,c_pitch) channels [c_off, c_off+C); channels [c_off+C, c_off+c_zero_to) := 0 */
+int hpvg_pack_cl(const float* d_x, int N, int C, int T, int H, int W, void* d_y, int c_pitch, int c_off,
+                 int c_zero_to, void* stream);
+/* bf16 (N,T,H,W,c_pitch) channels [c_off, c_off+C) -> fp32 (N,C,T,H,W) */
+int hpvg_unpack_cl(const void* d_x, int N, int C, int T, int H, int W, int c_pitch, int c_off, float* d_y,
+                   void* stream);
+
+/* ---------------------------------------------------------------- convolution
+ * Replaces nn.Conv3d / nn.Conv2d 3x3(x3), stride 1, zero pad 1 (networks_3d.py:48-50,380,399; networks_2d.py:47-49;
+ * spectral_norm.py:152).  Weights are first packed into the kernel's shared-memory image. */
+int hpvg_conv_wimg_bytes(int mode);
+/* d_w: fp32 (w_cout, w_cin, kt, 3, 3), kt in {1,3}.  Packs the sub-filter [cout_off, +cout) x [cin_off, +cin).
+ * transpose_flip = 1 packs the data-gradient filter (roles of cin/cout swapped, taps mirrored). */
+int hpvg_conv_pack_weights(const float* d_w, int w_cout, int w_cin, int kt, int mode, int transpose_flip,
+                           int cout_off, int cout, int cin_off, int cin, void* d_wimg, void* stream);
+/* y = act((conv(x) [+ addend_raw]) * scale + shift [+ residual]) ; see HPVG_OUT_* for the output layouts.
+ *  d_in     bf16 cl, in_pitch channels per voxel (the kernel reads 64 — or 8 — channels starting at d_in)
+ *  d_scale/d_shift fp32 [Cout]: bias, folded BatchNorm, 1/sigma of spectral norm
+ *  d_addend HPVG_OUT_BF16_CL: optional fp32 [voxels][64] partial sums (split-Cin accumulation)
+ *           HPVG_OUT_F32_NCDHW: optional fp32 ncdhw residual (tanh(block(x)+up), networks_3d.py:450)            */
+int hpvg_conv_cl(int mode, int N, int T, int H, int W, const void* d_in, int in_pitch, const void* d_wimg,
+                 const float* d_scale, const float* d_shift, int act, int out_mode, void* d_out, int out_pitch,
+                 int out_coff, int cout_real, const float* d_addend, void* stream);
+
+/* ---------------------------------------------------------------- linear resize
+ * Replaces UpsampleTrilinear3D(output_size, align_corners) (src/tools/trilinear.py:171-254, called from
+ * src/utils/images.py:54-61) and ops.ResizeBilinear (images.py:41).  Index / weight tables are computed on the host
+ * in IEEE fp32 with the reference's rule and are exposed for bit-exact checking. */
+int hpvg_linear_taps(int n_in, int n_out, int align_corners, int32_t* i0, int32_t* i1, float* l0, float* l1);
+/* the same tables computed by the device code path (test hook: device arrays of n_out entries) */
+int hpvg_linear_taps_dev(int n_in, int n_out, int align_corners, int32_t* d_i0, int32_t* d_i1, float* d_l0, float* d_l1,
+                         void* stream);
+int hpvg_resize3d_fwd(const float* d_x, int N, int C, int Ti, int Hi, int Wi, float* d_y, int To, int Ho, int Wo,
+                      int align_corners, void* stream);
+int hpvg_resize3d_bwd(const float* d_gy, int N, int C, int To, int Ho, int Wo, float* d_gx, int Ti, int Hi, int Wi,
+                      int align_corners, void* stream);
+/* fused block input stage (networks_3d.py:440-446): up = resize(x_prev); x_in = up + noise*amp;
+ * writes up (fp32 ncdhw, the residual) and x_in (bf16 cl, 8-channel padded).  d_noise may be NULL (no noise), or
+ * noise_seed != 0 generates N(0,1) on the device with Philox keyed by (seed, sample index, element). */
+int hpvg_upsample_noise_pack(const float* d_x, int N, int C, int Ti, int Hi, int Wi, int To, int Ho, int Wo,
+                             const float* d_noise, float amp, uint64_t noise_seed, uint64_t sample_base,
+                             float* d_up, void* d_xin_cl, void* stream);
+
+/* ---------------------------------------------------------------- BatchNorm (training mode), channels-last bf16, C == 64
+ * Replaces nn.BatchNorm3d in set_train() mode (networks_3d.py:52): batch mean / biased variance over N*T*H*W. */
+int hpvg_bn_stats_cl(const void* d_y, long long voxels, double* d_sum /*[64]*/, double* d_sumsq /*[64]*/,
+                     void* stream);
+/* scale = gamma/sqrt(var+eps), shift = beta - mean*scale; also updates moving stats (momentum 0.9) */
+int hpvg_bn_finalize(const double* d_sum, const double* d_sumsq, long long count, const float* d_gamma,
+                     const float* d_beta, float eps, float momentum, float* d_moving_mean, float* d_moving_var,
+                     float* d_scale, float* d_shift, float* d_mean, float* d_invstd, void* stream);
+/* x = lrelu(y*scale + shift), elementwise on (voxels, 64) bf16 */
+int hpvg_bn_apply_lrelu_cl(const void* d_y, long long voxels, const float* d_scale, const float* d_shift, int act,
+                           void* d_x, void* stream);
+
+/* ---------------------------------------------------------------- spectral norm (spectral_norm.py:142-151)
+ * One power iteration on W viewed (Cout, K): v <- l2n(W^T u); u <- l2n(W v); sigma = u^T W v.
+ * Updates d_u, d_v in place and writes sigma and 1/sigma. */
+int hpvg_sn_power_iter(const float* d_w, int cout, int k, float* d_u, float* d_v, float* d_sigma,
+                       float* d_inv_sigma, void* stream);
+
+/* ---------------------------------------------------------------- small fused elementwise / reductions */
+/* scale[c] = a[c]*mul ; shift[c] = b[c]  helpers for epilogue vectors */
+int hpvg_bn_fold_eval(const float* d_gamma, const float* d_beta, const float* d_mean, const float* d_var, float eps,
+                      const float* d_bias, int C, float* d_scale, float* d_shift, void* stream);
+int hpvg_affine_from_bias(const float* d_bias, const float* d_inv_sigma /*nullable*/, int C, float* d_scale,
+                          float* d_shift, void* stream);
+/* losses (src/modules/losses.py:5-7, train_video.py:163,339): results are fp32 scalars on the device */
+int hpvg_mse(const float* d_a, const float* d_b, long long n, float* d_out, void* stream);
+int hpvg_mean(const float* d_a, long long n, float* d_out, void* stream);
+int hpvg_kl(const float* d_mu, const float* d_logvar, long long n, float* d_out, void* stream);
+/* z = eps*exp(0.5*logvar)+mu (networks_3d.py:415-417) */
+int hpvg_reparam(const float* d_mu, const float* d_logvar, const float* d_eps, long long n, float* d_z, void* stream);
+
+/* ---------------------------------------------------------------- optimiser (src/modules/optimizers.py:33-43)
+ * Multi-tensor ClipByNorm(clip) + Adam in two launches.  Tensors are described by parallel arrays on the HOST. */
+int hpvg_adam_clip_multi(int n_tensors, float* const* d_params, const float* const* d_grads, float* const* d_m,
+                         float* const* d_v, const long long* sizes, const float* lrs, float beta1, float beta2,
+                         float eps, int step, float clip_norm /* <=0: no clipping */, void* stream);
+
+/* ---------------------------------------------------------------- MindSpore ops.Custom(func_type="aot") entry points
+ * int Name(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes, void* stream, void* extra)
+ * params = device pointers, inputs then outputs, pre-allocated by the framework. */
+int HpvgUpsampleTrilinear3D(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                            void* stream, void* extra); /* x -> y, align_corners=True */
+int HpvgUpsampleTrilinear3DGrad(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                                void* stream, void* extra); /* (dy, x) -> dx */
+int HpvgConv3dBiasLRelu(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes, void* stream,
+                        void* extra); /* (x ncdhw f32 C=64, w (64,64,3,3,3), b) -> y */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPVG_H_ */

@@ -1,0 +1,393 @@
+// extern "C" surface of libhpvg.so (declared in include/hpvg.h): a minimal CUDA runtime shim for the ctypes route
+// plus one entry point per operator of the hot path, and the MindSpore ops.Custom(func_type="aot") wrappers.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/hpvg.h"
+#include "conv3d_umma.h"
+#include "elementwise.h"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+float* g_adam_norms = nullptr;
+int g_sm_count = 0;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return HPVG_E_CUDA;
+}
+#define CU(x)                                          \
+  do {                                                 \
+    cudaError_t e_ = (x);                              \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #x);   \
+  } while (0)
+#define KL(x, n)                                       \
+  do {                                                 \
+    cudaError_t e_ = (x);                              \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #x);   \
+    g_launches += (n);                                 \
+  } while (0)
+
+inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+}  // namespace
+
+extern "C" {
+
+int hpvg_version(void) { return 100; }
+const char* hpvg_last_error(void) { return g_err.c_str(); }
+long long hpvg_launch_count(void) { return g_launches.load(); }
+
+int hpvg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+int hpvg_init(int device) {
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(HPVG_E_UNSUPPORTED, "libhpvg needs an sm_100a (B200) device");
+  g_sm_count = prop.multiProcessorCount;
+  if (!g_adam_norms) CU(cudaMalloc(&g_adam_norms, hpvg::ADAM_MAX_TENSORS * sizeof(float)));
+  return HPVG_OK;
+}
+int hpvg_sm_count(void) { return g_sm_count; }
+int hpvg_malloc(void** p, size_t bytes) {
+  CU(cudaMalloc(p, bytes ? bytes : 16));
+  return HPVG_OK;
+}
+int hpvg_free(void* p) {
+  CU(cudaFree(p));
+  return HPVG_OK;
+}
+int hpvg_host_alloc(void** p, size_t bytes) {
+  CU(cudaMallocHost(p, bytes ? bytes : 16));
+  return HPVG_OK;
+}
+int hpvg_host_free(void* p) {
+  CU(cudaFreeHost(p));
+  return HPVG_OK;
+}
+int hpvg_memset(void* p, int v, size_t bytes, void* st) {
+  CU(cudaMemsetAsync(p, v, bytes, S(st)));
+  return HPVG_OK;
+}
+int hpvg_h2d(void* d, const void* h, size_t bytes, void* st) {
+  CU(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, S(st)));
+  return HPVG_OK;
+}
+int hpvg_d2h(void* h, const void* d, size_t bytes, void* st) {
+  CU(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, S(st)));
+  return HPVG_OK;
+}
+int hpvg_d2d(void* d, const void* s, size_t bytes, void* st) {
+  CU(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, S(st)));
+  return HPVG_OK;
+}
+int hpvg_stream_create(void** st) {
+  cudaStream_t s;
+  CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *st = s;
+  return HPVG_OK;
+}
+int hpvg_stream_destroy(void* st) {
+  CU(cudaStreamDestroy(S(st)));
+  return HPVG_OK;
+}
+int hpvg_stream_sync(void* st) {
+  CU(cudaStreamSynchronize(S(st)));
+  return HPVG_OK;
+}
+int hpvg_device_sync(void) {
+  CU(cudaDeviceSynchronize());
+  return HPVG_OK;
+}
+int hpvg_event_create(void** ev) {
+  cudaEvent_t e;
+  CU(cudaEventCreate(&e));
+  *ev = e;
+  return HPVG_OK;
+}
+int hpvg_event_destroy(void* ev) {
+  CU(cudaEventDestroy(static_cast<cudaEvent_t>(ev)));
+  return HPVG_OK;
+}
+int hpvg_event_record(void* ev, void* st) {
+  CU(cudaEventRecord(static_cast<cudaEvent_t>(ev), S(st)));
+  return HPVG_OK;
+}
+int hpvg_event_sync(void* ev) {
+  CU(cudaEventSynchronize(static_cast<cudaEvent_t>(ev)));
+  return HPVG_OK;
+}
+int hpvg_event_elapsed_ms(void* a, void* b, float* ms) {
+  CU(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(a), static_cast<cudaEvent_t>(b)));
+  return HPVG_OK;
+}
+int hpvg_graph_begin(void* st) {
+  CU(cudaStreamBeginCapture(S(st), cudaStreamCaptureModeThreadLocal));
+  return HPVG_OK;
+}
+int hpvg_graph_end(void* st, void** exec) {
+  cudaGraph_t g;
+  CU(cudaStreamEndCapture(S(st), &g));
+  cudaGraphExec_t e;
+  cudaError_t r = cudaGraphInstantiate(&e, g, 0);
+  cudaGraphDestroy(g);
+  if (r != cudaSuccess) return cuda_fail(r, "cudaGraphInstantiate");
+  *exec = e;
+  return HPVG_OK;
+}
+int hpvg_graph_launch(void* exec, void* st) {
+  CU(cudaGraphLaunch(static_cast<cudaGraphExec_t>(exec), S(st)));
+  return HPVG_OK;
+}
+int hpvg_graph_destroy(void* exec) {
+  CU(cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(exec)));
+  return HPVG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ layout
+int hpvg_pack_cl(const float* x, int N, int C, int T, int H, int W, void* y, int c_pitch, int c_off, int c_zero_to,
+                 void* st) {
+  if ((c_off & 7) || (c_pitch & 7)) return fail(HPVG_E_ARG, "pack_cl: c_off and c_pitch must be multiples of 8");
+  if (c_zero_to > c_pitch || c_off + C > c_pitch) return fail(HPVG_E_ARG, "pack_cl: channels exceed pitch");
+  if (N <= 0 || C <= 0 || T <= 0 || H <= 0 || W <= 0) return HPVG_OK;
+  KL(hpvg::ew_pack_cl(x, N, C, static_cast<long long>(T) * H * W, static_cast<__nv_bfloat16*>(y), c_pitch, c_off,
+                      c_zero_to, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_unpack_cl(const void* x, int N, int C, int T, int H, int W, int c_pitch, int c_off, float* y, void* st) {
+  if ((c_off & 7) || (c_pitch & 7)) return fail(HPVG_E_ARG, "unpack_cl: c_off and c_pitch must be multiples of 8");
+  if (N <= 0 || C <= 0 || T <= 0 || H <= 0 || W <= 0) return HPVG_OK;
+  KL(hpvg::ew_unpack_cl(static_cast<const __nv_bfloat16*>(x), N, C, static_cast<long long>(T) * H * W, c_pitch,
+                        c_off, y, S(st)), 1);
+  return HPVG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ conv
+int hpvg_conv_wimg_bytes(int mode) { return hpvg::conv3d_umma_wimg_bytes(mode); }
+
+int hpvg_conv_pack_weights(const float* w, int w_cout, int w_cin, int kt, int mode, int transpose_flip, int cout_off,
+                           int cout, int cin_off, int cin, void* wimg, void* st) {
+  const int max_co = (mode == HPVG_CONV_64_16) ? 16 : 64;
+  const int max_ci = (mode == HPVG_CONV_8_64) ? 8 : 64;
+  if (cout > max_co || cin > max_ci || cout <= 0 || cin <= 0)
+    return fail(HPVG_E_ARG, "conv_pack_weights: channel counts exceed the kernel variant");
+  const char* e = hpvg::conv3d_pack_weights(w, w_cout, w_cin, kt, mode, transpose_flip, cout_off, cout, cin_off, cin,
+                                            wimg, S(st));
+  if (e) return fail(HPVG_E_CUDA, std::string("conv_pack_weights: ") + e);
+  g_launches += 1;
+  return HPVG_OK;
+}
+
+int hpvg_conv_cl(int mode, int N, int T, int H, int W, const void* in, int in_pitch, const void* wimg,
+                 const float* scale, const float* shift, int act, int out_mode, void* out, int out_pitch,
+                 int out_coff, int cout_real, const float* addend, void* st) {
+  if (N <= 0 || T <= 0 || H <= 0 || W <= 0) return HPVG_OK;  // empty input: nothing to do
+  if (!in || !wimg || !scale || !shift || !out) return fail(HPVG_E_ARG, "conv_cl: null pointer");
+  if (out_mode == HPVG_OUT_BF16_CL && ((out_pitch & 7) || (out_coff & 7)))
+    return fail(HPVG_E_ARG, "conv_cl: out_pitch/out_coff must be multiples of 8");
+  if (g_sm_count == 0) return fail(HPVG_E_ARG, "hpvg_init was not called");
+  hpvg::ConvLaunch L;
+  L.mode = mode;
+  L.N = N; L.T = T; L.H = H; L.W = W;
+  L.in = in; L.in_pitch = in_pitch;
+  L.wimg = wimg; L.scale = scale; L.shift = shift;
+  L.act = act; L.out_mode = out_mode;
+  L.out = out; L.out_pitch = out_pitch; L.out_coff = out_coff; L.cout_real = cout_real;
+  L.addend = addend;
+  L.max_pairs = g_sm_count / 2;
+  const char* e = hpvg::conv3d_umma_launch(L, S(st));
+  if (e) return fail(HPVG_E_CUDA, std::string("conv_cl: ") + e);
+  g_launches += 1;
+  return HPVG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ resize
+int hpvg_linear_taps(int n_in, int n_out, int align, int32_t* i0, int32_t* i1, float* l0, float* l1) {
+  if (n_in <= 0 || n_out <= 0) return fail(HPVG_E_ARG, "linear_taps: sizes must be positive");
+  hpvg::ew_linear_taps_host(n_in, n_out, align, i0, i1, l0, l1);
+  return HPVG_OK;
+}
+int hpvg_linear_taps_dev(int n_in, int n_out, int align, int32_t* i0, int32_t* i1, float* l0, float* l1, void* st) {
+  if (n_in <= 0 || n_out <= 0) return fail(HPVG_E_ARG, "linear_taps: sizes must be positive");
+  KL(hpvg::ew_linear_taps_dev(n_in, n_out, align, i0, i1, l0, l1, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_resize3d_fwd(const float* x, int N, int C, int Ti, int Hi, int Wi, float* y, int To, int Ho, int Wo,
+                      int align, void* st) {
+  if (Ti <= 0 || Hi <= 0 || Wi <= 0 || To <= 0 || Ho <= 0 || Wo <= 0)
+    return fail(HPVG_E_ARG, "resize3d: sizes must be positive");   // trilinear.py:246-249 validator
+  if (N * C == 0) return HPVG_OK;
+  KL(hpvg::ew_resize3d_fwd(x, static_cast<long long>(N) * C, Ti, Hi, Wi, y, To, Ho, Wo, align, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_resize3d_bwd(const float* gy, int N, int C, int To, int Ho, int Wo, float* gx, int Ti, int Hi, int Wi,
+                      int align, void* st) {
+  if (Ti <= 0 || Hi <= 0 || Wi <= 0 || To <= 0 || Ho <= 0 || Wo <= 0)
+    return fail(HPVG_E_ARG, "resize3d: sizes must be positive");
+  if (N * C == 0) return HPVG_OK;
+  KL(hpvg::ew_resize3d_bwd(gy, static_cast<long long>(N) * C, To, Ho, Wo, gx, Ti, Hi, Wi, align, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_upsample_noise_pack(const float* x, int N, int C, int Ti, int Hi, int Wi, int To, int Ho, int Wo,
+                             const float* noise, float amp, uint64_t seed, uint64_t sample_base, float* up,
+                             void* xin, void* st) {
+  if (C < 1 || C > 4) return fail(HPVG_E_ARG, "upsample_noise_pack: 1 <= C <= 4");
+  if (N <= 0) return HPVG_OK;
+  KL(hpvg::ew_upsample_noise_pack(x, N, C, Ti, Hi, Wi, To, Ho, Wo, noise, amp, seed, sample_base, up,
+                                  static_cast<__nv_bfloat16*>(xin), S(st)), 1);
+  return HPVG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ batch norm
+int hpvg_bn_stats_cl(const void* y, long long voxels, double* sum, double* sumsq, void* st) {
+  if (voxels <= 0) return fail(HPVG_E_ARG, "bn_stats: empty batch");
+  KL(hpvg::ew_bn_stats_cl(static_cast<const __nv_bfloat16*>(y), voxels, sum, sumsq, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_bn_finalize(const double* sum, const double* sumsq, long long count, const float* gamma, const float* beta,
+                     float eps, float momentum, float* mm, float* mv, float* scale, float* shift, float* mean,
+                     float* invstd, void* st) {
+  KL(hpvg::ew_bn_finalize(sum, sumsq, count, gamma, beta, eps, momentum, mm, mv, scale, shift, mean, invstd, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_bn_apply_lrelu_cl(const void* y, long long voxels, const float* scale, const float* shift, int act, void* x,
+                           void* st) {
+  if (voxels <= 0) return HPVG_OK;
+  KL(hpvg::ew_bn_apply_cl(static_cast<const __nv_bfloat16*>(y), voxels, scale, shift, act,
+                          static_cast<__nv_bfloat16*>(x), S(st)), 1);
+  return HPVG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ spectral norm
+int hpvg_sn_power_iter(const float* w, int cout, int k, float* u, float* v, float* sigma, float* inv_sigma,
+                       void* st) {
+  if (cout <= 0 || k <= 0 || (2 * cout + k) * 4 > 48 * 1024)
+    return fail(HPVG_E_ARG, "sn_power_iter: matrix too large for the single-CTA kernel");
+  KL(hpvg::ew_sn_power_iter(w, cout, k, u, v, sigma, inv_sigma, S(st)), 1);
+  return HPVG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ small ops
+int hpvg_bn_fold_eval(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                      const float* bias, int C, float* scale, float* shift, void* st) {
+  KL(hpvg::ew_bn_fold_eval(gamma, beta, mean, var, eps, bias, C, scale, shift, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_affine_from_bias(const float* bias, const float* inv_sigma, int C, float* scale, float* shift, void* st) {
+  KL(hpvg::ew_affine_from_bias(bias, inv_sigma, C, scale, shift, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_mse(const float* a, const float* b, long long n, float* out, void* st) {
+  if (n <= 0) return fail(HPVG_E_ARG, "mse: empty input");
+  KL(hpvg::ew_reduce(0, a, b, n, out, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_mean(const float* a, long long n, float* out, void* st) {
+  if (n <= 0) return fail(HPVG_E_ARG, "mean: empty input");
+  KL(hpvg::ew_reduce(1, a, nullptr, n, out, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_kl(const float* mu, const float* lv, long long n, float* out, void* st) {
+  if (n <= 0) return fail(HPVG_E_ARG, "kl: empty input");
+  KL(hpvg::ew_reduce(2, mu, lv, n, out, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_reparam(const float* mu, const float* lv, const float* eps, long long n, float* z, void* st) {
+  if (n <= 0) return HPVG_OK;
+  KL(hpvg::ew_reparam(mu, lv, eps, n, z, S(st)), 1);
+  return HPVG_OK;
+}
+
+int hpvg_adam_clip_multi(int n_tensors, float* const* params, const float* const* grads, float* const* m,
+                         float* const* v, const long long* sizes, const float* lrs, float beta1, float beta2,
+                         float eps, int step, float clip, void* st) {
+  if (step < 1) return fail(HPVG_E_ARG, "adam: step is 1-based");
+  if (!g_adam_norms) return fail(HPVG_E_ARG, "hpvg_init was not called");
+  const float bc = static_cast<float>(std::sqrt(1.0 - std::pow(static_cast<double>(beta2), step)) /
+                                      (1.0 - std::pow(static_cast<double>(beta1), step)));
+  for (int base = 0; base < n_tensors; base += hpvg::ADAM_MAX_TENSORS) {
+    hpvg::AdamTable tab;
+    std::memset(&tab, 0, sizeof(tab));
+    int cnt = 0;
+    for (int i = base; i < n_tensors && cnt < hpvg::ADAM_MAX_TENSORS; ++i, ++cnt) {
+      tab.p[cnt] = params[i];
+      tab.g[cnt] = grads[i];
+      tab.m[cnt] = m[i];
+      tab.v[cnt] = v[i];
+      tab.n[cnt] = sizes[i];
+      tab.lr[cnt] = lrs[i];
+    }
+    KL(hpvg::ew_adam_clip(tab, cnt, g_adam_norms, beta1, beta2, eps, bc, clip, S(st)), clip > 0.f ? 2 : 1);
+  }
+  return HPVG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ MindSpore AOT
+static bool is_f32(const char* s) { return s && std::strcmp(s, "float32") == 0; }
+
+int HpvgUpsampleTrilinear3D(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                            void* stream, void* /*extra*/) {
+  if (nparam != 2 || ndims[0] != 5 || ndims[1] != 5 || !is_f32(dtypes[0]) || !is_f32(dtypes[1])) return 1;
+  const int64_t* a = shapes[0];
+  const int64_t* b = shapes[1];
+  if (a[0] != b[0] || a[1] != b[1]) return 2;
+  return hpvg_resize3d_fwd(static_cast<const float*>(params[0]), (int)a[0], (int)a[1], (int)a[2], (int)a[3],
+                           (int)a[4], static_cast<float*>(params[1]), (int)b[2], (int)b[3], (int)b[4], 1, stream);
+}
+int HpvgUpsampleTrilinear3DGrad(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                                void* stream, void* /*extra*/) {
+  // inputs: dy (N,C,To,Ho,Wo), x (N,C,Ti,Hi,Wi) [shape only]; output: dx
+  if (nparam != 3 || ndims[0] != 5 || ndims[2] != 5 || !is_f32(dtypes[0]) || !is_f32(dtypes[2])) return 1;
+  const int64_t* a = shapes[0];
+  const int64_t* b = shapes[2];
+  return hpvg_resize3d_bwd(static_cast<const float*>(params[0]), (int)a[0], (int)a[1], (int)a[2], (int)a[3],
+                           (int)a[4], static_cast<float*>(params[2]), (int)b[2], (int)b[3], (int)b[4], 1, stream);
+}
+int HpvgConv3dBiasLRelu(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes, void* stream,
+                        void* /*extra*/) {
+  // x (N,64,T,H,W) f32, w (64,64,3,3,3) f32, b (64) f32 -> y (N,64,T,H,W) f32 ; workspace is allocated per call here
+  // (a production binding passes a workspace through `extra`)
+  if (nparam != 4 || ndims[0] != 5 || !is_f32(dtypes[0])) return 1;
+  const int64_t* a = shapes[0];
+  if (a[1] != 64 || shapes[1][0] != 64 || shapes[1][1] != 64) return 2;
+  const int N = (int)a[0], T = (int)a[2], H = (int)a[3], W = (int)a[4];
+  const size_t vox = (size_t)N * T * H * W;
+  void *xcl = nullptr, *ycl = nullptr, *wimg = nullptr;
+  float *scale = nullptr;
+  int rc = 0;
+  if (cudaMalloc(&xcl, vox * 128) != cudaSuccess || cudaMalloc(&ycl, vox * 128) != cudaSuccess ||
+      cudaMalloc(&wimg, hpvg_conv_wimg_bytes(HPVG_CONV_64_64)) != cudaSuccess ||
+      cudaMalloc(&scale, 128 * sizeof(float)) != cudaSuccess)
+    rc = 3;
+  if (!rc) rc = hpvg_pack_cl(static_cast<const float*>(params[0]), N, 64, T, H, W, xcl, 64, 0, 64, stream);
+  if (!rc) rc = hpvg_conv_pack_weights(static_cast<const float*>(params[1]), 64, 64, 3, HPVG_CONV_64_64, 0, 0, 64, 0,
+                                       64, wimg, stream);
+  if (!rc) rc = hpvg_affine_from_bias(static_cast<const float*>(params[2]), nullptr, 64, scale, scale + 64, stream);
+  if (!rc) rc = hpvg_conv_cl(HPVG_CONV_64_64, N, T, H, W, xcl, 64, wimg, scale, scale + 64, HPVG_ACT_LRELU,
+                             HPVG_OUT_BF16_CL, ycl, 64, 0, 64, nullptr, stream);
+  if (!rc) rc = hpvg_unpack_cl(ycl, N, 64, T, H, W, 64, 0, static_cast<float*>(params[3]), stream);
+  cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  cudaFree(xcl); cudaFree(ycl); cudaFree(wimg); cudaFree(scale);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,533 @@
+// 3x3x3 / stride 1 / zero-pad 1 convolution as an implicit GEMM on the 5th-gen tensor cores (tcgen05, sm_100a).
+//
+// Replaces the library call behind `nn.Conv3d` in reference ConvBlock3D (src/modules/networks_3d.py:48-50), the
+// decoder/body tail convs (networks_3d.py:380,399), `SpectualNormConv3d.conv3d` (src/tools/spectral_norm.py:152)
+// and, with repacked weights, their data-gradient.  Conv2d (networks_2d.py) is the T=1 case.
+//
+// Design:
+//   * activations live in HBM channels-last (N,T,H,W,C) bf16; one TMA box = one haloed (18h x 10w x C) input plane;
+//     out-of-bounds box elements are zero-filled by TMA, which IS the conv zero padding.
+//   * a CTA PAIR (cluster of 2, tcgen05 cta_group::2) owns two vertically adjacent 8w x 16h output tiles and walks
+//     along T.  M = 256 rows (128 voxels per CTA), N = Cout, K = 27 taps x Cin.  The A operand of tap (dt,dh,dw) is
+//     the SAME shared-memory plane addressed through a shifted matrix descriptor (start += (dh*10+dw) rows) — no
+//     im2col copy exists anywhere.  Input planes sit in a ring: plane t is loaded once per strip and used by the
+//     three output planes t-1, t, t+1.
+//   * the whole filter bank (27 taps) stays resident in shared memory, split across the pair (each CTA holds half
+//     of Cout), so the steady state moves only activations: ~1.4 x 128 B per voxel from L2.
+//   * FP32 accumulators in TMEM, double buffered: the epilogue of plane p (TMEM -> registers -> per-channel
+//     scale/shift (+bias, folded BN, 1/sigma of spectral norm) -> LeakyReLU/tanh -> bf16/f32 store) overlaps the
+//     MMAs of plane p+1.
+//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only) + TMEM owner, warps 2..5 = epilogue.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "conv3d_umma.h"
+#include "ptx.cuh"
+
+namespace hpvg {
+
+namespace {
+
+constexpr int TILE_W = 8;
+constexpr int TILE_H = 16;
+constexpr int BOX_W = TILE_W + 2;
+constexpr int BOX_H = TILE_H + 2;
+constexpr int NUM_THREADS = 192;
+
+template <int MODE>
+struct Cfg;
+// MODE 0: Cin 64 -> Cout 64 (SW128 planes, 4 K-steps per tap)
+template <>
+struct Cfg<CONV_MODE_64_64> {
+  static constexpr int CIN = 64, NOUT = 64, ROWS_PER_CTA = 32;
+  static constexpr int PLANE_BYTES = BOX_H * BOX_W * 128, SLOT_STRIDE = 23552, SLOTS = 4;
+  static constexpr int W_BYTES = 27 * ROWS_PER_CTA * 128, DT_BYTES = 9 * ROWS_PER_CTA * 128;
+  static constexpr int ACC_STRIDE = 64, TMEM_COLS = 128;
+};
+// MODE 1: Cin 64 -> Cout <= 16 (tail convs 64->3 / 64->1)
+template <>
+struct Cfg<CONV_MODE_64_16> {
+  static constexpr int CIN = 64, NOUT = 16, ROWS_PER_CTA = 8;
+  static constexpr int PLANE_BYTES = BOX_H * BOX_W * 128, SLOT_STRIDE = 23552, SLOTS = 6;
+  static constexpr int W_BYTES = 27 * ROWS_PER_CTA * 128, DT_BYTES = 9 * ROWS_PER_CTA * 128;
+  static constexpr int ACC_STRIDE = 32, TMEM_COLS = 64;
+};
+// MODE 2: Cin <= 8 -> Cout 64 (head convs 3->64); no-swizzle planes of 16 B per voxel, taps paired through LBO
+template <>
+struct Cfg<CONV_MODE_8_64> {
+  static constexpr int CIN = 8, NOUT = 64, ROWS_PER_CTA = 32;
+  static constexpr int PLANE_BYTES = BOX_H * BOX_W * 16, SLOT_STRIDE = 3072, SLOTS = 8;
+  static constexpr int W_BYTES = 3 * 5 * 1024, DT_BYTES = 5 * 1024;
+  static constexpr int ACC_STRIDE = 64, TMEM_COLS = 128;
+};
+
+struct Unit {
+  int n, h0, w0;
+};
+__device__ __forceinline__ Unit decode_unit(int u, const ConvParams& p, uint32_t rank) {
+  Unit r;
+  const int per_n = p.w_tiles * p.h_pairs;
+  r.n = u / per_n;
+  const int rem = u - r.n * per_n;
+  const int hp = rem / p.w_tiles;
+  const int wt = rem - hp * p.w_tiles;
+  r.h0 = (2 * hp + static_cast<int>(rank)) * TILE_H;
+  r.w0 = wt * TILE_W;
+  return r;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == CONV_ACT_LRELU) return v > 0.f ? v : 0.2f * v;
+  if (act == CONV_ACT_TANH) return tanhf(v);
+  return v;
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ConvParams p) {
+  using C = Cfg<MODE>;
+  extern __shared__ uint8_t smem_dyn[];
+  // carve (identical in both CTAs of the pair): [weights | plane ring | scale | shift | barriers | tmem ptr]
+  const uint32_t base_u32 = smem_u32(smem_dyn);
+  uint8_t* sm = smem_dyn + (((base_u32 + 1023u) & ~1023u) - base_u32);
+  uint8_t* w_sm = sm;
+  uint8_t* planes = sm + ((C::W_BYTES + 1023) & ~1023);
+  float* scale_sm = reinterpret_cast<float*>(planes + C::SLOTS * C::SLOT_STRIDE);
+  float* shift_sm = scale_sm + 64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(shift_sm + 64);
+  uint64_t* a_full = bars;                    // [SLOTS]  (used in the leader CTA; tx from both CTAs)
+  uint64_t* a_empty = a_full + C::SLOTS;      // [SLOTS]  (each CTA its own; multicast commit)
+  uint64_t* acc_full = a_empty + C::SLOTS;    // [2]      (each CTA its own; multicast commit)
+  uint64_t* acc_empty = acc_full + 2;         // [2]      (leader's is used; 8 arrivals = 4 warps x 2 CTAs)
+  uint64_t* w_full = acc_empty + 2;           // [1]      this CTA's filter bank has landed
+  uint64_t* w_peer = w_full + 1;              // [1]      (leader's is used) the peer's filter bank has landed
+  uint32_t* tmem_ptr_sm = reinterpret_cast<uint32_t*>(w_peer + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int n_pairs = gridDim.x >> 1;
+  const int T = p.T;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::SLOTS; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 8);
+    }
+    mbar_init(w_full, 1);
+    mbar_init(w_peer, 1);
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 64) {
+    scale_sm[threadIdx.x] = threadIdx.x < C::NOUT ? p.scale[threadIdx.x] : 0.f;
+    shift_sm[threadIdx.x] = threadIdx.x < C::NOUT ? p.shift[threadIdx.x] : 0.f;
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_ptr_sm, C::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_sm;
+
+  if (warp == 0) {
+    // =========================================================================== TMA producer (both CTAs)
+    if (elect_one()) {
+      tma_prefetch_desc(&tmap_in);
+      // resident filter bank: this CTA's half of Cout, all taps
+      mbar_expect_tx(w_full, C::W_BYTES);
+      const uint8_t* wsrc = p.wimg + static_cast<size_t>(rank) * C::W_BYTES;
+      constexpr int CHUNK = 13824;  // divides every W_BYTES here (110592, 27648) ; 15360 handled below
+      if constexpr (C::W_BYTES % CHUNK == 0) {
+        for (int off = 0; off < C::W_BYTES; off += CHUNK) bulk_load(w_sm + off, wsrc + off, CHUNK, w_full);
+      } else {
+        for (int off = 0; off < C::W_BYTES; off += 5120) bulk_load(w_sm + off, wsrc + off, 5120, w_full);
+      }
+      uint32_t leader_full[C::SLOTS];
+#pragma unroll
+      for (int i = 0; i < C::SLOTS; ++i) leader_full[i] = map_to_cta(smem_u32(&a_full[i]), 0);
+      uint32_t j = 0;
+      for (int u = pair; u < p.n_units; u += n_pairs) {
+        const Unit un = decode_unit(u, p, rank);
+        for (int t = 0; t < T; ++t, ++j) {
+          const uint32_t slot = j % C::SLOTS;
+          const uint32_t ph = (j / C::SLOTS) & 1u;
+          mbar_wait(&a_empty[slot], ph ^ 1u);
+          if (rank == 0) mbar_expect_tx(&a_full[slot], 2u * C::PLANE_BYTES);
+          uint32_t dst_bar = leader_full[0];
+#pragma unroll
+          for (int i = 1; i < C::SLOTS; ++i) dst_bar = (slot == static_cast<uint32_t>(i)) ? leader_full[i] : dst_bar;
+          tma_load_5d_pair(planes + slot * C::SLOT_STRIDE, &tmap_in, dst_bar, 0, un.w0 - 1, un.h0 - 1, t, un.n);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =========================================================================== MMA issuer (leader CTA only)
+    if (rank == 1 && elect_one()) {
+      // tell the leader that this CTA's half of the filter bank is resident
+      mbar_wait(w_full, 0);
+      mbar_arrive_cluster(map_to_cta(smem_u32(w_peer), 0));
+    }
+    if (rank == 0 && elect_one()) {
+      mbar_wait(w_full, 0);
+      mbar_wait(w_peer, 0);
+      const uint32_t idesc = make_idesc_bf16(256, C::NOUT);
+      const uint32_t w_addr = smem_u32(w_sm);
+      const uint32_t planes_addr = smem_u32(planes);
+      uint32_t j0 = 0, q = 0;
+      for (int u = pair; u < p.n_units; u += n_pairs) {
+        for (int pl = 0; pl < T; ++pl, ++q) {
+          const uint32_t ab = q & 1u;
+          mbar_wait(&acc_empty[ab], ((q >> 1) & 1u) ^ 1u);
+          if (pl == 0) {
+            const uint32_t jj = j0;
+            mbar_wait(&a_full[jj % C::SLOTS], (jj / C::SLOTS) & 1u);
+          }
+          if (pl + 1 < T) {
+            const uint32_t jj = j0 + pl + 1;
+            mbar_wait(&a_full[jj % C::SLOTS], (jj / C::SLOTS) & 1u);
+          }
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + ab * C::ACC_STRIDE;
+          uint32_t accum = 0;
+#pragma unroll 1
+          for (int dt = 0; dt < 3; ++dt) {
+            const int tin = pl + dt - 1;
+            if (tin < 0 || tin >= T) continue;
+            const uint32_t slot = (j0 + tin) % C::SLOTS;
+            const uint32_t a_base = planes_addr + slot * C::SLOT_STRIDE;
+            const uint32_t b_base = w_addr + dt * C::DT_BYTES;
+            if constexpr (MODE == CONV_MODE_8_64) {
+              // 9 in-plane taps, 8 channels (16 B) each -> 5 MMAs of K=16: (tap0 | zero-weight dummy), (1|2) ... (7|8)
+#pragma unroll
+              for (int s = 0; s < 5; ++s) {
+                const int ta = (s == 0) ? 0 : 2 * s - 1;
+                const int tb = (s == 0) ? 1 : 2 * s;
+                const uint32_t offa = ((ta / 3) * BOX_W + (ta % 3)) * 16;
+                const uint32_t offb = ((tb / 3) * BOX_W + (tb % 3)) * 16;
+                const uint64_t ad = make_smem_desc(a_base + offa, offb - offa, BOX_W * 16, 0);
+                const uint64_t bd = make_smem_desc(b_base + s * 1024, C::ROWS_PER_CTA * 16, 128, 0);
+                umma_bf16_pair(d_tmem, ad, bd, idesc, accum);
+                accum = 1;
+              }
+            } else {
+#pragma unroll
+              for (int s = 0; s < 9; ++s) {
+                const uint32_t a_tap = a_base + ((s / 3) * BOX_W + (s % 3)) * 128;
+                const uint32_t b_tap = b_base + s * (C::ROWS_PER_CTA * 128);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t ad = make_smem_desc(a_tap + k * 32, 16, BOX_W * 128, 2);
+                  const uint64_t bd = make_smem_desc(b_tap + k * 32, 16, 1024, 2);
+                  umma_bf16_pair(d_tmem, ad, bd, idesc, accum);
+                  accum = 1;
+                }
+              }
+            }
+          }
+          umma_commit_pair(&acc_full[ab], 3);
+          if (pl >= 1) umma_commit_pair(&a_empty[(j0 + pl - 1) % C::SLOTS], 3);
+          if (pl == T - 1) umma_commit_pair(&a_empty[(j0 + pl) % C::SLOTS], 3);
+        }
+        j0 += T;
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================================================================== epilogue (both CTAs, 4 warps)
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;          // accumulator row == voxel of this CTA's tile
+    const int hh = row >> 3, ww = row & 7;
+    uint32_t leader_empty[2];
+    leader_empty[0] = map_to_cta(smem_u32(&acc_empty[0]), 0);
+    leader_empty[1] = map_to_cta(smem_u32(&acc_empty[1]), 0);
+    uint32_t q = 0;
+    for (int u = pair; u < p.n_units; u += n_pairs) {
+      const Unit un = decode_unit(u, p, rank);
+      const int h = un.h0 + hh, w = un.w0 + ww;
+      const bool inb = (h < p.H) && (w < p.W);
+      for (int pl = 0; pl < T; ++pl, ++q) {
+        const uint32_t ab = q & 1u;
+        mbar_wait(&acc_full[ab], (q >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + ab * C::ACC_STRIDE;
+        const size_t vox = ((static_cast<size_t>(un.n) * T + pl) * p.H + h) * p.W + w;
+        if constexpr (C::NOUT == 64) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(taddr, r0);
+          tmem_ld32(taddr + 32, r1);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(leader_empty[ab]);
+          if (inb) {
+            if (p.out_mode == CONV_OUT_F32_RAW) {
+              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + vox * 64);
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                dst[c] = make_float4(__uint_as_float(r0[4 * c]), __uint_as_float(r0[4 * c + 1]),
+                                     __uint_as_float(r0[4 * c + 2]), __uint_as_float(r0[4 * c + 3]));
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                dst[8 + c] = make_float4(__uint_as_float(r1[4 * c]), __uint_as_float(r1[4 * c + 1]),
+                                         __uint_as_float(r1[4 * c + 2]), __uint_as_float(r1[4 * c + 3]));
+            } else {
+              const float* add = p.addend ? p.addend + vox * 64 : nullptr;
+              __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + vox * p.out_pitch + p.out_coff;
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                const uint32_t* r = half ? r1 : r0;
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                  float v[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const int c = half * 32 + c8 * 8 + e;
+                    float a = __uint_as_float(r[c8 * 8 + e]);
+                    if (add) a += add[c];
+                    v[e] = apply_act(fmaf(a, scale_sm[c], shift_sm[c]), p.act);
+                  }
+                  uint4 pk;
+                  pk.x = pack_bf16x2(v[0], v[1]);
+                  pk.y = pack_bf16x2(v[2], v[3]);
+                  pk.z = pack_bf16x2(v[4], v[5]);
+                  pk.w = pack_bf16x2(v[6], v[7]);
+                  *reinterpret_cast<uint4*>(dst + half * 32 + c8 * 8) = pk;
+                }
+              }
+            }
+          }
+        } else {
+          uint32_t r[16];
+          tmem_ld16(taddr, r);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(leader_empty[ab]);
+          if (inb) {
+            // fp32 NCDHW, cout_real channels: out[n][c][t][h][w] = act(acc*scale + shift (+ residual))
+            const size_t plane_sz = static_cast<size_t>(p.H) * p.W;
+            const size_t sp = (static_cast<size_t>(pl) * p.H + h) * p.W + w;
+            const size_t chan_sz = plane_sz * T;
+            float* out = static_cast<float*>(p.out);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (c < p.cout_real) {
+                const size_t idx = (static_cast<size_t>(un.n) * p.cout_real + c) * chan_sz + sp;
+                float v = fmaf(__uint_as_float(r[c]), scale_sm[c], shift_sm[c]);
+                if (p.addend) v += p.addend[idx];
+                out[idx] = apply_act(v, p.act);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  // =========================================================================== teardown
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+}
+
+template <int MODE>
+constexpr int smem_bytes_for() {
+  using C = Cfg<MODE>;
+  return 1024 + ((C::W_BYTES + 1023) & ~1023) + C::SLOTS * C::SLOT_STRIDE + 512 + (2 * C::SLOTS + 6) * 8 + 16;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+template <int MODE>
+cudaError_t launch_mode(const CUtensorMap& tmap, const ConvParams& prm, int n_pairs, cudaStream_t stream) {
+  static bool configured = false;
+  constexpr int smem = smem_bytes_for<MODE>();
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(conv3d_umma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  conv3d_umma_kernel<MODE><<<dim3(2 * n_pairs), dim3(NUM_THREADS), smem, stream>>>(tmap, prm);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+const char* conv3d_umma_launch(const ConvLaunch& L, cudaStream_t stream) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return "cuTensorMapEncodeTiled entry point not available";
+  const int cin_pitch = L.in_pitch;  // channels per voxel row in the input tensor
+  const int cin_box = (L.mode == CONV_MODE_8_64) ? 8 : 64;
+  if (L.mode == CONV_MODE_8_64 && cin_pitch != 8) return "mode 8->64 needs an 8-channel (16 B/voxel) input";
+  if ((reinterpret_cast<uintptr_t>(L.in) & 15) != 0) return "input not 16-byte aligned";
+  CUtensorMap tmap;
+  cuuint64_t gd[5] = {static_cast<cuuint64_t>(cin_box), static_cast<cuuint64_t>(L.W), static_cast<cuuint64_t>(L.H),
+                      static_cast<cuuint64_t>(L.T), static_cast<cuuint64_t>(L.N)};
+  const cuuint64_t vox = static_cast<cuuint64_t>(cin_pitch) * 2;
+  cuuint64_t gs[4] = {vox, vox * L.W, vox * L.W * L.H, vox * L.W * L.H * L.T};
+  cuuint32_t bx[5] = {static_cast<cuuint32_t>(cin_box), BOX_W, BOX_H, 1, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(L.in), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   L.mode == CONV_MODE_8_64 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed";
+
+  ConvParams prm;
+  prm.N = L.N;
+  prm.T = L.T;
+  prm.H = L.H;
+  prm.W = L.W;
+  prm.w_tiles = (L.W + TILE_W - 1) / TILE_W;
+  const int h_tiles = (L.H + TILE_H - 1) / TILE_H;
+  prm.h_pairs = (h_tiles + 1) / 2;
+  prm.n_units = L.N * prm.w_tiles * prm.h_pairs;
+  prm.wimg = static_cast<const uint8_t*>(L.wimg);
+  prm.scale = L.scale;
+  prm.shift = L.shift;
+  prm.act = L.act;
+  prm.out_mode = L.out_mode;
+  prm.out = L.out;
+  prm.out_pitch = L.out_pitch;
+  prm.out_coff = L.out_coff;
+  prm.cout_real = L.cout_real;
+  prm.addend = L.addend;
+  int n_pairs = prm.n_units < L.max_pairs ? prm.n_units : L.max_pairs;
+  if (n_pairs < 1) return nullptr;
+  cudaError_t e;
+  switch (L.mode) {
+    case CONV_MODE_64_64:
+      if (L.out_mode != CONV_OUT_BF16_NDHWC && L.out_mode != CONV_OUT_F32_RAW) return "bad out_mode for 64->64";
+      e = launch_mode<CONV_MODE_64_64>(tmap, prm, n_pairs, stream);
+      break;
+    case CONV_MODE_64_16:
+      if (L.out_mode != CONV_OUT_F32_NCDHW || L.cout_real > 4) return "bad out_mode for 64->16";
+      e = launch_mode<CONV_MODE_64_16>(tmap, prm, n_pairs, stream);
+      break;
+    case CONV_MODE_8_64:
+      if (L.out_mode != CONV_OUT_BF16_NDHWC && L.out_mode != CONV_OUT_F32_RAW) return "bad out_mode for 8->64";
+      e = launch_mode<CONV_MODE_8_64>(tmap, prm, n_pairs, stream);
+      break;
+    default:
+      return "unknown conv mode";
+  }
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+int conv3d_umma_wimg_bytes(int mode) {
+  switch (mode) {
+    case CONV_MODE_64_64: return 2 * Cfg<CONV_MODE_64_64>::W_BYTES;
+    case CONV_MODE_64_16: return 2 * Cfg<CONV_MODE_64_16>::W_BYTES;
+    case CONV_MODE_8_64: return 2 * Cfg<CONV_MODE_8_64>::W_BYTES;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Filter-bank packing: fp32 (Cout, Cin, 3,3,3) [or (Cout,Cin,3,3) with kt==1] -> the per-CTA shared-memory image the
+// conv kernel bulk-copies.  transpose_flip=1 packs the data-gradient filter (Cin<->Cout swapped, taps mirrored).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin, int kt, int mode,
+                                    int transpose_flip, int cin_off, int cout_off, int w_cout, int w_cin,
+                                    __nv_bfloat16* __restrict__ img, int total) {
+  // one thread per bf16 element of the image
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int rank, tap, row, ci;
+  float val = 0.f;
+  bool valid = true;
+  if (mode == CONV_MODE_64_64 || mode == CONV_MODE_64_16) {
+    const int rows = (mode == CONV_MODE_64_64) ? 32 : 8;
+    const int per_rank = 27 * rows * 64;
+    rank = idx / per_rank;
+    int rem = idx - rank * per_rank;
+    tap = rem / (rows * 64);
+    rem -= tap * rows * 64;
+    row = rem / 64;
+    const int within = rem - row * 64;          // element position inside the swizzled 128 B row
+    const int chunk_sw = within >> 3, e = within & 7;
+    const int chunk = chunk_sw ^ (row & 7);     // un-swizzle: stored position -> logical chunk
+    ci = chunk * 8 + e;
+  } else {
+    // [rank][dt 3][step 5][kg 2][row 32][8]
+    const int per_rank = 3 * 5 * 2 * 32 * 8;
+    rank = idx / per_rank;
+    int rem = idx - rank * per_rank;
+    const int dt = rem / (5 * 512);
+    rem -= dt * 5 * 512;
+    const int step = rem / 512;
+    rem -= step * 512;
+    const int kg = rem / 256;
+    rem -= kg * 256;
+    row = rem / 8;
+    ci = rem & 7;
+    int s;  // in-plane tap index 0..8
+    if (step == 0) {
+      s = 0;
+      valid = (kg == 0);
+    } else {
+      s = 2 * step - 1 + kg;
+    }
+    tap = dt * 9 + s;
+  }
+  const int rows_per = (mode == CONV_MODE_64_16) ? 8 : 32;
+  const int co = rank * rows_per + row;
+  int dt = tap / 9, dh = (tap / 3) % 3, dw = tap % 3;
+  if (kt == 1) {  // 2-D filter: only the centre temporal tap is populated
+    valid = valid && (dt == 1);
+    dt = 0;
+  }
+  if (valid && co < cout && ci < cin) {
+    // logical conv: out[co] += w_eff[co][ci][dt][dh][dw] * in[ci]
+    if (!transpose_flip) {
+      const size_t o = ((((static_cast<size_t>(co + cout_off) * w_cin) + (ci + cin_off)) * kt + dt) * 3 + dh) * 3 + dw;
+      val = w[o];
+    } else {
+      // data gradient: w_eff[co=ci_fwd][ci=co_fwd][taps mirrored]
+      const int fdt = (kt == 1) ? 0 : 2 - dt;
+      const size_t o =
+          ((((static_cast<size_t>(ci + cin_off) * w_cin) + (co + cout_off)) * kt + fdt) * 3 + (2 - dh)) * 3 + (2 - dw);
+      val = w[o];
+    }
+  }
+  (void)w_cout;
+  img[idx] = __float2bfloat16_rn(val);
+}
+
+const char* conv3d_pack_weights(const float* w, int w_cout, int w_cin, int kt, int mode, int transpose_flip,
+                                int cout_off, int cout, int cin_off, int cin, void* img, cudaStream_t stream) {
+  const int total = conv3d_umma_wimg_bytes(mode) / 2;
+  if (total == 0) return "unknown conv mode";
+  if (kt != 1 && kt != 3) return "kernel depth must be 1 or 3";
+  pack_weights_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w, cout, cin, kt, mode, transpose_flip, cin_off,
+                                                                cout_off, w_cout, w_cin,
+                                                                static_cast<__nv_bfloat16*>(img), total);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+}  // namespace hpvg

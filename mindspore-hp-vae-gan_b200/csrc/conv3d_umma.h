@@ -1,0 +1,51 @@
+// Internal interface of the tcgen05 implicit-GEMM convolution (see conv3d_umma.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace hpvg {
+
+enum ConvMode { CONV_MODE_64_64 = 0, CONV_MODE_64_16 = 1, CONV_MODE_8_64 = 2 };
+enum ConvAct { CONV_ACT_NONE = 0, CONV_ACT_LRELU = 1, CONV_ACT_TANH = 2 };
+enum ConvOut { CONV_OUT_BF16_NDHWC = 0, CONV_OUT_F32_NCDHW = 1, CONV_OUT_F32_RAW = 2 };
+
+// device-side parameter block (passed as __grid_constant__)
+struct ConvParams {
+  int N, T, H, W;
+  int w_tiles, h_pairs, n_units;
+  const uint8_t* wimg;   // [2 ranks][W_BYTES] packed filter bank (conv3d_pack_weights)
+  const float* scale;    // [Cout] epilogue multiplier  (gamma/sqrt(var+eps), 1/sigma, or 1)
+  const float* shift;    // [Cout] epilogue offset      (bias / folded BN shift)
+  int act;               // ConvAct
+  int out_mode;          // ConvOut
+  void* out;
+  int out_pitch;         // channels per voxel of the bf16 output tensor
+  int out_coff;          // first output channel inside that pitch
+  int cout_real;         // CONV_OUT_F32_NCDHW: number of real output channels (<= 4)
+  const float* addend;   // bf16 out: fp32 [V][64] partial sums added before scale/shift (split-Cin);
+                         // NCDHW out: fp32 NCDHW residual added after scale/shift, before the activation
+};
+
+// host-side launch description
+struct ConvLaunch {
+  int mode;              // ConvMode
+  int N, T, H, W;
+  const void* in;        // bf16 channels-last; for 64-ch modes may point at a 64-channel slice of a wider tensor
+  int in_pitch;          // channels per voxel of the input tensor (64, 128, ... or 8)
+  const void* wimg;
+  const float* scale;
+  const float* shift;
+  int act, out_mode;
+  void* out;
+  int out_pitch, out_coff, cout_real;
+  const float* addend;
+  int max_pairs;         // CTA pairs to launch (<= 74 on a 148-SM B200)
+};
+
+// returns nullptr on success, else a static error string
+const char* conv3d_umma_launch(const ConvLaunch& L, cudaStream_t stream);
+int conv3d_umma_wimg_bytes(int mode);
+const char* conv3d_pack_weights(const float* w, int w_cout, int w_cin, int kt, int mode, int transpose_flip,
+                                int cout_off, int cout, int cin_off, int cin, void* img, cudaStream_t stream);
+
+}  // namespace hpvg

@@ -1,0 +1,680 @@
+// Bandwidth-bound kernels of the HP-VAE-GAN hot path: layout changes at the API edge, linear resize (fwd/bwd),
+// the fused "upsample + noise + pack" block input stage, training-mode BatchNorm, spectral-norm power iteration,
+// losses, reparameterisation and the multi-tensor clip+Adam step.  All plain SIMT, coalesced, 16-byte vector
+// accesses where the layout allows it.  Reference call sites are cited per kernel.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "elementwise.h"
+
+namespace hpvg {
+
+namespace {
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+
+// ----------------------------------------------------------------------------------------------- pack / unpack
+// thread = (voxel, 8-channel group); consecutive threads walk consecutive voxels so the fp32 side is coalesced.
+__global__ void pack_cl_kernel(const float* __restrict__ x, int C, long long sp /*T*H*W*/, long long voxels,
+                               __nv_bfloat16* __restrict__ y, int c_pitch, int c_off, int groups) {
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= voxels * groups) return;
+  const int g = static_cast<int>(gid / voxels);
+  const long long v = gid - static_cast<long long>(g) * voxels;
+  const long long n = v / sp, s = v - n * sp;
+  float f[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = g * 8 + e;
+    f[e] = (c < C) ? x[(n * C + c) * sp + s] : 0.f;
+  }
+  uint4 pk = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+  *reinterpret_cast<uint4*>(y + v * c_pitch + c_off + g * 8) = pk;
+}
+
+__global__ void unpack_cl_kernel(const __nv_bfloat16* __restrict__ x, int C, long long sp, long long voxels,
+                                 int c_pitch, int c_off, float* __restrict__ y, int groups) {
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= voxels * groups) return;
+  const int g = static_cast<int>(gid / voxels);
+  const long long v = gid - static_cast<long long>(g) * voxels;
+  const long long n = v / sp, s = v - n * sp;
+  const uint4 pk = *reinterpret_cast<const uint4*>(x + v * c_pitch + c_off + g * 8);
+  const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+  for (int e2 = 0; e2 < 4; ++e2) {
+    const float2 f = unpack2(w[e2]);
+    const int c = g * 8 + 2 * e2;
+    if (c < C) y[(n * C + c) * sp + s] = f.x;
+    if (c + 1 < C) y[(n * C + c + 1) * sp + s] = f.y;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- linear resize
+// Source index / weight rule of UpsampleTrilinear3D / ResizeBilinear (ATen rule; trilinear.py:222-233 KAT).
+// IEEE fp32, no FMA contraction, identical on host (linear_tap_host) and device -> bit-exact tables.
+struct Tap {
+  int i0, i1;
+  float l0, l1;
+};
+__host__ __device__ __forceinline__ Tap linear_tap(int o, int n_in, float scale, int align_corners) {
+  float r;
+#ifdef __CUDA_ARCH__
+  if (align_corners) {
+    r = __fmul_rn(scale, static_cast<float>(o));
+  } else {
+    r = __fsub_rn(__fmul_rn(scale, __fadd_rn(static_cast<float>(o), 0.5f)), 0.5f);
+    r = fmaxf(r, 0.f);
+  }
+#else
+  if (align_corners) {
+    volatile float m = scale * static_cast<float>(o);
+    r = m;
+  } else {
+    volatile float a = static_cast<float>(o) + 0.5f;
+    volatile float m = scale * a;
+    volatile float s = m - 0.5f;
+    r = s < 0.f ? 0.f : s;
+  }
+#endif
+  Tap t;
+  t.i0 = static_cast<int>(r);
+  if (t.i0 > n_in - 1) t.i0 = n_in - 1;
+  t.i1 = t.i0 + (t.i0 < n_in - 1 ? 1 : 0);
+#ifdef __CUDA_ARCH__
+  t.l1 = __fsub_rn(r, static_cast<float>(t.i0));
+  t.l0 = __fsub_rn(1.0f, t.l1);
+#else
+  volatile float l1 = r - static_cast<float>(t.i0);
+  volatile float l0 = 1.0f - l1;
+  t.l1 = l1;
+  t.l0 = l0;
+#endif
+  return t;
+}
+
+__device__ __forceinline__ float lerp_rn(float l0, float a, float l1, float b) {
+  return __fadd_rn(__fmul_rn(l0, a), __fmul_rn(l1, b));
+}
+
+__device__ __forceinline__ float trilerp(const float* __restrict__ xc, int Hi, int Wi, const Tap& tt, const Tap& th,
+                                         const Tap& tw) {
+  const long long pw = static_cast<long long>(Hi) * Wi;
+  const float* p00 = xc + tt.i0 * pw + static_cast<long long>(th.i0) * Wi;
+  const float* p01 = xc + tt.i0 * pw + static_cast<long long>(th.i1) * Wi;
+  const float* p10 = xc + tt.i1 * pw + static_cast<long long>(th.i0) * Wi;
+  const float* p11 = xc + tt.i1 * pw + static_cast<long long>(th.i1) * Wi;
+  const float a00 = lerp_rn(tw.l0, __ldg(p00 + tw.i0), tw.l1, __ldg(p00 + tw.i1));
+  const float a01 = lerp_rn(tw.l0, __ldg(p01 + tw.i0), tw.l1, __ldg(p01 + tw.i1));
+  const float a10 = lerp_rn(tw.l0, __ldg(p10 + tw.i0), tw.l1, __ldg(p10 + tw.i1));
+  const float a11 = lerp_rn(tw.l0, __ldg(p11 + tw.i0), tw.l1, __ldg(p11 + tw.i1));
+  const float b0 = lerp_rn(th.l0, a00, th.l1, a01);
+  const float b1 = lerp_rn(th.l0, a10, th.l1, a11);
+  return lerp_rn(tt.l0, b0, tt.l1, b1);
+}
+
+struct ResizeGeom {
+  int Ti, Hi, Wi, To, Ho, Wo;
+  float st, sh, sw;
+  int align;
+};
+
+__global__ void resize3d_fwd_kernel(const float* __restrict__ x, long long NC, ResizeGeom g, float* __restrict__ y) {
+  const long long total = NC * g.To * g.Ho * g.Wo;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(idx % g.Wo);
+    long long r = idx / g.Wo;
+    const int h = static_cast<int>(r % g.Ho);
+    r /= g.Ho;
+    const int t = static_cast<int>(r % g.To);
+    const long long nc = r / g.To;
+    const Tap tt = linear_tap(t, g.Ti, g.st, g.align), th = linear_tap(h, g.Hi, g.sh, g.align),
+              tw = linear_tap(w, g.Wi, g.sw, g.align);
+    y[idx] = trilerp(x + nc * g.Ti * g.Hi * g.Wi, g.Hi, g.Wi, tt, th, tw);
+  }
+}
+
+// adjoint as a gather: each input element visits the (few) output positions whose taps touch it.
+__device__ __forceinline__ void cand_range(int i, int n_out, float scale, int align, int& lo, int& hi) {
+  if (scale <= 0.f) {
+    lo = 0;
+    hi = n_out - 1;
+    return;
+  }
+  const float inv = 1.0f / scale;
+  const float off = align ? 0.f : 0.5f;
+  lo = static_cast<int>(floorf((static_cast<float>(i) - 1.f + off) * inv - off)) - 1;
+  hi = static_cast<int>(ceilf((static_cast<float>(i) + 1.f + off) * inv - off)) + 1;
+  if (lo < 0) lo = 0;
+  if (hi > n_out - 1) hi = n_out - 1;
+}
+
+__global__ void resize3d_bwd_kernel(const float* __restrict__ gy, long long NC, ResizeGeom g,
+                                    float* __restrict__ gx) {
+  const long long total = NC * g.Ti * g.Hi * g.Wi;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(idx % g.Wi);
+    long long r = idx / g.Wi;
+    const int h = static_cast<int>(r % g.Hi);
+    r /= g.Hi;
+    const int t = static_cast<int>(r % g.Ti);
+    const long long nc = r / g.Ti;
+    int tlo, thi, hlo, hhi, wlo, whi;
+    cand_range(t, g.To, g.st, g.align, tlo, thi);
+    cand_range(h, g.Ho, g.sh, g.align, hlo, hhi);
+    cand_range(w, g.Wo, g.sw, g.align, wlo, whi);
+    const float* gyc = gy + nc * g.To * g.Ho * g.Wo;
+    float acc = 0.f;
+    for (int ot = tlo; ot <= thi; ++ot) {
+      const Tap a = linear_tap(ot, g.Ti, g.st, g.align);
+      const float ct = (a.i0 == t ? a.l0 : 0.f) + (a.i1 == t ? a.l1 : 0.f);
+      if (ct == 0.f) continue;
+      for (int oh = hlo; oh <= hhi; ++oh) {
+        const Tap b = linear_tap(oh, g.Hi, g.sh, g.align);
+        const float chh = (b.i0 == h ? b.l0 : 0.f) + (b.i1 == h ? b.l1 : 0.f);
+        if (chh == 0.f) continue;
+        const float cth = ct * chh;
+        const float* row = gyc + (static_cast<long long>(ot) * g.Ho + oh) * g.Wo;
+        for (int ow = wlo; ow <= whi; ++ow) {
+          const Tap c = linear_tap(ow, g.Wi, g.sw, g.align);
+          const float cw = (c.i0 == w ? c.l0 : 0.f) + (c.i1 == w ? c.l1 : 0.f);
+          if (cw != 0.f) acc = fmaf(cth * cw, __ldg(row + ow), acc);
+        }
+      }
+    }
+    gx[idx] = acc;
+  }
+}
+
+__global__ void linear_taps_kernel(int n_in, int n_out, float scale, int align, int* i0, int* i1, float* l0,
+                                   float* l1) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_out) return;
+  const Tap t = linear_tap(o, n_in, scale, align);
+  i0[o] = t.i0;
+  i1[o] = t.i1;
+  l0[o] = t.l0;
+  l1[o] = t.l1;
+}
+
+// ----------------------------------------------------------------------------------------------- Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (static_cast<float>(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+  const float r = sqrtf(-2.0f * logf(u01(a)));
+  float s, c;
+  sincosf(6.283185307179586f * u01(b), &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+
+// block input stage (networks_3d.py:440-446): up = resize(x_prev) ; x_in = up + noise*amp ; C <= 4
+__global__ void upsample_noise_pack_kernel(const float* __restrict__ x, int N, int C, ResizeGeom g,
+                                           const float* __restrict__ noise, float amp, unsigned long long seed,
+                                           unsigned long long sample_base, float* __restrict__ up,
+                                           __nv_bfloat16* __restrict__ xin) {
+  const long long spo = static_cast<long long>(g.To) * g.Ho * g.Wo;
+  const long long spi = static_cast<long long>(g.Ti) * g.Hi * g.Wi;
+  const long long total = static_cast<long long>(N) * spo;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = idx / spo, s = idx - n * spo;
+    const int w = static_cast<int>(s % g.Wo);
+    const long long r = s / g.Wo;
+    const int h = static_cast<int>(r % g.Ho);
+    const int t = static_cast<int>(r / g.Ho);
+    const Tap tt = linear_tap(t, g.Ti, g.st, g.align), th = linear_tap(h, g.Hi, g.sh, g.align),
+              tw = linear_tap(w, g.Wi, g.sw, g.align);
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    if (seed != 0ull) {
+      const unsigned long long sample = sample_base + static_cast<unsigned long long>(n);
+      const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(s), static_cast<uint32_t>(s >> 32),
+                                                 static_cast<uint32_t>(sample), static_cast<uint32_t>(sample >> 32)),
+                                      make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+      box_muller(rnd.x, rnd.y, z[0], z[1]);
+      box_muller(rnd.z, rnd.w, z[2], z[3]);
+    }
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < C; ++c) {
+      const float u = trilerp(x + (n * C + c) * spi, g.Hi, g.Wi, tt, th, tw);
+      const long long o = (n * C + c) * spo + s;
+      up[o] = u;
+      float nz = 0.f;
+      if (noise) nz = noise[o];
+      else if (seed != 0ull) nz = z[c];
+      v[c] = fmaf(nz, amp, u);
+    }
+    *reinterpret_cast<uint4*>(xin + idx * 8) =
+        make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- BatchNorm (train)
+// y: (voxels, 64) bf16.  thread -> one 16 B channel group; 8 groups per voxel; block = 256 threads = 32 voxels/iter.
+__global__ void bn_stats_cl_kernel(const __nv_bfloat16* __restrict__ y, long long voxels, double* __restrict__ sum,
+                                   double* __restrict__ sumsq) {
+  const int g = threadIdx.x & 7;         // channel group
+  const int vl = threadIdx.x >> 3;       // voxel lane 0..31
+  float a[8], b[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] = b[e] = 0.f;
+  for (long long v = static_cast<long long>(blockIdx.x) * 32 + vl; v < voxels;
+       v += static_cast<long long>(gridDim.x) * 32) {
+    const uint4 pk = *reinterpret_cast<const uint4*>(y + v * 64 + g * 8);
+    const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+    for (int e2 = 0; e2 < 4; ++e2) {
+      const float2 f = unpack2(w[e2]);
+      a[2 * e2] += f.x;
+      a[2 * e2 + 1] += f.y;
+      b[2 * e2] = fmaf(f.x, f.x, b[2 * e2]);
+      b[2 * e2 + 1] = fmaf(f.y, f.y, b[2 * e2 + 1]);
+    }
+  }
+  // reduce over the 32 voxel lanes that share a channel group: lanes with equal (threadIdx.x & 7)
+  // within a warp: 4 voxel lanes per group -> shuffle over xor 8, 16 ; then across 8 warps via smem
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    a[e] += __shfl_xor_sync(0xffffffffu, a[e], 8);
+    a[e] += __shfl_xor_sync(0xffffffffu, a[e], 16);
+    b[e] += __shfl_xor_sync(0xffffffffu, b[e], 8);
+    b[e] += __shfl_xor_sync(0xffffffffu, b[e], 16);
+  }
+  __shared__ float red[8][2][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 8) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      red[warp][0][lane * 8 + e] = a[e];
+      red[warp][1][lane * 8 + e] = b[e];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
+    double acc = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) acc += static_cast<double>(red[wv][which][c]);
+    atomicAdd((which ? sumsq : sum) + c, acc);
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* __restrict__ mm, float* __restrict__ mv,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_o,
+                                   float* __restrict__ invstd_o) {
+  const int c = threadIdx.x;
+  if (c >= 64) return;
+  const double mean = sum[c] / count;
+  double var = sumsq[c] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - static_cast<float>(mean) * sc;
+  if (mean_o) mean_o[c] = static_cast<float>(mean);
+  if (invstd_o) invstd_o[c] = invstd;
+  if (mm) mm[c] = momentum * mm[c] + (1.f - momentum) * static_cast<float>(mean);
+  if (mv) mv[c] = momentum * mv[c] + (1.f - momentum) * static_cast<float>(var);
+}
+
+__global__ void bn_apply_cl_kernel(const __nv_bfloat16* __restrict__ y, long long groups /*voxels*8*/,
+                                   const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                                   __nv_bfloat16* __restrict__ x) {
+  __shared__ float sc[64], sh[64];
+  if (threadIdx.x < 64) {
+    sc[threadIdx.x] = scale[threadIdx.x];
+    sh[threadIdx.x] = shift[threadIdx.x];
+  }
+  __syncthreads();
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < groups;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i & 7);
+    const uint4 pk = *reinterpret_cast<const uint4*>(y + i * 8);
+    const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e2 = 0; e2 < 4; ++e2) {
+      float2 f = unpack2(w[e2]);
+      const int c = g * 8 + 2 * e2;
+      f.x = fmaf(f.x, sc[c], sh[c]);
+      f.y = fmaf(f.y, sc[c + 1], sh[c + 1]);
+      if (act == 1) {
+        f.x = f.x > 0.f ? f.x : 0.2f * f.x;
+        f.y = f.y > 0.f ? f.y : 0.2f * f.y;
+      }
+      o[e2] = pack2(f.x, f.y);
+    }
+    *reinterpret_cast<uint4*>(x + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- spectral norm
+// One CTA.  W: (cout, k) fp32 row-major (the (Cout, Cin*27) view of spectral_norm.py:146).
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  return t;
+}
+
+__global__ void sn_power_iter_kernel(const float* __restrict__ w, int cout, int k, float* __restrict__ u,
+                                     float* __restrict__ v, float* __restrict__ sigma, float* __restrict__ inv_sigma) {
+  extern __shared__ float sm[];
+  float* su = sm;            // [cout]
+  float* sv = su + cout;     // [k]
+  float* swv = sv + k;       // [cout]
+  __shared__ float red[32];
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) su[i] = u[i];
+  __syncthreads();
+  // v = l2normalize(W^T u)
+  float part = 0.f;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    float acc = 0.f;
+    for (int i = 0; i < cout; ++i) acc = fmaf(w[static_cast<size_t>(i) * k + j], su[i], acc);
+    sv[j] = acc;
+    part = fmaf(acc, acc, part);
+  }
+  float nrm = block_sum(part, red);
+  float inv = rsqrtf(fmaxf(nrm, 1e-12f));
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    sv[j] *= inv;
+    v[j] = sv[j];
+  }
+  __syncthreads();
+  // Wv (one warp per output row, strided over rows)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int i = warp; i < cout; i += nw) {
+    float acc = 0.f;
+    for (int j = lane; j < k; j += 32) acc = fmaf(w[static_cast<size_t>(i) * k + j], sv[j], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) swv[i] = acc;
+  }
+  __syncthreads();
+  part = 0.f;
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) part = fmaf(swv[i], swv[i], part);
+  nrm = block_sum(part, red);
+  inv = rsqrtf(fmaxf(nrm, 1e-12f));
+  // u = l2normalize(Wv) ; sigma = u^T (W v)
+  part = 0.f;
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) {
+    const float un = swv[i] * inv;
+    u[i] = un;
+    part = fmaf(un, swv[i], part);
+  }
+  const float sg = block_sum(part, red);
+  if (threadIdx.x == 0) {
+    sigma[0] = sg;
+    inv_sigma[0] = 1.0f / sg;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- epilogue vectors
+__global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const float* mean, const float* var,
+                                    float eps, const float* bias, int C, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] / sqrtf(var[c] + eps);
+  scale[c] = sc;
+  shift[c] = (bias[c] - mean[c]) * sc + beta[c];
+}
+__global__ void affine_from_bias_kernel(const float* bias, const float* inv_sigma, int C, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  scale[c] = inv_sigma ? inv_sigma[0] : 1.0f;
+  shift[c] = bias ? bias[c] : 0.f;
+}
+
+// ----------------------------------------------------------------------------------------------- reductions
+template <int OP>  // 0: sum (a-b)^2 ; 1: sum a ; 2: sum -0.5(1+lv-mu^2-exp(lv))
+__global__ void reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float inv_n,
+                              float* __restrict__ out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    if (OP == 0) {
+      const float d = a[i] - b[i];
+      acc = fmaf(d, d, acc);
+    } else if (OP == 1) {
+      acc += a[i];
+    } else {
+      const float mu = a[i], lv = b[i];
+      acc += -0.5f * (1.f + lv - mu * mu - expf(lv));
+    }
+  }
+  const float t = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, t * inv_n);
+}
+
+__global__ void reparam_kernel(const float* __restrict__ mu, const float* __restrict__ lv,
+                               const float* __restrict__ eps, long long n, float* __restrict__ z) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    z[i] = fmaf(eps[i], expf(0.5f * lv[i]), mu[i]);
+}
+
+// ----------------------------------------------------------------------------------------------- clip + Adam
+__global__ void adam_norm_kernel(const AdamTable tab, float* __restrict__ norms) {
+  __shared__ float red[32];
+  const int t = blockIdx.y;
+  const float* g = tab.g[t];
+  const long long n = tab.n[t];
+  float acc = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    acc = fmaf(g[i], g[i], acc);
+  const float s = block_sum(acc, red);
+  if (threadIdx.x == 0 && s != 0.f) atomicAdd(norms + t, s);
+}
+
+__global__ void adam_apply_kernel(const AdamTable tab, const float* __restrict__ norms, float beta1, float beta2,
+                                  float eps, float bc /* sqrt(1-b2^t)/(1-b1^t) */, float clip) {
+  const int t = blockIdx.y;
+  float* p = tab.p[t];
+  const float* g = tab.g[t];
+  float* m = tab.m[t];
+  float* v = tab.v[t];
+  const long long n = tab.n[t];
+  const float lr_t = tab.lr[t] * bc;
+  float coef = 1.0f;
+  if (clip > 0.f) coef = clip / fmaxf(sqrtf(norms[t]), clip);   // ClipByNorm: g*c / max(||g||, c)
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * coef;
+    const float mi = m[i] + (gi - m[i]) * (1.f - beta1);
+    const float vi = v[i] + (gi * gi - v[i]) * (1.f - beta2);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+inline int grid_for(long long n, int block, int cap = 148 * 16) {
+  long long b = (n + block - 1) / block;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace
+
+// =============================================================================================== host wrappers
+#define LAUNCH_CHECK()                          \
+  do {                                          \
+    cudaError_t e_ = cudaGetLastError();        \
+    if (e_ != cudaSuccess) return e_;           \
+  } while (0)
+
+cudaError_t ew_pack_cl(const float* x, int N, int C, long long sp, __nv_bfloat16* y, int c_pitch, int c_off,
+                       int c_zero_to, cudaStream_t st) {
+  const long long voxels = static_cast<long long>(N) * sp;
+  const int groups = (c_zero_to - c_off > C ? c_zero_to - c_off : C) + 7 >> 3;
+  const long long total = voxels * groups;
+  pack_cl_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, C, sp, voxels, y, c_pitch, c_off,
+                                                                            groups);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_unpack_cl(const __nv_bfloat16* x, int N, int C, long long sp, int c_pitch, int c_off, float* y,
+                         cudaStream_t st) {
+  const long long voxels = static_cast<long long>(N) * sp;
+  const int groups = (C + 7) >> 3;
+  const long long total = voxels * groups;
+  unpack_cl_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, C, sp, voxels, c_pitch, c_off, y,
+                                                                              groups);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+static float axis_scale(int n_in, int n_out, int align) {
+  if (align) return n_out > 1 ? static_cast<float>(n_in - 1) / static_cast<float>(n_out - 1) : 0.f;
+  return static_cast<float>(n_in) / static_cast<float>(n_out);
+}
+static ResizeGeom make_geom(int Ti, int Hi, int Wi, int To, int Ho, int Wo, int align) {
+  ResizeGeom g;
+  g.Ti = Ti; g.Hi = Hi; g.Wi = Wi; g.To = To; g.Ho = Ho; g.Wo = Wo;
+  g.st = axis_scale(Ti, To, align);
+  g.sh = axis_scale(Hi, Ho, align);
+  g.sw = axis_scale(Wi, Wo, align);
+  g.align = align;
+  return g;
+}
+
+void ew_linear_taps_host(int n_in, int n_out, int align, int32_t* i0, int32_t* i1, float* l0, float* l1) {
+  const float s = axis_scale(n_in, n_out, align);
+  for (int o = 0; o < n_out; ++o) {
+    const Tap t = linear_tap(o, n_in, s, align);
+    i0[o] = t.i0; i1[o] = t.i1; l0[o] = t.l0; l1[o] = t.l1;
+  }
+}
+cudaError_t ew_linear_taps_dev(int n_in, int n_out, int align, int32_t* i0, int32_t* i1, float* l0, float* l1,
+                               cudaStream_t st) {
+  linear_taps_kernel<<<(n_out + 127) / 128, 128, 0, st>>>(n_in, n_out, axis_scale(n_in, n_out, align), align, i0, i1,
+                                                         l0, l1);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_resize3d_fwd(const float* x, long long NC, int Ti, int Hi, int Wi, float* y, int To, int Ho, int Wo,
+                            int align, cudaStream_t st) {
+  const ResizeGeom g = make_geom(Ti, Hi, Wi, To, Ho, Wo, align);
+  resize3d_fwd_kernel<<<grid_for(NC * To * Ho * Wo, 256), 256, 0, st>>>(x, NC, g, y);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_resize3d_bwd(const float* gy, long long NC, int To, int Ho, int Wo, float* gx, int Ti, int Hi, int Wi,
+                            int align, cudaStream_t st) {
+  const ResizeGeom g = make_geom(Ti, Hi, Wi, To, Ho, Wo, align);
+  resize3d_bwd_kernel<<<grid_for(NC * Ti * Hi * Wi, 128), 128, 0, st>>>(gy, NC, g, gx);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_upsample_noise_pack(const float* x, int N, int C, int Ti, int Hi, int Wi, int To, int Ho, int Wo,
+                                   const float* noise, float amp, unsigned long long seed,
+                                   unsigned long long sample_base, float* up, __nv_bfloat16* xin, cudaStream_t st) {
+  const ResizeGeom g = make_geom(Ti, Hi, Wi, To, Ho, Wo, 1);
+  upsample_noise_pack_kernel<<<grid_for(static_cast<long long>(N) * To * Ho * Wo, 256), 256, 0, st>>>(
+      x, N, C, g, noise, amp, seed, sample_base, up, xin);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_bn_stats_cl(const __nv_bfloat16* y, long long voxels, double* sum, double* sumsq, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(sum, 0, 64 * sizeof(double), st);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(sumsq, 0, 64 * sizeof(double), st);
+  if (e != cudaSuccess) return e;
+  bn_stats_cl_kernel<<<grid_for(voxels, 32, 148 * 8), 256, 0, st>>>(y, voxels, sum, sumsq);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_bn_finalize(const double* sum, const double* sumsq, long long count, const float* gamma,
+                           const float* beta, float eps, float momentum, float* mm, float* mv, float* scale,
+                           float* shift, float* mean, float* invstd, cudaStream_t st) {
+  bn_finalize_kernel<<<1, 64, 0, st>>>(sum, sumsq, static_cast<double>(count), gamma, beta, eps, momentum, mm, mv,
+                                       scale, shift, mean, invstd);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_bn_apply_cl(const __nv_bfloat16* y, long long voxels, const float* scale, const float* shift, int act,
+                           __nv_bfloat16* x, cudaStream_t st) {
+  bn_apply_cl_kernel<<<grid_for(voxels * 8, 256), 256, 0, st>>>(y, voxels * 8, scale, shift, act, x);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_sn_power_iter(const float* w, int cout, int k, float* u, float* v, float* sigma, float* inv_sigma,
+                             cudaStream_t st) {
+  const size_t smem = (2 * static_cast<size_t>(cout) + k) * sizeof(float);
+  sn_power_iter_kernel<<<1, 512, smem, st>>>(w, cout, k, u, v, sigma, inv_sigma);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_bn_fold_eval(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                            const float* bias, int C, float* scale, float* shift, cudaStream_t st) {
+  bn_fold_eval_kernel<<<(C + 63) / 64, 64, 0, st>>>(gamma, beta, mean, var, eps, bias, C, scale, shift);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_affine_from_bias(const float* bias, const float* inv_sigma, int C, float* scale, float* shift,
+                                cudaStream_t st) {
+  affine_from_bias_kernel<<<(C + 63) / 64, 64, 0, st>>>(bias, inv_sigma, C, scale, shift);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_reduce(int op, const float* a, const float* b, long long n, float* out, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float), st);
+  if (e != cudaSuccess) return e;
+  const int grid = grid_for(n, 256, 148 * 4);
+  const float inv = 1.0f / static_cast<float>(n);
+  if (op == 0) reduce_kernel<0><<<grid, 256, 0, st>>>(a, b, n, inv, out);
+  else if (op == 1) reduce_kernel<1><<<grid, 256, 0, st>>>(a, b, n, inv, out);
+  else reduce_kernel<2><<<grid, 256, 0, st>>>(a, b, n, inv, out);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_reparam(const float* mu, const float* lv, const float* eps, long long n, float* z, cudaStream_t st) {
+  reparam_kernel<<<grid_for(n, 256), 256, 0, st>>>(mu, lv, eps, n, z);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_adam_clip(const AdamTable& tab, int n_tensors, float* norms_scratch, float beta1, float beta2,
+                         float eps, float bias_corr, float clip, cudaStream_t st) {
+  if (clip > 0.f) {
+    cudaError_t e = cudaMemsetAsync(norms_scratch, 0, ADAM_MAX_TENSORS * sizeof(float), st);
+    if (e != cudaSuccess) return e;
+    adam_norm_kernel<<<dim3(32, n_tensors), 256, 0, st>>>(tab, norms_scratch);
+    LAUNCH_CHECK();
+  }
+  adam_apply_kernel<<<dim3(32, n_tensors), 256, 0, st>>>(tab, norms_scratch, beta1, beta2, eps, bias_corr, clip);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+}  // namespace hpvg

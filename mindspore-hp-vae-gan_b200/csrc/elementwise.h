@@ -1,0 +1,50 @@
+// Internal host-side launchers of the bandwidth-bound kernels (see elementwise.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace hpvg {
+
+constexpr int ADAM_MAX_TENSORS = 64;
+struct AdamTable {
+  float* p[ADAM_MAX_TENSORS];
+  const float* g[ADAM_MAX_TENSORS];
+  float* m[ADAM_MAX_TENSORS];
+  float* v[ADAM_MAX_TENSORS];
+  long long n[ADAM_MAX_TENSORS];
+  float lr[ADAM_MAX_TENSORS];
+};
+
+cudaError_t ew_pack_cl(const float* x, int N, int C, long long sp, __nv_bfloat16* y, int c_pitch, int c_off,
+                       int c_zero_to, cudaStream_t st);
+cudaError_t ew_unpack_cl(const __nv_bfloat16* x, int N, int C, long long sp, int c_pitch, int c_off, float* y,
+                         cudaStream_t st);
+void ew_linear_taps_host(int n_in, int n_out, int align, int32_t* i0, int32_t* i1, float* l0, float* l1);
+cudaError_t ew_linear_taps_dev(int n_in, int n_out, int align, int32_t* i0, int32_t* i1, float* l0, float* l1,
+                               cudaStream_t st);
+cudaError_t ew_resize3d_fwd(const float* x, long long NC, int Ti, int Hi, int Wi, float* y, int To, int Ho, int Wo,
+                            int align, cudaStream_t st);
+cudaError_t ew_resize3d_bwd(const float* gy, long long NC, int To, int Ho, int Wo, float* gx, int Ti, int Hi, int Wi,
+                            int align, cudaStream_t st);
+cudaError_t ew_upsample_noise_pack(const float* x, int N, int C, int Ti, int Hi, int Wi, int To, int Ho, int Wo,
+                                   const float* noise, float amp, unsigned long long seed,
+                                   unsigned long long sample_base, float* up, __nv_bfloat16* xin, cudaStream_t st);
+cudaError_t ew_bn_stats_cl(const __nv_bfloat16* y, long long voxels, double* sum, double* sumsq, cudaStream_t st);
+cudaError_t ew_bn_finalize(const double* sum, const double* sumsq, long long count, const float* gamma,
+                           const float* beta, float eps, float momentum, float* mm, float* mv, float* scale,
+                           float* shift, float* mean, float* invstd, cudaStream_t st);
+cudaError_t ew_bn_apply_cl(const __nv_bfloat16* y, long long voxels, const float* scale, const float* shift, int act,
+                           __nv_bfloat16* x, cudaStream_t st);
+cudaError_t ew_sn_power_iter(const float* w, int cout, int k, float* u, float* v, float* sigma, float* inv_sigma,
+                             cudaStream_t st);
+cudaError_t ew_bn_fold_eval(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                            const float* bias, int C, float* scale, float* shift, cudaStream_t st);
+cudaError_t ew_affine_from_bias(const float* bias, const float* inv_sigma, int C, float* scale, float* shift,
+                                cudaStream_t st);
+cudaError_t ew_reduce(int op, const float* a, const float* b, long long n, float* out, cudaStream_t st);
+cudaError_t ew_reparam(const float* mu, const float* lv, const float* eps, long long n, float* z, cudaStream_t st);
+cudaError_t ew_adam_clip(const AdamTable& tab, int n_tensors, float* norms_scratch, float beta1, float beta2,
+                         float eps, float bias_corr, float clip, cudaStream_t st);
+
+}  // namespace hpvg

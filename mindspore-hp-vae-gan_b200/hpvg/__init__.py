@@ -1,0 +1,7 @@
+"""hpvg — B200-native HP-VAE-GAN hot path (drop-in behind the reference's nn.Cell surface).
+
+Python host code + ctypes over libhpvg.so (hand-written sm_100a CUDA).  No torch / Triton / CPU fallback here."""
+from ._lib import EXPORTED, LIB_PATH, HpvgError, lib  # noqa: F401
+from .runtime import (BF16, F32, F64, I32, Event, PinnedBuffer, Stream, Tensor, device_sync, from_numpy,  # noqa: F401
+                      init, is_initialised, sm_count)
+from . import ops  # noqa: F401

@@ -1,0 +1,281 @@
+"""Functional operators over libhpvg's C ABI: one Python function per reference library-op call site
+(SURVEY.md §2.2).  Tensors are `hpvg.runtime.Tensor` (device memory); fp32 tensors use the reference's
+NCDHW layout, "cl" tensors are the kernels' internal channels-last bf16 layout."""
+import ctypes
+
+import numpy as np
+
+from . import runtime as rt
+from ._lib import HpvgError, check, lib
+from .runtime import BF16, F32, F64, I32, Tensor, _s
+
+CONV_64_64, CONV_64_16, CONV_8_64 = 0, 1, 2
+ACT_NONE, ACT_LRELU, ACT_TANH = 0, 1, 2
+OUT_BF16_CL, OUT_F32_NCDHW, OUT_F32_RAW = 0, 1, 2
+BN_EPS = 1e-5        # mindspore.nn.BatchNorm3d default
+BN_MOMENTUM = 0.9    # mindspore.nn.BatchNorm3d default (moving = 0.9*moving + 0.1*batch)
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.ptr)
+
+
+# ------------------------------------------------------------------------------------------------ layout
+def pack_cl(x, c_pitch=None, c_off=0, zero_to=None, out=None, stream=None):
+    """fp32 (N,C,T,H,W) -> bf16 (N,T,H,W,c_pitch)."""
+    N, C, T, H, W = x.shape
+    if c_pitch is None:
+        c_pitch = (C + 7) // 8 * 8
+    if zero_to is None:
+        zero_to = min(c_pitch, (c_off + C + 7) // 8 * 8)
+    if out is None:
+        out = Tensor((N, T, H, W, c_pitch), BF16)
+    check(lib.hpvg_pack_cl(_p(x), N, C, T, H, W, _p(out), c_pitch, c_off, zero_to, _s(stream)), "pack_cl")
+    return out
+
+
+def unpack_cl(x_cl, C=None, c_off=0, out=None, stream=None):
+    """bf16 (N,T,H,W,c_pitch) -> fp32 (N,C,T,H,W)."""
+    N, T, H, W, pitch = x_cl.shape
+    if C is None:
+        C = pitch - c_off
+    if out is None:
+        out = Tensor((N, C, T, H, W), F32)
+    check(lib.hpvg_unpack_cl(_p(x_cl), N, C, T, H, W, pitch, c_off, _p(out), _s(stream)), "unpack_cl")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ conv
+def conv_mode_for(cin, cout):
+    if cin <= 8 and cout == 64:
+        return CONV_8_64
+    if cin == 64 and cout == 64:
+        return CONV_64_64
+    if cin == 64 and cout <= 4:
+        return CONV_64_16
+    raise HpvgError("no single-pass conv kernel variant for Cin=%d Cout=%d" % (cin, cout))
+
+
+def pack_weights(w, mode, transpose_flip=False, cout_off=0, cout=None, cin_off=0, cin=None, out=None, stream=None):
+    """w: fp32 (Cout, Cin, [kt,] 3, 3) device tensor -> packed filter-bank image for `mode`."""
+    if len(w.shape) == 5:
+        w_cout, w_cin, kt = w.shape[0], w.shape[1], w.shape[2]
+    else:
+        w_cout, w_cin, kt = w.shape[0], w.shape[1], 1
+    eff_cout, eff_cin = (w_cin, w_cout) if transpose_flip else (w_cout, w_cin)
+    cout = eff_cout - cout_off if cout is None else cout
+    cin = eff_cin - cin_off if cin is None else cin
+    if out is None:
+        out = Tensor((lib.hpvg_conv_wimg_bytes(mode) // 2,), BF16)
+    check(lib.hpvg_conv_pack_weights(_p(w), w_cout, w_cin, kt, mode, 1 if transpose_flip else 0, cout_off, cout,
+                                     cin_off, cin, _p(out), _s(stream)), "conv_pack_weights")
+    return out
+
+
+def conv_cl(mode, x_cl, wimg, scale, shift, act=ACT_NONE, out_mode=OUT_BF16_CL, out=None, out_pitch=64, out_coff=0,
+            cout_real=64, addend=None, in_coff=0, stream=None):
+    """Raw kernel call.  x_cl: bf16 (N,T,H,W,in_pitch); reads channels [in_coff, in_coff+64|8)."""
+    N, T, H, W, in_pitch = x_cl.shape
+    if out is None:
+        if out_mode == OUT_BF16_CL:
+            out = Tensor((N, T, H, W, out_pitch), BF16)
+        elif out_mode == OUT_F32_RAW:
+            out = Tensor((N, T, H, W, 64), F32)
+        else:
+            out = Tensor((N, cout_real, T, H, W), F32)
+    in_ptr = ctypes.c_void_p(x_cl.ptr + 2 * in_coff)
+    check(lib.hpvg_conv_cl(mode, N, T, H, W, in_ptr, in_pitch, _p(wimg), _p(scale), _p(shift), act, out_mode, _p(out),
+                           out_pitch, out_coff, cout_real, _p(addend), _s(stream)), "conv_cl")
+    return out
+
+
+def affine_from_bias(bias, inv_sigma=None, C=None, out=None, stream=None):
+    """(scale, shift) = (1 or 1/sigma, bias) epilogue vectors; returned as one (2, 64) tensor."""
+    C = bias.shape[0] if C is None else C
+    Cp = max(64, (C + 63) // 64 * 64)
+    if out is None:
+        out = Tensor((2, Cp), F32).zero_(stream)
+    check(lib.hpvg_affine_from_bias(_p(bias), _p(inv_sigma), C, _p(out), ctypes.c_void_p(out.ptr + 4 * Cp),
+                                    _s(stream)), "affine_from_bias")
+    return out
+
+
+def bn_fold_eval(gamma, beta, mean, var, bias, out=None, eps=BN_EPS, stream=None):
+    """Eval-mode BatchNorm folded into the conv epilogue: scale = g/sqrt(v+eps), shift = (b-mean)*scale+beta."""
+    C = gamma.shape[0]
+    Cp = max(64, (C + 63) // 64 * 64)
+    if out is None:
+        out = Tensor((2, Cp), F32).zero_(stream)
+    check(lib.hpvg_bn_fold_eval(_p(gamma), _p(beta), _p(mean), _p(var), eps, _p(bias), C, _p(out),
+                                ctypes.c_void_p(out.ptr + 4 * Cp), _s(stream)), "bn_fold_eval")
+    return out
+
+
+def _sc(aff):
+    return aff, aff.view((64,), F32, 256)
+
+
+def conv3d_cl_any(x_cl, w, aff, act, cin, cout, out_mode=OUT_BF16_CL, residual=None, out=None, wimgs=None,
+                  transpose_flip=False, stream=None):
+    """Convolution for every channel combination on the hot path, composed from the kernel variants:
+    Cin in {<=8, 64, 128}, Cout in {<=4, 64, 128}.  aff: (2,64*ceil(cout/64)) epilogue vectors.
+    Returns bf16 cl (cout 64/128) or fp32 ncdhw (cout <= 4)."""
+    N, T, H, W, pitch = x_cl.shape
+    if cout <= 4:
+        assert cin == 64
+        wi = wimgs[0] if wimgs else pack_weights(w, CONV_64_16, transpose_flip, stream=stream)
+        s, b = _sc(aff)
+        return conv_cl(CONV_64_16, x_cl, wi, s, b, act, OUT_F32_NCDHW, out=out, cout_real=cout, addend=residual,
+                       stream=stream)
+    n_ob = cout // 64
+    n_ib = 1 if cin <= 8 else cin // 64
+    if out is None:
+        out = Tensor((N, T, H, W, cout), BF16)
+    k = 0
+    for ob in range(n_ob):
+        s = aff.view((64,), F32, ob * 256)
+        b = aff.view((64,), F32, (n_ob + ob) * 256)
+        partial = None
+        for ib in range(n_ib):
+            mode = CONV_8_64 if cin <= 8 else CONV_64_64
+            if wimgs:
+                wi = wimgs[k]
+            else:
+                wi = pack_weights(w, mode, transpose_flip, cout_off=ob * 64, cout=64, cin_off=ib * 64,
+                                  cin=min(cin, 64), stream=stream)
+            k += 1
+            last = ib == n_ib - 1
+            if not last:
+                partial = conv_cl(mode, x_cl, wi, s, b, ACT_NONE, OUT_F32_RAW, in_coff=ib * 64, stream=stream)
+            else:
+                conv_cl(mode, x_cl, wi, s, b, act, OUT_BF16_CL, out=out, out_pitch=cout, out_coff=ob * 64,
+                        addend=partial, in_coff=ib * 64, stream=stream)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ resize
+def linear_taps(n_in, n_out, align_corners=True):
+    """Host tables (i0, i1, l0, l1) of the resize rule — bit-exact contract with the reference."""
+    i0 = np.empty(n_out, np.int32)
+    i1 = np.empty(n_out, np.int32)
+    l0 = np.empty(n_out, np.float32)
+    l1 = np.empty(n_out, np.float32)
+    c = ctypes
+    check(lib.hpvg_linear_taps(n_in, n_out, int(align_corners), i0.ctypes.data_as(c.POINTER(c.c_int32)),
+                               i1.ctypes.data_as(c.POINTER(c.c_int32)), l0.ctypes.data_as(c.POINTER(c.c_float)),
+                               l1.ctypes.data_as(c.POINTER(c.c_float))), "linear_taps")
+    return i0, i1, l0, l1
+
+
+def linear_taps_device(n_in, n_out, align_corners=True):
+    """The same tables as computed by the device code path."""
+    i0, i1 = Tensor((n_out,), I32), Tensor((n_out,), I32)
+    l0, l1 = Tensor((n_out,), F32), Tensor((n_out,), F32)
+    check(lib.hpvg_linear_taps_dev(n_in, n_out, int(align_corners), _p(i0), _p(i1), _p(l0), _p(l1), None),
+          "linear_taps_dev")
+    return i0.numpy(), i1.numpy(), l0.numpy(), l1.numpy()
+
+
+def resize3d(x, size, align_corners=True, out=None, stream=None):
+    """UpsampleTrilinear3D(output_size=size, align_corners) forward (trilinear.py:171-254)."""
+    N, C, Ti, Hi, Wi = x.shape
+    To, Ho, Wo = (int(v) for v in size)
+    if out is None:
+        out = Tensor((N, C, To, Ho, Wo), F32)
+    check(lib.hpvg_resize3d_fwd(_p(x), N, C, Ti, Hi, Wi, _p(out), To, Ho, Wo, int(align_corners), _s(stream)),
+          "resize3d_fwd")
+    return out
+
+
+def resize3d_bwd(gy, in_size, align_corners=True, out=None, stream=None):
+    N, C, To, Ho, Wo = gy.shape
+    Ti, Hi, Wi = (int(v) for v in in_size)
+    if out is None:
+        out = Tensor((N, C, Ti, Hi, Wi), F32)
+    check(lib.hpvg_resize3d_bwd(_p(gy), N, C, To, Ho, Wo, _p(out), Ti, Hi, Wi, int(align_corners), _s(stream)),
+          "resize3d_bwd")
+    return out
+
+
+def upsample_noise_pack(x, size, noise=None, amp=0.0, seed=0, sample_base=0, up=None, xin=None, stream=None):
+    """Block input stage (networks_3d.py:440-446).  Returns (up fp32 ncdhw, x_in bf16 cl 8-channel)."""
+    N, C, Ti, Hi, Wi = x.shape
+    To, Ho, Wo = (int(v) for v in size)
+    if up is None:
+        up = Tensor((N, C, To, Ho, Wo), F32)
+    if xin is None:
+        xin = Tensor((N, To, Ho, Wo, 8), BF16)
+    check(lib.hpvg_upsample_noise_pack(_p(x), N, C, Ti, Hi, Wi, To, Ho, Wo, _p(noise), float(amp), int(seed),
+                                       int(sample_base), _p(up), _p(xin), _s(stream)), "upsample_noise_pack")
+    return up, xin
+
+
+# ------------------------------------------------------------------------------------------------ batch norm (train)
+def bn_train_cl(y_cl, gamma, beta, moving_mean, moving_var, act=ACT_LRELU, out=None, stats=None, stream=None):
+    """Training-mode BatchNorm + LeakyReLU over a (.., 64) bf16 cl tensor (networks_3d.py:52).  Updates the moving
+    statistics in place.  Returns (x_cl, saved) where saved = (scale, shift, mean, invstd) for the backward."""
+    voxels = int(np.prod(y_cl.shape[:-1]))
+    if stats is None:
+        stats = Tensor((2, 64), F64)
+    sums, sumsq = stats, stats.view((64,), F64, 512)
+    check(lib.hpvg_bn_stats_cl(_p(y_cl), voxels, _p(sums), _p(sumsq), _s(stream)), "bn_stats")
+    saved = Tensor((4, 64), F32)
+    sc, sh = saved, saved.view((64,), F32, 256)
+    mean, invstd = saved.view((64,), F32, 512), saved.view((64,), F32, 768)
+    check(lib.hpvg_bn_finalize(_p(sums), _p(sumsq), voxels, _p(gamma), _p(beta), BN_EPS, BN_MOMENTUM,
+                               _p(moving_mean), _p(moving_var), _p(sc), _p(sh), _p(mean), _p(invstd), _s(stream)),
+          "bn_finalize")
+    if out is None:
+        out = Tensor(y_cl.shape, BF16)
+    check(lib.hpvg_bn_apply_lrelu_cl(_p(y_cl), voxels, _p(sc), _p(sh), act, _p(out), _s(stream)), "bn_apply")
+    return out, saved
+
+
+# ------------------------------------------------------------------------------------------------ spectral norm
+def sn_power_iter(w, u, v, out=None, stream=None):
+    """spectral_norm.py:142-151.  Updates u, v in place; returns a (2,) tensor (sigma, 1/sigma)."""
+    cout = w.shape[0]
+    k = w.size // cout
+    if out is None:
+        out = Tensor((2,), F32)
+    check(lib.hpvg_sn_power_iter(_p(w), cout, k, _p(u), _p(v), _p(out), ctypes.c_void_p(out.ptr + 4), _s(stream)),
+          "sn_power_iter")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ losses / misc
+def mse(a, b, out=None, stream=None):
+    out = out or Tensor((1,), F32)
+    check(lib.hpvg_mse(_p(a), _p(b), a.size, _p(out), _s(stream)), "mse")
+    return out
+
+
+def mean(a, out=None, stream=None):
+    out = out or Tensor((1,), F32)
+    check(lib.hpvg_mean(_p(a), a.size, _p(out), _s(stream)), "mean")
+    return out
+
+
+def kl_criterion(mu, logvar, out=None, stream=None):
+    """losses.py:5-7."""
+    out = out or Tensor((1,), F32)
+    check(lib.hpvg_kl(_p(mu), _p(logvar), mu.size, _p(out), _s(stream)), "kl")
+    return out
+
+
+def reparam(mu, logvar, eps, out=None, stream=None):
+    """networks_3d.py:415-417."""
+    out = out or Tensor(mu.shape, F32)
+    check(lib.hpvg_reparam(_p(mu), _p(logvar), _p(eps), mu.size, _p(out), _s(stream)), "reparam")
+    return out
+
+
+def adam_clip_multi(params, grads, ms, vs, lrs, step, beta1=0.5, beta2=0.999, eps=1e-8, clip=0.0, stream=None):
+    """ClippedAdam.construct (optimizers.py:41-43) / nn.Adam for D (train_video.py:65): per-tensor ClipByNorm then Adam."""
+    n = len(params)
+    VP = ctypes.c_void_p * n
+    sizes = (ctypes.c_longlong * n)(*[p.size for p in params])
+    lr_arr = (ctypes.c_float * n)(*[float(x) for x in lrs])
+    check(lib.hpvg_adam_clip_multi(n, VP(*[p.ptr for p in params]), VP(*[g.ptr for g in grads]),
+                                   VP(*[m.ptr for m in ms]), VP(*[v.ptr for v in vs]), sizes, lr_arr, beta1, beta2,
+                                   eps, int(step), float(clip), _s(stream)), "adam_clip_multi")

@@ -1,0 +1,164 @@
+"""Device memory, streams and events over libhpvg's runtime shim (numpy on the host side, no torch)."""
+import ctypes
+
+import numpy as np
+
+from ._lib import HpvgError, check, lib
+
+_initialised = {"device": None}
+
+BF16 = "bfloat16"
+F32 = "float32"
+F64 = "float64"
+I32 = "int32"
+_ITEMSIZE = {BF16: 2, F32: 4, F64: 8, I32: 4}
+_NP = {F32: np.float32, F64: np.float64, I32: np.int32, BF16: np.uint16}
+
+
+def init(device=0):
+    """Select the GPU and create library scratch.  Raises when no sm_100a device is visible (no CPU fallback)."""
+    if lib.hpvg_device_count() <= 0:
+        raise HpvgError("no CUDA device visible: the hpvg product path requires a B200 (there is no CPU fallback)")
+    check(lib.hpvg_init(int(device)), "hpvg_init")
+    _initialised["device"] = int(device)
+
+
+def is_initialised():
+    return _initialised["device"] is not None
+
+
+def sm_count():
+    return lib.hpvg_sm_count()
+
+
+class Stream:
+    def __init__(self):
+        h = ctypes.c_void_p()
+        check(lib.hpvg_stream_create(ctypes.byref(h)), "stream_create")
+        self.handle = h
+
+    def sync(self):
+        check(lib.hpvg_stream_sync(self.handle), "stream_sync")
+
+
+class Event:
+    def __init__(self):
+        h = ctypes.c_void_p()
+        check(lib.hpvg_event_create(ctypes.byref(h)), "event_create")
+        self.handle = h
+
+    def record(self, stream=None):
+        check(lib.hpvg_event_record(self.handle, _s(stream)), "event_record")
+
+    def sync(self):
+        check(lib.hpvg_event_sync(self.handle), "event_sync")
+
+    def elapsed_ms(self, end):
+        ms = ctypes.c_float()
+        check(lib.hpvg_event_elapsed_ms(self.handle, end.handle, ctypes.byref(ms)), "event_elapsed")
+        return ms.value
+
+
+def _s(stream):
+    return stream.handle if stream is not None else None
+
+
+def device_sync():
+    check(lib.hpvg_device_sync(), "device_sync")
+
+
+class Tensor:
+    """A shaped view of caller-owned device memory.  dtype in {float32, bfloat16, float64, int32}."""
+
+    __slots__ = ("ptr", "shape", "dtype", "_owner", "nbytes")
+
+    def __init__(self, shape, dtype=F32, ptr=None, owner=None):
+        self.shape = tuple(int(v) for v in shape)
+        self.dtype = dtype
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * _ITEMSIZE[dtype] if len(self.shape) else _ITEMSIZE[dtype]
+        if ptr is None:
+            if not is_initialised():
+                raise HpvgError("hpvg.init() must be called before allocating device memory")
+            h = ctypes.c_void_p()
+            check(lib.hpvg_malloc(ctypes.byref(h), self.nbytes), "malloc")
+            self.ptr = h.value
+            self._owner = True
+        else:
+            self.ptr = int(ptr)
+            self._owner = owner   # keeps the parent allocation alive
+
+    def __del__(self):
+        try:
+            if self._owner is True and self.ptr:
+                lib.hpvg_free(ctypes.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+    @property
+    def size(self):
+        return int(np.prod(self.shape, dtype=np.int64)) if len(self.shape) else 1
+
+    def view(self, shape, dtype=None, byte_offset=0):
+        return Tensor(shape, dtype or self.dtype, ptr=self.ptr + byte_offset, owner=self)
+
+    def zero_(self, stream=None):
+        check(lib.hpvg_memset(self.ptr, 0, self.nbytes, _s(stream)), "memset")
+        return self
+
+    def copy_from_host(self, arr, stream=None):
+        a = np.ascontiguousarray(arr, dtype=_NP[self.dtype])
+        if a.nbytes != self.nbytes:
+            raise HpvgError("copy_from_host: size mismatch %d vs %d" % (a.nbytes, self.nbytes))
+        check(lib.hpvg_h2d(self.ptr, a.ctypes.data, self.nbytes, _s(stream)), "h2d")
+        if stream is not None:
+            stream.sync()   # pageable source must stay alive until the copy is done
+        return self
+
+    def numpy(self, stream=None):
+        out = np.empty(self.shape, dtype=_NP[self.dtype])
+        check(lib.hpvg_d2h(out.ctypes.data, self.ptr, self.nbytes, _s(stream)), "d2h")
+        if stream is not None:
+            stream.sync()
+        else:
+            device_sync()
+        return out
+
+    def copy_(self, other, stream=None):
+        if other.nbytes != self.nbytes:
+            raise HpvgError("copy_: size mismatch")
+        check(lib.hpvg_d2d(self.ptr, other.ptr, self.nbytes, _s(stream)), "d2d")
+        return self
+
+
+def from_numpy(arr, dtype=None, stream=None):
+    a = np.asarray(arr)
+    if dtype is None:
+        dtype = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.int32): I32}.get(a.dtype, F32)
+    t = Tensor(a.shape, dtype)
+    t.copy_from_host(a, stream)
+    return t
+
+
+def bf16_bits_to_f32(u16):
+    return (np.asarray(u16, dtype=np.uint16).astype(np.uint32) << 16).view(np.float32)
+
+
+class PinnedBuffer:
+    """Page-locked host staging buffer (for timed H2D/D2H in bench.py)."""
+
+    def __init__(self, nbytes):
+        h = ctypes.c_void_p()
+        check(lib.hpvg_host_alloc(ctypes.byref(h), int(nbytes)), "host_alloc")
+        self.ptr = h.value
+        self.nbytes = int(nbytes)
+
+    def as_array(self, shape, dtype=np.float32):
+        n = int(np.prod(shape))
+        buf = (ctypes.c_byte * (n * np.dtype(dtype).itemsize)).from_address(self.ptr)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def __del__(self):
+        try:
+            lib.hpvg_host_free(ctypes.c_void_p(self.ptr))
+        except Exception:
+            pass

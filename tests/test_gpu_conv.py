@@ -1,0 +1,136 @@
+"""Parity of the tcgen05 implicit-GEMM convolution (through the C ABI) against the torch-CPU oracle.
+
+Tolerance: north_star states rel-L2 <= 1e-2 for bf16 compute.  Inputs/weights are pre-rounded to bf16 so the only
+differences are accumulation order (fp32) and the bf16 rounding of the output — we assert 4e-3."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import bf16_round, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 4e-3
+
+
+def _conv_ref(x, w, b, act=None):
+    y = F.conv3d(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b), padding=1)
+    if act == "lrelu":
+        y = F.leaky_relu(y, 0.2)
+    if act == "tanh":
+        y = torch.tanh(y)
+    return y.numpy()
+
+
+@pytest.mark.parametrize("shape", [(1, 4, 24, 33), (2, 5, 16, 8), (1, 1, 7, 5), (1, 3, 40, 17), (1, 2, 33, 9)])
+def test_conv_64_64(hpvg_gpu, shape):
+    hp, ops = hpvg_gpu, hpvg_gpu.ops
+    N, T, H, W = shape
+    rng = np.random.default_rng(1)
+    x = bf16_round(rng.standard_normal((N, 64, T, H, W)))
+    w = bf16_round(rng.standard_normal((64, 64, 3, 3, 3)) * 0.05)
+    b = rng.standard_normal(64).astype(np.float32) * 0.1
+    x_cl = ops.pack_cl(hp.from_numpy(x))
+    aff = ops.affine_from_bias(hp.from_numpy(b))
+    y_cl = ops.conv3d_cl_any(x_cl, hp.from_numpy(w), aff, ops.ACT_LRELU, 64, 64)
+    y = ops.unpack_cl(y_cl).numpy()
+    ref = _conv_ref(x, w, b, "lrelu")
+    err = rel_l2(y, ref)
+    assert err < TOL, "conv 64->64 %s rel-L2 %.3e" % (shape, err)
+
+
+def test_conv_64_64_roundtrip_pack(hpvg_gpu):
+    hp, ops = hpvg_gpu, hpvg_gpu.ops
+    rng = np.random.default_rng(2)
+    x = bf16_round(rng.standard_normal((2, 64, 3, 9, 11)))
+    back = ops.unpack_cl(ops.pack_cl(hp.from_numpy(x))).numpy()
+    assert np.array_equal(back, x)
+
+
+@pytest.mark.parametrize("cout", [3, 1])
+def test_conv_tail(hpvg_gpu, cout):
+    hp, ops = hpvg_gpu, hpvg_gpu.ops
+    N, T, H, W = 1, 4, 30, 41
+    rng = np.random.default_rng(3)
+    x = bf16_round(rng.standard_normal((N, 64, T, H, W)))
+    w = bf16_round(rng.standard_normal((cout, 64, 3, 3, 3)) * 0.05)
+    b = rng.standard_normal(cout).astype(np.float32) * 0.1
+    res = rng.standard_normal((N, cout, T, H, W)).astype(np.float32) * 0.3
+    x_cl = ops.pack_cl(hp.from_numpy(x))
+    aff = ops.affine_from_bias(hp.from_numpy(b))
+    y = ops.conv3d_cl_any(x_cl, hp.from_numpy(w), aff, ops.ACT_TANH, 64, cout, residual=hp.from_numpy(res)).numpy()
+    ref = np.tanh(_conv_ref(x, w, b) + res)
+    err = rel_l2(y, ref)
+    assert err < TOL, "tail conv 64->%d rel-L2 %.3e" % (cout, err)
+
+
+def test_conv_head_3_64(hpvg_gpu):
+    hp, ops = hpvg_gpu, hpvg_gpu.ops
+    N, T, H, W = 2, 4, 24, 33
+    rng = np.random.default_rng(4)
+    x = bf16_round(rng.standard_normal((N, 3, T, H, W)))
+    w = bf16_round(rng.standard_normal((64, 3, 3, 3, 3)) * 0.2)
+    b = rng.standard_normal(64).astype(np.float32) * 0.1
+    x_cl = ops.pack_cl(hp.from_numpy(x), c_pitch=8)
+    aff = ops.affine_from_bias(hp.from_numpy(b))
+    y = ops.unpack_cl(ops.conv3d_cl_any(x_cl, hp.from_numpy(w), aff, ops.ACT_LRELU, 3, 64)).numpy()
+    ref = _conv_ref(x, w, b, "lrelu")
+    err = rel_l2(y, ref)
+    assert err < TOL, "head conv 3->64 rel-L2 %.3e" % err
+
+
+def test_conv_128_64_and_64_128(hpvg_gpu):
+    hp, ops = hpvg_gpu, hpvg_gpu.ops
+    N, T, H, W = 1, 4, 24, 33
+    rng = np.random.default_rng(5)
+    x = bf16_round(rng.standard_normal((N, 128, T, H, W)))
+    w = bf16_round(rng.standard_normal((64, 128, 3, 3, 3)) * 0.04)
+    b = rng.standard_normal(64).astype(np.float32) * 0.1
+    x_cl = ops.pack_cl(hp.from_numpy(x))
+    aff = ops.affine_from_bias(hp.from_numpy(b))
+    y = ops.unpack_cl(ops.conv3d_cl_any(x_cl, hp.from_numpy(w), aff, ops.ACT_NONE, 128, 64)).numpy()
+    err = rel_l2(y, _conv_ref(x, w, b))
+    assert err < TOL, "conv 128->64 rel-L2 %.3e" % err
+    x2 = bf16_round(rng.standard_normal((N, 64, T, H, W)))
+    w2 = bf16_round(rng.standard_normal((128, 64, 3, 3, 3)) * 0.05)
+    b2 = rng.standard_normal(128).astype(np.float32) * 0.1
+    aff2 = ops.affine_from_bias(hp.from_numpy(b2))
+    y2 = ops.unpack_cl(ops.conv3d_cl_any(ops.pack_cl(hp.from_numpy(x2)), hp.from_numpy(w2), aff2, ops.ACT_NONE, 64, 128)).numpy()
+    err2 = rel_l2(y2, _conv_ref(x2, w2, b2))
+    assert err2 < TOL, "conv 64->128 rel-L2 %.3e" % err2
+
+
+def test_conv_dgrad_matches_autograd(hpvg_gpu):
+    """Data gradient = the same kernel with the transposed/mirrored filter bank."""
+    hp, ops = hpvg_gpu, hpvg_gpu.ops
+    N, T, H, W = 1, 3, 20, 13
+    rng = np.random.default_rng(6)
+    gy = bf16_round(rng.standard_normal((N, 64, T, H, W)))
+    w = bf16_round(rng.standard_normal((64, 64, 3, 3, 3)) * 0.05)
+    x = torch.zeros((N, 64, T, H, W), requires_grad=True)
+    F.conv3d(x, torch.from_numpy(w), None, padding=1).backward(torch.from_numpy(gy))
+    zero = hp.from_numpy(np.zeros(64, np.float32))
+    aff = ops.affine_from_bias(zero)
+    gx = ops.unpack_cl(ops.conv3d_cl_any(ops.pack_cl(hp.from_numpy(gy)), hp.from_numpy(w), aff, ops.ACT_NONE, 64, 64,
+                                         transpose_flip=True)).numpy()
+    err = rel_l2(gx, x.grad.numpy())
+    assert err < TOL, "dgrad rel-L2 %.3e" % err
+
+
+def test_conv2d_is_t1(hpvg_gpu):
+    """Conv2d (networks_2d.py) = the T == 1 case with a (Cout, Cin, 3, 3) filter."""
+    hp, ops = hpvg_gpu, hpvg_gpu.ops
+    rng = np.random.default_rng(7)
+    x = bf16_round(rng.standard_normal((1, 64, 1, 39, 46)))
+    w = bf16_round(rng.standard_normal((64, 64, 3, 3)) * 0.05)
+    b = rng.standard_normal(64).astype(np.float32) * 0.1
+    aff = ops.affine_from_bias(hp.from_numpy(b))
+    y = ops.unpack_cl(ops.conv3d_cl_any(ops.pack_cl(hp.from_numpy(x)), hp.from_numpy(w), aff, ops.ACT_NONE, 64, 64)).numpy()
+    ref = F.conv2d(torch.from_numpy(x[:, :, 0]), torch.from_numpy(w), torch.from_numpy(b), padding=1).numpy()[:, :, None]
+    err = rel_l2(y, ref)
+    assert err < TOL, "conv2d rel-L2 %.3e" % err
+
+
+def test_conv_empty_input_is_noop(hpvg_gpu):
+    hp = hpvg_gpu
+    assert hp.lib.hpvg_conv_cl(0, 0, 4, 8, 8, None, 64, None, None, None, 0, 0, None, 64, 0, 64, None, None) == 0
