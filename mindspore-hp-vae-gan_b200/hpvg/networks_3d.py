@@ -1,0 +1,384 @@
+"""Host-side mirror of the reference's `src/modules/networks_3d.py` cells over libhpvg kernels.
+
+Same class names, constructor arguments, `construct` signatures and parameter names as the reference
+(ConvBlock3D :45, ConvBlock3DSN :57, FeatureExtractor :76, Encode3DVAE :89, WDiscriminator3D :170,
+GeneratorHPVAEGAN :354) so the parity tests read like the reference's own smoke blocks.  Instead of MindSpore
+library ops every layer is one launch of the fused tcgen05 convolution (conv + bias + folded BatchNorm / 1/sigma +
+LeakyReLU / tanh + residual), activations stay channels-last bf16 between layers.
+
+Forward only here; the training step (autodiff restated by hand) lives in `train.py`."""
+import numpy as np
+
+from . import ops
+from .ops import ACT_LRELU, ACT_NONE, ACT_TANH
+from .runtime import BF16, F32, HpvgError, Tensor, from_numpy
+from .utils import images as uimg
+
+
+class Workspace:
+    """Reusable device buffers keyed by (tag, shape, dtype): no allocation inside the steady-state loop."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, tag, shape, dtype):
+        key = (tag, tuple(int(s) for s in shape), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = Tensor(shape, dtype)
+            self._bufs[key] = t
+        return t
+
+    def nbytes(self):
+        return sum(t.nbytes for t in self._bufs.values())
+
+
+class Cell:
+    """Minimal stand-in for mindspore.nn.Cell: named parameters, train/eval flag, __call__ -> construct."""
+
+    def __init__(self):
+        self.training = False
+        self._cells = {}
+
+    def _add(self, name, cell):
+        self._cells[name] = cell
+        return cell
+
+    def cells(self):
+        return self._cells
+
+    def set_train(self, mode=True):
+        self.training = bool(mode)
+        for c in self._cells.values():
+            c.set_train(mode)
+        return self
+
+    def parameters_dict(self, prefix=""):
+        out = {}
+        for name, c in self._cells.items():
+            out.update(c.parameters_dict(prefix + name + "."))
+        return out
+
+    def load_parameters(self, params, strict=True):
+        """params: name -> numpy array (the reference's checkpoint contract, src/tools/pt2ms.py:129-188)."""
+        mine = self.parameters_dict()
+        for k, t in mine.items():
+            if k in params:
+                arr = np.asarray(params[k], np.float32)
+                if arr.size != t.size:
+                    raise HpvgError("parameter %s: size %d != %d" % (k, arr.size, t.size))
+                t.copy_from_host(arr.reshape(t.shape))
+            elif strict:
+                raise HpvgError("missing parameter %s" % k)
+        self.invalidate()
+
+    def invalidate(self):
+        for c in self._cells.values():
+            c.invalidate()
+
+    def __call__(self, *a, **k):
+        return self.construct(*a, **k)
+
+
+class ConvLayer(Cell):
+    """conv3x3x3(+bias) [-> BatchNorm3d] [-> act], or the spectrally normalised conv.  One fused kernel in eval mode."""
+
+    def __init__(self, cin, cout, bn=False, sn=False, act=None, bn_prefix="1.bn2d.", conv_prefix="0.", kt=3, rng=None):
+        super().__init__()
+        self.cin, self.cout, self.bn, self.sn, self.kt = cin, cout, bn, sn, kt
+        self.act = {None: ACT_NONE, "lrelu": ACT_LRELU, "tanh": ACT_TANH}[act]
+        self.conv_prefix, self.bn_prefix = conv_prefix, bn_prefix
+        rng = rng or np.random.default_rng(0)
+        wshape = (cout, cin, 3, 3, 3) if kt == 3 else (cout, cin, 3, 3)
+        self.p = {}
+        # weight_init=Normal(0.02, 0.0) -> N(mean 0, sigma 0.02)  (networks_3d.py:49)
+        self.p["weight"] = from_numpy((rng.standard_normal(wshape) * 0.02).astype(np.float32))
+        self.p["bias"] = from_numpy(np.zeros(cout, np.float32))
+        if sn:   # spectral_norm.py:137-140
+            k = cin * 9 * kt
+            u = rng.standard_normal((cout, 1)).astype(np.float32)
+            v = rng.standard_normal((k, 1)).astype(np.float32)
+            self.p["weight_u"] = from_numpy(u / max(np.linalg.norm(u), 1e-6))
+            self.p["weight_v"] = from_numpy(v / max(np.linalg.norm(v), 1e-6))
+        if bn:   # gamma_init=Normal(0.02, 1.0)  (networks_3d.py:52)
+            self.p["gamma"] = from_numpy((1.0 + rng.standard_normal(cout) * 0.02).astype(np.float32))
+            self.p["beta"] = from_numpy(np.zeros(cout, np.float32))
+            self.p["moving_mean"] = from_numpy(np.zeros(cout, np.float32))
+            self.p["moving_variance"] = from_numpy(np.ones(cout, np.float32))
+        self._wimgs = None
+        self._aff = None
+        self._sigma = None
+
+    # ---- parameters
+    def parameters_dict(self, prefix=""):
+        out = {}
+        for k, t in self.p.items():
+            pre = self.bn_prefix if k in ("gamma", "beta", "moving_mean", "moving_variance") else self.conv_prefix
+            out[prefix + pre + k] = t
+        return out
+
+    def invalidate(self):
+        self._wimgs = None
+        self._aff = None
+
+    def copy_from(self, other):
+        for k, t in self.p.items():
+            t.copy_(other.p[k])
+        self.invalidate()
+
+    # ---- forward
+    def _prepare(self, training, stream):
+        """(Re)build the packed filter bank and the epilogue vectors."""
+        if self._wimgs is None:
+            w = self.p["weight"]
+            if self.cout <= 4:
+                self._wimgs = [ops.pack_weights(w, ops.CONV_64_16, stream=stream)]
+            else:
+                self._wimgs = []
+                mode = ops.CONV_8_64 if self.cin <= 8 else ops.CONV_64_64
+                for ob in range(self.cout // 64):
+                    for ib in range(1 if self.cin <= 8 else self.cin // 64):
+                        self._wimgs.append(ops.pack_weights(w, mode, cout_off=ob * 64, cout=64, cin_off=ib * 64,
+                                                            cin=min(self.cin, 64), stream=stream))
+        if self.sn:
+            # Q5: u/v advance on EVERY forward, train or eval (spectral_norm.py:146-148)
+            self._sigma = ops.sn_power_iter(self.p["weight"], self.p["weight_u"], self.p["weight_v"],
+                                            out=self._sigma, stream=stream)
+            inv = self._sigma.view((1,), F32, 4)
+            self._aff = ops.affine_from_bias(self.p["bias"], inv, out=self._aff, stream=stream)
+        elif self.bn and not training:
+            if self._aff is None:
+                self._aff = ops.bn_fold_eval(self.p["gamma"], self.p["beta"], self.p["moving_mean"],
+                                             self.p["moving_variance"], self.p["bias"], stream=stream)
+        else:
+            if self._aff is None or (self.bn and training):
+                self._aff = ops.affine_from_bias(self.p["bias"], None, out=self._aff, stream=stream)
+
+    def forward_cl(self, x_cl, residual=None, out=None, ws=None, tag="", stream=None, saved=None):
+        """x_cl: bf16 channels-last.  Returns bf16 cl (Cout >= 64) or fp32 ncdhw (Cout <= 4)."""
+        training = self.training
+        self._prepare(training, stream)
+        if self.bn and training:
+            # batch statistics need the whole conv output first: conv(+bias) -> stats -> normalise+act
+            N, T, H, W, _ = x_cl.shape
+            raw = ws.get(tag + ".raw", (N, T, H, W, self.cout), BF16) if ws else None
+            y = ops.conv3d_cl_any(x_cl, self.p["weight"], self._aff, ACT_NONE, self.cin, self.cout, out=raw,
+                                  wimgs=self._wimgs, stream=stream)
+            x, sv = ops.bn_train_cl(y, self.p["gamma"], self.p["beta"], self.p["moving_mean"],
+                                    self.p["moving_variance"], self.act, out=out, stream=stream)
+            self._aff = None   # moving stats changed: a later eval-mode fold must be rebuilt
+            if saved is not None:
+                saved.update(raw=y, bn=sv)
+            return x
+        return ops.conv3d_cl_any(x_cl, self.p["weight"], self._aff, self.act, self.cin, self.cout,
+                                 residual=residual, out=out, wimgs=self._wimgs, stream=stream)
+
+
+def ConvBlock3D(in_channel, out_channel, ker_size=3, padding=1, stride=1, bn=True, act="lrelu", rng=None):
+    """networks_3d.py:45-54.  Only the 3x3x3 / stride 1 / pad 1 configuration exists on the hot path."""
+    _check_geometry(ker_size, padding, stride)
+    return ConvLayer(in_channel, out_channel, bn=bn, act=act, rng=rng)
+
+
+def ConvBlock3DSN(in_channel, out_channel, ker_size=3, padding=1, stride=1, bn=True, act="lrelu", rng=None):
+    """networks_3d.py:57-73: `bn=True` selects the spectrally normalised conv (there is no BatchNorm in it)."""
+    _check_geometry(ker_size, padding, stride)
+    if not bn:
+        raise HpvgError("ConvBlock3DSN(bn=False) (reflect-pad, bias-free) is unreachable in the reference's default "
+                        "path and is not implemented")
+    return ConvLayer(in_channel, out_channel, sn=True, act=act, rng=rng)
+
+
+def _check_geometry(ker_size, padding, stride):
+    if ker_size != 3 or padding != 1 or int(stride) != 1:
+        raise HpvgError("hpvg kernels implement ker_size=3, padding=1, stride=1 (the reference's only hot-path "
+                        "configuration, train_video.py:247-250); got k=%s p=%s s=%s" % (ker_size, padding, stride))
+
+
+class Sequential(Cell):
+    def __init__(self, layers):
+        super().__init__()
+        self.layers = list(layers)
+        for i, l in enumerate(self.layers):
+            self._add(str(i), l)
+
+    def append(self, layer):
+        self._add(str(len(self.layers)), layer)
+        self.layers.append(layer)
+
+    def __len__(self):
+        return len(self.layers)
+
+    def __getitem__(self, i):
+        return self.layers[i]
+
+
+class FeatureExtractor(Sequential):
+    """networks_3d.py:76-86: num_blocks+1 SN blocks."""
+
+    def __init__(self, in_channel, out_channel, ker_size, padding, stride, num_blocks=2, return_linear=False, rng=None):
+        if return_linear:
+            raise HpvgError("FeatureExtractor(return_linear=True) is never used by the reference; not implemented")
+        layers = [ConvBlock3DSN(in_channel, out_channel, ker_size, padding, stride, rng=rng)]
+        for _ in range(num_blocks - 1):
+            layers.append(ConvBlock3DSN(out_channel, out_channel, ker_size, padding, stride, rng=rng))
+        layers.append(ConvBlock3DSN(out_channel, out_channel, ker_size, padding, stride, rng=rng))
+        super().__init__(layers)
+
+
+class _Wrap(Sequential):
+    """A SequentialCell holding exactly one conv layer (gives the `.0.` level of the reference's names)."""
+
+
+class Encode3DVAE(Cell):
+    """networks_3d.py:89-112."""
+
+    def __init__(self, opt, out_dim=None, num_blocks=2, rng=None):
+        super().__init__()
+        output_dim = opt.nfc if out_dim is None else int(out_dim)
+        self._features = self._add("_features", FeatureExtractor(opt.nc_im, opt.nfc, opt.ker_size, opt.ker_size // 2,
+                                                                 1, num_blocks=num_blocks, rng=rng))
+        # the SN blocks are SequentialCells themselves: encode._features.{i}.0.weight
+        for l in self._features.layers:
+            l.conv_prefix = "0."
+        self._mu = self._add("_mu", ConvBlock3D(opt.nfc, output_dim, opt.ker_size, opt.ker_size // 2, 1, bn=False,
+                                                act=None, rng=rng))
+        self._logvar = self._add("_logvar", ConvBlock3D(opt.nfc, output_dim, opt.ker_size, opt.ker_size // 2, 1,
+                                                        bn=False, act=None, rng=rng))
+
+    def construct_cl(self, x_cl, stream=None):
+        f = x_cl
+        for l in self._features.layers:
+            f = l.forward_cl(f, stream=stream)
+        return self._mu.forward_cl(f, stream=stream), self._logvar.forward_cl(f, stream=stream), f
+
+    def construct(self, x):
+        mu, logvar, _ = self.construct_cl(ops.pack_cl(x, c_pitch=8))
+        return ops.unpack_cl(mu), ops.unpack_cl(logvar)
+
+
+class WDiscriminator3D(Cell):
+    """networks_3d.py:170-193: SN head, num_layer SN body blocks, plain tail conv N->1."""
+
+    def __init__(self, opt, rng=None):
+        super().__init__()
+        N = int(opt.nfc)
+        self.head = self._add("head", ConvBlock3DSN(opt.nc_im, N, opt.ker_size, opt.ker_size // 2, stride=1, rng=rng))
+        self.body = self._add("body", Sequential([ConvBlock3DSN(N, N, opt.ker_size, opt.ker_size // 2, stride=1, rng=rng)
+                                                  for _ in range(opt.num_layer)]))
+        self.tail = self._add("tail", ConvLayer(N, 1, conv_prefix="", rng=rng))
+
+    def construct(self, x, stream=None):
+        h = self.head.forward_cl(ops.pack_cl(x, c_pitch=8, stream=stream), stream=stream)
+        for l in self.body.layers:
+            h = l.forward_cl(h, stream=stream)
+        return self.tail.forward_cl(h, stream=stream)
+
+
+def _make_block(cin, opt, rng):
+    """decoder / body stage: ConvBlock3D(cin->N) + num_layer x ConvBlock3D(N->N) + Conv3d(N->nc_im)
+    (networks_3d.py:377-381, 395-401)."""
+    N = int(opt.nfc)
+    layers = [ConvBlock3D(cin, N, opt.ker_size, opt.padd_size, stride=1, rng=rng)]
+    for _ in range(opt.num_layer):
+        layers.append(ConvBlock3D(N, N, opt.ker_size, opt.padd_size, stride=1, rng=rng))
+    layers.append(ConvLayer(N, opt.nc_im, conv_prefix="", rng=rng))   # body.{s}.6.weight
+    return Sequential(layers)
+
+
+class GeneratorHPVAEGAN(Cell):
+    """networks_3d.py:354-451."""
+
+    def __init__(self, opt, is_training=False, seed=0):
+        super().__init__()
+        self.opt = opt
+        self.is_training = is_training           # Q2: the reference's drivers leave this False
+        self.vae_levels = opt.vae_levels
+        self.train_all = opt.train_all
+        self.N = int(opt.nfc)
+        self._rng = np.random.default_rng(seed)
+        self.encode = self._add("encode", Encode3DVAE(opt, out_dim=opt.latent_dim, num_blocks=opt.enc_blocks,
+                                                      rng=self._rng))
+        self.decoder = self._add("decoder", _make_block(opt.latent_dim, opt, self._rng))
+        self.body = self._add("body", Sequential([]))
+        self.ws = Workspace()
+        self.noise_seed = 0x9E3779B97F4A7C15   # device Philox key for internally drawn noise
+        self.sample_counter = 0
+
+    def init_next_stage(self):
+        """networks_3d.py:393-404: first stage is freshly initialised, later stages deep-copy the previous one."""
+        stage = _make_block(self.opt.nc_im, self.opt, self._rng)
+        if len(self.body) > 0:
+            for new, old in zip(stage.layers, self.body[-1].layers):
+                new.copy_from(old)
+        self.body.append(stage)
+        stage.set_train(self.training)
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _run_block(self, block, x_cl, residual, tag, stream, out=None):
+        ws = self.ws
+        N, T, H, W, _ = x_cl.shape
+        h = x_cl
+        for j, layer in enumerate(block.layers[:-1]):
+            buf = ws.get("%s.act%d" % (tag, j & 1), (N, T, H, W, self.N), BF16)
+            h = layer.forward_cl(h, out=buf, ws=ws, tag=tag, stream=stream)
+        tail = block.layers[-1]
+        tail.act = ACT_TANH    # tanh(block(x) [+ up]) is fused into the tail conv's epilogue (networks_3d.py:423,450)
+        return tail.forward_cl(h, residual=residual, out=out, stream=stream)
+
+    def construct(self, video, noise_amp, noise_init=None, sample_init=None, isRandom=False, noises=None, eps=None,
+                  z_pred=None, stream=None):
+        """Same contract as the reference (networks_3d.py:406-432).  Extra keyword-only hooks for testing:
+        `noises` {scale index: fp32 ncdhw Tensor} replaces the internally drawn refinement noise, `eps` / `z_pred`
+        replace the internally drawn reparameterisation noise."""
+        if sample_init is not None and len(self.body) <= sample_init[0]:
+            raise HpvgError("sample_init scale %d exceeds the %d stages" % (sample_init[0], len(self.body)))
+        mu = logvar = None
+        if noise_init is None:
+            mu, logvar = self.encode.construct(video)
+            if self.is_training:
+                if eps is None:
+                    eps = from_numpy(np.random.normal(size=mu.shape).astype(np.float32))   # networks_3d.py:28-30
+                z_vae = ops.reparam(mu, logvar, eps, stream=stream)
+            else:
+                z_vae = z_pred if z_pred is not None else from_numpy(
+                    np.random.normal(size=mu.shape).astype(np.float32))                     # networks_3d.py:32-34
+        else:
+            z_vae = noise_init
+        N = z_vae.shape[0]
+        z_cl = ops.pack_cl(z_vae, out=self.ws.get("z", (N,) + tuple(z_vae.shape[2:]) + (z_vae.shape[1],), BF16),
+                           stream=stream)
+        vae_out = self._run_block(self.decoder, z_cl, None, "dec", stream,
+                                  out=self.ws.get("vae_out", (N, self.opt.nc_im) + tuple(z_vae.shape[2:]), F32))
+        if sample_init is None:
+            x = self.refinement_layers(0, vae_out, noise_amp, isRandom, noises=noises, stream=stream)
+        else:
+            x = self.refinement_layers(sample_init[0], sample_init[1], noise_amp, isRandom, noises=noises,
+                                       stream=stream)
+        self.sample_counter += N
+        if noise_init is None:
+            return x, vae_out, mu, logvar
+        return x, vae_out
+
+    def refinement_layers(self, start_idx, x_prev_out, noise_amp, isRandom=False, noises=None, stream=None):
+        """networks_3d.py:434-451."""
+        opt = self.opt
+        for idx in range(start_idx, len(self.body)):
+            block = self.body[idx]
+            size = uimg.scale_shape(opt, idx + 1)
+            N = x_prev_out.shape[0]
+            up = self.ws.get("up%d" % idx, (N, opt.nc_im) + size, F32)
+            xin = self.ws.get("xin%d" % idx, (N,) + size + (8,), BF16)
+            add_noise = isRandom and opt.vae_levels <= idx + 1
+            noise_t, seed, amp = None, 0, 0.0
+            if add_noise:
+                amp = float(noise_amp[idx + 1])
+                if noises is not None and (idx + 1) in noises:
+                    noise_t = noises[idx + 1]
+                else:
+                    seed = (self.noise_seed + 0x632BE59BD9B4E019 * (idx + 1)) & 0xFFFFFFFFFFFFFFFF
+            ops.upsample_noise_pack(x_prev_out, size, noise=noise_t, amp=amp, seed=seed,
+                                    sample_base=self.sample_counter, up=up, xin=xin, stream=stream)
+            out = self.ws.get("out%d" % idx, (N, opt.nc_im) + size, F32)
+            x_prev_out = self._run_block(block, xin, up, "s%d" % idx, stream, out=out)
+        return x_prev_out

@@ -243,17 +243,34 @@ def init_generator_params(opt, n_body, seed=0, nd=3):
     return p
 
 
-def randomize_bn_stats(p, seed=1):
-    """Give the moving statistics non-trivial values (a trained-checkpoint stand-in) so eval-mode parity tests
-    exercise the BN fold."""
+def randomize_bn_stats(p, seed=1, opt=None, n_calib=1):
+    """Trained-checkpoint stand-in: moving statistics := the batch statistics of one random-mode forward (so
+    activations stay O(1) instead of vanishing/saturating), then perturbed by a few percent so that eval-mode
+    parity tests exercise a non-trivial BatchNorm fold; beta / hidden biases get small random values."""
+    global BN_MOMENTUM
     rng = np.random.default_rng(seed)
     for k in list(p):
+        if k.endswith("beta") or (k.endswith("bias") and p[k].shape[0] > 3):
+            p[k] = (rng.standard_normal(p[k].shape) * 0.05).astype(np.float32)
+    if opt is None:
+        opt = default_opt()
+    pt = to_torch(p)
+    nb = n_body(pt)
+    z = torch.from_numpy(rng.standard_normal((n_calib, opt.latent_dim) + scale_shape(opt, 0)).astype(np.float32))
+    noises = {s: torch.from_numpy(rng.standard_normal((n_calib, opt.nc_im) + scale_shape(opt, s)).astype(np.float32))
+              for s in range(1, nb + 1)}
+    saved, BN_MOMENTUM = BN_MOMENTUM, 0.0
+    try:
+        with torch.no_grad():
+            generator_forward(None, [1.0] + [0.1] * nb, pt, opt, noise_init=z, is_random=True, training=True,
+                              noises=noises)
+    finally:
+        BN_MOMENTUM = saved
+    for k in list(p):
         if k.endswith("moving_mean"):
-            p[k] = (rng.standard_normal(p[k].shape) * 0.05).astype(np.float32)
+            p[k] = (pt[k].numpy() + rng.standard_normal(p[k].shape) * 0.02).astype(np.float32)
         elif k.endswith("moving_variance"):
-            p[k] = (0.01 + 0.02 * rng.random(p[k].shape)).astype(np.float32)
-        elif k.endswith("beta") or (k.endswith("bias") and p[k].shape[0] > 3):
-            p[k] = (rng.standard_normal(p[k].shape) * 0.05).astype(np.float32)
+            p[k] = (pt[k].numpy() * (1.0 + 0.1 * (rng.random(p[k].shape) - 0.5))).astype(np.float32)
     return p
 
 

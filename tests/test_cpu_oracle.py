@@ -1,0 +1,203 @@
+"""CPU suite: pins the oracle against every golden vector the reference tree holds for this path,
+checks the oracle's internal consistency, the host-side geometry mirror, and that libhpvg.so loads and exports every
+symbol declared in include/hpvg.h.  No GPU calls."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import hpvg_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+# ------------------------------------------------------------------------------------------- reference golden vectors
+def test_trilinear_known_answer_from_reference_docstring():
+    """src/tools/trilinear.py:222-233: 2x2 -> (2,4,4), align_corners=False."""
+    x = np.arange(1, 5, dtype=np.float32).reshape(1, 1, 1, 2, 2)
+    want_plane = np.array([[1.0, 1.25, 1.75, 2.0], [1.5, 1.75, 2.25, 2.5], [2.5, 2.75, 3.25, 3.5], [3.0, 3.25, 3.75, 4.0]],
+                          np.float32)
+    y = orc.resize_linear_np(x, (2, 4, 4), align_corners=False)
+    assert y.shape == (1, 1, 2, 4, 4)
+    assert np.array_equal(y[0, 0, 0], want_plane) and np.array_equal(y[0, 0, 1], want_plane)
+
+
+def test_trilinear_shape_example_from_reference_docstring():
+    """trilinear.py:217-220: (2,3,4,512,256) -> output_size [4,64,48]."""
+    y = orc.resize_linear_np(np.zeros((2, 3, 4, 32, 16), np.float32), (4, 64, 48), True)
+    assert y.shape == (2, 3, 4, 64, 48)
+
+
+def test_geometry_value_from_reference_main_block():
+    """src/utils/images.py:126 prints get_scales_by_index(3, 0.7937005259840998, 9, 256) == 65."""
+    assert orc.get_scales_by_index(3, 0.7937005259840998, 9, 256) == 65
+
+
+def test_default_pyramid():
+    """SURVEY §8c golden (3): widths / time depths at the argparse defaults (images.py:64-93)."""
+    opt = orc.default_opt()
+    assert opt.stop_scale == 9
+    assert abs(opt.scale_factor - 0.7937005259840998) < 1e-15
+    shapes = [orc.scale_shape(opt, i) for i in range(10)]
+    assert [s[2] for s in shapes] == [33, 41, 51, 65, 81, 102, 129, 162, 204, 257]
+    assert [s[0] for s in shapes] == [4, 4, 4, 5, 5, 5, 7, 7, 7, 13]
+    assert shapes[9] == (13, 192, 257) and shapes[0] == (4, 24, 33)
+
+
+def test_smoke_block_shapes_networks_3d():
+    """networks_3d.py:554-593: ones (8,3,4,2,2), one init_next_stage, sf .75, stop_scale 9, ar 1 ->
+    outputs (8,3,4,26,26) and (8,3,4,2,2)."""
+    opt = orc.default_opt()
+    opt.scale_factor, opt.stop_scale, opt.img_size, opt.ar = 0.75, 9, 256, 1.0
+    opt.stop_scale_time = 9
+    p = orc.to_torch(orc.init_generator_params(opt, 1, seed=0))
+    z = torch.ones(8, opt.latent_dim, 4, 2, 2)
+    x, vae = orc.generator_forward(None, [1.0, 1.0], p, opt, noise_init=z, is_random=False)
+    assert tuple(vae.shape) == (8, 3, 4, 2, 2)
+    assert tuple(x.shape) == (8, 3, 4, 26, 26)
+
+
+# ------------------------------------------------------------------------------------------- oracle self-consistency
+@pytest.mark.parametrize("case", [((4, 24, 33), (4, 30, 41)), ((5, 9, 7), (7, 12, 10)), ((1, 8, 8), (1, 11, 13))])
+def test_resize_matches_aten(case):
+    (ti, hi, wi), size = case
+    x = np.random.default_rng(0).standard_normal((2, 3, ti, hi, wi)).astype(np.float32)
+    ref = F.interpolate(torch.from_numpy(x), size=size, mode="trilinear", align_corners=True).numpy()
+    got = orc.resize_linear_np(x, size, True)
+    assert np.max(np.abs(got - ref)) < 2e-6
+    got_t = orc.resize_linear(torch.from_numpy(x), size, True).numpy()
+    assert np.max(np.abs(got_t - got)) < 1e-6
+
+
+def test_resize_taps_partition_of_unity_and_monotone():
+    for n_in, n_out in [(33, 41), (4, 5), (7, 13), (192, 192), (5, 1), (1, 7)]:
+        i0, i1, l0, l1 = orc.linear_taps(n_in, n_out, True)
+        assert np.all(l0 + l1 == np.float32(1.0)) or np.max(np.abs(l0 + l1 - 1)) < 1e-7
+        assert np.all(i0 >= 0) and np.all(i1 <= n_in - 1) and np.all(np.diff(i0) >= 0)
+        assert i0[0] == 0 and (n_out == 1 or i1[-1] == n_in - 1)
+
+
+def test_resize_backward_is_adjoint():
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((1, 2, 4, 6, 5)).astype(np.float32)
+    gy = rng.standard_normal((1, 2, 5, 8, 7)).astype(np.float32)
+    y = orc.resize_linear_np(x, (5, 8, 7), True)
+    gx = orc.resize_linear_bwd_np(gy, (4, 6, 5), True)
+    assert abs(float((y.astype(np.float64) * gy).sum()) - float((x.astype(np.float64) * gx).sum())) < 1e-4
+    xt = torch.from_numpy(x).requires_grad_(True)
+    orc.resize_linear(xt, (5, 8, 7), True).backward(torch.from_numpy(gy))
+    assert np.max(np.abs(xt.grad.numpy() - gx)) < 1e-5
+
+
+def test_sn_sigma_matches_svd_after_iterations():
+    rng = np.random.default_rng(2)
+    w = torch.from_numpy(rng.standard_normal((64, 3, 3, 3, 3)).astype(np.float32))
+    u = torch.from_numpy(rng.standard_normal((64, 1)).astype(np.float32))
+    v = torch.from_numpy(rng.standard_normal((81, 1)).astype(np.float32))
+    for _ in range(200):
+        sigma, u, v = orc.sn_power_iteration(w, u, v)
+    top = torch.linalg.svdvals(w.reshape(64, -1))[0]
+    assert abs(float(sigma) - float(top)) / float(top) < 1e-3
+
+
+def test_adam_and_clip_reference_formulae():
+    g = np.full(100, 3.0, np.float32)          # ||g|| = 30 > 5 -> scaled to norm 5
+    c = orc.clip_by_norm(g, 5.0)
+    assert abs(np.linalg.norm(c) - 5.0) < 1e-5
+    small = np.full(4, 0.1, np.float32)
+    assert np.allclose(orc.clip_by_norm(small, 5.0), small)
+    w, m, v = orc.adam_step(np.ones(3, np.float32), np.full(3, 0.5, np.float32), np.zeros(3, np.float32),
+                            np.zeros(3, np.float32), 1, 1e-3, 0.5, 0.999)
+    # step 1: m = .25, v = 2.5e-4, lr_t = 1e-3*sqrt(1-.999)/(1-.5)
+    lr_t = 1e-3 * np.sqrt(1 - 0.999) / 0.5
+    assert np.allclose(w, 1 - lr_t * 0.25 / (np.sqrt(2.5e-4) + 1e-8), rtol=1e-6)
+
+
+def test_generator_eval_is_batch_independent():
+    """eval-mode BN => samples are independent: batching must not change results."""
+    opt = orc.default_opt(img_size=64)
+    p = orc.to_torch(orc.randomize_bn_stats(orc.init_generator_params(opt, 2, seed=3), opt=opt))
+    rng = np.random.default_rng(0)
+    t0 = orc.scale_shape(opt, 0)
+    z = torch.from_numpy(rng.standard_normal((2, 128) + t0).astype(np.float32))
+    amps = [1.0, 0.5, 0.25]
+    with torch.no_grad():
+        both, _ = orc.generator_forward(None, amps, p, opt, noise_init=z)
+        one, _ = orc.generator_forward(None, amps, p, opt, noise_init=z[1:2])
+    assert torch.allclose(both[1:2], one, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------- committed golden fixtures
+def test_oracle_matches_committed_golden_fixtures():
+    """tests/golden/*.npz were generated by tests/golden/make_golden.py from this oracle + torch-CPU; they freeze
+    the oracle's behaviour so that a silent change of the checker is caught."""
+    path = os.path.join(GOLDEN, "sample_small.npz")
+    g = np.load(path)
+    opt = orc.default_opt(img_size=int(g["img_size"]))
+    p = orc.to_torch(orc.randomize_bn_stats(orc.init_generator_params(opt, int(g["n_body"]), seed=int(g["seed"])), opt=opt))
+    z = torch.from_numpy(g["z"])
+    noises = {int(k[6:]): torch.from_numpy(g[k]) for k in g.files if k.startswith("noise_")}
+    with torch.no_grad():
+        x, vae = orc.generator_forward(None, list(g["amps"]), p, opt, noise_init=z, is_random=True, noises=noises)
+    assert np.max(np.abs(x.numpy() - g["x"])) < 1e-4
+    assert np.max(np.abs(vae.numpy() - g["vae"])) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------- host mirror + C ABI
+def test_host_geometry_mirror_matches_oracle():
+    from hpvg.utils import images as u
+    for kw in ({}, {"img_size": 64}, {"img_size": 128, "ar": 0.5625}):
+        a, b = orc.default_opt(**kw), u.default_opt(**kw)
+        assert a.stop_scale == b.stop_scale and a.scale_factor == b.scale_factor
+        for i in range(a.stop_scale + 1):
+            assert orc.scale_shape(a, i) == u.scale_shape(b, i)
+            assert orc.scale_shape_2d(a, i) == u.scale_shape_2d(b, i)
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    import hpvg
+    hdr = open(os.path.join(ROOT, "include", "hpvg.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(hpvg_[a-z0-9_]+|Hpvg[A-Za-z0-9]+)\s*\(", hdr))
+    assert len(declared) >= 45
+    for name in sorted(declared):
+        assert hasattr(hpvg.lib, name), "libhpvg.so does not export %s" % name
+    assert hpvg.lib.hpvg_version() >= 100
+
+
+def test_product_path_fails_loudly_without_gpu():
+    import hpvg
+    if hpvg.lib.hpvg_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(hpvg.HpvgError):
+        hpvg.init(0)
+    with pytest.raises(hpvg.HpvgError):
+        hpvg.Tensor((4,), hpvg.F32)
+
+
+@pytest.mark.parametrize("n_in,n_out", [(33, 41), (24, 30), (4, 5), (5, 7), (7, 13), (204, 257), (153, 192), (1, 4),
+                                        (6, 1), (257, 257)])
+@pytest.mark.parametrize("align", [True, False])
+def test_resize_tables_bit_exact_host(n_in, n_out, align):
+    """The bit-exact contract (north_star): indices and fp32 weights identical to the reference rule."""
+    import hpvg
+    i0, i1, l0, l1 = hpvg.ops.linear_taps(n_in, n_out, align)
+    r0, r1, m0, m1 = orc.linear_taps(n_in, n_out, align)
+    assert np.array_equal(i0, r0) and np.array_equal(i1, r1)
+    assert np.array_equal(l0.view(np.uint32), m0.view(np.uint32))
+    assert np.array_equal(l1.view(np.uint32), m1.view(np.uint32))
+
+
+def test_c_abi_argument_errors():
+    import ctypes
+    import hpvg
+    i0 = (ctypes.c_int32 * 4)()
+    f0 = (ctypes.c_float * 4)()
+    assert hpvg.lib.hpvg_linear_taps(0, 4, 1, i0, i0, f0, f0) == -2          # HPVG_E_ARG
+    assert b"positive" in hpvg.lib.hpvg_last_error()
+    assert hpvg.lib.hpvg_conv_wimg_bytes(0) == 2 * 27 * 32 * 128
+    assert hpvg.lib.hpvg_conv_wimg_bytes(99) == 0

@@ -1,0 +1,128 @@
+"""End-to-end parity of the sampling path (eval_video.py:53-82 semantics) against the CPU oracle and the committed
+golden fixture, plus layer-by-layer activation parity.  Tolerance (north_star): rel-L2 <= 1e-2 at bf16."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hpvg_oracle as orc
+from util import rel_l2
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-2
+
+
+def _build(hp, opt_kw, n_body, seed):
+    from hpvg import networks_3d as n3
+    from hpvg.utils import images as uimg
+    opt = uimg.default_opt(**opt_kw)
+    oopt = orc.default_opt(**opt_kw)
+    params = orc.randomize_bn_stats(orc.init_generator_params(oopt, n_body, seed=seed), opt=oopt)
+    net = n3.GeneratorHPVAEGAN(opt)
+    for _ in range(n_body):
+        net.init_next_stage()
+    net.load_parameters(params)
+    return net, opt, oopt, params
+
+
+def test_sample_matches_golden_fixture(hpvg_gpu):
+    hp = hpvg_gpu
+    g = np.load(os.path.join(GOLDEN, "sample_small.npz"))
+    net, opt, oopt, params = _build(hp, {"img_size": int(g["img_size"])}, int(g["n_body"]), int(g["seed"]))
+    noises = {int(k[6:]): hp.from_numpy(g[k]) for k in g.files if k.startswith("noise_")}
+    z = hp.from_numpy(g["z"])
+    x, vae = net(z, list(g["amps"]), noise_init=z, isRandom=True, noises=noises)
+    e_vae, e_x = rel_l2(vae.numpy(), g["vae"]), rel_l2(x.numpy(), g["x"])
+    assert e_vae < TOL, "vae_out rel-L2 %.3e" % e_vae
+    assert e_x < TOL, "sample rel-L2 %.3e" % e_x
+
+
+def test_sample_default_pyramid_first_scales_vs_oracle(hpvg_gpu):
+    """Default config (img_size 256): scales 0..3, reconstruction mode and random mode, batch 2."""
+    hp = hpvg_gpu
+    net, opt, oopt, params = _build(hp, {}, 3, seed=21)
+    rng = np.random.default_rng(7)
+    z = rng.standard_normal((2, 128) + orc.scale_shape(oopt, 0)).astype(np.float32)
+    amps = [1.0, 0.7, 0.5, 0.3]
+    noises = {3: rng.standard_normal((2, 3) + orc.scale_shape(oopt, 3)).astype(np.float32)}
+    pt = orc.to_torch(params)
+    with torch.no_grad():
+        rx, rv = orc.generator_forward(None, amps, pt, oopt, noise_init=torch.from_numpy(z), is_random=True,
+                                       noises={k: torch.from_numpy(v) for k, v in noises.items()})
+        rx2, _ = orc.generator_forward(None, amps, pt, oopt, noise_init=torch.from_numpy(z), is_random=False)
+    tz = hp.from_numpy(z)
+    x, vae = net(tz, amps, noise_init=tz, isRandom=True, noises={k: hp.from_numpy(v) for k, v in noises.items()})
+    assert tuple(x.shape) == tuple(rx.shape)
+    assert rel_l2(vae.numpy(), rv.numpy()) < TOL
+    assert rel_l2(x.numpy(), rx.numpy()) < TOL
+    x2, _ = net(tz, amps, noise_init=tz, isRandom=False)
+    assert rel_l2(x2.numpy(), rx2.numpy()) < TOL
+
+
+def test_smoke_block_shapes(hpvg_gpu):
+    """networks_3d.py:554-593: ones (8,128->3,4,2,2) -> (8,3,4,26,26) / (8,3,4,2,2)."""
+    hp = hpvg_gpu
+    from hpvg import networks_3d as n3
+    from hpvg.utils import images as uimg
+    opt = uimg.default_opt()
+    opt.scale_factor, opt.stop_scale, opt.img_size, opt.ar, opt.stop_scale_time = 0.75, 9, 256, 1.0, 9
+    net = n3.GeneratorHPVAEGAN(opt)
+    net.init_next_stage()
+    z = hp.from_numpy(np.ones((8, 128, 4, 2, 2), np.float32))
+    x, vae = net(z, [1.0, 1.0], noise_init=z, isRandom=False)
+    assert x.shape == (8, 3, 4, 26, 26) and vae.shape == (8, 3, 4, 2, 2)
+    assert np.all(np.isfinite(x.numpy()))
+
+
+def test_parameter_names_follow_reference_checkpoint_contract(hpvg_gpu):
+    """src/tools/pt2ms.py:129-188."""
+    from hpvg import networks_3d as n3
+    from hpvg.utils import images as uimg
+    opt = uimg.default_opt()
+    net = n3.GeneratorHPVAEGAN(opt)
+    net.init_next_stage()
+    net.init_next_stage()
+    names = set(net.parameters_dict())
+    want = set(orc.init_generator_params(orc.default_opt(), 2))
+    assert names == want, (sorted(names - want)[:5], sorted(want - names)[:5])
+    d = n3.WDiscriminator3D(opt)
+    assert set(d.parameters_dict()) == set(orc.init_discriminator_params(orc.default_opt()))
+
+
+def test_discriminator_forward_and_sn_state(hpvg_gpu):
+    hp = hpvg_gpu
+    from hpvg import networks_3d as n3
+    from hpvg.utils import images as uimg
+    opt = uimg.default_opt()
+    oopt = orc.default_opt()
+    params = orc.init_discriminator_params(oopt, seed=4)
+    rng = np.random.default_rng(0)
+    for k in params:
+        if k.endswith("bias"):
+            params[k] = (rng.standard_normal(params[k].shape) * 0.05).astype(np.float32)
+    d = n3.WDiscriminator3D(opt)
+    d.load_parameters(params)
+    x = rng.standard_normal((1, 3, 5, 48, 65)).astype(np.float32)
+    pt = orc.to_torch(params)
+    for _ in range(2):    # Q5: the power iteration state advances on every forward
+        with torch.no_grad():
+            ref = orc.discriminator(torch.from_numpy(x), pt, oopt).numpy()
+        out = d(hp.from_numpy(x)).numpy()
+        assert out.shape == ref.shape == (1, 1, 5, 48, 65)
+        assert rel_l2(out, ref) < TOL
+    got = d.parameters_dict()
+    assert np.allclose(got["head.0.weight_u"].numpy(), pt["head.0.weight_u"].numpy(), atol=1e-4)
+
+
+def test_encoder_forward(hpvg_gpu):
+    hp = hpvg_gpu
+    net, opt, oopt, params = _build(hp, {}, 0, seed=8)
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((1, 3) + orc.scale_shape(oopt, 0)).astype(np.float32)
+    pt = orc.to_torch(params)
+    with torch.no_grad():
+        rmu, rlv = orc.encode(torch.from_numpy(x), pt, oopt)
+    mu, lv = net.encode(hp.from_numpy(x))
+    assert rel_l2(mu.numpy(), rmu.numpy()) < TOL and rel_l2(lv.numpy(), rlv.numpy()) < TOL

@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Time the tcgen05 conv kernel variants with CUDA events on their own stream (development tool)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "mindspore-hp-vae-gan_b200"))
+import hpvg  # noqa: E402
+from hpvg import ops  # noqa: E402
+
+hpvg.init(0)
+st = hpvg.Stream()
+rng = np.random.default_rng(0)
+
+
+def bench(mode_name, cin, cout, shape, iters=10):
+    N, T, H, W = shape
+    cpad = 8 if cin <= 8 else cin
+    x_cl = hpvg.Tensor((N, T, H, W, cpad), hpvg.BF16).zero_()
+    w = hpvg.from_numpy((rng.standard_normal((cout, cin, 3, 3, 3)) * 0.05).astype(np.float32))
+    aff = ops.affine_from_bias(hpvg.from_numpy(np.zeros(max(cout, 1), np.float32)))
+    mode = ops.conv_mode_for(cin, cout)
+    wi = ops.pack_weights(w, mode)
+    if cout <= 4:
+        out = hpvg.Tensor((N, cout, T, H, W), hpvg.F32)
+        run = lambda: ops.conv_cl(mode, x_cl, wi, aff, aff.view((64,), hpvg.F32, 256), ops.ACT_TANH, ops.OUT_F32_NCDHW,
+                                  out=out, cout_real=cout, stream=st)
+    else:
+        out = hpvg.Tensor((N, T, H, W, 64), hpvg.BF16)
+        run = lambda: ops.conv_cl(mode, x_cl, wi, aff, aff.view((64,), hpvg.F32, 256), ops.ACT_LRELU, ops.OUT_BF16_CL,
+                                  out=out, stream=st)
+    for _ in range(3):
+        run()
+    st.sync()
+    e0, e1 = hpvg.Event(), hpvg.Event()
+    e0.record(st)
+    for _ in range(iters):
+        run()
+    e1.record(st)
+    e1.sync()
+    ms = e0.elapsed_ms(e1) / iters
+    vox = N * T * H * W
+    flops = 2.0 * 27 * cin * cout * vox
+    print("%-10s %-22s %8.3f ms  %8.1f TFLOP/s (algorithmic)  %6.2f ns/voxel" %
+          (mode_name, shape, ms, flops / ms / 1e9, ms * 1e6 / vox), flush=True)
+
+
+for shape in [(1, 13, 192, 257), (1, 16, 192, 257), (4, 13, 192, 257), (8, 13, 192, 257), (1, 7, 153, 204),
+              (16, 4, 24, 33), (64, 4, 24, 33)]:
+    bench("64->64", 64, 64, shape)
+for shape in [(1, 13, 192, 257), (8, 13, 192, 257)]:
+    bench("64->3", 64, 3, shape)
+    bench("3->64", 3, 64, shape)
