@@ -249,7 +249,11 @@ def run_ours(args):
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peaks_kind,
                 "launches_timed": len(prof), "avg_launch_ms": kms / max(len(prof), 1),
-                "share_of_step": kms / ms_dev, "traffic": None}
+                "share_of_step": kms / ms_dev,
+                # dram__bytes_read+write per launch from the committed ncu capture (profiles/r1_conv64_ncu_full_summary.csv:
+                # 609 MB for 4 x 641472 voxels = 237 B/voxel; algorithmic = 2 x 128 B/voxel), scaled to this run's launches
+                "traffic": 237.3 * (sum(v for v, _ in prof) / max(len(prof), 1)),
+                "traffic_unit": "bytes per launch (mean over timed launches)"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
