@@ -151,6 +151,39 @@ int hpvg_adam_clip_multi(int n_tensors, float* const* d_params, const float* con
                          float* const* d_v, const long long* sizes, const float* lrs, float beta1, float beta2,
                          float eps, int step, float clip_norm /* <=0: no clipping */, void* stream);
 
+/* ---------------------------------------------------------------- backward (hand-restated MindSpore autodiff)
+ * Data gradient of a conv = hpvg_conv_cl with a filter bank packed with transpose_flip = 1.
+ * Weight gradient: dW[(co_off+co)][(ci_off+ci)][tap] (+)= scale * sum_v gy[v][co] * x[v+tap][ci] for the 64x64 channel
+ * block starting at d_x / d_gy (bf16 cl, >= 64 channels per voxel; skinny layers are zero-padded to 64 and cropped
+ * with co_n / ci_n).  d_dw: fp32 (Cout, w_cin, kt, 3, 3). */
+int hpvg_conv_wgrad_cl(const void* d_x, int x_pitch, const void* d_gy, int gy_pitch, int N, int T, int H, int W,
+                       float* d_dw, int w_cin, int kt, int co_off, int co_n, int ci_off, int ci_n, int accumulate,
+                       float scale, void* stream);
+/* gz = ga * LeakyReLU'(a), a = stored activation (bf16 cl, elems % 8 == 0) */
+int hpvg_lrelu_bwd_cl(const void* d_ga, const void* d_a, long long elems, void* d_gz, void* stream);
+/* BatchNorm(train)+act backward on (voxels, 64) bf16: d_saved = (scale, shift, mean, invstd) from the forward
+ * (hpvg_bn_finalize); writes gy and (optionally accumulating) dgamma / dbeta. */
+int hpvg_bn_bwd_cl(const void* d_ga, const void* d_y, long long voxels, const float* d_saved, int act, void* d_gy,
+                   float* d_dgamma, float* d_dbeta, int accumulate, void* stream);
+/* out[c] (+)= sum_v g[v][c]  (bias gradient), (voxels, 64) bf16 */
+int hpvg_colsum_cl(const void* d_g, long long voxels, float* d_out, int accumulate, void* stream);
+/* g (+)= coef*(out - target)  (nn.MSELoss gradient with coef = weight*2/n) */
+int hpvg_mse_grad(const float* d_out, const float* d_target, long long n, float coef, int accumulate, float* d_g,
+                  void* stream);
+int hpvg_tanh_bwd(const float* d_g, const float* d_out, long long n, float* d_gpre, void* stream);
+int hpvg_axpby(float a, const float* d_x, float b, float* d_y, long long n, void* stream); /* y = a*x + b*y */
+int hpvg_fill(float* d_y, float value, long long n, void* stream);
+int hpvg_channel_sum(const float* d_g, int N, int C, long long spatial, int accumulate, float* d_out, void* stream);
+int hpvg_kl_grad(const float* d_mu, const float* d_logvar, long long n, float coef, float* d_gmu, float* d_glogvar,
+                 void* stream);
+/* spectral-norm chain rule with u, v held constant: gW (+)= (G - <G, W/sigma> u v^T)/sigma */
+int hpvg_sn_grad(const float* d_G, const float* d_w, const float* d_u, const float* d_v, const float* d_sigma,
+                 int cout, int k, int accumulate, float* d_gw, void* stream);
+/* WGAN-GP pieces (src/modules/losses.py:47-52) */
+int hpvg_lerp(const float* d_a, const float* d_b, float alpha, long long n, float* d_out, void* stream);
+int hpvg_gp_grad(const float* d_g, int N, int C, long long spatial, float lambda, float* d_G, float* d_gp,
+                 void* stream);
+
 /* ---------------------------------------------------------------- MindSpore ops.Custom(func_type="aot") entry points
  * int Name(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes, void* stream, void* extra)
  * params = device pointers, inputs then outputs, pre-allocated by the framework. */

@@ -18,6 +18,8 @@ namespace {
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 float* g_adam_norms = nullptr;
+float* g_wgrad_ws = nullptr;   // [sm/3][27][64][64] partial weight gradients
+double* g_sums = nullptr;      // [128] reduction scratch (BatchNorm backward, column sums)
 int g_sm_count = 0;
 
 int fail(int code, const std::string& msg) {
@@ -65,6 +67,8 @@ int hpvg_init(int device) {
   if (prop.major != 10) return fail(HPVG_E_UNSUPPORTED, "libhpvg needs an sm_100a (B200) device");
   g_sm_count = prop.multiProcessorCount;
   if (!g_adam_norms) CU(cudaMalloc(&g_adam_norms, hpvg::ADAM_MAX_TENSORS * sizeof(float)));
+  if (!g_wgrad_ws) CU(cudaMalloc(&g_wgrad_ws, hpvg::conv3d_wgrad_workspace_bytes(g_sm_count)));
+  if (!g_sums) CU(cudaMalloc(&g_sums, 128 * sizeof(double)));
   return HPVG_OK;
 }
 int hpvg_sm_count(void) { return g_sm_count; }
@@ -338,6 +342,90 @@ int hpvg_adam_clip_multi(int n_tensors, float* const* params, const float* const
     }
     KL(hpvg::ew_adam_clip(tab, cnt, g_adam_norms, beta1, beta2, eps, bc, clip, S(st)), clip > 0.f ? 2 : 1);
   }
+  return HPVG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+int hpvg_conv_wgrad_cl(const void* x, int x_pitch, const void* gy, int gy_pitch, int N, int T, int H, int W,
+                       float* dw, int w_cin, int kt, int co_off, int co_n, int ci_off, int ci_n, int accumulate,
+                       float scale, void* st) {
+  if (N <= 0 || T <= 0 || H <= 0 || W <= 0) return HPVG_OK;
+  if (!g_wgrad_ws) return fail(HPVG_E_ARG, "hpvg_init was not called");
+  if ((x_pitch & 7) || (gy_pitch & 7) || x_pitch < 64 || gy_pitch < 64)
+    return fail(HPVG_E_ARG, "conv_wgrad_cl: operands must be >= 64-channel bf16 channels-last tensors");
+  if (co_n < 1 || co_n > 64 || ci_n < 1 || ci_n > 64 || (kt != 1 && kt != 3))
+    return fail(HPVG_E_ARG, "conv_wgrad_cl: bad block extents");
+  const char* e = hpvg::conv3d_wgrad_launch(x, x_pitch, gy, gy_pitch, N, T, H, W, dw, w_cin, kt, co_off, co_n, ci_off,
+                                            ci_n, accumulate, scale, g_wgrad_ws, g_sm_count, S(st));
+  if (e) return fail(HPVG_E_CUDA, std::string("conv_wgrad_cl: ") + e);
+  g_launches += 2;
+  return HPVG_OK;
+}
+int hpvg_lrelu_bwd_cl(const void* ga, const void* a, long long elems, void* gz, void* st) {
+  if (elems <= 0) return HPVG_OK;
+  if (elems & 7) return fail(HPVG_E_ARG, "lrelu_bwd_cl: element count must be a multiple of 8");
+  KL(hpvg::ew_lrelu_bwd_cl(static_cast<const __nv_bfloat16*>(ga), static_cast<const __nv_bfloat16*>(a), elems,
+                           static_cast<__nv_bfloat16*>(gz), S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_bn_bwd_cl(const void* ga, const void* y, long long voxels, const float* saved, int act, void* gy,
+                   float* dgamma, float* dbeta, int accumulate, void* st) {
+  if (voxels <= 0) return fail(HPVG_E_ARG, "bn_bwd: empty batch");
+  if (!g_sums) return fail(HPVG_E_ARG, "hpvg_init was not called");
+  KL(hpvg::ew_bn_bwd_cl(static_cast<const __nv_bfloat16*>(ga), static_cast<const __nv_bfloat16*>(y), voxels, saved,
+                        act, g_sums, static_cast<__nv_bfloat16*>(gy), dgamma, dbeta, accumulate, S(st)), 4);
+  return HPVG_OK;
+}
+int hpvg_colsum_cl(const void* g, long long voxels, float* out, int accumulate, void* st) {
+  if (voxels <= 0) return fail(HPVG_E_ARG, "colsum: empty input");
+  if (!g_sums) return fail(HPVG_E_ARG, "hpvg_init was not called");
+  KL(hpvg::ew_colsum_cl(static_cast<const __nv_bfloat16*>(g), voxels, g_sums, out, accumulate, S(st)), 2);
+  return HPVG_OK;
+}
+int hpvg_mse_grad(const float* out, const float* target, long long n, float coef, int accumulate, float* g, void* st) {
+  if (n <= 0) return HPVG_OK;
+  KL(hpvg::ew_diff_scale(out, target, n, coef, accumulate, g, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_tanh_bwd(const float* g, const float* out, long long n, float* gpre, void* st) {
+  if (n <= 0) return HPVG_OK;
+  KL(hpvg::ew_tanh_bwd(g, out, n, gpre, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_axpby(float a, const float* x, float b, float* y, long long n, void* st) {
+  if (n <= 0) return HPVG_OK;
+  KL(hpvg::ew_axpby(a, x, b, y, n, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_fill(float* y, float v, long long n, void* st) {
+  if (n <= 0) return HPVG_OK;
+  KL(hpvg::ew_fill(y, v, n, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_channel_sum(const float* g, int N, int C, long long sp, int accumulate, float* out, void* st) {
+  if (N <= 0 || C <= 0 || sp <= 0) return fail(HPVG_E_ARG, "channel_sum: empty input");
+  KL(hpvg::ew_channel_sum_ncdhw(g, N, C, sp, accumulate, out, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_kl_grad(const float* mu, const float* lv, long long n, float coef, float* gmu, float* glv, void* st) {
+  if (n <= 0) return HPVG_OK;
+  KL(hpvg::ew_kl_grad(mu, lv, n, coef, gmu, glv, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_sn_grad(const float* G, const float* w, const float* u, const float* v, const float* sigma, int cout, int k,
+                 int accumulate, float* gw, void* st) {
+  if (cout <= 0 || k <= 0) return fail(HPVG_E_ARG, "sn_grad: empty matrix");
+  KL(hpvg::ew_sn_grad(G, w, u, v, sigma, cout, k, accumulate, gw, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_lerp(const float* a, const float* b, float alpha, long long n, float* out, void* st) {
+  if (n <= 0) return HPVG_OK;
+  KL(hpvg::ew_lerp(a, b, alpha, n, out, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_gp_grad(const float* g, int N, int C, long long sp, float lambda, float* Gout, float* gp, void* st) {
+  if (N <= 0 || C <= 0 || sp <= 0) return fail(HPVG_E_ARG, "gp_grad: empty input");
+  KL(hpvg::ew_gp_grad(g, N, C, sp, lambda, Gout, gp, S(st)), 1);
   return HPVG_OK;
 }
 

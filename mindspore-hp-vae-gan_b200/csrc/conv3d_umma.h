@@ -48,4 +48,10 @@ int conv3d_umma_wimg_bytes(int mode);
 const char* conv3d_pack_weights(const float* w, int w_cout, int w_cin, int kt, int mode, int transpose_flip,
                                 int cout_off, int cout, int cin_off, int cin, void* img, cudaStream_t stream);
 
+// weight gradient (conv3d_wgrad.cu)
+size_t conv3d_wgrad_workspace_bytes(int sm_count);
+const char* conv3d_wgrad_launch(const void* x, int x_pitch, const void* gy, int gy_pitch, int N, int T, int H, int W,
+                                float* dw, int w_cin, int kt, int co_off, int co_n, int ci_off, int ci_n, int accumulate,
+                                float scale, float* workspace, int sm_count, cudaStream_t stream);
+
 }  // namespace hpvg

@@ -1,0 +1,280 @@
+// Weight gradient of the 3x3x3 / stride 1 / pad 1 convolution on tcgen05 (sm_100a), 64 -> 64 channel blocks:
+//     dW[co][ci][dt][dh][dw] = sum_v gy[v][co] * x[v + (dt-1, dh-1, dw-1)][ci]
+// (what MindSpore autodiff produces for nn.Conv3d's weight, reference networks_3d.py:48-50 under
+// TrainOneStepCell, train_video.py:110-113; the same kernel serves the WGAN-GP double-backward).
+//
+// GEMM view per tap: D[ci][co] += X_tap^T[ci][k] * GY[k][co] with K = voxels.  Both operands are read straight
+// from the channels-last bf16 tensors as MN-major / 128B-swizzled UMMA operands: one voxel = one 128-byte row =
+// 64 channels, K runs over 16 consecutive voxels of an image row.  The tap shift is a shifted start address of
+// the SAME x tile (rows +dh, voxels +dw); two dh taps are stacked into one M=128 MMA through the descriptor's
+// leading-dimension offset (second 64-channel block = the x row below), the third uses an M=64 MMA.
+//
+// Work split: CTA c handles temporal tap dt = c % 3 (its 9 taps = 6 TMEM accumulators, 384 columns, live for the
+// whole kernel) and every (c/3 + i*G)-th tile (4 image rows x 64 voxels of gy, haloed 6 x 66 tile of x).
+// No masking is needed anywhere: TMA zero-fills out-of-bounds x (the conv padding) and out-of-bounds gy.
+// Partials [G][27][ci][co] are reduced (fixed order -> deterministic) and transposed by a second kernel.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "conv3d_umma.h"
+#include "ptx.cuh"
+
+namespace hpvg {
+
+namespace {
+
+constexpr int WG_NH = 4;                 // gy rows per tile
+constexpr int WG_WS = 64;                // gy voxels per row per tile
+constexpr int WG_XP = WG_WS + 2;         // x row pitch (voxels)
+constexpr int WG_X_BYTES = (WG_NH + 2) * WG_XP * 128;   // 50688
+constexpr int WG_X_STRIDE = 51200;                      // 1024-aligned
+constexpr int WG_GY_BYTES = WG_NH * WG_WS * 128;        // 32768
+constexpr int WG_STAGE = WG_X_STRIDE + WG_GY_BYTES;     // 83968
+constexpr int WG_STAGES = 2;
+constexpr int WG_THREADS = 192;
+constexpr int WG_SMEM = 1024 + WG_STAGES * WG_STAGE + 64;
+
+struct WgradParams {
+  int N, T, H, W;
+  int h_blocks, w_segs, n_tiles, groups;
+  float* partial;   // [groups][27][64 ci][64 co]
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_gy,
+                    const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t base_u32 = smem_u32(smem_dyn);
+  uint8_t* sm = smem_dyn + (((base_u32 + 1023u) & ~1023u) - base_u32);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + WG_STAGES * WG_STAGE);
+  uint64_t* full = bars;               // [2]
+  uint64_t* empty = bars + WG_STAGES;  // [2]
+  uint64_t* done = empty + WG_STAGES;  // [1]
+  uint32_t* tmem_ptr_sm = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dt = blockIdx.x % 3;
+  const int g = blockIdx.x / 3;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < WG_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_sm, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_sm;
+
+  const int per_plane = p.h_blocks * p.w_segs;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmap_x);
+      tma_prefetch_desc(&tmap_gy);
+      uint32_t j = 0;
+      for (int tile = g; tile < p.n_tiles; tile += p.groups) {
+        const int nt = tile / per_plane, rem = tile - nt * per_plane;
+        const int n = nt / p.T, t = nt - n * p.T;
+        const int t_in = t + dt - 1;
+        if (t_in < 0 || t_in >= p.T) continue;
+        const int hb = rem / p.w_segs, ws = rem - hb * p.w_segs;
+        const int h0 = hb * WG_NH, w0 = ws * WG_WS;
+        const uint32_t s = j % WG_STAGES, ph = (j / WG_STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_expect_tx(&full[s], WG_X_BYTES + WG_GY_BYTES);
+        uint8_t* st = sm + s * WG_STAGE;
+        tma_load_5d(st, &tmap_x, &full[s], 0, w0 - 1, h0 - 1, t_in, n);
+        tma_load_5d(st + WG_X_STRIDE, &tmap_gy, &full[s], 0, w0, h0, t, n);
+        ++j;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc128 = make_idesc_bf16(128, 64, 1, 1);
+      const uint32_t idesc64 = make_idesc_bf16(64, 64, 1, 1);
+      uint32_t j = 0;
+      uint32_t accum = 0;
+      for (int tile = g; tile < p.n_tiles; tile += p.groups) {
+        const int nt = tile / per_plane;
+        const int t = nt % p.T;
+        const int t_in = t + dt - 1;
+        if (t_in < 0 || t_in >= p.T) continue;
+        const uint32_t s = j % WG_STAGES, ph = (j / WG_STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t xs = smem_u32(sm + s * WG_STAGE);
+        const uint32_t gs = xs + WG_X_STRIDE;
+#pragma unroll 1
+        for (int hh = 0; hh < WG_NH; ++hh) {
+#pragma unroll
+          for (int ks = 0; ks < WG_WS / 16; ++ks) {
+            const uint64_t bd = make_smem_desc(gs + (hh * WG_WS + ks * 16) * 128, 16, 1024, 2);
+#pragma unroll
+            for (int dw = 0; dw < 3; ++dw) {
+              const uint32_t a0 = xs + ((hh * WG_XP) + ks * 16 + dw) * 128;
+              // dh = 0 and dh = 1 stacked along M: second 64-channel block = same voxels one x row below
+              umma_bf16(tmem_base + (dw * 2) * 64, make_smem_desc(a0, WG_XP * 128, 1024, 2), bd, idesc128, accum);
+              // dh = 2
+              umma_bf16(tmem_base + (dw * 2 + 1) * 64, make_smem_desc(a0 + 2 * WG_XP * 128, WG_XP * 128, 1024, 2),
+                        bd, idesc64, accum);
+            }
+            accum = 1;
+          }
+        }
+        umma_commit(&empty[s]);
+        ++j;
+      }
+      umma_commit(done);
+      // no tile at all for this CTA (tiny inputs): accumulators were never written -> flag through `accum`
+      if (accum == 0) *tmem_ptr_sm = 0xFFFFFFFFu;
+    }
+    __syncwarp();
+  }
+  // ---------------------------------------------------------------- readout: TMEM -> partial[g][tap][ci][co]
+  mbar_wait(done, 0);
+  tc_fence_after();
+  __syncthreads();
+  const bool empty_cta = (*tmem_ptr_sm == 0xFFFFFFFFu);
+  if (warp >= 2) {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;   // TMEM lane
+    float* pg = p.partial + static_cast<size_t>(g) * 27 * 4096;
+#pragma unroll 1
+    for (int dw = 0; dw < 3; ++dw) {
+#pragma unroll 1
+      for (int which = 0; which < 2; ++which) {
+        // which 0: M=128 tile: lanes 0..63 -> dh 0, lanes 64..127 -> dh 1 ; which 1: M=64 tile: dh 2, lane (i/16)*32+i%16
+        int dh, ci;
+        bool valid = true;
+        if (which == 0) {
+          dh = row >> 6;
+          ci = row & 63;
+        } else {
+          dh = 2;
+          valid = (row & 31) < 16;
+          ci = (row >> 5) * 16 + (row & 15);
+        }
+        const int tap = dt * 9 + dh * 3 + dw;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (dw * 2 + which) * 64;
+        uint32_t r0[32], r1[32];
+        if (!empty_cta) {
+          tmem_ld32(taddr, r0);
+          tmem_ld32(taddr + 32, r1);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r0[i] = r1[i] = 0u;
+        }
+        if (valid) {
+          float4* dst = reinterpret_cast<float4*>(pg + (static_cast<size_t>(tap) * 64 + ci) * 64);
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            dst[c] = make_float4(__uint_as_float(r0[4 * c]), __uint_as_float(r0[4 * c + 1]),
+                                 __uint_as_float(r0[4 * c + 2]), __uint_as_float(r0[4 * c + 3]));
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            dst[8 + c] = make_float4(__uint_as_float(r1[4 * c]), __uint_as_float(r1[4 * c + 1]),
+                                     __uint_as_float(r1[4 * c + 2]), __uint_as_float(r1[4 * c + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// dW[(co+co_off)][(ci+ci_off)][tap] (+)= sum_g partial[g][tap][ci][co]    (tap stride = 1; layout (Cout, Cin, kt,3,3))
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int groups, float* __restrict__ dw, int w_cin,
+                                    int kt, int co_off, int co_n, int ci_off, int ci_n, int accumulate, float scale) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over 27*64*64, co fastest (coalesced partial reads)
+  if (idx >= 27 * 4096) return;
+  const int co = idx & 63, ci = (idx >> 6) & 63, tap = idx >> 12;
+  if (co >= co_n || ci >= ci_n) return;   // zero-padded channels of skinny layers
+  float acc = 0.f;
+  for (int gg = 0; gg < groups; ++gg) acc += partial[static_cast<size_t>(gg) * 27 * 4096 + idx];
+  int tap_o = tap;
+  if (kt == 1) {
+    if (tap / 9 != 1) return;   // 2-D filter: only the centre temporal tap exists
+    tap_o = tap - 9;
+  }
+  const size_t o = (static_cast<size_t>(co + co_off) * w_cin + (ci + ci_off)) * (9 * kt) + tap_o;
+  dw[o] = (accumulate ? dw[o] : 0.f) + acc * scale;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn wg_get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+bool make_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, int pitch, int N, int T, int H, int W, int bw,
+              int bh) {
+  cuuint64_t gd[5] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)N};
+  const cuuint64_t vox = static_cast<cuuint64_t>(pitch) * 2;
+  cuuint64_t gs[4] = {vox, vox * W, vox * W * H, vox * W * H * T};
+  cuuint32_t bx[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gd, gs, bx, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+size_t conv3d_wgrad_workspace_bytes(int sm_count) {
+  const int groups = sm_count / 3;
+  return static_cast<size_t>(groups) * 27 * 4096 * sizeof(float);
+}
+
+// x: bf16 cl (N,T,H,W,x_pitch) [64 channels starting at x], gy: bf16 cl (N,T,H,W,gy_pitch) [64 channels at gy]
+// dw: fp32 (w_cout, w_cin, kt, 3, 3); the 64x64 block at (co_off, ci_off) is written (or accumulated into).
+const char* conv3d_wgrad_launch(const void* x, int x_pitch, const void* gy, int gy_pitch, int N, int T, int H, int W,
+                                float* dw, int w_cin, int kt, int co_off, int co_n, int ci_off, int ci_n, int accumulate,
+                                float scale, float* workspace, int sm_count, cudaStream_t stream) {
+  EncodeTiledFn enc = wg_get_encode();
+  if (!enc) return "cuTensorMapEncodeTiled entry point not available";
+  CUtensorMap mx, mg;
+  if (!make_map(enc, &mx, x, x_pitch, N, T, H, W, WG_XP, WG_NH + 2)) return "tensor map (x) failed";
+  if (!make_map(enc, &mg, gy, gy_pitch, N, T, H, W, WG_WS, WG_NH)) return "tensor map (gy) failed";
+  WgradParams p;
+  p.N = N; p.T = T; p.H = H; p.W = W;
+  p.h_blocks = (H + WG_NH - 1) / WG_NH;
+  p.w_segs = (W + WG_WS - 1) / WG_WS;
+  p.n_tiles = N * T * p.h_blocks * p.w_segs;
+  int groups = sm_count / 3;
+  if (groups > p.n_tiles) groups = p.n_tiles;
+  if (groups < 1) groups = 1;
+  p.groups = groups;
+  p.partial = workspace;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv3d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    configured = true;
+  }
+  conv3d_wgrad_kernel<<<3 * groups, WG_THREADS, WG_SMEM, stream>>>(mx, mg, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cudaGetErrorString(e);
+  wgrad_reduce_kernel<<<(27 * 4096 + 255) / 256, 256, 0, stream>>>(workspace, groups, dw, w_cin, kt, co_off, co_n,
+                                                                  ci_off, ci_n, accumulate, scale);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+}  // namespace hpvg

@@ -518,6 +518,230 @@ __global__ void adam_apply_kernel(const AdamTable tab, const float* __restrict__
   }
 }
 
+// ----------------------------------------------------------------------------------------------- backward pieces
+// gz = ga * lrelu'(a)  (a = the stored activation; sign(a) == sign(pre-activation))          bf16 cl, any width
+__global__ void lrelu_bwd_cl_kernel(const __nv_bfloat16* __restrict__ ga, const __nv_bfloat16* __restrict__ a,
+                                    long long groups, __nv_bfloat16* __restrict__ gz) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < groups;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 g4 = *reinterpret_cast<const uint4*>(ga + i * 8);
+    const uint4 a4 = *reinterpret_cast<const uint4*>(a + i * 8);
+    const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, aw[4] = {a4.x, a4.y, a4.z, a4.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 g = unpack2(gw[e]);
+      const float2 av = unpack2(aw[e]);
+      g.x = av.x > 0.f ? g.x : 0.2f * g.x;
+      g.y = av.y > 0.f ? g.y : 0.2f * g.y;
+      o[e] = pack2(g.x, g.y);
+    }
+    *reinterpret_cast<uint4*>(gz + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// BatchNorm(train)+LeakyReLU backward, pass 1: sums[0][c] = sum gz, sums[1][c] = sum gz*xhat
+//   z = y*scale+shift (mask), xhat = (y-mean)*invstd, gz = ga*lrelu'(z)
+__global__ void bn_bwd_reduce_cl_kernel(const __nv_bfloat16* __restrict__ ga, const __nv_bfloat16* __restrict__ y,
+                                        long long voxels, const float* __restrict__ saved /*[4][64]*/, int act,
+                                        double* __restrict__ sums) {
+  const int g = threadIdx.x & 7, vl = threadIdx.x >> 3;
+  float sc[8], sh[8], mu[8], is[8], s0[8], s1[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    sc[e] = saved[g * 8 + e];
+    sh[e] = saved[64 + g * 8 + e];
+    mu[e] = saved[128 + g * 8 + e];
+    is[e] = saved[192 + g * 8 + e];
+    s0[e] = s1[e] = 0.f;
+  }
+  for (long long v = static_cast<long long>(blockIdx.x) * 32 + vl; v < voxels;
+       v += static_cast<long long>(gridDim.x) * 32) {
+    const uint4 g4 = *reinterpret_cast<const uint4*>(ga + v * 64 + g * 8);
+    const uint4 y4 = *reinterpret_cast<const uint4*>(y + v * 64 + g * 8);
+    const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, yw[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+    for (int e2 = 0; e2 < 4; ++e2) {
+      const float2 gg = unpack2(gw[e2]), yy = unpack2(yw[e2]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int e = 2 * e2 + h;
+        const float yv = h ? yy.y : yy.x;
+        float gv = h ? gg.y : gg.x;
+        if (act == 1 && fmaf(yv, sc[e], sh[e]) <= 0.f) gv *= 0.2f;
+        s0[e] += gv;
+        s1[e] = fmaf(gv, (yv - mu[e]) * is[e], s1[e]);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    s0[e] += __shfl_xor_sync(0xffffffffu, s0[e], 8);
+    s0[e] += __shfl_xor_sync(0xffffffffu, s0[e], 16);
+    s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 8);
+    s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 16);
+  }
+  __shared__ float red[8][2][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 8) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      red[warp][0][lane * 8 + e] = s0[e];
+      red[warp][1][lane * 8 + e] = s1[e];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
+    double acc = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) acc += static_cast<double>(red[wv][which][c]);
+    atomicAdd(sums + which * 64 + c, acc);
+  }
+}
+
+// pass 2: gy = gamma*invstd*(gz - mean(gz) - xhat*mean(gz*xhat))   [scale == gamma*invstd]
+__global__ void bn_bwd_apply_cl_kernel(const __nv_bfloat16* __restrict__ ga, const __nv_bfloat16* __restrict__ y,
+                                       long long groups, const float* __restrict__ saved, int act,
+                                       const double* __restrict__ sums, double inv_count,
+                                       __nv_bfloat16* __restrict__ gy) {
+  __shared__ float sc[64], sh[64], mu[64], is[64], m0[64], m1[64];
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x;
+    sc[c] = saved[c];
+    sh[c] = saved[64 + c];
+    mu[c] = saved[128 + c];
+    is[c] = saved[192 + c];
+    m0[c] = static_cast<float>(sums[c] * inv_count);
+    m1[c] = static_cast<float>(sums[64 + c] * inv_count);
+  }
+  __syncthreads();
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < groups;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i & 7);
+    const uint4 g4 = *reinterpret_cast<const uint4*>(ga + i * 8);
+    const uint4 y4 = *reinterpret_cast<const uint4*>(y + i * 8);
+    const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, yw[4] = {y4.x, y4.y, y4.z, y4.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e2 = 0; e2 < 4; ++e2) {
+      const float2 gg = unpack2(gw[e2]), yy = unpack2(yw[e2]);
+      float r[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = g * 8 + 2 * e2 + h;
+        const float yv = h ? yy.y : yy.x;
+        float gv = h ? gg.y : gg.x;
+        if (act == 1 && fmaf(yv, sc[c], sh[c]) <= 0.f) gv *= 0.2f;
+        const float xh = (yv - mu[c]) * is[c];
+        r[h] = sc[c] * (gv - m0[c] - xh * m1[c]);
+      }
+      o[e2] = pack2(r[0], r[1]);
+    }
+    *reinterpret_cast<uint4*>(gy + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// out[c] (+)= scale * in[c]  (double -> float), used for dgamma / dbeta / bias gradients
+__global__ void d2f_kernel(const double* __restrict__ in, int n, float scale, int accumulate, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (accumulate ? out[i] : 0.f) + scale * static_cast<float>(in[i]);
+}
+
+// g (+)= coef*(a - b)                                               (MSE gradient, coef = weight*2/n)
+__global__ void diff_scale_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float coef,
+                                  int accumulate, float* __restrict__ g) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    g[i] = (accumulate ? g[i] : 0.f) + coef * (a[i] - b[i]);
+}
+// gpre = g*(1 - out^2)
+__global__ void tanh_bwd_kernel(const float* __restrict__ g, const float* __restrict__ out, long long n,
+                                float* __restrict__ gpre) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    gpre[i] = g[i] * (1.f - out[i] * out[i]);
+}
+// y = a*x + b*y
+__global__ void axpby_kernel(float a, const float* __restrict__ x, float b, float* __restrict__ y, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    y[i] = a * x[i] + (b == 0.f ? 0.f : b * y[i]);
+}
+__global__ void fill_kernel(float* __restrict__ y, float v, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    y[i] = v;
+}
+// out[c] (+)= sum over n, spatial of g[n][c][s]                       (bias gradient of the fp32 NCDHW tails)
+__global__ void channel_sum_ncdhw_kernel(const float* __restrict__ g, int N, int C, long long sp, int accumulate,
+                                         float* __restrict__ out) {
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  float acc = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float* p = g + (static_cast<long long>(n) * C + c) * sp;
+    for (long long i = threadIdx.x; i < sp; i += blockDim.x) acc += p[i];
+  }
+  const float t = block_sum(acc, red);
+  if (threadIdx.x == 0) out[c] = (accumulate ? out[c] : 0.f) + t;
+}
+// KL gradient (losses.py:5-7): d/dmu = coef*mu ; d/dlogvar = coef*0.5*(exp(lv)-1) ; coef = kl_weight/n
+__global__ void kl_grad_kernel(const float* __restrict__ mu, const float* __restrict__ lv, long long n, float coef,
+                               float* __restrict__ gmu, float* __restrict__ glv) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    gmu[i] = coef * mu[i];
+    glv[i] = coef * 0.5f * (expf(lv[i]) - 1.f);
+  }
+}
+// spectral-norm chain rule (u, v constants): gW (+)= (G - <G, W/sigma> u v^T) / sigma            one CTA
+__global__ void sn_grad_kernel(const float* __restrict__ G, const float* __restrict__ w, const float* __restrict__ u,
+                               const float* __restrict__ v, const float* __restrict__ sigma, int cout, int k,
+                               int accumulate, float* __restrict__ gw) {
+  __shared__ float red[32];
+  const float sg = sigma[0];
+  float part = 0.f;
+  const int n = cout * k;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) part = fmaf(G[i], w[i], part);
+  const float dot = block_sum(part, red) / sg;   // <G, W/sigma>
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int r = i / k, c = i - r * k;
+    const float val = (G[i] - dot * u[r] * v[c]) / sg;
+    gw[i] = (accumulate ? gw[i] : 0.f) + val;
+  }
+}
+// WGAN-GP (losses.py:47-52): xhat = alpha*real + (1-alpha)*fake
+__global__ void lerp_kernel(const float* __restrict__ a, const float* __restrict__ b, float alpha, long long n,
+                            float* __restrict__ out) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = alpha * a[i] + (1.f - alpha) * b[i];
+}
+// per voxel: nrm = ||g[:, v]||_2 over C channels ; gp += lambda*(nrm-1)^2/V ; G[c] = lambda*2*(nrm-1)/nrm*g[c]/V
+__global__ void gp_grad_kernel(const float* __restrict__ g, int N, int C, long long sp, float lambda,
+                               float* __restrict__ Gout, float* __restrict__ gp) {
+  __shared__ float red[32];
+  const long long V = static_cast<long long>(N) * sp;
+  const float invV = 1.0f / static_cast<float>(V);
+  float acc = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < V;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = i / sp, s = i - n * sp;
+    float ss = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float x = g[(n * C + c) * sp + s];
+      ss = fmaf(x, x, ss);
+    }
+    const float nrm = sqrtf(ss);
+    acc += (nrm - 1.f) * (nrm - 1.f);
+    const float coef = nrm > 0.f ? lambda * 2.f * (nrm - 1.f) / nrm * invV : 0.f;
+    for (int c = 0; c < C; ++c) Gout[(n * C + c) * sp + s] = coef * g[(n * C + c) * sp + s];
+  }
+  const float t = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(gp, t * lambda * invV);
+}
+
 inline int grid_for(long long n, int block, int cap = 148 * 16) {
   long long b = (n + block - 1) / block;
   if (b > cap) b = cap;
@@ -673,6 +897,93 @@ cudaError_t ew_adam_clip(const AdamTable& tab, int n_tensors, float* norms_scrat
     LAUNCH_CHECK();
   }
   adam_apply_kernel<<<dim3(32, n_tensors), 256, 0, st>>>(tab, norms_scratch, beta1, beta2, eps, bias_corr, clip);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t ew_lrelu_bwd_cl(const __nv_bfloat16* ga, const __nv_bfloat16* a, long long elems, __nv_bfloat16* gz,
+                            cudaStream_t st) {
+  lrelu_bwd_cl_kernel<<<grid_for(elems / 8, 256), 256, 0, st>>>(ga, a, elems / 8, gz);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_bn_bwd_cl(const __nv_bfloat16* ga, const __nv_bfloat16* y, long long voxels, const float* saved, int act,
+                         double* sums, __nv_bfloat16* gy, float* dgamma, float* dbeta, int accumulate,
+                         cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(sums, 0, 128 * sizeof(double), st);
+  if (e != cudaSuccess) return e;
+  bn_bwd_reduce_cl_kernel<<<grid_for(voxels, 32, 148 * 8), 256, 0, st>>>(ga, y, voxels, saved, act, sums);
+  LAUNCH_CHECK();
+  bn_bwd_apply_cl_kernel<<<grid_for(voxels * 8, 256), 256, 0, st>>>(ga, y, voxels * 8, saved, act, sums,
+                                                                    1.0 / static_cast<double>(voxels), gy);
+  LAUNCH_CHECK();
+  if (dbeta) {
+    d2f_kernel<<<1, 64, 0, st>>>(sums, 64, 1.f, accumulate, dbeta);
+    LAUNCH_CHECK();
+  }
+  if (dgamma) {
+    d2f_kernel<<<1, 64, 0, st>>>(sums + 64, 64, 1.f, accumulate, dgamma);
+    LAUNCH_CHECK();
+  }
+  return cudaSuccess;
+}
+cudaError_t ew_colsum_cl(const __nv_bfloat16* g, long long voxels, double* scratch, float* out, int accumulate,
+                         cudaStream_t st) {
+  cudaError_t e = ew_bn_stats_cl(g, voxels, scratch, scratch + 64, st);
+  if (e != cudaSuccess) return e;
+  d2f_kernel<<<1, 64, 0, st>>>(scratch, 64, 1.f, accumulate, out);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_diff_scale(const float* a, const float* b, long long n, float coef, int accumulate, float* g,
+                          cudaStream_t st) {
+  diff_scale_kernel<<<grid_for(n, 256), 256, 0, st>>>(a, b, n, coef, accumulate, g);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_tanh_bwd(const float* g, const float* out, long long n, float* gpre, cudaStream_t st) {
+  tanh_bwd_kernel<<<grid_for(n, 256), 256, 0, st>>>(g, out, n, gpre);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_axpby(float a, const float* x, float b, float* y, long long n, cudaStream_t st) {
+  axpby_kernel<<<grid_for(n, 256), 256, 0, st>>>(a, x, b, y, n);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_fill(float* y, float v, long long n, cudaStream_t st) {
+  fill_kernel<<<grid_for(n, 256), 256, 0, st>>>(y, v, n);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_channel_sum_ncdhw(const float* g, int N, int C, long long sp, int accumulate, float* out,
+                                 cudaStream_t st) {
+  channel_sum_ncdhw_kernel<<<C, 512, 0, st>>>(g, N, C, sp, accumulate, out);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_kl_grad(const float* mu, const float* lv, long long n, float coef, float* gmu, float* glv,
+                       cudaStream_t st) {
+  kl_grad_kernel<<<grid_for(n, 256), 256, 0, st>>>(mu, lv, n, coef, gmu, glv);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_sn_grad(const float* G, const float* w, const float* u, const float* v, const float* sigma, int cout,
+                       int k, int accumulate, float* gw, cudaStream_t st) {
+  sn_grad_kernel<<<1, 1024, 0, st>>>(G, w, u, v, sigma, cout, k, accumulate, gw);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_lerp(const float* a, const float* b, float alpha, long long n, float* out, cudaStream_t st) {
+  lerp_kernel<<<grid_for(n, 256), 256, 0, st>>>(a, b, alpha, n, out);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_gp_grad(const float* g, int N, int C, long long sp, float lambda, float* Gout, float* gp,
+                       cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(gp, 0, sizeof(float), st);
+  if (e != cudaSuccess) return e;
+  gp_grad_kernel<<<grid_for(static_cast<long long>(N) * sp, 256, 148 * 4), 256, 0, st>>>(g, N, C, sp, lambda, Gout, gp);
   LAUNCH_CHECK();
   return cudaSuccess;
 }

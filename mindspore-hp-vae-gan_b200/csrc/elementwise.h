@@ -47,4 +47,26 @@ cudaError_t ew_reparam(const float* mu, const float* lv, const float* eps, long 
 cudaError_t ew_adam_clip(const AdamTable& tab, int n_tensors, float* norms_scratch, float beta1, float beta2,
                          float eps, float bias_corr, float clip, cudaStream_t st);
 
+cudaError_t ew_lrelu_bwd_cl(const __nv_bfloat16* ga, const __nv_bfloat16* a, long long elems, __nv_bfloat16* gz,
+                            cudaStream_t st);
+cudaError_t ew_bn_bwd_cl(const __nv_bfloat16* ga, const __nv_bfloat16* y, long long voxels, const float* saved, int act,
+                         double* sums, __nv_bfloat16* gy, float* dgamma, float* dbeta, int accumulate,
+                         cudaStream_t st);
+cudaError_t ew_colsum_cl(const __nv_bfloat16* g, long long voxels, double* scratch, float* out, int accumulate,
+                         cudaStream_t st);
+cudaError_t ew_diff_scale(const float* a, const float* b, long long n, float coef, int accumulate, float* g,
+                          cudaStream_t st);
+cudaError_t ew_tanh_bwd(const float* g, const float* out, long long n, float* gpre, cudaStream_t st);
+cudaError_t ew_axpby(float a, const float* x, float b, float* y, long long n, cudaStream_t st);
+cudaError_t ew_fill(float* y, float v, long long n, cudaStream_t st);
+cudaError_t ew_channel_sum_ncdhw(const float* g, int N, int C, long long sp, int accumulate, float* out,
+                                 cudaStream_t st);
+cudaError_t ew_kl_grad(const float* mu, const float* lv, long long n, float coef, float* gmu, float* glv,
+                       cudaStream_t st);
+cudaError_t ew_sn_grad(const float* G, const float* w, const float* u, const float* v, const float* sigma, int cout,
+                       int k, int accumulate, float* gw, cudaStream_t st);
+cudaError_t ew_lerp(const float* a, const float* b, float alpha, long long n, float* out, cudaStream_t st);
+cudaError_t ew_gp_grad(const float* g, int N, int C, long long sp, float lambda, float* Gout, float* gp,
+                       cudaStream_t st);
+
 }  // namespace hpvg

@@ -72,6 +72,19 @@ _SIGS = {
     "hpvg_mean": ([vp, ll, vp, vp], c_int),
     "hpvg_kl": ([vp, vp, ll, vp, vp], c_int),
     "hpvg_reparam": ([vp, vp, vp, ll, vp, vp], c_int),
+    "hpvg_conv_wgrad_cl": ([vp, i, vp, i, i, i, i, i, vp, i, i, i, i, i, i, i, f, vp], c_int),
+    "hpvg_lrelu_bwd_cl": ([vp, vp, ll, vp, vp], c_int),
+    "hpvg_bn_bwd_cl": ([vp, vp, ll, vp, i, vp, vp, vp, i, vp], c_int),
+    "hpvg_colsum_cl": ([vp, ll, vp, i, vp], c_int),
+    "hpvg_mse_grad": ([vp, vp, ll, f, i, vp, vp], c_int),
+    "hpvg_tanh_bwd": ([vp, vp, ll, vp, vp], c_int),
+    "hpvg_axpby": ([f, vp, f, vp, ll, vp], c_int),
+    "hpvg_fill": ([vp, f, ll, vp], c_int),
+    "hpvg_channel_sum": ([vp, i, i, ll, i, vp, vp], c_int),
+    "hpvg_kl_grad": ([vp, vp, ll, f, vp, vp, vp], c_int),
+    "hpvg_sn_grad": ([vp, vp, vp, vp, vp, i, i, i, vp, vp], c_int),
+    "hpvg_lerp": ([vp, vp, f, ll, vp, vp], c_int),
+    "hpvg_gp_grad": ([vp, i, i, ll, f, vp, vp, vp], c_int),
     "hpvg_adam_clip_multi": ([i, POINTER(vp), POINTER(vp), POINTER(vp), POINTER(vp), POINTER(ll), POINTER(f), f, f,
                               f, i, f, vp], c_int),
 }

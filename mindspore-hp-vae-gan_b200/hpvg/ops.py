@@ -307,3 +307,96 @@ def adam_clip_multi(params, grads, ms, vs, lrs, step, beta1=0.5, beta2=0.999, ep
     check(lib.hpvg_adam_clip_multi(n, VP(*[p.ptr for p in params]), VP(*[g.ptr for g in grads]),
                                    VP(*[m.ptr for m in ms]), VP(*[v.ptr for v in vs]), sizes, lr_arr, beta1, beta2,
                                    eps, int(step), float(clip), _s(stream)), "adam_clip_multi")
+
+
+# ================================================================================================ backward operators
+def conv_wgrad_cl(x_cl, gy_cl, dw, co_off=0, co_n=64, ci_off=0, ci_n=64, x_coff=0, gy_coff=0, accumulate=False,
+                  scale=1.0, stream=None):
+    """dW block (+)= scale * sum_v gy[v] (x) x[v+tap].  x_cl / gy_cl: bf16 cl with >= 64 channels; dw: fp32
+    (Cout, Cin, [kt,] 3, 3)."""
+    N, T, H, W, xp = x_cl.shape
+    gp = gy_cl.shape[-1]
+    kt = dw.shape[2] if len(dw.shape) == 5 else 1
+    check(lib.hpvg_conv_wgrad_cl(ctypes.c_void_p(x_cl.ptr + 2 * x_coff), xp, ctypes.c_void_p(gy_cl.ptr + 2 * gy_coff),
+                                 gp, N, T, H, W, _p(dw), dw.shape[1], kt, co_off, co_n, ci_off, ci_n,
+                                 1 if accumulate else 0, float(scale), _s(stream)), "conv_wgrad_cl")
+    return dw
+
+
+def lrelu_bwd_cl(ga, a, out=None, stream=None):
+    out = out or Tensor(ga.shape, BF16)
+    check(lib.hpvg_lrelu_bwd_cl(_p(ga), _p(a), ga.size, _p(out), _s(stream)), "lrelu_bwd_cl")
+    return out
+
+
+def bn_bwd_cl(ga, y, saved, act=ACT_LRELU, out=None, dgamma=None, dbeta=None, accumulate=False, stream=None):
+    voxels = int(np.prod(ga.shape[:-1]))
+    out = out or Tensor(ga.shape, BF16)
+    check(lib.hpvg_bn_bwd_cl(_p(ga), _p(y), voxels, _p(saved), act, _p(out), _p(dgamma), _p(dbeta),
+                             1 if accumulate else 0, _s(stream)), "bn_bwd_cl")
+    return out
+
+
+def colsum_cl(g, out, accumulate=False, stream=None):
+    check(lib.hpvg_colsum_cl(_p(g), int(np.prod(g.shape[:-1])), _p(out), 1 if accumulate else 0, _s(stream)),
+          "colsum_cl")
+    return out
+
+
+def mse_grad(out_t, target, coef, g=None, accumulate=False, stream=None):
+    g = g or Tensor(out_t.shape, F32)
+    check(lib.hpvg_mse_grad(_p(out_t), _p(target), out_t.size, float(coef), 1 if accumulate else 0, _p(g), _s(stream)),
+          "mse_grad")
+    return g
+
+
+def tanh_bwd(g, out_t, gpre=None, stream=None):
+    gpre = gpre or Tensor(g.shape, F32)
+    check(lib.hpvg_tanh_bwd(_p(g), _p(out_t), g.size, _p(gpre), _s(stream)), "tanh_bwd")
+    return gpre
+
+
+def axpby(a, x, b, y, stream=None):
+    check(lib.hpvg_axpby(float(a), _p(x), float(b), _p(y), x.size, _s(stream)), "axpby")
+    return y
+
+
+def fill(t, value, stream=None):
+    check(lib.hpvg_fill(_p(t), float(value), t.size, _s(stream)), "fill")
+    return t
+
+
+def channel_sum(g, out, accumulate=False, stream=None):
+    N, C = g.shape[0], g.shape[1]
+    check(lib.hpvg_channel_sum(_p(g), N, C, g.size // (N * C), 1 if accumulate else 0, _p(out), _s(stream)),
+          "channel_sum")
+    return out
+
+
+def kl_grad(mu, logvar, coef, gmu=None, glv=None, stream=None):
+    gmu = gmu or Tensor(mu.shape, F32)
+    glv = glv or Tensor(mu.shape, F32)
+    check(lib.hpvg_kl_grad(_p(mu), _p(logvar), mu.size, float(coef), _p(gmu), _p(glv), _s(stream)), "kl_grad")
+    return gmu, glv
+
+
+def sn_grad(G, w, u, v, sigma, gw, accumulate=False, stream=None):
+    cout = w.shape[0]
+    check(lib.hpvg_sn_grad(_p(G), _p(w), _p(u), _p(v), _p(sigma), cout, w.size // cout, 1 if accumulate else 0, _p(gw),
+                           _s(stream)), "sn_grad")
+    return gw
+
+
+def lerp(a, b, alpha, out=None, stream=None):
+    out = out or Tensor(a.shape, F32)
+    check(lib.hpvg_lerp(_p(a), _p(b), float(alpha), a.size, _p(out), _s(stream)), "lerp")
+    return out
+
+
+def gp_grad(g, lam, Gout=None, gp=None, stream=None):
+    """losses.py:47-52: returns (G = d GP / d g, gp scalar tensor)."""
+    N, C = g.shape[0], g.shape[1]
+    Gout = Gout or Tensor(g.shape, F32)
+    gp = gp or Tensor((1,), F32)
+    check(lib.hpvg_gp_grad(_p(g), N, C, g.size // (N * C), float(lam), _p(Gout), _p(gp), _s(stream)), "gp_grad")
+    return Gout, gp

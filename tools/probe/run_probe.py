@@ -269,6 +269,35 @@ def test_m64():
     return True
 
 
+
+# ------------------------------------------------------------------------------------------ test 11: MN-major SW128 (wgrad operands)
+def test_mn_sw128():
+    """A = x^T, B = gy^T taken straight from channels-last [voxel][64ch] SW128 rows (what TMA writes):
+    D[m=ci (+64 for the second x row)][n=co] = sum_k x[row0+k(+P)][ci] * gy[g0+k][co], K = 16 voxels, shifted starts."""
+    ok = True
+    P = 66                                   # x row pitch in voxels (64 + 2 halo)
+    X = rnd(3 * P, 64)                       # 3 image rows of 66 voxels
+    GY = rnd(64, 64)                         # one gy row segment of 64 voxels
+    ia = sw128_image(X)                      # 198 rows * 128 = 25344 B
+    boff = (ia.nbytes + 1023) // 1024 * 1024
+    ib = sw128_image(GY)
+    img = np.concatenate([ia, np.zeros((boff - ia.nbytes) // 2, np.uint16), ib])
+    for (row0, g0) in ((0, 0), (1, 0), (19, 16), (2 + 32, 32), (5, 48)):
+        # M=128: block 0 = x rows starting row0, block 1 = the same voxels one image row below (LBO = P*128)
+        a = smem_desc(row0 * 128, P * 128, 1024, layout=2)
+        b = smem_desc(boff + g0 * 128, 16, 1024, layout=2)
+        out = run_umma(img, [(a, b, idesc_bf16(128, 64, 1, 1), 0, 0)], 64)
+        want = np.concatenate([X[row0:row0 + 16].T @ GY[g0:g0 + 16], X[row0 + P:row0 + P + 16].T @ GY[g0:g0 + 16]])
+        ok &= report("T11 MN-major SW128 M128 (2 x-rows via LBO) row0=%d g0=%d" % (row0, g0), out, want, tol=2e-2)
+    # M=64 variant
+    a = smem_desc(3 * 128, P * 128, 1024, layout=2)
+    b = smem_desc(boff, 16, 1024, layout=2)
+    out = run_umma(img, [(a, b, idesc_bf16(64, 64, 1, 1), 0, 0)], 64)
+    want = X[3:19].T @ GY[0:16]
+    lanes = [(i // 16) * 32 + i % 16 for i in range(64)]
+    ok &= report("T11 MN-major SW128 M64 (lane map (i/16)*32+i%16)", out[lanes], want, tol=2e-2)
+    return ok
+
 # ------------------------------------------------------------------------------------------ TMA
 def run_tma(src_u16, dims, strides_bytes, box, swizzle, coords):
     rank = len(dims)
@@ -371,7 +400,7 @@ def test_timing():
 TESTS = {
     "basic64": test_basic, "basic16": lambda: test_basic(16), "shift": test_shift, "lbo_overlap": test_lbo_overlap,
     "conv_nosw": test_conv_plane_nosw, "sw128": test_sw128, "conv_sw128": test_conv_plane_sw128,
-    "mn_major": test_mn_major, "m64": test_m64, "tma_nosw": test_tma_nosw, "tma_sw128": test_tma_sw128,
+    "mn_major": test_mn_major, "mn_sw128": test_mn_sw128, "m64": test_m64, "tma_nosw": test_tma_nosw, "tma_sw128": test_tma_sw128,
     "timing": test_timing,
 }
 
