@@ -382,7 +382,7 @@ const char* conv3d_umma_launch(const ConvLaunch& L, cudaStream_t stream) {
   if (!enc) return "cuTensorMapEncodeTiled entry point not available";
   const int cin_pitch = L.in_pitch;  // channels per voxel row in the input tensor
   const int cin_box = (L.mode == CONV_MODE_8_64) ? 8 : 64;
-  if (L.mode == CONV_MODE_8_64 && cin_pitch != 8) return "mode 8->64 needs an 8-channel (16 B/voxel) input";
+  if (cin_pitch < cin_box || (cin_pitch & 7)) return "input pitch must be a multiple of 8 channels and >= the box";
   if ((reinterpret_cast<uintptr_t>(L.in) & 15) != 0) return "input not 16-byte aligned";
   CUtensorMap tmap;
   cuuint64_t gd[5] = {static_cast<cuuint64_t>(cin_box), static_cast<cuuint64_t>(L.W), static_cast<cuuint64_t>(L.H),

@@ -127,8 +127,8 @@ class ConvLayer(Cell):
         self.invalidate()
 
     # ---- forward
-    def _prepare(self, training, stream):
-        """(Re)build the packed filter bank and the epilogue vectors."""
+    def _prepare_wimgs(self, stream=None):
+        """(Re)build the packed filter bank(s) — no side effects on the spectral-norm state."""
         if self._wimgs is None:
             w = self.p["weight"]
             if self.cout <= 4:
@@ -140,6 +140,10 @@ class ConvLayer(Cell):
                     for ib in range(1 if self.cin <= 8 else self.cin // 64):
                         self._wimgs.append(ops.pack_weights(w, mode, cout_off=ob * 64, cout=64, cin_off=ib * 64,
                                                             cin=min(self.cin, 64), stream=stream))
+
+    def _prepare(self, training, stream):
+        """Filter bank + the epilogue vectors (bias / folded BN / 1/sigma) for this forward."""
+        self._prepare_wimgs(stream)
         if self.sn:
             # Q5: u/v advance on EVERY forward, train or eval (spectral_norm.py:146-148)
             self._sigma = ops.sn_power_iter(self.p["weight"], self.p["weight_u"], self.p["weight_v"],

@@ -1,0 +1,563 @@
+"""Training step of HP-VAE-GAN on libhpvg kernels — mirror of the reference's `src/modules/losses.py`
+(DWithLoss :17, GWithLoss :59), `src/modules/optimizers.py` (ClippedAdam :33) and the way `train_video.py:65-113`
+wires them through `nn.TrainOneStepCell`.
+
+MindSpore's autodiff is restated by hand: every backward pass below is an explicit composition of the data-gradient
+convolution (the forward tcgen05 kernel with a transposed / mirrored filter bank), the tcgen05 weight-gradient kernel,
+and fused elementwise kernels (BatchNorm / LeakyReLU / tanh backward, spectral-norm chain rule, WGAN-GP pieces).
+Reference quirks are mirrored on purpose: the adversarial generator term carries no gradient
+(Q1), z is pure noise unless is_training (Q2), the GP alpha is drawn once (Q3), frozen blocks still run BatchNorm in
+batch-statistics mode and update their moving stats (Q4), spectral-norm u/v advance on every forward (Q5)."""
+import numpy as np
+
+from . import ops
+from .networks_3d import ConvLayer, Workspace
+from .ops import ACT_LRELU, ACT_NONE, ACT_TANH, CONV_64_16, CONV_64_64, CONV_8_64, OUT_BF16_CL, OUT_F32_NCDHW, OUT_F32_RAW
+from .runtime import BF16, F32, HpvgError, Tensor, from_numpy
+from .utils import images as uimg
+
+NON_TRAINABLE = ("weight_u", "weight_v", "moving_mean", "moving_variance")
+
+
+def trainable_params(cell, prefix=""):
+    """[(name, Tensor)] — mindspore Cell.trainable_params(): everything except u/v and the BN moving statistics."""
+    return [(k, t) for k, t in cell.parameters_dict(prefix).items() if not k.endswith(NON_TRAINABLE)]
+
+
+class GradBook:
+    """name-less gradient store keyed by the parameter Tensor's device pointer."""
+
+    def __init__(self):
+        self._g = {}
+
+    def of(self, param):
+        g = self._g.get(param.ptr)
+        if g is None:
+            g = Tensor(param.shape, F32).zero_()
+            self._g[param.ptr] = g
+        return g
+
+    def has(self, param):
+        return param.ptr in self._g
+
+    def zero(self, stream=None):
+        for g in self._g.values():
+            g.zero_(stream)
+
+
+# ================================================================================================ layer level
+_ZERO64 = {}
+
+
+def _unit_affine(stream=None):
+    """(scale=1, shift=0) epilogue vectors."""
+    t = _ZERO64.get("unit")
+    if t is None:
+        t = from_numpy(np.concatenate([np.ones(64, np.float32), np.zeros(64, np.float32)]).reshape(2, 64))
+        _ZERO64["unit"] = t
+    return t
+
+
+def layer_forward_train(layer, x_cl, ws, key, stream=None):
+    """Forward of one ConvLayer keeping what its backward needs.  Returns (output, ctx)."""
+    N, T, H, W, _ = x_cl.shape
+    layer._prepare(True, stream)
+    ctx = {"x": x_cl, "layer": layer}
+    if layer.bn:
+        y = ws.get(key + ".y", (N, T, H, W, layer.cout), BF16)
+        ops.conv3d_cl_any(x_cl, layer.p["weight"], layer._aff, ACT_NONE, layer.cin, layer.cout, out=y,
+                          wimgs=layer._wimgs, stream=stream)
+        a = ws.get(key + ".a", (N, T, H, W, layer.cout), BF16)
+        a, saved = ops.bn_train_cl(y, layer.p["gamma"], layer.p["beta"], layer.p["moving_mean"],
+                                   layer.p["moving_variance"], layer.act, out=a, stream=stream)
+        layer._aff = None
+        ctx.update(y=y, a=a, saved=saved)
+        return a, ctx
+    if layer.sn:
+        # keep this pass's (sigma, u, v): the chain rule needs the values used by THIS forward (Q5)
+        sig = Tensor((2,), F32).copy_(layer._sigma, stream)
+        u = Tensor(layer.p["weight_u"].shape, F32).copy_(layer.p["weight_u"], stream)
+        v = Tensor(layer.p["weight_v"].shape, F32).copy_(layer.p["weight_v"], stream)
+        aff = Tensor(layer._aff.shape, F32).copy_(layer._aff, stream)
+        ctx.update(sigma=sig, u=u, v=v, aff=aff)
+    if layer.cout <= 4:
+        raise HpvgError("tail convs are handled by the block-level code")
+    a = ws.get(key + ".a", (N, T, H, W, layer.cout), BF16)
+    ops.conv3d_cl_any(x_cl, layer.p["weight"], layer._aff, layer.act, layer.cin, layer.cout, out=a,
+                      wimgs=layer._wimgs, stream=stream)
+    ctx.update(a=a)
+    return a, ctx
+
+
+def _dgrad_wimgs(layer, stream=None):
+    """Filter banks of the data-gradient convolution of `layer` (roles of Cin/Cout swapped, taps mirrored)."""
+    w = layer.p["weight"]
+    cin, cout = layer.cin, layer.cout           # forward channels; dgrad maps cout -> cin
+    if cin <= 8:                                 # 64 -> (<=4): tail-type kernel
+        return [ops.pack_weights(w, CONV_64_16, True, cout=cin, stream=stream)]
+    if cout <= 4:                                # (<=4, zero padded to 8) -> 64: head-type kernel
+        return [ops.pack_weights(w, CONV_8_64, True, cin=cout, stream=stream)]
+    imgs = []
+    for ob in range(cin // 64):                  # output blocks of the dgrad = forward input blocks
+        for ib in range(cout // 64):
+            imgs.append(ops.pack_weights(w, CONV_64_64, True, cout_off=ob * 64, cout=64, cin_off=ib * 64, cin=64,
+                                         stream=stream))
+    return imgs
+
+
+def conv_backward(layer, ctx, gy_cl, grads, ws, key, need_dx=True, want_dw=True, inv_sigma_aff=None, stream=None,
+                  dw_target=None):
+    """Backward of the convolution of `layer` given gy (bf16 cl, Cout channels [zero padded to 64 for tails]).
+    Accumulates dW (into dw_target or grads) and db; returns dx: bf16 cl (Cin >= 64) or fp32 ncdhw (Cin <= 4)."""
+    x_cl = ctx["x"]
+    N, T, H, W, xp = x_cl.shape
+    cin, cout = layer.cin, layer.cout
+    w = layer.p["weight"]
+    if want_dw:
+        dw = dw_target if dw_target is not None else grads.of(w)
+        xw = ctx.get("x_wide", x_cl)             # head convs: the 64-channel zero-padded copy of the 8-channel input
+        for ob in range(max(1, cout // 64)):
+            for ib in range(max(1, cin // 64)):
+                ops.conv_wgrad_cl(xw, gy_cl, dw, co_off=ob * 64, co_n=min(cout, 64), ci_off=ib * 64,
+                                  ci_n=min(cin, 64), x_coff=ib * 64, gy_coff=ob * 64, accumulate=True, stream=stream)
+    if not need_dx:
+        return None
+    imgs = _dgrad_wimgs(layer, stream)
+    aff = inv_sigma_aff if inv_sigma_aff is not None else _unit_affine(stream)
+    sc, sh = aff.view((64,), F32, 0), _unit_affine(stream).view((64,), F32, 256)
+    if cin <= 8:
+        out = ws.get(key + ".dx3", (N, cin, T, H, W), F32)
+        return ops.conv_cl(CONV_64_16, gy_cl, imgs[0], sc, sh, ACT_NONE, OUT_F32_NCDHW, out=out, cout_real=cin,
+                           stream=stream)
+    dx = ws.get(key + ".dx", (N, T, H, W, cin), BF16)
+    if cout <= 4:
+        return ops.conv_cl(CONV_8_64, gy_cl, imgs[0], sc, sh, ACT_NONE, OUT_BF16_CL, out=dx, out_pitch=cin,
+                           stream=stream)
+    k = 0
+    for ob in range(cin // 64):
+        partial = None
+        n_ib = cout // 64
+        for ib in range(n_ib):
+            if ib < n_ib - 1:
+                partial = ops.conv_cl(CONV_64_64, gy_cl, imgs[k], sc, sh, ACT_NONE, OUT_F32_RAW, in_coff=ib * 64,
+                                      out=ws.get(key + ".dxp", (N, T, H, W, 64), F32), stream=stream)
+            else:
+                ops.conv_cl(CONV_64_64, gy_cl, imgs[k], sc, sh, ACT_NONE, OUT_BF16_CL, out=dx, out_pitch=cin,
+                            out_coff=ob * 64, addend=partial, in_coff=ib * 64, stream=stream)
+            k += 1
+    return dx
+
+
+def layer_backward(layer, ctx, ga_cl, grads, ws, key, need_dx=True, trainable=True, stream=None):
+    """Backward of conv -> [BN] -> LeakyReLU given ga (grad wrt the layer output, bf16 cl)."""
+    if layer.bn:
+        dg = grads.of(layer.p["gamma"]) if trainable else None
+        db = grads.of(layer.p["beta"]) if trainable else None
+        gy = ops.bn_bwd_cl(ga_cl, ctx["y"], ctx["saved"], layer.act, out=ws.get(key + ".gy", ga_cl.shape, BF16),
+                           dgamma=dg, dbeta=db, accumulate=True, stream=stream)
+        if trainable:
+            ops.colsum_cl(gy, grads.of(layer.p["bias"]), accumulate=True, stream=stream)
+        return conv_backward(layer, ctx, gy, grads, ws, key, need_dx, trainable, stream=stream)
+    gz = ga_cl
+    if layer.act == ACT_LRELU:
+        gz = ops.lrelu_bwd_cl(ga_cl, ctx["a"], out=ws.get(key + ".gz", ga_cl.shape, BF16), stream=stream)
+    if trainable:
+        if layer.cout == 64:
+            ops.colsum_cl(gz, grads.of(layer.p["bias"]), accumulate=True, stream=stream)
+        else:   # 128-channel outputs (mu / logvar): column sums per 64-channel half via an fp32 view
+            _colsum_wide(gz, grads.of(layer.p["bias"]), stream)
+    if layer.sn:
+        ghat = ws.get(key + ".ghat", layer.p["weight"].shape, F32).zero_(stream)
+        dx = conv_backward(layer, ctx, gz, grads, ws, key, need_dx, trainable, inv_sigma_aff=ctx["aff"],
+                           stream=stream, dw_target=ghat)
+        if trainable:
+            ops.sn_grad(ghat, layer.p["weight"], ctx["u"], ctx["v"], ctx["sigma"], grads.of(layer.p["weight"]),
+                        accumulate=True, stream=stream)
+        return dx
+    return conv_backward(layer, ctx, gz, grads, ws, key, need_dx, trainable, stream=stream)
+
+
+def _colsum_wide(g_cl, out, stream=None):
+    """bias gradient of a 128-channel bf16 cl tensor: unpack to fp32 ncdhw and reduce per channel."""
+    f = ops.unpack_cl(g_cl, stream=stream)
+    ops.channel_sum(f, out, accumulate=True, stream=stream)
+
+
+# ================================================================================================ block level
+def block_forward_train(block, x_cl, residual, ws, tag, stream=None, x_wide=None, out=None):
+    """decoder / body stage in training mode: returns (tanh(block(x) [+ residual]) fp32 ncdhw, ctxs)."""
+    ctxs = []
+    h = x_cl
+    for j, layer in enumerate(block.layers[:-1]):
+        h, c = layer_forward_train(layer, h, ws, "%s.%d" % (tag, j), stream)
+        if j == 0 and x_wide is not None:
+            c["x_wide"] = x_wide
+        ctxs.append(c)
+    tail = block.layers[-1]
+    tail.act = ACT_TANH
+    tail._prepare(True, stream)
+    o = tail.forward_cl(h, residual=residual, out=out, stream=stream)
+    ctxs.append({"x": h, "layer": tail, "out": o})
+    return o, ctxs
+
+
+def block_backward(block, ctxs, g_out, grads, ws, tag, need_dx, trainable=True, stream=None):
+    """g_out: grad wrt the block output tanh(pre [+ up]) (fp32 ncdhw).  Returns (g_pre, dx) where g_pre is the grad wrt
+    the pre-activation (== grad wrt the residual `up`) and dx the grad wrt the block input (None unless need_dx)."""
+    tail_ctx = ctxs[-1]
+    tail = tail_ctx["layer"]
+    o = tail_ctx["out"]
+    N, C, T, H, W = o.shape
+    g_pre = ops.tanh_bwd(g_out, o, gpre=ws.get(tag + ".gpre", o.shape, F32), stream=stream)
+    if trainable:
+        ops.channel_sum(g_pre, grads.of(tail.p["bias"]), accumulate=True, stream=stream)
+    gy = ops.pack_cl(g_pre, c_pitch=64, zero_to=64, out=ws.get(tag + ".gtail", (N, T, H, W, 64), BF16), stream=stream)
+    ga = conv_backward(tail, tail_ctx, gy, grads, ws, tag + ".t", True, trainable, stream=stream)
+    dx = None
+    for j in range(len(block.layers) - 2, -1, -1):
+        last = j == 0
+        ga = layer_backward(block.layers[j], ctxs[j], ga, grads, ws, "%s.%d" % (tag, j), need_dx or not last,
+                            trainable, stream)
+        if last:
+            dx = ga
+    return g_pre, dx
+
+
+# ================================================================================================ generator
+class GeneratorTrainer:
+    """Forward/backward of GeneratorHPVAEGAN in training mode (BatchNorm batch statistics everywhere, Q4)."""
+
+    def __init__(self, netG):
+        self.net = netG
+        self.ws = Workspace()
+
+    def _stage_input(self, x_prev, idx, noise_amp, is_random, noises, stream, wide):
+        net, opt = self.net, self.net.opt
+        size = uimg.scale_shape(opt, idx + 1)
+        N = x_prev.shape[0]
+        up = self.ws.get("up%d" % idx, (N, opt.nc_im) + size, F32)
+        xin = self.ws.get("xin%d" % idx, (N,) + size + (8,), BF16)
+        add_noise = is_random and opt.vae_levels <= idx + 1
+        noise_t, seed, amp = None, 0, 0.0
+        if add_noise:
+            amp = float(noise_amp[idx + 1])
+            if noises is not None and (idx + 1) in noises:
+                noise_t = noises[idx + 1]
+            else:
+                seed = (net.noise_seed + 0x632BE59BD9B4E019 * (idx + 1)) & 0xFFFFFFFFFFFFFFFF
+        ops.upsample_noise_pack(x_prev, size, noise=noise_t, amp=amp, seed=seed, sample_base=net.sample_counter,
+                                up=up, xin=xin, stream=stream)
+        x_wide = None
+        if wide:   # 64-channel zero-padded copy for the head conv's weight gradient
+            f = ops.unpack_cl(xin, C=opt.nc_im, out=self.ws.get("xinf%d" % idx, (N, opt.nc_im) + size, F32),
+                              stream=stream)
+            x_wide = ops.pack_cl(f, c_pitch=64, zero_to=64, out=self.ws.get("xinw%d" % idx, (N,) + size + (64,), BF16),
+                                 stream=stream)
+        return up, xin, x_wide
+
+    def forward(self, video, noise_amp, noise_init=None, is_random=False, noises=None, eps=None, z_pred=None,
+                save_from=None, save_decoder=False, save_encoder=False, stream=None):
+        """networks_3d.py:406-451 in set_train() mode.  Contexts are kept for the encoder / decoder when asked and
+        for body stages with index >= save_from.  Returns dict(x, vae_out, mu, logvar, ctx...)."""
+        net, opt, ws = self.net, self.net.opt, self.ws
+        out = {"body_ctx": {}, "ups": {}}
+        mu = logvar = None
+        if noise_init is None:
+            enc = net.encode
+            x_cl = ops.pack_cl(video, c_pitch=8, stream=stream)
+            ectx = []
+            h = x_cl
+            xw = None
+            if save_encoder:
+                xw = ops.pack_cl(video, c_pitch=64, zero_to=64, stream=stream)
+            for i, l in enumerate(enc._features.layers):
+                h, c = layer_forward_train(l, h, ws, "enc.%d" % i, stream)
+                if i == 0 and xw is not None:
+                    c["x_wide"] = xw
+                ectx.append(c)
+            mu_cl, cm = layer_forward_train(enc._mu, h, ws, "enc.mu", stream)
+            lv_cl, cl = layer_forward_train(enc._logvar, h, ws, "enc.lv", stream)
+            mu, logvar = ops.unpack_cl(mu_cl, stream=stream), ops.unpack_cl(lv_cl, stream=stream)
+            out.update(enc_ctx=ectx, mu_ctx=cm, lv_ctx=cl)
+            if net.is_training:
+                if eps is None:
+                    eps = from_numpy(np.random.normal(size=mu.shape).astype(np.float32))
+                z = ops.reparam(mu, logvar, eps, stream=stream)
+            else:
+                z = z_pred if z_pred is not None else from_numpy(np.random.normal(size=mu.shape).astype(np.float32))
+        else:
+            z = noise_init
+        N = z.shape[0]
+        z_cl = ops.pack_cl(z, out=ws.get("z", (N,) + tuple(z.shape[2:]) + (z.shape[1],), BF16), stream=stream)
+        vae_out, dctx = block_forward_train(net.decoder, z_cl, None, ws, "dec", stream,
+                                            out=ws.get("vae_out", (N, opt.nc_im) + tuple(z.shape[2:]), F32))
+        out.update(vae_out=vae_out, dec_ctx=dctx, mu=mu, logvar=logvar)
+        x = vae_out
+        for idx in range(len(net.body)):
+            keep = save_from is not None and idx >= save_from
+            up, xin, xw = self._stage_input(x, idx, noise_amp, is_random, noises, stream, wide=keep)
+            x, bctx = block_forward_train(net.body[idx], xin, up, ws, "s%d" % idx, stream, x_wide=xw,
+                                          out=ws.get("out%d" % idx, up.shape, F32))
+            if keep:
+                out["body_ctx"][idx] = bctx
+            out["ups"][idx] = up
+        out["x"] = x
+        return out
+
+
+class GWithLoss:
+    """losses.py:59-107.  `grad()` returns (loss value as float, GradBook)."""
+
+    def __init__(self, opt, netD, netG):
+        self._netD, self._netG, self.opt = netD, netG, opt
+        self.rec_weight, self.kl_weight, self.disc_loss_weight = opt.rec_weight, opt.kl_weight, opt.disc_loss_weight
+        self.trainer = GeneratorTrainer(netG)
+        self.grads = GradBook()
+
+    def grad(self, real, real_zero, noise_init, noise_amps, isVAE=False, trainable_body=(), train_codec=False,
+             noises=None, z_pred=None, eps=None, stream=None):
+        """trainable_body: indices of body stages whose parameters are optimised (train_video.py:76-105);
+        train_codec: whether encode/decoder are optimised (VAE phase)."""
+        net, opt, tr = self._netG, self.opt, self.trainer
+        g = self.grads
+        g.zero(stream)
+        nb = len(net.body)
+        if isVAE:
+            save_from = 0
+        else:
+            save_from = min(trainable_body) if trainable_body else nb
+        fw = tr.forward(real_zero, noise_amps, is_random=False, z_pred=z_pred, eps=eps, save_from=save_from,
+                        save_encoder=isVAE, stream=stream)
+        x, vae_out = fw["x"], fw["vae_out"]
+        ws = tr.ws
+        n = x.size
+        loss_t = ops.mse(x, real, stream=stream)
+        total = self.rec_weight * float(loss_t.numpy(stream)[0])
+        g_x = ops.mse_grad(x, real, self.rec_weight * 2.0 / n, g=ws.get("g_x", x.shape, F32), stream=stream)
+        if isVAE:
+            total += self.rec_weight * float(ops.mse(vae_out, real_zero, stream=stream).numpy(stream)[0])
+            total += self.kl_weight * float(ops.kl_criterion(fw["mu"], fw["logvar"], stream=stream).numpy(stream)[0])
+        # ---- backward through the refinement stages (networks_3d.py:434-451)
+        g_cur = g_x
+        lowest = save_from
+        for idx in range(nb - 1, lowest - 1, -1):
+            stop_here = (opt.vae_levels == idx + 1 and not opt.train_all)      # stop_gradient on the stage input
+            need_prev = isVAE and not stop_here
+            g_pre, dx = block_backward(net.body[idx], fw["body_ctx"][idx], g_cur, g, ws, "s%d" % idx,
+                                       need_dx=need_prev, trainable=idx in trainable_body, stream=stream)
+            if not need_prev:
+                g_cur = None
+                break
+            # grad wrt up = g_pre (residual) + dx (through the head conv); then through the resize
+            ops.axpby(1.0, g_pre, 1.0, dx, stream=stream)
+            prev_shape = (vae_out if idx == 0 else fw["ups"][idx - 1]).shape
+            g_cur = ops.resize3d_bwd(dx, prev_shape[2:], out=ws.get("g_prev%d" % idx, prev_shape, F32), stream=stream)
+        if isVAE:
+            # ---- decoder: grad = chain from the stages + rec_weight*MSE(vae_out, real_zero)
+            if nb == 0 or g_cur is None:
+                g_v = ops.mse_grad(vae_out, real_zero, self.rec_weight * 2.0 / vae_out.size,
+                                   g=ws.get("g_v", vae_out.shape, F32), stream=stream)
+                if nb == 0:   # generated IS vae_out: both MSE terms act on it
+                    ops.axpby(1.0, g_x, 1.0, g_v, stream=stream)
+            else:
+                g_v = ops.mse_grad(vae_out, real_zero, self.rec_weight * 2.0 / vae_out.size, g=g_cur, accumulate=True,
+                                   stream=stream)
+            block_backward(net.decoder, fw["dec_ctx"], g_v, g, ws, "dec", need_dx=False, trainable=train_codec,
+                           stream=stream)
+            # ---- encoder: only the KL term reaches it (Q2: z is pure noise unless is_training)
+            if net.is_training:
+                raise HpvgError("is_training=True (reparameterised z) backward is not implemented; the reference's "
+                                "drivers never enable it (train_video.py:387)")
+            mu, lv = fw["mu"], fw["logvar"]
+            gmu, glv = ops.kl_grad(mu, lv, self.kl_weight / mu.size, stream=stream)
+            gmu_cl, glv_cl = ops.pack_cl(gmu, stream=stream), ops.pack_cl(glv, stream=stream)
+            enc = net.encode
+            d1 = layer_backward(enc._mu, fw["mu_ctx"], gmu_cl, g, ws, "enc.mu", True, train_codec, stream)
+            d2 = layer_backward(enc._logvar, fw["lv_ctx"], glv_cl, g, ws, "enc.lv", True, train_codec, stream)
+            ga = _add_cl(d1, d2, ws, stream)
+            for i in range(len(enc._features.layers) - 1, -1, -1):
+                ga = layer_backward(enc._features.layers[i], fw["enc_ctx"][i], ga, g, ws, "enc.%d" % i, i > 0,
+                                    train_codec, stream)
+        else:
+            # ---- adversarial term: value only, no gradient reaches G (Q1, losses.py:93-98)
+            fw2 = tr.forward(None, noise_amps, noise_init=noise_init, is_random=True, noises=noises, stream=stream)
+            d_out = self._netD(fw2["x"], stream=stream)
+            total += -self.disc_loss_weight * float(ops.mean(d_out, stream=stream).numpy(stream)[0])
+        return total, g
+
+
+def _add_cl(a_cl, b_cl, ws, stream=None):
+    """a + b for bf16 cl tensors (through fp32)."""
+    fa, fb = ops.unpack_cl(a_cl, stream=stream), ops.unpack_cl(b_cl, stream=stream)
+    ops.axpby(1.0, fa, 1.0, fb, stream=stream)
+    return ops.pack_cl(fb, stream=stream)
+
+
+# ================================================================================================ discriminator
+class DWithLoss:
+    """losses.py:17-56: -mean D(real) + mean D(sg(G(z))) + lambda * mean((||grad_xhat sum D(xhat)||_2 - 1)^2)."""
+
+    def __init__(self, opt, netD, netG, alpha=None):
+        self._netD, self._netG, self.opt = netD, netG, opt
+        self.lambda_grad = opt.lambda_grad
+        self.alpha = float(np.random.uniform()) if alpha is None else float(alpha)    # Q3: drawn once (losses.py:25)
+        self.trainer = GeneratorTrainer(netG)
+        self.ws = Workspace()
+        self.grads = GradBook()
+
+    # ---- one D forward keeping the tape
+    def _forward(self, x, tag, stream):
+        D, ws = self._netD, self.ws
+        N = x.shape[0]
+        x8 = ops.pack_cl(x, c_pitch=8, out=ws.get(tag + ".x8", (N,) + tuple(x.shape[2:]) + (8,), BF16), stream=stream)
+        xw = ops.pack_cl(x, c_pitch=64, zero_to=64, out=ws.get(tag + ".xw", (N,) + tuple(x.shape[2:]) + (64,), BF16),
+                         stream=stream)
+        ctxs = []
+        h, c = layer_forward_train(D.head, x8, ws, tag + ".h", stream)
+        c["x_wide"] = xw
+        ctxs.append(c)
+        for j, l in enumerate(D.body.layers):
+            h, c = layer_forward_train(l, h, ws, "%s.b%d" % (tag, j), stream)
+            ctxs.append(c)
+        D.tail._prepare(True, stream)
+        out = D.tail.forward_cl(h, out=ws.get(tag + ".out", (N, 1) + tuple(x.shape[2:]), F32), stream=stream)
+        ctxs.append({"x": h, "layer": D.tail, "out": out})
+        return out, ctxs
+
+    def _layers(self):
+        D = self._netD
+        return [D.head] + list(D.body.layers)
+
+    def _backward_first_order(self, ctxs, coef, tag, stream):
+        """d(coef * sum D(x))/dW for one pass."""
+        D, ws, g = self._netD, self.ws, self.grads
+        out = ctxs[-1]["out"]
+        N, _, T, H, W = out.shape
+        go = ops.fill(ws.get(tag + ".go", out.shape, F32), coef, stream)
+        ops.channel_sum(go, g.of(D.tail.p["bias"]), accumulate=True, stream=stream)
+        gy = ops.pack_cl(go, c_pitch=64, zero_to=64, out=ws.get(tag + ".gyt", (N, T, H, W, 64), BF16), stream=stream)
+        ga = conv_backward(D.tail, ctxs[-1], gy, g, ws, tag + ".t", True, True, stream=stream)
+        layers = self._layers()
+        for j in range(len(layers) - 1, -1, -1):
+            ga = layer_backward(layers[j], ctxs[j], ga, g, ws, "%s.l%d" % (tag, j), j > 0, True, stream)
+
+    def _gradient_penalty(self, ctxs, tag, stream):
+        """calc_gradient_penalty (losses.py:47-52) and its gradient wrt D's weights (second order)."""
+        D, ws, g = self._netD, self.ws, self.grads
+        layers = self._layers()
+        out = ctxs[-1]["out"]
+        N, _, T, H, W = out.shape
+        # (1) input gradient of sum D(xhat): deltas[j] = grad wrt the pre-activation of layer j
+        ones = ops.fill(ws.get(tag + ".ones", out.shape, F32), 1.0, stream)
+        d_out = ops.pack_cl(ones, c_pitch=64, zero_to=64, out=ws.get(tag + ".dout", (N, T, H, W, 64), BF16),
+                            stream=stream)
+        ga = conv_backward(D.tail, ctxs[-1], d_out, g, ws, tag + ".gt", True, False, stream=stream)
+        deltas = [None] * len(layers)
+        for j in range(len(layers) - 1, -1, -1):
+            deltas[j] = ops.lrelu_bwd_cl(ga, ctxs[j]["a"], out=ws.get("%s.delta%d" % (tag, j), ga.shape, BF16),
+                                         stream=stream)
+            ga = conv_backward(layers[j], ctxs[j], deltas[j], g, ws, "%s.g%d" % (tag, j), True, False,
+                               inv_sigma_aff=ctxs[j]["aff"], stream=stream)
+        grad_x = ga                                                   # fp32 ncdhw (N, 3, T, H, W)
+        Gx, gp = ops.gp_grad(grad_x, self.lambda_grad, Gout=ws.get(tag + ".G", grad_x.shape, F32), stream=stream)
+        # (2) d GP / d W: push G forward through the SAME linear maps, masked by the LeakyReLU pattern of xhat
+        xi_wide = ops.pack_cl(Gx, c_pitch=64, zero_to=64, out=ws.get(tag + ".xiw", (N, T, H, W, 64), BF16),
+                              stream=stream)
+        xi8 = ops.pack_cl(Gx, c_pitch=8, out=ws.get(tag + ".xi8", (N, T, H, W, 8), BF16), stream=stream)
+        unit = _unit_affine(stream)
+        zero_shift = unit.view((64,), F32, 256)
+        xi = xi8
+        for j, layer in enumerate(layers):
+            ghat = ws.get("%s.ghat%d" % (tag, j), layer.p["weight"].shape, F32).zero_(stream)
+            xw = xi_wide if j == 0 else xi
+            ops.conv_wgrad_cl(xw, deltas[j], ghat, co_n=64, ci_n=min(layer.cin, 64), accumulate=True, stream=stream)
+            ops.sn_grad(ghat, layer.p["weight"], ctxs[j]["u"], ctxs[j]["v"], ctxs[j]["sigma"],
+                        g.of(layer.p["weight"]), accumulate=True, stream=stream)
+            # eta = conv(xi; W/sigma) (no bias, no activation); xi_next = eta * LeakyReLU'(a_j)
+            layer._prepare_wimgs(stream)
+            eta = ops.conv3d_cl_any(xi, layer.p["weight"], _scale_only(ctxs[j]["aff"], zero_shift, ws, tag, j, stream),
+                                    ACT_NONE, layer.cin, 64, out=ws.get("%s.eta%d" % (tag, j), deltas[j].shape, BF16),
+                                    wimgs=layer._wimgs, stream=stream)
+            xi = ops.lrelu_bwd_cl(eta, ctxs[j]["a"], out=ws.get("%s.xi%d" % (tag, j), eta.shape, BF16), stream=stream)
+        ops.conv_wgrad_cl(xi, d_out, g.of(D.tail.p["weight"]), co_n=1, ci_n=64, accumulate=True, stream=stream)
+        return gp
+
+    def grad(self, real, noise_init, noise_amps, noises=None, fake=None, stream=None):
+        g = self.grads
+        g.zero(stream)
+        if fake is None:
+            fake = self.trainer.forward(None, noise_amps, noise_init=noise_init, is_random=True, noises=noises,
+                                        stream=stream)["x"]                      # stop_gradient (losses.py:29-30)
+        V = real.size // real.shape[1]
+        out_r, ctx_r = self._forward(real, "R", stream)
+        self._backward_first_order(ctx_r, -1.0 / V, "R", stream)
+        out_f, ctx_f = self._forward(fake, "F", stream)
+        self._backward_first_order(ctx_f, 1.0 / V, "F", stream)
+        xhat = ops.lerp(real, fake, self.alpha, out=self.ws.get("xhat", real.shape, F32), stream=stream)
+        out_x, ctx_x = self._forward(xhat, "X", stream)
+        gp = self._gradient_penalty(ctx_x, "X", stream)
+        loss = (-float(ops.mean(out_r, stream=stream).numpy(stream)[0]) +
+                float(ops.mean(out_f, stream=stream).numpy(stream)[0]) + float(gp.numpy(stream)[0]))
+        return loss, g
+
+
+def _scale_only(aff, zero_shift, ws, tag, j, stream):
+    """(scale = 1/sigma, shift = 0) epilogue vectors built from a layer's (1/sigma, bias) pair."""
+    t = ws.get("%s.so%d" % (tag, j), (2, 64), F32)
+    t.view((64,), F32, 0).copy_(aff.view((64,), F32, 0), stream)
+    t.view((64,), F32, 256).copy_(zero_shift, stream)
+    return t
+
+
+# ================================================================================================ optimisers
+class Adam:
+    """mindspore.nn.Adam over a flat list or a list of {"params": [...], "lr": x} groups (train_video.py:65,76-108)."""
+
+    def __init__(self, params, learning_rate=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, clip=0.0):
+        self.beta1, self.beta2, self.eps, self.clip = beta1, beta2, eps, clip
+        self.items = []      # (param Tensor, lr)
+        if params and isinstance(params[0], dict):
+            for grp in params:
+                lr = grp.get("lr", learning_rate)
+                for p in grp["params"]:
+                    self.items.append((p[1] if isinstance(p, tuple) else p, lr))
+        else:
+            for p in params:
+                self.items.append((p[1] if isinstance(p, tuple) else p, learning_rate))
+        self.m = [Tensor(p.shape, F32).zero_() for p, _ in self.items]
+        self.v = [Tensor(p.shape, F32).zero_() for p, _ in self.items]
+        self.step = 0
+
+    def apply(self, grads, stream=None):
+        self.step += 1
+        ps = [p for p, _ in self.items]
+        gs = [grads.of(p) for p in ps]
+        ops.adam_clip_multi(ps, gs, self.m, self.v, [lr for _, lr in self.items], self.step, self.beta1, self.beta2,
+                            self.eps, self.clip, stream=stream)
+
+
+class ClippedAdam(Adam):
+    """optimizers.py:33-43: per-tensor ClipByNorm(opt.grad_clip) then Adam."""
+
+    def __init__(self, opt, params, learning_rate=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+        super().__init__(params, learning_rate, beta1, beta2, eps, clip=float(opt.grad_clip))
+
+
+class TrainOneStepCell:
+    """nn.TrainOneStepCell(loss_cell, optimizer): forward, backward, optimiser step; returns the loss."""
+
+    def __init__(self, network, optimizer, cells_to_invalidate=()):
+        self.network, self.optimizer = network, optimizer
+        self.cells = list(cells_to_invalidate)
+
+    def set_train(self, mode=True):
+        for c in (self.network._netG, self.network._netD):
+            c.set_train(mode)
+        return self
+
+    def __call__(self, *args, **kw):
+        loss, grads = self.network.grad(*args, **kw)
+        self.optimizer.apply(grads, stream=kw.get("stream"))
+        for c in self.cells:
+            c.invalidate()     # packed filter banks / folded BN vectors are stale after the update
+        return loss

@@ -298,9 +298,43 @@ def to_torch(p, requires_grad=()):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# Optional bf16 emulation.  The CUDA path stores weights and inter-layer activations in bfloat16.  LeakyReLU makes
+# the GRADIENT a discontinuous function of the forward activations, so comparing gradients against a pure-fp32
+# forward measures mask flips of near-zero pre-activations (~0.15 % of elements -> ~4 % rel-L2 per layer), not the
+# backward kernels.  Inside `with bf16_emulation():` the oracle rounds at exactly the points where the CUDA path
+# stores bf16 (straight-through gradient), which makes the gradient comparison a same-inputs comparison.
+# ----------------------------------------------------------------------------------------------------------------
+_QUANT = [False]
+
+
+class _STQuant(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _q(x):
+    return _STQuant.apply(x) if _QUANT[0] else x
+
+
+class bf16_emulation:
+    def __enter__(self):
+        self._old = _QUANT[0]
+        _QUANT[0] = True
+
+    def __exit__(self, *a):
+        _QUANT[0] = self._old
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # Layers
 # ----------------------------------------------------------------------------------------------------------------
 def _conv(x, w, b, pad):
+    w = _q(w)
     return F.conv3d(x, w, b, padding=pad) if x.dim() == 5 else F.conv2d(x, w, b, padding=pad)
 
 
@@ -327,6 +361,9 @@ def sn_conv(x, p, prefix, pad, update=True):
     sigma, u_new, v_new = sn_power_iteration(w, p[prefix + "weight_u"], p[prefix + "weight_v"])
     if update:
         p[prefix + "weight_u"], p[prefix + "weight_v"] = u_new, v_new
+    if _QUANT[0]:   # the CUDA path convolves with bf16(W) and applies 1/sigma and the bias in the fp32 epilogue
+        bshape = [1, -1] + [1] * (x.dim() - 2)
+        return _conv(x, w, None, pad) / sigma + p[prefix + "bias"].reshape(bshape)
     return _conv(x, w / sigma, p[prefix + "bias"], pad)
 
 
@@ -355,9 +392,12 @@ def conv_block(x, p, prefix, pad, training, bn=True, act=True, taps=None):
     if taps is not None:
         taps[prefix + "conv"] = y
     if bn:
+        if training:
+            y = _q(y)       # training mode stores the raw conv output in bf16 before the statistics pass
         y = batchnorm(y, p, prefix + "1.", training)
     if act:
         y = lrelu(y)
+    y = _q(y)
     if taps is not None:
         taps[prefix + "out"] = y
     return y
@@ -378,20 +418,20 @@ def block_forward(x, p, prefix, opt, training, taps=None):
 def encode(x, p, opt, update_sn=True):
     """Encode3DVAE.construct (networks_3d.py:107-112): FeatureExtractor (3 SN blocks) -> mu, logvar convs."""
     pad = opt.ker_size // 2
-    f = x
+    f = _q(x)
     for i in range(opt.enc_blocks + 1):
-        f = lrelu(sn_conv(f, p, f"encode._features.{i}.0.", pad, update_sn))
-    mu = _conv(f, p["encode._mu.0.weight"], p["encode._mu.0.bias"], pad)
-    logvar = _conv(f, p["encode._logvar.0.weight"], p["encode._logvar.0.bias"], pad)
+        f = _q(lrelu(sn_conv(f, p, f"encode._features.{i}.0.", pad, update_sn)))
+    mu = _q(_conv(f, p["encode._mu.0.weight"], p["encode._mu.0.bias"], pad))
+    logvar = _q(_conv(f, p["encode._logvar.0.weight"], p["encode._logvar.0.bias"], pad))
     return mu, logvar
 
 
 def discriminator(x, p, opt, update_sn=True):
     """WDiscriminator3D.construct (networks_3d.py:189-193)."""
     pad = opt.ker_size // 2
-    h = lrelu(sn_conv(x, p, "head.0.", pad, update_sn))
+    h = _q(lrelu(sn_conv(_q(x), p, "head.0.", pad, update_sn)))
     for j in range(opt.num_layer):
-        h = lrelu(sn_conv(h, p, f"body.{j}.0.", pad, update_sn))
+        h = _q(lrelu(sn_conv(h, p, f"body.{j}.0.", pad, update_sn)))
     return _conv(h, p["tail.weight"], p["tail.bias"], 1)
 
 
@@ -414,6 +454,7 @@ def refinement_layers(start_idx, x_prev_out, noise_amp, p, opt, is_random, train
             x_in = up + noises[idx + 1] * noise_amp[idx + 1]
         else:
             x_in = up
+        x_in = _q(x_in)
         if taps is not None:
             taps[f"body.{idx}.in"] = x_in
         x_prev = block_forward(x_in, p, f"body.{idx}.", opt, training, taps=taps)
@@ -436,7 +477,7 @@ def generator_forward(video, noise_amp, p, opt, noise_init=None, sample_init=Non
             z_vae = z_pred                                                       # Q2: pure N(0,1)
     else:
         z_vae = noise_init
-    vae_out = torch.tanh(block_forward(z_vae, p, "decoder.", opt, training, taps=taps))
+    vae_out = torch.tanh(block_forward(_q(z_vae), p, "decoder.", opt, training, taps=taps))
     if sample_init is None:
         x = refinement_layers(0, vae_out, noise_amp, p, opt, is_random, training, noises, nd, taps)
     else:
@@ -493,3 +534,18 @@ def adam_step(w, g, m, v, step, lr, beta1=0.5, beta2=0.999, eps=1e-8):
     lr_t = np.float32(lr * math.sqrt(1 - beta2 ** step) / (1 - beta1 ** step))
     w = (w - lr_t * m / (np.sqrt(v) + np.float32(eps))).astype(np.float32)
     return w, m, v
+
+
+def g_loss(real, real_zero, noise_init, noise_amps, pg, pd, opt, is_vae, z_pred=None, eps=None, noises=None,
+           is_training_flag=False):
+    """GWithLoss.construct (losses.py:70-103) in set_train() mode (BatchNorm batch statistics)."""
+    x, vae_out, mu, logvar = generator_forward(real_zero, noise_amps, pg, opt, is_random=False, training=True,
+                                               is_training_flag=is_training_flag, eps=eps, z_pred=z_pred)
+    if is_vae:
+        rec = mse(x, real) + mse(vae_out, real_zero)
+        return opt.rec_weight * rec + opt.kl_weight * kl_criterion(mu, logvar)
+    total = opt.rec_weight * mse(x, real)
+    fake, _ = generator_forward(None, noise_amps, pg, opt, noise_init=noise_init, is_random=True, training=True,
+                                noises=noises)
+    fake = fake.detach()                                                          # Q1 (losses.py:94)
+    return total + (-discriminator(fake, pd, opt).mean() * opt.disc_loss_weight)

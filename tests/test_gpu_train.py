@@ -1,0 +1,232 @@
+"""Parity of the hand-restated training step (GWithLoss / DWithLoss / ClippedAdam, src/modules/losses.py and
+optimizers.py) against torch-CPU autograd on the oracle, same weights / noise / inputs.
+Tolerance: north_star rel-L2 <= 1e-2 per layer for bf16 gradients; deep chains accumulate, stated per assertion."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hpvg_oracle as orc
+from util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(hp, n_body, seed=3, bias_noise=True):
+    from hpvg import networks_3d as n3
+    from hpvg.utils import images as uimg
+    opt, oopt = uimg.default_opt(), orc.default_opt()
+    pg = orc.init_generator_params(oopt, n_body, seed=seed)
+    pd = orc.init_discriminator_params(oopt, seed=seed)
+    rng = np.random.default_rng(seed)
+    if bias_noise:
+        for p in (pg, pd):
+            for k in p:
+                if k.endswith("bias") or k.endswith("beta"):
+                    p[k] = (rng.standard_normal(p[k].shape) * 0.05).astype(np.float32)
+    G = n3.GeneratorHPVAEGAN(opt)
+    for _ in range(n_body):
+        G.init_next_stage()
+    G.load_parameters(pg)
+    D = n3.WDiscriminator3D(opt)
+    D.load_parameters(pd)
+    return G, D, opt, oopt, pg, pd, rng
+
+
+def _grads_by_name(cell, book, names):
+    pd = cell.parameters_dict()
+    return {k: book.of(pd[k]).numpy() for k in names}
+
+
+def _cos(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(a @ b / max(np.linalg.norm(a) * np.linalg.norm(b), 1e-300))
+
+
+def _report(got, ref, tol, what, min_cos=None, only=None):
+    """rel-L2 (and optionally cosine) of every gradient tensor; prints the table, asserts at the end."""
+    worst, rows, bad = 0.0, [], []
+    for k in ref:
+        if only is not None and not only(k):
+            continue
+        r = ref[k]
+        if np.linalg.norm(r) < 1e-5:
+            # conv biases in front of a BatchNorm have an analytically ZERO gradient (BN removes the mean); the
+            # reference value is fp32 rounding noise, ours is bf16 rounding noise: absolute criterion
+            if np.linalg.norm(got[k]) >= 5e-3:
+                bad.append("%s should be ~0 (|g|=%.2e)" % (k, np.linalg.norm(got[k])))
+            continue
+        e, c = rel_l2(got[k], r), _cos(got[k], r)
+        rows.append("%-36s rel-L2 %.3e  cos %.5f  |ref| %.3e" % (k, e, c, np.linalg.norm(r)))
+        worst = max(worst, e)
+        if e >= tol or (min_cos is not None and c < min_cos):
+            bad.append("%s rel-L2 %.3e cos %.5f" % (k, e, c))
+    print("---- %s" % what)
+    print("\n".join(rows))
+    assert not bad, "%s: gradients outside tolerance %.1e: %s" % (what, tol, bad)
+    return worst
+
+
+# Conditioning note (measured with the oracle alone, tools/ + DESIGN.md §parity): in this randomly initialised
+# network a 1e-3 relative perturbation of the FORWARD activations changes the BatchNorm-path weight gradients by
+# 6-11 % rel-L2 (LeakyReLU mask flips coupled through batch statistics).  A bf16 forward differs from the oracle's
+# by ~3e-3 per layer, so end-to-end gradients can only agree to that conditioning; the kernels themselves are held to
+# rel-L2 <= 1e-2 by the teacher-forced per-layer test below and by tests/test_gpu_backward.py.
+E2E_BN_TOL, E2E_BN_COS = 0.20, 0.98
+
+
+def test_per_layer_backward_teacher_forced(hpvg_gpu):
+    """Every conv+BN+LeakyReLU layer of a refinement stage, fed with the ORACLE's input activation and upstream
+    gradient: dW, dgamma, dbeta and dx within rel-L2 1e-2 (north_star, bf16)."""
+    hp = hpvg_gpu
+    from hpvg import networks_3d as n3, ops, train as T
+    from util import bf16_round
+    G, D, opt, oopt, pg, pd, rng = _setup(hp, 1)
+    G.set_train(True)
+    shape = (1, 4, 30, 41)
+    x3 = bf16_round(rng.standard_normal((1, 3) + shape[1:]) * 0.5)
+    up = rng.standard_normal((1, 3) + shape[1:]).astype(np.float32) * 0.3
+    gout = rng.standard_normal((1, 3) + shape[1:]).astype(np.float32)
+    tg = orc.to_torch(pg, requires_grad=("body.",))
+    taps = {}
+    xt = torch.from_numpy(x3).requires_grad_(True)
+    with orc.bf16_emulation():
+        pre = orc.block_forward(xt, tg, "body.0.", oopt, True, taps=taps)
+        out = torch.tanh(pre + torch.from_numpy(up))
+    for v in taps.values():
+        if v.requires_grad:
+            v.retain_grad()
+    out.backward(torch.from_numpy(gout))
+    block = G.body[0]
+    pdict = G.parameters_dict()
+    ws = n3.Workspace()
+    for j in range(opt.num_layer + 1):
+        layer = block.layers[j]
+        xin = x3 if j == 0 else taps["body.0.%d.out" % (j - 1)].detach().numpy()
+        x_cl = ops.pack_cl(hp.from_numpy(xin), c_pitch=8 if j == 0 else 64)
+        a, ctx = T.layer_forward_train(layer, x_cl, ws, "tf%d" % j)
+        if j == 0:
+            ctx["x_wide"] = ops.pack_cl(hp.from_numpy(xin), c_pitch=64, zero_to=64)
+        ga = taps["body.0.%d.out" % j].grad.numpy()
+        book = T.GradBook()
+        dx = T.layer_backward(layer, ctx, ops.pack_cl(hp.from_numpy(ga)), book, ws, "tf%d" % j, need_dx=True)
+        pre_n = "body.0.%d." % j
+        for nm in ("0.weight", "1.bn2d.gamma", "1.bn2d.beta"):
+            e = rel_l2(book.of(pdict[pre_n + nm]).numpy(), tg[pre_n + nm].grad.numpy())
+            assert e < 1e-2, "layer %d %s rel-L2 %.3e" % (j, nm, e)
+        ref_dx = xt.grad.numpy() if j == 0 else taps["body.0.%d.out" % (j - 1)].grad.numpy()
+        got_dx = dx.numpy() if j == 0 else ops.unpack_cl(dx).numpy()
+        e = rel_l2(got_dx, ref_dx)
+        assert e < 1e-2, "layer %d dx rel-L2 %.3e" % (j, e)
+
+
+def test_vae_phase_g_step(hpvg_gpu):
+    """scale_idx = 1 (VAE phase, one refinement stage): loss and gradients of encode / decoder / body.0."""
+    hp = hpvg_gpu
+    from hpvg import train as T
+    G, D, opt, oopt, pg, pd, rng = _setup(hp, 1)
+    s0, s1 = orc.scale_shape(oopt, 0), orc.scale_shape(oopt, 1)
+    real = np.tanh(rng.standard_normal((1, 3) + s1)).astype(np.float32)
+    real_zero = np.tanh(rng.standard_normal((1, 3) + s0)).astype(np.float32)
+    z = rng.standard_normal((1, 128) + s0).astype(np.float32)
+    amps = [1.0, 0.0]
+    tg = orc.to_torch(pg, requires_grad=("encode.", "decoder.", "body."))
+    with orc.bf16_emulation():      # same quantisation points as the CUDA path (see oracle: bf16_emulation)
+        loss_ref = orc.g_loss(torch.from_numpy(real), torch.from_numpy(real_zero), None, amps, tg, None, oopt, True,
+                              z_pred=torch.from_numpy(z))
+    loss_ref.backward()
+    names = [k for k, t in tg.items() if t.requires_grad]
+    ref = {k: tg[k].grad.numpy() for k in names}
+    G.set_train(True)
+    gl = T.GWithLoss(opt, D, G)
+    loss, book = gl.grad(hp.from_numpy(real), hp.from_numpy(real_zero), None, amps, isVAE=True, trainable_body=(0,),
+                         train_codec=True, z_pred=hp.from_numpy(z))
+    assert abs(loss - float(loss_ref)) < 2e-2 * abs(float(loss_ref))
+    got = _grads_by_name(G, book, names)
+    # encoder: only the (smooth) KL term reaches it -> tight; decoder/body: conditioning-limited (see note above)
+    _report(got, ref, 1e-2, "VAE phase / encoder", only=lambda k: k.startswith("encode."))
+    _report(got, ref, E2E_BN_TOL, "VAE phase / decoder + body (BatchNorm path)", min_cos=E2E_BN_COS,
+            only=lambda k: not k.startswith("encode."))
+    # moving statistics were updated exactly like the oracle's (Q4)
+    mm = G.parameters_dict()["decoder.0.1.bn2d.moving_mean"].numpy()
+    assert np.allclose(mm, tg["decoder.0.1.bn2d.moving_mean"].numpy(), atol=2e-3)
+
+
+def test_gan_phase_g_and_d_steps(hpvg_gpu):
+    """scale_idx = 3 (first GAN scale): G step trains body[-1] only; D step incl. the WGAN-GP double backward."""
+    hp = hpvg_gpu
+    from hpvg import train as T
+    G, D, opt, oopt, pg, pd, rng = _setup(hp, 3, seed=5)
+    s0, s3 = orc.scale_shape(oopt, 0), orc.scale_shape(oopt, 3)
+    real = np.tanh(rng.standard_normal((1, 3) + s3)).astype(np.float32)
+    real_zero = np.tanh(rng.standard_normal((1, 3) + s0)).astype(np.float32)
+    z_pred = rng.standard_normal((1, 128) + s0).astype(np.float32)
+    noise_init = rng.standard_normal((1, 128) + s0).astype(np.float32)
+    nz = {3: rng.standard_normal((1, 3) + s3).astype(np.float32)}
+    amps = [1.0, 0.0, 0.0, 0.3]
+    alpha = 0.37
+    G.set_train(True)
+    D.set_train(True)
+    # ------------------------------------------------ D step (runs first, train_video.py:175)
+    tg = orc.to_torch(pg)
+    td = orc.to_torch(pd, requires_grad=("head.", "body.", "tail."))
+    with torch.no_grad(), orc.bf16_emulation():
+        fake_ref, _ = orc.generator_forward(None, amps, tg, oopt, noise_init=torch.from_numpy(noise_init),
+                                            is_random=True, training=True,
+                                            noises={k: torch.from_numpy(v) for k, v in nz.items()})
+    with orc.bf16_emulation():
+        dloss_ref = orc.d_loss(torch.from_numpy(real), fake_ref, alpha, td, oopt)
+    dloss_ref.backward()
+    dnames = [k for k, t in td.items() if t.requires_grad]
+    dref = {k: td[k].grad.numpy() for k in dnames}
+    dl = T.DWithLoss(opt, D, G, alpha=alpha)
+    dloss, dbook = dl.grad(hp.from_numpy(real), hp.from_numpy(noise_init), amps,
+                           noises={k: hp.from_numpy(v) for k, v in nz.items()})
+    assert abs(dloss - float(dloss_ref)) < 2e-2 * max(abs(float(dloss_ref)), 1e-2), (dloss, float(dloss_ref))
+    _report(_grads_by_name(D, dbook, dnames), dref, E2E_BN_TOL, "D step (incl. WGAN-GP double backward)",
+            min_cos=E2E_BN_COS)
+    # spectral-norm state advanced three times (real, fake, xhat) exactly like the oracle's (Q5)
+    assert np.allclose(D.parameters_dict()["body.2.0.weight_u"].numpy(), td["body.2.0.weight_u"].numpy(), atol=1e-4)
+    # ------------------------------------------------ G step
+    tg2 = orc.to_torch({k: v.detach().numpy() for k, v in tg.items()}, requires_grad=("body.2.",))
+    with orc.bf16_emulation():
+        gloss_ref = orc.g_loss(torch.from_numpy(real), torch.from_numpy(real_zero), torch.from_numpy(noise_init), amps,
+                               tg2, {k: v.detach() for k, v in td.items()}, oopt, False,
+                               z_pred=torch.from_numpy(z_pred), noises={k: torch.from_numpy(v) for k, v in nz.items()})
+    gloss_ref.backward()
+    gnames = [k for k, t in tg2.items() if t.requires_grad]
+    gref = {k: tg2[k].grad.numpy() for k in gnames}
+    gl = T.GWithLoss(opt, D, G)
+    gloss, gbook = gl.grad(hp.from_numpy(real), hp.from_numpy(real_zero), hp.from_numpy(noise_init), amps, isVAE=False,
+                           trainable_body=(2,), z_pred=hp.from_numpy(z_pred),
+                           noises={k: hp.from_numpy(v) for k, v in nz.items()})
+    assert abs(gloss - float(gloss_ref)) < 2e-2 * abs(float(gloss_ref)), (gloss, float(gloss_ref))
+    _report(_grads_by_name(G, gbook, gnames), gref, E2E_BN_TOL, "G step (GAN phase)", min_cos=E2E_BN_COS)
+
+
+def test_train_one_step_updates_parameters_like_clipped_adam(hpvg_gpu):
+    hp = hpvg_gpu
+    from hpvg import train as T
+    G, D, opt, oopt, pg, pd, rng = _setup(hp, 3, seed=7)
+    s0, s3 = orc.scale_shape(oopt, 0), orc.scale_shape(oopt, 3)
+    real = np.tanh(rng.standard_normal((1, 3) + s3)).astype(np.float32)
+    real_zero = np.tanh(rng.standard_normal((1, 3) + s0)).astype(np.float32)
+    z_pred = rng.standard_normal((1, 128) + s0).astype(np.float32)
+    noise_init = rng.standard_normal((1, 128) + s0).astype(np.float32)
+    amps = [1.0, 0.0, 0.0, 0.3]
+    nz = {3: rng.standard_normal((1, 3) + s3).astype(np.float32)}
+    block = G.body[-1]
+    groups = [{"params": T.trainable_params(block), "lr": opt.lr_g}]
+    optim = T.ClippedAdam(opt, groups, opt.lr_g, beta1=opt.beta1, beta2=0.999)
+    gl = T.GWithLoss(opt, D, G)
+    step = T.TrainOneStepCell(gl, optim, cells_to_invalidate=[block])
+    step.set_train()
+    before = {k: t.numpy() for k, t in T.trainable_params(block)}
+    loss = step(hp.from_numpy(real), hp.from_numpy(real_zero), hp.from_numpy(noise_init), amps, isVAE=False,
+                trainable_body=(2,), z_pred=hp.from_numpy(z_pred), noises={k: hp.from_numpy(v) for k, v in nz.items()})
+    assert np.isfinite(loss)
+    grads = {k: gl.grads.of(t).numpy() for k, t in T.trainable_params(block)}
+    for k, t in T.trainable_params(block):
+        want, _, _ = orc.adam_step(before[k], orc.clip_by_norm(grads[k], opt.grad_clip), np.zeros_like(before[k]),
+                                   np.zeros_like(before[k]), 1, opt.lr_g, 0.5, 0.999)
+        assert rel_l2(t.numpy(), want) < 1e-5, k
+        assert not np.array_equal(t.numpy(), before[k]) or np.linalg.norm(grads[k]) == 0
