@@ -40,6 +40,10 @@ def parse():
     ap.add_argument("--img-size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-clips", type=int, default=2, help="clips in the bounded CPU-baseline sample")
+    ap.add_argument("--workload", default="sample", choices=["sample", "train"],
+                    help="sample: sampled clips/s (scales over GPUs); train: GAN-phase train iter/s on 1 GPU")
+    ap.add_argument("--train-steps", type=int, default=3, help="train iterations timed for the extra `train` object")
+    ap.add_argument("--no-train", action="store_true", help="skip the extra train-iter/s measurement at N == 1")
     return ap.parse_args()
 
 
@@ -156,6 +160,65 @@ def run_reference(args):
     return 0
 
 
+
+# ------------------------------------------------------------------------------------------------- train iter/s
+def train_iter_bench(hpvg, opt, steps, warmup, st):
+    """One GAN-phase train iteration at the finest scale (train_video.py:170-177): D step (3 D forwards, 2 backwards,
+    WGAN-GP double backward, Adam) + G step (reconstruction forward of the whole pyramid in BatchNorm-train mode,
+    backward of the last stage, random forward + D forward for the loss value, ClippedAdam).  Inputs come from
+    pinned host buffers every iteration (the data loader + host noise of the reference); losses are read back."""
+    from hpvg import networks_3d as n3, train as T, sampling
+    from hpvg.utils import images as uimg
+    G = n3.GeneratorHPVAEGAN(opt, seed=0)
+    for _ in range(opt.stop_scale):
+        G.init_next_stage()
+    D = n3.WDiscriminator3D(opt, rng=np.random.default_rng(1))
+    amps = [1.0] + [0.1] * opt.stop_scale
+    top = uimg.scale_shape(opt, opt.stop_scale)
+    rng = np.random.default_rng(0)
+    shapes = {"real": (1, 3) + top, "real_zero": (1, 3) + uimg.scale_shape(opt, 0), "noise": sampling.z_init_size(opt, 1)}
+    host = {k: hpvg.PinnedBuffer(int(np.prod(v)) * 4) for k, v in shapes.items()}
+    for k, v in shapes.items():
+        a = rng.standard_normal(v).astype(np.float32)
+        host[k].as_array(v)[...] = np.tanh(a) if k != "noise" else a
+    dev = {k: hpvg.Tensor(v, hpvg.F32) for k, v in shapes.items()}
+    block = G.body[-1]
+    optG = T.ClippedAdam(opt, [{"params": T.trainable_params(block), "lr": opt.lr_g}], opt.lr_g, beta1=opt.beta1,
+                         beta2=0.999)
+    optD = T.Adam(T.trainable_params(D), opt.lr_d, beta1=opt.beta1, beta2=0.999)
+    g_step = T.TrainOneStepCell(T.GWithLoss(opt, D, G), optG, cells_to_invalidate=[block])
+    d_step = T.TrainOneStepCell(T.DWithLoss(opt, D, G), optD, cells_to_invalidate=[D])
+    g_step.set_train()
+    d_step.set_train()
+    nb = len(G.body)
+
+    def one_iter():
+        for k in dev:
+            hpvg.lib.hpvg_h2d(dev[k].ptr, host[k].ptr, dev[k].nbytes, st.handle)
+        dl = d_step(dev["real"], dev["noise"], amps, stream=st)
+        gl = g_step(dev["real"], dev["real_zero"], dev["noise"], amps, isVAE=False, trainable_body=(nb - 1,),
+                    stream=st)
+        return dl, gl
+
+    for _ in range(warmup):
+        one_iter()
+    st.sync()
+    l0 = hpvg.lib.hpvg_launch_count()
+    e0, e1 = hpvg.Event(), hpvg.Event()
+    e0.record(st)
+    for _ in range(steps):
+        dl, gl = one_iter()
+    e1.record(st)
+    e1.sync()
+    ms = e0.elapsed_ms(e1) / steps
+    return {"metric": "video train iter/s", "value": 1000.0 / ms, "unit": "iter/s", "ms_per_iter": ms, "steps": steps,
+            "warmup": warmup, "gpu_launches_per_iter": (hpvg.lib.hpvg_launch_count() - l0) // steps,
+            "h2d_bytes_per_iter": int(sum(t.nbytes for t in dev.values())), "last_losses": {"D": dl, "G": gl},
+            "config": {"workload": "train_video.py GAN-phase iteration (D step + G step, train_depth 1) at the finest "
+                                   "scale %dx%dx%d of the full %d-scale pyramid, batch 1, synthetic clip, random-init "
+                                   "weights; host->device copies of the clip/noise and loss read-backs included"
+                                   % (top + (opt.stop_scale + 1,))}}
+
 # ------------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -267,6 +330,15 @@ def run_ours(args):
         "clocks": sampler.summary(),
         "roofline": roofline,
     }
+    if world == 1 and not args.no_train:
+        del net
+        line["train"] = train_iter_bench(hpvg, opt, args.train_steps, 2, st)
+        if args.workload == "train":
+            tr = line["train"]
+            line.update(metric=tr["metric"], value=tr["value"], unit=tr["unit"], ms_per_step=tr["ms_per_iter"],
+                        steps=tr["steps"], warmup=tr["warmup"], scaling="replicas only", config=tr["config"],
+                        e2e={"value": tr["value"], "unit": tr["unit"], "h2d_bytes_per_step": tr["h2d_bytes_per_iter"],
+                             "d2h_bytes_per_step": 8})
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores = cpu_sample_clips({"img_size": args.img_size}, args.cpu_clips)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

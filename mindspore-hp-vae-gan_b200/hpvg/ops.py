@@ -105,7 +105,7 @@ def conv_cl(mode, x_cl, wimg, scale, shift, act=ACT_NONE, out_mode=OUT_BF16_CL, 
         else:
             out = Tensor((N, cout_real, T, H, W), F32)
     in_ptr = ctypes.c_void_p(x_cl.ptr + 2 * in_coff)
-    timed = _prof is not None and _prof["mode"] == mode
+    timed = _prof is not None and (_prof["mode"] == mode or _prof["mode"] is None)
     if timed:
         e0, e1 = rt.Event(), rt.Event()
         e0.record(stream)
@@ -113,7 +113,7 @@ def conv_cl(mode, x_cl, wimg, scale, shift, act=ACT_NONE, out_mode=OUT_BF16_CL, 
                            out_pitch, out_coff, cout_real, _p(addend), _s(stream)), "conv_cl")
     if timed:
         e1.record(stream)
-        _prof["items"].append((N * T * H * W, e0, e1))
+        _prof["items"].append((N * T * H * W, e0, e1) if _prof["mode"] is not None else ((mode, N * T * H * W), e0, e1))
     return out
 
 

@@ -73,10 +73,41 @@ def device_sync():
     check(lib.hpvg_device_sync(), "device_sync")
 
 
+# Caching allocator: cudaMalloc/cudaFree are slow and cudaFree synchronises the device, so freed blocks are kept in
+# size-keyed free lists and reused.  Safe because every consumer enqueues on ONE stream per process (in-order), so a
+# block is never rewritten before earlier kernels that read it have run.
+_POOL = {}
+_POOL_STATS = {"malloc": 0, "reuse": 0}
+
+
+def _pool_alloc(nbytes):
+    size = max(512, (int(nbytes) + 511) // 512 * 512)
+    lst = _POOL.get(size)
+    if lst:
+        _POOL_STATS["reuse"] += 1
+        return lst.pop(), size
+    h = ctypes.c_void_p()
+    check(lib.hpvg_malloc(ctypes.byref(h), size), "malloc")
+    _POOL_STATS["malloc"] += 1
+    return h.value, size
+
+
+def _pool_free(ptr, size):
+    _POOL.setdefault(size, []).append(ptr)
+
+
+def empty_cache():
+    device_sync()
+    for lst in _POOL.values():
+        for ptr in lst:
+            lib.hpvg_free(ctypes.c_void_p(ptr))
+    _POOL.clear()
+
+
 class Tensor:
     """A shaped view of caller-owned device memory.  dtype in {float32, bfloat16, float64, int32}."""
 
-    __slots__ = ("ptr", "shape", "dtype", "_owner", "nbytes")
+    __slots__ = ("ptr", "shape", "dtype", "_owner", "nbytes", "_cap")
 
     def __init__(self, shape, dtype=F32, ptr=None, owner=None):
         self.shape = tuple(int(v) for v in shape)
@@ -85,18 +116,17 @@ class Tensor:
         if ptr is None:
             if not is_initialised():
                 raise HpvgError("hpvg.init() must be called before allocating device memory")
-            h = ctypes.c_void_p()
-            check(lib.hpvg_malloc(ctypes.byref(h), self.nbytes), "malloc")
-            self.ptr = h.value
+            self.ptr, self._cap = _pool_alloc(self.nbytes)
             self._owner = True
         else:
             self.ptr = int(ptr)
+            self._cap = 0
             self._owner = owner   # keeps the parent allocation alive
 
     def __del__(self):
         try:
             if self._owner is True and self.ptr:
-                lib.hpvg_free(ctypes.c_void_p(self.ptr))
+                _pool_free(self.ptr, self._cap)
         except Exception:
             pass
 
