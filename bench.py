@@ -213,7 +213,7 @@ def train_iter_bench(hpvg, opt, steps, warmup, st):
     ms = e0.elapsed_ms(e1) / steps
     return {"metric": "video train iter/s", "value": 1000.0 / ms, "unit": "iter/s", "ms_per_iter": ms, "steps": steps,
             "warmup": warmup, "gpu_launches_per_iter": (hpvg.lib.hpvg_launch_count() - l0) // steps,
-            "h2d_bytes_per_iter": int(sum(t.nbytes for t in dev.values())), "last_losses": {"D": dl, "G": gl},
+            "h2d_bytes_per_iter": int(sum(t.nbytes for t in dev.values())), "last_losses": {"D": float(dl), "G": float(gl)},
             "config": {"workload": "train_video.py GAN-phase iteration (D step + G step, train_depth 1) at the finest "
                                    "scale %dx%dx%d of the full %d-scale pyramid, batch 1, synthetic clip, random-init "
                                    "weights; host->device copies of the clip/noise and loss read-backs included"
@@ -338,7 +338,7 @@ def run_ours(args):
             line.update(metric=tr["metric"], value=tr["value"], unit=tr["unit"], ms_per_step=tr["ms_per_iter"],
                         steps=tr["steps"], warmup=tr["warmup"], scaling="replicas only", config=tr["config"],
                         e2e={"value": tr["value"], "unit": tr["unit"], "h2d_bytes_per_step": tr["h2d_bytes_per_iter"],
-                             "d2h_bytes_per_step": 8})
+                             "d2h_bytes_per_step": 64})
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores = cpu_sample_clips({"img_size": args.img_size}, args.cpu_clips)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

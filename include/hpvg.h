@@ -90,10 +90,13 @@ int hpvg_conv_pack_weights(const float* d_w, int w_cout, int w_cin, int kt, int 
  *  d_in     bf16 cl, in_pitch channels per voxel (the kernel reads 64 — or 8 — channels starting at d_in)
  *  d_scale/d_shift fp32 [Cout]: bias, folded BatchNorm, 1/sigma of spectral norm
  *  d_addend HPVG_OUT_BF16_CL: optional fp32 [voxels][64] partial sums (split-Cin accumulation)
- *           HPVG_OUT_F32_NCDHW: optional fp32 ncdhw residual (tanh(block(x)+up), networks_3d.py:450)            */
+ *           HPVG_OUT_F32_NCDHW: optional fp32 ncdhw residual (tanh(block(x)+up), networks_3d.py:450)
+ *  d_stats  optional fp64 [2][64] (HPVG_OUT_BF16_CL, 64 output channels): += per-channel sum / sum of squares of the
+ *           stored output — the batch statistics of a following training-mode BatchNorm3d (networks_3d.py:52),
+ *           fused into the conv epilogue.  The caller zeroes it.                                                  */
 int hpvg_conv_cl(int mode, int N, int T, int H, int W, const void* d_in, int in_pitch, const void* d_wimg,
                  const float* d_scale, const float* d_shift, int act, int out_mode, void* d_out, int out_pitch,
-                 int out_coff, int cout_real, const float* d_addend, void* stream);
+                 int out_coff, int cout_real, const float* d_addend, double* d_stats, void* stream);
 
 /* ---------------------------------------------------------------- linear resize
  * Replaces UpsampleTrilinear3D(output_size, align_corners) (src/tools/trilinear.py:171-254, called from
@@ -126,11 +129,26 @@ int hpvg_bn_finalize(const double* d_sum, const double* d_sumsq, long long count
 int hpvg_bn_apply_lrelu_cl(const void* d_y, long long voxels, const float* d_scale, const float* d_shift, int act,
                            void* d_x, void* stream);
 
+/* one-pass training-mode BatchNorm: d_sums = the fp64 [2][64] statistics produced by hpvg_conv_cl(d_stats=...);
+ * finalises (scale, shift), updates the moving statistics, writes d_saved = (scale, shift, mean, invstd) [4][64]
+ * (nullable) and x = act(y*scale + shift) in a single launch. */
+int hpvg_bn_train_apply_cl(const void* d_y, long long voxels, const double* d_sums, const float* d_gamma,
+                           const float* d_beta, float eps, float momentum, float* d_moving_mean, float* d_moving_var,
+                           float* d_saved, int act, void* d_x, void* stream);
+
 /* ---------------------------------------------------------------- spectral norm (spectral_norm.py:142-151)
  * One power iteration on W viewed (Cout, K): v <- l2n(W^T u); u <- l2n(W v); sigma = u^T W v.
  * Updates d_u, d_v in place and writes sigma and 1/sigma. */
 int hpvg_sn_power_iter(const float* d_w, int cout, int k, float* d_u, float* d_v, float* d_sigma,
                        float* d_inv_sigma, void* stream);
+
+/* the same for every spectrally normalised layer of a network in ONE launch (arrays live on the host, <= 16 layers);
+ * d_sigma2[i] -> 2 floats (sigma, 1/sigma); d_aff[i] (nullable array / entries) -> [2][64] conv epilogue vectors
+ * (scale = 1/sigma, shift = bias); d_u_copy / d_v_copy (nullable) receive a snapshot of the updated u / v, which
+ * the backward of THIS pass needs because u, v advance on every forward (spectral_norm.py:146-148). */
+int hpvg_sn_power_iter_multi(int n_layers, const float* const* d_w, const int* cout, const int* k, float* const* d_u,
+                             float* const* d_v, float* const* d_sigma2, const float* const* d_bias,
+                             float* const* d_aff, float* const* d_u_copy, float* const* d_v_copy, void* stream);
 
 /* ---------------------------------------------------------------- small fused elementwise / reductions */
 /* scale[c] = a[c]*mul ; shift[c] = b[c]  helpers for epilogue vectors */

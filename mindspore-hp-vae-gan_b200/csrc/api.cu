@@ -20,6 +20,7 @@ std::atomic<long long> g_launches{0};
 float* g_adam_norms = nullptr;
 float* g_wgrad_ws = nullptr;   // [sm/3][27][64][64] partial weight gradients
 double* g_sums = nullptr;      // [128] reduction scratch (BatchNorm backward, column sums)
+float* g_fscratch = nullptr;   // [256] fp32 scratch (spectral-norm gradient partial dots)
 int g_sm_count = 0;
 
 int fail(int code, const std::string& msg) {
@@ -69,6 +70,7 @@ int hpvg_init(int device) {
   if (!g_adam_norms) CU(cudaMalloc(&g_adam_norms, hpvg::ADAM_MAX_TENSORS * sizeof(float)));
   if (!g_wgrad_ws) CU(cudaMalloc(&g_wgrad_ws, hpvg::conv3d_wgrad_workspace_bytes(g_sm_count)));
   if (!g_sums) CU(cudaMalloc(&g_sums, 128 * sizeof(double)));
+  if (!g_fscratch) CU(cudaMalloc(&g_fscratch, 256 * sizeof(float)));
   return HPVG_OK;
 }
 int hpvg_sm_count(void) { return g_sm_count; }
@@ -203,12 +205,14 @@ int hpvg_conv_pack_weights(const float* w, int w_cout, int w_cin, int kt, int mo
 
 int hpvg_conv_cl(int mode, int N, int T, int H, int W, const void* in, int in_pitch, const void* wimg,
                  const float* scale, const float* shift, int act, int out_mode, void* out, int out_pitch,
-                 int out_coff, int cout_real, const float* addend, void* st) {
+                 int out_coff, int cout_real, const float* addend, double* stats, void* st) {
   if (N <= 0 || T <= 0 || H <= 0 || W <= 0) return HPVG_OK;  // empty input: nothing to do
   if (!in || !wimg || !scale || !shift || !out) return fail(HPVG_E_ARG, "conv_cl: null pointer");
   if (out_mode == HPVG_OUT_BF16_CL && ((out_pitch & 7) || (out_coff & 7)))
     return fail(HPVG_E_ARG, "conv_cl: out_pitch/out_coff must be multiples of 8");
   if (g_sm_count == 0) return fail(HPVG_E_ARG, "hpvg_init was not called");
+  if (stats && (mode == HPVG_CONV_64_16 || out_mode != HPVG_OUT_BF16_CL))
+    return fail(HPVG_E_ARG, "conv_cl: fused BatchNorm statistics need a 64-channel bf16 output");
   hpvg::ConvLaunch L;
   L.mode = mode;
   L.N = N; L.T = T; L.H = H; L.W = W;
@@ -217,6 +221,7 @@ int hpvg_conv_cl(int mode, int N, int T, int H, int W, const void* in, int in_pi
   L.act = act; L.out_mode = out_mode;
   L.out = out; L.out_pitch = out_pitch; L.out_coff = out_coff; L.cout_real = cout_real;
   L.addend = addend;
+  L.stats = stats;
   L.max_pairs = g_sm_count / 2;
   const char* e = hpvg::conv3d_umma_launch(L, S(st));
   if (e) return fail(HPVG_E_CUDA, std::string("conv_cl: ") + e);
@@ -281,7 +286,36 @@ int hpvg_bn_apply_lrelu_cl(const void* y, long long voxels, const float* scale, 
   return HPVG_OK;
 }
 
+int hpvg_bn_train_apply_cl(const void* y, long long voxels, const double* sums, const float* gamma, const float* beta,
+                           float eps, float momentum, float* mm, float* mv, float* saved, int act, void* x, void* st) {
+  if (voxels <= 0) return fail(HPVG_E_ARG, "bn_train_apply: empty batch");
+  if (!y || !sums || !gamma || !beta || !x) return fail(HPVG_E_ARG, "bn_train_apply: null pointer");
+  KL(hpvg::ew_bn_train_apply_cl(static_cast<const __nv_bfloat16*>(y), voxels, sums, gamma, beta, eps, momentum, mm, mv,
+                                saved, act, static_cast<__nv_bfloat16*>(x), S(st)), 1);
+  return HPVG_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ spectral norm
+int hpvg_sn_power_iter_multi(int n_layers, const float* const* w, const int* cout, const int* k, float* const* u,
+                             float* const* v, float* const* sigma2, const float* const* bias, float* const* aff,
+                             float* const* u_copy, float* const* v_copy, void* st) {
+  if (n_layers < 1 || n_layers > hpvg::SN_MAX_LAYERS)
+    return fail(HPVG_E_ARG, "sn_power_iter_multi: 1..16 layers per call");
+  hpvg::SnTable tab;
+  std::memset(&tab, 0, sizeof(tab));
+  for (int i = 0; i < n_layers; ++i) {
+    if (cout[i] <= 0 || k[i] <= 0 || (2 * cout[i] + k[i]) * 4 > 48 * 1024)
+      return fail(HPVG_E_ARG, "sn_power_iter_multi: matrix too large for the single-CTA kernel");
+    tab.w[i] = w[i]; tab.u[i] = u[i]; tab.v[i] = v[i]; tab.sigma[i] = sigma2[i];
+    tab.bias[i] = bias ? bias[i] : nullptr;
+    tab.aff[i] = aff ? aff[i] : nullptr;
+    tab.u_copy[i] = u_copy ? u_copy[i] : nullptr;
+    tab.v_copy[i] = v_copy ? v_copy[i] : nullptr;
+    tab.cout[i] = cout[i]; tab.k[i] = k[i];
+  }
+  KL(hpvg::ew_sn_power_iter_multi(tab, n_layers, S(st)), 1);
+  return HPVG_OK;
+}
 int hpvg_sn_power_iter(const float* w, int cout, int k, float* u, float* v, float* sigma, float* inv_sigma,
                        void* st) {
   if (cout <= 0 || k <= 0 || (2 * cout + k) * 4 > 48 * 1024)
@@ -404,7 +438,9 @@ int hpvg_fill(float* y, float v, long long n, void* st) {
 }
 int hpvg_channel_sum(const float* g, int N, int C, long long sp, int accumulate, float* out, void* st) {
   if (N <= 0 || C <= 0 || sp <= 0) return fail(HPVG_E_ARG, "channel_sum: empty input");
-  KL(hpvg::ew_channel_sum_ncdhw(g, N, C, sp, accumulate, out, S(st)), 1);
+  if (!g_sums) return fail(HPVG_E_ARG, "hpvg_init was not called");
+  if (C > 128) return fail(HPVG_E_ARG, "channel_sum: at most 128 channels");
+  KL(hpvg::ew_channel_sum_ncdhw(g, N, C, sp, accumulate, g_sums, out, S(st)), 2);
   return HPVG_OK;
 }
 int hpvg_kl_grad(const float* mu, const float* lv, long long n, float coef, float* gmu, float* glv, void* st) {
@@ -415,7 +451,8 @@ int hpvg_kl_grad(const float* mu, const float* lv, long long n, float coef, floa
 int hpvg_sn_grad(const float* G, const float* w, const float* u, const float* v, const float* sigma, int cout, int k,
                  int accumulate, float* gw, void* st) {
   if (cout <= 0 || k <= 0) return fail(HPVG_E_ARG, "sn_grad: empty matrix");
-  KL(hpvg::ew_sn_grad(G, w, u, v, sigma, cout, k, accumulate, gw, S(st)), 1);
+  if (!g_fscratch) return fail(HPVG_E_ARG, "hpvg_init was not called");
+  KL(hpvg::ew_sn_grad(G, w, u, v, sigma, cout, k, accumulate, g_fscratch, gw, S(st)), 2);
   return HPVG_OK;
 }
 int hpvg_lerp(const float* a, const float* b, float alpha, long long n, float* out, void* st) {
@@ -471,7 +508,7 @@ int HpvgConv3dBiasLRelu(int nparam, void** params, int* ndims, int64_t** shapes,
                                        64, wimg, stream);
   if (!rc) rc = hpvg_affine_from_bias(static_cast<const float*>(params[2]), nullptr, 64, scale, scale + 64, stream);
   if (!rc) rc = hpvg_conv_cl(HPVG_CONV_64_64, N, T, H, W, xcl, 64, wimg, scale, scale + 64, HPVG_ACT_LRELU,
-                             HPVG_OUT_BF16_CL, ycl, 64, 0, 64, nullptr, stream);
+                             HPVG_OUT_BF16_CL, ycl, 64, 0, 64, nullptr, nullptr, stream);
   if (!rc) rc = hpvg_unpack_cl(ycl, N, 64, T, H, W, 64, 0, static_cast<float*>(params[3]), stream);
   cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
   cudaFree(xcl); cudaFree(ycl); cudaFree(wimg); cudaFree(scale);

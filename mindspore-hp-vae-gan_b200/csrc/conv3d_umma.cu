@@ -22,6 +22,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "conv3d_umma.h"
 #include "ptx.cuh"
 
@@ -88,7 +90,75 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-template <int MODE>
+// One accumulator row (64 fp32 channels in r0|r1) -> affine -> activation -> 128 bytes of bf16.  The activation and
+// the presence of an addend are compile-time so the 64-element body is branch-free straight-line code (the runtime
+// switch sits outside, once per plane).  KEEP: write the bf16-rounded results back into r0/r1 as fp32 bit patterns
+// (input of the fused BatchNorm statistics).
+template <int ACT, bool ADD, bool KEEP>
+__device__ __forceinline__ void epilogue_bf16_row(uint32_t (&r0)[32], uint32_t (&r1)[32], const float* scale_sm,
+                                                  const float* shift_sm, const float* __restrict__ add,
+                                                  __nv_bfloat16* __restrict__ dst) {
+  const float4* sc4 = reinterpret_cast<const float4*>(scale_sm);
+  const float4* sh4 = reinterpret_cast<const float4*>(shift_sm);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t* r = half ? r1 : r0;
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) {
+      const int cb = half * 32 + c8 * 8;
+      const float4 sa = sc4[cb / 4], sb = sc4[cb / 4 + 1], ha = sh4[cb / 4], hb = sh4[cb / 4 + 1];
+      const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+      const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+      float ad[8];
+      if constexpr (ADD) {
+        const float4 a0 = *reinterpret_cast<const float4*>(add + cb), a1 = *reinterpret_cast<const float4*>(add + cb + 4);
+        ad[0] = a0.x; ad[1] = a0.y; ad[2] = a0.z; ad[3] = a0.w;
+        ad[4] = a1.x; ad[5] = a1.y; ad[6] = a1.z; ad[7] = a1.w;
+      }
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float a = __uint_as_float(r[c8 * 8 + e]);
+        if constexpr (ADD) a += ad[e];
+        a = fmaf(a, sc[e], sh[e]);
+        if constexpr (ACT == CONV_ACT_LRELU) a = fmaxf(a, 0.2f * a);   // == a > 0 ? a : 0.2a
+        if constexpr (ACT == CONV_ACT_TANH) a = tanhf(a);
+        v[e] = a;
+      }
+      uint4 pk;
+      pk.x = pack_bf16x2(v[0], v[1]);
+      pk.y = pack_bf16x2(v[2], v[3]);
+      pk.z = pack_bf16x2(v[4], v[5]);
+      pk.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(dst + cb) = pk;
+      if constexpr (KEEP) {
+        const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+          r[c8 * 8 + 2 * e2] = pw[e2] << 16;
+          r[c8 * 8 + 2 * e2 + 1] = pw[e2] & 0xFFFF0000u;
+        }
+      }
+    }
+  }
+}
+
+template <bool KEEP>
+__device__ __forceinline__ void epilogue_bf16_dispatch(int act, uint32_t (&r0)[32], uint32_t (&r1)[32],
+                                                       const float* scale_sm, const float* shift_sm,
+                                                       const float* __restrict__ add, __nv_bfloat16* __restrict__ dst) {
+  if (add) {   // split-Cin accumulation (128 -> 64 layers): rare
+    if (act == CONV_ACT_LRELU) epilogue_bf16_row<CONV_ACT_LRELU, true, KEEP>(r0, r1, scale_sm, shift_sm, add, dst);
+    else if (act == CONV_ACT_TANH) epilogue_bf16_row<CONV_ACT_TANH, true, KEEP>(r0, r1, scale_sm, shift_sm, add, dst);
+    else epilogue_bf16_row<CONV_ACT_NONE, true, KEEP>(r0, r1, scale_sm, shift_sm, add, dst);
+  } else {
+    if (act == CONV_ACT_LRELU) epilogue_bf16_row<CONV_ACT_LRELU, false, KEEP>(r0, r1, scale_sm, shift_sm, add, dst);
+    else if (act == CONV_ACT_TANH) epilogue_bf16_row<CONV_ACT_TANH, false, KEEP>(r0, r1, scale_sm, shift_sm, add, dst);
+    else epilogue_bf16_row<CONV_ACT_NONE, false, KEEP>(r0, r1, scale_sm, shift_sm, add, dst);
+  }
+}
+
+template <int MODE, bool STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ConvParams p) {
   using C = Cfg<MODE>;
@@ -166,7 +236,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
           uint32_t dst_bar = leader_full[0];
 #pragma unroll
           for (int i = 1; i < C::SLOTS; ++i) dst_bar = (slot == static_cast<uint32_t>(i)) ? leader_full[i] : dst_bar;
-          tma_load_5d_pair(planes + slot * C::SLOT_STRIDE, &tmap_in, dst_bar, 0, un.w0 - 1, un.h0 - 1, t, un.n);
+          if (MODE == CONV_MODE_8_64 && p.in_merged)   // (C, W) merged into one 160-byte box row
+            tma_load_5d_pair(planes + slot * C::SLOT_STRIDE, &tmap_in, dst_bar, (un.w0 - 1) * 8, un.h0 - 1, t, un.n, 0);
+          else
+            tma_load_5d_pair(planes + slot * C::SLOT_STRIDE, &tmap_in, dst_bar, 0, un.w0 - 1, un.h0 - 1, t, un.n);
         }
       }
     }
@@ -252,6 +325,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
     leader_empty[0] = map_to_cta(smem_u32(&acc_empty[0]), 0);
     leader_empty[1] = map_to_cta(smem_u32(&acc_empty[1]), 0);
     uint32_t q = 0;
+    float st_s0 = 0.f, st_s1 = 0.f, st_q0 = 0.f, st_q1 = 0.f;   // BatchNorm partial sums of channels 2*lane, 2*lane+1
     for (int u = pair; u < p.n_units; u += n_pairs) {
       const Unit un = decode_unit(u, p, rank);
       const int h = un.h0 + hh, w = un.w0 + ww;
@@ -269,43 +343,67 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(leader_empty[ab]);
-          if (inb) {
-            if (p.out_mode == CONV_OUT_F32_RAW) {
-              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + vox * 64);
+          if (lane == 0) mbar_arrive_cluster_relaxed(leader_empty[ab]);
+          if constexpr (!STATS) {
+            if (inb) {
+              if (p.out_mode == CONV_OUT_F32_RAW) {
+                float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + vox * 64);
 #pragma unroll
-              for (int c = 0; c < 8; ++c)
-                dst[c] = make_float4(__uint_as_float(r0[4 * c]), __uint_as_float(r0[4 * c + 1]),
-                                     __uint_as_float(r0[4 * c + 2]), __uint_as_float(r0[4 * c + 3]));
+                for (int c = 0; c < 8; ++c)
+                  dst[c] = make_float4(__uint_as_float(r0[4 * c]), __uint_as_float(r0[4 * c + 1]),
+                                       __uint_as_float(r0[4 * c + 2]), __uint_as_float(r0[4 * c + 3]));
 #pragma unroll
-              for (int c = 0; c < 8; ++c)
-                dst[8 + c] = make_float4(__uint_as_float(r1[4 * c]), __uint_as_float(r1[4 * c + 1]),
-                                         __uint_as_float(r1[4 * c + 2]), __uint_as_float(r1[4 * c + 3]));
-            } else {
-              const float* add = p.addend ? p.addend + vox * 64 : nullptr;
-              __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + vox * p.out_pitch + p.out_coff;
-#pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                const uint32_t* r = half ? r1 : r0;
-#pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8) {
-                  float v[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    const int c = half * 32 + c8 * 8 + e;
-                    float a = __uint_as_float(r[c8 * 8 + e]);
-                    if (add) a += add[c];
-                    v[e] = apply_act(fmaf(a, scale_sm[c], shift_sm[c]), p.act);
-                  }
-                  uint4 pk;
-                  pk.x = pack_bf16x2(v[0], v[1]);
-                  pk.y = pack_bf16x2(v[2], v[3]);
-                  pk.z = pack_bf16x2(v[4], v[5]);
-                  pk.w = pack_bf16x2(v[6], v[7]);
-                  *reinterpret_cast<uint4*>(dst + half * 32 + c8 * 8) = pk;
-                }
+                for (int c = 0; c < 8; ++c)
+                  dst[8 + c] = make_float4(__uint_as_float(r1[4 * c]), __uint_as_float(r1[4 * c + 1]),
+                                           __uint_as_float(r1[4 * c + 2]), __uint_as_float(r1[4 * c + 3]));
+              } else {
+                const float* add = p.addend ? p.addend + vox * 64 : nullptr;
+                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + vox * p.out_pitch + p.out_coff;
+                epilogue_bf16_dispatch<false>(p.act, r0, r1, scale_sm, shift_sm, add, dst);
               }
             }
+          } else {
+            // bf16 output + BatchNorm batch statistics (sum, sum of squares of the values AS STORED, i.e. bf16-rounded)
+            if (inb) {
+              const float* add = p.addend ? p.addend + vox * 64 : nullptr;
+              __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + vox * p.out_pitch + p.out_coff;
+              epilogue_bf16_dispatch<true>(p.act, r0, r1, scale_sm, shift_sm, add, dst);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r0[i] = r1[i] = 0u;
+            }
+            // per-channel sums over the 32 voxels of this warp: a butterfly that halves the channel set at every
+            // step (62 shuffles per statistic instead of 320); lane L ends up with channels 2L, 2L+1.
+            float s[32], sq[32];
+            const bool up16 = lane & 16;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float lo = __uint_as_float(r0[i]), hi = __uint_as_float(r1[i]);
+              const float keep = up16 ? hi : lo, send = up16 ? lo : hi;
+              const float got = __shfl_xor_sync(0xffffffffu, send, 16);
+              const float gq = __shfl_xor_sync(0xffffffffu, send * send, 16);
+              s[i] = keep + got;
+              sq[i] = fmaf(keep, keep, gq);
+            }
+#define HPVG_BFLY(M_, N_)                                                              \
+  {                                                                                    \
+    const bool upm = lane & (M_);                                                      \
+    _Pragma("unroll") for (int i = 0; i < (N_); ++i) {                                 \
+      const float ks = upm ? s[(N_) + i] : s[i], ss = upm ? s[i] : s[(N_) + i];        \
+      const float kq = upm ? sq[(N_) + i] : sq[i], sx = upm ? sq[i] : sq[(N_) + i];    \
+      s[i] = ks + __shfl_xor_sync(0xffffffffu, ss, (M_));                              \
+      sq[i] = kq + __shfl_xor_sync(0xffffffffu, sx, (M_));                             \
+    }                                                                                  \
+  }
+            HPVG_BFLY(8, 16)
+            HPVG_BFLY(4, 8)
+            HPVG_BFLY(2, 4)
+            HPVG_BFLY(1, 2)
+#undef HPVG_BFLY
+            st_s0 += s[0];
+            st_s1 += s[1];
+            st_q0 += sq[0];
+            st_q1 += sq[1];
           }
         } else {
           uint32_t r[16];
@@ -313,24 +411,48 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(leader_empty[ab]);
+          if (lane == 0) mbar_arrive_cluster_relaxed(leader_empty[ab]);
           if (inb) {
             // fp32 NCDHW, cout_real channels: out[n][c][t][h][w] = act(acc*scale + shift (+ residual))
             const size_t plane_sz = static_cast<size_t>(p.H) * p.W;
             const size_t sp = (static_cast<size_t>(pl) * p.H + h) * p.W + w;
             const size_t chan_sz = plane_sz * T;
             float* out = static_cast<float*>(p.out);
+            float v[4];
+            size_t idx[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              if (c < p.cout_real) {
-                const size_t idx = (static_cast<size_t>(un.n) * p.cout_real + c) * chan_sz + sp;
-                float v = fmaf(__uint_as_float(r[c]), scale_sm[c], shift_sm[c]);
-                if (p.addend) v += p.addend[idx];
-                out[idx] = apply_act(v, p.act);
-              }
+              idx[c] = (static_cast<size_t>(un.n) * p.cout_real + c) * chan_sz + sp;
+              v[c] = fmaf(__uint_as_float(r[c]), scale_sm[c], shift_sm[c]);
+              if (p.addend && c < p.cout_real) v[c] += p.addend[idx[c]];
             }
+            if (p.act == CONV_ACT_TANH) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) v[c] = tanhf(v[c]);
+            } else if (p.act == CONV_ACT_LRELU) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) v[c] = v[c] > 0.f ? v[c] : 0.2f * v[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (c < p.cout_real) out[idx[c]] = v[c];
           }
         }
+      }
+    }
+    if constexpr (STATS) {
+      {
+        // all MMAs of this pair have completed (the last acc_full fired), so the plane ring is free: use it to combine
+        // the 4 epilogue warps, then one fp64 atomic per channel and statistic per CTA.
+        float* red = reinterpret_cast<float*>(planes);   // [4 warps][2 stats][64 ch]
+        red[(quad * 2 + 0) * 64 + 2 * lane] = st_s0;
+        red[(quad * 2 + 0) * 64 + 2 * lane + 1] = st_s1;
+        red[(quad * 2 + 1) * 64 + 2 * lane] = st_q0;
+        red[(quad * 2 + 1) * 64 + 2 * lane + 1] = st_q1;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int t = threadIdx.x - 64;   // 0..127 : statistic (t >> 6), channel (t & 63)
+        const float tot = red[t] + red[128 + t] + red[256 + t] + red[384 + t];
+        atomicAdd(p.stats + t, static_cast<double>(tot));
       }
     }
   }
@@ -361,17 +483,17 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-template <int MODE>
+template <int MODE, bool STATS>
 cudaError_t launch_mode(const CUtensorMap& tmap, const ConvParams& prm, int n_pairs, cudaStream_t stream) {
   static bool configured = false;
   constexpr int smem = smem_bytes_for<MODE>();
   if (!configured) {
     cudaError_t e =
-        cudaFuncSetAttribute(conv3d_umma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(conv3d_umma_kernel<MODE, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  conv3d_umma_kernel<MODE><<<dim3(2 * n_pairs), dim3(NUM_THREADS), smem, stream>>>(tmap, prm);
+  conv3d_umma_kernel<MODE, STATS><<<dim3(2 * n_pairs), dim3(NUM_THREADS), smem, stream>>>(tmap, prm);
   return cudaGetLastError();
 }
 
@@ -391,6 +513,15 @@ const char* conv3d_umma_launch(const ConvLaunch& L, cudaStream_t stream) {
   cuuint64_t gs[4] = {vox, vox * L.W, vox * L.W * L.H, vox * L.W * L.H * L.T};
   cuuint32_t bx[5] = {static_cast<cuuint32_t>(cin_box), BOX_W, BOX_H, 1, 1};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  // head convs on a densely packed 8-channel tensor: voxels of an image row are contiguous, so (C, W) merge into one
+  // dimension and every box row becomes ONE 160-byte request instead of ten 16-byte ones
+  static const bool no_merge = getenv("HPVG_NO_MERGE") != nullptr;
+  const bool merged = (L.mode == CONV_MODE_8_64 && cin_pitch == 8 && !no_merge);
+  if (merged) {
+    gd[0] = 8ull * L.W; gd[1] = L.H; gd[2] = L.T; gd[3] = L.N; gd[4] = 1;
+    gs[0] = vox * L.W; gs[1] = vox * L.W * L.H; gs[2] = vox * L.W * L.H * L.T; gs[3] = vox * L.W * L.H * L.T * L.N;
+    bx[0] = 8 * BOX_W; bx[1] = BOX_H; bx[2] = 1; bx[3] = 1; bx[4] = 1;
+  }
   CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(L.in), gd, gs, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE,
                    L.mode == CONV_MODE_8_64 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
@@ -416,21 +547,28 @@ const char* conv3d_umma_launch(const ConvLaunch& L, cudaStream_t stream) {
   prm.out_coff = L.out_coff;
   prm.cout_real = L.cout_real;
   prm.addend = L.addend;
+  prm.stats = L.stats;
+  prm.in_merged = merged ? 1 : 0;
   int n_pairs = prm.n_units < L.max_pairs ? prm.n_units : L.max_pairs;
   if (n_pairs < 1) return nullptr;
   cudaError_t e;
   switch (L.mode) {
     case CONV_MODE_64_64:
       if (L.out_mode != CONV_OUT_BF16_NDHWC && L.out_mode != CONV_OUT_F32_RAW) return "bad out_mode for 64->64";
-      e = launch_mode<CONV_MODE_64_64>(tmap, prm, n_pairs, stream);
+      if (L.stats && L.out_mode != CONV_OUT_BF16_NDHWC) return "fused statistics need the bf16 output mode";
+      e = L.stats ? launch_mode<CONV_MODE_64_64, true>(tmap, prm, n_pairs, stream)
+                  : launch_mode<CONV_MODE_64_64, false>(tmap, prm, n_pairs, stream);
       break;
     case CONV_MODE_64_16:
       if (L.out_mode != CONV_OUT_F32_NCDHW || L.cout_real > 4) return "bad out_mode for 64->16";
-      e = launch_mode<CONV_MODE_64_16>(tmap, prm, n_pairs, stream);
+      if (L.stats) return "fused statistics need a 64-channel output";
+      e = launch_mode<CONV_MODE_64_16, false>(tmap, prm, n_pairs, stream);
       break;
     case CONV_MODE_8_64:
       if (L.out_mode != CONV_OUT_BF16_NDHWC && L.out_mode != CONV_OUT_F32_RAW) return "bad out_mode for 8->64";
-      e = launch_mode<CONV_MODE_8_64>(tmap, prm, n_pairs, stream);
+      if (L.stats && L.out_mode != CONV_OUT_BF16_NDHWC) return "fused statistics need the bf16 output mode";
+      e = L.stats ? launch_mode<CONV_MODE_8_64, true>(tmap, prm, n_pairs, stream)
+                  : launch_mode<CONV_MODE_8_64, false>(tmap, prm, n_pairs, stream);
       break;
     default:
       return "unknown conv mode";

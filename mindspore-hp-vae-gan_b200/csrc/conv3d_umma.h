@@ -24,6 +24,9 @@ struct ConvParams {
   int cout_real;         // CONV_OUT_F32_NCDHW: number of real output channels (<= 4)
   const float* addend;   // bf16 out: fp32 [V][64] partial sums added before scale/shift (split-Cin);
                          // NCDHW out: fp32 NCDHW residual added after scale/shift, before the activation
+  int in_merged;         // head variant: the tensor map has (C, W) merged (densely packed 8-channel input)
+  double* stats;         // bf16 out, Cout 64: optional [2][64] fp64 accumulators (+= sum y, sum y^2 over all voxels of
+                         // the stored output): the training-mode BatchNorm statistics, fused into the epilogue
 };
 
 // host-side launch description
@@ -39,6 +42,7 @@ struct ConvLaunch {
   void* out;
   int out_pitch, out_coff, cout_real;
   const float* addend;
+  double* stats;
   int max_pairs;         // CTA pairs to launch (<= 74 on a 148-SM B200)
 };
 

@@ -371,6 +371,60 @@ __global__ void bn_apply_cl_kernel(const __nv_bfloat16* __restrict__ y, long lon
   }
 }
 
+// Training-mode BatchNorm in ONE pass over the data: the per-channel sums come from the producing conv's epilogue
+// (conv3d_umma.cu), every block redoes the 64-channel finalisation (cheaper than a separate launch), block 0 also
+// writes the saved (scale, shift, mean, invstd) vectors for the backward and updates the moving statistics.
+__global__ void bn_train_apply_cl_kernel(const __nv_bfloat16* __restrict__ y, long long groups /*voxels*8*/,
+                                         const double* __restrict__ sums /*[2][64]*/, double count,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                         float momentum, float* __restrict__ mm, float* __restrict__ mv,
+                                         float* __restrict__ saved /*[4][64], nullable*/, int act,
+                                         __nv_bfloat16* __restrict__ x) {
+  __shared__ float sc[64], sh[64];
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x;
+    const double mean = sums[c] / count;
+    double var = sums[64 + c] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float s = gamma[c] * invstd;
+    const float b = beta[c] - static_cast<float>(mean) * s;
+    sc[c] = s;
+    sh[c] = b;
+    if (blockIdx.x == 0) {
+      if (saved) {
+        saved[c] = s;
+        saved[64 + c] = b;
+        saved[128 + c] = static_cast<float>(mean);
+        saved[192 + c] = invstd;
+      }
+      if (mm) mm[c] = momentum * mm[c] + (1.f - momentum) * static_cast<float>(mean);
+      if (mv) mv[c] = momentum * mv[c] + (1.f - momentum) * static_cast<float>(var);
+    }
+  }
+  __syncthreads();
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < groups;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i & 7);
+    const uint4 pk = *reinterpret_cast<const uint4*>(y + i * 8);
+    const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e2 = 0; e2 < 4; ++e2) {
+      float2 f = unpack2(w[e2]);
+      const int c = g * 8 + 2 * e2;
+      f.x = fmaf(f.x, sc[c], sh[c]);
+      f.y = fmaf(f.y, sc[c + 1], sh[c + 1]);
+      if (act == 1) {
+        f.x = f.x > 0.f ? f.x : 0.2f * f.x;
+        f.y = f.y > 0.f ? f.y : 0.2f * f.y;
+      }
+      o[e2] = pack2(f.x, f.y);
+    }
+    *reinterpret_cast<uint4*>(x + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // ----------------------------------------------------------------------------------------------- spectral norm
 // One CTA.  W: (cout, k) fp32 row-major (the (Cout, Cin*27) view of spectral_norm.py:146).
 __device__ __forceinline__ float block_sum(float v, float* red) {
@@ -385,13 +439,13 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
-__global__ void sn_power_iter_kernel(const float* __restrict__ w, int cout, int k, float* __restrict__ u,
-                                     float* __restrict__ v, float* __restrict__ sigma, float* __restrict__ inv_sigma) {
-  extern __shared__ float sm[];
+__device__ void sn_power_iter_body(const float* __restrict__ w, int cout, int k, float* __restrict__ u,
+                                   float* __restrict__ v, float* __restrict__ sigma, float* __restrict__ inv_sigma,
+                                   const float* __restrict__ bias, float* __restrict__ aff /*[2][64] nullable*/,
+                                   float* __restrict__ u_copy, float* __restrict__ v_copy, float* sm, float* red) {
   float* su = sm;            // [cout]
   float* sv = su + cout;     // [k]
   float* swv = sv + k;       // [cout]
-  __shared__ float red[32];
   for (int i = threadIdx.x; i < cout; i += blockDim.x) su[i] = u[i];
   __syncthreads();
   // v = l2normalize(W^T u)
@@ -407,6 +461,7 @@ __global__ void sn_power_iter_kernel(const float* __restrict__ w, int cout, int 
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
     sv[j] *= inv;
     v[j] = sv[j];
+    if (v_copy) v_copy[j] = sv[j];
   }
   __syncthreads();
   // Wv (one warp per output row, strided over rows)
@@ -428,6 +483,7 @@ __global__ void sn_power_iter_kernel(const float* __restrict__ w, int cout, int 
   for (int i = threadIdx.x; i < cout; i += blockDim.x) {
     const float un = swv[i] * inv;
     u[i] = un;
+    if (u_copy) u_copy[i] = un;
     part = fmaf(un, swv[i], part);
   }
   const float sg = block_sum(part, red);
@@ -435,6 +491,27 @@ __global__ void sn_power_iter_kernel(const float* __restrict__ w, int cout, int 
     sigma[0] = sg;
     inv_sigma[0] = 1.0f / sg;
   }
+  if (aff && threadIdx.x < 64) {   // conv epilogue vectors: scale = 1/sigma, shift = bias
+    aff[threadIdx.x] = 1.0f / sg;
+    aff[64 + threadIdx.x] = (bias && threadIdx.x < cout) ? bias[threadIdx.x] : 0.f;
+  }
+}
+
+__global__ void sn_power_iter_kernel(const float* __restrict__ w, int cout, int k, float* __restrict__ u,
+                                     float* __restrict__ v, float* __restrict__ sigma,
+                                     float* __restrict__ inv_sigma) {
+  extern __shared__ float sm[];
+  __shared__ float red[32];
+  sn_power_iter_body(w, cout, k, u, v, sigma, inv_sigma, nullptr, nullptr, nullptr, nullptr, sm, red);
+}
+
+// all spectrally normalised layers of a network in one launch: block b = layer b
+__global__ void sn_power_iter_multi_kernel(const SnTable tab) {
+  extern __shared__ float sm[];
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  sn_power_iter_body(tab.w[b], tab.cout[b], tab.k[b], tab.u[b], tab.v[b], tab.sigma[b], tab.sigma[b] + 1, tab.bias[b],
+                     tab.aff[b], tab.u_copy[b], tab.v_copy[b], sm, red);
 }
 
 // ----------------------------------------------------------------------------------------------- epilogue vectors
@@ -483,39 +560,71 @@ __global__ void reparam_kernel(const float* __restrict__ mu, const float* __rest
 }
 
 // ----------------------------------------------------------------------------------------------- clip + Adam
+// grid (blocks, tensors); 16-byte vector accesses on the aligned body, scalar tail.  cudaMalloc'd tensors are
+// 256-byte aligned; a misaligned view falls back to the scalar loop (vec = 0).
 __global__ void adam_norm_kernel(const AdamTable tab, float* __restrict__ norms) {
   __shared__ float red[32];
   const int t = blockIdx.y;
-  const float* g = tab.g[t];
+  const float* __restrict__ g = tab.g[t];
   const long long n = tab.n[t];
+  const bool vec = (reinterpret_cast<uintptr_t>(g) & 15) == 0;
+  const long long n4 = vec ? n >> 2 : 0;
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
   float acc = 0.f;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x)
-    acc = fmaf(g[i], g[i], acc);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long long i = tid; i < n4; i += nth) {
+    const float4 v = g4[i];
+    acc = fmaf(v.x, v.x, acc);
+    acc = fmaf(v.y, v.y, acc);
+    acc = fmaf(v.z, v.z, acc);
+    acc = fmaf(v.w, v.w, acc);
+  }
+  for (long long i = (n4 << 2) + tid; i < n; i += nth) acc = fmaf(g[i], g[i], acc);
   const float s = block_sum(acc, red);
   if (threadIdx.x == 0 && s != 0.f) atomicAdd(norms + t, s);
+}
+
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float coef, float beta1, float beta2,
+                                         float eps, float lr_t) {
+  const float gi = g * coef;
+  m = m + (gi - m) * (1.f - beta1);
+  v = v + (gi * gi - v) * (1.f - beta2);
+  p = p - lr_t * m / (sqrtf(v) + eps);
 }
 
 __global__ void adam_apply_kernel(const AdamTable tab, const float* __restrict__ norms, float beta1, float beta2,
                                   float eps, float bc /* sqrt(1-b2^t)/(1-b1^t) */, float clip) {
   const int t = blockIdx.y;
-  float* p = tab.p[t];
-  const float* g = tab.g[t];
-  float* m = tab.m[t];
-  float* v = tab.v[t];
+  float* __restrict__ p = tab.p[t];
+  const float* __restrict__ g = tab.g[t];
+  float* __restrict__ m = tab.m[t];
+  float* __restrict__ v = tab.v[t];
   const long long n = tab.n[t];
   const float lr_t = tab.lr[t] * bc;
   float coef = 1.0f;
   if (clip > 0.f) coef = clip / fmaxf(sqrtf(norms[t]), clip);   // ClipByNorm: g*c / max(||g||, c)
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float gi = g[i] * coef;
-    const float mi = m[i] + (gi - m[i]) * (1.f - beta1);
-    const float vi = v[i] + (gi * gi - v[i]) * (1.f - beta2);
-    m[i] = mi;
-    v[i] = vi;
-    p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  const long long n4 = vec ? n >> 2 : 0;
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (long long i = tid; i < n4; i += nth) {
+    float4 pp = p4[i], mm = m4[i], vv = v4[i];
+    const float4 gg = g4[i];
+    adam_one(pp.x, gg.x, mm.x, vv.x, coef, beta1, beta2, eps, lr_t);
+    adam_one(pp.y, gg.y, mm.y, vv.y, coef, beta1, beta2, eps, lr_t);
+    adam_one(pp.z, gg.z, mm.z, vv.z, coef, beta1, beta2, eps, lr_t);
+    adam_one(pp.w, gg.w, mm.w, vv.w, coef, beta1, beta2, eps, lr_t);
+    m4[i] = mm;
+    v4[i] = vv;
+    p4[i] = pp;
   }
+  for (long long i = (n4 << 2) + tid; i < n; i += nth) adam_one(p[i], g[i], m[i], v[i], coef, beta1, beta2, eps, lr_t);
 }
 
 // ----------------------------------------------------------------------------------------------- backward pieces
@@ -674,17 +783,20 @@ __global__ void fill_kernel(float* __restrict__ y, float v, long long n) {
     y[i] = v;
 }
 // out[c] (+)= sum over n, spatial of g[n][c][s]                       (bias gradient of the fp32 NCDHW tails)
-__global__ void channel_sum_ncdhw_kernel(const float* __restrict__ g, int N, int C, long long sp, int accumulate,
-                                         float* __restrict__ out) {
+// grid (blocks, C): fp32 block partials -> fp64 atomics into scratch[c]; a d2f pass writes the result.
+__global__ void channel_sum_ncdhw_kernel(const float* __restrict__ g, int N, int C, long long sp,
+                                         double* __restrict__ scratch) {
   __shared__ float red[32];
-  const int c = blockIdx.x;
+  const int c = blockIdx.y;
   float acc = 0.f;
   for (int n = 0; n < N; ++n) {
     const float* p = g + (static_cast<long long>(n) * C + c) * sp;
-    for (long long i = threadIdx.x; i < sp; i += blockDim.x) acc += p[i];
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < sp;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+      acc += p[i];
   }
   const float t = block_sum(acc, red);
-  if (threadIdx.x == 0) out[c] = (accumulate ? out[c] : 0.f) + t;
+  if (threadIdx.x == 0) atomicAdd(scratch + c, static_cast<double>(t));
 }
 // KL gradient (losses.py:5-7): d/dmu = coef*mu ; d/dlogvar = coef*0.5*(exp(lv)-1) ; coef = kl_weight/n
 __global__ void kl_grad_kernel(const float* __restrict__ mu, const float* __restrict__ lv, long long n, float coef,
@@ -695,17 +807,28 @@ __global__ void kl_grad_kernel(const float* __restrict__ mu, const float* __rest
     glv[i] = coef * 0.5f * (expf(lv[i]) - 1.f);
   }
 }
-// spectral-norm chain rule (u, v constants): gW (+)= (G - <G, W/sigma> u v^T) / sigma            one CTA
-__global__ void sn_grad_kernel(const float* __restrict__ G, const float* __restrict__ w, const float* __restrict__ u,
-                               const float* __restrict__ v, const float* __restrict__ sigma, int cout, int k,
-                               int accumulate, float* __restrict__ gw) {
+// spectral-norm chain rule (u, v constants): gW (+)= (G - <G, W/sigma> u v^T) / sigma
+// pass 1: SN_GRAD_BLOCKS partial dot products <G, W> ; pass 2: every block sums them in fixed order and applies.
+constexpr int SN_GRAD_BLOCKS = 64;
+__global__ void sn_grad_dot_kernel(const float* __restrict__ G, const float* __restrict__ w, int n,
+                                   float* __restrict__ partial) {
   __shared__ float red[32];
-  const float sg = sigma[0];
   float part = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    part = fmaf(G[i], w[i], part);
+  const float t = block_sum(part, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+__global__ void sn_grad_apply_kernel(const float* __restrict__ G, const float* __restrict__ partial,
+                                     const float* __restrict__ u, const float* __restrict__ v,
+                                     const float* __restrict__ sigma, int cout, int k, int accumulate,
+                                     float* __restrict__ gw) {
+  const float sg = sigma[0];
+  float dot = 0.f;
+  for (int i = 0; i < SN_GRAD_BLOCKS; ++i) dot += partial[i];
+  dot /= sg;   // <G, W/sigma>
   const int n = cout * k;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) part = fmaf(G[i], w[i], part);
-  const float dot = block_sum(part, red) / sg;   // <G, W/sigma>
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int r = i / k, c = i - r * k;
     const float val = (G[i] - dot * u[r] * v[c]) / sg;
     gw[i] = (accumulate ? gw[i] : 0.f) + val;
@@ -860,6 +983,25 @@ cudaError_t ew_sn_power_iter(const float* w, int cout, int k, float* u, float* v
   LAUNCH_CHECK();
   return cudaSuccess;
 }
+cudaError_t ew_sn_power_iter_multi(const SnTable& tab, int n_layers, cudaStream_t st) {
+  size_t smem = 0;
+  for (int i = 0; i < n_layers; ++i) {
+    const size_t b = (2 * static_cast<size_t>(tab.cout[i]) + tab.k[i]) * sizeof(float);
+    if (b > smem) smem = b;
+  }
+  sn_power_iter_multi_kernel<<<n_layers, 512, smem, st>>>(tab);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_bn_train_apply_cl(const __nv_bfloat16* y, long long voxels, const double* sums, const float* gamma,
+                                 const float* beta, float eps, float momentum, float* mm, float* mv, float* saved,
+                                 int act, __nv_bfloat16* x, cudaStream_t st) {
+  bn_train_apply_cl_kernel<<<grid_for(voxels * 8, 256), 256, 0, st>>>(y, voxels * 8, sums,
+                                                                      static_cast<double>(voxels), gamma, beta, eps,
+                                                                      momentum, mm, mv, saved, act, x);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
 cudaError_t ew_bn_fold_eval(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                             const float* bias, int C, float* scale, float* shift, cudaStream_t st) {
   bn_fold_eval_kernel<<<(C + 63) / 64, 64, 0, st>>>(gamma, beta, mean, var, eps, bias, C, scale, shift);
@@ -890,13 +1032,20 @@ cudaError_t ew_reparam(const float* mu, const float* lv, const float* eps, long 
 }
 cudaError_t ew_adam_clip(const AdamTable& tab, int n_tensors, float* norms_scratch, float beta1, float beta2,
                          float eps, float bias_corr, float clip, cudaStream_t st) {
+  // blocks per tensor: enough to cover the largest tensor with ~2 float4 per thread, and to fill the 148 SMs
+  long long nmax = 1;
+  for (int i = 0; i < n_tensors; ++i) nmax = tab.n[i] > nmax ? tab.n[i] : nmax;
+  long long want = (nmax + 2047) / 2048;
+  const long long cap = (148LL * 16 + n_tensors - 1) / n_tensors;
+  if (want > cap) want = cap;
+  const int gx = static_cast<int>(want < 1 ? 1 : want);
   if (clip > 0.f) {
     cudaError_t e = cudaMemsetAsync(norms_scratch, 0, ADAM_MAX_TENSORS * sizeof(float), st);
     if (e != cudaSuccess) return e;
-    adam_norm_kernel<<<dim3(32, n_tensors), 256, 0, st>>>(tab, norms_scratch);
+    adam_norm_kernel<<<dim3(gx, n_tensors), 256, 0, st>>>(tab, norms_scratch);
     LAUNCH_CHECK();
   }
-  adam_apply_kernel<<<dim3(32, n_tensors), 256, 0, st>>>(tab, norms_scratch, beta1, beta2, eps, bias_corr, clip);
+  adam_apply_kernel<<<dim3(gx, n_tensors), 256, 0, st>>>(tab, norms_scratch, beta1, beta2, eps, bias_corr, clip);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -956,9 +1105,14 @@ cudaError_t ew_fill(float* y, float v, long long n, cudaStream_t st) {
   LAUNCH_CHECK();
   return cudaSuccess;
 }
-cudaError_t ew_channel_sum_ncdhw(const float* g, int N, int C, long long sp, int accumulate, float* out,
-                                 cudaStream_t st) {
-  channel_sum_ncdhw_kernel<<<C, 512, 0, st>>>(g, N, C, sp, accumulate, out);
+cudaError_t ew_channel_sum_ncdhw(const float* g, int N, int C, long long sp, int accumulate, double* scratch,
+                                 float* out, cudaStream_t st) {
+  if (C > 128) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, C * sizeof(double), st);
+  if (e != cudaSuccess) return e;
+  channel_sum_ncdhw_kernel<<<dim3(grid_for(sp, 512, 128), C), 512, 0, st>>>(g, N, C, sp, scratch);
+  LAUNCH_CHECK();
+  d2f_kernel<<<(C + 63) / 64, 64, 0, st>>>(scratch, C, 1.f, accumulate, out);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -969,8 +1123,11 @@ cudaError_t ew_kl_grad(const float* mu, const float* lv, long long n, float coef
   return cudaSuccess;
 }
 cudaError_t ew_sn_grad(const float* G, const float* w, const float* u, const float* v, const float* sigma, int cout,
-                       int k, int accumulate, float* gw, cudaStream_t st) {
-  sn_grad_kernel<<<1, 1024, 0, st>>>(G, w, u, v, sigma, cout, k, accumulate, gw);
+                       int k, int accumulate, float* scratch /*[SN_GRAD_BLOCKS]*/, float* gw, cudaStream_t st) {
+  const int n = cout * k;
+  sn_grad_dot_kernel<<<SN_GRAD_BLOCKS, 256, 0, st>>>(G, w, n, scratch);
+  LAUNCH_CHECK();
+  sn_grad_apply_kernel<<<grid_for(n, 256, 148 * 2), 256, 0, st>>>(G, scratch, u, v, sigma, cout, k, accumulate, gw);
   LAUNCH_CHECK();
   return cudaSuccess;
 }

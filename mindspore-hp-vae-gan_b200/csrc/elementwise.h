@@ -36,8 +36,25 @@ cudaError_t ew_bn_finalize(const double* sum, const double* sumsq, long long cou
                            float* shift, float* mean, float* invstd, cudaStream_t st);
 cudaError_t ew_bn_apply_cl(const __nv_bfloat16* y, long long voxels, const float* scale, const float* shift, int act,
                            __nv_bfloat16* x, cudaStream_t st);
+constexpr int SN_MAX_LAYERS = 16;
+struct SnTable {
+  const float* w[SN_MAX_LAYERS];
+  float* u[SN_MAX_LAYERS];
+  float* v[SN_MAX_LAYERS];
+  float* sigma[SN_MAX_LAYERS];      // [2]: sigma, 1/sigma
+  const float* bias[SN_MAX_LAYERS]; // nullable
+  float* aff[SN_MAX_LAYERS];        // nullable [2][64]: (1/sigma, bias) conv epilogue vectors
+  float* u_copy[SN_MAX_LAYERS];     // nullable: snapshot of the updated u / v for this pass's backward
+  float* v_copy[SN_MAX_LAYERS];
+  int cout[SN_MAX_LAYERS];
+  int k[SN_MAX_LAYERS];
+};
 cudaError_t ew_sn_power_iter(const float* w, int cout, int k, float* u, float* v, float* sigma, float* inv_sigma,
                              cudaStream_t st);
+cudaError_t ew_sn_power_iter_multi(const SnTable& tab, int n_layers, cudaStream_t st);
+cudaError_t ew_bn_train_apply_cl(const __nv_bfloat16* y, long long voxels, const double* sums, const float* gamma,
+                                 const float* beta, float eps, float momentum, float* mm, float* mv, float* saved,
+                                 int act, __nv_bfloat16* x, cudaStream_t st);
 cudaError_t ew_bn_fold_eval(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                             const float* bias, int C, float* scale, float* shift, cudaStream_t st);
 cudaError_t ew_affine_from_bias(const float* bias, const float* inv_sigma, int C, float* scale, float* shift,
@@ -59,12 +76,12 @@ cudaError_t ew_diff_scale(const float* a, const float* b, long long n, float coe
 cudaError_t ew_tanh_bwd(const float* g, const float* out, long long n, float* gpre, cudaStream_t st);
 cudaError_t ew_axpby(float a, const float* x, float b, float* y, long long n, cudaStream_t st);
 cudaError_t ew_fill(float* y, float v, long long n, cudaStream_t st);
-cudaError_t ew_channel_sum_ncdhw(const float* g, int N, int C, long long sp, int accumulate, float* out,
-                                 cudaStream_t st);
+cudaError_t ew_channel_sum_ncdhw(const float* g, int N, int C, long long sp, int accumulate, double* scratch,
+                                 float* out, cudaStream_t st);
 cudaError_t ew_kl_grad(const float* mu, const float* lv, long long n, float coef, float* gmu, float* glv,
                        cudaStream_t st);
 cudaError_t ew_sn_grad(const float* G, const float* w, const float* u, const float* v, const float* sigma, int cout,
-                       int k, int accumulate, float* gw, cudaStream_t st);
+                       int k, int accumulate, float* scratch, float* gw, cudaStream_t st);
 cudaError_t ew_lerp(const float* a, const float* b, float alpha, long long n, float* out, cudaStream_t st);
 cudaError_t ew_gp_grad(const float* g, int N, int C, long long sp, float lambda, float* Gout, float* gp,
                        cudaStream_t st);

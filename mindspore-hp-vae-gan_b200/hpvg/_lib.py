@@ -56,7 +56,7 @@ _SIGS = {
     "hpvg_unpack_cl": ([vp, i, i, i, i, i, i, i, vp, vp], c_int),
     "hpvg_conv_wimg_bytes": ([i], c_int),
     "hpvg_conv_pack_weights": ([vp, i, i, i, i, i, i, i, i, i, vp, vp], c_int),
-    "hpvg_conv_cl": ([i, i, i, i, i, vp, i, vp, vp, vp, i, i, vp, i, i, i, vp, vp], c_int),
+    "hpvg_conv_cl": ([i, i, i, i, i, vp, i, vp, vp, vp, i, i, vp, i, i, i, vp, vp, vp], c_int),
     "hpvg_linear_taps": ([i, i, i, POINTER(c_int32), POINTER(c_int32), POINTER(f), POINTER(f)], c_int),
     "hpvg_linear_taps_dev": ([i, i, i, vp, vp, vp, vp, vp], c_int),
     "hpvg_resize3d_fwd": ([vp, i, i, i, i, i, vp, i, i, i, i, vp], c_int),
@@ -65,7 +65,10 @@ _SIGS = {
     "hpvg_bn_stats_cl": ([vp, ll, vp, vp, vp], c_int),
     "hpvg_bn_finalize": ([vp, vp, ll, vp, vp, f, f, vp, vp, vp, vp, vp, vp, vp], c_int),
     "hpvg_bn_apply_lrelu_cl": ([vp, ll, vp, vp, i, vp, vp], c_int),
+    "hpvg_bn_train_apply_cl": ([vp, ll, vp, vp, vp, f, f, vp, vp, vp, i, vp, vp], c_int),
     "hpvg_sn_power_iter": ([vp, i, i, vp, vp, vp, vp, vp], c_int),
+    "hpvg_sn_power_iter_multi": ([i, POINTER(vp), POINTER(i), POINTER(i), POINTER(vp), POINTER(vp), POINTER(vp),
+                                  POINTER(vp), POINTER(vp), POINTER(vp), POINTER(vp), vp], c_int),
     "hpvg_bn_fold_eval": ([vp, vp, vp, vp, f, vp, i, vp, vp, vp], c_int),
     "hpvg_affine_from_bias": ([vp, vp, i, vp, vp, vp], c_int),
     "hpvg_mse": ([vp, vp, ll, vp, vp], c_int),

@@ -106,8 +106,12 @@ class ConvLayer(Cell):
             self.p["moving_mean"] = from_numpy(np.zeros(cout, np.float32))
             self.p["moving_variance"] = from_numpy(np.ones(cout, np.float32))
         self._wimgs = None
-        self._aff = None
-        self._sigma = None
+        self._aff = None        # epilogue vectors used by the current forward
+        self._aff_bias = None   # cached (1, bias): valid until the parameters change
+        self._aff_eval = None   # cached folded eval-mode BatchNorm: valid until parameters / moving stats change
+        self._aff_sn = None     # (1/sigma, bias) written by the power-iteration kernel
+        self._sigma = None      # (sigma, 1/sigma)
+        self._sn_fresh = False  # the power iteration of the coming forward was already run (batched per network)
 
     # ---- parameters
     def parameters_dict(self, prefix=""):
@@ -120,6 +124,8 @@ class ConvLayer(Cell):
     def invalidate(self):
         self._wimgs = None
         self._aff = None
+        self._aff_bias = None
+        self._aff_eval = None
 
     def copy_from(self, other):
         for k, t in self.p.items():
@@ -141,36 +147,61 @@ class ConvLayer(Cell):
                         self._wimgs.append(ops.pack_weights(w, mode, cout_off=ob * 64, cout=64, cin_off=ib * 64,
                                                             cin=min(self.cin, 64), stream=stream))
 
+    def sn_entry(self, sigma=None, aff=None, u_copy=None, v_copy=None):
+        """Table entry for ops.sn_power_iter_multi.  `sigma` / `aff` default to the layer's own persistent buffers;
+        the training tape passes per-pass tensors so the backward sees the values THIS forward used (Q5)."""
+        if sigma is None:
+            if self._sigma is None:
+                self._sigma = Tensor((2,), F32)
+            sigma = self._sigma
+        if aff is None:
+            if self._aff_sn is None:
+                self._aff_sn = Tensor((2, 64), F32)
+            aff = self._aff_sn
+        self._cur_sigma, self._cur_aff, self._cur_u, self._cur_v = sigma, aff, u_copy, v_copy
+        return {"w": self.p["weight"], "u": self.p["weight_u"], "v": self.p["weight_v"], "sigma": sigma,
+                "bias": self.p["bias"], "aff": aff, "u_copy": u_copy, "v_copy": v_copy}
+
     def _prepare(self, training, stream):
         """Filter bank + the epilogue vectors (bias / folded BN / 1/sigma) for this forward."""
         self._prepare_wimgs(stream)
         if self.sn:
             # Q5: u/v advance on EVERY forward, train or eval (spectral_norm.py:146-148)
-            self._sigma = ops.sn_power_iter(self.p["weight"], self.p["weight_u"], self.p["weight_v"],
-                                            out=self._sigma, stream=stream)
-            inv = self._sigma.view((1,), F32, 4)
-            self._aff = ops.affine_from_bias(self.p["bias"], inv, out=self._aff, stream=stream)
+            if not self._sn_fresh:
+                ops.sn_power_iter_multi([self.sn_entry()], stream=stream)
+            self._sn_fresh = False
+            self._aff = self._cur_aff
+            self._sigma_used = self._cur_sigma
         elif self.bn and not training:
-            if self._aff is None:
-                self._aff = ops.bn_fold_eval(self.p["gamma"], self.p["beta"], self.p["moving_mean"],
-                                             self.p["moving_variance"], self.p["bias"], stream=stream)
+            if self._aff_eval is None:
+                self._aff_eval = ops.bn_fold_eval(self.p["gamma"], self.p["beta"], self.p["moving_mean"],
+                                                  self.p["moving_variance"], self.p["bias"], stream=stream)
+            self._aff = self._aff_eval
         else:
-            if self._aff is None or (self.bn and training):
-                self._aff = ops.affine_from_bias(self.p["bias"], None, out=self._aff, stream=stream)
+            if self._aff_bias is None:
+                self._aff_bias = ops.affine_from_bias(self.p["bias"], None, stream=stream)
+            self._aff = self._aff_bias
 
-    def forward_cl(self, x_cl, residual=None, out=None, ws=None, tag="", stream=None, saved=None):
-        """x_cl: bf16 channels-last.  Returns bf16 cl (Cout >= 64) or fp32 ncdhw (Cout <= 4)."""
+    def forward_cl(self, x_cl, residual=None, out=None, ws=None, tag="", stream=None, saved=None, stats=None,
+                   raw=None):
+        """x_cl: bf16 channels-last.  Returns bf16 cl (Cout >= 64) or fp32 ncdhw (Cout <= 4).
+        Training-mode BatchNorm: conv(+bias) with the batch statistics accumulated in its epilogue, then ONE
+        normalise+activation pass.  `stats`: pre-zeroed fp64 (2,64) scratch (allocated here when absent);
+        `saved`: dict that receives raw=y and bn=(scale, shift, mean, invstd) for the backward."""
         training = self.training
         self._prepare(training, stream)
         if self.bn and training:
-            # batch statistics need the whole conv output first: conv(+bias) -> stats -> normalise+act
             N, T, H, W, _ = x_cl.shape
-            raw = ws.get(tag + ".raw", (N, T, H, W, self.cout), BF16) if ws else None
+            if raw is None:
+                raw = ws.get(tag + ".raw", (N, T, H, W, self.cout), BF16) if ws else Tensor((N, T, H, W, self.cout), BF16)
+            if stats is None:
+                stats = Tensor((2, 64), "float64").zero_(stream)
             y = ops.conv3d_cl_any(x_cl, self.p["weight"], self._aff, ACT_NONE, self.cin, self.cout, out=raw,
-                                  wimgs=self._wimgs, stream=stream)
-            x, sv = ops.bn_train_cl(y, self.p["gamma"], self.p["beta"], self.p["moving_mean"],
-                                    self.p["moving_variance"], self.act, out=out, stream=stream)
-            self._aff = None   # moving stats changed: a later eval-mode fold must be rebuilt
+                                  wimgs=self._wimgs, stats=stats, stream=stream)
+            sv = Tensor((4, 64), F32) if saved is not None else None
+            x = ops.bn_train_fused_cl(y, stats, self.p["gamma"], self.p["beta"], self.p["moving_mean"],
+                                      self.p["moving_variance"], self.act, out=out, saved=sv, stream=stream)
+            self._aff_eval = None   # moving stats changed: a later eval-mode fold must be rebuilt
             if saved is not None:
                 saved.update(raw=y, bn=sv)
             return x
@@ -178,19 +209,53 @@ class ConvLayer(Cell):
                                  residual=residual, out=out, wimgs=self._wimgs, stream=stream)
 
 
-def ConvBlock3D(in_channel, out_channel, ker_size=3, padding=1, stride=1, bn=True, act="lrelu", rng=None):
-    """networks_3d.py:45-54.  Only the 3x3x3 / stride 1 / pad 1 configuration exists on the hot path."""
+def sn_prepare_batch(layers, stream=None, entries=None):
+    """Run the power iteration of every spectrally normalised layer in `layers` in one launch and mark them fresh."""
+    sn = [l for l in layers if l.sn]
+    if not sn:
+        return
+    ops.sn_power_iter_multi(entries if entries is not None else [l.sn_entry() for l in sn], stream=stream)
+    for l in sn:
+        l._sn_fresh = True
+
+
+class BnStatsSlab:
+    """fp64 (2,64) accumulators for the fused BatchNorm statistics of one network pass: one slab, one memset."""
+
+    def __init__(self, n_slots=96):
+        self.n_slots = n_slots
+        self.t = None
+        self.i = 0
+
+    def reset(self, stream=None):
+        if self.t is None:
+            self.t = Tensor((self.n_slots, 2, 64), "float64")
+        self.t.zero_(stream)
+        self.i = 0
+
+    def take(self):
+        if self.t is None or self.i >= self.n_slots:
+            raise HpvgError("BnStatsSlab exhausted: reset() it at the start of the pass / raise n_slots")
+        v = self.t.view((2, 64), "float64", self.i * 1024)
+        self.i += 1
+        return v
+
+
+def ConvBlock3D(in_channel, out_channel, ker_size=3, padding=1, stride=1, bn=True, act="lrelu", rng=None, kt=3,
+                bn_prefix="1.bn2d."):
+    """networks_3d.py:45-54.  Only the 3x3x3 / stride 1 / pad 1 configuration exists on the hot path.
+    (kt=1, bn_prefix="1." gives the 2-D twin ConvBlock2D, networks_2d.py:44-53.)"""
     _check_geometry(ker_size, padding, stride)
-    return ConvLayer(in_channel, out_channel, bn=bn, act=act, rng=rng)
+    return ConvLayer(in_channel, out_channel, bn=bn, act=act, rng=rng, kt=kt, bn_prefix=bn_prefix)
 
 
-def ConvBlock3DSN(in_channel, out_channel, ker_size=3, padding=1, stride=1, bn=True, act="lrelu", rng=None):
+def ConvBlock3DSN(in_channel, out_channel, ker_size=3, padding=1, stride=1, bn=True, act="lrelu", rng=None, kt=3):
     """networks_3d.py:57-73: `bn=True` selects the spectrally normalised conv (there is no BatchNorm in it)."""
     _check_geometry(ker_size, padding, stride)
     if not bn:
         raise HpvgError("ConvBlock3DSN(bn=False) (reflect-pad, bias-free) is unreachable in the reference's default "
                         "path and is not implemented")
-    return ConvLayer(in_channel, out_channel, sn=True, act=act, rng=rng)
+    return ConvLayer(in_channel, out_channel, sn=True, act=act, rng=rng, kt=kt)
 
 
 def _check_geometry(ker_size, padding, stride):
@@ -220,13 +285,14 @@ class Sequential(Cell):
 class FeatureExtractor(Sequential):
     """networks_3d.py:76-86: num_blocks+1 SN blocks."""
 
-    def __init__(self, in_channel, out_channel, ker_size, padding, stride, num_blocks=2, return_linear=False, rng=None):
+    def __init__(self, in_channel, out_channel, ker_size, padding, stride, num_blocks=2, return_linear=False, rng=None,
+                 kt=3):
         if return_linear:
             raise HpvgError("FeatureExtractor(return_linear=True) is never used by the reference; not implemented")
-        layers = [ConvBlock3DSN(in_channel, out_channel, ker_size, padding, stride, rng=rng)]
+        layers = [ConvBlock3DSN(in_channel, out_channel, ker_size, padding, stride, rng=rng, kt=kt)]
         for _ in range(num_blocks - 1):
-            layers.append(ConvBlock3DSN(out_channel, out_channel, ker_size, padding, stride, rng=rng))
-        layers.append(ConvBlock3DSN(out_channel, out_channel, ker_size, padding, stride, rng=rng))
+            layers.append(ConvBlock3DSN(out_channel, out_channel, ker_size, padding, stride, rng=rng, kt=kt))
+        layers.append(ConvBlock3DSN(out_channel, out_channel, ker_size, padding, stride, rng=rng, kt=kt))
         super().__init__(layers)
 
 
@@ -234,64 +300,100 @@ class _Wrap(Sequential):
     """A SequentialCell holding exactly one conv layer (gives the `.0.` level of the reference's names)."""
 
 
+def as5d(t):
+    """(N,C,H,W) -> (N,C,1,H,W) view: 2-D data is the T == 1 case of every kernel."""
+    if t is None or len(t.shape) == 5:
+        return t
+    n, c, h, w = t.shape
+    return t.view((n, c, 1, h, w))
+
+
+def as4d(t):
+    if t is None or len(t.shape) == 4:
+        return t
+    n, c, _, h, w = t.shape
+    return t.view((n, c, h, w))
+
+
 class Encode3DVAE(Cell):
     """networks_3d.py:89-112."""
+    KT = 3
 
     def __init__(self, opt, out_dim=None, num_blocks=2, rng=None):
         super().__init__()
+        kt = self.KT
         output_dim = opt.nfc if out_dim is None else int(out_dim)
         self._features = self._add("_features", FeatureExtractor(opt.nc_im, opt.nfc, opt.ker_size, opt.ker_size // 2,
-                                                                 1, num_blocks=num_blocks, rng=rng))
+                                                                 1, num_blocks=num_blocks, rng=rng, kt=kt))
         # the SN blocks are SequentialCells themselves: encode._features.{i}.0.weight
         for l in self._features.layers:
             l.conv_prefix = "0."
         self._mu = self._add("_mu", ConvBlock3D(opt.nfc, output_dim, opt.ker_size, opt.ker_size // 2, 1, bn=False,
-                                                act=None, rng=rng))
+                                                act=None, rng=rng, kt=kt))
         self._logvar = self._add("_logvar", ConvBlock3D(opt.nfc, output_dim, opt.ker_size, opt.ker_size // 2, 1,
-                                                        bn=False, act=None, rng=rng))
+                                                        bn=False, act=None, rng=rng, kt=kt))
 
     def construct_cl(self, x_cl, stream=None):
         f = x_cl
+        sn_prepare_batch(self._features.layers, stream)
         for l in self._features.layers:
             f = l.forward_cl(f, stream=stream)
         return self._mu.forward_cl(f, stream=stream), self._logvar.forward_cl(f, stream=stream), f
 
     def construct(self, x):
-        mu, logvar, _ = self.construct_cl(ops.pack_cl(x, c_pitch=8))
-        return ops.unpack_cl(mu), ops.unpack_cl(logvar)
+        nd4 = len(x.shape) == 4
+        mu, logvar, _ = self.construct_cl(ops.pack_cl(as5d(x), c_pitch=8))
+        mu, logvar = ops.unpack_cl(mu), ops.unpack_cl(logvar)
+        return (as4d(mu), as4d(logvar)) if nd4 else (mu, logvar)
 
 
 class WDiscriminator3D(Cell):
     """networks_3d.py:170-193: SN head, num_layer SN body blocks, plain tail conv N->1."""
+    KT = 3
 
     def __init__(self, opt, rng=None):
         super().__init__()
-        N = int(opt.nfc)
-        self.head = self._add("head", ConvBlock3DSN(opt.nc_im, N, opt.ker_size, opt.ker_size // 2, stride=1, rng=rng))
-        self.body = self._add("body", Sequential([ConvBlock3DSN(N, N, opt.ker_size, opt.ker_size // 2, stride=1, rng=rng)
-                                                  for _ in range(opt.num_layer)]))
-        self.tail = self._add("tail", ConvLayer(N, 1, conv_prefix="", rng=rng))
+        N, kt = int(opt.nfc), self.KT
+        self.head = self._add("head", ConvBlock3DSN(opt.nc_im, N, opt.ker_size, opt.ker_size // 2, stride=1, rng=rng,
+                                                    kt=kt))
+        self.body = self._add("body", Sequential([ConvBlock3DSN(N, N, opt.ker_size, opt.ker_size // 2, stride=1,
+                                                                rng=rng, kt=kt) for _ in range(opt.num_layer)]))
+        self.tail = self._add("tail", ConvLayer(N, 1, conv_prefix="", rng=rng, kt=kt))
 
     def construct(self, x, stream=None):
-        h = self.head.forward_cl(ops.pack_cl(x, c_pitch=8, stream=stream), stream=stream)
+        nd4 = len(x.shape) == 4
+        sn_prepare_batch([self.head] + self.body.layers, stream)
+        h = self.head.forward_cl(ops.pack_cl(as5d(x), c_pitch=8, stream=stream), stream=stream)
         for l in self.body.layers:
             h = l.forward_cl(h, stream=stream)
-        return self.tail.forward_cl(h, stream=stream)
+        out = self.tail.forward_cl(h, stream=stream)
+        return as4d(out) if nd4 else out
 
 
-def _make_block(cin, opt, rng):
+def _make_block(cin, opt, rng, kt=3, bn_prefix="1.bn2d."):
     """decoder / body stage: ConvBlock3D(cin->N) + num_layer x ConvBlock3D(N->N) + Conv3d(N->nc_im)
-    (networks_3d.py:377-381, 395-401)."""
+    (networks_3d.py:377-381, 395-401; networks_2d.py:206-213, 226-234 with kt=1)."""
     N = int(opt.nfc)
-    layers = [ConvBlock3D(cin, N, opt.ker_size, opt.padd_size, stride=1, rng=rng)]
+    layers = [ConvBlock3D(cin, N, opt.ker_size, opt.padd_size, stride=1, rng=rng, kt=kt, bn_prefix=bn_prefix)]
     for _ in range(opt.num_layer):
-        layers.append(ConvBlock3D(N, N, opt.ker_size, opt.padd_size, stride=1, rng=rng))
-    layers.append(ConvLayer(N, opt.nc_im, conv_prefix="", rng=rng))   # body.{s}.6.weight
+        layers.append(ConvBlock3D(N, N, opt.ker_size, opt.padd_size, stride=1, rng=rng, kt=kt, bn_prefix=bn_prefix))
+    layers.append(ConvLayer(N, opt.nc_im, conv_prefix="", rng=rng, kt=kt))   # body.{s}.6.weight
     return Sequential(layers)
 
 
 class GeneratorHPVAEGAN(Cell):
     """networks_3d.py:354-451."""
+    KT = 3                      # temporal filter taps (1 for the 2-D twin)
+    BN_PREFIX = "1.bn2d."       # the 3-D BatchNorm wraps a 2-D one (pt2ms.py:173)
+    ENCODER = Encode3DVAE
+
+    def stage_shape(self, index):
+        """(T, H, W) of pyramid level `index` (images.py:96-107)."""
+        return uimg.scale_shape(self.opt, index)
+
+    def noise_at(self, index, is_random):
+        """Refinement noise is added in random mode from the first GAN level on (networks_3d.py:443-446)."""
+        return bool(is_random) and self.opt.vae_levels <= index
 
     def __init__(self, opt, is_training=False, seed=0):
         super().__init__()
@@ -301,17 +403,18 @@ class GeneratorHPVAEGAN(Cell):
         self.train_all = opt.train_all
         self.N = int(opt.nfc)
         self._rng = np.random.default_rng(seed)
-        self.encode = self._add("encode", Encode3DVAE(opt, out_dim=opt.latent_dim, num_blocks=opt.enc_blocks,
-                                                      rng=self._rng))
-        self.decoder = self._add("decoder", _make_block(opt.latent_dim, opt, self._rng))
+        self.encode = self._add("encode", self.ENCODER(opt, out_dim=opt.latent_dim, num_blocks=opt.enc_blocks,
+                                                       rng=self._rng))
+        self.decoder = self._add("decoder", _make_block(opt.latent_dim, opt, self._rng, self.KT, self.BN_PREFIX))
         self.body = self._add("body", Sequential([]))
         self.ws = Workspace()
+        self.bn_slab = BnStatsSlab()
         self.noise_seed = 0x9E3779B97F4A7C15   # device Philox key for internally drawn noise
         self.sample_counter = 0
 
     def init_next_stage(self):
         """networks_3d.py:393-404: first stage is freshly initialised, later stages deep-copy the previous one."""
-        stage = _make_block(self.opt.nc_im, self.opt, self._rng)
+        stage = _make_block(self.opt.nc_im, self.opt, self._rng, self.KT, self.BN_PREFIX)
         if len(self.body) > 0:
             for new, old in zip(stage.layers, self.body[-1].layers):
                 new.copy_from(old)
@@ -325,7 +428,8 @@ class GeneratorHPVAEGAN(Cell):
         h = x_cl
         for j, layer in enumerate(block.layers[:-1]):
             buf = ws.get("%s.act%d" % (tag, j & 1), (N, T, H, W, self.N), BF16)
-            h = layer.forward_cl(h, out=buf, ws=ws, tag=tag, stream=stream)
+            stats = self.bn_slab.take() if (layer.bn and layer.training) else None
+            h = layer.forward_cl(h, out=buf, ws=ws, tag=tag, stream=stream, stats=stats)
         tail = block.layers[-1]
         tail.act = ACT_TANH    # tanh(block(x) [+ up]) is fused into the tail conv's epilogue (networks_3d.py:423,450)
         return tail.forward_cl(h, residual=residual, out=out, stream=stream)
@@ -337,7 +441,15 @@ class GeneratorHPVAEGAN(Cell):
         replace the internally drawn reparameterisation noise."""
         if sample_init is not None and len(self.body) <= sample_init[0]:
             raise HpvgError("sample_init scale %d exceeds the %d stages" % (sample_init[0], len(self.body)))
+        nd4 = any(t is not None and len(t.shape) == 4 for t in (video, noise_init))
+        video, noise_init, eps, z_pred = as5d(video), as5d(noise_init), as5d(eps), as5d(z_pred)
+        if sample_init is not None:
+            sample_init = (sample_init[0], as5d(sample_init[1]))
+        if noises is not None:
+            noises = {k: as5d(v) for k, v in noises.items()}
         mu = logvar = None
+        if self.training:
+            self.bn_slab.reset(stream)
         if noise_init is None:
             mu, logvar = self.encode.construct(video)
             if self.is_training:
@@ -360,6 +472,8 @@ class GeneratorHPVAEGAN(Cell):
             x = self.refinement_layers(sample_init[0], sample_init[1], noise_amp, isRandom, noises=noises,
                                        stream=stream)
         self.sample_counter += N
+        if nd4:
+            x, vae_out, mu, logvar = as4d(x), as4d(vae_out), as4d(mu), as4d(logvar)
         if noise_init is None:
             return x, vae_out, mu, logvar
         return x, vae_out
@@ -369,11 +483,11 @@ class GeneratorHPVAEGAN(Cell):
         opt = self.opt
         for idx in range(start_idx, len(self.body)):
             block = self.body[idx]
-            size = uimg.scale_shape(opt, idx + 1)
+            size = self.stage_shape(idx + 1)
             N = x_prev_out.shape[0]
             up = self.ws.get("up%d" % idx, (N, opt.nc_im) + size, F32)
             xin = self.ws.get("xin%d" % idx, (N,) + size + (8,), BF16)
-            add_noise = isRandom and opt.vae_levels <= idx + 1
+            add_noise = self.noise_at(idx + 1, isRandom)
             noise_t, seed, amp = None, 0, 0.0
             if add_noise:
                 amp = float(noise_amp[idx + 1])

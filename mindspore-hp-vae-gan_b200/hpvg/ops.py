@@ -94,8 +94,9 @@ def pack_weights(w, mode, transpose_flip=False, cout_off=0, cout=None, cin_off=0
 
 
 def conv_cl(mode, x_cl, wimg, scale, shift, act=ACT_NONE, out_mode=OUT_BF16_CL, out=None, out_pitch=64, out_coff=0,
-            cout_real=64, addend=None, in_coff=0, stream=None):
-    """Raw kernel call.  x_cl: bf16 (N,T,H,W,in_pitch); reads channels [in_coff, in_coff+64|8)."""
+            cout_real=64, addend=None, in_coff=0, stats=None, stream=None):
+    """Raw kernel call.  x_cl: bf16 (N,T,H,W,in_pitch); reads channels [in_coff, in_coff+64|8).
+    stats: optional fp64 (2,64) tensor accumulating the per-channel sum / sum of squares of the stored output."""
     N, T, H, W, in_pitch = x_cl.shape
     if out is None:
         if out_mode == OUT_BF16_CL:
@@ -110,7 +111,7 @@ def conv_cl(mode, x_cl, wimg, scale, shift, act=ACT_NONE, out_mode=OUT_BF16_CL, 
         e0, e1 = rt.Event(), rt.Event()
         e0.record(stream)
     check(lib.hpvg_conv_cl(mode, N, T, H, W, in_ptr, in_pitch, _p(wimg), _p(scale), _p(shift), act, out_mode, _p(out),
-                           out_pitch, out_coff, cout_real, _p(addend), _s(stream)), "conv_cl")
+                           out_pitch, out_coff, cout_real, _p(addend), _p(stats), _s(stream)), "conv_cl")
     if timed:
         e1.record(stream)
         _prof["items"].append((N * T * H * W, e0, e1) if _prof["mode"] is not None else ((mode, N * T * H * W), e0, e1))
@@ -144,7 +145,7 @@ def _sc(aff):
 
 
 def conv3d_cl_any(x_cl, w, aff, act, cin, cout, out_mode=OUT_BF16_CL, residual=None, out=None, wimgs=None,
-                  transpose_flip=False, stream=None):
+                  transpose_flip=False, stats=None, stream=None):
     """Convolution for every channel combination on the hot path, composed from the kernel variants:
     Cin in {<=8, 64, 128}, Cout in {<=4, 64, 128}.  aff: (2,64*ceil(cout/64)) epilogue vectors.
     Returns bf16 cl (cout 64/128) or fp32 ncdhw (cout <= 4)."""
@@ -177,7 +178,7 @@ def conv3d_cl_any(x_cl, w, aff, act, cin, cout, out_mode=OUT_BF16_CL, residual=N
                 partial = conv_cl(mode, x_cl, wi, s, b, ACT_NONE, OUT_F32_RAW, in_coff=ib * 64, stream=stream)
             else:
                 conv_cl(mode, x_cl, wi, s, b, act, OUT_BF16_CL, out=out, out_pitch=cout, out_coff=ob * 64,
-                        addend=partial, in_coff=ib * 64, stream=stream)
+                        addend=partial, in_coff=ib * 64, stats=stats, stream=stream)
     return out
 
 
@@ -259,7 +260,38 @@ def bn_train_cl(y_cl, gamma, beta, moving_mean, moving_var, act=ACT_LRELU, out=N
     return out, saved
 
 
+def bn_train_fused_cl(y_cl, stats, gamma, beta, moving_mean, moving_var, act=ACT_LRELU, out=None, saved=None,
+                      stream=None):
+    """One-pass training-mode BatchNorm (+LeakyReLU): `stats` is the fp64 (2,64) tensor filled by the producing conv's
+    epilogue (conv_cl(stats=...)).  Updates the moving statistics; `saved` (4,64) receives (scale, shift, mean, invstd)."""
+    voxels = int(np.prod(y_cl.shape[:-1]))
+    if out is None:
+        out = Tensor(y_cl.shape, BF16)
+    check(lib.hpvg_bn_train_apply_cl(_p(y_cl), voxels, _p(stats), _p(gamma), _p(beta), BN_EPS, BN_MOMENTUM,
+                                     _p(moving_mean), _p(moving_var), _p(saved), act, _p(out), _s(stream)),
+          "bn_train_apply")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ spectral norm
+def sn_power_iter_multi(layers, stream=None):
+    """One launch for all spectrally normalised layers of a network.  layers: list of dicts with device tensors
+    w, u, v, sigma (2,), bias, aff (2,64) [, u_copy, v_copy]: updates u, v in place, writes (sigma, 1/sigma), the conv
+    epilogue vectors and (optionally) a snapshot of the updated u, v."""
+    n = len(layers)
+    VP = ctypes.c_void_p * n
+    IA = ctypes.c_int * n
+    couts = [l["w"].shape[0] for l in layers]
+    ks = [l["w"].size // c for l, c in zip(layers, couts)]
+    check(lib.hpvg_sn_power_iter_multi(n, VP(*[l["w"].ptr for l in layers]), IA(*couts), IA(*ks),
+                                       VP(*[l["u"].ptr for l in layers]), VP(*[l["v"].ptr for l in layers]),
+                                       VP(*[l["sigma"].ptr for l in layers]), VP(*[l["bias"].ptr for l in layers]),
+                                       VP(*[l["aff"].ptr for l in layers]),
+                                       VP(*[(l["u_copy"].ptr if l.get("u_copy") is not None else None) for l in layers]),
+                                       VP(*[(l["v_copy"].ptr if l.get("v_copy") is not None else None) for l in layers]),
+                                       _s(stream)), "sn_power_iter_multi")
+
+
 def sn_power_iter(w, u, v, out=None, stream=None):
     """spectral_norm.py:142-151.  Updates u, v in place; returns a (2,) tensor (sigma, 1/sigma)."""
     cout = w.shape[0]

@@ -11,7 +11,7 @@ batch-statistics mode and update their moving stats (Q4), spectral-norm u/v adva
 import numpy as np
 
 from . import ops
-from .networks_3d import ConvLayer, Workspace
+from .networks_3d import BnStatsSlab, ConvLayer, Workspace, as5d
 from .ops import ACT_LRELU, ACT_NONE, ACT_TANH, CONV_64_16, CONV_64_64, CONV_8_64, OUT_BF16_CL, OUT_F32_NCDHW, OUT_F32_RAW
 from .runtime import BF16, F32, HpvgError, Tensor, from_numpy
 from .utils import images as uimg
@@ -22,6 +22,51 @@ NON_TRAINABLE = ("weight_u", "weight_v", "moving_mean", "moving_variance")
 def trainable_params(cell, prefix=""):
     """[(name, Tensor)] — mindspore Cell.trainable_params(): everything except u/v and the BN moving statistics."""
     return [(k, t) for k, t in cell.parameters_dict(prefix).items() if not k.endswith(NON_TRAINABLE)]
+
+
+class LossTerms:
+    """Loss value assembled on the device side without stalling the stream: every term is reduced into its own slot of
+    a small device vector; `finish()` enqueues ONE async copy into pinned host memory and returns a LazyLoss whose
+    float() waits for that copy only when the caller actually looks at the number (the reference's loop reads losses
+    just for logging, train_video.py:188-194)."""
+    SLOTS = 8
+
+    def __init__(self):
+        from .runtime import PinnedBuffer
+        self.dev = Tensor((self.SLOTS,), F32)
+        self.host = PinnedBuffer(self.SLOTS * 4)
+        self.coefs = []
+
+    def slot(self, coef):
+        i = len(self.coefs)
+        self.coefs.append(float(coef))
+        return self.dev.view((1,), F32, 4 * i)
+
+    def begin(self):
+        self.coefs = []
+
+    def finish(self, stream=None):
+        from ._lib import check, lib
+        from .runtime import Event, _s
+        check(lib.hpvg_d2h(self.host.ptr, self.dev.ptr, self.dev.nbytes, _s(stream)), "d2h")
+        ev = Event()
+        ev.record(stream)
+        return LazyLoss(self.host, list(self.coefs), ev)
+
+
+class LazyLoss:
+    def __init__(self, host, coefs, event):
+        self._host, self._coefs, self._event, self._value = host, coefs, event, None
+
+    def __float__(self):
+        if self._value is None:
+            self._event.sync()
+            vals = self._host.as_array((len(self._coefs),)) if self._coefs else []
+            self._value = float(sum(c * float(v) for c, v in zip(self._coefs, vals)))
+        return self._value
+
+    def __repr__(self):
+        return "LazyLoss(%r)" % float(self)
 
 
 class GradBook:
@@ -58,28 +103,36 @@ def _unit_affine(stream=None):
     return t
 
 
-def layer_forward_train(layer, x_cl, ws, key, stream=None):
+def layer_forward_train(layer, x_cl, ws, key, stream=None, slab=None):
     """Forward of one ConvLayer keeping what its backward needs.  Returns (output, ctx)."""
     N, T, H, W, _ = x_cl.shape
     layer._prepare(True, stream)
     ctx = {"x": x_cl, "layer": layer}
     if layer.bn:
+        # conv(+bias) with the batch statistics accumulated in its epilogue, then ONE normalise+LeakyReLU pass
         y = ws.get(key + ".y", (N, T, H, W, layer.cout), BF16)
+        stats = slab.take() if slab is not None else Tensor((2, 64), "float64").zero_(stream)
         ops.conv3d_cl_any(x_cl, layer.p["weight"], layer._aff, ACT_NONE, layer.cin, layer.cout, out=y,
-                          wimgs=layer._wimgs, stream=stream)
+                          wimgs=layer._wimgs, stats=stats, stream=stream)
         a = ws.get(key + ".a", (N, T, H, W, layer.cout), BF16)
-        a, saved = ops.bn_train_cl(y, layer.p["gamma"], layer.p["beta"], layer.p["moving_mean"],
-                                   layer.p["moving_variance"], layer.act, out=a, stream=stream)
-        layer._aff = None
+        saved = ws.get(key + ".saved", (4, 64), F32)
+        ops.bn_train_fused_cl(y, stats, layer.p["gamma"], layer.p["beta"], layer.p["moving_mean"],
+                              layer.p["moving_variance"], layer.act, out=a, saved=saved, stream=stream)
+        layer._aff_eval = None
         ctx.update(y=y, a=a, saved=saved)
         return a, ctx
     if layer.sn:
-        # keep this pass's (sigma, u, v): the chain rule needs the values used by THIS forward (Q5)
-        sig = Tensor((2,), F32).copy_(layer._sigma, stream)
-        u = Tensor(layer.p["weight_u"].shape, F32).copy_(layer.p["weight_u"], stream)
-        v = Tensor(layer.p["weight_v"].shape, F32).copy_(layer.p["weight_v"], stream)
-        aff = Tensor(layer._aff.shape, F32).copy_(layer._aff, stream)
-        ctx.update(sigma=sig, u=u, v=v, aff=aff)
+        # the chain rule needs the (sigma, u, v) used by THIS forward (Q5): either the per-pass snapshot tensors the
+        # batched power iteration wrote (sn_tape_entries), or explicit copies
+        if layer._cur_u is not None:
+            ctx.update(sigma=layer._cur_sigma, u=layer._cur_u, v=layer._cur_v, aff=layer._cur_aff)
+        else:
+            sig = Tensor((2,), F32).copy_(layer._cur_sigma, stream)
+            u = Tensor(layer.p["weight_u"].shape, F32).copy_(layer.p["weight_u"], stream)
+            v = Tensor(layer.p["weight_v"].shape, F32).copy_(layer.p["weight_v"], stream)
+            aff = Tensor(layer._aff.shape, F32).copy_(layer._aff, stream)
+            ctx.update(sigma=sig, u=u, v=v, aff=aff)
+            layer._aff = aff
     if layer.cout <= 4:
         raise HpvgError("tail convs are handled by the block-level code")
     a = ws.get(key + ".a", (N, T, H, W, layer.cout), BF16)
@@ -87,6 +140,20 @@ def layer_forward_train(layer, x_cl, ws, key, stream=None):
                       wimgs=layer._wimgs, stream=stream)
     ctx.update(a=a)
     return a, ctx
+
+
+def sn_tape_prepare(layers, ws, tag, stream=None):
+    """Batched power iteration (one launch) for a training pass: (sigma, 1/sigma), the conv epilogue vectors and a
+    snapshot of the updated u, v go to per-pass workspace tensors that the backward of this pass reads."""
+    from .networks_3d import sn_prepare_batch
+    sn = [l for l in layers if l.sn]
+    entries = []
+    for i, l in enumerate(sn):
+        k = "%s.sn%d" % (tag, i)
+        entries.append(l.sn_entry(sigma=ws.get(k + ".sigma", (2,), F32), aff=ws.get(k + ".aff", (2, 64), F32),
+                                  u_copy=ws.get(k + ".u", l.p["weight_u"].shape, F32),
+                                  v_copy=ws.get(k + ".v", l.p["weight_v"].shape, F32)))
+    sn_prepare_batch(sn, stream, entries=entries)
 
 
 def _dgrad_wimgs(layer, stream=None):
@@ -184,12 +251,12 @@ def _colsum_wide(g_cl, out, stream=None):
 
 
 # ================================================================================================ block level
-def block_forward_train(block, x_cl, residual, ws, tag, stream=None, x_wide=None, out=None):
+def block_forward_train(block, x_cl, residual, ws, tag, stream=None, x_wide=None, out=None, slab=None):
     """decoder / body stage in training mode: returns (tanh(block(x) [+ residual]) fp32 ncdhw, ctxs)."""
     ctxs = []
     h = x_cl
     for j, layer in enumerate(block.layers[:-1]):
-        h, c = layer_forward_train(layer, h, ws, "%s.%d" % (tag, j), stream)
+        h, c = layer_forward_train(layer, h, ws, "%s.%d" % (tag, j), stream, slab=slab)
         if j == 0 and x_wide is not None:
             c["x_wide"] = x_wide
         ctxs.append(c)
@@ -230,14 +297,15 @@ class GeneratorTrainer:
     def __init__(self, netG):
         self.net = netG
         self.ws = Workspace()
+        self.slab = BnStatsSlab()
 
     def _stage_input(self, x_prev, idx, noise_amp, is_random, noises, stream, wide):
         net, opt = self.net, self.net.opt
-        size = uimg.scale_shape(opt, idx + 1)
+        size = net.stage_shape(idx + 1)
         N = x_prev.shape[0]
         up = self.ws.get("up%d" % idx, (N, opt.nc_im) + size, F32)
         xin = self.ws.get("xin%d" % idx, (N,) + size + (8,), BF16)
-        add_noise = is_random and opt.vae_levels <= idx + 1
+        add_noise = net.noise_at(idx + 1, is_random)
         noise_t, seed, amp = None, 0, 0.0
         if add_noise:
             amp = float(noise_amp[idx + 1])
@@ -262,8 +330,11 @@ class GeneratorTrainer:
         net, opt, ws = self.net, self.net.opt, self.ws
         out = {"body_ctx": {}, "ups": {}}
         mu = logvar = None
+        slab = self.slab
+        slab.reset(stream)
         if noise_init is None:
             enc = net.encode
+            sn_tape_prepare(enc._features.layers, ws, "enc", stream)
             x_cl = ops.pack_cl(video, c_pitch=8, stream=stream)
             ectx = []
             h = x_cl
@@ -289,14 +360,14 @@ class GeneratorTrainer:
             z = noise_init
         N = z.shape[0]
         z_cl = ops.pack_cl(z, out=ws.get("z", (N,) + tuple(z.shape[2:]) + (z.shape[1],), BF16), stream=stream)
-        vae_out, dctx = block_forward_train(net.decoder, z_cl, None, ws, "dec", stream,
+        vae_out, dctx = block_forward_train(net.decoder, z_cl, None, ws, "dec", stream, slab=slab,
                                             out=ws.get("vae_out", (N, opt.nc_im) + tuple(z.shape[2:]), F32))
         out.update(vae_out=vae_out, dec_ctx=dctx, mu=mu, logvar=logvar)
         x = vae_out
         for idx in range(len(net.body)):
             keep = save_from is not None and idx >= save_from
             up, xin, xw = self._stage_input(x, idx, noise_amp, is_random, noises, stream, wide=keep)
-            x, bctx = block_forward_train(net.body[idx], xin, up, ws, "s%d" % idx, stream, x_wide=xw,
+            x, bctx = block_forward_train(net.body[idx], xin, up, ws, "s%d" % idx, stream, x_wide=xw, slab=slab,
                                           out=ws.get("out%d" % idx, up.shape, F32))
             if keep:
                 out["body_ctx"][idx] = bctx
@@ -313,12 +384,16 @@ class GWithLoss:
         self.rec_weight, self.kl_weight, self.disc_loss_weight = opt.rec_weight, opt.kl_weight, opt.disc_loss_weight
         self.trainer = GeneratorTrainer(netG)
         self.grads = GradBook()
+        self.terms = LossTerms()
 
     def grad(self, real, real_zero, noise_init, noise_amps, isVAE=False, trainable_body=(), train_codec=False,
              noises=None, z_pred=None, eps=None, stream=None):
         """trainable_body: indices of body stages whose parameters are optimised (train_video.py:76-105);
         train_codec: whether encode/decoder are optimised (VAE phase)."""
         net, opt, tr = self._netG, self.opt, self.trainer
+        real, real_zero, noise_init, z_pred, eps = (as5d(t) for t in (real, real_zero, noise_init, z_pred, eps))
+        if noises is not None:
+            noises = {k: as5d(v) for k, v in noises.items()}
         g = self.grads
         g.zero(stream)
         nb = len(net.body)
@@ -331,12 +406,13 @@ class GWithLoss:
         x, vae_out = fw["x"], fw["vae_out"]
         ws = tr.ws
         n = x.size
-        loss_t = ops.mse(x, real, stream=stream)
-        total = self.rec_weight * float(loss_t.numpy(stream)[0])
+        terms = self.terms
+        terms.begin()
+        ops.mse(x, real, out=terms.slot(self.rec_weight), stream=stream)
         g_x = ops.mse_grad(x, real, self.rec_weight * 2.0 / n, g=ws.get("g_x", x.shape, F32), stream=stream)
         if isVAE:
-            total += self.rec_weight * float(ops.mse(vae_out, real_zero, stream=stream).numpy(stream)[0])
-            total += self.kl_weight * float(ops.kl_criterion(fw["mu"], fw["logvar"], stream=stream).numpy(stream)[0])
+            ops.mse(vae_out, real_zero, out=terms.slot(self.rec_weight), stream=stream)
+            ops.kl_criterion(fw["mu"], fw["logvar"], out=terms.slot(self.kl_weight), stream=stream)
         # ---- backward through the refinement stages (networks_3d.py:434-451)
         g_cur = g_x
         lowest = save_from
@@ -382,8 +458,8 @@ class GWithLoss:
             # ---- adversarial term: value only, no gradient reaches G (Q1, losses.py:93-98)
             fw2 = tr.forward(None, noise_amps, noise_init=noise_init, is_random=True, noises=noises, stream=stream)
             d_out = self._netD(fw2["x"], stream=stream)
-            total += -self.disc_loss_weight * float(ops.mean(d_out, stream=stream).numpy(stream)[0])
-        return total, g
+            ops.mean(d_out, out=terms.slot(-self.disc_loss_weight), stream=stream)
+        return terms.finish(stream), g
 
 
 def _add_cl(a_cl, b_cl, ws, stream=None):
@@ -404,6 +480,7 @@ class DWithLoss:
         self.trainer = GeneratorTrainer(netG)
         self.ws = Workspace()
         self.grads = GradBook()
+        self.terms = LossTerms()
 
     # ---- one D forward keeping the tape
     def _forward(self, x, tag, stream):
@@ -413,6 +490,7 @@ class DWithLoss:
         xw = ops.pack_cl(x, c_pitch=64, zero_to=64, out=ws.get(tag + ".xw", (N,) + tuple(x.shape[2:]) + (64,), BF16),
                          stream=stream)
         ctxs = []
+        sn_tape_prepare(self._layers(), ws, tag, stream)
         h, c = layer_forward_train(D.head, x8, ws, tag + ".h", stream)
         c["x_wide"] = xw
         ctxs.append(c)
@@ -459,7 +537,8 @@ class DWithLoss:
             ga = conv_backward(layers[j], ctxs[j], deltas[j], g, ws, "%s.g%d" % (tag, j), True, False,
                                inv_sigma_aff=ctxs[j]["aff"], stream=stream)
         grad_x = ga                                                   # fp32 ncdhw (N, 3, T, H, W)
-        Gx, gp = ops.gp_grad(grad_x, self.lambda_grad, Gout=ws.get(tag + ".G", grad_x.shape, F32), stream=stream)
+        Gx, gp = ops.gp_grad(grad_x, self.lambda_grad, Gout=ws.get(tag + ".G", grad_x.shape, F32),
+                             gp=self.terms.slot(1.0), stream=stream)
         # (2) d GP / d W: push G forward through the SAME linear maps, masked by the LeakyReLU pattern of xhat
         xi_wide = ops.pack_cl(Gx, c_pitch=64, zero_to=64, out=ws.get(tag + ".xiw", (N, T, H, W, 64), BF16),
                               stream=stream)
@@ -483,22 +562,27 @@ class DWithLoss:
         return gp
 
     def grad(self, real, noise_init, noise_amps, noises=None, fake=None, stream=None):
+        real, noise_init, fake = as5d(real), as5d(noise_init), as5d(fake)
+        if noises is not None:
+            noises = {k: as5d(v) for k, v in noises.items()}
         g = self.grads
         g.zero(stream)
         if fake is None:
             fake = self.trainer.forward(None, noise_amps, noise_init=noise_init, is_random=True, noises=noises,
                                         stream=stream)["x"]                      # stop_gradient (losses.py:29-30)
         V = real.size // real.shape[1]
+        terms = self.terms
+        terms.begin()
         out_r, ctx_r = self._forward(real, "R", stream)
         self._backward_first_order(ctx_r, -1.0 / V, "R", stream)
         out_f, ctx_f = self._forward(fake, "F", stream)
         self._backward_first_order(ctx_f, 1.0 / V, "F", stream)
         xhat = ops.lerp(real, fake, self.alpha, out=self.ws.get("xhat", real.shape, F32), stream=stream)
         out_x, ctx_x = self._forward(xhat, "X", stream)
-        gp = self._gradient_penalty(ctx_x, "X", stream)
-        loss = (-float(ops.mean(out_r, stream=stream).numpy(stream)[0]) +
-                float(ops.mean(out_f, stream=stream).numpy(stream)[0]) + float(gp.numpy(stream)[0]))
-        return loss, g
+        self._gradient_penalty(ctx_x, "X", stream)
+        ops.mean(out_r, out=terms.slot(-1.0), stream=stream)
+        ops.mean(out_f, out=terms.slot(1.0), stream=stream)
+        return terms.finish(stream), g
 
 
 def _scale_only(aff, zero_shift, ws, tag, j, stream):

@@ -243,7 +243,7 @@ def init_generator_params(opt, n_body, seed=0, nd=3):
     return p
 
 
-def randomize_bn_stats(p, seed=1, opt=None, n_calib=1):
+def randomize_bn_stats(p, seed=1, opt=None, n_calib=1, nd=3):
     """Trained-checkpoint stand-in: moving statistics := the batch statistics of one random-mode forward (so
     activations stay O(1) instead of vanishing/saturating), then perturbed by a few percent so that eval-mode
     parity tests exercise a non-trivial BatchNorm fold; beta / hidden biases get small random values."""
@@ -256,14 +256,15 @@ def randomize_bn_stats(p, seed=1, opt=None, n_calib=1):
         opt = default_opt()
     pt = to_torch(p)
     nb = n_body(pt)
-    z = torch.from_numpy(rng.standard_normal((n_calib, opt.latent_dim) + scale_shape(opt, 0)).astype(np.float32))
-    noises = {s: torch.from_numpy(rng.standard_normal((n_calib, opt.nc_im) + scale_shape(opt, s)).astype(np.float32))
+    shp = scale_shape if nd == 3 else scale_shape_2d
+    z = torch.from_numpy(rng.standard_normal((n_calib, opt.latent_dim) + shp(opt, 0)).astype(np.float32))
+    noises = {s: torch.from_numpy(rng.standard_normal((n_calib, opt.nc_im) + shp(opt, s)).astype(np.float32))
               for s in range(1, nb + 1)}
     saved, BN_MOMENTUM = BN_MOMENTUM, 0.0
     try:
         with torch.no_grad():
             generator_forward(None, [1.0] + [0.1] * nb, pt, opt, noise_init=z, is_random=True, training=True,
-                              noises=noises)
+                              noises=noises, nd=nd)
     finally:
         BN_MOMENTUM = saved
     for k in list(p):
@@ -537,15 +538,15 @@ def adam_step(w, g, m, v, step, lr, beta1=0.5, beta2=0.999, eps=1e-8):
 
 
 def g_loss(real, real_zero, noise_init, noise_amps, pg, pd, opt, is_vae, z_pred=None, eps=None, noises=None,
-           is_training_flag=False):
+           is_training_flag=False, nd=3):
     """GWithLoss.construct (losses.py:70-103) in set_train() mode (BatchNorm batch statistics)."""
     x, vae_out, mu, logvar = generator_forward(real_zero, noise_amps, pg, opt, is_random=False, training=True,
-                                               is_training_flag=is_training_flag, eps=eps, z_pred=z_pred)
+                                               is_training_flag=is_training_flag, eps=eps, z_pred=z_pred, nd=nd)
     if is_vae:
         rec = mse(x, real) + mse(vae_out, real_zero)
         return opt.rec_weight * rec + opt.kl_weight * kl_criterion(mu, logvar)
     total = opt.rec_weight * mse(x, real)
     fake, _ = generator_forward(None, noise_amps, pg, opt, noise_init=noise_init, is_random=True, training=True,
-                                noises=noises)
+                                noises=noises, nd=nd)
     fake = fake.detach()                                                          # Q1 (losses.py:94)
     return total + (-discriminator(fake, pd, opt).mean() * opt.disc_loss_weight)

@@ -133,4 +133,4 @@ def test_conv2d_is_t1(hpvg_gpu):
 
 def test_conv_empty_input_is_noop(hpvg_gpu):
     hp = hpvg_gpu
-    assert hp.lib.hpvg_conv_cl(0, 0, 4, 8, 8, None, 64, None, None, None, 0, 0, None, 64, 0, 64, None, None) == 0
+    assert hp.lib.hpvg_conv_cl(0, 0, 4, 8, 8, None, 64, None, None, None, 0, 0, None, 64, 0, 64, None, None, None) == 0

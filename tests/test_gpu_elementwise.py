@@ -97,6 +97,72 @@ def test_bn_train_cl(hpvg_gpu):
     assert np.allclose(tmv.numpy(), p["1.bn2d.moving_variance"].numpy(), rtol=1e-4)
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 17, 13), (1, 4, 33, 41), (3, 1, 9, 70)])
+def test_conv_epilogue_bn_statistics_and_one_pass_bn(hpvg_gpu, shape):
+    """Training-mode BatchNorm with the batch statistics fused into the conv epilogue (ragged tiles included):
+    sums must equal the sums over the stored bf16 output, and conv -> BN -> LeakyReLU must match the oracle."""
+    hp, ops = hpvg_gpu, hpvg_gpu.ops
+    rng = np.random.default_rng(21)
+    N, T, H, W = shape
+    x = bf16_round(rng.standard_normal((N, 64, T, H, W)))
+    w = bf16_round(rng.standard_normal((64, 64, 3, 3, 3)) * 0.05)
+    bias = (0.1 * rng.standard_normal(64)).astype(np.float32)
+    gamma = (1 + 0.1 * rng.standard_normal(64)).astype(np.float32)
+    beta = (0.1 * rng.standard_normal(64)).astype(np.float32)
+    mm, mv = np.zeros(64, np.float32), np.ones(64, np.float32)
+    tmm, tmv = hp.from_numpy(mm), hp.from_numpy(mv)
+    stats = hp.Tensor((2, 64), hp.F64).zero_()
+    aff = ops.affine_from_bias(hp.from_numpy(bias))
+    y_cl = ops.conv3d_cl_any(ops.pack_cl(hp.from_numpy(x)), hp.from_numpy(w), aff, ops.ACT_NONE, 64, 64, stats=stats)
+    y = ops.unpack_cl(y_cl).numpy().astype(np.float64)
+    st = stats.numpy()
+    assert np.allclose(st[0], y.sum(axis=(0, 2, 3, 4)), rtol=1e-5, atol=1e-3)
+    assert np.allclose(st[1], (y * y).sum(axis=(0, 2, 3, 4)), rtol=1e-5, atol=1e-3)
+    saved = hp.Tensor((4, 64), hp.F32)
+    a_cl = ops.bn_train_fused_cl(y_cl, stats, hp.from_numpy(gamma), hp.from_numpy(beta), tmm, tmv, saved=saved)
+    p = {"0.weight": torch.from_numpy(w), "0.bias": torch.from_numpy(bias),
+         "1.bn2d.gamma": torch.from_numpy(gamma), "1.bn2d.beta": torch.from_numpy(beta),
+         "1.bn2d.moving_mean": torch.from_numpy(mm.copy()), "1.bn2d.moving_variance": torch.from_numpy(mv.copy())}
+    ref = orc.conv_block(torch.from_numpy(x), p, "", 1, True).numpy()
+    assert rel_l2(ops.unpack_cl(a_cl).numpy(), ref) < 5e-3
+    assert np.allclose(tmm.numpy(), p["1.bn2d.moving_mean"].numpy(), atol=1e-3)
+    assert np.allclose(tmv.numpy(), p["1.bn2d.moving_variance"].numpy(), rtol=5e-3)
+    sv = saved.numpy()
+    mean = y.mean(axis=(0, 2, 3, 4))
+    var = y.var(axis=(0, 2, 3, 4))
+    assert np.allclose(sv[2], mean, atol=1e-5) and np.allclose(sv[3], 1 / np.sqrt(var + 1e-5), rtol=1e-5)
+    assert np.allclose(sv[0], gamma * sv[3], rtol=1e-6) and np.allclose(sv[1], beta - sv[2] * sv[0], atol=1e-5)
+
+
+def test_sn_power_iter_multi_matches_single_layer_oracle(hpvg_gpu):
+    """All SN layers of a network in one launch: per-layer sigma, u, v, the snapshot copies and the fused
+    (1/sigma, bias) epilogue vectors."""
+    hp, ops = hpvg_gpu, hpvg_gpu.ops
+    rng = np.random.default_rng(31)
+    layers, refs = [], []
+    for cin in (3, 64, 64):
+        w = (rng.standard_normal((64, cin, 3, 3, 3)) * 0.02).astype(np.float32)
+        u = orc._l2normalize_np(rng.standard_normal((64, 1)).astype(np.float32))
+        v = orc._l2normalize_np(rng.standard_normal((cin * 27, 1)).astype(np.float32))
+        b = rng.standard_normal(64).astype(np.float32)
+        layers.append({"w": hp.from_numpy(w), "u": hp.from_numpy(u), "v": hp.from_numpy(v), "bias": hp.from_numpy(b),
+                       "sigma": hp.Tensor((2,), hp.F32), "aff": hp.Tensor((2, 64), hp.F32),
+                       "u_copy": hp.Tensor((64, 1), hp.F32), "v_copy": hp.Tensor((cin * 27, 1), hp.F32)})
+        refs.append([w, torch.from_numpy(u), torch.from_numpy(v), b])
+    for it in range(2):
+        ops.sn_power_iter_multi(layers)
+        for l, ref in zip(layers, refs):
+            w, u_, v_, b = ref
+            sigma, un, vn = orc.sn_power_iteration(torch.from_numpy(w), u_, v_)
+            ref[1], ref[2] = un, vn
+            sg = l["sigma"].numpy()
+            assert abs(sg[0] - float(sigma)) / float(sigma) < 1e-5 and abs(sg[0] * sg[1] - 1) < 1e-6
+            assert np.allclose(l["u"].numpy(), un.numpy(), atol=1e-5) and np.allclose(l["v"].numpy(), vn.numpy(), atol=1e-5)
+            assert np.array_equal(l["u"].numpy(), l["u_copy"].numpy()) and np.array_equal(l["v"].numpy(), l["v_copy"].numpy())
+            aff = l["aff"].numpy()
+            assert np.allclose(aff[0], sg[1]) and np.array_equal(aff[1], b)
+
+
 @pytest.mark.parametrize("cin", [3, 64])
 def test_sn_power_iter(hpvg_gpu, cin):
     hp, ops = hpvg_gpu, hpvg_gpu.ops

@@ -140,7 +140,7 @@ def test_vae_phase_g_step(hpvg_gpu):
     gl = T.GWithLoss(opt, D, G)
     loss, book = gl.grad(hp.from_numpy(real), hp.from_numpy(real_zero), None, amps, isVAE=True, trainable_body=(0,),
                          train_codec=True, z_pred=hp.from_numpy(z))
-    assert abs(loss - float(loss_ref)) < 2e-2 * abs(float(loss_ref))
+    assert abs(float(loss) - float(loss_ref)) < 2e-2 * abs(float(loss_ref))
     got = _grads_by_name(G, book, names)
     # encoder: only the (smooth) KL term reaches it -> tight; decoder/body: conditioning-limited (see note above)
     _report(got, ref, 1e-2, "VAE phase / encoder", only=lambda k: k.startswith("encode."))
@@ -181,7 +181,7 @@ def test_gan_phase_g_and_d_steps(hpvg_gpu):
     dl = T.DWithLoss(opt, D, G, alpha=alpha)
     dloss, dbook = dl.grad(hp.from_numpy(real), hp.from_numpy(noise_init), amps,
                            noises={k: hp.from_numpy(v) for k, v in nz.items()})
-    assert abs(dloss - float(dloss_ref)) < 2e-2 * max(abs(float(dloss_ref)), 1e-2), (dloss, float(dloss_ref))
+    assert abs(float(dloss) - float(dloss_ref)) < 2e-2 * max(abs(float(dloss_ref)), 1e-2), (float(dloss), float(dloss_ref))
     _report(_grads_by_name(D, dbook, dnames), dref, E2E_BN_TOL, "D step (incl. WGAN-GP double backward)",
             min_cos=E2E_BN_COS)
     # spectral-norm state advanced three times (real, fake, xhat) exactly like the oracle's (Q5)
@@ -199,7 +199,7 @@ def test_gan_phase_g_and_d_steps(hpvg_gpu):
     gloss, gbook = gl.grad(hp.from_numpy(real), hp.from_numpy(real_zero), hp.from_numpy(noise_init), amps, isVAE=False,
                            trainable_body=(2,), z_pred=hp.from_numpy(z_pred),
                            noises={k: hp.from_numpy(v) for k, v in nz.items()})
-    assert abs(gloss - float(gloss_ref)) < 2e-2 * abs(float(gloss_ref)), (gloss, float(gloss_ref))
+    assert abs(float(gloss) - float(gloss_ref)) < 2e-2 * abs(float(gloss_ref)), (float(gloss), float(gloss_ref))
     _report(_grads_by_name(G, gbook, gnames), gref, E2E_BN_TOL, "G step (GAN phase)", min_cos=E2E_BN_COS)
 
 
@@ -223,7 +223,7 @@ def test_train_one_step_updates_parameters_like_clipped_adam(hpvg_gpu):
     before = {k: t.numpy() for k, t in T.trainable_params(block)}
     loss = step(hp.from_numpy(real), hp.from_numpy(real_zero), hp.from_numpy(noise_init), amps, isVAE=False,
                 trainable_body=(2,), z_pred=hp.from_numpy(z_pred), noises={k: hp.from_numpy(v) for k, v in nz.items()})
-    assert np.isfinite(loss)
+    assert np.isfinite(float(loss))
     grads = {k: gl.grads.of(t).numpy() for k, t in T.trainable_params(block)}
     for k, t in T.trainable_params(block):
         want, _, _ = orc.adam_step(before[k], orc.clip_by_norm(grads[k], opt.grad_clip), np.zeros_like(before[k]),

@@ -15,7 +15,7 @@ st = hpvg.Stream()
 rng = np.random.default_rng(0)
 
 
-def bench(mode_name, cin, cout, shape, iters=10):
+def bench(mode_name, cin, cout, shape, iters=10, stats=False):
     N, T, H, W = shape
     cpad = 8 if cin <= 8 else cin
     x_cl = hpvg.Tensor((N, T, H, W, cpad), hpvg.BF16).zero_()
@@ -29,8 +29,9 @@ def bench(mode_name, cin, cout, shape, iters=10):
                                   out=out, cout_real=cout, stream=st)
     else:
         out = hpvg.Tensor((N, T, H, W, 64), hpvg.BF16)
+        stt = hpvg.Tensor((2, 64), hpvg.F64).zero_() if stats else None
         run = lambda: ops.conv_cl(mode, x_cl, wi, aff, aff.view((64,), hpvg.F32, 256), ops.ACT_LRELU, ops.OUT_BF16_CL,
-                                  out=out, stream=st)
+                                  out=out, stats=stt, stream=st)
     for _ in range(3):
         run()
     st.sync()
@@ -43,13 +44,20 @@ def bench(mode_name, cin, cout, shape, iters=10):
     ms = e0.elapsed_ms(e1) / iters
     vox = N * T * H * W
     flops = 2.0 * 27 * cin * cout * vox
-    print("%-10s %-22s %8.3f ms  %8.1f TFLOP/s (algorithmic)  %6.2f ns/voxel" %
-          (mode_name, shape, ms, flops / ms / 1e9, ms * 1e6 / vox), flush=True)
+    print("%-16s %-22s %8.3f ms  %8.1f TFLOP/s (algorithmic)  %6.2f ns/voxel" %
+          (mode_name + ("+bnstats" if stats else ""), shape, ms, flops / ms / 1e9, ms * 1e6 / vox), flush=True)
 
 
+if len(sys.argv) > 1:   # e.g. `perf_conv.py 64 64 8,13,192,257 [stats]` : one case only (ncu captures)
+    cin, cout = int(sys.argv[1]), int(sys.argv[2])
+    shape = tuple(int(v) for v in sys.argv[3].split(","))
+    bench("%d->%d" % (cin, cout), cin, cout, shape, iters=3, stats=len(sys.argv) > 4)
+    sys.exit(0)
 for shape in [(1, 13, 192, 257), (1, 16, 192, 257), (4, 13, 192, 257), (8, 13, 192, 257), (1, 7, 153, 204),
               (16, 4, 24, 33), (64, 4, 24, 33)]:
     bench("64->64", 64, 64, shape)
+for shape in [(1, 13, 192, 257), (8, 13, 192, 257)]:
+    bench("64->64", 64, 64, shape, stats=True)
 for shape in [(1, 13, 192, 257), (8, 13, 192, 257)]:
     bench("64->3", 64, 3, shape)
     bench("3->64", 3, 64, shape)
