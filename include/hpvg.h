@@ -191,6 +191,10 @@ int hpvg_mse_grad(const float* d_out, const float* d_target, long long n, float 
 int hpvg_tanh_bwd(const float* d_g, const float* d_out, long long n, float* d_gpre, void* stream);
 int hpvg_axpby(float a, const float* d_x, float b, float* d_y, long long n, void* stream); /* y = a*x + b*y */
 int hpvg_fill(float* d_y, float value, long long n, void* stream);
+/* dst[i] = src[i*stride + offset], i < n (e.g. one filter tap of a weight-gradient tensor: the 64x64 second-moment
+ * matrix of a feature map for sinFID, src/sinFID/fid_score.py:176-177) */
+int hpvg_gather_strided(const float* d_src, long long n, long long stride, long long offset, float* d_dst,
+                        void* stream);
 int hpvg_channel_sum(const float* d_g, int N, int C, long long spatial, int accumulate, float* d_out, void* stream);
 int hpvg_kl_grad(const float* d_mu, const float* d_logvar, long long n, float coef, float* d_gmu, float* d_glogvar,
                  void* stream);

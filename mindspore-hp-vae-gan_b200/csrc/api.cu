@@ -436,6 +436,12 @@ int hpvg_fill(float* y, float v, long long n, void* st) {
   KL(hpvg::ew_fill(y, v, n, S(st)), 1);
   return HPVG_OK;
 }
+int hpvg_gather_strided(const float* src, long long n, long long stride, long long offset, float* dst, void* st) {
+  if (n <= 0) return HPVG_OK;
+  if (!src || !dst || stride < 1 || offset < 0) return fail(HPVG_E_ARG, "gather_strided: bad arguments");
+  KL(hpvg::ew_gather_strided(src, n, stride, offset, dst, S(st)), 1);
+  return HPVG_OK;
+}
 int hpvg_channel_sum(const float* g, int N, int C, long long sp, int accumulate, float* out, void* st) {
   if (N <= 0 || C <= 0 || sp <= 0) return fail(HPVG_E_ARG, "channel_sum: empty input");
   if (!g_sums) return fail(HPVG_E_ARG, "hpvg_init was not called");

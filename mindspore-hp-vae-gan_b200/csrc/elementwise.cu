@@ -777,6 +777,13 @@ __global__ void axpby_kernel(float a, const float* __restrict__ x, float b, floa
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     y[i] = a * x[i] + (b == 0.f ? 0.f : b * y[i]);
 }
+// dst[i] = src[i*stride + offset]   (e.g. one tap of a (Cout,Cin,27) weight-gradient tensor)
+__global__ void gather_strided_kernel(const float* __restrict__ src, long long n, long long stride, long long offset,
+                                      float* __restrict__ dst) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] = src[i * stride + offset];
+}
 __global__ void fill_kernel(float* __restrict__ y, float v, long long n) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
@@ -1097,6 +1104,12 @@ cudaError_t ew_tanh_bwd(const float* g, const float* out, long long n, float* gp
 }
 cudaError_t ew_axpby(float a, const float* x, float b, float* y, long long n, cudaStream_t st) {
   axpby_kernel<<<grid_for(n, 256), 256, 0, st>>>(a, x, b, y, n);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_gather_strided(const float* src, long long n, long long stride, long long offset, float* dst,
+                              cudaStream_t st) {
+  gather_strided_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, n, stride, offset, dst);
   LAUNCH_CHECK();
   return cudaSuccess;
 }

@@ -76,6 +76,8 @@ cudaError_t ew_diff_scale(const float* a, const float* b, long long n, float coe
 cudaError_t ew_tanh_bwd(const float* g, const float* out, long long n, float* gpre, cudaStream_t st);
 cudaError_t ew_axpby(float a, const float* x, float b, float* y, long long n, cudaStream_t st);
 cudaError_t ew_fill(float* y, float v, long long n, cudaStream_t st);
+cudaError_t ew_gather_strided(const float* src, long long n, long long stride, long long offset, float* dst,
+                              cudaStream_t st);
 cudaError_t ew_channel_sum_ncdhw(const float* g, int N, int C, long long sp, int accumulate, double* scratch,
                                  float* out, cudaStream_t st);
 cudaError_t ew_kl_grad(const float* mu, const float* lv, long long n, float coef, float* gmu, float* glv,

@@ -83,6 +83,7 @@ _SIGS = {
     "hpvg_tanh_bwd": ([vp, vp, ll, vp, vp], c_int),
     "hpvg_axpby": ([f, vp, f, vp, ll, vp], c_int),
     "hpvg_fill": ([vp, f, ll, vp], c_int),
+    "hpvg_gather_strided": ([vp, ll, ll, ll, vp, vp], c_int),
     "hpvg_channel_sum": ([vp, i, i, ll, i, vp, vp], c_int),
     "hpvg_kl_grad": ([vp, vp, ll, f, vp, vp, vp], c_int),
     "hpvg_sn_grad": ([vp, vp, vp, vp, vp, i, i, i, vp, vp], c_int),

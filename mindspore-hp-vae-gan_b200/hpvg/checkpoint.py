@@ -1,0 +1,138 @@
+"""Checkpoint / state I/O with the reference's parameter names.
+
+The reference saves one `netG_{i}.ckpt` / `netD_{i}.ckpt` per scale plus `intermediate.json`
+(`train_video.py:224-227`, `src/utils/saver.py:55-76`) and can import the original PyTorch `.pth` through the key map of
+`src/tools/pt2ms.py:129-188`.  MindSpore's `.ckpt` is a protobuf that only MindSpore can parse, so the container here
+is `.npz` — ONE array per parameter under exactly the reference's key (`decoder.0.1.bn2d.moving_mean`, ...), which is
+what `mindspore.load_param_into_net` matches on.  A maintainer converts with
+`np.savez(path, **{k: v.asnumpy() for k, v in mindspore.load_checkpoint(f).items()})`."""
+import json
+import os
+import re
+
+import numpy as np
+
+from .runtime import HpvgError
+
+
+def state_dict(cell):
+    """name -> float32 numpy array (device -> host copy of every parameter of `cell`)."""
+    return {k: t.numpy() for k, t in cell.parameters_dict().items()}
+
+
+def save_checkpoint(cell, filename):
+    """saver.py:55-57.  Writes `<filename>` (suffix forced to .npz)."""
+    filename = _npz(filename)
+    os.makedirs(os.path.dirname(os.path.abspath(filename)), exist_ok=True)
+    np.savez(filename, **state_dict(cell))
+    return filename
+
+
+def load_checkpoint(filename):
+    """saver.py:59-63 -> {name: array}."""
+    with np.load(_npz(filename)) as f:
+        return {k: f[k] for k in f.files}
+
+
+def load_param_into_net(cell, params, strict=True):
+    """mindspore.load_param_into_net: match by name; returns the list of parameters that were NOT loaded."""
+    mine = cell.parameters_dict()
+    missing = [k for k in mine if k not in params]
+    if strict and missing:
+        raise HpvgError("checkpoint is missing %d parameters, e.g. %s" % (len(missing), missing[:3]))
+    cell.load_parameters(params, strict=False)
+    return missing
+
+
+def save_json(obj, filename):
+    """saver.py:65-68 (`intermediate.json`: {'noise_amps': [...], 'scale_idx': i}, train_video.py:224)."""
+    os.makedirs(os.path.dirname(os.path.abspath(filename)), exist_ok=True)
+    with open(filename, "w+") as f:
+        json.dump(obj, f)
+
+
+def load_json(filename):
+    with open(filename, "r") as f:
+        return json.load(f)
+
+
+def _npz(filename):
+    root, ext = os.path.splitext(filename)
+    return filename if ext == ".npz" else root + ".npz"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Original-PyTorch key map (pt2ms.py:129-188 for 3-D, :30-89 for 2-D): `state` maps the PyTorch HP-VAE-GAN names
+# (encode.features.conv_block_i.conv.weight_orig, decoder.head.conv.weight, body.s.blockj.norm.running_mean, ...) to
+# arrays; the result uses this package's (= the MindSpore reference's) names.
+# ---------------------------------------------------------------------------------------------------------------------
+_BN = {"weight": "gamma", "bias": "beta", "running_mean": "moving_mean", "running_var": "moving_variance"}
+
+
+def _p2m(state, bn_prefix, n_layers):
+    out = {}
+    for key, value in state.items():
+        if key.endswith("num_batches_tracked"):
+            continue
+        parts = key.split(".")
+        new = []
+        i = 0
+        top = parts[0]
+        if top == "encode":
+            new.append("encode")
+            i = 1
+            if parts[i] == "features":
+                m = re.fullmatch(r"conv_block_(\d+)", parts[i + 1])
+                if not m:
+                    raise HpvgError("unexpected encoder key %s" % key)
+                new += ["_features", m.group(1)]
+                i += 2
+            elif parts[i] in ("mu", "logvar"):
+                new.append("_" + parts[i])
+                i += 1
+            rest = parts[i:]
+            if rest[0] == "conv":
+                rest = ["0"] + rest[1:]
+            rest = ["weight" if r == "weight_orig" else r for r in rest]
+            new += rest
+        elif top in ("decoder", "body"):
+            new.append(top)
+            i = 1
+            if top == "body":
+                new.append(parts[i])      # stage index
+                i += 1
+            blk = parts[i]
+            if blk == "head":
+                new.append("0")
+            elif blk == "tail":
+                new.append(str(n_layers + 1))
+            else:
+                m = re.fullmatch(r"block(\d+)", blk)
+                if not m:
+                    raise HpvgError("unexpected block key %s" % key)
+                new.append(str(int(m.group(1)) + 1))
+            rest = parts[i + 1:]
+            if rest and rest[0] == "conv":
+                new += ["0"] + rest[1:]
+            elif rest and rest[0] == "norm":
+                new += [bn_prefix.rstrip(".")] if bn_prefix == "1." else ["1", "bn2d"]
+                new.append(_BN.get(rest[1], rest[1]))
+            else:
+                new += rest              # plain tail conv: decoder.tail.weight -> decoder.6.weight
+        else:
+            new = parts
+        arr = np.asarray(value, np.float32)
+        if new[-1] in ("weight_u", "weight_v") and arr.ndim == 1:
+            arr = arr[:, None]           # pt2ms.py:185-186
+        out[".".join(new)] = arr
+    return out
+
+
+def p2m_HPVAEGAN_3d(state, num_layer=5):
+    """pt2ms.py:129-188."""
+    return _p2m(state.get("state_dict", state), "1.bn2d.", num_layer)
+
+
+def p2m_HPVAEGAN_2d(state, num_layer=5):
+    """pt2ms.py:30-89."""
+    return _p2m(state.get("state_dict", state), "1.", num_layer)

@@ -398,6 +398,13 @@ def fill(t, value, stream=None):
     return t
 
 
+def gather_tap(dw, tap, out, stream=None):
+    """out[co][ci] = dw[co][ci][tap] for a (Cout, Cin, kt, 3, 3) tensor."""
+    n = dw.shape[0] * dw.shape[1]
+    check(lib.hpvg_gather_strided(_p(dw), n, dw.size // n, int(tap), _p(out), _s(stream)), "gather_strided")
+    return out
+
+
 def channel_sum(g, out, accumulate=False, stream=None):
     N, C = g.shape[0], g.shape[1]
     check(lib.hpvg_channel_sum(_p(g), N, C, g.size // (N * C), 1 if accumulate else 0, _p(out), _s(stream)),

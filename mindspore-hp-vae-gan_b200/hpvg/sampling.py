@@ -45,3 +45,46 @@ def generate(netG, noise_amps, num_samples, rank=0, world=1, batch=8, seed=0, st
         if keep:
             outs.append(x.numpy(stream))
     return idxs, (np.concatenate(outs) if outs and keep else None)
+
+
+def generate_moments(netG, noise_amps, num_samples, features, comm=None, batch=8, seed=0, stream=None, keep=False):
+    """eval_video.py:53-82 + the statistics half of calculate_SVFID (fid_score.py:219-242), sharded:
+    every rank generates its samples, reduces each clip ON THE DEVICE to 4160 moment floats, and ONE all-gather
+    (NCCL over NVLink on GPUs) collects them.  Returns (rows (num_samples, 4160) in global sample order — identical on
+    every rank —, voxels per clip, local clips or None)."""
+    from . import fid
+    from .dist import SingleProcess, shard_rows, unshard_rows
+    comm = comm or SingleProcess()
+    opt = netG.opt
+    shp = z_init_size(opt, 1)[1:]
+    idx = shard_rows(num_samples, batch, comm.rank, comm.world)
+    rows = Tensor((len(idx), fid.MOMENT_FLOATS), F32).zero_(stream)
+    clips = []
+    count = None
+    for c0 in range(0, len(idx), batch):
+        chunk = [i for i in idx[c0:c0 + batch] if i >= 0]
+        if not chunk:
+            continue
+        z = np.stack([host_noise_for_sample(seed, i, shp) for i in chunk])
+        tz = from_numpy(z, stream=stream)
+        netG.sample_counter = chunk[0]
+        x, _ = netG(tz, noise_amps, noise_init=tz, isRandom=True, stream=stream)
+        f = features(x, stream=stream)
+        count = int(np.prod(f.shape[1:4]))
+        fid.sample_moments(f, out=rows.view((len(chunk), fid.MOMENT_FLOATS), F32, c0 * fid.MOMENT_FLOATS * 4),
+                           stream=stream)
+        if keep:
+            clips.append(x.numpy(stream))
+    gathered = comm.all_gather_rows(rows, stream=stream)
+    all_rows = unshard_rows(gathered, num_samples, batch, comm.world)
+    return all_rows, count, (np.concatenate(clips) if clips else None)
+
+
+def evaluate_svfid(netG, noise_amps, real_clip, num_samples, features=None, comm=None, batch=8, seed=0, stream=None):
+    """Mean per-sample Fréchet distance between generated clips and the real clip (calculate_SVFID semantics)."""
+    from . import fid
+    features = features or fid.RandomFeatures3D(netG.opt.nc_im, kt=netG.KT)
+    rows, count, _ = generate_moments(netG, noise_amps, num_samples, features, comm, batch, seed, stream)
+    real_rows = fid.sample_moments(features(real_clip, stream=stream), stream=stream).numpy(stream)
+    value, per_sample = fid.svfid_from_moments(real_rows[0], rows, count)
+    return value, per_sample
