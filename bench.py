@@ -42,8 +42,9 @@ def parse():
     ap.add_argument("--cpu-clips", type=int, default=2, help="clips in the bounded CPU-baseline sample")
     ap.add_argument("--workload", default="sample", choices=["sample", "train"],
                     help="sample: sampled clips/s (scales over GPUs); train: GAN-phase train iter/s on 1 GPU")
-    ap.add_argument("--train-steps", type=int, default=3, help="train iterations timed for the extra `train` object")
+    ap.add_argument("--train-steps", type=int, default=10, help="train iterations timed for the extra `train` object")
     ap.add_argument("--no-train", action="store_true", help="skip the extra train-iter/s measurement at N == 1")
+    ap.add_argument("--no-graph", action="store_true", help="train iterations launched eagerly instead of as a CUDA graph")
     return ap.parse_args()
 
 
@@ -162,7 +163,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------- train iter/s
-def train_iter_bench(hpvg, opt, steps, warmup, st):
+def train_iter_bench(hpvg, opt, steps, warmup, st, graph=True):
     """One GAN-phase train iteration at the finest scale (train_video.py:170-177): D step (3 D forwards, 2 backwards,
     WGAN-GP double backward, Adam) + G step (reconstruction forward of the whole pyramid in BatchNorm-train mode,
     backward of the last stage, random forward + D forward for the loss value, ClippedAdam).  Inputs come from
@@ -184,21 +185,52 @@ def train_iter_bench(hpvg, opt, steps, warmup, st):
     dev = {k: hpvg.Tensor(v, hpvg.F32) for k, v in shapes.items()}
     block = G.body[-1]
     optG = T.ClippedAdam(opt, [{"params": T.trainable_params(block), "lr": opt.lr_g}], opt.lr_g, beta1=opt.beta1,
-                         beta2=0.999)
-    optD = T.Adam(T.trainable_params(D), opt.lr_d, beta1=opt.beta1, beta2=0.999)
-    g_step = T.TrainOneStepCell(T.GWithLoss(opt, D, G), optG, cells_to_invalidate=[block])
-    d_step = T.TrainOneStepCell(T.DWithLoss(opt, D, G), optD, cells_to_invalidate=[D])
+                         beta2=0.999, device_step=graph)
+    optD = T.Adam(T.trainable_params(D), opt.lr_d, beta1=opt.beta1, beta2=0.999, device_step=graph)
+    g_step = T.TrainOneStepCell(T.GWithLoss(opt, D, G, device_rng=graph), optG, cells_to_invalidate=[block])
+    d_step = T.TrainOneStepCell(T.DWithLoss(opt, D, G, device_rng=graph), optD, cells_to_invalidate=[D])
     g_step.set_train()
     d_step.set_train()
     nb = len(G.body)
+    # second pinned noise buffer: the host draws iteration i+1's noise_init (numpy, like images.py:17-21) while the GPU
+    # runs iteration i; an event per buffer guards its reuse
+    host2 = hpvg.PinnedBuffer(host["noise"].nbytes)
+    noise_bufs = [host["noise"], host2]
+    noise_evs = [None, None]
+    counter = [0]
 
-    def one_iter():
-        for k in dev:
-            hpvg.lib.hpvg_h2d(dev[k].ptr, host[k].ptr, dev[k].nbytes, st.handle)
-        dl = d_step(dev["real"], dev["noise"], amps, stream=st)
-        gl = g_step(dev["real"], dev["real_zero"], dev["noise"], amps, isVAE=False, trainable_body=(nb - 1,),
-                    stream=st)
-        return dl, gl
+    def upload():
+        k = counter[0] & 1
+        counter[0] += 1
+        if noise_evs[k] is not None:
+            noise_evs[k].sync()
+        noise_bufs[k].as_array(shapes["noise"])[...] = np.random.standard_normal(shapes["noise"]).astype(np.float32)
+        hpvg.lib.hpvg_h2d(dev["real"].ptr, host["real"].ptr, dev["real"].nbytes, st.handle)
+        hpvg.lib.hpvg_h2d(dev["real_zero"].ptr, host["real_zero"].ptr, dev["real_zero"].nbytes, st.handle)
+        hpvg.lib.hpvg_h2d(dev["noise"].ptr, noise_bufs[k].ptr, dev["noise"].nbytes, st.handle)
+        ev = hpvg.Event()
+        ev.record(st)
+        noise_evs[k] = ev
+
+    if graph:
+        it = T.GraphedIteration(st, g_step, d_step, dev["real"], dev["real_zero"], dev["noise"], amps,
+                                dict(isVAE=False, trainable_body=(nb - 1,)))
+        upload()
+        it.warmup(max(warmup, 2))
+        it.capture()
+        per_iter = it.kernels_per_launch
+
+        def one_iter():
+            upload()
+            return it()
+    else:
+        def one_iter():
+            upload()
+            dl = d_step(dev["real"], dev["noise"], amps, stream=st)
+            gl = g_step(dev["real"], dev["real_zero"], dev["noise"], amps, isVAE=False, trainable_body=(nb - 1,),
+                        stream=st)
+            return dl, gl
+        per_iter = None
 
     for _ in range(warmup):
         one_iter()
@@ -211,12 +243,16 @@ def train_iter_bench(hpvg, opt, steps, warmup, st):
     e1.record(st)
     e1.sync()
     ms = e0.elapsed_ms(e1) / steps
+    if per_iter is None:
+        per_iter = (hpvg.lib.hpvg_launch_count() - l0) // steps
     return {"metric": "video train iter/s", "value": 1000.0 / ms, "unit": "iter/s", "ms_per_iter": ms, "steps": steps,
-            "warmup": warmup, "gpu_launches_per_iter": (hpvg.lib.hpvg_launch_count() - l0) // steps,
-            "h2d_bytes_per_iter": int(sum(t.nbytes for t in dev.values())), "last_losses": {"D": float(dl), "G": float(gl)},
+            "warmup": warmup, "gpu_launches_per_iter": int(per_iter), "cuda_graph": bool(graph),
+            "h2d_bytes_per_iter": int(sum(t.nbytes for t in dev.values())), "d2h_bytes_per_iter": 64,
+            "last_losses": {"D": float(dl), "G": float(gl)},
             "config": {"workload": "train_video.py GAN-phase iteration (D step + G step, train_depth 1) at the finest "
                                    "scale %dx%dx%d of the full %d-scale pyramid, batch 1, synthetic clip, random-init "
-                                   "weights; host->device copies of the clip/noise and loss read-backs included"
+                                   "weights; host noise draw, host->device copies of the clip/noise and loss "
+                                   "read-backs included; the iteration is replayed as one CUDA graph"
                                    % (top + (opt.stop_scale + 1,))}}
 
 # ------------------------------------------------------------------------------------------------- our arm
@@ -332,7 +368,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_train:
         del net
-        line["train"] = train_iter_bench(hpvg, opt, args.train_steps, 2, st)
+        line["train"] = train_iter_bench(hpvg, opt, args.train_steps, 3, st, graph=not args.no_graph)
         if args.workload == "train":
             tr = line["train"]
             line.update(metric=tr["metric"], value=tr["value"], unit=tr["unit"], ms_per_step=tr["ms_per_iter"],

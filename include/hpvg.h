@@ -115,7 +115,12 @@ int hpvg_resize3d_bwd(const float* d_gy, int N, int C, int To, int Ho, int Wo, f
  * noise_seed != 0 generates N(0,1) on the device with Philox keyed by (seed, sample index, element). */
 int hpvg_upsample_noise_pack(const float* d_x, int N, int C, int Ti, int Hi, int Wi, int To, int Ho, int Wo,
                              const float* d_noise, float amp, uint64_t noise_seed, uint64_t sample_base,
+                             const uint64_t* d_sample_offset /* nullable: device draw counter added to sample_base */,
                              float* d_up, void* d_xin_cl, void* stream);
+/* z ~ N(0,1) on the device (Philox4x32-10 + Box-Muller), keyed by (seed, offset [+ *d_offset], element): stand-in for
+ * the reference's host numpy draws (images.py:17-21, networks_3d.py:28-34) inside CUDA-graph replays */
+int hpvg_randn(float* d_z, long long n, uint64_t seed, uint64_t offset, const uint64_t* d_offset, void* stream);
+int hpvg_counter_add(uint64_t* d_counter, uint64_t inc, void* stream);
 
 /* ---------------------------------------------------------------- BatchNorm (training mode), channels-last bf16, C == 64
  * Replaces nn.BatchNorm3d in set_train() mode (networks_3d.py:52): batch mean / biased variance over N*T*H*W. */
@@ -167,7 +172,9 @@ int hpvg_reparam(const float* d_mu, const float* d_logvar, const float* d_eps, l
  * Multi-tensor ClipByNorm(clip) + Adam in two launches.  Tensors are described by parallel arrays on the HOST. */
 int hpvg_adam_clip_multi(int n_tensors, float* const* d_params, const float* const* d_grads, float* const* d_m,
                          float* const* d_v, const long long* sizes, const float* lrs, float beta1, float beta2,
-                         float eps, int step, float clip_norm /* <=0: no clipping */, void* stream);
+                         float eps, int step, float clip_norm /* <=0: no clipping */,
+                         const uint64_t* d_step /* nullable: 1-based step read on the device instead of `step` */,
+                         void* stream);
 
 /* ---------------------------------------------------------------- backward (hand-restated MindSpore autodiff)
  * Data gradient of a conv = hpvg_conv_cl with a filter bank packed with transpose_flip = 1.

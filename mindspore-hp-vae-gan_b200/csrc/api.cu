@@ -147,7 +147,7 @@ int hpvg_event_elapsed_ms(void* a, void* b, float* ms) {
   return HPVG_OK;
 }
 int hpvg_graph_begin(void* st) {
-  CU(cudaStreamBeginCapture(S(st), cudaStreamCaptureModeThreadLocal));
+  CU(cudaStreamBeginCapture(S(st), cudaStreamCaptureModeRelaxed));
   return HPVG_OK;
 }
 int hpvg_graph_end(void* st, void** exec) {
@@ -257,11 +257,12 @@ int hpvg_resize3d_bwd(const float* gy, int N, int C, int To, int Ho, int Wo, flo
   return HPVG_OK;
 }
 int hpvg_upsample_noise_pack(const float* x, int N, int C, int Ti, int Hi, int Wi, int To, int Ho, int Wo,
-                             const float* noise, float amp, uint64_t seed, uint64_t sample_base, float* up,
-                             void* xin, void* st) {
+                             const float* noise, float amp, uint64_t seed, uint64_t sample_base,
+                             const uint64_t* d_sample_offset, float* up, void* xin, void* st) {
   if (C < 1 || C > 4) return fail(HPVG_E_ARG, "upsample_noise_pack: 1 <= C <= 4");
   if (N <= 0) return HPVG_OK;
-  KL(hpvg::ew_upsample_noise_pack(x, N, C, Ti, Hi, Wi, To, Ho, Wo, noise, amp, seed, sample_base, up,
+  KL(hpvg::ew_upsample_noise_pack(x, N, C, Ti, Hi, Wi, To, Ho, Wo, noise, amp, seed, sample_base,
+                                  reinterpret_cast<const unsigned long long*>(d_sample_offset), up,
                                   static_cast<__nv_bfloat16*>(xin), S(st)), 1);
   return HPVG_OK;
 }
@@ -357,8 +358,9 @@ int hpvg_reparam(const float* mu, const float* lv, const float* eps, long long n
 
 int hpvg_adam_clip_multi(int n_tensors, float* const* params, const float* const* grads, float* const* m,
                          float* const* v, const long long* sizes, const float* lrs, float beta1, float beta2,
-                         float eps, int step, float clip, void* st) {
-  if (step < 1) return fail(HPVG_E_ARG, "adam: step is 1-based");
+                         float eps, int step, float clip, const uint64_t* d_step, void* st) {
+  if (step < 1 && !d_step) return fail(HPVG_E_ARG, "adam: step is 1-based");
+  if (step < 1) step = 1;
   if (!g_adam_norms) return fail(HPVG_E_ARG, "hpvg_init was not called");
   const float bc = static_cast<float>(std::sqrt(1.0 - std::pow(static_cast<double>(beta2), step)) /
                                       (1.0 - std::pow(static_cast<double>(beta1), step)));
@@ -374,7 +376,8 @@ int hpvg_adam_clip_multi(int n_tensors, float* const* params, const float* const
       tab.n[cnt] = sizes[i];
       tab.lr[cnt] = lrs[i];
     }
-    KL(hpvg::ew_adam_clip(tab, cnt, g_adam_norms, beta1, beta2, eps, bc, clip, S(st)), clip > 0.f ? 2 : 1);
+    KL(hpvg::ew_adam_clip(tab, cnt, g_adam_norms, beta1, beta2, eps, bc, clip,
+                          reinterpret_cast<const unsigned long long*>(d_step), S(st)), clip > 0.f ? 2 : 1);
   }
   return HPVG_OK;
 }
@@ -434,6 +437,17 @@ int hpvg_axpby(float a, const float* x, float b, float* y, long long n, void* st
 int hpvg_fill(float* y, float v, long long n, void* st) {
   if (n <= 0) return HPVG_OK;
   KL(hpvg::ew_fill(y, v, n, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_randn(float* z, long long n, uint64_t seed, uint64_t offset, const uint64_t* d_offset, void* st) {
+  if (n <= 0) return HPVG_OK;
+  if (!z) return fail(HPVG_E_ARG, "randn: null pointer");
+  KL(hpvg::ew_randn(z, n, seed, offset, reinterpret_cast<const unsigned long long*>(d_offset), S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_counter_add(uint64_t* d_counter, uint64_t inc, void* st) {
+  if (!d_counter) return fail(HPVG_E_ARG, "counter_add: null pointer");
+  KL(hpvg::ew_counter_add(reinterpret_cast<unsigned long long*>(d_counter), inc, S(st)), 1);
   return HPVG_OK;
 }
 int hpvg_gather_strided(const float* src, long long n, long long stride, long long offset, float* dst, void* st) {

@@ -229,11 +229,34 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
   z1 = r * s;
 }
 
+// z[i] ~ N(0,1): Philox4x32-10 keyed by `seed`, counter = (element/4, offset [+ *d_offset]) — the device stand-in for
+// the reference's host numpy draws (images.py:17-21, networks_3d.py:28-34) when the step is replayed as a CUDA graph.
+__global__ void randn_kernel(float* __restrict__ z, long long n, unsigned long long seed, unsigned long long offset,
+                             const unsigned long long* __restrict__ d_offset) {
+  if (d_offset) offset += *d_offset;
+  const long long n4 = (n + 3) >> 2;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32),
+                                               static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32)),
+                                    make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+    float v[4];
+    box_muller(rnd.x, rnd.y, v[0], v[1]);
+    box_muller(rnd.z, rnd.w, v[2], v[3]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (4 * i + e < n) z[4 * i + e] = v[e];
+  }
+}
+__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) { *c += inc; }
+
 // block input stage (networks_3d.py:440-446): up = resize(x_prev) ; x_in = up + noise*amp ; C <= 4
 __global__ void upsample_noise_pack_kernel(const float* __restrict__ x, int N, int C, ResizeGeom g,
                                            const float* __restrict__ noise, float amp, unsigned long long seed,
-                                           unsigned long long sample_base, float* __restrict__ up,
-                                           __nv_bfloat16* __restrict__ xin) {
+                                           unsigned long long sample_base,
+                                           const unsigned long long* __restrict__ d_sample_offset,
+                                           float* __restrict__ up, __nv_bfloat16* __restrict__ xin) {
+  if (d_sample_offset) sample_base += *d_sample_offset;   // device-resident draw counter (CUDA-graph replays)
   const long long spo = static_cast<long long>(g.To) * g.Ho * g.Wo;
   const long long spi = static_cast<long long>(g.Ti) * g.Hi * g.Wi;
   const long long total = static_cast<long long>(N) * spo;
@@ -594,7 +617,12 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 }
 
 __global__ void adam_apply_kernel(const AdamTable tab, const float* __restrict__ norms, float beta1, float beta2,
-                                  float eps, float bc /* sqrt(1-b2^t)/(1-b1^t) */, float clip) {
+                                  float eps, float bc /* sqrt(1-b2^t)/(1-b1^t) */, float clip,
+                                  const unsigned long long* __restrict__ d_step) {
+  if (d_step) {   // 1-based step lives on the device (CUDA-graph replays): same formula as the host path, in fp64
+    const double t = static_cast<double>(*d_step);
+    bc = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), t)) / (1.0 - pow(static_cast<double>(beta1), t)));
+  }
   const int t = blockIdx.y;
   float* __restrict__ p = tab.p[t];
   const float* __restrict__ g = tab.g[t];
@@ -953,10 +981,11 @@ cudaError_t ew_resize3d_bwd(const float* gy, long long NC, int To, int Ho, int W
 }
 cudaError_t ew_upsample_noise_pack(const float* x, int N, int C, int Ti, int Hi, int Wi, int To, int Ho, int Wo,
                                    const float* noise, float amp, unsigned long long seed,
-                                   unsigned long long sample_base, float* up, __nv_bfloat16* xin, cudaStream_t st) {
+                                   unsigned long long sample_base, const unsigned long long* d_sample_offset,
+                                   float* up, __nv_bfloat16* xin, cudaStream_t st) {
   const ResizeGeom g = make_geom(Ti, Hi, Wi, To, Ho, Wo, 1);
   upsample_noise_pack_kernel<<<grid_for(static_cast<long long>(N) * To * Ho * Wo, 256), 256, 0, st>>>(
-      x, N, C, g, noise, amp, seed, sample_base, up, xin);
+      x, N, C, g, noise, amp, seed, sample_base, d_sample_offset, up, xin);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -1038,7 +1067,7 @@ cudaError_t ew_reparam(const float* mu, const float* lv, const float* eps, long 
   return cudaSuccess;
 }
 cudaError_t ew_adam_clip(const AdamTable& tab, int n_tensors, float* norms_scratch, float beta1, float beta2,
-                         float eps, float bias_corr, float clip, cudaStream_t st) {
+                         float eps, float bias_corr, float clip, const unsigned long long* d_step, cudaStream_t st) {
   // blocks per tensor: enough to cover the largest tensor with ~2 float4 per thread, and to fill the 148 SMs
   long long nmax = 1;
   for (int i = 0; i < n_tensors; ++i) nmax = tab.n[i] > nmax ? tab.n[i] : nmax;
@@ -1052,7 +1081,8 @@ cudaError_t ew_adam_clip(const AdamTable& tab, int n_tensors, float* norms_scrat
     adam_norm_kernel<<<dim3(gx, n_tensors), 256, 0, st>>>(tab, norms_scratch);
     LAUNCH_CHECK();
   }
-  adam_apply_kernel<<<dim3(gx, n_tensors), 256, 0, st>>>(tab, norms_scratch, beta1, beta2, eps, bias_corr, clip);
+  adam_apply_kernel<<<dim3(gx, n_tensors), 256, 0, st>>>(tab, norms_scratch, beta1, beta2, eps, bias_corr, clip,
+                                                         d_step);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -1110,6 +1140,17 @@ cudaError_t ew_axpby(float a, const float* x, float b, float* y, long long n, cu
 cudaError_t ew_gather_strided(const float* src, long long n, long long stride, long long offset, float* dst,
                               cudaStream_t st) {
   gather_strided_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, n, stride, offset, dst);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_randn(float* z, long long n, unsigned long long seed, unsigned long long offset,
+                     const unsigned long long* d_offset, cudaStream_t st) {
+  randn_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(z, n, seed, offset, d_offset);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_counter_add(unsigned long long* c, unsigned long long inc, cudaStream_t st) {
+  counter_add_kernel<<<1, 1, 0, st>>>(c, inc);
   LAUNCH_CHECK();
   return cudaSuccess;
 }

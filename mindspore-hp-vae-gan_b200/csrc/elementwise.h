@@ -29,7 +29,11 @@ cudaError_t ew_resize3d_bwd(const float* gy, long long NC, int To, int Ho, int W
                             int align, cudaStream_t st);
 cudaError_t ew_upsample_noise_pack(const float* x, int N, int C, int Ti, int Hi, int Wi, int To, int Ho, int Wo,
                                    const float* noise, float amp, unsigned long long seed,
-                                   unsigned long long sample_base, float* up, __nv_bfloat16* xin, cudaStream_t st);
+                                   unsigned long long sample_base, const unsigned long long* d_sample_offset,
+                                   float* up, __nv_bfloat16* xin, cudaStream_t st);
+cudaError_t ew_randn(float* z, long long n, unsigned long long seed, unsigned long long offset,
+                     const unsigned long long* d_offset, cudaStream_t st);
+cudaError_t ew_counter_add(unsigned long long* c, unsigned long long inc, cudaStream_t st);
 cudaError_t ew_bn_stats_cl(const __nv_bfloat16* y, long long voxels, double* sum, double* sumsq, cudaStream_t st);
 cudaError_t ew_bn_finalize(const double* sum, const double* sumsq, long long count, const float* gamma,
                            const float* beta, float eps, float momentum, float* mm, float* mv, float* scale,
@@ -62,7 +66,7 @@ cudaError_t ew_affine_from_bias(const float* bias, const float* inv_sigma, int C
 cudaError_t ew_reduce(int op, const float* a, const float* b, long long n, float* out, cudaStream_t st);
 cudaError_t ew_reparam(const float* mu, const float* lv, const float* eps, long long n, float* z, cudaStream_t st);
 cudaError_t ew_adam_clip(const AdamTable& tab, int n_tensors, float* norms_scratch, float beta1, float beta2,
-                         float eps, float bias_corr, float clip, cudaStream_t st);
+                         float eps, float bias_corr, float clip, const unsigned long long* d_step, cudaStream_t st);
 
 cudaError_t ew_lrelu_bwd_cl(const __nv_bfloat16* ga, const __nv_bfloat16* a, long long elems, __nv_bfloat16* gz,
                             cudaStream_t st);

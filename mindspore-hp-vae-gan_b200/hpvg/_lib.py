@@ -61,7 +61,9 @@ _SIGS = {
     "hpvg_linear_taps_dev": ([i, i, i, vp, vp, vp, vp, vp], c_int),
     "hpvg_resize3d_fwd": ([vp, i, i, i, i, i, vp, i, i, i, i, vp], c_int),
     "hpvg_resize3d_bwd": ([vp, i, i, i, i, i, vp, i, i, i, i, vp], c_int),
-    "hpvg_upsample_noise_pack": ([vp, i, i, i, i, i, i, i, i, vp, f, u64, u64, vp, vp, vp], c_int),
+    "hpvg_upsample_noise_pack": ([vp, i, i, i, i, i, i, i, i, vp, f, u64, u64, vp, vp, vp, vp], c_int),
+    "hpvg_randn": ([vp, ll, u64, u64, vp, vp], c_int),
+    "hpvg_counter_add": ([vp, u64, vp], c_int),
     "hpvg_bn_stats_cl": ([vp, ll, vp, vp, vp], c_int),
     "hpvg_bn_finalize": ([vp, vp, ll, vp, vp, f, f, vp, vp, vp, vp, vp, vp, vp], c_int),
     "hpvg_bn_apply_lrelu_cl": ([vp, ll, vp, vp, i, vp, vp], c_int),
@@ -90,7 +92,7 @@ _SIGS = {
     "hpvg_lerp": ([vp, vp, f, ll, vp, vp], c_int),
     "hpvg_gp_grad": ([vp, i, i, ll, f, vp, vp, vp], c_int),
     "hpvg_adam_clip_multi": ([i, POINTER(vp), POINTER(vp), POINTER(vp), POINTER(vp), POINTER(ll), POINTER(f), f, f,
-                              f, i, f, vp], c_int),
+                              f, i, f, vp, vp], c_int),
 }
 # MindSpore ops.Custom(func_type="aot") entry points
 _AOT = ["HpvgUpsampleTrilinear3D", "HpvgUpsampleTrilinear3DGrad", "HpvgConv3dBiasLRelu"]

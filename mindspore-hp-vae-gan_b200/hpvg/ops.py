@@ -226,7 +226,21 @@ def resize3d_bwd(gy, in_size, align_corners=True, out=None, stream=None):
     return out
 
 
-def upsample_noise_pack(x, size, noise=None, amp=0.0, seed=0, sample_base=0, up=None, xin=None, stream=None):
+def randn(shape, seed, offset=0, d_offset=None, out=None, stream=None):
+    """N(0,1) drawn on the device, keyed by (seed, offset [+ device counter], element)."""
+    out = out or Tensor(shape, F32)
+    check(lib.hpvg_randn(_p(out), out.size, int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset), _p(d_offset), _s(stream)),
+          "randn")
+    return out
+
+
+def counter_add(counter, inc=1, stream=None):
+    check(lib.hpvg_counter_add(_p(counter), int(inc), _s(stream)), "counter_add")
+    return counter
+
+
+def upsample_noise_pack(x, size, noise=None, amp=0.0, seed=0, sample_base=0, up=None, xin=None, stream=None,
+                        d_sample_offset=None):
     """Block input stage (networks_3d.py:440-446).  Returns (up fp32 ncdhw, x_in bf16 cl 8-channel)."""
     N, C, Ti, Hi, Wi = x.shape
     To, Ho, Wo = (int(v) for v in size)
@@ -235,7 +249,8 @@ def upsample_noise_pack(x, size, noise=None, amp=0.0, seed=0, sample_base=0, up=
     if xin is None:
         xin = Tensor((N, To, Ho, Wo, 8), BF16)
     check(lib.hpvg_upsample_noise_pack(_p(x), N, C, Ti, Hi, Wi, To, Ho, Wo, _p(noise), float(amp), int(seed),
-                                       int(sample_base), _p(up), _p(xin), _s(stream)), "upsample_noise_pack")
+                                       int(sample_base), _p(d_sample_offset), _p(up), _p(xin), _s(stream)),
+          "upsample_noise_pack")
     return up, xin
 
 
@@ -330,7 +345,8 @@ def reparam(mu, logvar, eps, out=None, stream=None):
     return out
 
 
-def adam_clip_multi(params, grads, ms, vs, lrs, step, beta1=0.5, beta2=0.999, eps=1e-8, clip=0.0, stream=None):
+def adam_clip_multi(params, grads, ms, vs, lrs, step, beta1=0.5, beta2=0.999, eps=1e-8, clip=0.0, stream=None,
+                    d_step=None):
     """ClippedAdam.construct (optimizers.py:41-43) / nn.Adam for D (train_video.py:65): per-tensor ClipByNorm then Adam."""
     n = len(params)
     VP = ctypes.c_void_p * n
@@ -338,7 +354,7 @@ def adam_clip_multi(params, grads, ms, vs, lrs, step, beta1=0.5, beta2=0.999, ep
     lr_arr = (ctypes.c_float * n)(*[float(x) for x in lrs])
     check(lib.hpvg_adam_clip_multi(n, VP(*[p.ptr for p in params]), VP(*[g.ptr for g in grads]),
                                    VP(*[m.ptr for m in ms]), VP(*[v.ptr for v in vs]), sizes, lr_arr, beta1, beta2,
-                                   eps, int(step), float(clip), _s(stream)), "adam_clip_multi")
+                                   eps, int(step), float(clip), _p(d_step), _s(stream)), "adam_clip_multi")
 
 
 # ================================================================================================ backward operators

@@ -11,8 +11,9 @@ BF16 = "bfloat16"
 F32 = "float32"
 F64 = "float64"
 I32 = "int32"
-_ITEMSIZE = {BF16: 2, F32: 4, F64: 8, I32: 4}
-_NP = {F32: np.float32, F64: np.float64, I32: np.int32, BF16: np.uint16}
+U64 = "uint64"
+_ITEMSIZE = {BF16: 2, F32: 4, F64: 8, I32: 4, U64: 8}
+_NP = {F32: np.float32, F64: np.float64, I32: np.int32, BF16: np.uint16, U64: np.uint64}
 
 
 def init(device=0):
@@ -92,8 +93,14 @@ def _pool_alloc(nbytes):
     return h.value, size
 
 
+_CAPTURE_HOLD = [None]   # while a CUDA graph is being captured: blocks freed meanwhile stay reserved for the graph
+
+
 def _pool_free(ptr, size):
-    _POOL.setdefault(size, []).append(ptr)
+    if _CAPTURE_HOLD[0] is not None:
+        _CAPTURE_HOLD[0].append((ptr, size))
+    else:
+        _POOL.setdefault(size, []).append(ptr)
 
 
 def empty_cache():
@@ -166,10 +173,48 @@ class Tensor:
         return self
 
 
+class Graph:
+    """CUDA graph of everything enqueued on `stream` inside the `with` block.  Device blocks that are released to the
+    allocator during capture stay reserved for the graph (their addresses are baked into the captured kernel
+    arguments) until `destroy()`.  After capture, drive the captured objects ONLY through `launch()`."""
+
+    def __init__(self, stream):
+        self.stream, self.exec, self._held = stream, None, []
+
+    def __enter__(self):
+        if _CAPTURE_HOLD[0] is not None:
+            raise HpvgError("nested graph capture")
+        _CAPTURE_HOLD[0] = self._held
+        check(lib.hpvg_graph_begin(self.stream.handle), "graph_begin")
+        return self
+
+    def __exit__(self, et, ev, tb):
+        _CAPTURE_HOLD[0] = None
+        h = ctypes.c_void_p()
+        rc = lib.hpvg_graph_end(self.stream.handle, ctypes.byref(h))
+        if et is None:
+            check(rc, "graph_end")
+            self.exec = h
+        return False
+
+    def launch(self):
+        check(lib.hpvg_graph_launch(self.exec, self.stream.handle), "graph_launch")
+
+    def destroy(self):
+        if self.exec is not None:
+            self.stream.sync()
+            lib.hpvg_graph_destroy(self.exec)
+            self.exec = None
+        for ptr, size in self._held:
+            _POOL.setdefault(size, []).append(ptr)
+        self._held = []
+
+
 def from_numpy(arr, dtype=None, stream=None):
     a = np.asarray(arr)
     if dtype is None:
-        dtype = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.int32): I32}.get(a.dtype, F32)
+        dtype = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.int32): I32,
+                 np.dtype(np.uint64): U64}.get(a.dtype, F32)
     t = Tensor(a.shape, dtype)
     t.copy_from_host(a, stream)
     return t

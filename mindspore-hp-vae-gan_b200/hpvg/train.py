@@ -13,7 +13,7 @@ import numpy as np
 from . import ops
 from .networks_3d import BnStatsSlab, ConvLayer, Workspace, as5d
 from .ops import ACT_LRELU, ACT_NONE, ACT_TANH, CONV_64_16, CONV_64_64, CONV_8_64, OUT_BF16_CL, OUT_F32_NCDHW, OUT_F32_RAW
-from .runtime import BF16, F32, HpvgError, Tensor, from_numpy
+from .runtime import BF16, F32, U64, Graph, HpvgError, Tensor, from_numpy
 from .utils import images as uimg
 
 NON_TRAINABLE = ("weight_u", "weight_v", "moving_mean", "moving_variance")
@@ -28,17 +28,22 @@ class LossTerms:
     """Loss value assembled on the device side without stalling the stream: every term is reduced into its own slot of
     a small device vector; `finish()` enqueues ONE async copy into pinned host memory and returns a LazyLoss whose
     float() waits for that copy only when the caller actually looks at the number (the reference's loop reads losses
-    just for logging, train_video.py:188-194)."""
+    just for logging, train_video.py:188-194).  A ring of host slots keeps earlier iterations' values readable."""
     SLOTS = 8
+    RING = 16
 
     def __init__(self):
         from .runtime import PinnedBuffer
         self.dev = Tensor((self.SLOTS,), F32)
-        self.host = PinnedBuffer(self.SLOTS * 4)
+        self.host = PinnedBuffer(self.SLOTS * 4 * self.RING)
         self.coefs = []
+        self._pending = [None] * self.RING
+        self._next = 0
 
     def slot(self, coef):
         i = len(self.coefs)
+        if i >= self.SLOTS:
+            raise HpvgError("LossTerms: too many terms")
         self.coefs.append(float(coef))
         return self.dev.view((1,), F32, 4 * i)
 
@@ -48,21 +53,28 @@ class LossTerms:
     def finish(self, stream=None):
         from ._lib import check, lib
         from .runtime import Event, _s
-        check(lib.hpvg_d2h(self.host.ptr, self.dev.ptr, self.dev.nbytes, _s(stream)), "d2h")
+        k = self._next
+        self._next = (k + 1) % self.RING
+        if self._pending[k] is not None:
+            float(self._pending[k])          # materialise the value that lived in this host slot
+        check(lib.hpvg_d2h(self.host.ptr + k * self.SLOTS * 4, self.dev.ptr, self.dev.nbytes, _s(stream)), "d2h")
         ev = Event()
         ev.record(stream)
-        return LazyLoss(self.host, list(self.coefs), ev)
+        lazy = LazyLoss(self.host, k * self.SLOTS, list(self.coefs), ev)
+        self._pending[k] = lazy
+        return lazy
 
 
 class LazyLoss:
-    def __init__(self, host, coefs, event):
-        self._host, self._coefs, self._event, self._value = host, coefs, event, None
+    def __init__(self, host, first, coefs, event):
+        self._host, self._first, self._coefs, self._event, self._value = host, first, coefs, event, None
 
     def __float__(self):
         if self._value is None:
             self._event.sync()
-            vals = self._host.as_array((len(self._coefs),)) if self._coefs else []
+            vals = self._host.as_array((LossTerms.SLOTS * LossTerms.RING,))[self._first:self._first + len(self._coefs)]
             self._value = float(sum(c * float(v) for c, v in zip(self._coefs, vals)))
+            self._host = self._event = None
         return self._value
 
     def __repr__(self):
@@ -294,10 +306,24 @@ def block_backward(block, ctxs, g_out, grads, ws, tag, need_dx, trainable=True, 
 class GeneratorTrainer:
     """Forward/backward of GeneratorHPVAEGAN in training mode (BatchNorm batch statistics everywhere, Q4)."""
 
-    def __init__(self, netG):
+    def __init__(self, netG, device_rng=False, salt=0):
         self.net = netG
         self.ws = Workspace()
         self.slab = BnStatsSlab()
+        self.salt = int(salt)        # distinct Philox keys for the D-step and G-step generator passes
+        self.host_draws = 0          # forward counter (host mirror of `draws`): fresh noise on every forward
+        # device_rng: every N(0,1) draw the reference makes on the host inside a forward (z when no noise_init is
+        # given, networks_3d.py:28-34; refinement noise, images.py:30-37) comes from the device Philox generator keyed
+        # by a DEVICE-resident draw counter, so the whole step can be replayed as a CUDA graph with fresh noise.
+        self.device_rng = device_rng
+        self.draws = Tensor((1,), U64).zero_() if device_rng else None
+
+    def _draw(self, shape, stream):
+        """N(0,1) of `shape`: host numpy global RNG like the reference (Q7), or the device generator (device_rng)."""
+        if self.device_rng:
+            return ops.randn(shape, (self.net.noise_seed ^ 0x5DEECE66D) + self.salt, d_offset=self.draws,
+                             out=self.ws.get("zdraw", shape, F32), stream=stream)
+        return from_numpy(np.random.normal(size=shape).astype(np.float32))
 
     def _stage_input(self, x_prev, idx, noise_amp, is_random, noises, stream, wide):
         net, opt = self.net, self.net.opt
@@ -312,9 +338,11 @@ class GeneratorTrainer:
             if noises is not None and (idx + 1) in noises:
                 noise_t = noises[idx + 1]
             else:
-                seed = (net.noise_seed + 0x632BE59BD9B4E019 * (idx + 1)) & 0xFFFFFFFFFFFFFFFF
-        ops.upsample_noise_pack(x_prev, size, noise=noise_t, amp=amp, seed=seed, sample_base=net.sample_counter,
-                                up=up, xin=xin, stream=stream)
+                seed = (net.noise_seed + 0x632BE59BD9B4E019 * (idx + 1) +
+                        0x94D049BB133111EB * self.salt) & 0xFFFFFFFFFFFFFFFF
+        base = net.sample_counter + (0 if self.device_rng else self.host_draws)
+        ops.upsample_noise_pack(x_prev, size, noise=noise_t, amp=amp, seed=seed, sample_base=base,
+                                up=up, xin=xin, stream=stream, d_sample_offset=self.draws)
         x_wide = None
         if wide:   # 64-channel zero-padded copy for the head conv's weight gradient
             f = ops.unpack_cl(xin, C=opt.nc_im, out=self.ws.get("xinf%d" % idx, (N, opt.nc_im) + size, F32),
@@ -332,6 +360,10 @@ class GeneratorTrainer:
         mu = logvar = None
         slab = self.slab
         slab.reset(stream)
+        n_draw = 1 if noise_init is None else noise_init.shape[0]
+        self.host_draws += n_draw
+        if self.device_rng:
+            ops.counter_add(self.draws, n_draw, stream)
         if noise_init is None:
             enc = net.encode
             sn_tape_prepare(enc._features.layers, ws, "enc", stream)
@@ -352,10 +384,10 @@ class GeneratorTrainer:
             out.update(enc_ctx=ectx, mu_ctx=cm, lv_ctx=cl)
             if net.is_training:
                 if eps is None:
-                    eps = from_numpy(np.random.normal(size=mu.shape).astype(np.float32))
+                    eps = self._draw(mu.shape, stream)
                 z = ops.reparam(mu, logvar, eps, stream=stream)
             else:
-                z = z_pred if z_pred is not None else from_numpy(np.random.normal(size=mu.shape).astype(np.float32))
+                z = z_pred if z_pred is not None else self._draw(mu.shape, stream)
         else:
             z = noise_init
         N = z.shape[0]
@@ -379,15 +411,15 @@ class GeneratorTrainer:
 class GWithLoss:
     """losses.py:59-107.  `grad()` returns (loss value as float, GradBook)."""
 
-    def __init__(self, opt, netD, netG):
+    def __init__(self, opt, netD, netG, device_rng=False):
         self._netD, self._netG, self.opt = netD, netG, opt
         self.rec_weight, self.kl_weight, self.disc_loss_weight = opt.rec_weight, opt.kl_weight, opt.disc_loss_weight
-        self.trainer = GeneratorTrainer(netG)
+        self.trainer = GeneratorTrainer(netG, device_rng, salt=1)
         self.grads = GradBook()
         self.terms = LossTerms()
 
     def grad(self, real, real_zero, noise_init, noise_amps, isVAE=False, trainable_body=(), train_codec=False,
-             noises=None, z_pred=None, eps=None, stream=None):
+             noises=None, z_pred=None, eps=None, stream=None, finish=True):
         """trainable_body: indices of body stages whose parameters are optimised (train_video.py:76-105);
         train_codec: whether encode/decoder are optimised (VAE phase)."""
         net, opt, tr = self._netG, self.opt, self.trainer
@@ -459,7 +491,7 @@ class GWithLoss:
             fw2 = tr.forward(None, noise_amps, noise_init=noise_init, is_random=True, noises=noises, stream=stream)
             d_out = self._netD(fw2["x"], stream=stream)
             ops.mean(d_out, out=terms.slot(-self.disc_loss_weight), stream=stream)
-        return terms.finish(stream), g
+        return (terms.finish(stream) if finish else terms), g
 
 
 def _add_cl(a_cl, b_cl, ws, stream=None):
@@ -473,11 +505,11 @@ def _add_cl(a_cl, b_cl, ws, stream=None):
 class DWithLoss:
     """losses.py:17-56: -mean D(real) + mean D(sg(G(z))) + lambda * mean((||grad_xhat sum D(xhat)||_2 - 1)^2)."""
 
-    def __init__(self, opt, netD, netG, alpha=None):
+    def __init__(self, opt, netD, netG, alpha=None, device_rng=False):
         self._netD, self._netG, self.opt = netD, netG, opt
         self.lambda_grad = opt.lambda_grad
         self.alpha = float(np.random.uniform()) if alpha is None else float(alpha)    # Q3: drawn once (losses.py:25)
-        self.trainer = GeneratorTrainer(netG)
+        self.trainer = GeneratorTrainer(netG, device_rng, salt=2)
         self.ws = Workspace()
         self.grads = GradBook()
         self.terms = LossTerms()
@@ -561,7 +593,7 @@ class DWithLoss:
         ops.conv_wgrad_cl(xi, d_out, g.of(D.tail.p["weight"]), co_n=1, ci_n=64, accumulate=True, stream=stream)
         return gp
 
-    def grad(self, real, noise_init, noise_amps, noises=None, fake=None, stream=None):
+    def grad(self, real, noise_init, noise_amps, noises=None, fake=None, stream=None, finish=True):
         real, noise_init, fake = as5d(real), as5d(noise_init), as5d(fake)
         if noises is not None:
             noises = {k: as5d(v) for k, v in noises.items()}
@@ -582,7 +614,7 @@ class DWithLoss:
         self._gradient_penalty(ctx_x, "X", stream)
         ops.mean(out_r, out=terms.slot(-1.0), stream=stream)
         ops.mean(out_f, out=terms.slot(1.0), stream=stream)
-        return terms.finish(stream), g
+        return (terms.finish(stream) if finish else terms), g
 
 
 def _scale_only(aff, zero_shift, ws, tag, j, stream):
@@ -597,8 +629,11 @@ def _scale_only(aff, zero_shift, ws, tag, j, stream):
 class Adam:
     """mindspore.nn.Adam over a flat list or a list of {"params": [...], "lr": x} groups (train_video.py:65,76-108)."""
 
-    def __init__(self, params, learning_rate=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, clip=0.0):
+    def __init__(self, params, learning_rate=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, clip=0.0, device_step=False):
         self.beta1, self.beta2, self.eps, self.clip = beta1, beta2, eps, clip
+        # device_step: the 1-based step counter (bias correction) lives on the device so the update can be replayed
+        # inside a CUDA graph
+        self.d_step = Tensor((1,), U64).zero_() if device_step else None
         self.items = []      # (param Tensor, lr)
         if params and isinstance(params[0], dict):
             for grp in params:
@@ -614,17 +649,19 @@ class Adam:
 
     def apply(self, grads, stream=None):
         self.step += 1
+        if self.d_step is not None:
+            ops.counter_add(self.d_step, 1, stream)
         ps = [p for p, _ in self.items]
         gs = [grads.of(p) for p in ps]
         ops.adam_clip_multi(ps, gs, self.m, self.v, [lr for _, lr in self.items], self.step, self.beta1, self.beta2,
-                            self.eps, self.clip, stream=stream)
+                            self.eps, self.clip, stream=stream, d_step=self.d_step)
 
 
 class ClippedAdam(Adam):
     """optimizers.py:33-43: per-tensor ClipByNorm(opt.grad_clip) then Adam."""
 
-    def __init__(self, opt, params, learning_rate=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
-        super().__init__(params, learning_rate, beta1, beta2, eps, clip=float(opt.grad_clip))
+    def __init__(self, opt, params, learning_rate=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, device_step=False):
+        super().__init__(params, learning_rate, beta1, beta2, eps, clip=float(opt.grad_clip), device_step=device_step)
 
 
 class TrainOneStepCell:
@@ -645,3 +682,69 @@ class TrainOneStepCell:
         for c in self.cells:
             c.invalidate()     # packed filter banks / folded BN vectors are stale after the update
         return loss
+
+
+class GraphedIteration:
+    """One whole training iteration of train_video.py:170-177 (GAN phase: D step then G step; VAE phase: G step) captured
+    ONCE as a CUDA graph and replayed: ~750 kernel launches per iteration stop costing host time, the GPU runs the
+    iteration back to back.  Requirements (all provided by this module): the loss cells are built with
+    device_rng=True and the optimisers with device_step=True, so every per-iteration varying quantity (noise draws,
+    Adam bias correction) is read from device memory; inputs live in fixed device tensors the caller refreshes
+    (hpvg_h2d on the same stream) before each launch; losses are read back after the launch.
+
+    Usage:   it = GraphedIteration(stream, g_step, d_step, inputs..., g_kwargs)
+             it.warmup(2); it.capture(); loop: [refresh inputs]; d_loss, g_loss = it()"""
+
+    def __init__(self, stream, g_step, d_step, real, real_zero, noise_init, noise_amps, g_kwargs):
+        self.stream, self.g_step, self.d_step = stream, g_step, d_step
+        self.real, self.real_zero, self.noise_init, self.amps = real, real_zero, noise_init, list(noise_amps)
+        self.g_kwargs = dict(g_kwargs)
+        self.graph = None
+        self.kernels_per_launch = 0
+        for cell in (g_step, d_step):
+            if cell is None:
+                continue
+            if cell.optimizer.d_step is None or not cell.network.trainer.device_rng:
+                raise HpvgError("GraphedIteration needs device_step=True optimisers and device_rng=True loss cells")
+
+    def _body(self, finish):
+        st = self.stream
+        # make the iteration CLOSED: packed filter banks / epilogue vectors derived from trainable weights must be
+        # rebuilt inside the iteration, never carried over from the previous one through a Python-side cache (a
+        # replayed graph would keep reading the buffer that was current at capture time)
+        for cell in (self.d_step, self.g_step):
+            if cell is not None:
+                for c in cell.cells:
+                    c.invalidate()
+        dl = None
+        if self.d_step is not None:
+            dl = self.d_step(self.real, self.noise_init, self.amps, stream=st, finish=finish)
+        gl = self.g_step(self.real, self.real_zero, self.noise_init, self.amps, stream=st, finish=finish,
+                         **self.g_kwargs)
+        return dl, gl
+
+    def warmup(self, n=2):
+        """Eager iterations: first-use allocations, cudaFuncSetAttribute, cached epilogue vectors."""
+        out = None
+        for _ in range(n):
+            out = self._body(True)
+        self.stream.sync()
+        return out
+
+    def capture(self):
+        from ._lib import lib
+        n0 = lib.hpvg_launch_count()
+        self.graph = Graph(self.stream)
+        with self.graph:
+            self._terms = self._body(False)
+        self.kernels_per_launch = int(lib.hpvg_launch_count() - n0)
+        return self
+
+    def __call__(self):
+        self.graph.launch()
+        return tuple(t.finish(self.stream) if t is not None else None for t in self._terms)
+
+    def destroy(self):
+        if self.graph is not None:
+            self.graph.destroy()
+            self.graph = None

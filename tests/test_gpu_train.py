@@ -230,3 +230,74 @@ def test_train_one_step_updates_parameters_like_clipped_adam(hpvg_gpu):
                                    np.zeros_like(before[k]), 1, opt.lr_g, 0.5, 0.999)
         assert rel_l2(t.numpy(), want) < 1e-5, k
         assert not np.array_equal(t.numpy(), before[k]) or np.linalg.norm(grads[k]) == 0
+
+
+def test_device_randn_statistics_and_counter(hpvg_gpu):
+    hp, ops = hpvg_gpu, hpvg_gpu.ops
+    ctr = hp.Tensor((1,), hp.U64).zero_()
+    a = ops.randn((1, 128, 4, 24, 33), seed=77, d_offset=ctr).numpy()
+    assert abs(a.mean()) < 5e-3 and abs(a.std() - 1.0) < 5e-3
+    assert np.array_equal(a, ops.randn(a.shape, seed=77, d_offset=ctr).numpy())      # same key -> same draw
+    ops.counter_add(ctr, 1)
+    b = ops.randn(a.shape, seed=77, d_offset=ctr).numpy()
+    assert not np.array_equal(a, b) and abs(float((a * b).mean())) < 5e-3            # fresh, uncorrelated draw
+    assert np.array_equal(b, ops.randn(a.shape, seed=77, offset=1).numpy())          # device counter == host offset
+
+
+def test_cuda_graph_iteration_matches_eager_iteration(hpvg_gpu):
+    """The whole GAN-phase iteration (D step + G step + both Adam updates) replayed as ONE CUDA graph must evolve the
+    weights exactly like the eager launch sequence: same kernels, device-resident noise counters and Adam step."""
+    hp = hpvg_gpu
+    from hpvg import train as T
+
+    def run(graphed, iters=3):
+        G, D, opt, oopt, pg, pd, rng = _setup(hp, 3, seed=5)
+        G.noise_seed = 0x1234567
+        s0, s3 = orc.scale_shape(oopt, 0), orc.scale_shape(oopt, 3)
+        st = hp.Stream()
+        real = hp.from_numpy(np.tanh(rng.standard_normal((1, 3) + s3)).astype(np.float32))
+        real_zero = hp.from_numpy(np.tanh(rng.standard_normal((1, 3) + s0)).astype(np.float32))
+        noise = hp.from_numpy(rng.standard_normal((1, 128) + s0).astype(np.float32))
+        amps = [1.0, 0.0, 0.0, 0.3]
+        block = G.body[-1]
+        optG = T.ClippedAdam(opt, [{"params": T.trainable_params(block), "lr": opt.lr_g}], opt.lr_g, beta1=0.5,
+                             beta2=0.999, device_step=True)
+        optD = T.Adam(T.trainable_params(D), opt.lr_d, beta1=0.5, beta2=0.999, device_step=True)
+        g_step = T.TrainOneStepCell(T.GWithLoss(opt, D, G, device_rng=True), optG, cells_to_invalidate=[block])
+        d_step = T.TrainOneStepCell(T.DWithLoss(opt, D, G, alpha=0.37, device_rng=True), optD, cells_to_invalidate=[D])
+        g_step.set_train()
+        d_step.set_train()
+        it = T.GraphedIteration(st, g_step, d_step, real, real_zero, noise, amps, dict(isVAE=False, trainable_body=(2,)))
+        losses = []
+        it.warmup(1)
+        if graphed:
+            it.capture()
+            assert it.kernels_per_launch > 100
+            for _ in range(iters):
+                losses.append(it())
+        else:
+            for _ in range(iters):
+                losses.append(it._body(True))
+        st.sync()
+        out = ({k: t.numpy() for k, t in D.parameters_dict().items()},
+               {k: t.numpy() for k, t in block.parameters_dict("b.").items()},
+               [(float(a), float(b)) for a, b in losses])
+        if graphed:
+            it.destroy()
+        return out
+
+    d_e, g_e, l_e = run(False)
+    d_g, g_g, l_g = run(True)
+    for (de, ge), (dg, gg) in zip(l_e, l_g):
+        assert abs(de - dg) < 1e-4 * max(1.0, abs(de)) and abs(ge - gg) < 1e-4 * max(1.0, abs(ge)), (l_e, l_g)
+    # fp64 atomics in the BatchNorm statistics make the summation order non-deterministic at the 1e-16 level; after
+    # three Adam steps the weights agree to float32 round-off
+    for ref, got in ((d_e, d_g), (g_e, g_g)):
+        for k in ref:
+            if k.startswith("b.") and k.endswith(".0.bias") and not k.startswith("b.6"):
+                # conv bias in front of a BatchNorm: its gradient is analytically ZERO, so Adam normalises pure
+                # rounding noise into +-lr steps — not reproducible run to run even eagerly (measured); bounded only
+                assert np.abs(got[k] - ref[k]).max() <= 2 * 3 * 5e-4 + 1e-6, k
+                continue
+            assert rel_l2(got[k], ref[k]) < 1e-4, k
+    assert l_e[0] != l_e[1]        # noise really changes from iteration to iteration

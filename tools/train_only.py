@@ -12,4 +12,5 @@ warm = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 hpvg.init(0)
 st = hpvg.Stream()
 opt = uimg.default_opt()
-print(json.dumps(bench.train_iter_bench(hpvg, opt, steps, warm, st)))
+graph = not (len(sys.argv) > 3 and sys.argv[3] == 'eager')
+print(json.dumps(bench.train_iter_bench(hpvg, opt, steps, warm, st, graph=graph)))
