@@ -167,6 +167,9 @@ int hpvg_mean(const float* d_a, long long n, float* d_out, void* stream);
 int hpvg_kl(const float* d_mu, const float* d_logvar, long long n, float* d_out, void* stream);
 /* z = eps*exp(0.5*logvar)+mu (networks_3d.py:415-417) */
 int hpvg_reparam(const float* d_mu, const float* d_logvar, const float* d_eps, long long n, float* d_z, void* stream);
+/* its backward: d_gmu += gz ; d_glogvar += gz * eps * 0.5 * exp(0.5*logvar) */
+int hpvg_reparam_bwd(const float* d_gz, const float* d_eps, const float* d_logvar, long long n, float* d_gmu,
+                     float* d_glogvar, void* stream);
 
 /* ---------------------------------------------------------------- optimiser (src/modules/optimizers.py:33-43)
  * Multi-tensor ClipByNorm(clip) + Adam in two launches.  Tensors are described by parallel arrays on the HOST. */

@@ -356,6 +356,13 @@ int hpvg_reparam(const float* mu, const float* lv, const float* eps, long long n
   return HPVG_OK;
 }
 
+int hpvg_reparam_bwd(const float* gz, const float* eps, const float* lv, long long n, float* gmu, float* glv, void* st) {
+  if (n <= 0) return HPVG_OK;
+  if (!gz || !eps || !lv || !gmu || !glv) return fail(HPVG_E_ARG, "reparam_bwd: null pointer");
+  KL(hpvg::ew_reparam_bwd(gz, eps, lv, n, gmu, glv, S(st)), 1);
+  return HPVG_OK;
+}
+
 int hpvg_adam_clip_multi(int n_tensors, float* const* params, const float* const* grads, float* const* m,
                          float* const* v, const long long* sizes, const float* lrs, float beta1, float beta2,
                          float eps, int step, float clip, const uint64_t* d_step, void* st) {

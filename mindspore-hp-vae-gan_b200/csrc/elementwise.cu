@@ -229,6 +229,337 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
   z1 = r * s;
 }
 
+// ----------------------------------------------------------------------------------------------- tiled resize
+// Shared-memory-staged, separable versions of the three resize kernels (the generic ones above remain as fallback for
+// shapes whose tile does not fit).  One CTA = one (n, c) slice x one band of rows x ALL frames.
+//   forward : stage the W-interpolated source rows of the band once (Ti x n_hs x Wo floats), then every output voxel
+//             is 4 shared-memory reads + an H and a T interpolation — same operation order as trilerp() => same bits.
+//   backward: accumulate ct*ch*gy into b[ti][hs][wo] (frame planes owned by thread rows, columns by thread columns,
+//             fixed loop order => deterministic, no atomics), then contract the W axis with an inverse tap table.
+// Thread layout (nx, ny): nx = ceil(Wo / cpt) columns (cpt = columns per thread, so odd widths like 257 do not waste a
+// whole pass), ny thread rows split the image rows.  Tap tables live in shared memory.
+struct TiledGeom {
+  ResizeGeom g;
+  int band;       // output rows per CTA (forward) / source rows per CTA (backward); power of two
+  int band_log2;
+  int n_hs;       // forward: staged source rows per frame (upper bound)
+  int nx, ny, cpt;
+};
+struct TapRow {   // one interpolation tap pair, pre-multiplied row offsets into the staged tile
+  int o0, o1;
+  float l0, l1;
+};
+
+__device__ __forceinline__ void build_w_taps(const ResizeGeom& g, int* tw_i0, float* tw_l1, int tid, int nthreads) {
+  for (int wo = tid; wo < g.Wo; wo += nthreads) {
+    const Tap t = linear_tap(wo, g.Wi, g.sw, g.align);
+    tw_i0[wo] = t.i0;
+    tw_l1[wo] = t.l1;
+  }
+}
+
+// stage a[ti][r][wo] = W-lerp of source row (hs_lo + r) of frame ti, for r < n_rows.  Column-outer (the W tap of a
+// column is read once), four rows per step with all eight loads issued before the arithmetic (memory-level parallelism).
+__device__ __forceinline__ void stage_w_lerp(const float* __restrict__ xc, const TiledGeom& tg, int hs_lo, int n_rows,
+                                             const int* tw_i0, const float* tw_l1, float* a) {
+  const ResizeGeom& g = tg.g;
+  const int rows = g.Ti * n_rows;
+  const int frame_skip = (g.Hi - n_rows) * g.Wi;      // source offset jump between the last band row of a frame and
+  for (int wo = threadIdx.x; wo < g.Wo; wo += tg.nx) {   // the first of the next
+    const int i0 = tw_i0[wo];
+    const int i1 = i0 + (i0 < g.Wi - 1 ? 1 : 0);
+    const float l1 = tw_l1[wo];
+    const float l0 = __fsub_rn(1.0f, l1);
+    for (int r0 = threadIdx.y; r0 < rows; r0 += 4 * tg.ny) {
+      float va[4], vb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u * tg.ny;
+        if (r < rows) {
+          const int ti = r / n_rows;
+          const float* src = xc + static_cast<long long>(hs_lo + r) * g.Wi + static_cast<long long>(ti) * frame_skip;
+          va[u] = __ldg(src + i0);
+          vb[u] = __ldg(src + i1);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u * tg.ny;
+        if (r < rows) a[static_cast<long long>(r) * g.Wo + wo] = lerp_rn(l0, va[u], l1, vb[u]);
+      }
+    }
+  }
+}
+
+// T / H tap tables of one band, offsets in floats into the staged tile a[Ti][n_rows][Wo]
+__device__ __forceinline__ void build_th_taps(const TiledGeom& tg, int ho0, int ho1, int hs_lo, int n_rows, TapRow* ttab,
+                                              TapRow* htab, int tid, int nthreads) {
+  const ResizeGeom& g = tg.g;
+  for (int i = tid; i < g.To + (ho1 - ho0); i += nthreads) {
+    if (i < g.To) {
+      const Tap t = linear_tap(i, g.Ti, g.st, g.align);
+      ttab[i] = TapRow{t.i0 * n_rows * g.Wo, t.i1 * n_rows * g.Wo, t.l0, t.l1};
+    } else {
+      const int hl = i - g.To;
+      const Tap t = linear_tap(ho0 + hl, g.Hi, g.sh, g.align);
+      htab[hl] = TapRow{(t.i0 - hs_lo) * g.Wo, (t.i1 - hs_lo) * g.Wo, t.l0, t.l1};
+    }
+  }
+}
+
+// y[to][ho][wo] for the band from the staged tile: same H-then-T order as trilerp().  A thread walks along T for its
+// (row, column): the H-interpolated value of a source frame is computed once and reused by the ~To/Ti outputs that
+// tap it (the branches depend only on `to`, i.e. they are uniform).
+__device__ __forceinline__ void interp_band(const TiledGeom& tg, int ho0, int ho1, const float* a, const TapRow* ttab,
+                                            const TapRow* htab, float* __restrict__ yc) {
+  const ResizeGeom& g = tg.g;
+  const long long plane = static_cast<long long>(g.Ho) * g.Wo;
+  for (int hl = threadIdx.y; hl < ho1 - ho0; hl += tg.ny) {
+    const TapRow th = htab[hl];
+    float* drow = yc + static_cast<long long>(ho0 + hl) * g.Wo;
+    for (int wo = threadIdx.x; wo < g.Wo; wo += tg.nx) {
+      const float* c0 = a + th.o0 + wo;
+      const float* c1 = a + th.o1 + wo;
+      int k0 = -1, k1 = -1;          // frame offsets of the cached H-interpolated values v0, v1
+      float v0 = 0.f, v1 = 0.f;
+      float* dst = drow + wo;
+      for (int to = 0; to < g.To; ++to, dst += plane) {
+        const TapRow tt = ttab[to];
+        float n0, n1;
+        if (tt.o0 == k0) n0 = v0;
+        else if (tt.o0 == k1) n0 = v1;
+        else n0 = lerp_rn(th.l0, c0[tt.o0], th.l1, c1[tt.o0]);
+        if (tt.o1 == tt.o0) n1 = n0;
+        else if (tt.o1 == k1) n1 = v1;
+        else if (tt.o1 == k0) n1 = v0;
+        else n1 = lerp_rn(th.l0, c0[tt.o1], th.l1, c1[tt.o1]);
+        k0 = tt.o0; k1 = tt.o1; v0 = n0; v1 = n1;
+        *dst = lerp_rn(tt.l0, n0, tt.l1, n1);
+      }
+    }
+  }
+}
+
+struct FwdTile {
+  float* a;
+  int* tw_i0;
+  float* tw_l1;
+  TapRow* ttab;
+  TapRow* htab;
+  int ho0, ho1, hs_lo, n_rows;
+};
+__device__ __forceinline__ FwdTile carve_fwd(float* sm, const TiledGeom& tg) {
+  const ResizeGeom& g = tg.g;
+  FwdTile f;
+  f.ttab = reinterpret_cast<TapRow*>(sm);                               // 16-byte aligned first
+  f.htab = f.ttab + g.To;
+  f.a = reinterpret_cast<float*>(f.htab + tg.band);
+  f.tw_i0 = reinterpret_cast<int*>(f.a + static_cast<long long>(g.Ti) * tg.n_hs * g.Wo);
+  f.tw_l1 = reinterpret_cast<float*>(f.tw_i0 + g.Wo);
+  f.ho0 = blockIdx.x * tg.band;
+  f.ho1 = min(f.ho0 + tg.band, g.Ho);
+  f.hs_lo = linear_tap(f.ho0, g.Hi, g.sh, g.align).i0;
+  f.n_rows = linear_tap(f.ho1 - 1, g.Hi, g.sh, g.align).i1 - f.hs_lo + 1;   // <= tg.n_hs by construction
+  return f;
+}
+
+__global__ void resize3d_fwd_tiled_kernel(const float* __restrict__ x, const TiledGeom tg, float* __restrict__ y) {
+  extern __shared__ __align__(16) float rs_sm[];
+  const ResizeGeom& g = tg.g;
+  const FwdTile f = carve_fwd(rs_sm, tg);
+  const int tid = threadIdx.y * tg.nx + threadIdx.x, nth = tg.nx * tg.ny;
+  const long long nc = blockIdx.y;
+  build_w_taps(g, f.tw_i0, f.tw_l1, tid, nth);
+  build_th_taps(tg, f.ho0, f.ho1, f.hs_lo, f.n_rows, f.ttab, f.htab, tid, nth);
+  __syncthreads();
+  stage_w_lerp(x + nc * g.Ti * g.Hi * g.Wi, tg, f.hs_lo, f.n_rows, f.tw_i0, f.tw_l1, f.a);
+  __syncthreads();
+  interp_band(tg, f.ho0, f.ho1, f.a, f.ttab, f.htab, y + nc * g.To * g.Ho * g.Wo);
+}
+
+// fused block input stage, tiled: per channel stage + interpolate -> up ; then x_in = bf16(up + noise*amp) for the voxels
+// this thread just wrote (same thread <-> same voxel in both loops, so it re-reads its own stores).
+__global__ void upsample_noise_pack_tiled_kernel(const float* __restrict__ x, int C, const TiledGeom tg,
+                                                 const float* __restrict__ noise, float amp, unsigned long long seed,
+                                                 unsigned long long sample_base,
+                                                 const unsigned long long* __restrict__ d_sample_offset,
+                                                 float* __restrict__ up, __nv_bfloat16* __restrict__ xin) {
+  extern __shared__ __align__(16) float rs_sm[];
+  const ResizeGeom& g = tg.g;
+  if (d_sample_offset) sample_base += *d_sample_offset;
+  const FwdTile f = carve_fwd(rs_sm, tg);
+  const int tid = threadIdx.y * tg.nx + threadIdx.x, nth = tg.nx * tg.ny;
+  const long long n = blockIdx.y;
+  const long long spo = static_cast<long long>(g.To) * g.Ho * g.Wo;
+  const long long spi = static_cast<long long>(g.Ti) * g.Hi * g.Wi;
+  build_w_taps(g, f.tw_i0, f.tw_l1, tid, nth);
+  build_th_taps(tg, f.ho0, f.ho1, f.hs_lo, f.n_rows, f.ttab, f.htab, tid, nth);
+  for (int c = 0; c < C; ++c) {
+    __syncthreads();
+    stage_w_lerp(x + (n * C + c) * spi, tg, f.hs_lo, f.n_rows, f.tw_i0, f.tw_l1, f.a);
+    __syncthreads();
+    interp_band(tg, f.ho0, f.ho1, f.a, f.ttab, f.htab, up + (n * C + c) * spo);
+  }
+  // pack: x_in[n][to][ho][wo][0..7] = bf16(up + noise*amp), zero padded to 8 channels.  SAME (row, column) -> thread
+  // mapping as interp_band(), so every thread re-reads only values it stored itself.
+  const unsigned long long sample = sample_base + static_cast<unsigned long long>(n);
+  for (int hl = threadIdx.y; hl < f.ho1 - f.ho0; hl += tg.ny) {
+    for (int wo = threadIdx.x; wo < g.Wo; wo += tg.nx) {
+      for (int to = 0; to < g.To; ++to) {
+        const long long sidx = (static_cast<long long>(to) * g.Ho + (f.ho0 + hl)) * g.Wo + wo;
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!noise && seed != 0ull) {
+          const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(sidx), static_cast<uint32_t>(sidx >> 32),
+                                                     static_cast<uint32_t>(sample), static_cast<uint32_t>(sample >> 32)),
+                                          make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+          box_muller(rnd.x, rnd.y, z[0], z[1]);
+          box_muller(rnd.z, rnd.w, z[2], z[3]);
+        }
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < C; ++c) {
+          const long long o = (n * C + c) * spo + sidx;
+          const float u = up[o];
+          const float nz = noise ? noise[o] : z[c];
+          v[c] = fmaf(nz, amp, u);
+        }
+        *reinterpret_cast<uint4*>(xin + (n * spo + sidx) * 8) =
+            make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+      }
+    }
+  }
+}
+
+// backward: a thread owns (source row hs, column wo) and walks along T_out with register accumulators for the (at
+// most two) source frames currently being fed — no shared-memory read-modify-write, fixed order => deterministic.
+__global__ void resize3d_bwd_tiled_kernel(const float* __restrict__ gy, const TiledGeom tg, float* __restrict__ gx) {
+  extern __shared__ __align__(16) float rs_sm[];
+  const ResizeGeom& g = tg.g;
+  const int hs0 = blockIdx.x * tg.band;
+  const int hs1 = min(hs0 + tg.band, g.Hi);
+  const int n_rows = hs1 - hs0;
+  TapRow* htab = reinterpret_cast<TapRow*>(rs_sm);                     // [Ho]: (i0, i1, l0, l1) of every output row
+  TapRow* ttab = htab + g.Ho;                                          // [To]
+  float* b = reinterpret_cast<float*>(ttab + g.To);                    // [Ti][band][Wo]
+  int* tw_i0 = reinterpret_cast<int*>(b + static_cast<long long>(g.Ti) * tg.band * g.Wo);
+  float* tw_l1 = reinterpret_cast<float*>(tw_i0 + g.Wo);
+  int* first = reinterpret_cast<int*>(tw_l1 + g.Wo);                   // [Wi + 2]: first[i] = min{wo : i0[wo] >= i}
+  int* hfirst = first + g.Wi + 2;                                      // [Hi + 2]: first[i] = min{ho : i0[ho] >= i}
+  const int tid = threadIdx.y * tg.nx + threadIdx.x, nth = tg.nx * tg.ny;
+  const long long nc = blockIdx.y;
+  build_w_taps(g, tw_i0, tw_l1, tid, nth);
+  for (int i = tid; i < g.Ho + g.To; i += nth) {
+    if (i < g.Ho) {
+      const Tap t = linear_tap(i, g.Hi, g.sh, g.align);
+      htab[i] = TapRow{t.i0, t.i1, t.l0, t.l1};
+    } else {
+      const Tap t = linear_tap(i - g.Ho, g.Ti, g.st, g.align);
+      ttab[i - g.Ho] = TapRow{t.i0, t.i1, t.l0, t.l1};
+    }
+  }
+  __syncthreads();
+  for (int wo = tid; wo < g.Wo; wo += nth) {                           // inverse W table
+    const int cur = tw_i0[wo];
+    const int lo = (wo == 0) ? 0 : tw_i0[wo - 1] + 1;
+    for (int i = lo; i <= cur; ++i) first[i] = wo;
+    if (wo == g.Wo - 1)
+      for (int i = cur + 1; i <= g.Wi + 1; ++i) first[i] = g.Wo;
+  }
+  for (int ho = tid; ho < g.Ho; ho += nth) {                           // inverse H table
+    const int cur = htab[ho].o0;
+    const int lo = (ho == 0) ? 0 : htab[ho - 1].o0 + 1;
+    for (int i = lo; i <= cur; ++i) hfirst[i] = ho;
+    if (ho == g.Ho - 1)
+      for (int i = cur + 1; i <= g.Hi + 1; ++i) hfirst[i] = g.Ho;
+  }
+  __syncthreads();
+  const float* gyc = gy + nc * g.To * g.Ho * g.Wo;
+  const long long plane = static_cast<long long>(g.Ho) * g.Wo;
+  const long long fs = static_cast<long long>(tg.band) * g.Wo;         // frame stride inside b
+  // stage 1: b[ti][hs][wo] = sum_to ct(to -> ti) * sum_ho ch(ho -> hs) * gy[to][ho][wo]
+  for (int hl = threadIdx.y; hl < n_rows; hl += tg.ny) {
+    const int hs = hs0 + hl;
+    const int h_lo = hfirst[hs > 0 ? hs - 1 : 0], h_hi = hfirst[hs + 1];   // candidates: i0(ho) in {hs-1, hs}
+    for (int wo = threadIdx.x; wo < g.Wo; wo += tg.nx) {
+      float* bcol = b + static_cast<long long>(hl) * g.Wo + wo;
+      int f_lo = 0;
+      float acc_lo = 0.f, acc_hi = 0.f;
+      const float* src = gyc + wo + static_cast<long long>(h_lo) * g.Wo;
+      const int nh = h_hi - h_lo;
+      float chv[4] = {0.f, 0.f, 0.f, 0.f};   // H coefficients of the candidate rows (constant along T)
+      if (nh <= 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < nh) {
+            const TapRow th = htab[h_lo + k];
+            chv[k] = (th.o0 == hs ? th.l0 : 0.f) + (th.o1 == hs ? th.l1 : 0.f);
+          }
+      }
+      float cur[4] = {0.f, 0.f, 0.f, 0.f};
+      if (nh <= 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < nh) cur[k] = __ldg(src + static_cast<long long>(k) * g.Wo);
+      }
+      for (int to = 0; to < g.To; ++to, src += plane) {
+        float sh = 0.f;
+        if (nh <= 4) {
+          float nxt[4] = {0.f, 0.f, 0.f, 0.f};
+          if (to + 1 < g.To) {       // issue the next frame's loads before consuming this frame's
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < nh) nxt[k] = __ldg(src + plane + static_cast<long long>(k) * g.Wo);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) sh = fmaf(chv[k], cur[k], sh);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
+        } else {
+          for (int k = 0; k < nh; ++k) {
+            const TapRow th = htab[h_lo + k];
+            const float ch = (th.o0 == hs ? th.l0 : 0.f) + (th.o1 == hs ? th.l1 : 0.f);
+            sh = fmaf(ch, __ldg(src + static_cast<long long>(k) * g.Wo), sh);
+          }
+        }
+        const TapRow tt = ttab[to];
+        while (f_lo < tt.o0) {        // frames below i0(to) are complete (i0 is non-decreasing in `to`)
+          bcol[f_lo * fs] = acc_lo;
+          acc_lo = acc_hi;
+          acc_hi = 0.f;
+          ++f_lo;
+        }
+        acc_lo = fmaf(tt.l0, sh, acc_lo);
+        if (tt.o1 == f_lo) acc_lo = fmaf(tt.l1, sh, acc_lo);
+        else acc_hi = fmaf(tt.l1, sh, acc_hi);
+      }
+      for (; f_lo < g.Ti; ++f_lo) {
+        bcol[f_lo * fs] = acc_lo;
+        acc_lo = acc_hi;
+        acc_hi = 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  // stage 2: gx[ti][hs][wi] = sum_wo cw(wo -> wi) * b[ti][hs][wo]
+  float* gxc = gx + nc * g.Ti * g.Hi * g.Wi;
+  for (int r = threadIdx.y; r < g.Ti * n_rows; r += tg.ny) {
+    const int ti = r / n_rows, hl = r - ti * n_rows;
+    const float* brow = b + (static_cast<long long>(ti) * tg.band + hl) * g.Wo;
+    float* dst = gxc + (static_cast<long long>(ti) * g.Hi + (hs0 + hl)) * g.Wi;
+    for (int wi = threadIdx.x; wi < g.Wi; wi += tg.nx) {
+      const int lo = first[wi > 0 ? wi - 1 : 0], hi = first[wi + 1];
+      float acc = 0.f;
+      for (int wo = lo; wo < hi; ++wo) {
+        const int i0 = tw_i0[wo];
+        const int i1 = i0 + (i0 < g.Wi - 1 ? 1 : 0);
+        const float l1 = tw_l1[wo];
+        const float cw = (i0 == wi ? __fsub_rn(1.0f, l1) : 0.f) + (i1 == wi ? l1 : 0.f);
+        acc = fmaf(cw, brow[wo], acc);
+      }
+      dst[wi] = acc;
+    }
+  }
+}
+
 // z[i] ~ N(0,1): Philox4x32-10 keyed by `seed`, counter = (element/4, offset [+ *d_offset]) — the device stand-in for
 // the reference's host numpy draws (images.py:17-21, networks_3d.py:28-34) when the step is replayed as a CUDA graph.
 __global__ void randn_kernel(float* __restrict__ z, long long n, unsigned long long seed, unsigned long long offset,
@@ -580,6 +911,18 @@ __global__ void reparam_kernel(const float* __restrict__ mu, const float* __rest
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     z[i] = fmaf(eps[i], expf(0.5f * lv[i]), mu[i]);
+}
+
+// backward of z = eps*exp(0.5*logvar) + mu (networks_3d.py:415-417): gmu += gz ; glogvar += gz*eps*0.5*exp(0.5*logvar)
+__global__ void reparam_bwd_kernel(const float* __restrict__ gz, const float* __restrict__ eps,
+                                   const float* __restrict__ lv, long long n, float* __restrict__ gmu,
+                                   float* __restrict__ glv) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float g = gz[i];
+    gmu[i] += g;
+    glv[i] = fmaf(g * eps[i], 0.5f * expf(0.5f * lv[i]), glv[i]);
+  }
 }
 
 // ----------------------------------------------------------------------------------------------- clip + Adam
@@ -965,17 +1308,86 @@ cudaError_t ew_linear_taps_dev(int n_in, int n_out, int align, int32_t* i0, int3
   LAUNCH_CHECK();
   return cudaSuccess;
 }
+// Tile planning for the shared-memory-staged resize kernels.  Forward: `band` output rows need at most
+// floor((band-1)*sh) + 3 source rows.  Returns false when even a 1-row band does not fit (-> generic kernel).
+constexpr size_t RS_SMEM_BUDGET = 72 * 1024;   // three CTAs per SM
+static void plan_threads(int Wo, int max_ny, TiledGeom* tg) {
+  tg->cpt = (Wo + 255) / 256;
+  tg->nx = (Wo + tg->cpt - 1) / tg->cpt;
+  int ny = 512 / tg->nx;
+  if (ny < 1) ny = 1;
+  if (ny > max_ny) ny = max_ny;
+  tg->ny = ny;
+}
+static bool plan_fwd_tiles(const ResizeGeom& g, TiledGeom* tg, size_t* smem) {
+  for (int lg = 4; lg >= 0; --lg) {
+    const int band = 1 << lg;
+    const int n_hs = static_cast<int>((band - 1) * (g.sh > 0.f ? g.sh : 0.f)) + 3;
+    const size_t bytes = (static_cast<size_t>(g.Ti) * n_hs * g.Wo + 2 * static_cast<size_t>(g.Wo)) * 4 +
+                         (static_cast<size_t>(g.To) + band) * 16;
+    if (bytes <= RS_SMEM_BUDGET) {
+      tg->g = g; tg->band = band; tg->band_log2 = lg; tg->n_hs = n_hs;
+      plan_threads(g.Wo, 64, tg);
+      *smem = bytes;
+      return true;
+    }
+  }
+  return false;
+}
+static bool plan_bwd_tiles(const ResizeGeom& g, TiledGeom* tg, size_t* smem) {
+  for (int lg = 3; lg >= 0; --lg) {
+    const int band = 1 << lg;
+    const size_t bytes = (static_cast<size_t>(g.Ti) * band * g.Wo + 2 * static_cast<size_t>(g.Wo) + g.Wi + g.Hi + 4) * 4 +
+                         (static_cast<size_t>(g.Ho) + g.To) * 16;
+    if (bytes <= RS_SMEM_BUDGET) {
+      tg->g = g; tg->band = band; tg->band_log2 = lg; tg->n_hs = 0;
+      plan_threads(g.Wo, band, tg);       // thread rows own source rows of the band
+      *smem = bytes;
+      return true;
+    }
+  }
+  return false;
+}
+template <typename K>
+static cudaError_t rs_allow_smem(K kernel, bool* done) {
+  if (*done) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(RS_SMEM_BUDGET));
+  if (e == cudaSuccess) *done = true;
+  return e;
+}
+
 cudaError_t ew_resize3d_fwd(const float* x, long long NC, int Ti, int Hi, int Wi, float* y, int To, int Ho, int Wo,
                             int align, cudaStream_t st) {
   const ResizeGeom g = make_geom(Ti, Hi, Wi, To, Ho, Wo, align);
-  resize3d_fwd_kernel<<<grid_for(NC * To * Ho * Wo, 256), 256, 0, st>>>(x, NC, g, y);
+  TiledGeom tg;
+  size_t smem;
+  if (NC <= 65535 && plan_fwd_tiles(g, &tg, &smem)) {
+    static bool ok = false;
+    cudaError_t e = rs_allow_smem(resize3d_fwd_tiled_kernel, &ok);
+    if (e != cudaSuccess) return e;
+    resize3d_fwd_tiled_kernel<<<dim3((Ho + tg.band - 1) / tg.band, static_cast<unsigned>(NC)), dim3(tg.nx, tg.ny), smem, st>>>(
+        x, tg, y);
+  } else {
+    resize3d_fwd_kernel<<<grid_for(NC * To * Ho * Wo, 256), 256, 0, st>>>(x, NC, g, y);
+  }
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_resize3d_bwd(const float* gy, long long NC, int To, int Ho, int Wo, float* gx, int Ti, int Hi, int Wi,
                             int align, cudaStream_t st) {
   const ResizeGeom g = make_geom(Ti, Hi, Wi, To, Ho, Wo, align);
-  resize3d_bwd_kernel<<<grid_for(NC * Ti * Hi * Wi, 128), 128, 0, st>>>(gy, NC, g, gx);
+  TiledGeom tg;
+  size_t smem;
+  if (NC <= 65535 && plan_bwd_tiles(g, &tg, &smem)) {
+    static bool ok = false;
+    cudaError_t e = rs_allow_smem(resize3d_bwd_tiled_kernel, &ok);
+    if (e != cudaSuccess) return e;
+    resize3d_bwd_tiled_kernel<<<dim3((Hi + tg.band - 1) / tg.band, static_cast<unsigned>(NC)), dim3(tg.nx, tg.ny), smem, st>>>(
+        gy, tg, gx);
+  } else {
+    resize3d_bwd_kernel<<<grid_for(NC * Ti * Hi * Wi, 128), 128, 0, st>>>(gy, NC, g, gx);
+  }
   LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -984,8 +1396,18 @@ cudaError_t ew_upsample_noise_pack(const float* x, int N, int C, int Ti, int Hi,
                                    unsigned long long sample_base, const unsigned long long* d_sample_offset,
                                    float* up, __nv_bfloat16* xin, cudaStream_t st) {
   const ResizeGeom g = make_geom(Ti, Hi, Wi, To, Ho, Wo, 1);
-  upsample_noise_pack_kernel<<<grid_for(static_cast<long long>(N) * To * Ho * Wo, 256), 256, 0, st>>>(
-      x, N, C, g, noise, amp, seed, sample_base, d_sample_offset, up, xin);
+  TiledGeom tg;
+  size_t smem;
+  if (N <= 65535 && plan_fwd_tiles(g, &tg, &smem)) {
+    static bool ok = false;
+    cudaError_t e = rs_allow_smem(upsample_noise_pack_tiled_kernel, &ok);
+    if (e != cudaSuccess) return e;
+    upsample_noise_pack_tiled_kernel<<<dim3((Ho + tg.band - 1) / tg.band, N), dim3(tg.nx, tg.ny), smem, st>>>(
+        x, C, tg, noise, amp, seed, sample_base, d_sample_offset, up, xin);
+  } else {
+    upsample_noise_pack_kernel<<<grid_for(static_cast<long long>(N) * To * Ho * Wo, 256), 256, 0, st>>>(
+        x, N, C, g, noise, amp, seed, sample_base, d_sample_offset, up, xin);
+  }
   LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -1063,6 +1485,12 @@ cudaError_t ew_reduce(int op, const float* a, const float* b, long long n, float
 }
 cudaError_t ew_reparam(const float* mu, const float* lv, const float* eps, long long n, float* z, cudaStream_t st) {
   reparam_kernel<<<grid_for(n, 256), 256, 0, st>>>(mu, lv, eps, n, z);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_reparam_bwd(const float* gz, const float* eps, const float* lv, long long n, float* gmu, float* glv,
+                           cudaStream_t st) {
+  reparam_bwd_kernel<<<grid_for(n, 256), 256, 0, st>>>(gz, eps, lv, n, gmu, glv);
   LAUNCH_CHECK();
   return cudaSuccess;
 }

@@ -64,6 +64,8 @@ cudaError_t ew_bn_fold_eval(const float* gamma, const float* beta, const float* 
 cudaError_t ew_affine_from_bias(const float* bias, const float* inv_sigma, int C, float* scale, float* shift,
                                 cudaStream_t st);
 cudaError_t ew_reduce(int op, const float* a, const float* b, long long n, float* out, cudaStream_t st);
+cudaError_t ew_reparam_bwd(const float* gz, const float* eps, const float* lv, long long n, float* gmu, float* glv,
+                           cudaStream_t st);
 cudaError_t ew_reparam(const float* mu, const float* lv, const float* eps, long long n, float* z, cudaStream_t st);
 cudaError_t ew_adam_clip(const AdamTable& tab, int n_tensors, float* norms_scratch, float beta1, float beta2,
                          float eps, float bias_corr, float clip, const unsigned long long* d_step, cudaStream_t st);

@@ -77,6 +77,7 @@ _SIGS = {
     "hpvg_mean": ([vp, ll, vp, vp], c_int),
     "hpvg_kl": ([vp, vp, ll, vp, vp], c_int),
     "hpvg_reparam": ([vp, vp, vp, ll, vp, vp], c_int),
+    "hpvg_reparam_bwd": ([vp, vp, vp, ll, vp, vp, vp], c_int),
     "hpvg_conv_wgrad_cl": ([vp, i, vp, i, i, i, i, i, vp, i, i, i, i, i, i, i, f, vp], c_int),
     "hpvg_lrelu_bwd_cl": ([vp, vp, ll, vp, vp], c_int),
     "hpvg_bn_bwd_cl": ([vp, vp, ll, vp, i, vp, vp, vp, i, vp], c_int),

@@ -345,6 +345,12 @@ def reparam(mu, logvar, eps, out=None, stream=None):
     return out
 
 
+def reparam_bwd(gz, eps, logvar, gmu, glv, stream=None):
+    """Backward of networks_3d.py:415-417: gmu += gz ; glogvar += gz*eps*0.5*exp(0.5*logvar)."""
+    check(lib.hpvg_reparam_bwd(_p(gz), _p(eps), _p(logvar), gz.size, _p(gmu), _p(glv), _s(stream)), "reparam_bwd")
+    return gmu, glv
+
+
 def adam_clip_multi(params, grads, ms, vs, lrs, step, beta1=0.5, beta2=0.999, eps=1e-8, clip=0.0, stream=None,
                     d_step=None):
     """ClippedAdam.construct (optimizers.py:41-43) / nn.Adam for D (train_video.py:65): per-tensor ClipByNorm then Adam."""

@@ -386,6 +386,7 @@ class GeneratorTrainer:
                 if eps is None:
                     eps = self._draw(mu.shape, stream)
                 z = ops.reparam(mu, logvar, eps, stream=stream)
+                out["eps"] = eps
             else:
                 z = z_pred if z_pred is not None else self._draw(mu.shape, stream)
         else:
@@ -470,14 +471,15 @@ class GWithLoss:
             else:
                 g_v = ops.mse_grad(vae_out, real_zero, self.rec_weight * 2.0 / vae_out.size, g=g_cur, accumulate=True,
                                    stream=stream)
-            block_backward(net.decoder, fw["dec_ctx"], g_v, g, ws, "dec", need_dx=False, trainable=train_codec,
-                           stream=stream)
-            # ---- encoder: only the KL term reaches it (Q2: z is pure noise unless is_training)
-            if net.is_training:
-                raise HpvgError("is_training=True (reparameterised z) backward is not implemented; the reference's "
-                                "drivers never enable it (train_video.py:387)")
+            _, g_z_cl = block_backward(net.decoder, fw["dec_ctx"], g_v, g, ws, "dec", need_dx=net.is_training,
+                                       trainable=train_codec, stream=stream)
+            # ---- encoder: the KL term always reaches it; the reconstruction terms only through the reparameterised z,
+            # i.e. only with is_training=True (Q2: the reference's drivers leave it False, then z is pure noise)
             mu, lv = fw["mu"], fw["logvar"]
             gmu, glv = ops.kl_grad(mu, lv, self.kl_weight / mu.size, stream=stream)
+            if net.is_training:
+                g_z = ops.unpack_cl(g_z_cl, stream=stream)
+                ops.reparam_bwd(g_z, fw["eps"], lv, gmu, glv, stream=stream)
             gmu_cl, glv_cl = ops.pack_cl(gmu, stream=stream), ops.pack_cl(glv, stream=stream)
             enc = net.encode
             d1 = layer_backward(enc._mu, fw["mu_ctx"], gmu_cl, g, ws, "enc.mu", True, train_codec, stream)
