@@ -56,6 +56,14 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def traffic_per_voxel():
+    p = os.path.join(ROOT, "profiles", "conv64_traffic.json")
+    try:
+        return float(json.load(open(p))["dram_bytes_per_voxel"])
+    except Exception:
+        return float("nan")
+
+
 def workload_name(opt, batch):
     from hpvg.utils import images as uimg
     t, h, w = uimg.scale_shape(opt, opt.stop_scale)
@@ -107,8 +115,8 @@ def cpu_sample_clips(opt_kw, n_clips, threads=None):
     """Time the CPU oracle (torch-CPU fp32, all host cores) generating n_clips full-pyramid samples."""
     import torch
     from oracle import hpvg_oracle as orc
-    if threads:
-        torch.set_num_threads(threads)
+    # all host cores: torchrun exports OMP_NUM_THREADS=1 to its workers, which would throttle the CPU arm
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     opt = orc.default_opt(**opt_kw)
     p = orc.to_torch(orc.init_generator_params(opt, opt.stop_scale, seed=0))
     rng = np.random.default_rng(0)
@@ -349,9 +357,9 @@ def run_ours(args):
                 "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peaks_kind,
                 "launches_timed": len(prof), "avg_launch_ms": kms / max(len(prof), 1),
                 "share_of_step": kms / ms_dev,
-                # dram__bytes_read+write per launch from the committed ncu capture (profiles/r1_conv64_ncu_full_summary.csv:
-                # 609 MB for 4 x 641472 voxels = 237 B/voxel; algorithmic = 2 x 128 B/voxel), scaled to this run's launches
-                "traffic": 237.3 * (sum(v for v, _ in prof) / max(len(prof), 1)),
+                # dram__bytes_read+write per voxel from the committed `ncu --set full` capture of this kernel
+                # (profiles/conv64_traffic.json; algorithmic = 2 x 128 B/voxel), scaled to this run's mean launch
+                "traffic": traffic_per_voxel() * (sum(v for v, _ in prof) / max(len(prof), 1)),
                 "traffic_unit": "bytes per launch (mean over timed launches)"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

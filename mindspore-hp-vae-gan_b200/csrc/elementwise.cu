@@ -221,10 +221,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 __device__ __forceinline__ float u01(uint32_t x) { return (static_cast<float>(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+// Box-Muller on the SFU fast paths (__logf / __sincosf: abs error ~1e-6, irrelevant for a noise source, and 5x cheaper
+// than the range-reduced library versions — the fused block-input kernel is ALU-bound by this)
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
-  const float r = sqrtf(-2.0f * logf(u01(a)));
+  const float r = sqrtf(-2.0f * __logf(u01(a)));
   float s, c;
-  sincosf(6.283185307179586f * u01(b), &s, &c);
+  __sincosf(6.283185307179586f * u01(b), &s, &c);
   z0 = r * c;
   z1 = r * s;
 }
@@ -291,57 +293,39 @@ __device__ __forceinline__ void stage_w_lerp(const float* __restrict__ xc, const
   }
 }
 
-// T / H tap tables of one band, offsets in floats into the staged tile a[Ti][n_rows][Wo]
-__device__ __forceinline__ void build_th_taps(const TiledGeom& tg, int ho0, int ho1, int hs_lo, int n_rows, TapRow* ttab,
-                                              TapRow* htab, int tid, int nthreads) {
+// H stage: hb[ti][hl][wo] = lerp_h(a[ti][h0(hl)][wo], a[ti][h1(hl)][wo]) for the rows of the band
+__device__ __forceinline__ void interp_h(const TiledGeom& tg, int band_rows, int n_rows, const float* a,
+                                         const TapRow* htab, float* hb) {
   const ResizeGeom& g = tg.g;
-  for (int i = tid; i < g.To + (ho1 - ho0); i += nthreads) {
-    if (i < g.To) {
-      const Tap t = linear_tap(i, g.Ti, g.st, g.align);
-      ttab[i] = TapRow{t.i0 * n_rows * g.Wo, t.i1 * n_rows * g.Wo, t.l0, t.l1};
-    } else {
-      const int hl = i - g.To;
-      const Tap t = linear_tap(ho0 + hl, g.Hi, g.sh, g.align);
-      htab[hl] = TapRow{(t.i0 - hs_lo) * g.Wo, (t.i1 - hs_lo) * g.Wo, t.l0, t.l1};
-    }
+  const int rows = g.Ti * band_rows;
+  for (int r = threadIdx.y; r < rows; r += tg.ny) {
+    const int ti = r / band_rows, hl = r - ti * band_rows;
+    const TapRow th = htab[hl];
+    const float* r0 = a + ti * n_rows * g.Wo + th.o0;
+    const float* r1 = a + ti * n_rows * g.Wo + th.o1;
+    float* dst = hb + r * g.Wo;
+    for (int wo = threadIdx.x; wo < g.Wo; wo += tg.nx) dst[wo] = lerp_rn(th.l0, r0[wo], th.l1, r1[wo]);
   }
 }
 
-// y[to][ho][wo] for the band from the staged tile: same H-then-T order as trilerp().  A thread walks along T for its
-// (row, column): the H-interpolated value of a source frame is computed once and reused by the ~To/Ti outputs that
-// tap it (the branches depend only on `to`, i.e. they are uniform).
-__device__ __forceinline__ void interp_band(const TiledGeom& tg, int ho0, int ho1, const float* a, const TapRow* ttab,
-                                            const TapRow* htab, float* __restrict__ yc) {
+// T stage: the band's rows are contiguous both in hb (per frame) and in y (per frame): a pure streaming loop
+__device__ __forceinline__ void interp_t(const TiledGeom& tg, int band_rows, int ho0, const float* hb,
+                                         const TapRow* ttab, float* __restrict__ yc, int tid, int nth) {
   const ResizeGeom& g = tg.g;
+  const int n = band_rows * g.Wo, fs = band_rows * g.Wo;
+  float* dst = yc + static_cast<long long>(ho0) * g.Wo;
   const long long plane = static_cast<long long>(g.Ho) * g.Wo;
-  for (int hl = threadIdx.y; hl < ho1 - ho0; hl += tg.ny) {
-    const TapRow th = htab[hl];
-    float* drow = yc + static_cast<long long>(ho0 + hl) * g.Wo;
-    for (int wo = threadIdx.x; wo < g.Wo; wo += tg.nx) {
-      const float* c0 = a + th.o0 + wo;
-      const float* c1 = a + th.o1 + wo;
-      int k0 = -1, k1 = -1;          // frame offsets of the cached H-interpolated values v0, v1
-      float v0 = 0.f, v1 = 0.f;
-      float* dst = drow + wo;
-      for (int to = 0; to < g.To; ++to, dst += plane) {
-        const TapRow tt = ttab[to];
-        float n0, n1;
-        if (tt.o0 == k0) n0 = v0;
-        else if (tt.o0 == k1) n0 = v1;
-        else n0 = lerp_rn(th.l0, c0[tt.o0], th.l1, c1[tt.o0]);
-        if (tt.o1 == tt.o0) n1 = n0;
-        else if (tt.o1 == k1) n1 = v1;
-        else if (tt.o1 == k0) n1 = v0;
-        else n1 = lerp_rn(th.l0, c0[tt.o1], th.l1, c1[tt.o1]);
-        k0 = tt.o0; k1 = tt.o1; v0 = n0; v1 = n1;
-        *dst = lerp_rn(tt.l0, n0, tt.l1, n1);
-      }
-    }
+  for (int to = 0; to < g.To; ++to, dst += plane) {
+    const TapRow tt = ttab[to];                 // o0 / o1 = source frame indices here
+    const float* f0 = hb + tt.o0 * fs;
+    const float* f1 = hb + tt.o1 * fs;
+    for (int i = tid; i < n; i += nth) dst[i] = lerp_rn(tt.l0, f0[i], tt.l1, f1[i]);
   }
 }
 
 struct FwdTile {
   float* a;
+  float* hb;
   int* tw_i0;
   float* tw_l1;
   TapRow* ttab;
@@ -354,13 +338,29 @@ __device__ __forceinline__ FwdTile carve_fwd(float* sm, const TiledGeom& tg) {
   f.ttab = reinterpret_cast<TapRow*>(sm);                               // 16-byte aligned first
   f.htab = f.ttab + g.To;
   f.a = reinterpret_cast<float*>(f.htab + tg.band);
-  f.tw_i0 = reinterpret_cast<int*>(f.a + static_cast<long long>(g.Ti) * tg.n_hs * g.Wo);
+  f.hb = f.a + g.Ti * tg.n_hs * g.Wo;
+  f.tw_i0 = reinterpret_cast<int*>(f.hb + g.Ti * tg.band * g.Wo);
   f.tw_l1 = reinterpret_cast<float*>(f.tw_i0 + g.Wo);
   f.ho0 = blockIdx.x * tg.band;
   f.ho1 = min(f.ho0 + tg.band, g.Ho);
   f.hs_lo = linear_tap(f.ho0, g.Hi, g.sh, g.align).i0;
   f.n_rows = linear_tap(f.ho1 - 1, g.Hi, g.sh, g.align).i1 - f.hs_lo + 1;   // <= tg.n_hs by construction
   return f;
+}
+
+// T / H tap tables of one band: ttab = source frame indices, htab = row offsets (floats) inside one staged frame
+__device__ __forceinline__ void build_th_taps(const TiledGeom& tg, const FwdTile& f, int tid, int nthreads) {
+  const ResizeGeom& g = tg.g;
+  for (int i = tid; i < g.To + (f.ho1 - f.ho0); i += nthreads) {
+    if (i < g.To) {
+      const Tap t = linear_tap(i, g.Ti, g.st, g.align);
+      f.ttab[i] = TapRow{t.i0, t.i1, t.l0, t.l1};
+    } else {
+      const int hl = i - g.To;
+      const Tap t = linear_tap(f.ho0 + hl, g.Hi, g.sh, g.align);
+      f.htab[hl] = TapRow{(t.i0 - f.hs_lo) * g.Wo, (t.i1 - f.hs_lo) * g.Wo, t.l0, t.l1};
+    }
+  }
 }
 
 __global__ void resize3d_fwd_tiled_kernel(const float* __restrict__ x, const TiledGeom tg, float* __restrict__ y) {
@@ -370,15 +370,17 @@ __global__ void resize3d_fwd_tiled_kernel(const float* __restrict__ x, const Til
   const int tid = threadIdx.y * tg.nx + threadIdx.x, nth = tg.nx * tg.ny;
   const long long nc = blockIdx.y;
   build_w_taps(g, f.tw_i0, f.tw_l1, tid, nth);
-  build_th_taps(tg, f.ho0, f.ho1, f.hs_lo, f.n_rows, f.ttab, f.htab, tid, nth);
+  build_th_taps(tg, f, tid, nth);
   __syncthreads();
   stage_w_lerp(x + nc * g.Ti * g.Hi * g.Wi, tg, f.hs_lo, f.n_rows, f.tw_i0, f.tw_l1, f.a);
   __syncthreads();
-  interp_band(tg, f.ho0, f.ho1, f.a, f.ttab, f.htab, y + nc * g.To * g.Ho * g.Wo);
+  interp_h(tg, f.ho1 - f.ho0, f.n_rows, f.a, f.htab, f.hb);
+  __syncthreads();
+  interp_t(tg, f.ho1 - f.ho0, f.ho0, f.hb, f.ttab, y + nc * g.To * g.Ho * g.Wo, tid, nth);
 }
 
-// fused block input stage, tiled: per channel stage + interpolate -> up ; then x_in = bf16(up + noise*amp) for the voxels
-// this thread just wrote (same thread <-> same voxel in both loops, so it re-reads its own stores).
+// fused block input stage, tiled: per channel W / H / T stages -> up ; then x_in = bf16(up + noise*amp) for the voxels
+// this thread just wrote (same thread <-> same voxel in the T stage and in the pack loop).
 __global__ void upsample_noise_pack_tiled_kernel(const float* __restrict__ x, int C, const TiledGeom tg,
                                                  const float* __restrict__ noise, float amp, unsigned long long seed,
                                                  unsigned long long sample_base,
@@ -392,21 +394,154 @@ __global__ void upsample_noise_pack_tiled_kernel(const float* __restrict__ x, in
   const long long n = blockIdx.y;
   const long long spo = static_cast<long long>(g.To) * g.Ho * g.Wo;
   const long long spi = static_cast<long long>(g.Ti) * g.Hi * g.Wi;
+  const int band_rows = f.ho1 - f.ho0;
   build_w_taps(g, f.tw_i0, f.tw_l1, tid, nth);
-  build_th_taps(tg, f.ho0, f.ho1, f.hs_lo, f.n_rows, f.ttab, f.htab, tid, nth);
+  build_th_taps(tg, f, tid, nth);
   for (int c = 0; c < C; ++c) {
     __syncthreads();
     stage_w_lerp(x + (n * C + c) * spi, tg, f.hs_lo, f.n_rows, f.tw_i0, f.tw_l1, f.a);
     __syncthreads();
-    interp_band(tg, f.ho0, f.ho1, f.a, f.ttab, f.htab, up + (n * C + c) * spo);
+    interp_h(tg, band_rows, f.n_rows, f.a, f.htab, f.hb);
+    __syncthreads();
+    interp_t(tg, band_rows, f.ho0, f.hb, f.ttab, up + (n * C + c) * spo, tid, nth);
   }
-  // pack: x_in[n][to][ho][wo][0..7] = bf16(up + noise*amp), zero padded to 8 channels.  SAME (row, column) -> thread
-  // mapping as interp_band(), so every thread re-reads only values it stored itself.
+  // pack: x_in[n][to][ho][wo][0..7] = bf16(up + noise*amp), zero padded to 8 channels.  SAME (frame, element) -> thread
+  // mapping as interp_t(), so every thread re-reads only values it stored itself.
   const unsigned long long sample = sample_base + static_cast<unsigned long long>(n);
-  for (int hl = threadIdx.y; hl < f.ho1 - f.ho0; hl += tg.ny) {
-    for (int wo = threadIdx.x; wo < g.Wo; wo += tg.nx) {
-      for (int to = 0; to < g.To; ++to) {
-        const long long sidx = (static_cast<long long>(to) * g.Ho + (f.ho0 + hl)) * g.Wo + wo;
+  const int nel = band_rows * g.Wo;
+  const long long plane = static_cast<long long>(g.Ho) * g.Wo;
+  for (int to = 0; to < g.To; ++to) {
+    const long long base = to * plane + static_cast<long long>(f.ho0) * g.Wo;
+    for (int i = tid; i < nel; i += nth) {
+      const long long sidx = base + i;
+      float z[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!noise && seed != 0ull) {
+        const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(sidx), static_cast<uint32_t>(sidx >> 32),
+                                                   static_cast<uint32_t>(sample), static_cast<uint32_t>(sample >> 32)),
+                                        make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+        box_muller(rnd.x, rnd.y, z[0], z[1]);
+        box_muller(rnd.z, rnd.w, z[2], z[3]);
+      }
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int c = 0; c < C; ++c) {
+        const long long o = (n * C + c) * spo + sidx;
+        const float u = up[o];
+        const float nz = noise ? noise[o] : z[c];
+        v[c] = fmaf(nz, amp, u);
+      }
+      *reinterpret_cast<uint4*>(xin + (n * spo + sidx) * 8) =
+          make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- column-walk resize
+// Register-only forward for Ti <= 8 (every pyramid level): a thread owns one output column (ho, wo), loads the 4 source
+// values of every source frame up front (4*Ti independent loads, served by L1/L2 — neighbouring threads share them),
+// forms the W- then H-interpolated value hv[ti] of each frame ONCE, and walks along T_out writing ~To/Ti outputs per
+// frame.  Same W -> H -> T operation order as trilerp() => identical bits.  No shared-memory tile, no barriers except
+// the one that publishes the T tap table.
+constexpr int CW_MAX_TI = 8;
+constexpr int CW_THREADS = 256;
+
+template <int C>
+__device__ __forceinline__ void colwalk_load(const float* __restrict__ xs, long long spi, const ResizeGeom& g,
+                                             const Tap& th, const Tap& tw, float (&hv)[C][CW_MAX_TI + 1]) {
+  const int o00 = th.i0 * g.Wi + tw.i0, o01 = th.i0 * g.Wi + tw.i1;
+  const int o10 = th.i1 * g.Wi + tw.i0, o11 = th.i1 * g.Wi + tw.i1;
+  const int fsz = g.Hi * g.Wi;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float v[CW_MAX_TI][4];
+#pragma unroll
+    for (int f = 0; f < CW_MAX_TI; ++f) {
+      if (f < g.Ti) {
+        const float* p = xs + c * spi + f * fsz;
+        v[f][0] = __ldg(p + o00);
+        v[f][1] = __ldg(p + o01);
+        v[f][2] = __ldg(p + o10);
+        v[f][3] = __ldg(p + o11);
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < CW_MAX_TI; ++f) {
+      hv[c][f] = 0.f;
+      if (f < g.Ti) {
+        const float a0 = lerp_rn(tw.l0, v[f][0], tw.l1, v[f][1]);
+        const float a1 = lerp_rn(tw.l0, v[f][2], tw.l1, v[f][3]);
+        hv[c][f] = lerp_rn(th.l0, a0, th.l1, a1);
+      }
+    }
+    hv[c][CW_MAX_TI] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(CW_THREADS)
+resize3d_fwd_colwalk_kernel(const float* __restrict__ x, const ResizeGeom g, float* __restrict__ y) {
+  __shared__ TapRow ttab[64];
+  for (int i = threadIdx.x; i < g.To; i += blockDim.x) {
+    const Tap t = linear_tap(i, g.Ti, g.st, g.align);
+    ttab[i] = TapRow{t.i0, t.i1, t.l0, t.l1};
+  }
+  __syncthreads();
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= g.Ho * g.Wo) return;
+  const int ho = col / g.Wo, wo = col - ho * g.Wo;
+  const long long nc = blockIdx.y;
+  const Tap th = linear_tap(ho, g.Hi, g.sh, g.align), tw = linear_tap(wo, g.Wi, g.sw, g.align);
+  const long long spi = static_cast<long long>(g.Ti) * g.Hi * g.Wi;
+  float hv[1][CW_MAX_TI + 1];
+  colwalk_load<1>(x + nc * spi, spi, g, th, tw, hv);
+  const int plane = g.Ho * g.Wo;
+  float* dst = y + nc * g.To * plane + col;
+  int to = 0;
+#pragma unroll
+  for (int f = 0; f < CW_MAX_TI; ++f) {
+    if (f < g.Ti) {
+      while (to < g.To) {
+        const TapRow tt = ttab[to];
+        if (tt.o0 != f) break;
+        const float hi = (tt.o1 == f) ? hv[0][f] : hv[0][f + 1];
+        *dst = lerp_rn(tt.l0, hv[0][f], tt.l1, hi);
+        dst += plane;
+        ++to;
+      }
+    }
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(CW_THREADS)
+upsample_noise_pack_colwalk_kernel(const float* __restrict__ x, const ResizeGeom g, const float* __restrict__ noise,
+                                   float amp, unsigned long long seed, unsigned long long sample_base,
+                                   const unsigned long long* __restrict__ d_sample_offset, float* __restrict__ up,
+                                   __nv_bfloat16* __restrict__ xin) {
+  __shared__ TapRow ttab[64];
+  for (int i = threadIdx.x; i < g.To; i += blockDim.x) {
+    const Tap t = linear_tap(i, g.Ti, g.st, g.align);
+    ttab[i] = TapRow{t.i0, t.i1, t.l0, t.l1};
+  }
+  __syncthreads();
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= g.Ho * g.Wo) return;
+  if (d_sample_offset) sample_base += *d_sample_offset;
+  const int ho = col / g.Wo, wo = col - ho * g.Wo;
+  const long long n = blockIdx.y;
+  const Tap th = linear_tap(ho, g.Hi, g.sh, g.align), tw = linear_tap(wo, g.Wi, g.sw, g.align);
+  const long long spi = static_cast<long long>(g.Ti) * g.Hi * g.Wi;
+  const int plane = g.Ho * g.Wo;
+  const long long spo = static_cast<long long>(g.To) * plane;
+  float hv[C][CW_MAX_TI + 1];
+  colwalk_load<C>(x + n * C * spi, spi, g, th, tw, hv);
+  const unsigned long long sample = sample_base + static_cast<unsigned long long>(n);
+  long long sidx = col;               // spatial index inside the sample
+  int to = 0;
+#pragma unroll
+  for (int f = 0; f < CW_MAX_TI; ++f) {
+    if (f < g.Ti) {
+      while (to < g.To) {
+        const TapRow tt = ttab[to];
+        if (tt.o0 != f) break;
         float z[4] = {0.f, 0.f, 0.f, 0.f};
         if (!noise && seed != 0ull) {
           const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(sidx), static_cast<uint32_t>(sidx >> 32),
@@ -416,14 +551,19 @@ __global__ void upsample_noise_pack_tiled_kernel(const float* __restrict__ x, in
           box_muller(rnd.z, rnd.w, z[2], z[3]);
         }
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
         for (int c = 0; c < C; ++c) {
+          const float hi = (tt.o1 == f) ? hv[c][f] : hv[c][f + 1];
+          const float u = lerp_rn(tt.l0, hv[c][f], tt.l1, hi);
           const long long o = (n * C + c) * spo + sidx;
-          const float u = up[o];
+          up[o] = u;
           const float nz = noise ? noise[o] : z[c];
           v[c] = fmaf(nz, amp, u);
         }
         *reinterpret_cast<uint4*>(xin + (n * spo + sidx) * 8) =
             make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+        sidx += plane;
+        ++to;
       }
     }
   }
@@ -1310,7 +1450,8 @@ cudaError_t ew_linear_taps_dev(int n_in, int n_out, int align, int32_t* i0, int3
 }
 // Tile planning for the shared-memory-staged resize kernels.  Forward: `band` output rows need at most
 // floor((band-1)*sh) + 3 source rows.  Returns false when even a 1-row band does not fit (-> generic kernel).
-constexpr size_t RS_SMEM_BUDGET = 72 * 1024;   // three CTAs per SM
+constexpr size_t RS_SMEM_BUDGET = 72 * 1024;   // backward: three CTAs per SM
+constexpr size_t RS_SMEM_FWD = 110 * 1024;     // forward (two staged tiles): two CTAs per SM
 static void plan_threads(int Wo, int max_ny, TiledGeom* tg) {
   tg->cpt = (Wo + 255) / 256;
   tg->nx = (Wo + tg->cpt - 1) / tg->cpt;
@@ -1319,14 +1460,18 @@ static void plan_threads(int Wo, int max_ny, TiledGeom* tg) {
   if (ny > max_ny) ny = max_ny;
   tg->ny = ny;
 }
+// the register-only forward needs Ti <= 8 frames, To <= 64 taps, int-sized slices; i0 must be non-decreasing (always)
+static bool colwalk_ok(const ResizeGeom& g, long long slices) {
+  return g.Ti <= CW_MAX_TI && g.To <= 64 && slices <= 65535 &&
+         static_cast<long long>(g.To) * g.Ho * g.Wo < (1LL << 31) && static_cast<long long>(g.Ti) * g.Hi * g.Wi < (1LL << 31);
+}
 static bool plan_fwd_tiles(const ResizeGeom& g, TiledGeom* tg, size_t* smem) {
-  for (int lg = 4; lg >= 0; --lg) {
-    const int band = 1 << lg;
+  for (int band = 16; band >= 1; --band) {
     const int n_hs = static_cast<int>((band - 1) * (g.sh > 0.f ? g.sh : 0.f)) + 3;
-    const size_t bytes = (static_cast<size_t>(g.Ti) * n_hs * g.Wo + 2 * static_cast<size_t>(g.Wo)) * 4 +
+    const size_t bytes = (static_cast<size_t>(g.Ti) * (n_hs + band) * g.Wo + 2 * static_cast<size_t>(g.Wo)) * 4 +
                          (static_cast<size_t>(g.To) + band) * 16;
-    if (bytes <= RS_SMEM_BUDGET) {
-      tg->g = g; tg->band = band; tg->band_log2 = lg; tg->n_hs = n_hs;
+    if (bytes <= RS_SMEM_FWD) {
+      tg->g = g; tg->band = band; tg->band_log2 = 0; tg->n_hs = n_hs;
       plan_threads(g.Wo, 64, tg);
       *smem = bytes;
       return true;
@@ -1352,7 +1497,7 @@ template <typename K>
 static cudaError_t rs_allow_smem(K kernel, bool* done) {
   if (*done) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(RS_SMEM_BUDGET));
+                                       static_cast<int>(RS_SMEM_FWD));
   if (e == cudaSuccess) *done = true;
   return e;
 }
@@ -1362,7 +1507,10 @@ cudaError_t ew_resize3d_fwd(const float* x, long long NC, int Ti, int Hi, int Wi
   const ResizeGeom g = make_geom(Ti, Hi, Wi, To, Ho, Wo, align);
   TiledGeom tg;
   size_t smem;
-  if (NC <= 65535 && plan_fwd_tiles(g, &tg, &smem)) {
+  if (colwalk_ok(g, NC)) {
+    resize3d_fwd_colwalk_kernel<<<dim3((Ho * Wo + CW_THREADS - 1) / CW_THREADS, static_cast<unsigned>(NC)), CW_THREADS,
+                                  0, st>>>(x, g, y);
+  } else if (NC <= 65535 && plan_fwd_tiles(g, &tg, &smem)) {
     static bool ok = false;
     cudaError_t e = rs_allow_smem(resize3d_fwd_tiled_kernel, &ok);
     if (e != cudaSuccess) return e;
@@ -1398,7 +1546,16 @@ cudaError_t ew_upsample_noise_pack(const float* x, int N, int C, int Ti, int Hi,
   const ResizeGeom g = make_geom(Ti, Hi, Wi, To, Ho, Wo, 1);
   TiledGeom tg;
   size_t smem;
-  if (N <= 65535 && plan_fwd_tiles(g, &tg, &smem)) {
+  if (colwalk_ok(g, N) && C >= 1 && C <= 4) {
+    const dim3 grid((Ho * Wo + CW_THREADS - 1) / CW_THREADS, N);
+#define HPVG_CW(C_) upsample_noise_pack_colwalk_kernel<C_><<<grid, CW_THREADS, 0, st>>>( \
+      x, g, noise, amp, seed, sample_base, d_sample_offset, up, xin)
+    if (C == 1) HPVG_CW(1);
+    else if (C == 2) HPVG_CW(2);
+    else if (C == 3) HPVG_CW(3);
+    else HPVG_CW(4);
+#undef HPVG_CW
+  } else if (N <= 65535 && plan_fwd_tiles(g, &tg, &smem)) {
     static bool ok = false;
     cudaError_t e = rs_allow_smem(upsample_noise_pack_tiled_kernel, &ok);
     if (e != cudaSuccess) return e;
