@@ -32,6 +32,7 @@ extern "C" {
 #define HPVG_CONV_64_64 0 /* Cin 64 -> Cout 64                                   */
 #define HPVG_CONV_64_16 1 /* Cin 64 -> Cout <= 4 real (tail convs 64->3, 64->1)  */
 #define HPVG_CONV_8_64 2  /* Cin <= 8 (zero padded to 8) -> Cout 64 (head convs) */
+#define HPVG_CONV_64_3 3  /* Cin 64 -> Cout <= 3, in-plane taps folded into N (fast tail convs; fp32 ncdhw out) */
 #define HPVG_ACT_NONE 0
 #define HPVG_ACT_LRELU 1 /* LeakyReLU(0.2): mindspore.nn.LeakyReLU default, networks_3d.py:20 */
 #define HPVG_ACT_TANH 2

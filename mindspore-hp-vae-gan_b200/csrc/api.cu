@@ -192,7 +192,7 @@ int hpvg_conv_wimg_bytes(int mode) { return hpvg::conv3d_umma_wimg_bytes(mode); 
 
 int hpvg_conv_pack_weights(const float* w, int w_cout, int w_cin, int kt, int mode, int transpose_flip, int cout_off,
                            int cout, int cin_off, int cin, void* wimg, void* st) {
-  const int max_co = (mode == HPVG_CONV_64_16) ? 16 : 64;
+  const int max_co = (mode == HPVG_CONV_64_16) ? 16 : (mode == HPVG_CONV_64_3) ? 3 : 64;
   const int max_ci = (mode == HPVG_CONV_8_64) ? 8 : 64;
   if (cout > max_co || cin > max_ci || cout <= 0 || cin <= 0)
     return fail(HPVG_E_ARG, "conv_pack_weights: channel counts exceed the kernel variant");
@@ -211,7 +211,7 @@ int hpvg_conv_cl(int mode, int N, int T, int H, int W, const void* in, int in_pi
   if (out_mode == HPVG_OUT_BF16_CL && ((out_pitch & 7) || (out_coff & 7)))
     return fail(HPVG_E_ARG, "conv_cl: out_pitch/out_coff must be multiples of 8");
   if (g_sm_count == 0) return fail(HPVG_E_ARG, "hpvg_init was not called");
-  if (stats && (mode == HPVG_CONV_64_16 || out_mode != HPVG_OUT_BF16_CL))
+  if (stats && (mode == HPVG_CONV_64_16 || mode == HPVG_CONV_64_3 || out_mode != HPVG_OUT_BF16_CL))
     return fail(HPVG_E_ARG, "conv_cl: fused BatchNorm statistics need a 64-channel bf16 output");
   hpvg::ConvLaunch L;
   L.mode = mode;

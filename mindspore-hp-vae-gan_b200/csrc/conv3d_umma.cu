@@ -500,6 +500,7 @@ cudaError_t launch_mode(const CUtensorMap& tmap, const ConvParams& prm, int n_pa
 }  // namespace
 
 const char* conv3d_umma_launch(const ConvLaunch& L, cudaStream_t stream) {
+  if (L.mode == CONV_MODE_64_T) return conv3d_tail_launch(L, 2 * L.max_pairs, stream);
   EncodeTiledFn enc = get_encode();
   if (!enc) return "cuTensorMapEncodeTiled entry point not available";
   const int cin_pitch = L.in_pitch;  // channels per voxel row in the input tensor
@@ -581,6 +582,7 @@ int conv3d_umma_wimg_bytes(int mode) {
     case CONV_MODE_64_64: return 2 * Cfg<CONV_MODE_64_64>::W_BYTES;
     case CONV_MODE_64_16: return 2 * Cfg<CONV_MODE_64_16>::W_BYTES;
     case CONV_MODE_8_64: return 2 * Cfg<CONV_MODE_8_64>::W_BYTES;
+    case CONV_MODE_64_T: return conv3d_tail_wimg_bytes();
   }
   return 0;
 }
@@ -598,6 +600,38 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int c
   int rank, tap, row, ci;
   float val = 0.f;
   bool valid = true;
+  if (mode == CONV_MODE_64_T) {
+    // [dt 3][row n = (dh*3+dw)*3 + co (32 rows, 27 used)][64 ci], 128B-swizzled rows; no CTA split
+    const int dt = idx / (32 * 64);
+    const int rem = idx - dt * 32 * 64;
+    const int n = rem / 64, within = rem - n * 64;
+    const int chunk = (within >> 3) ^ (n & 7);
+    ci = chunk * 8 + (within & 7);
+    const int s = n / 3, co3 = n - s * 3;
+    valid = n < 27;
+    {
+      const int dh = s / 3, dw = s - dh * 3;
+      int dtt = dt;
+      if (kt == 1) {
+        valid = valid && (dt == 1);
+        dtt = 0;
+      }
+      if (valid && co3 < cout && ci < cin) {
+        if (!transpose_flip) {
+          const size_t o =
+              ((((static_cast<size_t>(co3 + cout_off) * w_cin) + (ci + cin_off)) * kt + dtt) * 3 + dh) * 3 + dw;
+          val = w[o];
+        } else {
+          const int fdt = (kt == 1) ? 0 : 2 - dtt;
+          const size_t o =
+              ((((static_cast<size_t>(ci + cin_off) * w_cin) + (co3 + cout_off)) * kt + fdt) * 3 + (2 - dh)) * 3 + (2 - dw);
+          val = w[o];
+        }
+      }
+    }
+    img[idx] = __float2bfloat16_rn(val);
+    return;
+  }
   if (mode == CONV_MODE_64_64 || mode == CONV_MODE_64_16) {
     const int rows = (mode == CONV_MODE_64_64) ? 32 : 8;
     const int per_rank = 27 * rows * 64;

@@ -5,7 +5,7 @@
 
 namespace hpvg {
 
-enum ConvMode { CONV_MODE_64_64 = 0, CONV_MODE_64_16 = 1, CONV_MODE_8_64 = 2 };
+enum ConvMode { CONV_MODE_64_64 = 0, CONV_MODE_64_16 = 1, CONV_MODE_8_64 = 2, CONV_MODE_64_T = 3 };
 enum ConvAct { CONV_ACT_NONE = 0, CONV_ACT_LRELU = 1, CONV_ACT_TANH = 2 };
 enum ConvOut { CONV_OUT_BF16_NDHWC = 0, CONV_OUT_F32_NCDHW = 1, CONV_OUT_F32_RAW = 2 };
 
@@ -51,6 +51,11 @@ const char* conv3d_umma_launch(const ConvLaunch& L, cudaStream_t stream);
 int conv3d_umma_wimg_bytes(int mode);
 const char* conv3d_pack_weights(const float* w, int w_cout, int w_cin, int kt, int mode, int transpose_flip,
                                 int cout_off, int cout, int cin_off, int cin, void* img, cudaStream_t stream);
+
+// 64 -> (<= 3) tail convolution with the in-plane taps folded into N (conv3d_tail.cu); uses ConvLaunch with
+// mode == CONV_MODE_64_T, out_mode == CONV_OUT_F32_NCDHW
+const char* conv3d_tail_launch(const ConvLaunch& L, int sm_count, cudaStream_t stream);
+int conv3d_tail_wimg_bytes();
 
 // weight gradient (conv3d_wgrad.cu)
 size_t conv3d_wgrad_workspace_bytes(int sm_count);

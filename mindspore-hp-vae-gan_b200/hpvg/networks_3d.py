@@ -138,7 +138,7 @@ class ConvLayer(Cell):
         if self._wimgs is None:
             w = self.p["weight"]
             if self.cout <= 4:
-                self._wimgs = [ops.pack_weights(w, ops.CONV_64_16, stream=stream)]
+                self._wimgs = [ops.pack_weights(w, ops.tail_mode(self.cout), stream=stream)]
             else:
                 self._wimgs = []
                 mode = ops.CONV_8_64 if self.cin <= 8 else ops.CONV_64_64

@@ -9,7 +9,7 @@ from . import runtime as rt
 from ._lib import HpvgError, check, lib
 from .runtime import BF16, F32, F64, I32, Tensor, _s
 
-CONV_64_64, CONV_64_16, CONV_8_64 = 0, 1, 2
+CONV_64_64, CONV_64_16, CONV_8_64, CONV_64_3 = 0, 1, 2, 3
 ACT_NONE, ACT_LRELU, ACT_TANH = 0, 1, 2
 OUT_BF16_CL, OUT_F32_NCDHW, OUT_F32_RAW = 0, 1, 2
 BN_EPS = 1e-5        # mindspore.nn.BatchNorm3d default
@@ -72,9 +72,16 @@ def conv_mode_for(cin, cout):
         return CONV_8_64
     if cin == 64 and cout == 64:
         return CONV_64_64
+    if cin == 64 and cout <= 3:
+        return CONV_64_3
     if cin == 64 and cout <= 4:
         return CONV_64_16
     raise HpvgError("no single-pass conv kernel variant for Cin=%d Cout=%d" % (cin, cout))
+
+
+def tail_mode(cout):
+    """Kernel variant for a 64 -> cout (<= 4) convolution with fp32 NCDHW output."""
+    return CONV_64_3 if cout <= 3 else CONV_64_16
 
 
 def pack_weights(w, mode, transpose_flip=False, cout_off=0, cout=None, cin_off=0, cin=None, out=None, stream=None):
@@ -152,9 +159,10 @@ def conv3d_cl_any(x_cl, w, aff, act, cin, cout, out_mode=OUT_BF16_CL, residual=N
     N, T, H, W, pitch = x_cl.shape
     if cout <= 4:
         assert cin == 64
-        wi = wimgs[0] if wimgs else pack_weights(w, CONV_64_16, transpose_flip, stream=stream)
+        mode = tail_mode(cout)
+        wi = wimgs[0] if wimgs else pack_weights(w, mode, transpose_flip, stream=stream)
         s, b = _sc(aff)
-        return conv_cl(CONV_64_16, x_cl, wi, s, b, act, OUT_F32_NCDHW, out=out, cout_real=cout, addend=residual,
+        return conv_cl(mode, x_cl, wi, s, b, act, OUT_F32_NCDHW, out=out, cout_real=cout, addend=residual,
                        stream=stream)
     n_ob = cout // 64
     n_ib = 1 if cin <= 8 else cin // 64

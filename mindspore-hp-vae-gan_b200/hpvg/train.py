@@ -173,7 +173,7 @@ def _dgrad_wimgs(layer, stream=None):
     w = layer.p["weight"]
     cin, cout = layer.cin, layer.cout           # forward channels; dgrad maps cout -> cin
     if cin <= 8:                                 # 64 -> (<=4): tail-type kernel
-        return [ops.pack_weights(w, CONV_64_16, True, cout=cin, stream=stream)]
+        return [ops.pack_weights(w, ops.tail_mode(cin), True, cout=cin, stream=stream)]
     if cout <= 4:                                # (<=4, zero padded to 8) -> 64: head-type kernel
         return [ops.pack_weights(w, CONV_8_64, True, cin=cout, stream=stream)]
     imgs = []
@@ -206,7 +206,7 @@ def conv_backward(layer, ctx, gy_cl, grads, ws, key, need_dx=True, want_dw=True,
     sc, sh = aff.view((64,), F32, 0), _unit_affine(stream).view((64,), F32, 256)
     if cin <= 8:
         out = ws.get(key + ".dx3", (N, cin, T, H, W), F32)
-        return ops.conv_cl(CONV_64_16, gy_cl, imgs[0], sc, sh, ACT_NONE, OUT_F32_NCDHW, out=out, cout_real=cin,
+        return ops.conv_cl(ops.tail_mode(cin), gy_cl, imgs[0], sc, sh, ACT_NONE, OUT_F32_NCDHW, out=out, cout_real=cin,
                            stream=stream)
     dx = ws.get(key + ".dx", (N, T, H, W, cin), BF16)
     if cout <= 4:

@@ -29,7 +29,11 @@ def peak_gbs():
     return 6650.0, "fallback"
 
 
-def timed(st, fn, iters=10, warm=3):
+ITERS, WARM = [10], [3]
+
+
+def timed(st, fn, iters=None, warm=None):
+    iters, warm = iters or ITERS[0], WARM[0] if warm is None else warm
     for _ in range(warm):
         fn()
     st.sync()
@@ -47,7 +51,10 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--clips", type=int, default=48, help="3-channel clips per launch for the resize kernels")
     ap.add_argument("--wide", type=int, default=6, help="64-channel finest-scale clips per launch for the BN kernels")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--warm", type=int, default=3)
     args = ap.parse_args()
+    ITERS[0], WARM[0] = max(args.iters, 1), max(args.warm, 0)
     hpvg.init(0)
     st = hpvg.Stream()
     peak, kind = peak_gbs()
