@@ -62,6 +62,7 @@ int hpvg_event_create(void** event);
 int hpvg_event_destroy(void* event);
 int hpvg_event_record(void* event, void* stream);
 int hpvg_event_sync(void* event);
+int hpvg_stream_wait_event(void* stream, void* event); /* later work on `stream` waits for `event` */
 int hpvg_event_elapsed_ms(void* start, void* stop, float* ms);
 /* CUDA-graph capture of everything enqueued on `stream` between begin and end */
 int hpvg_graph_begin(void* stream);

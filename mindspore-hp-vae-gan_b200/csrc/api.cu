@@ -138,6 +138,10 @@ int hpvg_event_record(void* ev, void* st) {
   CU(cudaEventRecord(static_cast<cudaEvent_t>(ev), S(st)));
   return HPVG_OK;
 }
+int hpvg_stream_wait_event(void* st, void* ev) {
+  CU(cudaStreamWaitEvent(S(st), static_cast<cudaEvent_t>(ev), 0));
+  return HPVG_OK;
+}
 int hpvg_event_sync(void* ev) {
   CU(cudaEventSynchronize(static_cast<cudaEvent_t>(ev)));
   return HPVG_OK;

@@ -46,6 +46,7 @@ _SIGS = {
     "hpvg_event_destroy": ([vp], c_int),
     "hpvg_event_record": ([vp, vp], c_int),
     "hpvg_event_sync": ([vp], c_int),
+    "hpvg_stream_wait_event": ([vp, vp], c_int),
     "hpvg_event_elapsed_ms": ([vp, vp, POINTER(f)], c_int),
     "hpvg_graph_begin": ([vp], c_int),
     "hpvg_graph_end": ([vp, POINTER(vp)], c_int),

@@ -411,6 +411,8 @@ class GeneratorHPVAEGAN(Cell):
         self.bn_slab = BnStatsSlab()
         self.noise_seed = 0x9E3779B97F4A7C15   # device Philox key for internally drawn noise
         self.sample_counter = 0
+        self.out_slot = 0    # which of the alternating buffers receives the final clip (lets a caller overlap the
+                             # device->host copy of clip i with the generation of clip i+1)
 
     def init_next_stage(self):
         """networks_3d.py:393-404: first stage is freshly initialised, later stages deep-copy the previous one."""
@@ -497,6 +499,7 @@ class GeneratorHPVAEGAN(Cell):
                     seed = (self.noise_seed + 0x632BE59BD9B4E019 * (idx + 1)) & 0xFFFFFFFFFFFFFFFF
             ops.upsample_noise_pack(x_prev_out, size, noise=noise_t, amp=amp, seed=seed,
                                     sample_base=self.sample_counter, up=up, xin=xin, stream=stream)
-            out = self.ws.get("out%d" % idx, (N, opt.nc_im) + size, F32)
+            last = idx == len(self.body) - 1
+            out = self.ws.get("out%d%s" % (idx, ".%d" % self.out_slot if last else ""), (N, opt.nc_im) + size, F32)
             x_prev_out = self._run_block(block, xin, up, "s%d" % idx, stream, out=out)
         return x_prev_out

@@ -41,6 +41,10 @@ class Stream:
     def sync(self):
         check(lib.hpvg_stream_sync(self.handle), "stream_sync")
 
+    def wait_event(self, event):
+        """Work enqueued on this stream after the call waits for `event` (device-side, the host does not block)."""
+        check(lib.hpvg_stream_wait_event(self.handle, event.handle), "stream_wait_event")
+
 
 class Event:
     def __init__(self):

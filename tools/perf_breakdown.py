@@ -32,4 +32,10 @@ agg = collections.defaultdict(float)
 for (mode, vox), ms in items: agg[mode] += ms
 tot = sum(agg.values())
 print("conv kernels in one step: total %.2f ms: " % tot + ", ".join("mode %d: %.2f ms" % (m, v) for m, v in sorted(agg.items())))
+per = collections.defaultdict(lambda: [0, 0.0])
+for (mode, vox), ms in items:
+    per[(mode, vox)][0] += 1; per[(mode, vox)][1] += ms
+print("mode  voxels/launch  launches   ms_total   ns/voxel   TFLOP/s(64->64)")
+for (mode, vox), (n, ms) in sorted(per.items()):
+    print("%4d %12d %8d %10.3f %10.3f %10.1f" % (mode, vox, n, ms, ms * 1e6 / (vox * n), (2*27*64*64*vox*n/ms/1e9) if mode == 0 else 0))
 print("pool stats", hpvg.runtime._POOL_STATS)
