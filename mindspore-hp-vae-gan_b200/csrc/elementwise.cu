@@ -569,6 +569,101 @@ upsample_noise_pack_colwalk_kernel(const float* __restrict__ x, const ResizeGeom
   }
 }
 
+// Register-only backward (adjoint) for moderate up-sampling (at most 4 output rows / columns tap one source row /
+// column, i.e. ratio <= 1.5 in H and W — every pyramid level): a thread owns one SOURCE column (hs, wi), its <= 4 x 4
+// contributing (ho, wo) positions and their H/W coefficients are fixed along T, so it walks T_out once,
+//     S(to) = sum_k ch[k] sum_j cw[j] gy[to][h_lo+k][w_lo+j],
+// and feeds S into register accumulators of the (at most two) source frames that `to` taps; a frame is stored as soon
+// as the walk has passed it.  Deterministic (fixed order), no atomics, no shared-memory tile.
+struct InvTap {
+  int lo, n;        // contributing outputs [lo, lo+n)
+  float c[4];       // their coefficients
+};
+__device__ __forceinline__ int first_output_at_or_above(int i, int n_in, int n_out, float scale, int align) {
+  // min{o : i0(o) >= i}; i0 is non-decreasing in o
+  if (i <= 0) return 0;
+  if (scale <= 0.f) return n_out;
+  const float off = align ? 0.f : 0.5f;
+  int o = static_cast<int>(floorf((static_cast<float>(i) + off) / scale - off)) - 1;
+  if (o < 0) o = 0;
+  while (o < n_out && linear_tap(o, n_in, scale, align).i0 < i) ++o;
+  return o;
+}
+__device__ __forceinline__ InvTap make_inv_tap(int i, int n_in, int n_out, float scale, int align) {
+  InvTap e;
+  e.lo = first_output_at_or_above(i - 1, n_in, n_out, scale, align);
+  const int hi = (i + 1 > n_in - 1 + 1) ? n_out : first_output_at_or_above(i + 1, n_in, n_out, scale, align);
+  e.n = hi - e.lo;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    e.c[k] = 0.f;
+    if (k < e.n) {
+      const Tap t = linear_tap(e.lo + k, n_in, scale, align);
+      e.c[k] = (t.i0 == i ? t.l0 : 0.f) + (t.i1 == i ? t.l1 : 0.f);
+    }
+  }
+  return e;
+}
+
+constexpr int BW_TX = 32, BW_TY = 8;
+__global__ void __launch_bounds__(BW_TX * BW_TY)
+resize3d_bwd_colwalk_kernel(const float* __restrict__ gy, const ResizeGeom g, float* __restrict__ gx) {
+  __shared__ TapRow ttab[64];
+  __shared__ InvTap htab[BW_TY], wtab[BW_TX];
+  const int tid = threadIdx.y * BW_TX + threadIdx.x;
+  const int hs0 = blockIdx.y * BW_TY, wi0 = blockIdx.x * BW_TX;
+  for (int i = tid; i < g.To; i += BW_TX * BW_TY) {
+    const Tap t = linear_tap(i, g.Ti, g.st, g.align);
+    ttab[i] = TapRow{t.i0, t.i1, t.l0, t.l1};
+  }
+  if (tid < BW_TY) {
+    if (hs0 + tid < g.Hi) htab[tid] = make_inv_tap(hs0 + tid, g.Hi, g.Ho, g.sh, g.align);
+  } else if (tid >= 32 && tid < 32 + BW_TX) {
+    const int j = tid - 32;
+    if (wi0 + j < g.Wi) wtab[j] = make_inv_tap(wi0 + j, g.Wi, g.Wo, g.sw, g.align);
+  }
+  __syncthreads();
+  const int hs = hs0 + threadIdx.y, wi = wi0 + threadIdx.x;
+  if (hs >= g.Hi || wi >= g.Wi) return;
+  const InvTap eh = htab[threadIdx.y], ew = wtab[threadIdx.x];
+  const long long nc = blockIdx.z;
+  const int plane_o = g.Ho * g.Wo, plane_i = g.Hi * g.Wi;
+  const float* src = gy + nc * g.To * plane_o + eh.lo * g.Wo + ew.lo;
+  float* dst = gx + nc * g.Ti * plane_i + hs * g.Wi + wi;
+  int f_lo = 0;
+  float acc_lo = 0.f, acc_hi = 0.f;
+  for (int to = 0; to < g.To; ++to, src += plane_o) {
+    float v[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[k][j] = (k < eh.n && j < ew.n) ? __ldg(src + k * g.Wo + j) : 0.f;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float r = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r = fmaf(ew.c[j], v[k][j], r);
+      s = fmaf(eh.c[k], r, s);
+    }
+    const TapRow tt = ttab[to];
+    while (f_lo < tt.o0) {          // frames below i0(to) are complete (i0 is non-decreasing in `to`)
+      dst[f_lo * plane_i] = acc_lo;
+      acc_lo = acc_hi;
+      acc_hi = 0.f;
+      ++f_lo;
+    }
+    acc_lo = fmaf(tt.l0, s, acc_lo);
+    if (tt.o1 == f_lo) acc_lo = fmaf(tt.l1, s, acc_lo);
+    else acc_hi = fmaf(tt.l1, s, acc_hi);
+  }
+  for (; f_lo < g.Ti; ++f_lo) {
+    dst[f_lo * plane_i] = acc_lo;
+    acc_lo = acc_hi;
+    acc_hi = 0.f;
+  }
+}
+
 // backward: a thread owns (source row hs, column wo) and walks along T_out with register accumulators for the (at
 // most two) source frames currently being fed — no shared-memory read-modify-write, fixed order => deterministic.
 __global__ void resize3d_bwd_tiled_kernel(const float* __restrict__ gy, const TiledGeom tg, float* __restrict__ gx) {
@@ -1527,7 +1622,14 @@ cudaError_t ew_resize3d_bwd(const float* gy, long long NC, int To, int Ho, int W
   const ResizeGeom g = make_geom(Ti, Hi, Wi, To, Ho, Wo, align);
   TiledGeom tg;
   size_t smem;
-  if (NC <= 65535 && plan_bwd_tiles(g, &tg, &smem)) {
+  // register-only adjoint: needs <= 4 contributing outputs per source row / column (floor(2/s) + 1 <= 4), To <= 64
+  const bool few_h = (Ho == 1) || (g.sh > 0.f && static_cast<int>(2.0f / g.sh) + 1 <= 4);
+  const bool few_w = (Wo == 1) || (g.sw > 0.f && static_cast<int>(2.0f / g.sw) + 1 <= 4);
+  if (few_h && few_w && To <= 64 && NC <= 65535 && static_cast<long long>(To) * Ho * Wo < (1LL << 31) &&
+      static_cast<long long>(Ti) * Hi * Wi < (1LL << 31)) {
+    resize3d_bwd_colwalk_kernel<<<dim3((Wi + BW_TX - 1) / BW_TX, (Hi + BW_TY - 1) / BW_TY, static_cast<unsigned>(NC)),
+                                  dim3(BW_TX, BW_TY), 0, st>>>(gy, g, gx);
+  } else if (NC <= 65535 && plan_bwd_tiles(g, &tg, &smem)) {
     static bool ok = false;
     cudaError_t e = rs_allow_smem(resize3d_bwd_tiled_kernel, &ok);
     if (e != cudaSuccess) return e;

@@ -70,17 +70,24 @@ def main():
         h, rows = full_rows(os.path.join(src, rep))
         if not rows:
             continue
-        hdr = hdr or h
-        if rep.startswith("hbm_kernels"):
-            seen = set()
+        if rep.startswith("hbm_kernels"):     # section-based capture: its own columns -> its own file
+            seen, sub = set(), []
             for row in rows:          # one representative launch per kernel
                 key = re.sub(r"\(.*", "", row[0])
                 if key in seen:
                     continue
                 seen.add(key)
-                table.append([rep] + row)
-        else:
-            table.append([rep] + rows[0])
+                sub.append(row)
+            with open(os.path.join(dst, "%s_ncu_hbm_kernels.csv" % tag), "w", newline="") as f:
+                w = csv.writer(f)
+                w.writerow(h)
+                w.writerows(sub)
+            continue
+        if hdr is None:
+            hdr = h
+        if h != hdr:
+            continue
+        table.append([rep] + rows[0])
         if rep == "conv64.ncu-rep":
             d = dict(zip(h, rows[0]))
             rd = float([v for k, v in d.items() if k.startswith("dram__bytes_read.sum")][0])
