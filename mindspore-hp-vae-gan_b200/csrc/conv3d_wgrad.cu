@@ -106,6 +106,10 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const int t = nt % p.T;
         const int t_in = t + dt - 1;
         if (t_in < 0 || t_in >= p.T) continue;
+        // K-steps (16 voxels each) that contain at least one real voxel: the rest of a ragged last segment is TMA
+        // zero fill and contributes nothing (W = 257: 4.06 instead of 5 segments' worth of MMAs)
+        const int w0 = ((tile - nt * per_plane) % p.w_segs) * WG_WS;
+        const int nks = (p.W - w0 >= WG_WS) ? WG_WS / 16 : (p.W - w0 + 15) / 16;
         const uint32_t s = j % WG_STAGES, ph = (j / WG_STAGES) & 1u;
         mbar_wait(&full[s], ph);
         tc_fence_after();
@@ -115,16 +119,20 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         for (int hh = 0; hh < WG_NH; ++hh) {
 #pragma unroll
           for (int ks = 0; ks < WG_WS / 16; ++ks) {
+            if (ks >= nks) break;
             const uint64_t bd = make_smem_desc(gs + (hh * WG_WS + ks * 16) * 128, 16, 1024, 2);
+            // nine taps in five MMAs: any two taps whose A tiles differ by a CONSTANT byte offset stack along M through
+            // the descriptor's leading-dimension offset (second 64-channel block = first + LBO).
+            //   acc 0..2: (dh 0, dw) + (dh 1, dw)   LBO = one x row      acc 3: (dh 2, dw 0) + (dh 2, dw 1)   LBO = one voxel
+            //   acc 4   : (dh 2, dw 2) alone (M = 64)
+            const uint32_t a_row0 = xs + ((hh * WG_XP) + ks * 16) * 128;
 #pragma unroll
-            for (int dw = 0; dw < 3; ++dw) {
-              const uint32_t a0 = xs + ((hh * WG_XP) + ks * 16 + dw) * 128;
-              // dh = 0 and dh = 1 stacked along M: second 64-channel block = same voxels one x row below
-              umma_bf16(tmem_base + (dw * 2) * 64, make_smem_desc(a0, WG_XP * 128, 1024, 2), bd, idesc128, accum);
-              // dh = 2
-              umma_bf16(tmem_base + (dw * 2 + 1) * 64, make_smem_desc(a0 + 2 * WG_XP * 128, WG_XP * 128, 1024, 2),
-                        bd, idesc64, accum);
-            }
+            for (int dw = 0; dw < 3; ++dw)
+              umma_bf16(tmem_base + dw * 64, make_smem_desc(a_row0 + dw * 128, WG_XP * 128, 1024, 2), bd, idesc128,
+                        accum);
+            const uint32_t a_row2 = a_row0 + 2 * WG_XP * 128;
+            umma_bf16(tmem_base + 3 * 64, make_smem_desc(a_row2, 128, 1024, 2), bd, idesc128, accum);
+            umma_bf16(tmem_base + 4 * 64, make_smem_desc(a_row2 + 2 * 128, WG_XP * 128, 1024, 2), bd, idesc64, accum);
             accum = 1;
           }
         }
@@ -147,42 +155,45 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     const int row = quad * 32 + lane;   // TMEM lane
     float* pg = p.partial + static_cast<size_t>(g) * 27 * 4096;
 #pragma unroll 1
-    for (int dw = 0; dw < 3; ++dw) {
-#pragma unroll 1
-      for (int which = 0; which < 2; ++which) {
-        // which 0: M=128 tile: lanes 0..63 -> dh 0, lanes 64..127 -> dh 1 ; which 1: M=64 tile: dh 2, lane (i/16)*32+i%16
-        int dh, ci;
-        bool valid = true;
-        if (which == 0) {
-          dh = row >> 6;
-          ci = row & 63;
-        } else {
-          dh = 2;
-          valid = (row & 31) < 16;
-          ci = (row >> 5) * 16 + (row & 15);
-        }
-        const int tap = dt * 9 + dh * 3 + dw;
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (dw * 2 + which) * 64;
-        uint32_t r0[32], r1[32];
-        if (!empty_cta) {
-          tmem_ld32(taddr, r0);
-          tmem_ld32(taddr + 32, r1);
-          tmem_ld_wait();
-        } else {
+    for (int a = 0; a < 5; ++a) {
+      // accumulator a -> (dh, dw) of this TMEM lane (see the MMA issue loop)
+      int dh, dw, ci;
+      bool valid = true;
+      if (a < 3) {
+        dh = row >> 6;
+        dw = a;
+        ci = row & 63;
+      } else if (a == 3) {
+        dh = 2;
+        dw = row >> 6;
+        ci = row & 63;
+      } else {   // M = 64 tile: row i sits in lane (i/16)*32 + i%16
+        dh = 2;
+        dw = 2;
+        valid = (row & 31) < 16;
+        ci = (row >> 5) * 16 + (row & 15);
+      }
+      const int tap = dt * 9 + dh * 3 + dw;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + a * 64;
+      uint32_t r0[32], r1[32];
+      if (!empty_cta) {
+        tmem_ld32(taddr, r0);
+        tmem_ld32(taddr + 32, r1);
+        tmem_ld_wait();
+      } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r0[i] = r1[i] = 0u;
-        }
-        if (valid) {
-          float4* dst = reinterpret_cast<float4*>(pg + (static_cast<size_t>(tap) * 64 + ci) * 64);
+        for (int i = 0; i < 32; ++i) r0[i] = r1[i] = 0u;
+      }
+      if (valid) {
+        float4* dst = reinterpret_cast<float4*>(pg + (static_cast<size_t>(tap) * 64 + ci) * 64);
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            dst[c] = make_float4(__uint_as_float(r0[4 * c]), __uint_as_float(r0[4 * c + 1]),
-                                 __uint_as_float(r0[4 * c + 2]), __uint_as_float(r0[4 * c + 3]));
+        for (int c = 0; c < 8; ++c)
+          dst[c] = make_float4(__uint_as_float(r0[4 * c]), __uint_as_float(r0[4 * c + 1]),
+                               __uint_as_float(r0[4 * c + 2]), __uint_as_float(r0[4 * c + 3]));
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            dst[8 + c] = make_float4(__uint_as_float(r1[4 * c]), __uint_as_float(r1[4 * c + 1]),
-                                     __uint_as_float(r1[4 * c + 2]), __uint_as_float(r1[4 * c + 3]));
-        }
+        for (int c = 0; c < 8; ++c)
+          dst[8 + c] = make_float4(__uint_as_float(r1[4 * c]), __uint_as_float(r1[4 * c + 1]),
+                                   __uint_as_float(r1[4 * c + 2]), __uint_as_float(r1[4 * c + 3]));
       }
     }
   }

@@ -445,22 +445,24 @@ constexpr int CW_MAX_TI = 8;
 constexpr int CW_THREADS = 256;
 
 template <int C>
-__device__ __forceinline__ void colwalk_load(const float* __restrict__ xs, long long spi, const ResizeGeom& g,
-                                             const Tap& th, const Tap& tw, float (&hv)[C][CW_MAX_TI + 1]) {
-  const int o00 = th.i0 * g.Wi + tw.i0, o01 = th.i0 * g.Wi + tw.i1;
-  const int o10 = th.i1 * g.Wi + tw.i0, o11 = th.i1 * g.Wi + tw.i1;
-  const int fsz = g.Hi * g.Wi;
+__device__ __forceinline__ void colwalk_load(const float* __restrict__ xs /* block-uniform slice base */, unsigned spi,
+                                             const ResizeGeom& g, const Tap& th, const Tap& tw,
+                                             float (&hv)[C][CW_MAX_TI + 1]) {
+  // 32-bit element indices relative to the uniform base: one integer op per load instead of 64-bit pointer math
+  const unsigned o00 = th.i0 * g.Wi + tw.i0, o01 = th.i0 * g.Wi + tw.i1;
+  const unsigned o10 = th.i1 * g.Wi + tw.i0, o11 = th.i1 * g.Wi + tw.i1;
+  const unsigned fsz = g.Hi * g.Wi;
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     float v[CW_MAX_TI][4];
 #pragma unroll
     for (int f = 0; f < CW_MAX_TI; ++f) {
       if (f < g.Ti) {
-        const float* p = xs + c * spi + f * fsz;
-        v[f][0] = __ldg(p + o00);
-        v[f][1] = __ldg(p + o01);
-        v[f][2] = __ldg(p + o10);
-        v[f][3] = __ldg(p + o11);
+        const unsigned b = c * spi + f * fsz;
+        v[f][0] = __ldg(xs + (b + o00));
+        v[f][1] = __ldg(xs + (b + o01));
+        v[f][2] = __ldg(xs + (b + o10));
+        v[f][3] = __ldg(xs + (b + o11));
       }
     }
 #pragma unroll
@@ -489,11 +491,12 @@ resize3d_fwd_colwalk_kernel(const float* __restrict__ x, const ResizeGeom g, flo
   const int ho = col / g.Wo, wo = col - ho * g.Wo;
   const long long nc = blockIdx.y;
   const Tap th = linear_tap(ho, g.Hi, g.sh, g.align), tw = linear_tap(wo, g.Wi, g.sw, g.align);
-  const long long spi = static_cast<long long>(g.Ti) * g.Hi * g.Wi;
+  const unsigned spi = g.Ti * g.Hi * g.Wi;
   float hv[1][CW_MAX_TI + 1];
   colwalk_load<1>(x + nc * spi, spi, g, th, tw, hv);
-  const int plane = g.Ho * g.Wo;
-  float* dst = y + nc * g.To * plane + col;
+  const unsigned plane = g.Ho * g.Wo;
+  float* __restrict__ ys = y + nc * g.To * plane;     // block-uniform base
+  unsigned oidx = col;
   int to = 0;
 #pragma unroll
   for (int f = 0; f < CW_MAX_TI; ++f) {
@@ -502,8 +505,8 @@ resize3d_fwd_colwalk_kernel(const float* __restrict__ x, const ResizeGeom g, flo
         const TapRow tt = ttab[to];
         if (tt.o0 != f) break;
         const float hi = (tt.o1 == f) ? hv[0][f] : hv[0][f + 1];
-        *dst = lerp_rn(tt.l0, hv[0][f], tt.l1, hi);
-        dst += plane;
+        ys[oidx] = lerp_rn(tt.l0, hv[0][f], tt.l1, hi);
+        oidx += plane;
         ++to;
       }
     }
@@ -528,11 +531,11 @@ upsample_noise_pack_colwalk_kernel(const float* __restrict__ x, const ResizeGeom
   const int ho = col / g.Wo, wo = col - ho * g.Wo;
   const long long n = blockIdx.y;
   const Tap th = linear_tap(ho, g.Hi, g.sh, g.align), tw = linear_tap(wo, g.Wi, g.sw, g.align);
-  const long long spi = static_cast<long long>(g.Ti) * g.Hi * g.Wi;
+  const unsigned spi = g.Ti * g.Hi * g.Wi;
   const int plane = g.Ho * g.Wo;
   const long long spo = static_cast<long long>(g.To) * plane;
   float hv[C][CW_MAX_TI + 1];
-  colwalk_load<C>(x + n * C * spi, spi, g, th, tw, hv);
+  colwalk_load<C>(x + n * C * static_cast<long long>(spi), spi, g, th, tw, hv);
   const unsigned long long sample = sample_base + static_cast<unsigned long long>(n);
   long long sidx = col;               // spatial index inside the sample
   int to = 0;
