@@ -36,6 +36,7 @@ extern "C" {
 #define HPVG_ACT_NONE 0
 #define HPVG_ACT_LRELU 1 /* LeakyReLU(0.2): mindspore.nn.LeakyReLU default, networks_3d.py:20 */
 #define HPVG_ACT_TANH 2
+#define HPVG_ACT_LRELU_MASK 3 /* y = v * LeakyReLU'(mask): LeakyReLU backward fused into a data-gradient conv */
 #define HPVG_OUT_BF16_CL 0
 #define HPVG_OUT_F32_NCDHW 1
 #define HPVG_OUT_F32_RAW 2
@@ -95,10 +96,14 @@ int hpvg_conv_pack_weights(const float* d_w, int w_cout, int w_cin, int kt, int 
  *           HPVG_OUT_F32_NCDHW: optional fp32 ncdhw residual (tanh(block(x)+up), networks_3d.py:450)
  *  d_stats  optional fp64 [2][64] (HPVG_OUT_BF16_CL, 64 output channels): += per-channel sum / sum of squares of the
  *           stored output — the batch statistics of a following training-mode BatchNorm3d (networks_3d.py:52),
- *           fused into the conv epilogue.  The caller zeroes it.                                                  */
+ *           fused into the conv epilogue.  The caller zeroes it.
+ *  d_mask   HPVG_ACT_LRELU_MASK only: bf16 cl tensor of the same voxels (64 channels at d_mask, mask_pitch channels
+ *           per voxel) holding a stored LeakyReLU activation a; the epilogue applies v * (a > 0 ? 1 : 0.2), i.e. the
+ *           backward of that LeakyReLU, so the data-gradient conv emits the next layer's pre-activation gradient.    */
 int hpvg_conv_cl(int mode, int N, int T, int H, int W, const void* d_in, int in_pitch, const void* d_wimg,
                  const float* d_scale, const float* d_shift, int act, int out_mode, void* d_out, int out_pitch,
-                 int out_coff, int cout_real, const float* d_addend, double* d_stats, void* stream);
+                 int out_coff, int cout_real, const float* d_addend, double* d_stats, const void* d_mask,
+                 int mask_pitch, void* stream);
 
 /* ---------------------------------------------------------------- linear resize
  * Replaces UpsampleTrilinear3D(output_size, align_corners) (src/tools/trilinear.py:171-254, called from

@@ -209,7 +209,8 @@ int hpvg_conv_pack_weights(const float* w, int w_cout, int w_cin, int kt, int mo
 
 int hpvg_conv_cl(int mode, int N, int T, int H, int W, const void* in, int in_pitch, const void* wimg,
                  const float* scale, const float* shift, int act, int out_mode, void* out, int out_pitch,
-                 int out_coff, int cout_real, const float* addend, double* stats, void* st) {
+                 int out_coff, int cout_real, const float* addend, double* stats, const void* mask, int mask_pitch,
+                 void* st) {
   if (N <= 0 || T <= 0 || H <= 0 || W <= 0) return HPVG_OK;  // empty input: nothing to do
   if (!in || !wimg || !scale || !shift || !out) return fail(HPVG_E_ARG, "conv_cl: null pointer");
   if (out_mode == HPVG_OUT_BF16_CL && ((out_pitch & 7) || (out_coff & 7)))
@@ -226,6 +227,8 @@ int hpvg_conv_cl(int mode, int N, int T, int H, int W, const void* in, int in_pi
   L.out = out; L.out_pitch = out_pitch; L.out_coff = out_coff; L.cout_real = cout_real;
   L.addend = addend;
   L.stats = stats;
+  L.mask = mask;
+  L.mask_pitch = mask_pitch;
   L.max_pairs = g_sm_count / 2;
   const char* e = hpvg::conv3d_umma_launch(L, S(st));
   if (e) return fail(HPVG_E_CUDA, std::string("conv_cl: ") + e);
@@ -539,7 +542,7 @@ int HpvgConv3dBiasLRelu(int nparam, void** params, int* ndims, int64_t** shapes,
                                        64, wimg, stream);
   if (!rc) rc = hpvg_affine_from_bias(static_cast<const float*>(params[2]), nullptr, 64, scale, scale + 64, stream);
   if (!rc) rc = hpvg_conv_cl(HPVG_CONV_64_64, N, T, H, W, xcl, 64, wimg, scale, scale + 64, HPVG_ACT_LRELU,
-                             HPVG_OUT_BF16_CL, ycl, 64, 0, 64, nullptr, nullptr, stream);
+                             HPVG_OUT_BF16_CL, ycl, 64, 0, 64, nullptr, nullptr, nullptr, 0, stream);
   if (!rc) rc = hpvg_unpack_cl(ycl, N, 64, T, H, W, 64, 0, static_cast<float*>(params[3]), stream);
   cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
   cudaFree(xcl); cudaFree(ycl); cudaFree(wimg); cudaFree(scale);

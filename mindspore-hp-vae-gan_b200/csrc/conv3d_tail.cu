@@ -259,6 +259,7 @@ const char* conv3d_tail_launch(const ConvLaunch& L, int sm_count, cudaStream_t s
   if (L.in_pitch < 64 || (L.in_pitch & 7)) return "input pitch must be a multiple of 8 channels and >= 64";
   if ((reinterpret_cast<uintptr_t>(L.in) & 15) != 0) return "input not 16-byte aligned";
   if (L.out_mode != CONV_OUT_F32_NCDHW || L.cout_real < 1 || L.cout_real > 3) return "tail conv: 1..3 fp32 NCDHW outputs";
+  if (L.act == CONV_ACT_LRELU_MASK) return "tail conv: LRELU_MASK is a bf16-output epilogue";
   CUtensorMap tmap;
   cuuint64_t gd[5] = {64, static_cast<cuuint64_t>(L.W), static_cast<cuuint64_t>(L.H), static_cast<cuuint64_t>(L.T),
                       static_cast<cuuint64_t>(L.N)};

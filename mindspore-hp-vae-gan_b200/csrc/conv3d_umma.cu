@@ -97,7 +97,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 template <int ACT, bool ADD, bool KEEP>
 __device__ __forceinline__ void epilogue_bf16_row(uint32_t (&r0)[32], uint32_t (&r1)[32], const float* scale_sm,
                                                   const float* shift_sm, const float* __restrict__ add,
-                                                  __nv_bfloat16* __restrict__ dst) {
+                                                  __nv_bfloat16* __restrict__ dst,
+                                                  const __nv_bfloat16* __restrict__ mask = nullptr) {
   const float4* sc4 = reinterpret_cast<const float4*>(scale_sm);
   const float4* sh4 = reinterpret_cast<const float4*>(shift_sm);
 #pragma unroll
@@ -115,6 +116,16 @@ __device__ __forceinline__ void epilogue_bf16_row(uint32_t (&r0)[32], uint32_t (
         ad[0] = a0.x; ad[1] = a0.y; ad[2] = a0.z; ad[3] = a0.w;
         ad[4] = a1.x; ad[5] = a1.y; ad[6] = a1.z; ad[7] = a1.w;
       }
+      float mk[8];
+      if constexpr (ACT == CONV_ACT_LRELU_MASK) {   // LeakyReLU'(stored activation): sign(activation) == sign(pre-act)
+        const uint4 m4 = *reinterpret_cast<const uint4*>(mask + cb);
+        const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+          mk[2 * e2] = __uint_as_float(mw[e2] << 16);
+          mk[2 * e2 + 1] = __uint_as_float(mw[e2] & 0xFFFF0000u);
+        }
+      }
       float v[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -123,6 +134,7 @@ __device__ __forceinline__ void epilogue_bf16_row(uint32_t (&r0)[32], uint32_t (
         a = fmaf(a, sc[e], sh[e]);
         if constexpr (ACT == CONV_ACT_LRELU) a = fmaxf(a, 0.2f * a);   // == a > 0 ? a : 0.2a
         if constexpr (ACT == CONV_ACT_TANH) a = tanhf(a);
+        if constexpr (ACT == CONV_ACT_LRELU_MASK) a = mk[e] > 0.f ? a : 0.2f * a;
         v[e] = a;
       }
       uint4 pk;
@@ -146,7 +158,13 @@ __device__ __forceinline__ void epilogue_bf16_row(uint32_t (&r0)[32], uint32_t (
 template <bool KEEP>
 __device__ __forceinline__ void epilogue_bf16_dispatch(int act, uint32_t (&r0)[32], uint32_t (&r1)[32],
                                                        const float* scale_sm, const float* shift_sm,
-                                                       const float* __restrict__ add, __nv_bfloat16* __restrict__ dst) {
+                                                       const float* __restrict__ add, __nv_bfloat16* __restrict__ dst,
+                                                       const __nv_bfloat16* __restrict__ mask) {
+  if (act == CONV_ACT_LRELU_MASK) {
+    if (add) epilogue_bf16_row<CONV_ACT_LRELU_MASK, true, KEEP>(r0, r1, scale_sm, shift_sm, add, dst, mask);
+    else epilogue_bf16_row<CONV_ACT_LRELU_MASK, false, KEEP>(r0, r1, scale_sm, shift_sm, add, dst, mask);
+    return;
+  }
   if (add) {   // split-Cin accumulation (128 -> 64 layers): rare
     if (act == CONV_ACT_LRELU) epilogue_bf16_row<CONV_ACT_LRELU, true, KEEP>(r0, r1, scale_sm, shift_sm, add, dst);
     else if (act == CONV_ACT_TANH) epilogue_bf16_row<CONV_ACT_TANH, true, KEEP>(r0, r1, scale_sm, shift_sm, add, dst);
@@ -359,7 +377,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
               } else {
                 const float* add = p.addend ? p.addend + vox * 64 : nullptr;
                 __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + vox * p.out_pitch + p.out_coff;
-                epilogue_bf16_dispatch<false>(p.act, r0, r1, scale_sm, shift_sm, add, dst);
+                const __nv_bfloat16* mk =
+                    p.mask ? static_cast<const __nv_bfloat16*>(p.mask) + vox * p.mask_pitch : nullptr;
+                epilogue_bf16_dispatch<false>(p.act, r0, r1, scale_sm, shift_sm, add, dst, mk);
               }
             }
           } else {
@@ -367,7 +387,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
             if (inb) {
               const float* add = p.addend ? p.addend + vox * 64 : nullptr;
               __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + vox * p.out_pitch + p.out_coff;
-              epilogue_bf16_dispatch<true>(p.act, r0, r1, scale_sm, shift_sm, add, dst);
+              const __nv_bfloat16* mk =
+                  p.mask ? static_cast<const __nv_bfloat16*>(p.mask) + vox * p.mask_pitch : nullptr;
+              epilogue_bf16_dispatch<true>(p.act, r0, r1, scale_sm, shift_sm, add, dst, mk);
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) r0[i] = r1[i] = 0u;
@@ -529,6 +551,9 @@ const char* conv3d_umma_launch(const ConvLaunch& L, cudaStream_t stream) {
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed";
 
+  if (L.act == CONV_ACT_LRELU_MASK && (!L.mask || L.out_mode != CONV_OUT_BF16_NDHWC || (L.mask_pitch & 7) ||
+                                       (reinterpret_cast<uintptr_t>(L.mask) & 15)))
+    return "LRELU_MASK needs a 16-byte aligned bf16 mask tensor and the bf16 output mode";
   ConvParams prm;
   prm.N = L.N;
   prm.T = L.T;
@@ -549,6 +574,8 @@ const char* conv3d_umma_launch(const ConvLaunch& L, cudaStream_t stream) {
   prm.cout_real = L.cout_real;
   prm.addend = L.addend;
   prm.stats = L.stats;
+  prm.mask = L.mask;
+  prm.mask_pitch = L.mask_pitch;
   prm.in_merged = merged ? 1 : 0;
   int n_pairs = prm.n_units < L.max_pairs ? prm.n_units : L.max_pairs;
   if (n_pairs < 1) return nullptr;

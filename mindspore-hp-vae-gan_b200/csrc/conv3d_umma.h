@@ -6,7 +6,7 @@
 namespace hpvg {
 
 enum ConvMode { CONV_MODE_64_64 = 0, CONV_MODE_64_16 = 1, CONV_MODE_8_64 = 2, CONV_MODE_64_T = 3 };
-enum ConvAct { CONV_ACT_NONE = 0, CONV_ACT_LRELU = 1, CONV_ACT_TANH = 2 };
+enum ConvAct { CONV_ACT_NONE = 0, CONV_ACT_LRELU = 1, CONV_ACT_TANH = 2, CONV_ACT_LRELU_MASK = 3 };
 enum ConvOut { CONV_OUT_BF16_NDHWC = 0, CONV_OUT_F32_NCDHW = 1, CONV_OUT_F32_RAW = 2 };
 
 // device-side parameter block (passed as __grid_constant__)
@@ -24,6 +24,8 @@ struct ConvParams {
   int cout_real;         // CONV_OUT_F32_NCDHW: number of real output channels (<= 4)
   const float* addend;   // bf16 out: fp32 [V][64] partial sums added before scale/shift (split-Cin);
                          // NCDHW out: fp32 NCDHW residual added after scale/shift, before the activation
+  const void* mask;      // CONV_ACT_LRELU_MASK: bf16 cl tensor (same voxels, 64 channels at `mask`, mask_pitch per voxel)
+  int mask_pitch;        //   y = v * LeakyReLU'(mask): the backward of a LeakyReLU fused into the data-gradient conv
   int in_merged;         // head variant: the tensor map has (C, W) merged (densely packed 8-channel input)
   double* stats;         // bf16 out, Cout 64: optional [2][64] fp64 accumulators (+= sum y, sum y^2 over all voxels of
                          // the stored output): the training-mode BatchNorm statistics, fused into the epilogue
@@ -43,6 +45,8 @@ struct ConvLaunch {
   int out_pitch, out_coff, cout_real;
   const float* addend;
   double* stats;
+  const void* mask;
+  int mask_pitch;
   int max_pairs;         // CTA pairs to launch (<= 74 on a 148-SM B200)
 };
 

@@ -10,7 +10,7 @@ from ._lib import HpvgError, check, lib
 from .runtime import BF16, F32, F64, I32, Tensor, _s
 
 CONV_64_64, CONV_64_16, CONV_8_64, CONV_64_3 = 0, 1, 2, 3
-ACT_NONE, ACT_LRELU, ACT_TANH = 0, 1, 2
+ACT_NONE, ACT_LRELU, ACT_TANH, ACT_LRELU_MASK = 0, 1, 2, 3
 OUT_BF16_CL, OUT_F32_NCDHW, OUT_F32_RAW = 0, 1, 2
 BN_EPS = 1e-5        # mindspore.nn.BatchNorm3d default
 BN_MOMENTUM = 0.9    # mindspore.nn.BatchNorm3d default (moving = 0.9*moving + 0.1*batch)
@@ -101,9 +101,10 @@ def pack_weights(w, mode, transpose_flip=False, cout_off=0, cout=None, cin_off=0
 
 
 def conv_cl(mode, x_cl, wimg, scale, shift, act=ACT_NONE, out_mode=OUT_BF16_CL, out=None, out_pitch=64, out_coff=0,
-            cout_real=64, addend=None, in_coff=0, stats=None, stream=None):
+            cout_real=64, addend=None, in_coff=0, stats=None, mask=None, mask_coff=0, stream=None):
     """Raw kernel call.  x_cl: bf16 (N,T,H,W,in_pitch); reads channels [in_coff, in_coff+64|8).
-    stats: optional fp64 (2,64) tensor accumulating the per-channel sum / sum of squares of the stored output."""
+    stats: optional fp64 (2,64) tensor accumulating the per-channel sum / sum of squares of the stored output.
+    mask (act=ACT_LRELU_MASK): bf16 cl tensor of a stored LeakyReLU activation; output = v * LeakyReLU'(mask)."""
     N, T, H, W, in_pitch = x_cl.shape
     if out is None:
         if out_mode == OUT_BF16_CL:
@@ -118,7 +119,9 @@ def conv_cl(mode, x_cl, wimg, scale, shift, act=ACT_NONE, out_mode=OUT_BF16_CL, 
         e0, e1 = rt.Event(), rt.Event()
         e0.record(stream)
     check(lib.hpvg_conv_cl(mode, N, T, H, W, in_ptr, in_pitch, _p(wimg), _p(scale), _p(shift), act, out_mode, _p(out),
-                           out_pitch, out_coff, cout_real, _p(addend), _p(stats), _s(stream)), "conv_cl")
+                           out_pitch, out_coff, cout_real, _p(addend), _p(stats),
+                           None if mask is None else ctypes.c_void_p(mask.ptr + 2 * mask_coff),
+                           0 if mask is None else mask.shape[-1], _s(stream)), "conv_cl")
     if timed:
         e1.record(stream)
         _prof["items"].append((N * T * H * W, e0, e1) if _prof["mode"] is not None else ((mode, N * T * H * W), e0, e1))
@@ -152,7 +155,7 @@ def _sc(aff):
 
 
 def conv3d_cl_any(x_cl, w, aff, act, cin, cout, out_mode=OUT_BF16_CL, residual=None, out=None, wimgs=None,
-                  transpose_flip=False, stats=None, stream=None):
+                  transpose_flip=False, stats=None, mask=None, stream=None):
     """Convolution for every channel combination on the hot path, composed from the kernel variants:
     Cin in {<=8, 64, 128}, Cout in {<=4, 64, 128}.  aff: (2,64*ceil(cout/64)) epilogue vectors.
     Returns bf16 cl (cout 64/128) or fp32 ncdhw (cout <= 4)."""
@@ -186,7 +189,7 @@ def conv3d_cl_any(x_cl, w, aff, act, cin, cout, out_mode=OUT_BF16_CL, residual=N
                 partial = conv_cl(mode, x_cl, wi, s, b, ACT_NONE, OUT_F32_RAW, in_coff=ib * 64, stream=stream)
             else:
                 conv_cl(mode, x_cl, wi, s, b, act, OUT_BF16_CL, out=out, out_pitch=cout, out_coff=ob * 64,
-                        addend=partial, in_coff=ib * 64, stats=stats, stream=stream)
+                        addend=partial, in_coff=ib * 64, stats=stats, mask=mask, mask_coff=ob * 64, stream=stream)
     return out
 
 

@@ -12,10 +12,16 @@ import numpy as np
 
 from . import ops
 from .networks_3d import BnStatsSlab, ConvLayer, Workspace, as5d
-from .ops import ACT_LRELU, ACT_NONE, ACT_TANH, CONV_64_16, CONV_64_64, CONV_8_64, OUT_BF16_CL, OUT_F32_NCDHW, OUT_F32_RAW
+from .ops import ACT_LRELU, ACT_LRELU_MASK, ACT_NONE, ACT_TANH, CONV_64_16, CONV_64_64, CONV_8_64, OUT_BF16_CL, OUT_F32_NCDHW, OUT_F32_RAW
 from .runtime import BF16, F32, U64, Graph, HpvgError, Tensor, from_numpy
 from .utils import images as uimg
 
+import os as _os
+# The LeakyReLU backward CAN be fused into the producing data-gradient conv (HPVG_ACT_LRELU_MASK), but measured on the
+# same B200 (A/B, finest scale, batch 1) the fused iteration is 0.6 ms SLOWER: at batch 1 the conv is paced by its
+# epilogue, and the extra 128 B/voxel mask load there costs more than the separate pass, which streams at 97 % of the
+# HBM copy bandwidth.  So the fusion is opt-in.
+_MASK_FUSION = bool(_os.environ.get("HPVG_MASK_FUSION"))
 NON_TRAINABLE = ("weight_u", "weight_v", "moving_mean", "moving_variance")
 
 
@@ -185,9 +191,12 @@ def _dgrad_wimgs(layer, stream=None):
 
 
 def conv_backward(layer, ctx, gy_cl, grads, ws, key, need_dx=True, want_dw=True, inv_sigma_aff=None, stream=None,
-                  dw_target=None):
+                  dw_target=None, mask_input=False, dx_out=None):
     """Backward of the convolution of `layer` given gy (bf16 cl, Cout channels [zero padded to 64 for tails]).
-    Accumulates dW (into dw_target or grads) and db; returns dx: bf16 cl (Cin >= 64) or fp32 ncdhw (Cin <= 4)."""
+    Accumulates dW (into dw_target or grads) and db; returns dx: bf16 cl (Cin >= 64) or fp32 ncdhw (Cin <= 4).
+    mask_input: the conv's input x is the stored output of a LeakyReLU (no BatchNorm in between): the data-gradient
+    kernel multiplies by LeakyReLU'(x) in its epilogue, so the result is already the gradient wrt that layer's
+    PRE-activation (saves a separate elementwise pass over a finest-scale activation tensor)."""
     x_cl = ctx["x"]
     N, T, H, W, xp = x_cl.shape
     cin, cout = layer.cin, layer.cout
@@ -208,10 +217,16 @@ def conv_backward(layer, ctx, gy_cl, grads, ws, key, need_dx=True, want_dw=True,
         out = ws.get(key + ".dx3", (N, cin, T, H, W), F32)
         return ops.conv_cl(ops.tail_mode(cin), gy_cl, imgs[0], sc, sh, ACT_NONE, OUT_F32_NCDHW, out=out, cout_real=cin,
                            stream=stream)
-    dx = ws.get(key + ".dx", (N, T, H, W, cin), BF16)
+    dx = dx_out if dx_out is not None else ws.get(key + ".dx", (N, T, H, W, cin), BF16)
+    if mask_input and not _MASK_FUSION:     # default: data gradient, then the (bandwidth-bound) lrelu backward pass
+        raw = ws.get(key + ".dxraw", (N, T, H, W, cin), BF16)
+        conv_backward(layer, ctx, gy_cl, grads, ws, key, True, False, inv_sigma_aff, stream, None, False, raw)
+        return ops.lrelu_bwd_cl(raw, x_cl, out=dx, stream=stream)
+    act = ACT_LRELU_MASK if mask_input else ACT_NONE
+    mask = x_cl if mask_input else None
     if cout <= 4:
-        return ops.conv_cl(CONV_8_64, gy_cl, imgs[0], sc, sh, ACT_NONE, OUT_BF16_CL, out=dx, out_pitch=cin,
-                           stream=stream)
+        return ops.conv_cl(CONV_8_64, gy_cl, imgs[0], sc, sh, act, OUT_BF16_CL, out=dx, out_pitch=cin,
+                           mask=mask, stream=stream)
     k = 0
     for ob in range(cin // 64):
         partial = None
@@ -221,14 +236,18 @@ def conv_backward(layer, ctx, gy_cl, grads, ws, key, need_dx=True, want_dw=True,
                 partial = ops.conv_cl(CONV_64_64, gy_cl, imgs[k], sc, sh, ACT_NONE, OUT_F32_RAW, in_coff=ib * 64,
                                       out=ws.get(key + ".dxp", (N, T, H, W, 64), F32), stream=stream)
             else:
-                ops.conv_cl(CONV_64_64, gy_cl, imgs[k], sc, sh, ACT_NONE, OUT_BF16_CL, out=dx, out_pitch=cin,
-                            out_coff=ob * 64, addend=partial, in_coff=ib * 64, stream=stream)
+                ops.conv_cl(CONV_64_64, gy_cl, imgs[k], sc, sh, act, OUT_BF16_CL, out=dx, out_pitch=cin,
+                            out_coff=ob * 64, addend=partial, in_coff=ib * 64, mask=mask, mask_coff=ob * 64,
+                            stream=stream)
             k += 1
     return dx
 
 
-def layer_backward(layer, ctx, ga_cl, grads, ws, key, need_dx=True, trainable=True, stream=None):
-    """Backward of conv -> [BN] -> LeakyReLU given ga (grad wrt the layer output, bf16 cl)."""
+def layer_backward(layer, ctx, ga_cl, grads, ws, key, need_dx=True, trainable=True, stream=None, ga_masked=False,
+                   mask_input=False):
+    """Backward of conv -> [BN] -> LeakyReLU given ga (grad wrt the layer output, bf16 cl).
+    ga_masked: ga is already the gradient wrt this layer's pre-activation (the upper layer's data-gradient conv applied
+    LeakyReLU' in its epilogue); mask_input: ask OUR data-gradient conv to do the same for the layer below."""
     if layer.bn:
         dg = grads.of(layer.p["gamma"]) if trainable else None
         db = grads.of(layer.p["beta"]) if trainable else None
@@ -238,7 +257,7 @@ def layer_backward(layer, ctx, ga_cl, grads, ws, key, need_dx=True, trainable=Tr
             ops.colsum_cl(gy, grads.of(layer.p["bias"]), accumulate=True, stream=stream)
         return conv_backward(layer, ctx, gy, grads, ws, key, need_dx, trainable, stream=stream)
     gz = ga_cl
-    if layer.act == ACT_LRELU:
+    if layer.act == ACT_LRELU and not ga_masked:
         gz = ops.lrelu_bwd_cl(ga_cl, ctx["a"], out=ws.get(key + ".gz", ga_cl.shape, BF16), stream=stream)
     if trainable:
         if layer.cout == 64:
@@ -248,12 +267,12 @@ def layer_backward(layer, ctx, ga_cl, grads, ws, key, need_dx=True, trainable=Tr
     if layer.sn:
         ghat = ws.get(key + ".ghat", layer.p["weight"].shape, F32).zero_(stream)
         dx = conv_backward(layer, ctx, gz, grads, ws, key, need_dx, trainable, inv_sigma_aff=ctx["aff"],
-                           stream=stream, dw_target=ghat)
+                           stream=stream, dw_target=ghat, mask_input=mask_input)
         if trainable:
             ops.sn_grad(ghat, layer.p["weight"], ctx["u"], ctx["v"], ctx["sigma"], grads.of(layer.p["weight"]),
                         accumulate=True, stream=stream)
         return dx
-    return conv_backward(layer, ctx, gz, grads, ws, key, need_dx, trainable, stream=stream)
+    return conv_backward(layer, ctx, gz, grads, ws, key, need_dx, trainable, stream=stream, mask_input=mask_input)
 
 
 def _colsum_wide(g_cl, out, stream=None):
@@ -548,10 +567,13 @@ class DWithLoss:
         go = ops.fill(ws.get(tag + ".go", out.shape, F32), coef, stream)
         ops.channel_sum(go, g.of(D.tail.p["bias"]), accumulate=True, stream=stream)
         gy = ops.pack_cl(go, c_pitch=64, zero_to=64, out=ws.get(tag + ".gyt", (N, T, H, W, 64), BF16), stream=stream)
-        ga = conv_backward(D.tail, ctxs[-1], gy, g, ws, tag + ".t", True, True, stream=stream)
+        # every D layer is SN-conv + LeakyReLU (no BatchNorm): each data-gradient conv applies the LeakyReLU' of the
+        # layer below in its epilogue, so no separate lrelu-backward pass runs
+        ga = conv_backward(D.tail, ctxs[-1], gy, g, ws, tag + ".t", True, True, stream=stream, mask_input=True)
         layers = self._layers()
         for j in range(len(layers) - 1, -1, -1):
-            ga = layer_backward(layers[j], ctxs[j], ga, g, ws, "%s.l%d" % (tag, j), j > 0, True, stream)
+            ga = layer_backward(layers[j], ctxs[j], ga, g, ws, "%s.l%d" % (tag, j), j > 0, True, stream,
+                                ga_masked=True, mask_input=j > 0)
 
     def _gradient_penalty(self, ctxs, tag, stream):
         """calc_gradient_penalty (losses.py:47-52) and its gradient wrt D's weights (second order)."""
@@ -563,13 +585,17 @@ class DWithLoss:
         ones = ops.fill(ws.get(tag + ".ones", out.shape, F32), 1.0, stream)
         d_out = ops.pack_cl(ones, c_pitch=64, zero_to=64, out=ws.get(tag + ".dout", (N, T, H, W, 64), BF16),
                             stream=stream)
-        ga = conv_backward(D.tail, ctxs[-1], d_out, g, ws, tag + ".gt", True, False, stream=stream)
-        deltas = [None] * len(layers)
-        for j in range(len(layers) - 1, -1, -1):
-            deltas[j] = ops.lrelu_bwd_cl(ga, ctxs[j]["a"], out=ws.get("%s.delta%d" % (tag, j), ga.shape, BF16),
-                                         stream=stream)
+        # LeakyReLU' of the layer below is applied in each data-gradient conv's epilogue: its output IS delta[j-1]
+        nl = len(layers)
+        dshape = ctxs[-1]["x"].shape
+        deltas = [ws.get("%s.delta%d" % (tag, j), dshape, BF16) for j in range(nl)]
+        conv_backward(D.tail, ctxs[-1], d_out, g, ws, tag + ".gt", True, False, stream=stream, mask_input=True,
+                      dx_out=deltas[nl - 1])
+        ga = None
+        for j in range(nl - 1, -1, -1):
             ga = conv_backward(layers[j], ctxs[j], deltas[j], g, ws, "%s.g%d" % (tag, j), True, False,
-                               inv_sigma_aff=ctxs[j]["aff"], stream=stream)
+                               inv_sigma_aff=ctxs[j]["aff"], stream=stream, mask_input=j > 0,
+                               dx_out=deltas[j - 1] if j > 0 else None)
         grad_x = ga                                                   # fp32 ncdhw (N, 3, T, H, W)
         Gx, gp = ops.gp_grad(grad_x, self.lambda_grad, Gout=ws.get(tag + ".G", grad_x.shape, F32),
                              gp=self.terms.slot(1.0), stream=stream)
@@ -588,10 +614,17 @@ class DWithLoss:
                         g.of(layer.p["weight"]), accumulate=True, stream=stream)
             # eta = conv(xi; W/sigma) (no bias, no activation); xi_next = eta * LeakyReLU'(a_j)
             layer._prepare_wimgs(stream)
-            eta = ops.conv3d_cl_any(xi, layer.p["weight"], _scale_only(ctxs[j]["aff"], zero_shift, ws, tag, j, stream),
-                                    ACT_NONE, layer.cin, 64, out=ws.get("%s.eta%d" % (tag, j), deltas[j].shape, BF16),
-                                    wimgs=layer._wimgs, stream=stream)
-            xi = ops.lrelu_bwd_cl(eta, ctxs[j]["a"], out=ws.get("%s.xi%d" % (tag, j), eta.shape, BF16), stream=stream)
+            so = _scale_only(ctxs[j]["aff"], zero_shift, ws, tag, j, stream)
+            if _MASK_FUSION:   # the mask of this layer's own LeakyReLU applied in the conv epilogue
+                xi = ops.conv3d_cl_any(xi, layer.p["weight"], so, ACT_LRELU_MASK, layer.cin, 64,
+                                       out=ws.get("%s.xi%d" % (tag, j), deltas[j].shape, BF16), wimgs=layer._wimgs,
+                                       mask=ctxs[j]["a"], stream=stream)
+            else:
+                eta = ops.conv3d_cl_any(xi, layer.p["weight"], so, ACT_NONE, layer.cin, 64,
+                                        out=ws.get("%s.eta%d" % (tag, j), deltas[j].shape, BF16), wimgs=layer._wimgs,
+                                        stream=stream)
+                xi = ops.lrelu_bwd_cl(eta, ctxs[j]["a"], out=ws.get("%s.xi%d" % (tag, j), eta.shape, BF16),
+                                      stream=stream)
         ops.conv_wgrad_cl(xi, d_out, g.of(D.tail.p["weight"]), co_n=1, ci_n=64, accumulate=True, stream=stream)
         return gp
 

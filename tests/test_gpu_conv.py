@@ -64,6 +64,75 @@ def test_conv_tail(hpvg_gpu, cout):
     assert err < TOL, "tail conv 64->%d rel-L2 %.3e" % (cout, err)
 
 
+@pytest.mark.parametrize("shape", [(3, 1, 17, 9), (1, 13, 35, 70), (2, 2, 16, 8), (1, 5, 1, 1)])
+def test_conv_tail_folded_taps_ragged_shapes_and_legacy_variant(hpvg_gpu, shape):
+    """The 64->3 tail kernel with the in-plane taps folded into N (conv3d_tail.cu): ragged tiles, T = 1, single-voxel
+    planes, batch > 1; and it must agree with the generic skinny variant (HPVG_CONV_64_16) it replaces."""
+    hp, ops = hpvg_gpu, hpvg_gpu.ops
+    N, T, H, W = shape
+    rng = np.random.default_rng(13)
+    x = bf16_round(rng.standard_normal((N, 64, T, H, W)))
+    w = bf16_round(rng.standard_normal((3, 64, 3, 3, 3)) * 0.05)
+    b = rng.standard_normal(3).astype(np.float32) * 0.1
+    x_cl = ops.pack_cl(hp.from_numpy(x))
+    aff = ops.affine_from_bias(hp.from_numpy(b))
+    tw = hp.from_numpy(w)
+    y = ops.conv3d_cl_any(x_cl, tw, aff, ops.ACT_NONE, 64, 3).numpy()
+    ref = _conv_ref(x, w, b)
+    assert rel_l2(y, ref) < TOL
+    s, sh = aff, aff.view((64,), hp.F32, 256)
+    legacy = ops.conv_cl(ops.CONV_64_16, x_cl, ops.pack_weights(tw, ops.CONV_64_16), s, sh, ops.ACT_NONE,
+                         ops.OUT_F32_NCDHW, cout_real=3).numpy()
+    assert np.abs(y - legacy).max() < 1e-4 * max(1.0, np.abs(ref).max())
+    # data-gradient filter bank (roles of Cin/Cout swapped, taps mirrored): dgrad of a 3 -> 64 head conv
+    wh = bf16_round(rng.standard_normal((64, 3, 3, 3, 3)) * 0.05)
+    gy = bf16_round(rng.standard_normal((N, 64, T, H, W)))
+    xt = torch.zeros((N, 3, T, H, W), requires_grad=True)
+    F.conv3d(xt, torch.from_numpy(wh), padding=1).backward(torch.from_numpy(gy))
+    unit = hp.from_numpy(np.concatenate([np.ones(64, np.float32), np.zeros(64, np.float32)]).reshape(2, 64))
+    dx = ops.conv_cl(ops.CONV_64_3, ops.pack_cl(hp.from_numpy(gy)),
+                     ops.pack_weights(hp.from_numpy(wh), ops.CONV_64_3, True, cout=3), unit, unit.view((64,), hp.F32, 256),
+                     ops.ACT_NONE, ops.OUT_F32_NCDHW, cout_real=3).numpy()
+    assert rel_l2(dx, xt.grad.numpy()) < TOL
+
+
+def test_conv_epilogue_lrelu_backward_mask(hpvg_gpu):
+    """HPVG_ACT_LRELU_MASK: the data-gradient conv multiplies its result by LeakyReLU'(stored activation), i.e. emits
+    the next (lower) layer's pre-activation gradient directly — must equal dgrad followed by hpvg_lrelu_bwd_cl."""
+    hp, ops = hpvg_gpu, hpvg_gpu.ops
+    rng = np.random.default_rng(15)
+    N, T, H, W = 2, 3, 19, 21
+    gy = bf16_round(rng.standard_normal((N, 64, T, H, W)))
+    a = bf16_round(rng.standard_normal((N, 64, T, H, W)))            # stored activation of the layer below
+    w = bf16_round(rng.standard_normal((64, 64, 3, 3, 3)) * 0.05)
+    unit = hp.from_numpy(np.concatenate([np.ones(64, np.float32), np.zeros(64, np.float32)]).reshape(2, 64))
+    tw, gy_cl, a_cl = hp.from_numpy(w), ops.pack_cl(hp.from_numpy(gy)), ops.pack_cl(hp.from_numpy(a))
+    plain = ops.conv3d_cl_any(gy_cl, tw, unit, ops.ACT_NONE, 64, 64, transpose_flip=True)
+    want = ops.unpack_cl(ops.lrelu_bwd_cl(plain, a_cl)).numpy()
+    got = ops.unpack_cl(ops.conv3d_cl_any(gy_cl, tw, unit, ops.ACT_LRELU_MASK, 64, 64, transpose_flip=True,
+                                          mask=a_cl)).numpy()
+    # one bf16 rounding fewer on the fused path (the unfused one rounds dgrad, then rounds again after the mask)
+    assert rel_l2(got, want) < 3e-3
+    xt = torch.from_numpy(a).clone().requires_grad_(True)    # autograd: d/dx of conv(lrelu(x)) at lrelu output a
+    pre = torch.from_numpy(a).clone().requires_grad_(True)
+    y = F.conv3d(F.leaky_relu(pre, 0.2), torch.from_numpy(w), padding=1)
+    y.backward(torch.from_numpy(gy))
+    assert rel_l2(got, pre.grad.numpy()) < TOL
+
+
+def test_conv_tail_2d(hpvg_gpu):
+    """Conv2d(N, nc_im) tail of the image path (networks_2d.py:212): 3x3 filter in the centre temporal tap."""
+    hp, ops = hpvg_gpu, hpvg_gpu.ops
+    rng = np.random.default_rng(14)
+    x = bf16_round(rng.standard_normal((2, 64, 1, 29, 39)))
+    w = bf16_round(rng.standard_normal((3, 64, 3, 3)) * 0.05)
+    b = rng.standard_normal(3).astype(np.float32) * 0.1
+    aff = ops.affine_from_bias(hp.from_numpy(b))
+    y = ops.conv3d_cl_any(ops.pack_cl(hp.from_numpy(x)), hp.from_numpy(w), aff, ops.ACT_TANH, 64, 3).numpy()
+    ref = np.tanh(F.conv2d(torch.from_numpy(x[:, :, 0]), torch.from_numpy(w), torch.from_numpy(b), padding=1).numpy())
+    assert rel_l2(y[:, :, 0], ref) < TOL
+
+
 def test_conv_head_3_64(hpvg_gpu):
     hp, ops = hpvg_gpu, hpvg_gpu.ops
     N, T, H, W = 2, 4, 24, 33
@@ -133,4 +202,4 @@ def test_conv2d_is_t1(hpvg_gpu):
 
 def test_conv_empty_input_is_noop(hpvg_gpu):
     hp = hpvg_gpu
-    assert hp.lib.hpvg_conv_cl(0, 0, 4, 8, 8, None, 64, None, None, None, 0, 0, None, 64, 0, 64, None, None, None) == 0
+    assert hp.lib.hpvg_conv_cl(0, 0, 4, 8, 8, None, 64, None, None, None, 0, 0, None, 64, 0, 64, None, None, None, 0, None) == 0
