@@ -413,7 +413,14 @@ def run_ours(args):
     }
     if world == 1 and not args.no_train:
         del net
-        line["train"] = train_iter_bench(hpvg, opt, args.train_steps, 3, st, graph=not args.no_graph)
+        try:
+            line["train"] = train_iter_bench(hpvg, opt, args.train_steps, 3, st, graph=not args.no_graph)
+        except hpvg.HpvgError as e:     # graph capture refused on this driver/box: same iteration, launched eagerly
+            if args.no_graph:
+                raise
+            sys.stderr.write("bench: CUDA-graph train iteration failed (%s); falling back to eager launches\n" % e)
+            hpvg.device_sync()
+            line["train"] = train_iter_bench(hpvg, opt, args.train_steps, 3, st, graph=False)
         if args.workload == "train":
             tr = line["train"]
             line.update(metric=tr["metric"], value=tr["value"], unit=tr["unit"], ms_per_step=tr["ms_per_iter"],
