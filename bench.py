@@ -44,6 +44,9 @@ def parse():
                     help="sample: sampled clips/s (scales over GPUs); train: GAN-phase train iter/s on 1 GPU")
     ap.add_argument("--train-steps", type=int, default=10, help="train iterations timed for the extra `train` object")
     ap.add_argument("--no-train", action="store_true", help="skip the extra train-iter/s measurement at N == 1")
+    ap.add_argument("--train-frames", type=int, default=16,
+                    help="frames of the synthetic clip at the finest scale for the train workload (BASELINE.json config 3: "
+                         "16; the reference's own schedule gives 13)")
     ap.add_argument("--no-graph", action="store_true", help="train iterations launched eagerly instead of as a CUDA graph")
     return ap.parse_args()
 
@@ -171,13 +174,15 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------- train iter/s
-def train_iter_bench(hpvg, opt, steps, warmup, st, graph=True):
+def train_iter_bench(hpvg, opt, steps, warmup, st, graph=True, frames=None):
     """One GAN-phase train iteration at the finest scale (train_video.py:170-177): D step (3 D forwards, 2 backwards,
     WGAN-GP double backward, Adam) + G step (reconstruction forward of the whole pyramid in BatchNorm-train mode,
     backward of the last stage, random forward + D forward for the loss value, ClippedAdam).  Inputs come from
     pinned host buffers every iteration (the data loader + host noise of the reference); losses are read back."""
     from hpvg import networks_3d as n3, train as T, sampling
     from hpvg.utils import images as uimg
+    if frames:
+        opt.td_override = {opt.stop_scale: int(frames)}
     G = n3.GeneratorHPVAEGAN(opt, seed=0)
     for _ in range(opt.stop_scale):
         G.init_next_stage()
@@ -258,7 +263,7 @@ def train_iter_bench(hpvg, opt, steps, warmup, st, graph=True):
             "h2d_bytes_per_iter": int(sum(t.nbytes for t in dev.values())), "d2h_bytes_per_iter": 64,
             "last_losses": {"D": float(dl), "G": float(gl)},
             "config": {"workload": "train_video.py GAN-phase iteration (D step + G step, train_depth 1) at the finest "
-                                   "scale %dx%dx%d of the full %d-scale pyramid, batch 1, synthetic clip, random-init "
+                                   "scale %dx%dx%d (BASELINE.json config 3) of the full %d-scale pyramid, batch 1, synthetic clip, random-init "
                                    "weights; host noise draw, host->device copies of the clip/noise and loss "
                                    "read-backs included; the iteration is replayed as one CUDA graph"
                                    % (top + (opt.stop_scale + 1,))}}
@@ -414,13 +419,15 @@ def run_ours(args):
     if world == 1 and not args.no_train:
         del net
         try:
-            line["train"] = train_iter_bench(hpvg, opt, args.train_steps, 3, st, graph=not args.no_graph)
+            line["train"] = train_iter_bench(hpvg, uimg.default_opt(img_size=args.img_size), args.train_steps, 3, st,
+                                             graph=not args.no_graph, frames=args.train_frames)
         except hpvg.HpvgError as e:     # graph capture refused on this driver/box: same iteration, launched eagerly
             if args.no_graph:
                 raise
             sys.stderr.write("bench: CUDA-graph train iteration failed (%s); falling back to eager launches\n" % e)
             hpvg.device_sync()
-            line["train"] = train_iter_bench(hpvg, opt, args.train_steps, 3, st, graph=False)
+            line["train"] = train_iter_bench(hpvg, uimg.default_opt(img_size=args.img_size), args.train_steps, 3, st,
+                                             graph=False, frames=args.train_frames)
         if args.workload == "train":
             tr = line["train"]
             line.update(metric=tr["metric"], value=tr["value"], unit=tr["unit"], ms_per_step=tr["ms_per_iter"],

@@ -78,6 +78,9 @@ def scale_shape(opt, index):
     """(T, H, W) of pyramid level `index` (images.py:99-101)."""
     s = get_scales_by_index(index, opt.scale_factor, opt.stop_scale, opt.img_size)
     _, td, _ = get_fps_td_by_index(index, opt.stop_scale_time, opt.sampling_rates, opt.org_fps, opt.fps_lcm)
+    # synthetic benchmark clips may pin the time depth of a level (BASELINE.json config 3: "16-frame clips at the
+    # finest scale"); the reference always derives it from the sampling rates
+    td = getattr(opt, "td_override", {}).get(index, td)
     return (td, int(s * opt.ar), s)
 
 

@@ -13,4 +13,5 @@ hpvg.init(0)
 st = hpvg.Stream()
 opt = uimg.default_opt()
 graph = not (len(sys.argv) > 3 and sys.argv[3] == 'eager')
-print(json.dumps(bench.train_iter_bench(hpvg, opt, steps, warm, st, graph=graph)))
+frames = int(sys.argv[4]) if len(sys.argv) > 4 else None
+print(json.dumps(bench.train_iter_bench(hpvg, opt, steps, warm, st, graph=graph, frames=frames)))
