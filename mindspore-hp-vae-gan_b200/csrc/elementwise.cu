@@ -40,6 +40,26 @@ __global__ void pack_cl_kernel(const float* __restrict__ x, int C, long long sp 
   *reinterpret_cast<uint4*>(y + v * c_pitch + c_off + g * 8) = pk;
 }
 
+// Skinny source (C <= 8: the 3-channel clips / gradients) zero-padded to a wide channels-last tensor: consecutive
+// threads walk the 16-byte groups of ONE voxel, so a warp writes 512 contiguous bytes (the voxel-fastest mapping above
+// would write 16 bytes out of every 128); only group 0 reads anything.
+__global__ void pack_cl_skinny_kernel(const float* __restrict__ x, int C, long long sp, long long voxels,
+                                      __nv_bfloat16* __restrict__ y, int c_pitch, int c_off, int groups) {
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= voxels * groups) return;
+  const long long v = gid / groups;
+  const int g = static_cast<int>(gid - v * groups);
+  uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+  if (g == 0) {
+    const long long n = v / sp, s = v - n * sp;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = (e < C) ? __ldg(x + (n * C + e) * sp + s) : 0.f;
+    pk = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+  }
+  *reinterpret_cast<uint4*>(y + v * c_pitch + c_off + g * 8) = pk;
+}
+
 __global__ void unpack_cl_kernel(const __nv_bfloat16* __restrict__ x, int C, long long sp, long long voxels,
                                  int c_pitch, int c_off, float* __restrict__ y, int groups) {
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -1502,8 +1522,12 @@ cudaError_t ew_pack_cl(const float* x, int N, int C, long long sp, __nv_bfloat16
   const long long voxels = static_cast<long long>(N) * sp;
   const int groups = (c_zero_to - c_off > C ? c_zero_to - c_off : C) + 7 >> 3;
   const long long total = voxels * groups;
-  pack_cl_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, C, sp, voxels, y, c_pitch, c_off,
-                                                                            groups);
+  if (C <= 8 && groups > 1)
+    pack_cl_skinny_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, C, sp, voxels, y, c_pitch,
+                                                                                     c_off, groups);
+  else
+    pack_cl_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, C, sp, voxels, y, c_pitch, c_off,
+                                                                              groups);
   LAUNCH_CHECK();
   return cudaSuccess;
 }

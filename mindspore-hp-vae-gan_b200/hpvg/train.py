@@ -13,7 +13,7 @@ import numpy as np
 from . import ops
 from .networks_3d import BnStatsSlab, ConvLayer, Workspace, as5d
 from .ops import ACT_LRELU, ACT_LRELU_MASK, ACT_NONE, ACT_TANH, CONV_64_16, CONV_64_64, CONV_8_64, OUT_BF16_CL, OUT_F32_NCDHW, OUT_F32_RAW
-from .runtime import BF16, F32, U64, Graph, HpvgError, Tensor, from_numpy
+from .runtime import BF16, F32, U64, Graph, HpvgError, Tensor, device_sync, from_numpy
 from .utils import images as uimg
 
 import os as _os
@@ -97,6 +97,7 @@ class GradBook:
         g = self._g.get(param.ptr)
         if g is None:
             g = Tensor(param.shape, F32).zero_()
+            device_sync()       # first use only: the memset ran on the legacy stream, consumers use their own stream
             self._g[param.ptr] = g
         return g
 
@@ -336,6 +337,8 @@ class GeneratorTrainer:
         # by a DEVICE-resident draw counter, so the whole step can be replayed as a CUDA graph with fresh noise.
         self.device_rng = device_rng
         self.draws = Tensor((1,), U64).zero_() if device_rng else None
+        if device_rng:
+            device_sync()
 
     def _draw(self, shape, stream):
         """N(0,1) of `shape`: host numpy global RNG like the reference (Q7), or the device generator (device_rng)."""
@@ -680,6 +683,7 @@ class Adam:
                 self.items.append((p[1] if isinstance(p, tuple) else p, learning_rate))
         self.m = [Tensor(p.shape, F32).zero_() for p, _ in self.items]
         self.v = [Tensor(p.shape, F32).zero_() for p, _ in self.items]
+        device_sync()           # the memsets above ran on the legacy stream
         self.step = 0
 
     def apply(self, grads, stream=None):
