@@ -268,6 +268,76 @@ def train_iter_bench(hpvg, opt, steps, warmup, st, graph=True, frames=None):
                                    "read-backs included; the iteration is replayed as one CUDA graph"
                                    % (top + (opt.stop_scale + 1,))}}
 
+def train_vae_bench(hpvg, opt, steps, warmup, st, scale_idx=2, graph=True):
+    """BASELINE.json config 2: VAE-phase train iteration at the coarsest scales (train_video.py:170-172 with
+    scale_idx < vae_levels): one G step — reconstruction forward through encoder, decoder and the refinement stages in
+    BatchNorm-train mode, MSE + MSE + KL losses, backward into encode / decoder / body[-1] (through the resize
+    backward), per-tensor clip + Adam with the per-group learning rates of train_video.py:76-105."""
+    from hpvg import driver, networks_3d as n3, train as T, sampling
+    from hpvg.utils import images as uimg
+    G = n3.GeneratorHPVAEGAN(opt, seed=0)
+    for _ in range(scale_idx):
+        G.init_next_stage()
+    amps = [1.0] + [0.1] * scale_idx
+    rng = np.random.default_rng(0)
+    shapes = {"real": (1, 3) + uimg.scale_shape(opt, scale_idx), "real_zero": (1, 3) + uimg.scale_shape(opt, 0),
+              "noise": sampling.z_init_size(opt, 1)}
+    host = {k: hpvg.PinnedBuffer(int(np.prod(v)) * 4) for k, v in shapes.items()}
+    for k, v in shapes.items():
+        a = rng.standard_normal(v).astype(np.float32)
+        host[k].as_array(v)[...] = np.tanh(a) if k != "noise" else a
+    dev = {k: hpvg.Tensor(v, hpvg.F32) for k, v in shapes.items()}
+    groups, body_idx, codec = driver.generator_param_groups(opt, G, scale_idx)
+    optG = T.ClippedAdam(opt, groups, opt.lr_g, beta1=opt.beta1, beta2=0.999, device_step=graph)
+    cells = [G.body[i] for i in body_idx] + [G.encode, G.decoder]
+    g_step = T.TrainOneStepCell(T.GWithLoss(opt, None, G, device_rng=graph), optG, cells_to_invalidate=cells)
+    G.set_train(True)
+    kw = dict(isVAE=True, trainable_body=body_idx, train_codec=codec)
+
+    def upload():
+        for k in dev:
+            hpvg.lib.hpvg_h2d(dev[k].ptr, host[k].ptr, dev[k].nbytes, st.handle)
+
+    if graph:
+        it = T.GraphedIteration(st, g_step, None, dev["real"], dev["real_zero"], dev["noise"], amps, kw)
+        upload()
+        it.warmup(max(warmup, 2))
+        it.capture()
+        per_iter = it.kernels_per_launch
+
+        def one_iter():
+            upload()
+            return it()[1]
+    else:
+        per_iter = None
+
+        def one_iter():
+            upload()
+            return g_step(dev["real"], dev["real_zero"], dev["noise"], amps, stream=st, **kw)
+
+    for _ in range(warmup):
+        one_iter()
+    st.sync()
+    l0 = hpvg.lib.hpvg_launch_count()
+    e0, e1 = hpvg.Event(), hpvg.Event()
+    e0.record(st)
+    for _ in range(steps):
+        gl = one_iter()
+    e1.record(st)
+    e1.sync()
+    ms = e0.elapsed_ms(e1) / steps
+    if per_iter is None:
+        per_iter = (hpvg.lib.hpvg_launch_count() - l0) // steps
+    t, h, w = uimg.scale_shape(opt, scale_idx)
+    return {"metric": "video train iter/s", "value": 1000.0 / ms, "unit": "iter/s", "ms_per_iter": ms, "steps": steps,
+            "warmup": warmup, "gpu_launches_per_iter": int(per_iter), "cuda_graph": bool(graph),
+            "last_loss": float(gl),
+            "config": {"workload": "train_video.py VAE-phase iteration (BASELINE.json config 2) at scale %d = %dx%dx%d of "
+                                   "the 13-frame pyramid: G step with encode + decoder + body[-1] trainable, batch 1, "
+                                   "synthetic clip, random-init weights; H2D of the clips and loss read-back included"
+                                   % (scale_idx, t, h, w)}}
+
+
 # ------------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -428,6 +498,11 @@ def run_ours(args):
             hpvg.device_sync()
             line["train"] = train_iter_bench(hpvg, uimg.default_opt(img_size=args.img_size), args.train_steps, 3, st,
                                              graph=False, frames=args.train_frames)
+        try:
+            line["train_vae"] = train_vae_bench(hpvg, uimg.default_opt(img_size=args.img_size), 50, 5, st,
+                                                graph=not args.no_graph)
+        except hpvg.HpvgError as e:
+            sys.stderr.write("bench: VAE-phase train measurement failed: %s\n" % e)
         if args.workload == "train":
             tr = line["train"]
             line.update(metric=tr["metric"], value=tr["value"], unit=tr["unit"], ms_per_step=tr["ms_per_iter"],
