@@ -464,45 +464,43 @@ __global__ void upsample_noise_pack_tiled_kernel(const float* __restrict__ x, in
 constexpr int CW_MAX_TI = 8;
 constexpr int CW_THREADS = 256;
 
-template <int C>
+template <int C, int TI>
 __device__ __forceinline__ void colwalk_load(const float* __restrict__ xs /* block-uniform slice base */, unsigned spi,
                                              const ResizeGeom& g, const Tap& th, const Tap& tw,
-                                             float (&hv)[C][CW_MAX_TI + 1]) {
-  // 32-bit element indices relative to the uniform base: one integer op per load instead of 64-bit pointer math
-  const unsigned o00 = th.i0 * g.Wi + tw.i0, o01 = th.i0 * g.Wi + tw.i1;
-  const unsigned o10 = th.i1 * g.Wi + tw.i0, o11 = th.i1 * g.Wi + tw.i1;
+                                             float (&hv)[C][TI + 1]) {
+  // four running pointers (one per corner) advanced by one frame: 2 integer ops per load instead of index math
   const unsigned fsz = g.Hi * g.Wi;
 #pragma unroll
   for (int c = 0; c < C; ++c) {
-    float v[CW_MAX_TI][4];
+    const float* p00 = xs + (c * spi + th.i0 * g.Wi + tw.i0);
+    const float* p01 = xs + (c * spi + th.i0 * g.Wi + tw.i1);
+    const float* p10 = xs + (c * spi + th.i1 * g.Wi + tw.i0);
+    const float* p11 = xs + (c * spi + th.i1 * g.Wi + tw.i1);
+    float v[TI][4];
 #pragma unroll
-    for (int f = 0; f < CW_MAX_TI; ++f) {
-      if (f < g.Ti) {
-        const unsigned b = c * spi + f * fsz;
-        v[f][0] = __ldg(xs + (b + o00));
-        v[f][1] = __ldg(xs + (b + o01));
-        v[f][2] = __ldg(xs + (b + o10));
-        v[f][3] = __ldg(xs + (b + o11));
-      }
+    for (int f = 0; f < TI; ++f) {
+      v[f][0] = __ldg(p00);
+      v[f][1] = __ldg(p01);
+      v[f][2] = __ldg(p10);
+      v[f][3] = __ldg(p11);
+      p00 += fsz; p01 += fsz; p10 += fsz; p11 += fsz;
     }
 #pragma unroll
-    for (int f = 0; f < CW_MAX_TI; ++f) {
-      hv[c][f] = 0.f;
-      if (f < g.Ti) {
-        const float a0 = lerp_rn(tw.l0, v[f][0], tw.l1, v[f][1]);
-        const float a1 = lerp_rn(tw.l0, v[f][2], tw.l1, v[f][3]);
-        hv[c][f] = lerp_rn(th.l0, a0, th.l1, a1);
-      }
+    for (int f = 0; f < TI; ++f) {
+      const float a0 = lerp_rn(tw.l0, v[f][0], tw.l1, v[f][1]);
+      const float a1 = lerp_rn(tw.l0, v[f][2], tw.l1, v[f][3]);
+      hv[c][f] = lerp_rn(th.l0, a0, th.l1, a1);
     }
-    hv[c][CW_MAX_TI] = 0.f;
+    hv[c][TI] = 0.f;
   }
 }
 
+template <int TI>
 __global__ void __launch_bounds__(CW_THREADS)
 resize3d_fwd_colwalk_kernel(const float* __restrict__ x, const ResizeGeom g, float* __restrict__ y) {
   __shared__ TapRow ttab[64];
   for (int i = threadIdx.x; i < g.To; i += blockDim.x) {
-    const Tap t = linear_tap(i, g.Ti, g.st, g.align);
+    const Tap t = linear_tap(i, TI, g.st, g.align);
     ttab[i] = TapRow{t.i0, t.i1, t.l0, t.l1};
   }
   __syncthreads();
@@ -511,29 +509,27 @@ resize3d_fwd_colwalk_kernel(const float* __restrict__ x, const ResizeGeom g, flo
   const int ho = col / g.Wo, wo = col - ho * g.Wo;
   const long long nc = blockIdx.y;
   const Tap th = linear_tap(ho, g.Hi, g.sh, g.align), tw = linear_tap(wo, g.Wi, g.sw, g.align);
-  const unsigned spi = g.Ti * g.Hi * g.Wi;
-  float hv[1][CW_MAX_TI + 1];
-  colwalk_load<1>(x + nc * spi, spi, g, th, tw, hv);
+  const unsigned spi = TI * g.Hi * g.Wi;
+  float hv[1][TI + 1];
+  colwalk_load<1, TI>(x + nc * spi, spi, g, th, tw, hv);
   const unsigned plane = g.Ho * g.Wo;
-  float* __restrict__ ys = y + nc * g.To * plane;     // block-uniform base
-  unsigned oidx = col;
+  float* __restrict__ dst = y + nc * g.To * plane + col;
+  const int To = g.To;
   int to = 0;
 #pragma unroll
-  for (int f = 0; f < CW_MAX_TI; ++f) {
-    if (f < g.Ti) {
-      while (to < g.To) {
-        const TapRow tt = ttab[to];
-        if (tt.o0 != f) break;
-        const float hi = (tt.o1 == f) ? hv[0][f] : hv[0][f + 1];
-        ys[oidx] = lerp_rn(tt.l0, hv[0][f], tt.l1, hi);
-        oidx += plane;
-        ++to;
-      }
+  for (int f = 0; f < TI; ++f) {
+    while (to < To) {
+      const TapRow tt = ttab[to];
+      if (tt.o0 != f) break;
+      const float hi = (tt.o1 == f) ? hv[0][f] : hv[0][f + 1];
+      *dst = lerp_rn(tt.l0, hv[0][f], tt.l1, hi);
+      dst += plane;
+      ++to;
     }
   }
 }
 
-template <int C>
+template <int C, int TI>
 __global__ void __launch_bounds__(CW_THREADS)
 upsample_noise_pack_colwalk_kernel(const float* __restrict__ x, const ResizeGeom g, const float* __restrict__ noise,
                                    float amp, unsigned long long seed, unsigned long long sample_base,
@@ -541,7 +537,7 @@ upsample_noise_pack_colwalk_kernel(const float* __restrict__ x, const ResizeGeom
                                    __nv_bfloat16* __restrict__ xin) {
   __shared__ TapRow ttab[64];
   for (int i = threadIdx.x; i < g.To; i += blockDim.x) {
-    const Tap t = linear_tap(i, g.Ti, g.st, g.align);
+    const Tap t = linear_tap(i, TI, g.st, g.align);
     ttab[i] = TapRow{t.i0, t.i1, t.l0, t.l1};
   }
   __syncthreads();
@@ -551,43 +547,42 @@ upsample_noise_pack_colwalk_kernel(const float* __restrict__ x, const ResizeGeom
   const int ho = col / g.Wo, wo = col - ho * g.Wo;
   const long long n = blockIdx.y;
   const Tap th = linear_tap(ho, g.Hi, g.sh, g.align), tw = linear_tap(wo, g.Wi, g.sw, g.align);
-  const unsigned spi = g.Ti * g.Hi * g.Wi;
+  const unsigned spi = TI * g.Hi * g.Wi;
   const int plane = g.Ho * g.Wo;
   const long long spo = static_cast<long long>(g.To) * plane;
-  float hv[C][CW_MAX_TI + 1];
-  colwalk_load<C>(x + n * C * static_cast<long long>(spi), spi, g, th, tw, hv);
+  float hv[C][TI + 1];
+  colwalk_load<C, TI>(x + n * C * static_cast<long long>(spi), spi, g, th, tw, hv);
   const unsigned long long sample = sample_base + static_cast<unsigned long long>(n);
   long long sidx = col;               // spatial index inside the sample
+  const int To = g.To;
   int to = 0;
 #pragma unroll
-  for (int f = 0; f < CW_MAX_TI; ++f) {
-    if (f < g.Ti) {
-      while (to < g.To) {
-        const TapRow tt = ttab[to];
-        if (tt.o0 != f) break;
-        float z[4] = {0.f, 0.f, 0.f, 0.f};
-        if (!noise && seed != 0ull) {
-          const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(sidx), static_cast<uint32_t>(sidx >> 32),
-                                                     static_cast<uint32_t>(sample), static_cast<uint32_t>(sample >> 32)),
-                                          make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
-          box_muller(rnd.x, rnd.y, z[0], z[1]);
-          box_muller(rnd.z, rnd.w, z[2], z[3]);
-        }
-        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const float hi = (tt.o1 == f) ? hv[c][f] : hv[c][f + 1];
-          const float u = lerp_rn(tt.l0, hv[c][f], tt.l1, hi);
-          const long long o = (n * C + c) * spo + sidx;
-          up[o] = u;
-          const float nz = noise ? noise[o] : z[c];
-          v[c] = fmaf(nz, amp, u);
-        }
-        *reinterpret_cast<uint4*>(xin + (n * spo + sidx) * 8) =
-            make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-        sidx += plane;
-        ++to;
+  for (int f = 0; f < TI; ++f) {
+    while (to < To) {
+      const TapRow tt = ttab[to];
+      if (tt.o0 != f) break;
+      float z[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!noise && seed != 0ull) {
+        const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(sidx), static_cast<uint32_t>(sidx >> 32),
+                                                   static_cast<uint32_t>(sample), static_cast<uint32_t>(sample >> 32)),
+                                        make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+        box_muller(rnd.x, rnd.y, z[0], z[1]);
+        box_muller(rnd.z, rnd.w, z[2], z[3]);
       }
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float hi = (tt.o1 == f) ? hv[c][f] : hv[c][f + 1];
+        const float u = lerp_rn(tt.l0, hv[c][f], tt.l1, hi);
+        const long long o = (n * C + c) * spo + sidx;
+        up[o] = u;
+        const float nz = noise ? noise[o] : z[c];
+        v[c] = fmaf(nz, amp, u);
+      }
+      *reinterpret_cast<uint4*>(xin + (n * spo + sidx) * 8) =
+          make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+      sidx += plane;
+      ++to;
     }
   }
 }
@@ -1630,8 +1625,19 @@ cudaError_t ew_resize3d_fwd(const float* x, long long NC, int Ti, int Hi, int Wi
   TiledGeom tg;
   size_t smem;
   if (colwalk_ok(g, NC)) {
-    resize3d_fwd_colwalk_kernel<<<dim3((Ho * Wo + CW_THREADS - 1) / CW_THREADS, static_cast<unsigned>(NC)), CW_THREADS,
-                                  0, st>>>(x, g, y);
+    const dim3 grid((Ho * Wo + CW_THREADS - 1) / CW_THREADS, static_cast<unsigned>(NC));
+#define HPVG_CWF(T_) resize3d_fwd_colwalk_kernel<T_><<<grid, CW_THREADS, 0, st>>>(x, g, y)
+    switch (Ti) {   // the frame count is a template parameter: no per-frame predicates in the unrolled body
+      case 1: HPVG_CWF(1); break;
+      case 2: HPVG_CWF(2); break;
+      case 3: HPVG_CWF(3); break;
+      case 4: HPVG_CWF(4); break;
+      case 5: HPVG_CWF(5); break;
+      case 6: HPVG_CWF(6); break;
+      case 7: HPVG_CWF(7); break;
+      default: HPVG_CWF(8); break;
+    }
+#undef HPVG_CWF
   } else if (NC <= 65535 && plan_fwd_tiles(g, &tg, &smem)) {
     static bool ok = false;
     cudaError_t e = rs_allow_smem(resize3d_fwd_tiled_kernel, &ok);
@@ -1675,14 +1681,23 @@ cudaError_t ew_upsample_noise_pack(const float* x, int N, int C, int Ti, int Hi,
   const ResizeGeom g = make_geom(Ti, Hi, Wi, To, Ho, Wo, 1);
   TiledGeom tg;
   size_t smem;
-  if (colwalk_ok(g, N) && C >= 1 && C <= 4) {
+  if (colwalk_ok(g, N) && (C == 1 || C == 3) && static_cast<long long>(C) * Ti * Hi * Wi < (1LL << 31)) {
     const dim3 grid((Ho * Wo + CW_THREADS - 1) / CW_THREADS, N);
-#define HPVG_CW(C_) upsample_noise_pack_colwalk_kernel<C_><<<grid, CW_THREADS, 0, st>>>( \
+#define HPVG_CW(C_, T_) upsample_noise_pack_colwalk_kernel<C_, T_><<<grid, CW_THREADS, 0, st>>>( \
       x, g, noise, amp, seed, sample_base, d_sample_offset, up, xin)
-    if (C == 1) HPVG_CW(1);
-    else if (C == 2) HPVG_CW(2);
-    else if (C == 3) HPVG_CW(3);
-    else HPVG_CW(4);
+#define HPVG_CWT(C_)                       \
+    switch (Ti) {                            \
+      case 1: HPVG_CW(C_, 1); break;         \
+      case 2: HPVG_CW(C_, 2); break;         \
+      case 3: HPVG_CW(C_, 3); break;         \
+      case 4: HPVG_CW(C_, 4); break;         \
+      case 5: HPVG_CW(C_, 5); break;         \
+      case 6: HPVG_CW(C_, 6); break;         \
+      case 7: HPVG_CW(C_, 7); break;         \
+      default: HPVG_CW(C_, 8); break;        \
+    }
+    if (C == 1) { HPVG_CWT(1) } else { HPVG_CWT(3) }
+#undef HPVG_CWT
 #undef HPVG_CW
   } else if (N <= 65535 && plan_fwd_tiles(g, &tg, &smem)) {
     static bool ok = false;
