@@ -624,6 +624,7 @@ __device__ __forceinline__ InvTap make_inv_tap(int i, int n_in, int n_out, float
 }
 
 constexpr int BW_TX = 32, BW_TY = 8;
+template <int NH, int NW>   // compile-time bounds on the contributing rows / columns (floor(2/scale) + 1)
 __global__ void __launch_bounds__(BW_TX * BW_TY)
 resize3d_bwd_colwalk_kernel(const float* __restrict__ gy, const ResizeGeom g, float* __restrict__ gx) {
   __shared__ TapRow ttab[64];
@@ -651,17 +652,17 @@ resize3d_bwd_colwalk_kernel(const float* __restrict__ gy, const ResizeGeom g, fl
   int f_lo = 0;
   float acc_lo = 0.f, acc_hi = 0.f;
   for (int to = 0; to < g.To; ++to, src += plane_o) {
-    float v[4][4];
+    float v[NH][NW];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < NH; ++k)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[k][j] = (k < eh.n && j < ew.n) ? __ldg(src + k * g.Wo + j) : 0.f;
+      for (int j = 0; j < NW; ++j) v[k][j] = (k < eh.n && j < ew.n) ? __ldg(src + k * g.Wo + j) : 0.f;
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < NH; ++k) {
       float r = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) r = fmaf(ew.c[j], v[k][j], r);
+      for (int j = 0; j < NW; ++j) r = fmaf(ew.c[j], v[k][j], r);
       s = fmaf(eh.c[k], r, s);
     }
     const TapRow tt = ttab[to];
@@ -1660,8 +1661,11 @@ cudaError_t ew_resize3d_bwd(const float* gy, long long NC, int To, int Ho, int W
   const bool few_w = (Wo == 1) || (g.sw > 0.f && static_cast<int>(2.0f / g.sw) + 1 <= 4);
   if (few_h && few_w && To <= 64 && NC <= 65535 && static_cast<long long>(To) * Ho * Wo < (1LL << 31) &&
       static_cast<long long>(Ti) * Hi * Wi < (1LL << 31)) {
-    resize3d_bwd_colwalk_kernel<<<dim3((Wi + BW_TX - 1) / BW_TX, (Hi + BW_TY - 1) / BW_TY, static_cast<unsigned>(NC)),
-                                  dim3(BW_TX, BW_TY), 0, st>>>(gy, g, gx);
+    const dim3 grid((Wi + BW_TX - 1) / BW_TX, (Hi + BW_TY - 1) / BW_TY, static_cast<unsigned>(NC));
+    const dim3 block(BW_TX, BW_TY);
+    const int nh = (Ho == 1) ? 1 : static_cast<int>(2.0f / g.sh) + 1, nw = (Wo == 1) ? 1 : static_cast<int>(2.0f / g.sw) + 1;
+    if (nh <= 3 && nw <= 3) resize3d_bwd_colwalk_kernel<3, 3><<<grid, block, 0, st>>>(gy, g, gx);
+    else resize3d_bwd_colwalk_kernel<4, 4><<<grid, block, 0, st>>>(gy, g, gx);
   } else if (NC <= 65535 && plan_bwd_tiles(g, &tg, &smem)) {
     static bool ok = false;
     cudaError_t e = rs_allow_smem(resize3d_bwd_tiled_kernel, &ok);
