@@ -230,7 +230,7 @@ def train_iter_bench(hpvg, opt, steps, warmup, st, graph=True, frames=None):
                                 dict(isVAE=False, trainable_body=(nb - 1,)))
         upload()
         it.warmup(max(warmup, 2))
-        it.capture()
+        it.capture(concurrent=not os.environ.get("HPVG_NO_OVERLAP"))
         per_iter = it.kernels_per_launch
 
         def one_iter():

@@ -148,6 +148,12 @@ int hpvg_bn_train_apply_cl(const void* d_y, long long voxels, const double* d_su
                            const float* d_beta, float eps, float momentum, float* d_moving_mean, float* d_moving_var,
                            float* d_saved, int act, void* d_x, void* stream);
 
+/* deferred moving-statistics update of many BatchNorm layers in one launch (pointer arrays on the host): pass
+ * d_moving_mean = d_moving_var = NULL to hpvg_bn_train_apply_cl, keep its d_saved, and replay the updates later in the
+ * reference's order — needed when training-mode forwards of one network run concurrently on several streams */
+int hpvg_bn_moving_update_multi(int n_layers, const float* const* d_saved, float* const* d_moving_mean,
+                                float* const* d_moving_var, float eps, float momentum, void* stream);
+
 /* ---------------------------------------------------------------- spectral norm (spectral_norm.py:142-151)
  * One power iteration on W viewed (Cout, K): v <- l2n(W^T u); u <- l2n(W v); sigma = u^T W v.
  * Updates d_u, d_v in place and writes sigma and 1/sigma. */

@@ -303,6 +303,22 @@ int hpvg_bn_train_apply_cl(const void* y, long long voxels, const double* sums, 
   return HPVG_OK;
 }
 
+int hpvg_bn_moving_update_multi(int n_layers, const float* const* saved, float* const* mm, float* const* mv, float eps,
+                                float momentum, void* st) {
+  if (n_layers < 0 || !saved || !mm || !mv) return fail(HPVG_E_ARG, "bn_moving_update_multi: bad arguments");
+  for (int base = 0; base < n_layers; base += hpvg::BN_MOVING_MAX_LAYERS) {
+    hpvg::BnMovingTable tab;
+    std::memset(&tab, 0, sizeof(tab));
+    int cnt = 0;
+    for (int i = base; i < n_layers && cnt < hpvg::BN_MOVING_MAX_LAYERS; ++i, ++cnt) {
+      if (!saved[i] || !mm[i] || !mv[i]) return fail(HPVG_E_ARG, "bn_moving_update_multi: null pointer");
+      tab.saved[cnt] = saved[i]; tab.mm[cnt] = mm[i]; tab.mv[cnt] = mv[i];
+    }
+    KL(hpvg::ew_bn_moving_update_multi(tab, cnt, eps, momentum, S(st)), 1);
+  }
+  return HPVG_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ spectral norm
 int hpvg_sn_power_iter_multi(int n_layers, const float* const* w, const int* cout, const int* k, float* const* u,
                              float* const* v, float* const* sigma2, const float* const* bias, float* const* aff,

@@ -1033,6 +1033,19 @@ __global__ void bn_train_apply_cl_kernel(const __nv_bfloat16* __restrict__ y, lo
   }
 }
 
+// Deferred moving-statistics update for many BatchNorm layers in one launch (block b = layer b): when several
+// training-mode forwards of the same network run CONCURRENTLY (hpvg/train.py:GraphedIteration) their read-modify-write
+// of the shared moving statistics is taken out of the forwards and replayed afterwards, forward by forward, in the
+// reference's order.  saved = (scale, shift, mean, invstd) of bn_train_apply_cl; var = 1/invstd^2 - eps.
+__global__ void bn_moving_update_multi_kernel(const BnMovingTable tab, float eps, float momentum) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  const float* sv = tab.saved[b];
+  const float mean = sv[128 + c], invstd = sv[192 + c];
+  const float var = fmaxf(1.0f / (invstd * invstd) - eps, 0.f);
+  tab.mm[b][c] = momentum * tab.mm[b][c] + (1.f - momentum) * mean;
+  tab.mv[b][c] = momentum * tab.mv[b][c] + (1.f - momentum) * var;
+}
+
 // ----------------------------------------------------------------------------------------------- spectral norm
 // One CTA.  W: (cout, k) fp32 row-major (the (Cout, Cin*27) view of spectral_norm.py:146).
 __device__ __forceinline__ float block_sum(float v, float* red) {
@@ -1753,6 +1766,12 @@ cudaError_t ew_sn_power_iter_multi(const SnTable& tab, int n_layers, cudaStream_
     if (b > smem) smem = b;
   }
   sn_power_iter_multi_kernel<<<n_layers, 512, smem, st>>>(tab);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_bn_moving_update_multi(const BnMovingTable& tab, int n_layers, float eps, float momentum,
+                                      cudaStream_t st) {
+  bn_moving_update_multi_kernel<<<n_layers, 64, 0, st>>>(tab, eps, momentum);
   LAUNCH_CHECK();
   return cudaSuccess;
 }

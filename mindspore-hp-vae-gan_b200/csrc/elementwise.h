@@ -56,6 +56,14 @@ struct SnTable {
 cudaError_t ew_sn_power_iter(const float* w, int cout, int k, float* u, float* v, float* sigma, float* inv_sigma,
                              cudaStream_t st);
 cudaError_t ew_sn_power_iter_multi(const SnTable& tab, int n_layers, cudaStream_t st);
+constexpr int BN_MOVING_MAX_LAYERS = 64;
+struct BnMovingTable {
+  const float* saved[BN_MOVING_MAX_LAYERS];
+  float* mm[BN_MOVING_MAX_LAYERS];
+  float* mv[BN_MOVING_MAX_LAYERS];
+};
+cudaError_t ew_bn_moving_update_multi(const BnMovingTable& tab, int n_layers, float eps, float momentum,
+                                      cudaStream_t st);
 cudaError_t ew_bn_train_apply_cl(const __nv_bfloat16* y, long long voxels, const double* sums, const float* gamma,
                                  const float* beta, float eps, float momentum, float* mm, float* mv, float* saved,
                                  int act, __nv_bfloat16* x, cudaStream_t st);

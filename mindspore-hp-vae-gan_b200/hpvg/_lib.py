@@ -69,6 +69,7 @@ _SIGS = {
     "hpvg_bn_finalize": ([vp, vp, ll, vp, vp, f, f, vp, vp, vp, vp, vp, vp, vp], c_int),
     "hpvg_bn_apply_lrelu_cl": ([vp, ll, vp, vp, i, vp, vp], c_int),
     "hpvg_bn_train_apply_cl": ([vp, ll, vp, vp, vp, f, f, vp, vp, vp, i, vp, vp], c_int),
+    "hpvg_bn_moving_update_multi": ([i, POINTER(vp), POINTER(vp), POINTER(vp), f, f, vp], c_int),
     "hpvg_sn_power_iter": ([vp, i, i, vp, vp, vp, vp, vp], c_int),
     "hpvg_sn_power_iter_multi": ([i, POINTER(vp), POINTER(i), POINTER(i), POINTER(vp), POINTER(vp), POINTER(vp),
                                   POINTER(vp), POINTER(vp), POINTER(vp), POINTER(vp), vp], c_int),

@@ -299,6 +299,17 @@ def bn_train_fused_cl(y_cl, stats, gamma, beta, moving_mean, moving_var, act=ACT
     return out
 
 
+def bn_moving_update_multi(items, stream=None):
+    """items: [(saved (4,64), moving_mean, moving_var)] in the order the forwards ran: moving = 0.9*moving + 0.1*batch."""
+    n = len(items)
+    if n == 0:
+        return
+    VP = ctypes.c_void_p * n
+    check(lib.hpvg_bn_moving_update_multi(n, VP(*[a.ptr for a, _, _ in items]), VP(*[b.ptr for _, b, _ in items]),
+                                          VP(*[c.ptr for _, _, c in items]), BN_EPS, BN_MOMENTUM, _s(stream)),
+          "bn_moving_update_multi")
+
+
 # ------------------------------------------------------------------------------------------------ spectral norm
 def sn_power_iter_multi(layers, stream=None):
     """One launch for all spectrally normalised layers of a network.  layers: list of dicts with device tensors

@@ -13,7 +13,7 @@ import numpy as np
 from . import ops
 from .networks_3d import BnStatsSlab, ConvLayer, Workspace, as5d
 from .ops import ACT_LRELU, ACT_LRELU_MASK, ACT_NONE, ACT_TANH, CONV_64_16, CONV_64_64, CONV_8_64, OUT_BF16_CL, OUT_F32_NCDHW, OUT_F32_RAW
-from .runtime import BF16, F32, U64, Graph, HpvgError, Tensor, device_sync, from_numpy
+from .runtime import BF16, F32, U64, Event, Graph, HpvgError, Tensor, device_sync, from_numpy
 from .utils import images as uimg
 
 import os as _os
@@ -122,8 +122,10 @@ def _unit_affine(stream=None):
     return t
 
 
-def layer_forward_train(layer, x_cl, ws, key, stream=None, slab=None):
-    """Forward of one ConvLayer keeping what its backward needs.  Returns (output, ctx)."""
+def layer_forward_train(layer, x_cl, ws, key, stream=None, slab=None, defer=None):
+    """Forward of one ConvLayer keeping what its backward needs.  Returns (output, ctx).
+    defer: list that receives (saved, moving_mean, moving_var) INSTEAD of updating the moving statistics in the BatchNorm
+    kernel — used when several forwards of the network run concurrently (see GraphedIteration)."""
     N, T, H, W, _ = x_cl.shape
     layer._prepare(True, stream)
     ctx = {"x": x_cl, "layer": layer}
@@ -135,8 +137,13 @@ def layer_forward_train(layer, x_cl, ws, key, stream=None, slab=None):
                           wimgs=layer._wimgs, stats=stats, stream=stream)
         a = ws.get(key + ".a", (N, T, H, W, layer.cout), BF16)
         saved = ws.get(key + ".saved", (4, 64), F32)
-        ops.bn_train_fused_cl(y, stats, layer.p["gamma"], layer.p["beta"], layer.p["moving_mean"],
-                              layer.p["moving_variance"], layer.act, out=a, saved=saved, stream=stream)
+        if defer is None:
+            ops.bn_train_fused_cl(y, stats, layer.p["gamma"], layer.p["beta"], layer.p["moving_mean"],
+                                  layer.p["moving_variance"], layer.act, out=a, saved=saved, stream=stream)
+        else:
+            ops.bn_train_fused_cl(y, stats, layer.p["gamma"], layer.p["beta"], None, None, layer.act, out=a, saved=saved,
+                                  stream=stream)
+            defer.append((saved, layer.p["moving_mean"], layer.p["moving_variance"]))
         layer._aff_eval = None
         ctx.update(y=y, a=a, saved=saved)
         return a, ctx
@@ -283,12 +290,12 @@ def _colsum_wide(g_cl, out, stream=None):
 
 
 # ================================================================================================ block level
-def block_forward_train(block, x_cl, residual, ws, tag, stream=None, x_wide=None, out=None, slab=None):
+def block_forward_train(block, x_cl, residual, ws, tag, stream=None, x_wide=None, out=None, slab=None, defer=None):
     """decoder / body stage in training mode: returns (tanh(block(x) [+ residual]) fp32 ncdhw, ctxs)."""
     ctxs = []
     h = x_cl
     for j, layer in enumerate(block.layers[:-1]):
-        h, c = layer_forward_train(layer, h, ws, "%s.%d" % (tag, j), stream, slab=slab)
+        h, c = layer_forward_train(layer, h, ws, "%s.%d" % (tag, j), stream, slab=slab, defer=defer)
         if j == 0 and x_wide is not None:
             c["x_wide"] = x_wide
         ctxs.append(c)
@@ -373,12 +380,22 @@ class GeneratorTrainer:
                                  stream=stream)
         return up, xin, x_wide
 
+    def prepare_shared(self, stream=None):
+        """Pack the filter banks / bias vectors of every decoder and body layer on `stream`.  Forwards that run
+        concurrently on other streams afterwards only READ these caches."""
+        for block in [self.net.decoder] + list(self.net.body.layers):
+            for layer in block.layers:
+                layer._prepare(True, stream)
+
     def forward(self, video, noise_amp, noise_init=None, is_random=False, noises=None, eps=None, z_pred=None,
-                save_from=None, save_decoder=False, save_encoder=False, stream=None):
+                save_from=None, save_decoder=False, save_encoder=False, stream=None, defer_bn=False):
         """networks_3d.py:406-451 in set_train() mode.  Contexts are kept for the encoder / decoder when asked and
-        for body stages with index >= save_from.  Returns dict(x, vae_out, mu, logvar, ctx...)."""
+        for body stages with index >= save_from.  Returns dict(x, vae_out, mu, logvar, ctx...).
+        defer_bn: do not touch the BatchNorm moving statistics; out["bn_deferred"] lists the pending updates."""
         net, opt, ws = self.net, self.net.opt, self.ws
         out = {"body_ctx": {}, "ups": {}}
+        defer = [] if defer_bn else None
+        out["bn_deferred"] = defer
         mu = logvar = None
         slab = self.slab
         slab.reset(stream)
@@ -415,7 +432,7 @@ class GeneratorTrainer:
             z = noise_init
         N = z.shape[0]
         z_cl = ops.pack_cl(z, out=ws.get("z", (N,) + tuple(z.shape[2:]) + (z.shape[1],), BF16), stream=stream)
-        vae_out, dctx = block_forward_train(net.decoder, z_cl, None, ws, "dec", stream, slab=slab,
+        vae_out, dctx = block_forward_train(net.decoder, z_cl, None, ws, "dec", stream, slab=slab, defer=defer,
                                             out=ws.get("vae_out", (N, opt.nc_im) + tuple(z.shape[2:]), F32))
         out.update(vae_out=vae_out, dec_ctx=dctx, mu=mu, logvar=logvar)
         x = vae_out
@@ -423,7 +440,7 @@ class GeneratorTrainer:
             keep = save_from is not None and idx >= save_from
             up, xin, xw = self._stage_input(x, idx, noise_amp, is_random, noises, stream, wide=keep)
             x, bctx = block_forward_train(net.body[idx], xin, up, ws, "s%d" % idx, stream, x_wide=xw, slab=slab,
-                                          out=ws.get("out%d" % idx, up.shape, F32))
+                                          defer=defer, out=ws.get("out%d" % idx, up.shape, F32))
             if keep:
                 out["body_ctx"][idx] = bctx
             out["ups"][idx] = up
@@ -441,8 +458,17 @@ class GWithLoss:
         self.grads = GradBook()
         self.terms = LossTerms()
 
+    def recon_forward_args(self, isVAE, trainable_body):
+        """Keyword arguments of the reconstruction forward that grad() runs (for callers that run it themselves)."""
+        nb = len(self._netG.body)
+        save_from = 0 if isVAE else (min(trainable_body) if trainable_body else nb)
+        return dict(is_random=False, save_from=save_from, save_encoder=isVAE)
+
     def grad(self, real, real_zero, noise_init, noise_amps, isVAE=False, trainable_body=(), train_codec=False,
-             noises=None, z_pred=None, eps=None, stream=None, finish=True):
+             noises=None, z_pred=None, eps=None, stream=None, finish=True, recon_fw=None, random_x=None,
+             wait_recon=None, wait_random=None):
+        """recon_fw / random_x: results of the reconstruction / random-mode generator forwards when the caller already
+        ran them (possibly on other streams: wait_recon / wait_random are the events to wait for)."""
         """trainable_body: indices of body stages whose parameters are optimised (train_video.py:76-105);
         train_codec: whether encode/decoder are optimised (VAE phase)."""
         net, opt, tr = self._netG, self.opt, self.trainer
@@ -456,8 +482,13 @@ class GWithLoss:
             save_from = 0
         else:
             save_from = min(trainable_body) if trainable_body else nb
-        fw = tr.forward(real_zero, noise_amps, is_random=False, z_pred=z_pred, eps=eps, save_from=save_from,
-                        save_encoder=isVAE, stream=stream)
+        if recon_fw is None:
+            fw = tr.forward(real_zero, noise_amps, is_random=False, z_pred=z_pred, eps=eps, save_from=save_from,
+                            save_encoder=isVAE, stream=stream)
+        else:
+            fw = recon_fw
+            if wait_recon is not None:
+                stream.wait_event(wait_recon)
         x, vae_out = fw["x"], fw["vae_out"]
         ws = tr.ws
         n = x.size
@@ -512,8 +543,12 @@ class GWithLoss:
                                     train_codec, stream)
         else:
             # ---- adversarial term: value only, no gradient reaches G (Q1, losses.py:93-98)
-            fw2 = tr.forward(None, noise_amps, noise_init=noise_init, is_random=True, noises=noises, stream=stream)
-            d_out = self._netD(fw2["x"], stream=stream)
+            if random_x is None:
+                random_x = tr.forward(None, noise_amps, noise_init=noise_init, is_random=True, noises=noises,
+                                      stream=stream)["x"]
+            elif wait_random is not None:
+                stream.wait_event(wait_random)
+            d_out = self._netD(random_x, stream=stream)
             ops.mean(d_out, out=terms.slot(-self.disc_loss_weight), stream=stream)
         return (terms.finish(stream) if finish else terms), g
 
@@ -631,7 +666,7 @@ class DWithLoss:
         ops.conv_wgrad_cl(xi, d_out, g.of(D.tail.p["weight"]), co_n=1, ci_n=64, accumulate=True, stream=stream)
         return gp
 
-    def grad(self, real, noise_init, noise_amps, noises=None, fake=None, stream=None, finish=True):
+    def grad(self, real, noise_init, noise_amps, noises=None, fake=None, stream=None, finish=True, wait_fake=None):
         real, noise_init, fake = as5d(real), as5d(noise_init), as5d(fake)
         if noises is not None:
             noises = {k: as5d(v) for k, v in noises.items()}
@@ -645,6 +680,8 @@ class DWithLoss:
         terms.begin()
         out_r, ctx_r = self._forward(real, "R", stream)
         self._backward_first_order(ctx_r, -1.0 / V, "R", stream)
+        if wait_fake is not None:       # the fake clip was generated on another stream
+            stream.wait_event(wait_fake)
         out_f, ctx_f = self._forward(fake, "F", stream)
         self._backward_first_order(ctx_f, 1.0 / V, "F", stream)
         xhat = ops.lerp(real, fake, self.alpha, out=self.ws.get("xhat", real.shape, F32), stream=stream)
@@ -740,13 +777,18 @@ class GraphedIteration:
         self.g_kwargs = dict(g_kwargs)
         self.graph = None
         self.kernels_per_launch = 0
+        self.side = None
+        if d_step is not None:
+            # third generator pass (the G step's random clip) gets its own workspace / draw counter so that it can run
+            # next to the reconstruction pass
+            self.trainer3 = GeneratorTrainer(g_step.network._netG, device_rng=True, salt=3)
         for cell in (g_step, d_step):
             if cell is None:
                 continue
             if cell.optimizer.d_step is None or not cell.network.trainer.device_rng:
                 raise HpvgError("GraphedIteration needs device_step=True optimisers and device_rng=True loss cells")
 
-    def _body(self, finish):
+    def _body(self, finish, concurrent=False):
         st = self.stream
         # make the iteration CLOSED: packed filter banks / epilogue vectors derived from trainable weights must be
         # rebuilt inside the iteration, never carried over from the previous one through a Python-side cache (a
@@ -755,11 +797,43 @@ class GraphedIteration:
             if cell is not None:
                 for c in cell.cells:
                     c.invalidate()
-        dl = None
-        if self.d_step is not None:
-            dl = self.d_step(self.real, self.noise_init, self.amps, stream=st, finish=finish)
+        if self.d_step is None:      # VAE phase: one forward, nothing to overlap
+            return None, self.g_step(self.real, self.real_zero, self.noise_init, self.amps, stream=st, finish=finish,
+                                     **self.g_kwargs)
+        # GAN phase (train_video.py:175-177).  The three generator forwards of an iteration — the D step's fake clip, the
+        # G step's reconstruction and the G step's random clip — are independent of each other and of the D passes on
+        # the real clip, and their nine coarse scales are far too small to fill 148 SMs.  They are issued on side
+        # streams (captured as parallel branches of the graph) so that their small kernels fill the gaps of the main
+        # stream's finest-scale kernels.  Semantics are unchanged: all three read the same generator weights (G's
+        # update comes last), D passes and both Adam steps stay in order on the main stream, the BatchNorm moving
+        # statistics are updated afterwards, forward by forward, in the reference's order (Q4).
+        d_loss, g_loss = self.d_step.network, self.g_step.network
+        s1, s2, s3 = self.side if concurrent else (st, st, st)
+        g_loss.trainer.prepare_shared(st)
+        fork = Event()
+        fork.record(st)
+        evs = []
+        for s in (s1, s2, s3):
+            if s is not st:
+                s.wait_event(fork)
+        fake = d_loss.trainer.forward(None, self.amps, noise_init=self.noise_init, is_random=True, stream=s1,
+                                      defer_bn=True)
+        rkw = g_loss.recon_forward_args(self.g_kwargs.get("isVAE", False), self.g_kwargs.get("trainable_body", ()))
+        recon = g_loss.trainer.forward(self.real_zero, self.amps, stream=s2, defer_bn=True, **rkw)
+        rand = self.trainer3.forward(None, self.amps, noise_init=self.noise_init, is_random=True, stream=s3,
+                                     defer_bn=True)
+        for s in (s1, s2, s3):
+            ev = Event()
+            ev.record(s)
+            evs.append(ev)
+        dl = self.d_step(self.real, self.noise_init, self.amps, stream=st, finish=finish, fake=fake["x"],
+                         wait_fake=evs[0] if concurrent else None)
         gl = self.g_step(self.real, self.real_zero, self.noise_init, self.amps, stream=st, finish=finish,
-                         **self.g_kwargs)
+                         recon_fw=recon, random_x=rand["x"], wait_recon=evs[1] if concurrent else None,
+                         wait_random=evs[2] if concurrent else None, **self.g_kwargs)
+        for fw in (fake, recon, rand):     # one launch per forward: a layer appears once per launch, order = reference order
+            ops.bn_moving_update_multi(fw["bn_deferred"], stream=st)
+        self._events = [fork] + evs      # keep the events alive as long as the captured graph
         return dl, gl
 
     def warmup(self, n=2):
@@ -770,12 +844,15 @@ class GraphedIteration:
         self.stream.sync()
         return out
 
-    def capture(self):
+    def capture(self, concurrent=True):
         from ._lib import lib
+        from .runtime import Stream
         n0 = lib.hpvg_launch_count()
+        if concurrent and self.d_step is not None and self.side is None:
+            self.side = (Stream(), Stream(), Stream())
         self.graph = Graph(self.stream)
         with self.graph:
-            self._terms = self._body(False)
+            self._terms = self._body(False, concurrent=concurrent and self.d_step is not None)
         self.kernels_per_launch = int(lib.hpvg_launch_count() - n0)
         return self
 
