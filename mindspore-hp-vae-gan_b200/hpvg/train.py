@@ -183,18 +183,28 @@ def sn_tape_prepare(layers, ws, tag, stream=None):
 
 
 def _dgrad_wimgs(layer, stream=None):
-    """Filter banks of the data-gradient convolution of `layer` (roles of Cin/Cout swapped, taps mirrored)."""
+    """Filter banks of the data-gradient convolution of `layer` (roles of Cin/Cout swapped, taps mirrored).  Cached on
+    the layer until its parameters change (ConvLayer.invalidate): the D step back-propagates through every D layer
+    three times per iteration with the same weights."""
+    cached = getattr(layer, "_dgrad_cache", None)
+    if cached is not None and layer._wimgs is not None and cached[0] is layer._wimgs:
+        return cached[1]
     w = layer.p["weight"]
     cin, cout = layer.cin, layer.cout           # forward channels; dgrad maps cout -> cin
     if cin <= 8:                                 # 64 -> (<=4): tail-type kernel
-        return [ops.pack_weights(w, ops.tail_mode(cin), True, cout=cin, stream=stream)]
-    if cout <= 4:                                # (<=4, zero padded to 8) -> 64: head-type kernel
-        return [ops.pack_weights(w, CONV_8_64, True, cin=cout, stream=stream)]
-    imgs = []
-    for ob in range(cin // 64):                  # output blocks of the dgrad = forward input blocks
-        for ib in range(cout // 64):
-            imgs.append(ops.pack_weights(w, CONV_64_64, True, cout_off=ob * 64, cout=64, cin_off=ib * 64, cin=64,
-                                         stream=stream))
+        imgs = [ops.pack_weights(w, ops.tail_mode(cin), True, cout=cin, stream=stream)]
+    elif cout <= 4:                              # (<=4, zero padded to 8) -> 64: head-type kernel
+        imgs = [ops.pack_weights(w, CONV_8_64, True, cin=cout, stream=stream)]
+    else:
+        imgs = []
+        for ob in range(cin // 64):              # output blocks of the dgrad = forward input blocks
+            for ib in range(cout // 64):
+                imgs.append(ops.pack_weights(w, CONV_64_64, True, cout_off=ob * 64, cout=64, cin_off=ib * 64, cin=64,
+                                             stream=stream))
+    # keyed by the identity of the forward filter-bank list: invalidate() drops that list, so a stale entry can never
+    # be returned after a weight update
+    if layer._wimgs is not None:
+        layer._dgrad_cache = (layer._wimgs, imgs)
     return imgs
 
 
