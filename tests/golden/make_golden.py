@@ -36,5 +36,56 @@ def sample_small():
     print("sample_small:", x.shape, float(x.abs().mean()))
 
 
+def ops_small():
+    """Per-operator fixtures (small): resize fwd/bwd + tap tables, BatchNorm(train)+LeakyReLU, one spectral-norm power
+    iteration, KL / MSE, ClipByNorm + Adam — the oracle's outputs on fixed seeded inputs."""
+    rng = np.random.default_rng(123)
+    out = {}
+    # resize (images.py:54-61 / trilinear.py:171-254), align_corners=True, scale 0 -> 1 of the default pyramid
+    x = rng.standard_normal((1, 3, 4, 24, 33)).astype(np.float32)
+    gy = rng.standard_normal((1, 3, 4, 30, 41)).astype(np.float32)
+    out["rs_x"], out["rs_gy"] = x, gy
+    out["rs_y"] = orc.resize_linear_np(x, (4, 30, 41), True)
+    out["rs_gx"] = orc.resize_linear_bwd_np(gy, (4, 24, 33), True)
+    i0, i1, l0, l1 = orc.linear_taps(33, 41, True)
+    out["rs_i0"], out["rs_i1"], out["rs_l0"], out["rs_l1"] = i0, i1, l0, l1
+    # BatchNorm3d (train) + LeakyReLU(0.2) (networks_3d.py:52,20)
+    y = (rng.standard_normal((2, 64, 2, 9, 10)) * 1.5 + 0.2).astype(np.float32)
+    y = torch.from_numpy(y).to(torch.bfloat16).to(torch.float32).numpy()
+    gamma = (1 + 0.1 * rng.standard_normal(64)).astype(np.float32)
+    beta = (0.1 * rng.standard_normal(64)).astype(np.float32)
+    p = {"1.bn2d.gamma": torch.from_numpy(gamma), "1.bn2d.beta": torch.from_numpy(beta),
+         "1.bn2d.moving_mean": torch.zeros(64), "1.bn2d.moving_variance": torch.ones(64)}
+    out["bn_y"], out["bn_gamma"], out["bn_beta"] = y, gamma, beta
+    out["bn_out"] = orc.lrelu(orc.batchnorm(torch.from_numpy(y), p, "1.", True)).numpy()
+    out["bn_mm"], out["bn_mv"] = p["1.bn2d.moving_mean"].numpy(), p["1.bn2d.moving_variance"].numpy()
+    # spectral norm (spectral_norm.py:142-151)
+    w = (rng.standard_normal((64, 3, 3, 3, 3)) * 0.02).astype(np.float32)
+    u = orc._l2normalize_np(rng.standard_normal((64, 1)).astype(np.float32))
+    v = orc._l2normalize_np(rng.standard_normal((81, 1)).astype(np.float32))
+    sigma, un, vn = orc.sn_power_iteration(torch.from_numpy(w), torch.from_numpy(u), torch.from_numpy(v))
+    out["sn_w"], out["sn_u"], out["sn_v"] = w, u, v
+    out["sn_sigma"], out["sn_u1"], out["sn_v1"] = np.float32(sigma), un.numpy(), vn.numpy()
+    # losses (losses.py:5-7, nn.MSELoss)
+    mu = rng.standard_normal((1, 128, 4, 6, 7)).astype(np.float32)
+    lv = (0.3 * rng.standard_normal((1, 128, 4, 6, 7))).astype(np.float32)
+    out["kl_mu"], out["kl_lv"] = mu, lv
+    out["kl"] = np.float32(orc.kl_criterion(torch.from_numpy(mu), torch.from_numpy(lv)))
+    out["mse"] = np.float32(orc.mse(torch.from_numpy(mu), torch.from_numpy(lv)))
+    # ClipByNorm(5) + Adam (optimizers.py:33-43), two steps
+    wt = rng.standard_normal((64, 27)).astype(np.float32)
+    g1 = (rng.standard_normal((64, 27)) * 0.5).astype(np.float32)      # ||g|| > 5: clipped
+    g2 = (rng.standard_normal((64, 27)) * 0.01).astype(np.float32)     # ||g|| < 5: untouched
+    m = np.zeros_like(wt)
+    vv = np.zeros_like(wt)
+    out["ad_w0"], out["ad_g1"], out["ad_g2"] = wt, g1, g2
+    w1, m, vv = orc.adam_step(wt, orc.clip_by_norm(g1, 5.0), m, vv, 1, 5e-4)
+    w2, m, vv = orc.adam_step(w1, orc.clip_by_norm(g2, 5.0), m, vv, 2, 5e-4)
+    out["ad_w1"], out["ad_w2"] = w1, w2
+    np.savez_compressed(os.path.join(HERE, "ops_small.npz"), **out)
+    print("ops_small:", sorted(out))
+
+
 if __name__ == "__main__":
     sample_small()
+    ops_small()

@@ -201,3 +201,28 @@ def test_c_abi_argument_errors():
     assert b"positive" in hpvg.lib.hpvg_last_error()
     assert hpvg.lib.hpvg_conv_wimg_bytes(0) == 2 * 27 * 32 * 128
     assert hpvg.lib.hpvg_conv_wimg_bytes(99) == 0
+
+
+def test_oracle_reproduces_operator_fixtures():
+    """tests/golden/ops_small.npz (made by tests/golden/make_golden.py) pins the per-operator oracle functions against
+    drift: resize fwd/bwd + tap tables, BatchNorm(train), spectral-norm iteration, KL / MSE, ClipByNorm + Adam."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ops_small.npz"))
+    assert np.array_equal(orc.resize_linear_np(g["rs_x"], (4, 30, 41), True), g["rs_y"])
+    assert np.array_equal(orc.resize_linear_bwd_np(g["rs_gy"], (4, 24, 33), True), g["rs_gx"])
+    i0, i1, l0, l1 = orc.linear_taps(33, 41, True)
+    assert np.array_equal(i0, g["rs_i0"]) and np.array_equal(i1, g["rs_i1"])
+    assert np.array_equal(l0.view(np.uint32), g["rs_l0"].view(np.uint32))
+    assert np.array_equal(l1.view(np.uint32), g["rs_l1"].view(np.uint32))
+    p = {"1.bn2d.gamma": torch.from_numpy(g["bn_gamma"]), "1.bn2d.beta": torch.from_numpy(g["bn_beta"]),
+         "1.bn2d.moving_mean": torch.zeros(64), "1.bn2d.moving_variance": torch.ones(64)}
+    out = orc.lrelu(orc.batchnorm(torch.from_numpy(g["bn_y"]), p, "1.", True)).numpy()
+    assert np.allclose(out, g["bn_out"], atol=1e-6) and np.allclose(p["1.bn2d.moving_mean"].numpy(), g["bn_mm"], atol=1e-7)
+    sigma, un, vn = orc.sn_power_iteration(torch.from_numpy(g["sn_w"]), torch.from_numpy(g["sn_u"]),
+                                           torch.from_numpy(g["sn_v"]))
+    assert abs(float(sigma) - float(g["sn_sigma"])) < 1e-7 and np.allclose(un.numpy(), g["sn_u1"], atol=1e-7)
+    assert abs(float(orc.kl_criterion(torch.from_numpy(g["kl_mu"]), torch.from_numpy(g["kl_lv"]))) - float(g["kl"])) < 1e-6
+    m = np.zeros_like(g["ad_w0"])
+    v = np.zeros_like(g["ad_w0"])
+    w1, m, v = orc.adam_step(g["ad_w0"], orc.clip_by_norm(g["ad_g1"], 5.0), m, v, 1, 5e-4)
+    w2, m, v = orc.adam_step(w1, orc.clip_by_norm(g["ad_g2"], 5.0), m, v, 2, 5e-4)
+    assert np.array_equal(w1, g["ad_w1"]) and np.array_equal(w2, g["ad_w2"])

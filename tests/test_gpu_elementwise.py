@@ -224,3 +224,44 @@ def test_adam_clip_multi(hpvg_gpu):
     ops.adam_clip_multi([t[0]], [t[1]], [t[2]], [t[3]], [5e-4], 1, clip=0.0)
     ref, _, _ = orc.adam_step(w0, g0, np.zeros(1000, np.float32), np.zeros(1000, np.float32), 1, 5e-4)
     assert rel_l2(t[0].numpy(), ref) < 1e-6
+
+
+def test_operators_match_committed_golden_fixtures(hpvg_gpu):
+    """The CUDA operators against tests/golden/ops_small.npz (frozen oracle outputs; the fixture travels to the GPU box,
+    /root/reference does not)."""
+    import os
+    hp, ops = hpvg_gpu, hpvg_gpu.ops
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ops_small.npz"))
+    # resize: tables bit-exact, values within 1e-6, adjoint within 1e-6 rel-L2
+    i0, i1, l0, l1 = ops.linear_taps(33, 41, True)
+    assert np.array_equal(i0, g["rs_i0"]) and np.array_equal(i1, g["rs_i1"])
+    assert np.array_equal(l0.view(np.uint32), g["rs_l0"].view(np.uint32))
+    assert np.array_equal(l1.view(np.uint32), g["rs_l1"].view(np.uint32))
+    d0, d1, dl0, dl1 = ops.linear_taps_device(33, 41, True)
+    assert np.array_equal(d0, g["rs_i0"]) and np.array_equal(dl1.view(np.uint32), g["rs_l1"].view(np.uint32))
+    y = ops.resize3d(hp.from_numpy(g["rs_x"]), (4, 30, 41)).numpy()
+    assert np.abs(y - g["rs_y"]).max() <= 1e-6 and float(np.mean(y == g["rs_y"])) > 0.99
+    gx = ops.resize3d_bwd(hp.from_numpy(g["rs_gy"]), (4, 24, 33)).numpy()
+    assert rel_l2(gx, g["rs_gx"]) < 1e-6
+    # BatchNorm (train) + LeakyReLU, moving statistics
+    tmm, tmv = hp.from_numpy(np.zeros(64, np.float32)), hp.from_numpy(np.ones(64, np.float32))
+    x_cl, _ = ops.bn_train_cl(ops.pack_cl(hp.from_numpy(g["bn_y"])), hp.from_numpy(g["bn_gamma"]),
+                              hp.from_numpy(g["bn_beta"]), tmm, tmv)
+    assert rel_l2(ops.unpack_cl(x_cl).numpy(), g["bn_out"]) < 5e-3           # bf16 output
+    assert np.allclose(tmm.numpy(), g["bn_mm"], atol=1e-5) and np.allclose(tmv.numpy(), g["bn_mv"], rtol=1e-4)
+    # spectral norm
+    tu, tv = hp.from_numpy(g["sn_u"]), hp.from_numpy(g["sn_v"])
+    sg = ops.sn_power_iter(hp.from_numpy(g["sn_w"]), tu, tv).numpy()
+    assert abs(sg[0] - float(g["sn_sigma"])) / float(g["sn_sigma"]) < 1e-5
+    assert np.allclose(tu.numpy(), g["sn_u1"], atol=1e-5) and np.allclose(tv.numpy(), g["sn_v1"], atol=1e-5)
+    # losses
+    mu, lv = hp.from_numpy(g["kl_mu"]), hp.from_numpy(g["kl_lv"])
+    assert abs(ops.kl_criterion(mu, lv).numpy()[0] - float(g["kl"])) < 1e-5 * max(1.0, abs(float(g["kl"])))
+    assert abs(ops.mse(mu, lv).numpy()[0] - float(g["mse"])) < 1e-5 * float(g["mse"])
+    # ClipByNorm + Adam, two steps (second one unclipped)
+    w = hp.from_numpy(g["ad_w0"])
+    m, v = hp.Tensor(w.shape, hp.F32).zero_(), hp.Tensor(w.shape, hp.F32).zero_()
+    ops.adam_clip_multi([w], [hp.from_numpy(g["ad_g1"])], [m], [v], [5e-4], 1, clip=5.0)
+    assert np.allclose(w.numpy(), g["ad_w1"], atol=1e-6)
+    ops.adam_clip_multi([w], [hp.from_numpy(g["ad_g2"])], [m], [v], [5e-4], 2, clip=5.0)
+    assert np.allclose(w.numpy(), g["ad_w2"], atol=1e-6)
