@@ -464,26 +464,41 @@ __global__ void upsample_noise_pack_tiled_kernel(const float* __restrict__ x, in
 constexpr int CW_MAX_TI = 8;
 constexpr int CW_THREADS = 256;
 
+// T-axis walk of one launch, built on the HOST with linear_tap() (bit-identical to the device function, §3.4 of
+// DESIGN.md) and passed as a kernel parameter: the constant bank serves block-uniform reads for free, so the kernels
+// carry no shared-memory tap table, no barrier and no per-output tap arithmetic.
+constexpr int CW_MAX_PER_FRAME = 4;
+struct TWalk {
+  // outputs whose lower tap is source frame f, in order: lambda pairs at COMPILE-TIME constant-bank offsets (the
+  // unrolled walk reads them as immediate c[][] operands — no table load, no loop counter, no index arithmetic)
+  float l0[CW_MAX_TI][CW_MAX_PER_FRAME], l1[CW_MAX_TI][CW_MAX_PER_FRAME];
+  int n[CW_MAX_TI];            // how many outputs frame f feeds as the lower tap (<= CW_MAX_PER_FRAME)
+  unsigned col_magic;          // ceil(2^32 / Wo): ho = umulhi(col, magic), exact while Ho*Wo*Wo < 2^32 (0: Wo == 1)
+};
+
 template <int C, int TI>
 __device__ __forceinline__ void colwalk_load(const float* __restrict__ xs /* block-uniform slice base */, unsigned spi,
                                              const ResizeGeom& g, const Tap& th, const Tap& tw,
                                              float (&hv)[C][TI + 1]) {
-  // four running pointers (one per corner) advanced by one frame: 2 integer ops per load instead of index math
-  const unsigned fsz = g.Hi * g.Wi;
+  // two row pointers per channel; the W neighbour is the +4-byte immediate of the same address register (the last
+  // column, where i1 == i0, re-uses its own value instead), frames are one multiply-add-wide away: ~1 integer
+  // instruction per load instead of 4
+  const unsigned fsz4 = g.Hi * g.Wi * 4u;   // frame stride in bytes (< 2^31, checked by the launcher)
+  const unsigned dw = (tw.i1 - tw.i0) * 4u;  // 0 on the last column (i1 == i0), else 4 bytes
 #pragma unroll
   for (int c = 0; c < C; ++c) {
-    const float* p00 = xs + (c * spi + th.i0 * g.Wi + tw.i0);
-    const float* p01 = xs + (c * spi + th.i0 * g.Wi + tw.i1);
-    const float* p10 = xs + (c * spi + th.i1 * g.Wi + tw.i0);
-    const float* p11 = xs + (c * spi + th.i1 * g.Wi + tw.i1);
+    const char* p00 = reinterpret_cast<const char*>(xs + (c * spi + th.i0 * g.Wi + tw.i0));
+    const char* p10 = reinterpret_cast<const char*>(xs + (c * spi + th.i1 * g.Wi + tw.i0));
+    const char* p01 = p00 + dw;
+    const char* p11 = p10 + dw;
     float v[TI][4];
 #pragma unroll
-    for (int f = 0; f < TI; ++f) {
-      v[f][0] = __ldg(p00);
-      v[f][1] = __ldg(p01);
-      v[f][2] = __ldg(p10);
-      v[f][3] = __ldg(p11);
-      p00 += fsz; p01 += fsz; p10 += fsz; p11 += fsz;
+    for (int f = 0; f < TI; ++f) {   // all 4*TI loads are independent: issued back to back, one round trip
+      const unsigned long long off = static_cast<unsigned long long>(f) * fsz4;
+      v[f][0] = __ldg(reinterpret_cast<const float*>(p00 + off));
+      v[f][1] = __ldg(reinterpret_cast<const float*>(p01 + off));
+      v[f][2] = __ldg(reinterpret_cast<const float*>(p10 + off));
+      v[f][3] = __ldg(reinterpret_cast<const float*>(p11 + off));
     }
 #pragma unroll
     for (int f = 0; f < TI; ++f) {
@@ -491,39 +506,42 @@ __device__ __forceinline__ void colwalk_load(const float* __restrict__ xs /* blo
       const float a1 = lerp_rn(tw.l0, v[f][2], tw.l1, v[f][3]);
       hv[c][f] = lerp_rn(th.l0, a0, th.l1, a1);
     }
-    hv[c][TI] = 0.f;
+    hv[c][TI] = hv[c][TI - 1];   // i1 == i0 on the last source frame
   }
+}
+
+__device__ __forceinline__ void colwalk_split(unsigned col, const ResizeGeom& g, const TWalk& w, unsigned& ho,
+                                              unsigned& wo) {
+  ho = w.col_magic ? __umulhi(col, w.col_magic) : col;
+  wo = col - ho * g.Wo;
 }
 
 template <int TI>
 __global__ void __launch_bounds__(CW_THREADS)
-resize3d_fwd_colwalk_kernel(const float* __restrict__ x, const ResizeGeom g, float* __restrict__ y) {
-  __shared__ TapRow ttab[64];
-  for (int i = threadIdx.x; i < g.To; i += blockDim.x) {
-    const Tap t = linear_tap(i, TI, g.st, g.align);
-    ttab[i] = TapRow{t.i0, t.i1, t.l0, t.l1};
-  }
-  __syncthreads();
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= g.Ho * g.Wo) return;
-  const int ho = col / g.Wo, wo = col - ho * g.Wo;
+resize3d_fwd_colwalk_kernel(const float* __restrict__ x, const ResizeGeom g, const __grid_constant__ TWalk w,
+                            float* __restrict__ y) {
+  const unsigned plane = g.Ho * g.Wo;
+  const unsigned col = blockIdx.x * CW_THREADS + threadIdx.x;
+  if (col >= plane) return;
+  unsigned ho, wo;
+  colwalk_split(col, g, w, ho, wo);
   const long long nc = blockIdx.y;
   const Tap th = linear_tap(ho, g.Hi, g.sh, g.align), tw = linear_tap(wo, g.Wi, g.sw, g.align);
   const unsigned spi = TI * g.Hi * g.Wi;
   float hv[1][TI + 1];
   colwalk_load<1, TI>(x + nc * spi, spi, g, th, tw, hv);
-  const unsigned plane = g.Ho * g.Wo;
-  float* __restrict__ dst = y + nc * g.To * plane + col;
-  const int To = g.To;
-  int to = 0;
+  char* __restrict__ dst = reinterpret_cast<char*>(y + (nc * g.To * plane + col));
+  const unsigned plane4 = plane * 4u;
+  unsigned to = 0;                       // block-uniform: lives in a uniform register
 #pragma unroll
   for (int f = 0; f < TI; ++f) {
-    while (to < To) {
-      const TapRow tt = ttab[to];
-      if (tt.o0 != f) break;
-      const float hi = (tt.o1 == f) ? hv[0][f] : hv[0][f + 1];
-      *dst = lerp_rn(tt.l0, hv[0][f], tt.l1, hi);
-      dst += plane;
+    const int n = w.n[f];
+    const float a = hv[0][f], b = hv[0][f + 1];
+#pragma unroll
+    for (int k = 0; k < CW_MAX_PER_FRAME; ++k) {
+      if (k >= n) break;
+      *reinterpret_cast<float*>(dst + static_cast<unsigned long long>(to) * plane4) =
+          lerp_rn(w.l0[f][k], a, w.l1[f][k], b);
       ++to;
     }
   }
@@ -531,58 +549,59 @@ resize3d_fwd_colwalk_kernel(const float* __restrict__ x, const ResizeGeom g, flo
 
 template <int C, int TI>
 __global__ void __launch_bounds__(CW_THREADS)
-upsample_noise_pack_colwalk_kernel(const float* __restrict__ x, const ResizeGeom g, const float* __restrict__ noise,
-                                   float amp, unsigned long long seed, unsigned long long sample_base,
+upsample_noise_pack_colwalk_kernel(const float* __restrict__ x, const ResizeGeom g, const __grid_constant__ TWalk w,
+                                   const float* __restrict__ noise, float amp, unsigned long long seed,
+                                   unsigned long long sample_base,
                                    const unsigned long long* __restrict__ d_sample_offset, float* __restrict__ up,
                                    __nv_bfloat16* __restrict__ xin) {
-  __shared__ TapRow ttab[64];
-  for (int i = threadIdx.x; i < g.To; i += blockDim.x) {
-    const Tap t = linear_tap(i, TI, g.st, g.align);
-    ttab[i] = TapRow{t.i0, t.i1, t.l0, t.l1};
-  }
-  __syncthreads();
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= g.Ho * g.Wo) return;
+  const unsigned plane = g.Ho * g.Wo;
+  const unsigned col = blockIdx.x * CW_THREADS + threadIdx.x;
+  if (col >= plane) return;
   if (d_sample_offset) sample_base += *d_sample_offset;
-  const int ho = col / g.Wo, wo = col - ho * g.Wo;
+  unsigned ho, wo;
+  colwalk_split(col, g, w, ho, wo);
   const long long n = blockIdx.y;
   const Tap th = linear_tap(ho, g.Hi, g.sh, g.align), tw = linear_tap(wo, g.Wi, g.sw, g.align);
   const unsigned spi = TI * g.Hi * g.Wi;
-  const int plane = g.Ho * g.Wo;
-  const long long spo = static_cast<long long>(g.To) * plane;
+  const unsigned spo = g.To * plane;                 // C * spo < 2^31 (checked by the launcher)
   float hv[C][TI + 1];
   colwalk_load<C, TI>(x + n * C * static_cast<long long>(spi), spi, g, th, tw, hv);
   const unsigned long long sample = sample_base + static_cast<unsigned long long>(n);
-  long long sidx = col;               // spatial index inside the sample
-  const int To = g.To;
-  int to = 0;
+  const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  const bool draw = !noise && seed != 0ull;
+  unsigned sidx = col;                                 // spatial index inside the sample
+  float* __restrict__ up_p = up + (n * C * spo + col);
+  const float* __restrict__ nz_p = noise ? noise + (n * C * spo + col) : nullptr;
+  uint4* __restrict__ xin_p = reinterpret_cast<uint4*>(xin) + (n * spo + col);
 #pragma unroll
   for (int f = 0; f < TI; ++f) {
-    while (to < To) {
-      const TapRow tt = ttab[to];
-      if (tt.o0 != f) break;
+    const int nf = w.n[f];
+#pragma unroll
+    for (int k = 0; k < CW_MAX_PER_FRAME; ++k) {
+      if (k >= nf) break;
+      const float l0 = w.l0[f][k], l1 = w.l1[f][k];
       float z[4] = {0.f, 0.f, 0.f, 0.f};
-      if (!noise && seed != 0ull) {
-        const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(sidx), static_cast<uint32_t>(sidx >> 32),
-                                                   static_cast<uint32_t>(sample), static_cast<uint32_t>(sample >> 32)),
-                                        make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+      if (draw) {
+        const uint4 rnd = philox4x32_10(make_uint4(sidx, 0u, static_cast<uint32_t>(sample),
+                                                   static_cast<uint32_t>(sample >> 32)), key);
         box_muller(rnd.x, rnd.y, z[0], z[1]);
         box_muller(rnd.z, rnd.w, z[2], z[3]);
+      } else if (nz_p) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) z[c] = __ldg(nz_p + c * spo);
+        nz_p += plane;
       }
       float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const float hi = (tt.o1 == f) ? hv[c][f] : hv[c][f + 1];
-        const float u = lerp_rn(tt.l0, hv[c][f], tt.l1, hi);
-        const long long o = (n * C + c) * spo + sidx;
-        up[o] = u;
-        const float nz = noise ? noise[o] : z[c];
-        v[c] = fmaf(nz, amp, u);
+        const float u = lerp_rn(l0, hv[c][f], l1, hv[c][f + 1]);
+        up_p[c * spo] = u;
+        v[c] = fmaf(z[c], amp, u);
       }
-      *reinterpret_cast<uint4*>(xin + (n * spo + sidx) * 8) =
-          make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+      *xin_p = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+      up_p += plane;
+      xin_p += plane;
       sidx += plane;
-      ++to;
     }
   }
 }
@@ -1591,10 +1610,32 @@ static void plan_threads(int Wo, int max_ny, TiledGeom* tg) {
   if (ny > max_ny) ny = max_ny;
   tg->ny = ny;
 }
-// the register-only forward needs Ti <= 8 frames, To <= 64 taps, int-sized slices; i0 must be non-decreasing (always)
-static bool colwalk_ok(const ResizeGeom& g, long long slices) {
+// the register-only forward needs Ti <= 8 frames, To <= 64 taps, int-sized slices, an exact magic division of the
+// column index; i0 must be non-decreasing along T (always true for a linear map) — make_twalk() verifies it
+static bool colwalk_ok(const ResizeGeom& g, long long slices, int C = 1) {
   return g.Ti <= CW_MAX_TI && g.To <= 64 && slices <= 65535 &&
-         static_cast<long long>(g.To) * g.Ho * g.Wo < (1LL << 31) && static_cast<long long>(g.Ti) * g.Hi * g.Wi < (1LL << 31);
+         static_cast<long long>(C) * g.To * g.Ho * g.Wo < (1LL << 31) &&
+         static_cast<long long>(C) * g.Ti * g.Hi * g.Wi < (1LL << 31) &&
+         static_cast<long long>(g.Ho) * g.Wo * g.Wo < (1LL << 32);
+}
+static bool make_twalk(const ResizeGeom& g, TWalk* w) {
+  int to = 0;
+  for (int f = 0; f < CW_MAX_TI; ++f) {
+    int k = 0;
+    for (int j = 0; j < CW_MAX_PER_FRAME; ++j) w->l0[f][j] = w->l1[f][j] = 0.f;
+    while (f < g.Ti && to < g.To) {
+      const Tap t = linear_tap(to, g.Ti, g.st, g.align);
+      if (t.i0 != f) break;
+      if (k == CW_MAX_PER_FRAME) return false;     // > 4x temporal up-sampling: the tiled kernel handles it
+      w->l0[f][k] = t.l0;
+      w->l1[f][k] = t.l1;
+      ++k;
+      ++to;
+    }
+    w->n[f] = k;
+  }
+  w->col_magic = g.Wo > 1 ? static_cast<unsigned>(((1ULL << 32) + g.Wo - 1) / g.Wo) : 0u;
+  return to == g.To;
 }
 static bool plan_fwd_tiles(const ResizeGeom& g, TiledGeom* tg, size_t* smem) {
   for (int band = 16; band >= 1; --band) {
@@ -1638,9 +1679,10 @@ cudaError_t ew_resize3d_fwd(const float* x, long long NC, int Ti, int Hi, int Wi
   const ResizeGeom g = make_geom(Ti, Hi, Wi, To, Ho, Wo, align);
   TiledGeom tg;
   size_t smem;
-  if (colwalk_ok(g, NC)) {
+  TWalk tw;
+  if (colwalk_ok(g, NC) && make_twalk(g, &tw)) {
     const dim3 grid((Ho * Wo + CW_THREADS - 1) / CW_THREADS, static_cast<unsigned>(NC));
-#define HPVG_CWF(T_) resize3d_fwd_colwalk_kernel<T_><<<grid, CW_THREADS, 0, st>>>(x, g, y)
+#define HPVG_CWF(T_) resize3d_fwd_colwalk_kernel<T_><<<grid, CW_THREADS, 0, st>>>(x, g, tw, y)
     switch (Ti) {   // the frame count is a template parameter: no per-frame predicates in the unrolled body
       case 1: HPVG_CWF(1); break;
       case 2: HPVG_CWF(2); break;
@@ -1698,10 +1740,11 @@ cudaError_t ew_upsample_noise_pack(const float* x, int N, int C, int Ti, int Hi,
   const ResizeGeom g = make_geom(Ti, Hi, Wi, To, Ho, Wo, 1);
   TiledGeom tg;
   size_t smem;
-  if (colwalk_ok(g, N) && (C == 1 || C == 3) && static_cast<long long>(C) * Ti * Hi * Wi < (1LL << 31)) {
+  TWalk tw;
+  if ((C == 1 || C == 3) && colwalk_ok(g, N, C) && make_twalk(g, &tw)) {
     const dim3 grid((Ho * Wo + CW_THREADS - 1) / CW_THREADS, N);
 #define HPVG_CW(C_, T_) upsample_noise_pack_colwalk_kernel<C_, T_><<<grid, CW_THREADS, 0, st>>>( \
-      x, g, noise, amp, seed, sample_base, d_sample_offset, up, xin)
+      x, g, tw, noise, amp, seed, sample_base, d_sample_offset, up, xin)
 #define HPVG_CWT(C_)                       \
     switch (Ti) {                            \
       case 1: HPVG_CW(C_, 1); break;         \
