@@ -241,12 +241,16 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 __device__ __forceinline__ float u01(uint32_t x) { return (static_cast<float>(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
-// Box-Muller on the SFU fast paths (__logf / __sincosf: abs error ~1e-6, irrelevant for a noise source, and 5x cheaper
-// than the range-reduced library versions — the fused block-input kernel is ALU-bound by this)
+// Box-Muller straight on the SFU (MUFU.LG2 / SQRT / SIN / COS: abs error ~1e-6, irrelevant for a noise source).  The
+// IEEE sqrtf() alone costs ~10 instructions plus a divergent slow-path guard, and the fused block-input kernel is
+// instruction-issue bound by exactly this code.
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
-  const float r = sqrtf(-2.0f * __logf(u01(a)));
-  float s, c;
-  __sincosf(6.283185307179586f * u01(b), &s, &c);
+  float lg, r, s, c;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u01(a)));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(lg * -1.3862943611198906f));   // sqrt(-2 ln u)
+  const float ang = 6.283185307179586f * u01(b);
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(ang));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(ang));
   z0 = r * c;
   z1 = r * s;
 }
@@ -616,7 +620,7 @@ struct InvTap {
   int lo, n;        // contributing outputs [lo, lo+n)
   float c[4];       // their coefficients
 };
-__device__ __forceinline__ int first_output_at_or_above(int i, int n_in, int n_out, float scale, int align) {
+__host__ __device__ __forceinline__ int first_output_at_or_above(int i, int n_in, int n_out, float scale, int align) {
   // min{o : i0(o) >= i}; i0 is non-decreasing in o
   if (i <= 0) return 0;
   if (scale <= 0.f) return n_out;
@@ -626,12 +630,14 @@ __device__ __forceinline__ int first_output_at_or_above(int i, int n_in, int n_o
   while (o < n_out && linear_tap(o, n_in, scale, align).i0 < i) ++o;
   return o;
 }
-__device__ __forceinline__ InvTap make_inv_tap(int i, int n_in, int n_out, float scale, int align) {
+__host__ __device__ __forceinline__ InvTap make_inv_tap(int i, int n_in, int n_out, float scale, int align) {
   InvTap e;
   e.lo = first_output_at_or_above(i - 1, n_in, n_out, scale, align);
   const int hi = (i + 1 > n_in - 1 + 1) ? n_out : first_output_at_or_above(i + 1, n_in, n_out, scale, align);
   e.n = hi - e.lo;
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
   for (int k = 0; k < 4; ++k) {
     e.c[k] = 0.f;
     if (k < e.n) {
@@ -643,63 +649,88 @@ __device__ __forceinline__ InvTap make_inv_tap(int i, int n_in, int n_out, float
 }
 
 constexpr int BW_TX = 32, BW_TY = 8;
-template <int NH, int NW>   // compile-time bounds on the contributing rows / columns (floor(2/scale) + 1)
+// The block first stages the gy window of its 32 x 8 source tile for ALL output frames in shared memory (coalesced
+// row segments, every load independent: the register-only version spent 12 of 16 cycles per instruction waiting on
+// its serial per-frame gathers), then each thread reduces its <= NH x NW window per frame out of shared memory.
+struct BwdWin {
+  int rows, cols;     // window extent (max over blocks, computed on the host with the same tap functions)
+};
+template <int NH, int NW, int TI>   // compile-time bounds on the contributing rows / columns (floor(2/scale) + 1), frames
 __global__ void __launch_bounds__(BW_TX * BW_TY)
-resize3d_bwd_colwalk_kernel(const float* __restrict__ gy, const ResizeGeom g, float* __restrict__ gx) {
-  __shared__ TapRow ttab[64];
+resize3d_bwd_colwalk_kernel(const float* __restrict__ gy, const ResizeGeom g, const __grid_constant__ TWalk w,
+                            const BwdWin win, float* __restrict__ gx) {
+  extern __shared__ __align__(16) float bw_sm[];          // [To][win.rows][win.cols]
   __shared__ InvTap htab[BW_TY], wtab[BW_TX];
   const int tid = threadIdx.y * BW_TX + threadIdx.x;
   const int hs0 = blockIdx.y * BW_TY, wi0 = blockIdx.x * BW_TX;
-  for (int i = tid; i < g.To; i += BW_TX * BW_TY) {
-    const Tap t = linear_tap(i, g.Ti, g.st, g.align);
-    ttab[i] = TapRow{t.i0, t.i1, t.l0, t.l1};
-  }
   if (tid < BW_TY) {
-    if (hs0 + tid < g.Hi) htab[tid] = make_inv_tap(hs0 + tid, g.Hi, g.Ho, g.sh, g.align);
+    htab[tid] = make_inv_tap(min(hs0 + tid, g.Hi - 1), g.Hi, g.Ho, g.sh, g.align);
   } else if (tid >= 32 && tid < 32 + BW_TX) {
     const int j = tid - 32;
-    if (wi0 + j < g.Wi) wtab[j] = make_inv_tap(wi0 + j, g.Wi, g.Wo, g.sw, g.align);
+    wtab[j] = make_inv_tap(min(wi0 + j, g.Wi - 1), g.Wi, g.Wo, g.sw, g.align);
+  }
+  __syncthreads();
+  const long long nc = blockIdx.z;
+  const unsigned plane_o = g.Ho * g.Wo, plane_i = g.Hi * g.Wi;
+  const int ho_lo = htab[0].lo, wo_lo = wtab[0].lo;
+  const int rows = min(htab[BW_TY - 1].lo + htab[BW_TY - 1].n, g.Ho) - ho_lo;      // <= win.rows
+  const int cols = min(wtab[BW_TX - 1].lo + wtab[BW_TX - 1].n, g.Wo) - wo_lo;      // <= win.cols
+  {
+    const float* src = gy + (nc * g.To * plane_o + ho_lo * g.Wo + wo_lo);
+    const int warp = tid >> 5, lane = tid & 31;
+    const int n_rows = g.To * rows;
+    int to = 0, r = warp;                                  // (frame, row) of the row segment this warp copies next
+    while (r >= rows) { r -= rows; ++to; }
+    for (int i = warp; i < n_rows; i += BW_TY) {
+      const float* srow = src + (static_cast<unsigned>(to) * plane_o + r * g.Wo);
+      float* drow = bw_sm + (to * win.rows + r) * win.cols;
+      // 4-byte cp.async: global -> shared without a register round trip, so every copy of the tile is in flight at
+      // once (a load/store loop serialises on each store's scoreboard wait)
+      for (int c = lane; c < cols; c += 32)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(
+                         __cvta_generic_to_shared(drow + c))), "l"(srow + c) : "memory");
+      r += BW_TY;
+      while (r >= rows) { r -= rows; ++to; }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   }
   __syncthreads();
   const int hs = hs0 + threadIdx.y, wi = wi0 + threadIdx.x;
   if (hs >= g.Hi || wi >= g.Wi) return;
   const InvTap eh = htab[threadIdx.y], ew = wtab[threadIdx.x];
-  const long long nc = blockIdx.z;
-  const int plane_o = g.Ho * g.Wo, plane_i = g.Hi * g.Wi;
-  const float* src = gy + nc * g.To * plane_o + eh.lo * g.Wo + ew.lo;
-  float* dst = gx + nc * g.Ti * plane_i + hs * g.Wi + wi;
-  int f_lo = 0;
-  float acc_lo = 0.f, acc_hi = 0.f;
-  for (int to = 0; to < g.To; ++to, src += plane_o) {
-    float v[NH][NW];
+  const float* wp = bw_sm + (eh.lo - ho_lo) * win.cols + (ew.lo - wo_lo);
+  int off[NH][NW];    // positions past the contributing range alias (0, .) / (., 0) and meet a zero coefficient
 #pragma unroll
-    for (int k = 0; k < NH; ++k)
+  for (int k = 0; k < NH; ++k)
 #pragma unroll
-      for (int j = 0; j < NW; ++j) v[k][j] = (k < eh.n && j < ew.n) ? __ldg(src + k * g.Wo + j) : 0.f;
-    float s = 0.f;
+    for (int j = 0; j < NW; ++j) off[k][j] = (k < eh.n ? k : 0) * win.cols + (j < ew.n ? j : 0);
+  const int fstride = win.rows * win.cols;
+  float acc[TI];
 #pragma unroll
-    for (int k = 0; k < NH; ++k) {
-      float r = 0.f;
+  for (int f = 0; f < TI; ++f) acc[f] = 0.f;
 #pragma unroll
-      for (int j = 0; j < NW; ++j) r = fmaf(ew.c[j], v[k][j], r);
-      s = fmaf(eh.c[k], r, s);
+  for (int f = 0; f < TI; ++f) {
+    const int n = w.n[f];
+#pragma unroll
+    for (int q = 0; q < CW_MAX_PER_FRAME; ++q) {
+      if (q >= n) break;
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < NH; ++k) {
+        float r = 0.f;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) r = fmaf(ew.c[j], wp[off[k][j]], r);
+        s = fmaf(eh.c[k], r, s);
+      }
+      wp += fstride;
+      acc[f] = fmaf(w.l0[f][q], s, acc[f]);
+      if (f == TI - 1) acc[f] = fmaf(w.l1[f][q], s, acc[f]);
+      else acc[f + 1] = fmaf(w.l1[f][q], s, acc[f + 1]);
     }
-    const TapRow tt = ttab[to];
-    while (f_lo < tt.o0) {          // frames below i0(to) are complete (i0 is non-decreasing in `to`)
-      dst[f_lo * plane_i] = acc_lo;
-      acc_lo = acc_hi;
-      acc_hi = 0.f;
-      ++f_lo;
-    }
-    acc_lo = fmaf(tt.l0, s, acc_lo);
-    if (tt.o1 == f_lo) acc_lo = fmaf(tt.l1, s, acc_lo);
-    else acc_hi = fmaf(tt.l1, s, acc_hi);
   }
-  for (; f_lo < g.Ti; ++f_lo) {
-    dst[f_lo * plane_i] = acc_lo;
-    acc_lo = acc_hi;
-    acc_hi = 0.f;
-  }
+  float* dst = gx + (nc * TI * plane_i + hs * g.Wi + wi);
+#pragma unroll
+  for (int f = 0; f < TI; ++f) dst[static_cast<size_t>(f) * plane_i] = acc[f];
 }
 
 // backward: a thread owns (source row hs, column wo) and walks along T_out with register accumulators for the (at
@@ -1706,6 +1737,26 @@ cudaError_t ew_resize3d_fwd(const float* x, long long NC, int Ti, int Hi, int Wi
   LAUNCH_CHECK();
   return cudaSuccess;
 }
+// window extent of a backward block (max over block rows / columns), from the same inverse-tap function the kernel uses
+static bool plan_bwd_window(const ResizeGeom& g, BwdWin* win, size_t* bytes) {
+  win->rows = win->cols = 1;
+  for (int h0 = 0; h0 < g.Hi; h0 += BW_TY) {
+    const int last = (h0 + BW_TY - 1 < g.Hi) ? h0 + BW_TY - 1 : g.Hi - 1;
+    const InvTap a = make_inv_tap(h0, g.Hi, g.Ho, g.sh, g.align), b = make_inv_tap(last, g.Hi, g.Ho, g.sh, g.align);
+    const int hi = (b.lo + b.n < g.Ho) ? b.lo + b.n : g.Ho;
+    if (hi - a.lo > win->rows) win->rows = hi - a.lo;
+  }
+  for (int w0 = 0; w0 < g.Wi; w0 += BW_TX) {
+    const int last = (w0 + BW_TX - 1 < g.Wi) ? w0 + BW_TX - 1 : g.Wi - 1;
+    const InvTap a = make_inv_tap(w0, g.Wi, g.Wo, g.sw, g.align), b = make_inv_tap(last, g.Wi, g.Wo, g.sw, g.align);
+    const int hi = (b.lo + b.n < g.Wo) ? b.lo + b.n : g.Wo;
+    if (hi - a.lo > win->cols) win->cols = hi - a.lo;
+  }
+  win->cols |= 1;   // odd row pitch: the ~1.26-strided window reads spread over the banks
+  *bytes = static_cast<size_t>(g.To) * win->rows * win->cols * sizeof(float);
+  return *bytes <= 100 * 1024;
+}
+
 cudaError_t ew_resize3d_bwd(const float* gy, long long NC, int To, int Ho, int Wo, float* gx, int Ti, int Hi, int Wi,
                             int align, cudaStream_t st) {
   const ResizeGeom g = make_geom(Ti, Hi, Wi, To, Ho, Wo, align);
@@ -1714,13 +1765,40 @@ cudaError_t ew_resize3d_bwd(const float* gy, long long NC, int To, int Ho, int W
   // register-only adjoint: needs <= 4 contributing outputs per source row / column (floor(2/s) + 1 <= 4), To <= 64
   const bool few_h = (Ho == 1) || (g.sh > 0.f && static_cast<int>(2.0f / g.sh) + 1 <= 4);
   const bool few_w = (Wo == 1) || (g.sw > 0.f && static_cast<int>(2.0f / g.sw) + 1 <= 4);
-  if (few_h && few_w && To <= 64 && NC <= 65535 && static_cast<long long>(To) * Ho * Wo < (1LL << 31) &&
-      static_cast<long long>(Ti) * Hi * Wi < (1LL << 31)) {
+  TWalk tw;
+  BwdWin win;
+  size_t bw_smem = 0;
+  if (few_h && few_w && Ti <= CW_MAX_TI && To <= 64 && NC <= 65535 &&
+      static_cast<long long>(To) * Ho * Wo < (1LL << 29) && static_cast<long long>(Ti) * Hi * Wi < (1LL << 31) &&
+      make_twalk(g, &tw) && plan_bwd_window(g, &win, &bw_smem)) {
     const dim3 grid((Wi + BW_TX - 1) / BW_TX, (Hi + BW_TY - 1) / BW_TY, static_cast<unsigned>(NC));
     const dim3 block(BW_TX, BW_TY);
     const int nh = (Ho == 1) ? 1 : static_cast<int>(2.0f / g.sh) + 1, nw = (Wo == 1) ? 1 : static_cast<int>(2.0f / g.sw) + 1;
-    if (nh <= 3 && nw <= 3) resize3d_bwd_colwalk_kernel<3, 3><<<grid, block, 0, st>>>(gy, g, gx);
-    else resize3d_bwd_colwalk_kernel<4, 4><<<grid, block, 0, st>>>(gy, g, gx);
+#define HPVG_BW(H_, W_, T_)                                                                                        \
+  {                                                                                                                \
+    static bool ok_ = false;                                                                                       \
+    if (!ok_) {                                                                                                    \
+      cudaError_t e_ = cudaFuncSetAttribute(resize3d_bwd_colwalk_kernel<H_, W_, T_>,                               \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);              \
+      if (e_ != cudaSuccess) return e_;                                                                            \
+      ok_ = true;                                                                                                  \
+    }                                                                                                              \
+    resize3d_bwd_colwalk_kernel<H_, W_, T_><<<grid, block, bw_smem, st>>>(gy, g, tw, win, gx);                     \
+  }
+#define HPVG_BWT(H_, W_)                    \
+    switch (Ti) {                             \
+      case 1: HPVG_BW(H_, W_, 1); break;      \
+      case 2: HPVG_BW(H_, W_, 2); break;      \
+      case 3: HPVG_BW(H_, W_, 3); break;      \
+      case 4: HPVG_BW(H_, W_, 4); break;      \
+      case 5: HPVG_BW(H_, W_, 5); break;      \
+      case 6: HPVG_BW(H_, W_, 6); break;      \
+      case 7: HPVG_BW(H_, W_, 7); break;      \
+      default: HPVG_BW(H_, W_, 8); break;     \
+    }
+    if (nh <= 3 && nw <= 3) { HPVG_BWT(3, 3) } else { HPVG_BWT(4, 4) }
+#undef HPVG_BWT
+#undef HPVG_BW
   } else if (NC <= 65535 && plan_bwd_tiles(g, &tg, &smem)) {
     static bool ok = false;
     cudaError_t e = rs_allow_smem(resize3d_bwd_tiled_kernel, &ok);
