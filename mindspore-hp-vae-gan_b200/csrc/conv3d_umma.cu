@@ -79,6 +79,26 @@ __device__ __forceinline__ Unit decode_unit(int u, const ConvParams& p, uint32_t
   return r;
 }
 
+// Work partition: the (unit, output plane) sequence is cut into n_pairs contiguous ranges of equal length (+-1), so a
+// CTA pair owns a partial strip at either end of its range and whole strips in between.  Splitting strips along T
+// costs at most two re-loaded halo planes per pair and removes the wave quantisation of whole-strip scheduling
+// (198 strips on 74 pairs: 3 waves for 2.68 waves of work at the finest scale, batch 1).
+struct Item {
+  int u, t0, t1;   // strip, output planes [t0, t1)
+};
+__device__ __forceinline__ void work_range(int pair, int n_pairs, const ConvParams& p, int& g0, int& g1) {
+  const long long P = static_cast<long long>(p.n_units) * p.T;
+  g0 = static_cast<int>(P * pair / n_pairs);
+  g1 = static_cast<int>(P * (pair + 1) / n_pairs);
+}
+__device__ __forceinline__ Item next_item(int g, int g1, int T) {
+  Item it;
+  it.u = g / T;
+  it.t0 = g - it.u * T;
+  it.t1 = min(T, it.t0 + (g1 - g));
+  return it;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -193,9 +213,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
   uint64_t* a_empty = a_full + C::SLOTS;      // [SLOTS]  (each CTA its own; multicast commit)
   uint64_t* acc_full = a_empty + C::SLOTS;    // [2]      (each CTA its own; multicast commit)
   uint64_t* acc_empty = acc_full + 2;         // [2]      (leader's is used; 8 arrivals = 4 warps x 2 CTAs)
-  uint64_t* w_full = acc_empty + 2;           // [1]      this CTA's filter bank has landed
-  uint64_t* w_peer = w_full + 1;              // [1]      (leader's is used) the peer's filter bank has landed
-  uint32_t* tmem_ptr_sm = reinterpret_cast<uint32_t*>(w_peer + 1);
+  uint64_t* w_full = acc_empty + 2;           // [3]      this CTA's filter taps of temporal offset dt have landed
+  uint64_t* w_peer = w_full + 3;              // [3]      (leader's is used) the peer's taps of dt have landed
+  uint32_t* tmem_ptr_sm = reinterpret_cast<uint32_t*>(w_peer + 3);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -213,8 +233,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 8);
     }
-    mbar_init(w_full, 1);
-    mbar_init(w_peer, 1);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_peer[i], 1);
+    }
     fence_mbar_init();
   }
   if (threadIdx.x < 64) {
@@ -231,22 +253,30 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
     // =========================================================================== TMA producer (both CTAs)
     if (elect_one()) {
       tma_prefetch_desc(&tmap_in);
-      // resident filter bank: this CTA's half of Cout, all taps
-      mbar_expect_tx(w_full, C::W_BYTES);
+      // resident filter bank: this CTA's half of Cout, all taps — one barrier per temporal offset, so the first MMAs
+      // start after a third of the bank (dt = 1 first: the strip's first plane has no dt = 0 tap)
       const uint8_t* wsrc = p.wimg + static_cast<size_t>(rank) * C::W_BYTES;
-      constexpr int CHUNK = 13824;  // divides every W_BYTES here (110592, 27648) ; 15360 handled below
-      if constexpr (C::W_BYTES % CHUNK == 0) {
-        for (int off = 0; off < C::W_BYTES; off += CHUNK) bulk_load(w_sm + off, wsrc + off, CHUNK, w_full);
-      } else {
-        for (int off = 0; off < C::W_BYTES; off += 5120) bulk_load(w_sm + off, wsrc + off, 5120, w_full);
+      constexpr int CHUNK = (C::DT_BYTES % 3 == 0 && C::DT_BYTES / 3 >= 1024) ? C::DT_BYTES / 3 : C::DT_BYTES;
+      static_assert(C::W_BYTES == 3 * C::DT_BYTES && C::DT_BYTES % CHUNK == 0 && CHUNK % 16 == 0, "filter bank layout");
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int dt = (i + 1) % 3;   // 1, 2, 0
+        mbar_expect_tx(&w_full[dt], C::DT_BYTES);
+        for (int off = dt * C::DT_BYTES; off < (dt + 1) * C::DT_BYTES; off += CHUNK)
+          bulk_load(w_sm + off, wsrc + off, CHUNK, &w_full[dt]);
       }
       uint32_t leader_full[C::SLOTS];
 #pragma unroll
       for (int i = 0; i < C::SLOTS; ++i) leader_full[i] = map_to_cta(smem_u32(&a_full[i]), 0);
       uint32_t j = 0;
-      for (int u = pair; u < p.n_units; u += n_pairs) {
-        const Unit un = decode_unit(u, p, rank);
-        for (int t = 0; t < T; ++t, ++j) {
+      int g0, g1;
+      work_range(pair, n_pairs, p, g0, g1);
+      for (int g = g0; g < g1;) {
+        const Item it = next_item(g, g1, T);
+        g += it.t1 - it.t0;
+        const Unit un = decode_unit(it.u, p, rank);
+        const int tlo = max(it.t0 - 1, 0), thi = min(it.t1, T - 1);   // input planes incl. the temporal halo
+        for (int t = tlo; t <= thi; ++t, ++j) {
           const uint32_t slot = j % C::SLOTS;
           const uint32_t ph = (j / C::SLOTS) & 1u;
           mbar_wait(&a_empty[slot], ph ^ 1u);
@@ -265,27 +295,32 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
   } else if (warp == 1) {
     // =========================================================================== MMA issuer (leader CTA only)
     if (rank == 1 && elect_one()) {
-      // tell the leader that this CTA's half of the filter bank is resident
-      mbar_wait(w_full, 0);
-      mbar_arrive_cluster(map_to_cta(smem_u32(w_peer), 0));
+      // tell the leader as each third of this CTA's half of the filter bank becomes resident
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int dt = (i + 1) % 3;
+        mbar_wait(&w_full[dt], 0);
+        mbar_arrive_cluster(map_to_cta(smem_u32(&w_peer[dt]), 0));
+      }
     }
     if (rank == 0 && elect_one()) {
-      mbar_wait(w_full, 0);
-      mbar_wait(w_peer, 0);
+      uint32_t w_ready = 0;                      // bit dt: the taps of temporal offset dt are resident in both CTAs
       const uint32_t idesc = make_idesc_bf16(256, C::NOUT);
       const uint32_t w_addr = smem_u32(w_sm);
       const uint32_t planes_addr = smem_u32(planes);
       uint32_t j0 = 0, q = 0;
-      for (int u = pair; u < p.n_units; u += n_pairs) {
-        for (int pl = 0; pl < T; ++pl, ++q) {
+      int g0, g1;
+      work_range(pair, n_pairs, p, g0, g1);
+      for (int g = g0; g < g1;) {
+        const Item it = next_item(g, g1, T);
+        g += it.t1 - it.t0;
+        const int tlo = max(it.t0 - 1, 0), thi = min(it.t1, T - 1);
+        int arrived = tlo;                       // input planes [tlo, arrived) of this item have been waited for
+        for (int pl = it.t0; pl < it.t1; ++pl, ++q) {
           const uint32_t ab = q & 1u;
           mbar_wait(&acc_empty[ab], ((q >> 1) & 1u) ^ 1u);
-          if (pl == 0) {
-            const uint32_t jj = j0;
-            mbar_wait(&a_full[jj % C::SLOTS], (jj / C::SLOTS) & 1u);
-          }
-          if (pl + 1 < T) {
-            const uint32_t jj = j0 + pl + 1;
+          for (const int need = min(pl + 1, T - 1); arrived <= need; ++arrived) {
+            const uint32_t jj = j0 + static_cast<uint32_t>(arrived - tlo);
             mbar_wait(&a_full[jj % C::SLOTS], (jj / C::SLOTS) & 1u);
           }
           tc_fence_after();
@@ -295,7 +330,13 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
           for (int dt = 0; dt < 3; ++dt) {
             const int tin = pl + dt - 1;
             if (tin < 0 || tin >= T) continue;
-            const uint32_t slot = (j0 + tin) % C::SLOTS;
+            if (!(w_ready & (1u << dt))) {
+              mbar_wait(&w_full[dt], 0);
+              mbar_wait(&w_peer[dt], 0);
+              tc_fence_after();
+              w_ready |= 1u << dt;
+            }
+            const uint32_t slot = (j0 + static_cast<uint32_t>(tin - tlo)) % C::SLOTS;
             const uint32_t a_base = planes_addr + slot * C::SLOT_STRIDE;
             const uint32_t b_base = w_addr + dt * C::DT_BYTES;
             if constexpr (MODE == CONV_MODE_8_64) {
@@ -327,11 +368,19 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
             }
           }
           umma_commit_pair(&acc_full[ab], 3);
-          if (pl >= 1) umma_commit_pair(&a_empty[(j0 + pl - 1) % C::SLOTS], 3);
-          if (pl == T - 1) umma_commit_pair(&a_empty[(j0 + pl) % C::SLOTS], 3);
+          // plane pl-1 has fed its last output plane; the item's last output also frees planes pl and pl+1
+          if (pl - 1 >= tlo) umma_commit_pair(&a_empty[(j0 + static_cast<uint32_t>(pl - 1 - tlo)) % C::SLOTS], 3);
+          if (pl == it.t1 - 1) {
+            umma_commit_pair(&a_empty[(j0 + static_cast<uint32_t>(pl - tlo)) % C::SLOTS], 3);
+            if (pl + 1 <= thi) umma_commit_pair(&a_empty[(j0 + static_cast<uint32_t>(pl + 1 - tlo)) % C::SLOTS], 3);
+          }
         }
-        j0 += T;
+        j0 += static_cast<uint32_t>(thi - tlo + 1);
       }
+      // never leave with a bulk copy into this CTA's shared memory still in flight (T == 1 uses only dt == 1)
+#pragma unroll
+      for (int dt = 0; dt < 3; ++dt)
+        if (!(w_ready & (1u << dt))) mbar_wait(&w_full[dt], 0);
     }
     __syncwarp();
   } else {
@@ -344,11 +393,15 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
     leader_empty[1] = map_to_cta(smem_u32(&acc_empty[1]), 0);
     uint32_t q = 0;
     float st_s0 = 0.f, st_s1 = 0.f, st_q0 = 0.f, st_q1 = 0.f;   // BatchNorm partial sums of channels 2*lane, 2*lane+1
-    for (int u = pair; u < p.n_units; u += n_pairs) {
-      const Unit un = decode_unit(u, p, rank);
+    int g0, g1;
+    work_range(pair, n_pairs, p, g0, g1);
+    for (int g = g0; g < g1;) {
+      const Item it = next_item(g, g1, T);
+      g += it.t1 - it.t0;
+      const Unit un = decode_unit(it.u, p, rank);
       const int h = un.h0 + hh, w = un.w0 + ww;
       const bool inb = (h < p.H) && (w < p.W);
-      for (int pl = 0; pl < T; ++pl, ++q) {
+      for (int pl = it.t0; pl < it.t1; ++pl, ++q) {
         const uint32_t ab = q & 1u;
         mbar_wait(&acc_full[ab], (q >> 1) & 1u);
         tc_fence_after();
@@ -487,7 +540,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
 template <int MODE>
 constexpr int smem_bytes_for() {
   using C = Cfg<MODE>;
-  return 1024 + ((C::W_BYTES + 1023) & ~1023) + C::SLOTS * C::SLOT_STRIDE + 512 + (2 * C::SLOTS + 6) * 8 + 16;
+  return 1024 + ((C::W_BYTES + 1023) & ~1023) + C::SLOTS * C::SLOT_STRIDE + 512 + (2 * C::SLOTS + 10) * 8 + 16;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -577,7 +630,9 @@ const char* conv3d_umma_launch(const ConvLaunch& L, cudaStream_t stream) {
   prm.mask = L.mask;
   prm.mask_pitch = L.mask_pitch;
   prm.in_merged = merged ? 1 : 0;
-  int n_pairs = prm.n_units < L.max_pairs ? prm.n_units : L.max_pairs;
+  const long long out_planes = static_cast<long long>(prm.n_units) * L.T;   // work items of one plane each
+  if (out_planes >= (1LL << 31) / (L.max_pairs + 1)) return "problem too large for the int work partition";
+  int n_pairs = out_planes < L.max_pairs ? static_cast<int>(out_planes) : L.max_pairs;
   if (n_pairs < 1) return nullptr;
   cudaError_t e;
   switch (L.mode) {
