@@ -46,6 +46,34 @@ def test_resize_fwd_bwd(hpvg_gpu, case):
     assert rel_l2(gx, gref) < 1e-6
 
 
+@pytest.mark.parametrize("case", [
+    ((2, 6, 7), (13, 8, 9)),       # > 4 outputs per source frame: the register walk declines, tiled kernel takes over
+    ((7, 20, 27), (16, 25, 33)),   # 7 -> 16 frames (BASELINE config 3): 3/2/3/2/3/2/1 outputs per source frame
+    ((3, 5, 7), (3, 5, 7)),        # identity
+    ((8, 12, 9), (5, 9, 5)),       # down-sampling: source frames that are nobody's lower tap
+    ((4, 10, 1), (5, 13, 1)),      # a single column (no division by the row length)
+    ((5, 1, 40), (7, 1, 51)),      # a single row
+    ((9, 6, 6), (11, 8, 8)),       # more than 8 source frames: not the register walk
+])
+@pytest.mark.parametrize("align", [True, False])
+def test_resize_edge_shapes(hpvg_gpu, case, align):
+    """Every dispatch branch of the resize launchers (constant-bank T walk, window-staged adjoint, tiled, generic)."""
+    hp = hpvg_gpu
+    in_size, out_size = case
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((3, 1) + in_size).astype(np.float32)
+    gy = rng.standard_normal((3, 1) + out_size).astype(np.float32)
+    y = hp.ops.resize3d(hp.from_numpy(x), out_size, align_corners=align).numpy()
+    ref = orc.resize_linear_np(x, out_size, align)
+    assert np.max(np.abs(y - ref)) <= 1e-6
+    gx = hp.ops.resize3d_bwd(hp.from_numpy(gy), in_size, align_corners=align).numpy()
+    gref = orc.resize_linear_bwd_np(gy, in_size, align)
+    assert rel_l2(gx, gref) < 1e-6
+    # adjointness <R x, gy> == <x, R^T gy>
+    lhs, rhs = float(np.sum(y.astype(np.float64) * gy)), float(np.sum(x.astype(np.float64) * gx))
+    assert abs(lhs - rhs) <= 1e-5 * max(1.0, abs(lhs))
+
+
 def test_resize_rejects_bad_sizes(hpvg_gpu):
     hp = hpvg_gpu
     x = hp.from_numpy(np.zeros((1, 1, 2, 2, 2), np.float32))
