@@ -124,6 +124,14 @@ int hpvg_upsample_noise_pack(const float* d_x, int N, int C, int Ti, int Hi, int
                              const float* d_noise, float amp, uint64_t noise_seed, uint64_t sample_base,
                              const uint64_t* d_sample_offset /* nullable: device draw counter added to sample_base */,
                              float* d_up, void* d_xin_cl, void* stream);
+/* Device-side data path between the video decoder and the network.  d_frames: uint8 [F][Hs][Ws][3]
+ * decoded frames (bgr != 0: decoder order, as cv2.VideoCapture returns them).  Writes the fp32 clip [1][3][T][H][W] the
+ * reference's SingleVideoDataset.__getitem__ yields for window `start` and rate `every`:
+ *   generate_frames.py:42-46  cv2.cvtColor(BGR2RGB) + cv2.resize(INTER_LINEAR) on uint8 (restated bit-exactly)
+ *   video.py:52-59            frames[start : start + lcm + 1 : every], float32 / 255
+ *   video.py:75-86            optional horizontal flip, Normalize(mean .5, std .5), (C, T, H, W) */
+int hpvg_frames_to_clip(const uint8_t* d_frames, int F, int Hs, int Ws, int bgr, int start, int every, int T, int H,
+                        int W, int hflip, float* d_clip, void* stream);
 /* z ~ N(0,1) on the device (Philox4x32-10 + Box-Muller), keyed by (seed, offset [+ *d_offset], element): stand-in for
  * the reference's host numpy draws (images.py:17-21, networks_3d.py:28-34) inside CUDA-graph replays */
 int hpvg_randn(float* d_z, long long n, uint64_t seed, uint64_t offset, const uint64_t* d_offset, void* stream);

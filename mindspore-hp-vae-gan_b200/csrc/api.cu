@@ -469,6 +469,16 @@ int hpvg_fill(float* y, float v, long long n, void* st) {
   KL(hpvg::ew_fill(y, v, n, S(st)), 1);
   return HPVG_OK;
 }
+int hpvg_frames_to_clip(const uint8_t* frames, int F, int Hs, int Ws, int bgr, int start, int every, int T, int H, int W,
+                        int hflip, float* clip, void* st) {
+  if (F <= 0 || Hs <= 0 || Ws <= 0 || T <= 0 || H <= 0 || W <= 0 || every <= 0 || start < 0)
+    return fail(HPVG_E_ARG, "frames_to_clip: sizes must be positive");
+  if (static_cast<long long>(start) + static_cast<long long>(T - 1) * every >= F)
+    return fail(HPVG_E_ARG, "frames_to_clip: frame window runs past the decoded frames");
+  if (!frames || !clip) return fail(HPVG_E_ARG, "frames_to_clip: null pointer");
+  KL(hpvg::ew_frames_to_clip(frames, Hs, Ws, bgr ? 1 : 0, start, every, T, H, W, hflip ? 1 : 0, clip, S(st)), 1);
+  return HPVG_OK;
+}
 int hpvg_randn(float* z, long long n, uint64_t seed, uint64_t offset, const uint64_t* d_offset, void* st) {
   if (n <= 0) return HPVG_OK;
   if (!z) return fail(HPVG_E_ARG, "randn: null pointer");

@@ -864,6 +864,77 @@ __global__ void resize3d_bwd_tiled_kernel(const float* __restrict__ gy, const Ti
   }
 }
 
+// ----------------------------------------------------------------------------------------------- clip from frames
+// Device-side restatement of the reference's data path between the decoder and the network:
+// generate_frames.py:42-46 (cv2.resize(rgb, INTER_LINEAR) on uint8) -> video.py:52-59 (frames[idx : idx+lcm+1 : every],
+// float32 / 255) -> video.py:75-86 (optional horizontal flip, Normalize(mean .5, std .5), (C, T, H, W)).
+// The resize is OpenCV's 8-bit fixed-point bilinear, restated exactly: half-pixel centres, float fractions from a
+// double coordinate, 11-bit coefficients (cvRound(f * 2048), saturated to short), x indices clamped WITH their
+// fraction zeroed, y rows clamped WITHOUT touching the fraction, int horizontal pass, vertical pass
+// ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2 >> 2; an exact 2x decimation is OpenCV's 2x2 box mean.
+struct FrameGeom {
+  int Hs, Ws, H, W, T, start, every, hflip, bgr;
+  double sx, sy;      // Ws / W, Hs / H
+};
+__device__ __forceinline__ int sat_short(int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); }
+__device__ __forceinline__ float cv_coord(int d, double scale, int& s) {
+  const float f = static_cast<float>(__dsub_rn(__dmul_rn(__dadd_rn(static_cast<double>(d), 0.5), scale), 0.5));
+  const float fl = floorf(f);
+  s = static_cast<int>(fl);
+  return __fsub_rn(f, fl);
+}
+__global__ void frames_to_clip_kernel(const uint8_t* __restrict__ frames, const FrameGeom g, float* __restrict__ clip) {
+  const long long total = static_cast<long long>(g.T) * g.H * g.W;
+  const long long plane = static_cast<long long>(g.H) * g.W;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(idx % g.W);
+    const long long r = idx / g.W;
+    const int h = static_cast<int>(r % g.H);
+    const int t = static_cast<int>(r / g.H);
+    const uint8_t* f = frames + static_cast<size_t>(g.start + t * g.every) * g.Hs * g.Ws * 3;
+    int v[3];
+    if (g.Hs == g.H && g.Ws == g.W) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = f[(static_cast<size_t>(h) * g.Ws + w) * 3 + c];
+    } else if (g.Hs == 2 * g.H && g.Ws == 2 * g.W) {
+      const uint8_t* p0 = f + (static_cast<size_t>(2 * h) * g.Ws + 2 * w) * 3;
+      const uint8_t* p1 = p0 + static_cast<size_t>(g.Ws) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = (p0[c] + p0[3 + c] + p1[c] + p1[3 + c] + 2) >> 2;
+    } else {
+      int sx, sy;
+      float fx = cv_coord(w, g.sx, sx);
+      const float fy = cv_coord(h, g.sy, sy);
+      if (sx < 0) { fx = 0.f; sx = 0; }
+      if (sx >= g.Ws - 1) { fx = 0.f; sx = g.Ws - 1; }
+      const int a0 = sat_short(__float2int_rn(__fmul_rn(__fsub_rn(1.f, fx), 2048.f)));
+      const int a1 = sat_short(__float2int_rn(__fmul_rn(fx, 2048.f)));
+      const int b0 = sat_short(__float2int_rn(__fmul_rn(__fsub_rn(1.f, fy), 2048.f)));
+      const int b1 = sat_short(__float2int_rn(__fmul_rn(fy, 2048.f)));
+      const int x1 = min(sx + 1, g.Ws - 1);
+      const int r0 = min(max(sy, 0), g.Hs - 1), r1 = min(max(sy + 1, 0), g.Hs - 1);
+      const uint8_t* p0 = f + static_cast<size_t>(r0) * g.Ws * 3;
+      const uint8_t* p1 = f + static_cast<size_t>(r1) * g.Ws * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int S0 = p0[sx * 3 + c] * a0 + p0[x1 * 3 + c] * a1;
+        const int S1 = p1[sx * 3 + c] * a0 + p1[x1 * 3 + c] * a1;
+        const int o = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+        v[c] = min(max(o, 0), 255);
+      }
+    }
+    const int wo = g.hflip ? g.W - 1 - w : w;
+    float* dst = clip + (static_cast<long long>(t) * g.H + h) * g.W + wo;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int cs = g.bgr ? 2 - c : c;     // decoder order -> RGB (cv2.COLOR_BGR2RGB, generate_frames.py:42)
+      const float x01 = __fdiv_rn(static_cast<float>(v[cs]), 255.f);
+      dst[c * g.T * plane] = __fdiv_rn(__fsub_rn(x01, 0.5f), 0.5f);
+    }
+  }
+}
+
 // z[i] ~ N(0,1): Philox4x32-10 keyed by `seed`, counter = (element/4, offset [+ *d_offset]) — the device stand-in for
 // the reference's host numpy draws (images.py:17-21, networks_3d.py:28-34) when the step is replayed as a CUDA graph.
 __global__ void randn_kernel(float* __restrict__ z, long long n, unsigned long long seed, unsigned long long offset,
@@ -2013,6 +2084,16 @@ cudaError_t ew_axpby(float a, const float* x, float b, float* y, long long n, cu
 cudaError_t ew_gather_strided(const float* src, long long n, long long stride, long long offset, float* dst,
                               cudaStream_t st) {
   gather_strided_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, n, stride, offset, dst);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t ew_frames_to_clip(const uint8_t* frames, int Hs, int Ws, int bgr, int start, int every, int T, int H, int W,
+                              int hflip, float* clip, cudaStream_t st) {
+  FrameGeom g;
+  g.Hs = Hs; g.Ws = Ws; g.H = H; g.W = W; g.T = T; g.start = start; g.every = every; g.hflip = hflip; g.bgr = bgr;
+  g.sx = static_cast<double>(Ws) / W;
+  g.sy = static_cast<double>(Hs) / H;
+  frames_to_clip_kernel<<<grid_for(static_cast<long long>(T) * H * W, 256), 256, 0, st>>>(frames, g, clip);
   LAUNCH_CHECK();
   return cudaSuccess;
 }

@@ -31,6 +31,8 @@ cudaError_t ew_upsample_noise_pack(const float* x, int N, int C, int Ti, int Hi,
                                    const float* noise, float amp, unsigned long long seed,
                                    unsigned long long sample_base, const unsigned long long* d_sample_offset,
                                    float* up, __nv_bfloat16* xin, cudaStream_t st);
+cudaError_t ew_frames_to_clip(const uint8_t* frames, int Hs, int Ws, int bgr, int start, int every, int T, int H, int W,
+                              int hflip, float* clip, cudaStream_t st);
 cudaError_t ew_randn(float* z, long long n, unsigned long long seed, unsigned long long offset,
                      const unsigned long long* d_offset, cudaStream_t st);
 cudaError_t ew_counter_add(unsigned long long* c, unsigned long long inc, cudaStream_t st);

@@ -237,6 +237,22 @@ def resize3d_bwd(gy, in_size, align_corners=True, out=None, stream=None):
     return out
 
 
+def frames_to_clip(frames, size, start=0, every=1, n_frames=None, hflip=False, bgr=False, out=None, stream=None):
+    """Decoded uint8 frames (F, Hs, Ws, 3) on the device -> the fp32 clip (1, 3, T, H, W) in [-1, 1] that the
+    reference's SingleVideoDataset yields (generate_frames.py:42-46 cv2.resize INTER_LINEAR, video.py:52-59 frame
+    window + /255, video.py:75-86 flip + Normalize + CTHW)."""
+    F_, Hs, Ws, C = frames.shape
+    if C != 3 or frames.dtype != "uint8":
+        raise HpvgError("frames_to_clip: frames must be uint8 (F, H, W, 3)")
+    H, W = (int(v) for v in size)
+    T = int(n_frames) if n_frames is not None else (F_ - int(start) + int(every) - 1) // int(every)
+    if out is None:
+        out = Tensor((1, 3, T, H, W), F32)
+    check(lib.hpvg_frames_to_clip(_p(frames), F_, Hs, Ws, int(bool(bgr)), int(start), int(every), T, H, W,
+                                  int(bool(hflip)), _p(out), _s(stream)), "frames_to_clip")
+    return out
+
+
 def randn(shape, seed, offset=0, d_offset=None, out=None, stream=None):
     """N(0,1) drawn on the device, keyed by (seed, offset [+ device counter], element)."""
     out = out or Tensor(shape, F32)

@@ -12,8 +12,9 @@ F32 = "float32"
 F64 = "float64"
 I32 = "int32"
 U64 = "uint64"
-_ITEMSIZE = {BF16: 2, F32: 4, F64: 8, I32: 4, U64: 8}
-_NP = {F32: np.float32, F64: np.float64, I32: np.int32, BF16: np.uint16, U64: np.uint64}
+U8 = "uint8"
+_ITEMSIZE = {BF16: 2, F32: 4, F64: 8, I32: 4, U64: 8, U8: 1}
+_NP = {F32: np.float32, F64: np.float64, I32: np.int32, BF16: np.uint16, U64: np.uint64, U8: np.uint8}
 
 
 def init(device=0):
@@ -218,7 +219,7 @@ def from_numpy(arr, dtype=None, stream=None):
     a = np.asarray(arr)
     if dtype is None:
         dtype = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.int32): I32,
-                 np.dtype(np.uint64): U64}.get(a.dtype, F32)
+                 np.dtype(np.uint64): U64, np.dtype(np.uint8): U8}.get(a.dtype, F32)
     t = Tensor(a.shape, dtype)
     t.copy_from_host(a, stream)
     return t

@@ -97,6 +97,88 @@ def scale_shape_2d(opt, index):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# Data path between the decoder and the network            (src/datasets/generate_frames.py:42-46, video.py:45-86)
+# ----------------------------------------------------------------------------------------------------------------
+def _cv_sat_short(v):
+    return max(-32768, min(32767, int(np.rint(np.float32(v) * np.float32(2048)))))   # saturate_cast<short>(f * 2048)
+
+
+def _cv_x_coeffs(n_in, n_out):
+    """OpenCV resize.cpp, INTER_LINEAR: half-pixel centres; at the borders the index is clamped AND the fraction
+    zeroed (x axis only)."""
+    scale = n_in / n_out
+    i0 = np.empty(n_out, np.int64)
+    a = np.empty((n_out, 2), np.int64)
+    for d in range(n_out):
+        fx = np.float32((d + 0.5) * scale - 0.5)
+        sx = int(np.floor(fx))
+        fx = np.float32(fx - np.float32(sx))
+        if sx < 0:
+            fx, sx = np.float32(0), 0
+        if sx >= n_in - 1:
+            fx, sx = np.float32(0), n_in - 1
+        i0[d] = sx
+        a[d] = _cv_sat_short(np.float32(1.0) - fx), _cv_sat_short(fx)
+    return i0, a
+
+
+def _cv_y_coeffs(n_in, n_out):
+    """Rows are clamped into the image, the fraction is NOT touched (so a clamped border row is blended with itself)."""
+    scale = n_in / n_out
+    r0 = np.empty(n_out, np.int64)
+    r1 = np.empty(n_out, np.int64)
+    b = np.empty((n_out, 2), np.int64)
+    for d in range(n_out):
+        fy = np.float32((d + 0.5) * scale - 0.5)
+        sy = int(np.floor(fy))
+        fy = np.float32(fy - np.float32(sy))
+        r0[d] = min(max(sy, 0), n_in - 1)
+        r1[d] = min(max(sy + 1, 0), n_in - 1)
+        b[d] = _cv_sat_short(np.float32(1.0) - fy), _cv_sat_short(fy)
+    return r0, r1, b
+
+
+def cv_resize_linear_u8(src, size):
+    """cv2.resize(src, (W, H), interpolation=cv2.INTER_LINEAR) for uint8 HxWxC, restated: 11-bit fixed-point
+    coefficients, int horizontal pass, vertical pass ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2 >> 2; an exact 2x
+    decimation is the 2x2 box mean (cv::resize switches INTER_LINEAR to INTER_AREA there).  Pinned against cv2
+    itself in tests/test_cpu_oracle.py (generate_frames.py:44-46)."""
+    src = np.asarray(src, dtype=np.uint8)
+    H, W = int(size[0]), int(size[1])
+    Hs, Ws = src.shape[:2]
+    if (Hs, Ws) == (H, W):
+        return src.copy()
+    s = src.astype(np.int64)
+    if Hs == 2 * H and Ws == 2 * W:
+        return ((s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+    xi, xa = _cv_x_coeffs(Ws, W)
+    r0, r1, yb = _cv_y_coeffs(Hs, H)
+    x1 = np.minimum(xi + 1, Ws - 1)
+    hr = s[:, xi] * xa[:, 0][None, :, None] + s[:, x1] * xa[:, 1][None, :, None]
+    b0, b1 = yb[:, 0][:, None, None], yb[:, 1][:, None, None]
+    out = (((b0 * (hr[r0] >> 4)) >> 16) + ((b1 * (hr[r1] >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def frames_to_clip_np(frames, size, start=0, every=1, n_frames=None, hflip=False, bgr=False):
+    """SingleVideoDataset.__getitem__ for one window (video.py:45-86) on already decoded uint8 frames (F, Hs, Ws, 3):
+    BGR->RGB + resize (generate_frames.py:42-46), frames[start : ... : every] (video.py:52), /255 (video.py:56),
+    horizontal flip (video.py:78-79), Normalize(mean .5, std .5)‡ (video.py:81-82), (C, T, H, W) (video.py:84).
+    Returns float32 (1, 3, T, H, W)."""
+    frames = np.asarray(frames, dtype=np.uint8)
+    T = int(n_frames) if n_frames is not None else (frames.shape[0] - start + every - 1) // every
+    sel = frames[start:start + (T - 1) * every + 1:every]
+    if bgr:
+        sel = sel[..., ::-1]
+    res = np.stack([cv_resize_linear_u8(f, size) for f in sel])                  # (T, H, W, 3)
+    x = res.transpose(0, 3, 1, 2).astype(np.float32) / np.float32(255)           # (T, C, H, W) in [0, 1]
+    if hflip:
+        x = np.flip(x, -1)
+    x = (x - np.float32(0.5)) / np.float32(0.5)
+    return np.ascontiguousarray(x.transpose(1, 0, 2, 3)[None])
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # Linear resize (UpsampleTrilinear3D / ResizeBilinear, align_corners)                 (src/tools/trilinear.py:171-254)
 # ----------------------------------------------------------------------------------------------------------------
 def linear_taps(n_in, n_out, align_corners=True):

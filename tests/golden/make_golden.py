@@ -86,6 +86,46 @@ def ops_small():
     print("ops_small:", sorted(out))
 
 
+def frames_small():
+    """Data-path fixtures (generate_frames.py:42-46, video.py:45-86, image.py:36-75) made by running the reference's
+    OWN library calls here — cv2.cvtColor / cv2.resize(INTER_LINEAR) / numpy — on (a) seeded synthetic frames and
+    (b) a crop of the reference's real image data/imgs/air_balloons.jpg.  The oracle restatement and the CUDA kernel
+    must both reproduce these bits."""
+    import cv2
+
+    def reference_clip(frames_bgr, size, start, every, T, hflip):
+        mem = []
+        for image in frames_bgr:                                           # generate_frames.py:42-47
+            rgb = cv2.cvtColor(image, cv2.COLOR_BGR2RGB)
+            mem.append(cv2.resize(rgb, (size[1], size[0]), interpolation=cv2.INTER_LINEAR))
+        frames = np.stack(mem)[start:start + (T - 1) * every + 1:every]    # video.py:52
+        frames = frames.transpose(0, 3, 1, 2).astype(np.float32) / 255     # video.py:53-56
+        if hflip:
+            frames = np.flip(frames, -1)                                   # video.py:78-79
+        frames = (frames - np.float32(0.5)) / np.float32(0.5)              # Normalize(mean .5, std .5), video.py:81-82
+        return np.ascontiguousarray(frames.transpose(1, 0, 2, 3)[None])    # video.py:84
+
+    rng = np.random.default_rng(2024)
+    out = {}
+    fr = rng.integers(0, 256, (13, 45, 60, 3), dtype=np.uint8)             # 13 decoded BGR frames, ar 0.75
+    out["frames_bgr"] = fr
+    out["clip_s0"] = reference_clip(fr, (24, 33), 0, 4, 4, False)          # scale 0: every 4th frame, 4 frames
+    out["clip_up_flip"] = reference_clip(fr, (57, 76), 1, 3, 4, True)      # up-sampling + flip + offset window
+    path = "/root/reference/data/imgs/air_balloons.jpg"
+    if os.path.exists(path):
+        img = cv2.imread(path)[40:136, 60:188]                             # 96 x 128 BGR crop of the real image
+        out["image_bgr"] = img
+        out["image_s0"] = reference_clip(img[None], (24, 33), 0, 1, 1, False)
+        out["image_half"] = reference_clip(img[None], (48, 64), 0, 1, 1, False)   # exact 2x decimation (box mean)
+    else:                                                                  # keep the previous real-image entries
+        old = np.load(os.path.join(HERE, "frames_small.npz"))
+        for k in ("image_bgr", "image_s0", "image_half"):
+            out[k] = old[k]
+    np.savez_compressed(os.path.join(HERE, "frames_small.npz"), **out)
+    print("frames_small:", sorted(out))
+
+
 if __name__ == "__main__":
     sample_small()
     ops_small()
+    frames_small()

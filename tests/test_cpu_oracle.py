@@ -226,3 +226,41 @@ def test_oracle_reproduces_operator_fixtures():
     w1, m, v = orc.adam_step(g["ad_w0"], orc.clip_by_norm(g["ad_g1"], 5.0), m, v, 1, 5e-4)
     w2, m, v = orc.adam_step(w1, orc.clip_by_norm(g["ad_g2"], 5.0), m, v, 2, 5e-4)
     assert np.array_equal(w1, g["ad_w1"]) and np.array_equal(w2, g["ad_w2"])
+
+
+# ------------------------------------------------------------------------------------------- data path
+@pytest.mark.parametrize("src,dst", [((186, 248), (24, 33)), ((186, 248), (192, 257)), ((50, 60), (121, 162)),
+                                     ((100, 120), (50, 60)), ((64, 64), (64, 64)), ((9, 7), (3, 20)),
+                                     ((720, 1280), (153, 204))])
+def test_cv_resize_restatement_matches_cv2(src, dst):
+    """generate_frames.py:44-46 / image.py:72: the oracle's fixed-point bilinear is cv2.resize(INTER_LINEAR) on
+    uint8, bit for bit — checked against the library the reference itself calls (cv2 is in this image)."""
+    cv2 = pytest.importorskip("cv2")
+    img = np.random.default_rng(src[0] * 1000 + dst[1]).integers(0, 256, src + (3,), dtype=np.uint8)
+    assert np.array_equal(orc.cv_resize_linear_u8(img, dst), cv2.resize(img, (dst[1], dst[0]),
+                                                                        interpolation=cv2.INTER_LINEAR))
+
+
+def test_oracle_reproduces_data_path_fixtures():
+    """tests/golden/frames_small.npz was produced by the reference's own library calls (cv2.cvtColor / cv2.resize /
+    numpy, statement by statement as in generate_frames.py:42-47 and video.py:52-84) on seeded frames and on a crop
+    of the reference's real image: the restatement must reproduce those bits."""
+    g = np.load(os.path.join(GOLDEN, "frames_small.npz"))
+    fr = g["frames_bgr"]
+    assert np.array_equal(orc.frames_to_clip_np(fr, (24, 33), 0, 4, 4, False, True), g["clip_s0"])
+    assert np.array_equal(orc.frames_to_clip_np(fr, (57, 76), 1, 3, 4, True, True), g["clip_up_flip"])
+    img = g["image_bgr"][None]
+    assert np.array_equal(orc.frames_to_clip_np(img, (24, 33), 0, 1, 1, False, True), g["image_s0"])
+    assert np.array_equal(orc.frames_to_clip_np(img, (48, 64), 0, 1, 1, False, True), g["image_half"])
+    assert g["clip_s0"].shape == (1, 3, 4, 24, 33) and float(np.abs(g["clip_s0"]).max()) <= 1.0
+
+
+def test_frames_to_clip_argument_errors():
+    import ctypes
+    import hpvg
+    buf = (ctypes.c_uint8 * 16)()
+    out = (ctypes.c_float * 16)()
+    # window runs past the decoded frames: 3 frames, start 1, every 2, T 2 -> needs frame 3
+    assert hpvg.lib.hpvg_frames_to_clip(buf, 3, 2, 2, 0, 1, 2, 2, 2, 2, 0, out, None) == -2
+    assert b"past the decoded frames" in hpvg.lib.hpvg_last_error()
+    assert hpvg.lib.hpvg_frames_to_clip(buf, 3, 2, 2, 0, 0, 0, 2, 2, 2, 0, out, None) == -2      # every == 0

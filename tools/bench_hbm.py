@@ -83,6 +83,18 @@ def main():
            "resize + in-kernel N(0,1) + bf16 block input")
     del x, y, gx, xin
 
+    # ---------------------------------------------------------------- frames -> clip (generate_frames.py:42-46, video.py:45-86)
+    F_ = 64
+    fr = Tensor((F_, 540, 960, 3), "uint8").zero_(st)
+    clip = Tensor((1, 3, F_, 1080, 1920), F32)
+    report("frames_to_clip 540p->1080p x%d" % F_, F_ * (540 * 960 * 3 + 1080 * 1920 * 12),
+           timed(st, lambda: ops.frames_to_clip(fr, (1080, 1920), n_frames=F_, bgr=True, out=clip, stream=st)),
+           "cv2-exact u8 bilinear + /255 + normalise, fp32 CTHW out")
+    fr2 = Tensor((F_, 1080, 1920, 3), "uint8").zero_(st)
+    report("frames_to_clip 1080p same size x%d" % F_, F_ * 1080 * 1920 * 15,
+           timed(st, lambda: ops.frames_to_clip(fr2, (1080, 1920), n_frames=F_, bgr=True, out=clip, stream=st)))
+    del fr, fr2, clip
+
     # ---------------------------------------------------------------- BatchNorm (train) on 64-channel bf16 cl
     B = args.wide
     vox = B * vo
