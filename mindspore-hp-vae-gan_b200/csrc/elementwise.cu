@@ -883,15 +883,16 @@ __device__ __forceinline__ float cv_coord(int d, double scale, int& s) {
   s = static_cast<int>(fl);
   return __fsub_rn(f, fl);
 }
-__global__ void frames_to_clip_kernel(const uint8_t* __restrict__ frames, const FrameGeom g, float* __restrict__ clip) {
-  const long long total = static_cast<long long>(g.T) * g.H * g.W;
+__global__ void __launch_bounds__(256)
+frames_to_clip_kernel(const uint8_t* __restrict__ frames, const FrameGeom g, float* __restrict__ clip) {
+  // ((v / 255) - 0.5) / 0.5 for the 256 possible pixel values, each with the reference's correctly rounded fp32
+  // operations, once per block: the per-pixel epilogue becomes three shared-memory lookups instead of six divisions
+  __shared__ float lut[256];
+  lut[threadIdx.x] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(threadIdx.x), 255.f), 0.5f), 0.5f);
+  __syncthreads();
   const long long plane = static_cast<long long>(g.H) * g.W;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int w = static_cast<int>(idx % g.W);
-    const long long r = idx / g.W;
-    const int h = static_cast<int>(r % g.H);
-    const int t = static_cast<int>(r / g.H);
+  const int h = blockIdx.y, t = blockIdx.z;            // one output row per (y, z): no index division
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < g.W; w += gridDim.x * blockDim.x) {
     const uint8_t* f = frames + static_cast<size_t>(g.start + t * g.every) * g.Hs * g.Ws * 3;
     int v[3];
     if (g.Hs == g.H && g.Ws == g.W) {
@@ -929,8 +930,7 @@ __global__ void frames_to_clip_kernel(const uint8_t* __restrict__ frames, const 
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const int cs = g.bgr ? 2 - c : c;     // decoder order -> RGB (cv2.COLOR_BGR2RGB, generate_frames.py:42)
-      const float x01 = __fdiv_rn(static_cast<float>(v[cs]), 255.f);
-      dst[c * g.T * plane] = __fdiv_rn(__fsub_rn(x01, 0.5f), 0.5f);
+      dst[c * g.T * plane] = lut[v[cs]];
     }
   }
 }
@@ -2093,7 +2093,8 @@ cudaError_t ew_frames_to_clip(const uint8_t* frames, int Hs, int Ws, int bgr, in
   g.Hs = Hs; g.Ws = Ws; g.H = H; g.W = W; g.T = T; g.start = start; g.every = every; g.hflip = hflip; g.bgr = bgr;
   g.sx = static_cast<double>(Ws) / W;
   g.sy = static_cast<double>(Hs) / H;
-  frames_to_clip_kernel<<<grid_for(static_cast<long long>(T) * H * W, 256), 256, 0, st>>>(frames, g, clip);
+  if (H > 65535 || T > 65535) return cudaErrorInvalidValue;
+  frames_to_clip_kernel<<<dim3((W + 255) / 256, H, T), 256, 0, st>>>(frames, g, clip);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
