@@ -78,6 +78,80 @@ __global__ void unpack_cl_kernel(const __nv_bfloat16* __restrict__ x, int C, lon
   }
 }
 
+// Wide tensors (C > 8): a 64-voxel x 64-channel tile goes through shared memory so that BOTH sides are coalesced —
+// the fp32 NCDHW side as 256-byte runs of one channel, the channels-last side as whole 128-byte voxel rows.  The
+// direct mapping above writes 16 bytes out of every 128 per warp store (32 % of the copy bandwidth).  Tile rows are
+// 33 words apart: conflict-free for the channel-pair writes (bank = v + pair) and for the 16-byte row reads
+// (bank = v + 4*chunk + k).
+constexpr int PK_VOX = 64, PK_PITCH = 33;
+__global__ void __launch_bounds__(256)
+pack_cl_tiled_kernel(const float* __restrict__ x, int C, long long sp, long long voxels, __nv_bfloat16* __restrict__ y,
+                     int c_pitch, int c_off, int groups) {
+  __shared__ uint32_t tile[PK_VOX * PK_PITCH];
+  const int cb = blockIdx.y * 64;                      // first channel of this block's 64-channel slab
+  const long long v0 = static_cast<long long>(blockIdx.x) * PK_VOX;
+  {
+    const int vl = threadIdx.x & 63, p = threadIdx.x >> 6;
+    const long long v = v0 + vl;
+    if (v < voxels) {
+      const long long n = v / sp, s = v - n * sp;
+      const float* src = x + (n * C) * sp + s;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = cb + (p * 8 + j) * 2;
+        const float f0 = (c < C) ? __ldg(src + static_cast<long long>(c) * sp) : 0.f;
+        const float f1 = (c + 1 < C) ? __ldg(src + static_cast<long long>(c + 1) * sp) : 0.f;
+        tile[vl * PK_PITCH + p * 8 + j] = pack2(f0, f1);
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int idx = threadIdx.x + k * 256;
+    const int vl = idx >> 3, ch = idx & 7;
+    const long long v = v0 + vl;
+    if (v < voxels && (cb >> 3) + ch < groups) {
+      const uint32_t* t = tile + vl * PK_PITCH + ch * 4;
+      *reinterpret_cast<uint4*>(y + v * c_pitch + c_off + cb + ch * 8) = make_uint4(t[0], t[1], t[2], t[3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+unpack_cl_tiled_kernel(const __nv_bfloat16* __restrict__ x, int C, long long sp, long long voxels, int c_pitch, int c_off,
+                       float* __restrict__ y, int groups) {
+  __shared__ uint32_t tile[PK_VOX * PK_PITCH];
+  const int cb = blockIdx.y * 64;
+  const long long v0 = static_cast<long long>(blockIdx.x) * PK_VOX;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int idx = threadIdx.x + k * 256;
+    const int vl = idx >> 3, ch = idx & 7;
+    const long long v = v0 + vl;
+    if (v < voxels && (cb >> 3) + ch < groups) {
+      const uint4 pk = *reinterpret_cast<const uint4*>(x + v * c_pitch + c_off + cb + ch * 8);
+      uint32_t* t = tile + vl * PK_PITCH + ch * 4;
+      t[0] = pk.x; t[1] = pk.y; t[2] = pk.z; t[3] = pk.w;
+    }
+  }
+  __syncthreads();
+  const int vl = threadIdx.x & 63, p = threadIdx.x >> 6;
+  const long long v = v0 + vl;
+  if (v >= voxels) return;
+  const long long n = v / sp, s = v - n * sp;
+  float* dst = y + (n * C) * sp + s;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cb + (p * 8 + j) * 2;
+    if (c < C) {
+      const float2 f = unpack2(tile[vl * PK_PITCH + p * 8 + j]);
+      dst[static_cast<long long>(c) * sp] = f.x;
+      if (c + 1 < C) dst[static_cast<long long>(c + 1) * sp] = f.y;
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------- linear resize
 // Source index / weight rule of UpsampleTrilinear3D / ResizeBilinear (ATen rule; trilinear.py:222-233 KAT).
 // IEEE fp32, no FMA contraction, identical on host (linear_tap_host) and device -> bit-exact tables.
@@ -1655,6 +1729,9 @@ cudaError_t ew_pack_cl(const float* x, int N, int C, long long sp, __nv_bfloat16
   if (C <= 8 && groups > 1)
     pack_cl_skinny_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, C, sp, voxels, y, c_pitch,
                                                                                      c_off, groups);
+  else if (C > 8 && (voxels + PK_VOX - 1) / PK_VOX < (1LL << 31))
+    pack_cl_tiled_kernel<<<dim3(static_cast<unsigned>((voxels + PK_VOX - 1) / PK_VOX), (groups + 7) / 8), 256, 0, st>>>(
+        x, C, sp, voxels, y, c_pitch, c_off, groups);
   else
     pack_cl_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, C, sp, voxels, y, c_pitch, c_off,
                                                                               groups);
@@ -1666,8 +1743,12 @@ cudaError_t ew_unpack_cl(const __nv_bfloat16* x, int N, int C, long long sp, int
   const long long voxels = static_cast<long long>(N) * sp;
   const int groups = (C + 7) >> 3;
   const long long total = voxels * groups;
-  unpack_cl_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, C, sp, voxels, c_pitch, c_off, y,
-                                                                              groups);
+  if (C > 8 && (voxels + PK_VOX - 1) / PK_VOX < (1LL << 31))
+    unpack_cl_tiled_kernel<<<dim3(static_cast<unsigned>((voxels + PK_VOX - 1) / PK_VOX), (groups + 7) / 8), 256, 0, st>>>(
+        x, C, sp, voxels, c_pitch, c_off, y, groups);
+  else
+    unpack_cl_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, C, sp, voxels, c_pitch, c_off, y,
+                                                                                groups);
   LAUNCH_CHECK();
   return cudaSuccess;
 }

@@ -47,6 +47,26 @@ def test_conv_64_64_roundtrip_pack(hpvg_gpu):
     assert np.array_equal(back, x)
 
 
+@pytest.mark.parametrize("C,pitch,off", [(64, 64, 0), (128, 128, 0), (64, 128, 64), (20, 24, 0), (72, 80, 0),
+                                         (12, 64, 8), (3, 8, 0), (3, 64, 0)])
+def test_pack_unpack_layouts(hpvg_gpu, C, pitch, off):
+    """NCDHW fp32 <-> channels-last bf16 at the API edge: every kernel variant (shared-memory tile for wide tensors,
+    skinny, direct), channel offsets inside a wider pitch, ragged channel counts, voxel counts off the tile size, and
+    samples that straddle a tile.  Exact: the values are bf16-representable."""
+    hp, ops = hpvg_gpu, hpvg_gpu.ops
+    rng = np.random.default_rng(C * 7 + pitch + off)
+    x = bf16_round(rng.standard_normal((3, C, 2, 7, 13)))          # 182 voxels per sample: not a multiple of 64
+    cl = hp.Tensor((3, 2, 7, 13, pitch), hp.BF16)
+    cl.copy_from_host(np.full((3, 2, 7, 13, pitch), 0x3F80, np.uint16))   # 1.0 everywhere: untouched channels must stay
+    ops.pack_cl(hp.from_numpy(x), c_pitch=pitch, c_off=off, out=cl)
+    raw = hp.bf16_bits_to_f32(cl.numpy())
+    assert np.array_equal(np.moveaxis(raw[..., off:off + C], -1, 1), x)
+    lo, hi = off + C, min(pitch, (off + C + 7) // 8 * 8)                 # zero padding up to the 8-channel group
+    assert not raw[..., lo:hi].any()
+    assert np.all(raw[..., :off] == 1.0) and np.all(raw[..., hi:] == 1.0)
+    assert np.array_equal(ops.unpack_cl(cl, C=C, c_off=off).numpy(), x)
+
+
 @pytest.mark.parametrize("cout", [3, 1])
 def test_conv_tail(hpvg_gpu, cout):
     hp, ops = hpvg_gpu, hpvg_gpu.ops
