@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--train-frames", type=int, default=16,
                     help="frames of the synthetic clip at the finest scale for the train workload (BASELINE.json config 3: "
                          "16; the reference's own schedule gives 13)")
+    ap.add_argument("--no-hbm", action="store_true", help="skip the extra `hbm_kernels` table at N == 1")
     ap.add_argument("--no-graph", action="store_true", help="train iterations launched eagerly instead of as a CUDA graph")
     return ap.parse_args()
 
@@ -509,6 +510,19 @@ def run_ours(args):
                         steps=tr["steps"], warmup=tr["warmup"], scaling="replicas only", config=tr["config"],
                         e2e={"value": tr["value"], "unit": tr["unit"], "h2d_bytes_per_step": tr["h2d_bytes_per_iter"],
                              "d2h_bytes_per_step": 64})
+    if world == 1 and not args.no_hbm:
+        # achieved HBM bandwidth of the bandwidth-bound kernels on batched inputs (tools/bench_hbm.py: >= 0.5 GB per
+        # launch, CUDA events on our stream) against the measured copy peak: north_star's resize / BN / Adam target
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_hbm
+            hpvg.empty_cache()
+            line["hbm_kernels"] = [{"kernel": r["kernel"], "achieved_gbs": round(r["achieved_gbs"], 1),
+                                    "frac": round(r["frac"], 3), "mb_per_launch": round(r["bytes_per_launch"] / 1e6, 1)}
+                                   for r in bench_hbm.measure(st, out=None)]
+            line["hbm_peak"] = {"gbs": bench_hbm.peak_gbs()[0], "source": bench_hbm.peak_gbs()[1] + " copy bandwidth"}
+        except Exception as e:   # the table is evidence, never a reason to lose the headline line
+            sys.stderr.write("bench: hbm_kernels table failed: %r\n" % (e,))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores = cpu_sample_clips({"img_size": args.img_size}, args.cpu_clips)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

@@ -54,9 +54,19 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warm", type=int, default=3)
     args = ap.parse_args()
-    ITERS[0], WARM[0] = max(args.iters, 1), max(args.warm, 0)
     hpvg.init(0)
-    st = hpvg.Stream()
+    rows = measure(hpvg.Stream(), args)
+    if args.json:
+        with open(args.json, "w") as f:
+            json.dump(rows, f, indent=1)
+
+
+def measure(st, args=None, out=sys.stdout):
+    """Times every bandwidth-bound kernel on `st`; returns one dict per kernel.  bench.py calls this at N == 1 so the
+    HBM fractions sit in the same JSON line as the headline numbers (`hbm_kernels`)."""
+    if args is None:
+        args = argparse.Namespace(clips=48, wide=6, iters=10, warm=3)
+    ITERS[0], WARM[0] = max(args.iters, 1), max(args.warm, 0)
     peak, kind = peak_gbs()
     rows = []
 
@@ -64,8 +74,9 @@ def main():
         gbs = nbytes / ms / 1e6
         rows.append({"kernel": name, "bytes_per_launch": int(nbytes), "ms": ms, "achieved_gbs": gbs, "peak_gbs": peak,
                      "frac": gbs / peak, "peak_source": kind, "note": note})
-        print("%-34s %9.1f MB  %8.3f ms  %8.1f GB/s  %5.1f%% of %s peak %s" %
-              (name, nbytes / 1e6, ms, gbs, 100 * gbs / peak, kind, note), flush=True)
+        if out is not None:
+            print("%-34s %9.1f MB  %8.3f ms  %8.1f GB/s  %5.1f%% of %s peak %s" %
+                  (name, nbytes / 1e6, ms, gbs, 100 * gbs / peak, kind, note), file=out, flush=True)
 
     # ---------------------------------------------------------------- trilinear resize s8 -> s9 (images.py:54-61)
     N = args.clips
@@ -145,9 +156,7 @@ def main():
     report("mse (160M elements)", 8 * n, timed(st, lambda: ops.mse(a, b, out=out, stream=st)))
     report("kl_criterion (160M elements)", 8 * n, timed(st, lambda: ops.kl_criterion(a, b, out=out, stream=st)))
     report("mse_grad", 12 * n, timed(st, lambda: ops.mse_grad(a, b, 0.5, g=a, stream=st)))
-    if args.json:
-        with open(args.json, "w") as f:
-            json.dump(rows, f, indent=1)
+    return rows
 
 
 if __name__ == "__main__":

@@ -7,13 +7,13 @@ OUT=gpurun_out/prof_$TAG
 mkdir -p $OUT
 NCU="ncu --clock-control none"
 # ---- plain runs first
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train > $OUT/bench_sample_plain.log 2>&1 || exit 1
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train --no-hbm > $OUT/bench_sample_plain.log 2>&1 || exit 1
 python tools/train_only.py 1 1 eager > $OUT/train_plain.log 2>&1 || exit 1
 python tools/bench_hbm.py --json $OUT/hbm.json > $OUT/hbm.log 2>&1 || exit 1
 python tools/perf_conv.py > $OUT/perf_conv.log 2>&1 || exit 1
 # ---- launch lists (per-launch durations; cold-cache, serialised: compare SHARES)
 $NCU --metrics gpu__time_duration.sum --csv --log-file $OUT/launches_sample.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train > $OUT/ncu_sample.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train --no-hbm > $OUT/ncu_sample.log 2>&1
 $NCU --metrics gpu__time_duration.sum --csv --log-file $OUT/launches_train.csv \
     python tools/train_only.py 1 1 eager > $OUT/ncu_train.log 2>&1
 # ---- full captures of the dominant kernels

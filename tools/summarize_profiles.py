@@ -57,7 +57,7 @@ def full_rows(rep):
 
 
 def main():
-    for name, title in (("launches_sample.csv", "bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train (sampling, 16 clips/step)"),
+    for name, title in (("launches_sample.csv", "bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train --no-hbm (sampling, 16 clips/step)"),
                         ("launches_train.csv", "tools/train_only.py 1 1 eager (2 GAN-phase train iterations at the finest scale)")):
         p = os.path.join(src, name)
         if os.path.exists(p):
