@@ -957,54 +957,72 @@ __device__ __forceinline__ float cv_coord(int d, double scale, int& s) {
   s = static_cast<int>(fl);
   return __fsub_rn(f, fl);
 }
+constexpr int FC_ROWS = 4;      // output rows per block: a thread keeps its column coefficients for FC_ROWS x T pixels
 __global__ void __launch_bounds__(256)
 frames_to_clip_kernel(const uint8_t* __restrict__ frames, const FrameGeom g, float* __restrict__ clip) {
   // ((v / 255) - 0.5) / 0.5 for the 256 possible pixel values, each with the reference's correctly rounded fp32
   // operations, once per block: the per-pixel epilogue becomes three shared-memory lookups instead of six divisions
   __shared__ float lut[256];
+  __shared__ int yrow[FC_ROWS][4];                     // r0 * Ws * 3, r1 * Ws * 3, b0, b1 of the block's rows
   lut[threadIdx.x] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(threadIdx.x), 255.f), 0.5f), 0.5f);
+  const int h0 = blockIdx.y * FC_ROWS;
+  const int mode = (g.Hs == g.H && g.Ws == g.W) ? 0 : (g.Hs == 2 * g.H && g.Ws == 2 * g.W) ? 1 : 2;
+  if (mode == 2 && threadIdx.x < FC_ROWS && h0 + threadIdx.x < g.H) {
+    int sy;
+    const float fy = cv_coord(h0 + threadIdx.x, g.sy, sy);
+    yrow[threadIdx.x][0] = min(max(sy, 0), g.Hs - 1) * g.Ws * 3;
+    yrow[threadIdx.x][1] = min(max(sy + 1, 0), g.Hs - 1) * g.Ws * 3;
+    yrow[threadIdx.x][2] = sat_short(__float2int_rn(__fmul_rn(__fsub_rn(1.f, fy), 2048.f)));
+    yrow[threadIdx.x][3] = sat_short(__float2int_rn(__fmul_rn(fy, 2048.f)));
+  }
   __syncthreads();
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= g.W) return;
+  int x0 = 0, x1 = 0, a0 = 0, a1 = 0;                  // column taps: the same for every row and frame
+  if (mode == 2) {
+    int sx;
+    float fx = cv_coord(w, g.sx, sx);
+    if (sx < 0) { fx = 0.f; sx = 0; }
+    if (sx >= g.Ws - 1) { fx = 0.f; sx = g.Ws - 1; }
+    a0 = sat_short(__float2int_rn(__fmul_rn(__fsub_rn(1.f, fx), 2048.f)));
+    a1 = sat_short(__float2int_rn(__fmul_rn(fx, 2048.f)));
+    x0 = sx * 3;
+    x1 = min(sx + 1, g.Ws - 1) * 3;
+  }
   const long long plane = static_cast<long long>(g.H) * g.W;
-  const int h = blockIdx.y, t = blockIdx.z;            // one output row per (y, z): no index division
-  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < g.W; w += gridDim.x * blockDim.x) {
-    const uint8_t* f = frames + static_cast<size_t>(g.start + t * g.every) * g.Hs * g.Ws * 3;
-    int v[3];
-    if (g.Hs == g.H && g.Ws == g.W) {
+  const size_t fsz = static_cast<size_t>(g.Hs) * g.Ws * 3;
+  const int wo = g.hflip ? g.W - 1 - w : w;
+  const int c0 = g.bgr ? 2 : 0, cstep = g.bgr ? -1 : 1;   // decoder order -> RGB (cv2.COLOR_BGR2RGB, generate_frames.py:42)
+  const int rows = min(FC_ROWS, g.H - h0);
+  for (int t = 0; t < g.T; ++t) {
+    const uint8_t* f = frames + static_cast<size_t>(g.start + t * g.every) * fsz;
+    for (int r = 0; r < rows; ++r) {
+      const int h = h0 + r;
+      int v[3];
+      if (mode == 0) {
+        const uint8_t* p = f + (static_cast<size_t>(h) * g.Ws + w) * 3;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) v[c] = f[(static_cast<size_t>(h) * g.Ws + w) * 3 + c];
-    } else if (g.Hs == 2 * g.H && g.Ws == 2 * g.W) {
-      const uint8_t* p0 = f + (static_cast<size_t>(2 * h) * g.Ws + 2 * w) * 3;
-      const uint8_t* p1 = p0 + static_cast<size_t>(g.Ws) * 3;
+        for (int c = 0; c < 3; ++c) v[c] = p[c];
+      } else if (mode == 1) {
+        const uint8_t* p0 = f + (static_cast<size_t>(2 * h) * g.Ws + 2 * w) * 3;
+        const uint8_t* p1 = p0 + static_cast<size_t>(g.Ws) * 3;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) v[c] = (p0[c] + p0[3 + c] + p1[c] + p1[3 + c] + 2) >> 2;
-    } else {
-      int sx, sy;
-      float fx = cv_coord(w, g.sx, sx);
-      const float fy = cv_coord(h, g.sy, sy);
-      if (sx < 0) { fx = 0.f; sx = 0; }
-      if (sx >= g.Ws - 1) { fx = 0.f; sx = g.Ws - 1; }
-      const int a0 = sat_short(__float2int_rn(__fmul_rn(__fsub_rn(1.f, fx), 2048.f)));
-      const int a1 = sat_short(__float2int_rn(__fmul_rn(fx, 2048.f)));
-      const int b0 = sat_short(__float2int_rn(__fmul_rn(__fsub_rn(1.f, fy), 2048.f)));
-      const int b1 = sat_short(__float2int_rn(__fmul_rn(fy, 2048.f)));
-      const int x1 = min(sx + 1, g.Ws - 1);
-      const int r0 = min(max(sy, 0), g.Hs - 1), r1 = min(max(sy + 1, 0), g.Hs - 1);
-      const uint8_t* p0 = f + static_cast<size_t>(r0) * g.Ws * 3;
-      const uint8_t* p1 = f + static_cast<size_t>(r1) * g.Ws * 3;
+        for (int c = 0; c < 3; ++c) v[c] = (p0[c] + p0[3 + c] + p1[c] + p1[3 + c] + 2) >> 2;
+      } else {
+        const uint8_t* p0 = f + yrow[r][0];
+        const uint8_t* p1 = f + yrow[r][1];
+        const int b0 = yrow[r][2], b1 = yrow[r][3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int S0 = p0[sx * 3 + c] * a0 + p0[x1 * 3 + c] * a1;
-        const int S1 = p1[sx * 3 + c] * a0 + p1[x1 * 3 + c] * a1;
-        const int o = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
-        v[c] = min(max(o, 0), 255);
+        for (int c = 0; c < 3; ++c) {
+          const int S0 = p0[x0 + c] * a0 + p0[x1 + c] * a1;
+          const int S1 = p1[x0 + c] * a0 + p1[x1 + c] * a1;
+          const int o = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+          v[c] = min(max(o, 0), 255);
+        }
       }
-    }
-    const int wo = g.hflip ? g.W - 1 - w : w;
-    float* dst = clip + (static_cast<long long>(t) * g.H + h) * g.W + wo;
+      float* dst = clip + (static_cast<long long>(t) * g.H + h) * g.W + wo;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const int cs = g.bgr ? 2 - c : c;     // decoder order -> RGB (cv2.COLOR_BGR2RGB, generate_frames.py:42)
-      dst[c * g.T * plane] = lut[v[cs]];
+      for (int c = 0; c < 3; ++c) dst[c * g.T * plane] = lut[v[c0 + cstep * c]];
     }
   }
 }
@@ -2174,8 +2192,9 @@ cudaError_t ew_frames_to_clip(const uint8_t* frames, int Hs, int Ws, int bgr, in
   g.Hs = Hs; g.Ws = Ws; g.H = H; g.W = W; g.T = T; g.start = start; g.every = every; g.hflip = hflip; g.bgr = bgr;
   g.sx = static_cast<double>(Ws) / W;
   g.sy = static_cast<double>(Hs) / H;
-  if (H > 65535 || T > 65535) return cudaErrorInvalidValue;
-  frames_to_clip_kernel<<<dim3((W + 255) / 256, H, T), 256, 0, st>>>(frames, g, clip);
+  if ((H + FC_ROWS - 1) / FC_ROWS > 65535 || static_cast<long long>(Hs) * Ws * 3 >= (1LL << 31))
+    return cudaErrorInvalidValue;
+  frames_to_clip_kernel<<<dim3((W + 255) / 256, (H + FC_ROWS - 1) / FC_ROWS), 256, 0, st>>>(frames, g, clip);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
