@@ -418,8 +418,10 @@ int hpvg_conv_wgrad_cl(const void* x, int x_pitch, const void* gy, int gy_pitch,
                        float scale, void* st) {
   if (N <= 0 || T <= 0 || H <= 0 || W <= 0) return HPVG_OK;
   if (!g_wgrad_ws) return fail(HPVG_E_ARG, "hpvg_init was not called");
-  if ((x_pitch & 7) || (gy_pitch & 7) || x_pitch < 64 || gy_pitch < 64)
-    return fail(HPVG_E_ARG, "conv_wgrad_cl: operands must be >= 64-channel bf16 channels-last tensors");
+  if ((x_pitch & 7) || (gy_pitch & 7) || x_pitch < 8 || gy_pitch < 8)
+    return fail(HPVG_E_ARG, "conv_wgrad_cl: operands must be bf16 channels-last tensors with a pitch of 8k channels");
+  if ((x_pitch < 64 && ci_n > x_pitch) || (gy_pitch < 64 && co_n > gy_pitch))
+    return fail(HPVG_E_ARG, "conv_wgrad_cl: block extent exceeds the channels of a narrow operand");
   if (co_n < 1 || co_n > 64 || ci_n < 1 || ci_n > 64 || (kt != 1 && kt != 3))
     return fail(HPVG_E_ARG, "conv_wgrad_cl: bad block extents");
   const char* e = hpvg::conv3d_wgrad_launch(x, x_pitch, gy, gy_pitch, N, T, H, W, dw, w_cin, kt, co_off, co_n, ci_off,

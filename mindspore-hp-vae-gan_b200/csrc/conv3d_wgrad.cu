@@ -236,7 +236,10 @@ EncodeTiledFn wg_get_encode() {
 
 bool make_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, int pitch, int N, int T, int H, int W, int bw,
               int bh) {
-  cuuint64_t gd[5] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)N};
+  // a narrow tensor (pitch < 64: the 8-channel block inputs / tail gradients) is mapped with its real channel count:
+  // the box still spans 64 channels and TMA zero-fills the out-of-bounds ones, so no zero-padded 64-channel copy of a
+  // 3-channel tensor ever exists in HBM (it used to cost a pack kernel and 8x the operand traffic)
+  cuuint64_t gd[5] = {(cuuint64_t)(pitch < 64 ? pitch : 64), (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)N};
   const cuuint64_t vox = static_cast<cuuint64_t>(pitch) * 2;
   cuuint64_t gs[4] = {vox, vox * W, vox * W * H, vox * W * H * T};
   cuuint32_t bx[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
@@ -253,7 +256,8 @@ size_t conv3d_wgrad_workspace_bytes(int sm_count) {
   return static_cast<size_t>(groups) * 27 * 4096 * sizeof(float);
 }
 
-// x: bf16 cl (N,T,H,W,x_pitch) [64 channels starting at x], gy: bf16 cl (N,T,H,W,gy_pitch) [64 channels at gy]
+// x: bf16 cl (N,T,H,W,x_pitch) [64 channels starting at x], gy: bf16 cl (N,T,H,W,gy_pitch) [64 channels at gy];
+// a pitch below 64 (multiple of 8) means "all channels of a narrow tensor, the rest zero"
 // dw: fp32 (w_cout, w_cin, kt, 3, 3); the 64x64 block at (co_off, ci_off) is written (or accumulated into).
 const char* conv3d_wgrad_launch(const void* x, int x_pitch, const void* gy, int gy_pitch, int N, int T, int H, int W,
                                 float* dw, int w_cin, int kt, int co_off, int co_n, int ci_off, int ci_n, int accumulate,

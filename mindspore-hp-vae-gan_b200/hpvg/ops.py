@@ -404,10 +404,13 @@ def adam_clip_multi(params, grads, ms, vs, lrs, step, beta1=0.5, beta2=0.999, ep
 # ================================================================================================ backward operators
 def conv_wgrad_cl(x_cl, gy_cl, dw, co_off=0, co_n=64, ci_off=0, ci_n=64, x_coff=0, gy_coff=0, accumulate=False,
                   scale=1.0, stream=None):
-    """dW block (+)= scale * sum_v gy[v] (x) x[v+tap].  x_cl / gy_cl: bf16 cl with >= 64 channels; dw: fp32
+    """dW block (+)= scale * sum_v gy[v] (x) x[v+tap].  x_cl / gy_cl: bf16 cl, either >= 64 channels (a 64-channel
+    slice at x_coff / gy_coff) or a narrow tensor (pitch 8..56: all of its channels, the rest read as zero); dw: fp32
     (Cout, Cin, [kt,] 3, 3)."""
     N, T, H, W, xp = x_cl.shape
     gp = gy_cl.shape[-1]
+    if (xp < 64 and x_coff) or (gp < 64 and gy_coff):
+        raise HpvgError("conv_wgrad_cl: a narrow operand cannot be sliced")
     kt = dw.shape[2] if len(dw.shape) == 5 else 1
     check(lib.hpvg_conv_wgrad_cl(ctypes.c_void_p(x_cl.ptr + 2 * x_coff), xp, ctypes.c_void_p(gy_cl.ptr + 2 * gy_coff),
                                  gp, N, T, H, W, _p(dw), dw.shape[1], kt, co_off, co_n, ci_off, ci_n,

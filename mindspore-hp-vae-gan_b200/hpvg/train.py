@@ -327,7 +327,7 @@ def block_backward(block, ctxs, g_out, grads, ws, tag, need_dx, trainable=True, 
     g_pre = ops.tanh_bwd(g_out, o, gpre=ws.get(tag + ".gpre", o.shape, F32), stream=stream)
     if trainable:
         ops.channel_sum(g_pre, grads.of(tail.p["bias"]), accumulate=True, stream=stream)
-    gy = ops.pack_cl(g_pre, c_pitch=64, zero_to=64, out=ws.get(tag + ".gtail", (N, T, H, W, 64), BF16), stream=stream)
+    gy = ops.pack_cl(g_pre, c_pitch=8, out=ws.get(tag + ".gtail", (N, T, H, W, 8), BF16), stream=stream)
     ga = conv_backward(tail, tail_ctx, gy, grads, ws, tag + ".t", True, trainable, stream=stream)
     dx = None
     for j in range(len(block.layers) - 2, -1, -1):
@@ -383,11 +383,8 @@ class GeneratorTrainer:
         ops.upsample_noise_pack(x_prev, size, noise=noise_t, amp=amp, seed=seed, sample_base=base,
                                 up=up, xin=xin, stream=stream, d_sample_offset=self.draws)
         x_wide = None
-        if wide:   # 64-channel zero-padded copy for the head conv's weight gradient
-            f = ops.unpack_cl(xin, C=opt.nc_im, out=self.ws.get("xinf%d" % idx, (N, opt.nc_im) + size, F32),
-                              stream=stream)
-            x_wide = ops.pack_cl(f, c_pitch=64, zero_to=64, out=self.ws.get("xinw%d" % idx, (N,) + size + (64,), BF16),
-                                 stream=stream)
+        if wide:   # the head conv's weight gradient reads the 8-channel block input itself (TMA zero-fills 8..63)
+            x_wide = xin
         return up, xin, x_wide
 
     def prepare_shared(self, stream=None):
@@ -421,7 +418,7 @@ class GeneratorTrainer:
             h = x_cl
             xw = None
             if save_encoder:
-                xw = ops.pack_cl(video, c_pitch=64, zero_to=64, stream=stream)
+                xw = x_cl
             for i, l in enumerate(enc._features.layers):
                 h, c = layer_forward_train(l, h, ws, "enc.%d" % i, stream)
                 if i == 0 and xw is not None:
@@ -588,8 +585,7 @@ class DWithLoss:
         D, ws = self._netD, self.ws
         N = x.shape[0]
         x8 = ops.pack_cl(x, c_pitch=8, out=ws.get(tag + ".x8", (N,) + tuple(x.shape[2:]) + (8,), BF16), stream=stream)
-        xw = ops.pack_cl(x, c_pitch=64, zero_to=64, out=ws.get(tag + ".xw", (N,) + tuple(x.shape[2:]) + (64,), BF16),
-                         stream=stream)
+        xw = x8       # narrow operand of the head conv's weight gradient
         ctxs = []
         sn_tape_prepare(self._layers(), ws, tag, stream)
         h, c = layer_forward_train(D.head, x8, ws, tag + ".h", stream)
@@ -614,7 +610,7 @@ class DWithLoss:
         N, _, T, H, W = out.shape
         go = ops.fill(ws.get(tag + ".go", out.shape, F32), coef, stream)
         ops.channel_sum(go, g.of(D.tail.p["bias"]), accumulate=True, stream=stream)
-        gy = ops.pack_cl(go, c_pitch=64, zero_to=64, out=ws.get(tag + ".gyt", (N, T, H, W, 64), BF16), stream=stream)
+        gy = ops.pack_cl(go, c_pitch=8, out=ws.get(tag + ".gyt", (N, T, H, W, 8), BF16), stream=stream)
         # every D layer is SN-conv + LeakyReLU (no BatchNorm): each data-gradient conv applies the LeakyReLU' of the
         # layer below in its epilogue, so no separate lrelu-backward pass runs
         ga = conv_backward(D.tail, ctxs[-1], gy, g, ws, tag + ".t", True, True, stream=stream, mask_input=True)
@@ -631,8 +627,7 @@ class DWithLoss:
         N, _, T, H, W = out.shape
         # (1) input gradient of sum D(xhat): deltas[j] = grad wrt the pre-activation of layer j
         ones = ops.fill(ws.get(tag + ".ones", out.shape, F32), 1.0, stream)
-        d_out = ops.pack_cl(ones, c_pitch=64, zero_to=64, out=ws.get(tag + ".dout", (N, T, H, W, 64), BF16),
-                            stream=stream)
+        d_out = ops.pack_cl(ones, c_pitch=8, out=ws.get(tag + ".dout", (N, T, H, W, 8), BF16), stream=stream)
         # LeakyReLU' of the layer below is applied in each data-gradient conv's epilogue: its output IS delta[j-1]
         nl = len(layers)
         dshape = ctxs[-1]["x"].shape
@@ -648,9 +643,8 @@ class DWithLoss:
         Gx, gp = ops.gp_grad(grad_x, self.lambda_grad, Gout=ws.get(tag + ".G", grad_x.shape, F32),
                              gp=self.terms.slot(1.0), stream=stream)
         # (2) d GP / d W: push G forward through the SAME linear maps, masked by the LeakyReLU pattern of xhat
-        xi_wide = ops.pack_cl(Gx, c_pitch=64, zero_to=64, out=ws.get(tag + ".xiw", (N, T, H, W, 64), BF16),
-                              stream=stream)
         xi8 = ops.pack_cl(Gx, c_pitch=8, out=ws.get(tag + ".xi8", (N, T, H, W, 8), BF16), stream=stream)
+        xi_wide = xi8
         unit = _unit_affine(stream)
         zero_shift = unit.view((64,), F32, 256)
         xi = xi8

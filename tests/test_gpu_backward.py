@@ -51,6 +51,29 @@ def test_wgrad_skinny_layers_via_zero_padding(hpvg_gpu):
     assert rel_l2(dw2.numpy(), w2.grad.numpy()) < TOL
 
 
+def test_wgrad_narrow_operands_equal_zero_padded_ones(hpvg_gpu):
+    """Head / tail convs in the train step: the 8-channel tensors go to the weight-gradient kernel as they are (the
+    tensor map carries their real channel count, TMA zero-fills channels 8..63 of the box) — bit-identical to the
+    64-channel zero-padded copy that used to be materialised."""
+    hp, ops = hpvg_gpu, hpvg_gpu.ops
+    N, T, H, W = 2, 5, 21, 70          # ragged last W segment, more than one H block
+    rng = np.random.default_rng(11)
+    x3 = hp.from_numpy(bf16_round(rng.standard_normal((N, 3, T, H, W))))
+    gy3 = hp.from_numpy(bf16_round(rng.standard_normal((N, 3, T, H, W))))
+    x = ops.pack_cl(hp.from_numpy(bf16_round(rng.standard_normal((N, 64, T, H, W)))))
+    gy = ops.pack_cl(hp.from_numpy(bf16_round(rng.standard_normal((N, 64, T, H, W)))))
+    a, b = hp.Tensor((64, 3, 3, 3, 3), hp.F32), hp.Tensor((64, 3, 3, 3, 3), hp.F32)
+    ops.conv_wgrad_cl(ops.pack_cl(x3, c_pitch=64, zero_to=64), gy, a, ci_n=3)
+    ops.conv_wgrad_cl(ops.pack_cl(x3, c_pitch=8), gy, b, ci_n=3)
+    assert np.array_equal(a.numpy(), b.numpy()) and np.abs(a.numpy()).max() > 0
+    c, d = hp.Tensor((3, 64, 3, 3, 3), hp.F32), hp.Tensor((3, 64, 3, 3, 3), hp.F32)
+    ops.conv_wgrad_cl(x, ops.pack_cl(gy3, c_pitch=64, zero_to=64), c, co_n=3)
+    ops.conv_wgrad_cl(x, ops.pack_cl(gy3, c_pitch=8), d, co_n=3)
+    assert np.array_equal(c.numpy(), d.numpy()) and np.abs(c.numpy()).max() > 0
+    with pytest.raises(hp.HpvgError):   # a block wider than the narrow operand
+        ops.conv_wgrad_cl(ops.pack_cl(x3, c_pitch=8), gy, hp.Tensor((64, 64, 3, 3, 3), hp.F32), ci_n=64)
+
+
 def test_wgrad_2d(hpvg_gpu):
     hp, ops = hpvg_gpu, hpvg_gpu.ops
     rng = np.random.default_rng(2)
