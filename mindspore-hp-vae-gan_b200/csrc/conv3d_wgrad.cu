@@ -38,6 +38,7 @@ constexpr int WG_SMEM = 1024 + WG_STAGES * WG_STAGE + 64;
 struct WgradParams {
   int N, T, H, W;
   int h_blocks, w_segs, n_tiles, groups;
+  int ncols;        // MMA N: 64, or 16 when gy is a narrow tensor (tail convs: co_n <= 16) — a quarter of the MMA time
   float* partial;   // [groups][27][64 ci][64 co]
 };
 
@@ -97,8 +98,8 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     __syncwarp();
   } else if (warp == 1) {
     if (elect_one()) {
-      const uint32_t idesc128 = make_idesc_bf16(128, 64, 1, 1);
-      const uint32_t idesc64 = make_idesc_bf16(64, 64, 1, 1);
+      const uint32_t idesc128 = make_idesc_bf16(128, p.ncols, 1, 1);
+      const uint32_t idesc64 = make_idesc_bf16(64, p.ncols, 1, 1);
       uint32_t j = 0;
       uint32_t accum = 0;
       for (int tile = g; tile < p.n_tiles; tile += p.groups) {
@@ -276,6 +277,7 @@ const char* conv3d_wgrad_launch(const void* x, int x_pitch, const void* gy, int 
   if (groups > p.n_tiles) groups = p.n_tiles;
   if (groups < 1) groups = 1;
   p.groups = groups;
+  p.ncols = (co_n <= 16) ? 16 : 64;      // accumulator columns >= ncols are never written and never read back
   p.partial = workspace;
   static bool configured = false;
   if (!configured) {
