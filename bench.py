@@ -519,7 +519,7 @@ def run_ours(args):
             hpvg.empty_cache()
             line["hbm_kernels"] = [{"kernel": r["kernel"], "achieved_gbs": round(r["achieved_gbs"], 1),
                                     "frac": round(r["frac"], 3), "mb_per_launch": round(r["bytes_per_launch"] / 1e6, 1)}
-                                   for r in bench_hbm.measure(st, out=None)]
+                                   for r in bench_hbm.measure(st, log=None)]
             line["hbm_peak"] = {"gbs": bench_hbm.peak_gbs()[0], "source": bench_hbm.peak_gbs()[1] + " copy bandwidth"}
         except Exception as e:   # the table is evidence, never a reason to lose the headline line
             sys.stderr.write("bench: hbm_kernels table failed: %r\n" % (e,))

@@ -61,7 +61,7 @@ def main():
             json.dump(rows, f, indent=1)
 
 
-def measure(st, args=None, out=sys.stdout):
+def measure(st, args=None, log=sys.stdout):
     """Times every bandwidth-bound kernel on `st`; returns one dict per kernel.  bench.py calls this at N == 1 so the
     HBM fractions sit in the same JSON line as the headline numbers (`hbm_kernels`)."""
     if args is None:
@@ -74,9 +74,9 @@ def measure(st, args=None, out=sys.stdout):
         gbs = nbytes / ms / 1e6
         rows.append({"kernel": name, "bytes_per_launch": int(nbytes), "ms": ms, "achieved_gbs": gbs, "peak_gbs": peak,
                      "frac": gbs / peak, "peak_source": kind, "note": note})
-        if out is not None:
+        if log is not None:
             print("%-34s %9.1f MB  %8.3f ms  %8.1f GB/s  %5.1f%% of %s peak %s" %
-                  (name, nbytes / 1e6, ms, gbs, 100 * gbs / peak, kind, note), file=out, flush=True)
+                  (name, nbytes / 1e6, ms, gbs, 100 * gbs / peak, kind, note), file=log, flush=True)
 
     # ---------------------------------------------------------------- trilinear resize s8 -> s9 (images.py:54-61)
     N = args.clips
