@@ -723,17 +723,21 @@ __host__ __device__ __forceinline__ InvTap make_inv_tap(int i, int n_in, int n_o
 }
 
 constexpr int BW_TX = 32, BW_TY = 8;
-// The block first stages the gy window of its 32 x 8 source tile for ALL output frames in shared memory (coalesced
-// row segments, every load independent: the register-only version spent 12 of 16 cycles per instruction waiting on
-// its serial per-frame gathers), then each thread reduces its <= NH x NW window per frame out of shared memory.
+// Adjoint in two register-resident stages per block (source tile 32 x 8, all frames):
+//   1. T first: every gy column of the tile's window (rows x cols, halo included) is walked along T_out by one thread —
+//      coalesced, all of a column's loads issued back to back (predicated, no control flow) — and reduced straight to
+//      the TI source frames with the constant-bank walk; the TI values go to shared memory [TI][rows][cols].
+//   2. H / W: each source voxel's thread gathers its <= NH x NW window per source frame from shared memory.
+// Reducing T before H / W runs the 3 x 3 gather TI (7) instead of To (13) times and never stages raw gy in shared
+// memory; fixed summation order => deterministic, no atomics.
 struct BwdWin {
   int rows, cols;     // window extent (max over blocks, computed on the host with the same tap functions)
 };
-template <int NH, int NW, int TI>   // compile-time bounds on the contributing rows / columns (floor(2/scale) + 1), frames
+template <int NH, int NW, int TI, int NK>   // bounds: contributing rows / columns, source frames, outputs per frame
 __global__ void __launch_bounds__(BW_TX * BW_TY)
 resize3d_bwd_colwalk_kernel(const float* __restrict__ gy, const ResizeGeom g, const __grid_constant__ TWalk w,
                             const BwdWin win, float* __restrict__ gx) {
-  extern __shared__ __align__(16) float bw_sm[];          // [To][win.rows][win.cols]
+  extern __shared__ __align__(16) float bw_sm[];          // [TI][win.rows][win.cols]
   __shared__ InvTap htab[BW_TY], wtab[BW_TX];
   const int tid = threadIdx.y * BW_TX + threadIdx.x;
   const int hs0 = blockIdx.y * BW_TY, wi0 = blockIdx.x * BW_TX;
@@ -749,24 +753,42 @@ resize3d_bwd_colwalk_kernel(const float* __restrict__ gy, const ResizeGeom g, co
   const int ho_lo = htab[0].lo, wo_lo = wtab[0].lo;
   const int rows = min(htab[BW_TY - 1].lo + htab[BW_TY - 1].n, g.Ho) - ho_lo;      // <= win.rows
   const int cols = min(wtab[BW_TX - 1].lo + wtab[BW_TX - 1].n, g.Wo) - wo_lo;      // <= win.cols
+  const int fstride = win.rows * win.cols;
   {
-    const float* src = gy + (nc * g.To * plane_o + ho_lo * g.Wo + wo_lo);
+    const char* src = reinterpret_cast<const char*>(gy + (nc * g.To * plane_o + ho_lo * g.Wo + wo_lo));
+    const unsigned plane4 = plane_o * 4u;
     const int warp = tid >> 5, lane = tid & 31;
-    const int n_rows = g.To * rows;
-    int to = 0, r = warp;                                  // (frame, row) of the row segment this warp copies next
-    while (r >= rows) { r -= rows; ++to; }
-    for (int i = warp; i < n_rows; i += BW_TY) {
-      const float* srow = src + (static_cast<unsigned>(to) * plane_o + r * g.Wo);
-      float* drow = bw_sm + (to * win.rows + r) * win.cols;
-      // 4-byte cp.async: global -> shared without a register round trip, so every copy of the tile is in flight at
-      // once (a load/store loop serialises on each store's scoreboard wait)
-      for (int c = lane; c < cols; c += 32)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(
-                         __cvta_generic_to_shared(drow + c))), "l"(srow + c) : "memory");
-      r += BW_TY;
-      while (r >= rows) { r -= rows; ++to; }
+    for (int r = warp; r < rows; r += BW_TY) {
+      for (int c = lane; c < cols; c += 32) {
+        const char* p = src + static_cast<unsigned>(r * g.Wo + c) * 4u;
+        float gv[TI][NK];
+        unsigned to = 0;                                   // block-uniform
+#pragma unroll
+        for (int f = 0; f < TI; ++f) {
+          const int n = w.n[f];
+#pragma unroll
+          for (int k = 0; k < NK; ++k)
+            gv[f][k] = (k < n) ? __ldg(reinterpret_cast<const float*>(p + static_cast<unsigned long long>(to + k) * plane4))
+                               : 0.f;
+          to += n;
+        }
+        float acc[TI];
+#pragma unroll
+        for (int f = 0; f < TI; ++f) acc[f] = 0.f;
+#pragma unroll
+        for (int f = 0; f < TI; ++f) {
+#pragma unroll
+          for (int k = 0; k < NK; ++k) {                   // lambdas past n[f] are zero (make_twalk)
+            acc[f] = fmaf(w.l0[f][k], gv[f][k], acc[f]);
+            if (f == TI - 1) acc[f] = fmaf(w.l1[f][k], gv[f][k], acc[f]);
+            else acc[f + 1] = fmaf(w.l1[f][k], gv[f][k], acc[f + 1]);
+          }
+        }
+        float* d = bw_sm + r * win.cols + c;
+#pragma unroll
+        for (int f = 0; f < TI; ++f) d[f * fstride] = acc[f];
+      }
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
   }
   __syncthreads();
   const int hs = hs0 + threadIdx.y, wi = wi0 + threadIdx.x;
@@ -778,33 +800,20 @@ resize3d_bwd_colwalk_kernel(const float* __restrict__ gy, const ResizeGeom g, co
   for (int k = 0; k < NH; ++k)
 #pragma unroll
     for (int j = 0; j < NW; ++j) off[k][j] = (k < eh.n ? k : 0) * win.cols + (j < ew.n ? j : 0);
-  const int fstride = win.rows * win.cols;
-  float acc[TI];
-#pragma unroll
-  for (int f = 0; f < TI; ++f) acc[f] = 0.f;
-#pragma unroll
-  for (int f = 0; f < TI; ++f) {
-    const int n = w.n[f];
-#pragma unroll
-    for (int q = 0; q < CW_MAX_PER_FRAME; ++q) {
-      if (q >= n) break;
-      float s = 0.f;
-#pragma unroll
-      for (int k = 0; k < NH; ++k) {
-        float r = 0.f;
-#pragma unroll
-        for (int j = 0; j < NW; ++j) r = fmaf(ew.c[j], wp[off[k][j]], r);
-        s = fmaf(eh.c[k], r, s);
-      }
-      wp += fstride;
-      acc[f] = fmaf(w.l0[f][q], s, acc[f]);
-      if (f == TI - 1) acc[f] = fmaf(w.l1[f][q], s, acc[f]);
-      else acc[f + 1] = fmaf(w.l1[f][q], s, acc[f + 1]);
-    }
-  }
   float* dst = gx + (nc * TI * plane_i + hs * g.Wi + wi);
 #pragma unroll
-  for (int f = 0; f < TI; ++f) dst[static_cast<size_t>(f) * plane_i] = acc[f];
+  for (int f = 0; f < TI; ++f) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NH; ++k) {
+      float r = 0.f;
+#pragma unroll
+      for (int j = 0; j < NW; ++j) r = fmaf(ew.c[j], wp[off[k][j]], r);
+      s = fmaf(eh.c[k], r, s);
+    }
+    wp += fstride;
+    dst[static_cast<size_t>(f) * plane_i] = s;
+  }
 }
 
 // backward: a thread owns (source row hs, column wo) and walks along T_out with register accumulators for the (at
@@ -1923,7 +1932,7 @@ static bool plan_bwd_window(const ResizeGeom& g, BwdWin* win, size_t* bytes) {
     if (hi - a.lo > win->cols) win->cols = hi - a.lo;
   }
   win->cols |= 1;   // odd row pitch: the ~1.26-strided window reads spread over the banks
-  *bytes = static_cast<size_t>(g.To) * win->rows * win->cols * sizeof(float);
+  *bytes = static_cast<size_t>(g.Ti) * win->rows * win->cols * sizeof(float);
   return *bytes <= 100 * 1024;
 }
 
@@ -1944,29 +1953,35 @@ cudaError_t ew_resize3d_bwd(const float* gy, long long NC, int To, int Ho, int W
     const dim3 grid((Wi + BW_TX - 1) / BW_TX, (Hi + BW_TY - 1) / BW_TY, static_cast<unsigned>(NC));
     const dim3 block(BW_TX, BW_TY);
     const int nh = (Ho == 1) ? 1 : static_cast<int>(2.0f / g.sh) + 1, nw = (Wo == 1) ? 1 : static_cast<int>(2.0f / g.sw) + 1;
-#define HPVG_BW(H_, W_, T_)                                                                                        \
+    int max_n = 0;
+    for (int f = 0; f < CW_MAX_TI; ++f) max_n = tw.n[f] > max_n ? tw.n[f] : max_n;
+#define HPVG_BW(H_, W_, T_, K_)                                                                                    \
   {                                                                                                                \
     static bool ok_ = false;                                                                                       \
     if (!ok_) {                                                                                                    \
-      cudaError_t e_ = cudaFuncSetAttribute(resize3d_bwd_colwalk_kernel<H_, W_, T_>,                               \
+      cudaError_t e_ = cudaFuncSetAttribute(resize3d_bwd_colwalk_kernel<H_, W_, T_, K_>,                           \
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);              \
       if (e_ != cudaSuccess) return e_;                                                                            \
       ok_ = true;                                                                                                  \
     }                                                                                                              \
-    resize3d_bwd_colwalk_kernel<H_, W_, T_><<<grid, block, bw_smem, st>>>(gy, g, tw, win, gx);                     \
+    resize3d_bwd_colwalk_kernel<H_, W_, T_, K_><<<grid, block, bw_smem, st>>>(gy, g, tw, win, gx);                 \
   }
-#define HPVG_BWT(H_, W_)                    \
-    switch (Ti) {                             \
-      case 1: HPVG_BW(H_, W_, 1); break;      \
-      case 2: HPVG_BW(H_, W_, 2); break;      \
-      case 3: HPVG_BW(H_, W_, 3); break;      \
-      case 4: HPVG_BW(H_, W_, 4); break;      \
-      case 5: HPVG_BW(H_, W_, 5); break;      \
-      case 6: HPVG_BW(H_, W_, 6); break;      \
-      case 7: HPVG_BW(H_, W_, 7); break;      \
-      default: HPVG_BW(H_, W_, 8); break;     \
+#define HPVG_BWT(H_, W_, K_)                    \
+    switch (Ti) {                                 \
+      case 1: HPVG_BW(H_, W_, 1, K_); break;      \
+      case 2: HPVG_BW(H_, W_, 2, K_); break;      \
+      case 3: HPVG_BW(H_, W_, 3, K_); break;      \
+      case 4: HPVG_BW(H_, W_, 4, K_); break;      \
+      case 5: HPVG_BW(H_, W_, 5, K_); break;      \
+      case 6: HPVG_BW(H_, W_, 6, K_); break;      \
+      case 7: HPVG_BW(H_, W_, 7, K_); break;      \
+      default: HPVG_BW(H_, W_, 8, K_); break;     \
     }
-    if (nh <= 3 && nw <= 3) { HPVG_BWT(3, 3) } else { HPVG_BWT(4, 4) }
+    if (nh <= 3 && nw <= 3) {
+      if (max_n <= 2) { HPVG_BWT(3, 3, 2) } else { HPVG_BWT(3, 3, 4) }
+    } else {
+      if (max_n <= 2) { HPVG_BWT(4, 4, 2) } else { HPVG_BWT(4, 4, 4) }
+    }
 #undef HPVG_BWT
 #undef HPVG_BW
   } else if (NC <= 65535 && plan_bwd_tiles(g, &tg, &smem)) {
