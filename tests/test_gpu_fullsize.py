@@ -1,8 +1,10 @@
-"""Parity at BASELINE.json's FULL sizes (finest scale 13 x 192 x 257, full 10-scale pyramid) through size-independent
-properties — the CPU oracle would need minutes per case here, so these tests use identities the operators must
-satisfy exactly or to bf16 round-off: linearity, adjointness (<Ax, y> == <x, A^T y>), Euler's identity for the weight
-gradient, partition of unity, batch / shard invariance, and agreement between the fused and the stand-alone
-statistics paths.  The small-size oracle comparisons live in the other test files."""
+"""Parity at BASELINE.json's FULL sizes (finest scale 13 x 192 x 257 / 16 x 192 x 257, full 10-scale pyramid).
+The whole pyramid or a whole train step would cost the CPU oracle minutes per case, so those are covered by
+size-independent identities the operators must satisfy exactly or to bf16 round-off: linearity, adjointness
+(<Ax, y> == <x, A^T y>), Euler's identity for the weight gradient, partition of unity, batch / shard invariance, and
+agreement between the fused and the stand-alone statistics paths.  Single layers and single networks at the full
+size ARE within the oracle's reach (seconds of oneDNN): the second half of the file compares them value by value.
+The small-size oracle comparisons live in the other test files."""
 import numpy as np
 import pytest
 
@@ -124,3 +126,101 @@ def test_full_pyramid_sample_is_batch_and_slot_invariant(hpvg_gpu):
     idx1, alone = sampling.generate(net, amps, 3, rank=2, world=3, batch=1, seed=5)     # only sample 2, batch of one
     assert idx1 == [2] and np.array_equal(alone[0], clips[2])
     assert not np.array_equal(clips[0], clips[1])
+
+
+# ------------------------------------------------------------------------------------------- direct oracle, full size
+# A single layer at the full size IS within reach of the CPU oracle (a few seconds of oneDNN on the box's host cores):
+# the three operators that carry the work — conv fprop, its weight gradient, the pyramid resize — are also compared
+# value by value at BASELINE.json's sizes, including the 16-frame finest scale of config 3.
+@pytest.mark.parametrize("frames", [13, 16])
+def test_conv_block_matches_oracle_at_full_size(hpvg_gpu, frames):
+    """ConvBlock3D without BatchNorm (networks_3d.py:45-54: Conv3d 3x3x3 pad 1 + bias -> LeakyReLU(0.2)), 64 -> 64."""
+    import torch
+    import torch.nn.functional as F
+    hp, ops = hpvg_gpu, hpvg_gpu.ops
+    rng = np.random.default_rng(frames)
+    T, H, W = frames, FULL[1], FULL[2]
+    x = bf16_round(rng.standard_normal((1, 64, T, H, W)))
+    w = bf16_round(rng.standard_normal((64, 64, 3, 3, 3)) * 0.02)
+    b = (rng.standard_normal(64) * 0.1).astype(np.float32)
+    aff = hp.from_numpy(np.stack([np.ones(64, np.float32), b]))
+    y = ops.unpack_cl(ops.conv3d_cl_any(ops.pack_cl(hp.from_numpy(x)), hp.from_numpy(w), aff, ops.ACT_LRELU, 64, 64)).numpy()
+    with torch.no_grad():
+        ref = F.leaky_relu(F.conv3d(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b), padding=1), 0.2).numpy()
+    assert rel_l2(y, ref) < 4e-3          # bf16 output rounding only: operands are bf16-exact, accumulation fp32
+    assert np.max(np.abs(y - ref)) < 2e-2
+
+
+def test_wgrad_matches_oracle_at_full_size(hpvg_gpu):
+    """MindSpore autodiff of Conv3d wrt its weight (restated with torch-CPU autograd) on one full-size layer."""
+    import torch
+    import torch.nn.functional as F
+    hp, ops = hpvg_gpu, hpvg_gpu.ops
+    rng = np.random.default_rng(7)
+    T, H, W = FULL
+    x = bf16_round(rng.standard_normal((1, 64, T, H, W)))
+    gy = bf16_round(rng.standard_normal((1, 64, T, H, W)))
+    w = torch.zeros(64, 64, 3, 3, 3, requires_grad=True)
+    F.conv3d(torch.from_numpy(x), w, None, padding=1).backward(torch.from_numpy(gy))
+    dw = hp.Tensor((64, 64, 3, 3, 3), hp.F32)
+    ops.conv_wgrad_cl(ops.pack_cl(hp.from_numpy(x)), ops.pack_cl(hp.from_numpy(gy)), dw)
+    assert rel_l2(dw.numpy(), w.grad.numpy()) < 1e-4     # bf16-exact operands, fp32 accumulation over 641 k voxels
+
+
+def test_resize_matches_oracle_at_full_size(hpvg_gpu):
+    """UpsampleTrilinear3D(align_corners=True) s8 -> s9 (images.py:54-61) and its adjoint, against the numpy oracle."""
+    from oracle import hpvg_oracle as orc
+    hp = hpvg_gpu
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((2, 3) + PREV).astype(np.float32)
+    y = hp.ops.resize3d(hp.from_numpy(x), FULL).numpy()
+    ref = orc.resize_linear_np(x, FULL, True)
+    assert np.max(np.abs(y - ref)) <= 1e-6 and float(np.mean(y == ref)) > 0.99
+    gy = rng.standard_normal((2, 3) + FULL).astype(np.float32)
+    gx = hp.ops.resize3d_bwd(hp.from_numpy(gy), PREV).numpy()
+    assert rel_l2(gx, orc.resize_linear_bwd_np(gy, PREV, True)) < 1e-6
+
+
+
+def test_discriminator_matches_oracle_at_full_size(hpvg_gpu):
+    """WDiscriminator3D (networks_3d.py:170-193: SN head 3 -> 64, five SN 64 -> 64 blocks, plain tail 64 -> 1) on one
+    full-size clip, spectral-norm power iteration included."""
+    import torch
+    from oracle import hpvg_oracle as orc
+    hp = hpvg_gpu
+    from hpvg import networks_3d as n3
+    from hpvg.utils import images as uimg
+    opt, oopt = uimg.default_opt(), orc.default_opt()
+    params = orc.init_discriminator_params(oopt, seed=21)
+    d = n3.WDiscriminator3D(opt)
+    d.load_parameters(params)
+    x = np.tanh(np.random.default_rng(3).standard_normal((1, 3) + FULL)).astype(np.float32)
+    with torch.no_grad():
+        ref = orc.discriminator(torch.from_numpy(x), orc.to_torch(params), oopt).numpy()
+    out = d(hp.from_numpy(x)).numpy()
+    assert out.shape == ref.shape == (1, 1) + FULL
+    assert rel_l2(out, ref) < 1e-2          # 7 bf16-operand layers deep
+
+
+def test_body_block_train_mode_matches_oracle_at_full_size(hpvg_gpu):
+    """One refinement block (networks_3d.py:395-401: 3 -> 64 -> 64 x 4 -> 3, BatchNorm in training mode — batch statistics
+    over all 641 k voxels fused into the conv epilogues) + residual + tanh at the finest scale."""
+    import torch
+    from oracle import hpvg_oracle as orc
+    hp = hpvg_gpu
+    from hpvg import networks_3d as n3
+    from hpvg.utils import images as uimg
+    opt, oopt = uimg.default_opt(), orc.default_opt()
+    params = orc.init_generator_params(oopt, 1, seed=31)
+    net = n3.GeneratorHPVAEGAN(opt)
+    net.init_next_stage()
+    net.load_parameters(params)
+    net.set_train(True)
+    up = np.tanh(np.random.default_rng(4).standard_normal((1, 3) + FULL)).astype(np.float32)
+    pt = orc.to_torch(params)
+    with torch.no_grad():
+        ref = torch.tanh(orc.block_forward(torch.from_numpy(up), pt, "body.0.", oopt, True) + torch.from_numpy(up)).numpy()
+    x_in = hp.ops.pack_cl(hp.from_numpy(up), c_pitch=8)
+    net.bn_slab.reset()                     # what construct() does at the start of a pass
+    out = net._run_block(net.body[0], x_in, hp.from_numpy(up), "t", None).numpy()
+    assert rel_l2(out, ref) < 1e-2
