@@ -203,8 +203,10 @@ int hpvg_adam_clip_multi(int n_tensors, float* const* d_params, const float* con
 /* ---------------------------------------------------------------- backward (hand-restated MindSpore autodiff)
  * Data gradient of a conv = hpvg_conv_cl with a filter bank packed with transpose_flip = 1.
  * Weight gradient: dW[(co_off+co)][(ci_off+ci)][tap] (+)= scale * sum_v gy[v][co] * x[v+tap][ci] for the 64x64 channel
- * block starting at d_x / d_gy (bf16 cl, >= 64 channels per voxel; skinny layers are zero-padded to 64 and cropped
- * with co_n / ci_n).  d_dw: fp32 (Cout, w_cin, kt, 3, 3). */
+ * block starting at d_x / d_gy (bf16 cl).  A pitch >= 64 selects the 64-channel slice at the pointer; a pitch of
+ * 8..56 (multiple of 8) is a NARROW operand — the 8-channel block inputs of head convs, the 8-channel output
+ * gradients of tail convs — read as it is: all of its channels, the rest of the 64-wide block as zero (TMA
+ * out-of-bounds fill), cropped with co_n / ci_n.  d_dw: fp32 (Cout, w_cin, kt, 3, 3). */
 int hpvg_conv_wgrad_cl(const void* d_x, int x_pitch, const void* d_gy, int gy_pitch, int N, int T, int H, int W,
                        float* d_dw, int w_cin, int kt, int co_off, int co_n, int ci_off, int ci_n, int accumulate,
                        float scale, void* stream);
