@@ -537,8 +537,7 @@ __global__ void upsample_noise_pack_tiled_kernel(const float* __restrict__ x, in
 // Register-only forward for Ti <= 8 (every pyramid level): a thread owns one output column (ho, wo), loads the 4 source
 // values of every source frame up front (4*Ti independent loads, served by L1/L2 — neighbouring threads share them),
 // forms the W- then H-interpolated value hv[ti] of each frame ONCE, and walks along T_out writing ~To/Ti outputs per
-// frame.  Same W -> H -> T operation order as trilerp() => identical bits.  No shared-memory tile, no barriers except
-// the one that publishes the T tap table.
+// frame.  Same W -> H -> T operation order as trilerp() => identical bits.  No shared-memory tile and no barrier.
 constexpr int CW_MAX_TI = 8;
 constexpr int CW_THREADS = 256;
 
@@ -684,12 +683,9 @@ upsample_noise_pack_colwalk_kernel(const float* __restrict__ x, const ResizeGeom
   }
 }
 
-// Register-only backward (adjoint) for moderate up-sampling (at most 4 output rows / columns tap one source row /
-// column, i.e. ratio <= 1.5 in H and W — every pyramid level): a thread owns one SOURCE column (hs, wi), its <= 4 x 4
-// contributing (ho, wo) positions and their H/W coefficients are fixed along T, so it walks T_out once,
-//     S(to) = sum_k ch[k] sum_j cw[j] gy[to][h_lo+k][w_lo+j],
-// and feeds S into register accumulators of the (at most two) source frames that `to` taps; a frame is stored as soon
-// as the walk has passed it.  Deterministic (fixed order), no atomics, no shared-memory tile.
+// Backward (adjoint) for moderate up-sampling (at most 4 output rows / columns tap one source row / column, i.e. ratio
+// <= 1.5 in H and W — every pyramid level).  InvTap: for one source row (column) the run of output rows (columns) that
+// tap it and their coefficients — fixed along T.  The kernel that uses them (resize3d_bwd_colwalk_kernel) is below.
 struct InvTap {
   int lo, n;        // contributing outputs [lo, lo+n)
   float c[4];       // their coefficients
