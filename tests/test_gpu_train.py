@@ -203,6 +203,35 @@ def test_gan_phase_g_and_d_steps(hpvg_gpu):
     _report(_grads_by_name(G, gbook, gnames), gref, E2E_BN_TOL, "G step (GAN phase)", min_cos=E2E_BN_COS)
 
 
+@pytest.mark.parametrize("scale,shape", [(7, (7, 121, 162)), (9, (13, 192, 257))])
+def test_d_step_with_gradient_penalty_at_large_scales(hpvg_gpu, scale, shape):
+    """DWithLoss (losses.py:27-56) at realistic sizes — scale 7 of the default pyramid (137 k voxels, ragged tiles in H
+    and W) and the finest scale (13 x 192 x 257 = 641 k voxels, BASELINE.json's size) — on given real / fake clips:
+    loss, first-order terms and the WGAN-GP double backward of all seven discriminator layers against torch-CPU
+    autograd (create_graph=True) on the oracle."""
+    hp = hpvg_gpu
+    from hpvg import train as T
+    G, D, opt, oopt, pg, pd, rng = _setup(hp, 0, seed=9)
+    s7 = orc.scale_shape(oopt, scale)
+    assert s7 == shape
+    real = np.tanh(rng.standard_normal((1, 3) + s7)).astype(np.float32)
+    fake = np.tanh(rng.standard_normal((1, 3) + s7)).astype(np.float32)
+    alpha = 0.61
+    D.set_train(True)
+    td = orc.to_torch(pd, requires_grad=("head.", "body.", "tail."))
+    with orc.bf16_emulation():
+        dloss_ref = orc.d_loss(torch.from_numpy(real), torch.from_numpy(fake), alpha, td, oopt)
+    dloss_ref.backward()
+    dnames = [k for k, t in td.items() if t.requires_grad]
+    dref = {k: td[k].grad.numpy() for k in dnames}
+    dl = T.DWithLoss(opt, D, G, alpha=alpha)
+    dloss, dbook = dl.grad(hp.from_numpy(real), None, None, fake=hp.from_numpy(fake))
+    assert abs(float(dloss) - float(dloss_ref.detach())) < 2e-2 * max(abs(float(dloss_ref.detach())), 1e-2)
+    # no BatchNorm in D => none of the conditioning caveat below: the north_star per-layer tolerance applies end to end
+    _report(_grads_by_name(D, dbook, dnames), dref, 1e-2, "D step at scale %d (incl. WGAN-GP double backward)" % scale,
+            min_cos=0.9999)
+
+
 def test_train_one_step_updates_parameters_like_clipped_adam(hpvg_gpu):
     hp = hpvg_gpu
     from hpvg import train as T
