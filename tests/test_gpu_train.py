@@ -74,15 +74,16 @@ def _report(got, ref, tol, what, min_cos=None, only=None):
 E2E_BN_TOL, E2E_BN_COS = 0.20, 0.98
 
 
-def test_per_layer_backward_teacher_forced(hpvg_gpu):
+@pytest.mark.parametrize("shape", [(1, 4, 30, 41), (1, 13, 192, 257)])
+def test_per_layer_backward_teacher_forced(hpvg_gpu, shape):
     """Every conv+BN+LeakyReLU layer of a refinement stage, fed with the ORACLE's input activation and upstream
-    gradient: dW, dgamma, dbeta and dx within rel-L2 1e-2 (north_star, bf16)."""
+    gradient: dW, dgamma, dbeta and dx within rel-L2 1e-2 (north_star, bf16) — at scale 1 and at the finest scale
+    (13 x 192 x 257, BASELINE.json's size: BatchNorm statistics and their backward over 641 k voxels)."""
     hp = hpvg_gpu
     from hpvg import networks_3d as n3, ops, train as T
     from util import bf16_round
     G, D, opt, oopt, pg, pd, rng = _setup(hp, 1)
     G.set_train(True)
-    shape = (1, 4, 30, 41)
     x3 = bf16_round(rng.standard_normal((1, 3) + shape[1:]) * 0.5)
     up = rng.standard_normal((1, 3) + shape[1:]).astype(np.float32) * 0.3
     gout = rng.standard_normal((1, 3) + shape[1:]).astype(np.float32)
@@ -104,8 +105,8 @@ def test_per_layer_backward_teacher_forced(hpvg_gpu):
         xin = x3 if j == 0 else taps["body.0.%d.out" % (j - 1)].detach().numpy()
         x_cl = ops.pack_cl(hp.from_numpy(xin), c_pitch=8 if j == 0 else 64)
         a, ctx = T.layer_forward_train(layer, x_cl, ws, "tf%d" % j)
-        if j == 0:
-            ctx["x_wide"] = ops.pack_cl(hp.from_numpy(xin), c_pitch=64, zero_to=64)
+        if j == 0:     # head conv weight gradient: zero-padded 64-channel copy (small case) or the narrow tensor itself
+            ctx["x_wide"] = ops.pack_cl(hp.from_numpy(xin), c_pitch=64, zero_to=64) if shape[1] == 4 else x_cl
         ga = taps["body.0.%d.out" % j].grad.numpy()
         book = T.GradBook()
         dx = T.layer_backward(layer, ctx, ops.pack_cl(hp.from_numpy(ga)), book, ws, "tf%d" % j, need_dx=True)
