@@ -118,6 +118,19 @@ def test_per_layer_backward_teacher_forced(hpvg_gpu, shape):
         got_dx = dx.numpy() if j == 0 else ops.unpack_cl(dx).numpy()
         e = rel_l2(got_dx, ref_dx)
         assert e < 1e-2, "layer %d dx rel-L2 %.3e" % (j, e)
+    # the tail conv 64 -> 3 (networks_3d.py:399): weight gradient from the narrow (8-channel) output gradient, data
+    # gradient through the transposed bank — fed with the oracle's gradient wrt the tail's output
+    jt = opt.num_layer + 1
+    tail = block.layers[jt]
+    x_t = ops.pack_cl(hp.from_numpy(taps["body.0.%d.out" % (jt - 1)].detach().numpy()))
+    g_pre = taps["body.0.%d.conv" % jt].grad.numpy()
+    book = T.GradBook()
+    dx = T.conv_backward(tail, {"x": x_t, "layer": tail}, ops.pack_cl(hp.from_numpy(g_pre), c_pitch=8), book, ws, "tft",
+                         need_dx=True, want_dw=True)
+    e = rel_l2(book.of(pdict["body.0.%d.weight" % jt]).numpy(), tg["body.0.%d.weight" % jt].grad.numpy())
+    assert e < 1e-2, "tail weight rel-L2 %.3e" % e
+    e = rel_l2(ops.unpack_cl(dx).numpy(), taps["body.0.%d.out" % (jt - 1)].grad.numpy())
+    assert e < 1e-2, "tail dx rel-L2 %.3e" % e
 
 
 def test_vae_phase_g_step(hpvg_gpu):
