@@ -148,3 +148,21 @@ def test_train_image_vae_step_loss_and_update(hpvg_gpu):
     optim.apply(book)
     after = mine["decoder.6.weight"].numpy()
     assert np.isfinite(after).all() and np.abs(after - before).max() > 0
+
+
+def test_discriminator_2d_at_the_full_image_size(hpvg_gpu):
+    """WDiscriminator2D on a 192 x 257 image (the finest scale of the default 256-pixel pyramid): with T == 1 the 198
+    strips of the conv kernel are single planes, so every CTA pair's work range crosses strip boundaries."""
+    hp = hpvg_gpu
+    from hpvg import networks_2d as n2
+    from hpvg.utils import images as uimg
+    opt, oopt = uimg.default_opt(), orc.default_opt()
+    pd = orc.init_discriminator_params(oopt, seed=14, nd=2)
+    D = n2.WDiscriminator2D(opt)
+    D.load_parameters(pd)
+    x = np.tanh(np.random.default_rng(15).standard_normal((2, 3, 192, 257))).astype(np.float32)
+    with torch.no_grad():
+        ref = orc.discriminator(torch.from_numpy(x), orc.to_torch(pd), oopt)
+    out = D(hp.from_numpy(x))
+    assert out.shape == (2, 1, 192, 257)
+    assert rel_l2(out.numpy(), ref.numpy()) < TOL
