@@ -287,21 +287,24 @@ def test_device_randn_statistics_and_counter(hpvg_gpu):
     assert np.array_equal(b, ops.randn(a.shape, seed=77, offset=1).numpy())          # device counter == host offset
 
 
-def test_cuda_graph_iteration_matches_eager_iteration(hpvg_gpu):
+@pytest.mark.parametrize("n_body", [3, 9])
+def test_cuda_graph_iteration_matches_eager_iteration(hpvg_gpu, n_body):
     """The whole GAN-phase iteration (D step + G step + both Adam updates) replayed as ONE CUDA graph must evolve the
-    weights exactly like the eager launch sequence: same kernels, device-resident noise counters and Adam step."""
+    weights exactly like the eager launch sequence: same kernels, device-resident noise counters and Adam step.
+    n_body = 3: the first GAN scale; n_body = 9: the full pyramid at the finest scale 13 x 192 x 257 — the size at which
+    the graph's three parallel generator branches really overlap with the main stream's kernels."""
     hp = hpvg_gpu
     from hpvg import train as T
 
     def run(graphed, iters=3):
-        G, D, opt, oopt, pg, pd, rng = _setup(hp, 3, seed=5)
+        G, D, opt, oopt, pg, pd, rng = _setup(hp, n_body, seed=5)
         G.noise_seed = 0x1234567
-        s0, s3 = orc.scale_shape(oopt, 0), orc.scale_shape(oopt, 3)
+        s0, s3 = orc.scale_shape(oopt, 0), orc.scale_shape(oopt, n_body)
         st = hp.Stream()
         real = hp.from_numpy(np.tanh(rng.standard_normal((1, 3) + s3)).astype(np.float32))
         real_zero = hp.from_numpy(np.tanh(rng.standard_normal((1, 3) + s0)).astype(np.float32))
         noise = hp.from_numpy(rng.standard_normal((1, 128) + s0).astype(np.float32))
-        amps = [1.0, 0.0, 0.0, 0.3]
+        amps = [1.0, 0.0, 0.0] + [0.3] * (n_body - 2)
         block = G.body[-1]
         optG = T.ClippedAdam(opt, [{"params": T.trainable_params(block), "lr": opt.lr_g}], opt.lr_g, beta1=0.5,
                              beta2=0.999, device_step=True)
@@ -310,7 +313,8 @@ def test_cuda_graph_iteration_matches_eager_iteration(hpvg_gpu):
         d_step = T.TrainOneStepCell(T.DWithLoss(opt, D, G, alpha=0.37, device_rng=True), optD, cells_to_invalidate=[D])
         g_step.set_train()
         d_step.set_train()
-        it = T.GraphedIteration(st, g_step, d_step, real, real_zero, noise, amps, dict(isVAE=False, trainable_body=(2,)))
+        it = T.GraphedIteration(st, g_step, d_step, real, real_zero, noise, amps,
+                                dict(isVAE=False, trainable_body=(n_body - 1,)))
         losses = []
         it.warmup(1)
         if graphed:
