@@ -33,6 +33,13 @@ extern "C" {
 #define HPVG_CONV_64_16 1 /* Cin 64 -> Cout <= 4 real (tail convs 64->3, 64->1)  */
 #define HPVG_CONV_8_64 2  /* Cin <= 8 (zero padded to 8) -> Cout 64 (head convs) */
 #define HPVG_CONV_64_3 3  /* Cin 64 -> Cout <= 3, in-plane taps folded into N (fast tail convs; fp32 ncdhw out) */
+/* kind::tf32 variants over fp32 channels-last activations ("f32cl": (N,T,H,W,Cpitch) fp32, values rounded to tf32).
+ * The reference computes in fp32 (networks_3d.py:48-50 nn.Conv3d on fp32 Tensors); these are the fp32-accurate path
+ * (per-layer rel-L2 <= 1e-3).  A 64-channel input is consumed 32 channels per launch: the first launch writes raw fp32
+ * partial sums (HPVG_OUT_F32_RAW), the last adds them through d_addend and applies the epilogue. */
+#define HPVG_CONV_T32_64 4 /* Cin 32 (a 32-channel slice at d_in) -> Cout 64            */
+#define HPVG_CONV_T4_64 5  /* Cin <= 4 (zero padded to 4) -> Cout 64 (head convs)        */
+#define HPVG_CONV_T32_3 6  /* Cin 32 -> Cout <= 3 (tail convs; fp32 ncdhw out)           */
 #define HPVG_ACT_NONE 0
 #define HPVG_ACT_LRELU 1 /* LeakyReLU(0.2): mindspore.nn.LeakyReLU default, networks_3d.py:20 */
 #define HPVG_ACT_TANH 2
@@ -40,6 +47,7 @@ extern "C" {
 #define HPVG_OUT_BF16_CL 0
 #define HPVG_OUT_F32_NCDHW 1
 #define HPVG_OUT_F32_RAW 2
+#define HPVG_OUT_F32_CL 3 /* fp32 channels-last (tf32 variants only) */
 
 /* ---------------------------------------------------------------- runtime (ctypes route; MindSpore owns these itself) */
 int hpvg_version(void);
@@ -80,6 +88,12 @@ int hpvg_pack_cl(const float* d_x, int N, int C, int T, int H, int W, void* d_y,
 /* bf16 (N,T,H,W,c_pitch) channels [c_off, c_off+C) -> fp32 (N,C,T,H,W) */
 int hpvg_unpack_cl(const void* d_x, int N, int C, int T, int H, int W, int c_pitch, int c_off, float* d_y,
                    void* stream);
+
+/* the same for fp32 channels-last tensors (tf32 precision mode); c_off / c_pitch multiples of 4 */
+int hpvg_pack_cl_f32(const float* d_x, int N, int C, int T, int H, int W, float* d_y, int c_pitch, int c_off,
+                     int c_zero_to, void* stream);
+int hpvg_unpack_cl_f32(const float* d_x, int N, int C, int T, int H, int W, int c_pitch, int c_off, float* d_y,
+                       void* stream);
 
 /* ---------------------------------------------------------------- convolution
  * Replaces nn.Conv3d / nn.Conv2d 3x3(x3), stride 1, zero pad 1 (networks_3d.py:48-50,380,399; networks_2d.py:47-49;
@@ -124,6 +138,10 @@ int hpvg_upsample_noise_pack(const float* d_x, int N, int C, int Ti, int Hi, int
                              const float* d_noise, float amp, uint64_t noise_seed, uint64_t sample_base,
                              const uint64_t* d_sample_offset /* nullable: device draw counter added to sample_base */,
                              float* d_up, void* d_xin_cl, void* stream);
+/* tf32 precision mode: x_in is fp32 channels-last, 4 channels (16 bytes) per voxel */
+int hpvg_upsample_noise_pack_f32(const float* d_x, int N, int C, int Ti, int Hi, int Wi, int To, int Ho, int Wo,
+                                 const float* d_noise, float amp, uint64_t noise_seed, uint64_t sample_base,
+                                 const uint64_t* d_sample_offset, float* d_up, float* d_xin_cl, void* stream);
 /* Device-side data path between the video decoder and the network.  d_frames: uint8 [F][Hs][Ws][3]
  * decoded frames (bgr != 0: decoder order, as cv2.VideoCapture returns them).  Writes the fp32 clip [1][3][T][H][W] the
  * reference's SingleVideoDataset.__getitem__ yields for window `start` and rate `every`:
@@ -210,6 +228,22 @@ int hpvg_adam_clip_multi(int n_tensors, float* const* d_params, const float* con
 int hpvg_conv_wgrad_cl(const void* d_x, int x_pitch, const void* d_gy, int gy_pitch, int N, int T, int H, int W,
                        float* d_dw, int w_cin, int kt, int co_off, int co_n, int ci_off, int ci_n, int accumulate,
                        float scale, void* stream);
+/* The weight gradient on kind::tf32 over fp32 channels-last operands (pitches in fp32 channels: >= 64 selects the
+ * 64-channel slice at the pointer, 4..28 is a narrow operand read as it is). */
+int hpvg_conv_wgrad_cl_tf32(const float* d_x, int x_pitch, const float* d_gy, int gy_pitch, int N, int T, int H, int W,
+                            float* d_dw, int w_cin, int kt, int co_off, int co_n, int ci_off, int ci_n, int accumulate,
+                            float scale, void* stream);
+/* fp32 channels-last twins of the BatchNorm / LeakyReLU / column-sum kernels (C == 64, tf32 precision mode) */
+int hpvg_bn_stats_cl_f32(const float* d_y, long long voxels, double* d_sum, double* d_sumsq, void* stream);
+int hpvg_bn_apply_lrelu_cl_f32(const float* d_y, long long voxels, const float* d_scale, const float* d_shift, int act,
+                               float* d_x, void* stream);
+int hpvg_bn_train_apply_cl_f32(const float* d_y, long long voxels, const double* d_sums, const float* d_gamma,
+                               const float* d_beta, float eps, float momentum, float* d_moving_mean,
+                               float* d_moving_var, float* d_saved, int act, float* d_x, void* stream);
+int hpvg_lrelu_bwd_cl_f32(const float* d_ga, const float* d_a, long long elems, float* d_gz, void* stream);
+int hpvg_bn_bwd_cl_f32(const float* d_ga, const float* d_y, long long voxels, const float* d_saved, int act,
+                       float* d_gy, float* d_dgamma, float* d_dbeta, int accumulate, void* stream);
+int hpvg_colsum_cl_f32(const float* d_g, long long voxels, float* d_out, int accumulate, void* stream);
 /* gz = ga * LeakyReLU'(a), a = stored activation (bf16 cl, elems % 8 == 0) */
 int hpvg_lrelu_bwd_cl(const void* d_ga, const void* d_a, long long elems, void* d_gz, void* stream);
 /* BatchNorm(train)+act backward on (voxels, 64) bf16: d_saved = (scale, shift, mean, invstd) from the forward

@@ -191,13 +191,29 @@ int hpvg_unpack_cl(const void* x, int N, int C, int T, int H, int W, int c_pitch
   return HPVG_OK;
 }
 
+int hpvg_pack_cl_f32(const float* x, int N, int C, int T, int H, int W, float* y, int c_pitch, int c_off,
+                     int c_zero_to, void* st) {
+  if ((c_off & 3) || (c_pitch & 3)) return fail(HPVG_E_ARG, "pack_cl_f32: c_off and c_pitch must be multiples of 4");
+  if (c_zero_to > c_pitch || c_off + C > c_pitch) return fail(HPVG_E_ARG, "pack_cl_f32: channels exceed pitch");
+  if (N <= 0 || C <= 0 || T <= 0 || H <= 0 || W <= 0) return HPVG_OK;
+  KL(hpvg::ew_pack_cl_f32(x, N, C, static_cast<long long>(T) * H * W, y, c_pitch, c_off, c_zero_to, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_unpack_cl_f32(const float* x, int N, int C, int T, int H, int W, int c_pitch, int c_off, float* y, void* st) {
+  if (c_off + C > c_pitch) return fail(HPVG_E_ARG, "unpack_cl_f32: channels exceed pitch");
+  if (N <= 0 || C <= 0 || T <= 0 || H <= 0 || W <= 0) return HPVG_OK;
+  KL(hpvg::ew_unpack_cl_f32(x, N, C, static_cast<long long>(T) * H * W, c_pitch, c_off, y, S(st)), 1);
+  return HPVG_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ conv
 int hpvg_conv_wimg_bytes(int mode) { return hpvg::conv3d_umma_wimg_bytes(mode); }
 
 int hpvg_conv_pack_weights(const float* w, int w_cout, int w_cin, int kt, int mode, int transpose_flip, int cout_off,
                            int cout, int cin_off, int cin, void* wimg, void* st) {
-  const int max_co = (mode == HPVG_CONV_64_16) ? 16 : (mode == HPVG_CONV_64_3) ? 3 : 64;
-  const int max_ci = (mode == HPVG_CONV_8_64) ? 8 : 64;
+  const int max_co = (mode == HPVG_CONV_64_16) ? 16 : (mode == HPVG_CONV_64_3 || mode == HPVG_CONV_T32_3) ? 3 : 64;
+  const int max_ci = (mode == HPVG_CONV_8_64) ? 8 : (mode == HPVG_CONV_T4_64) ? 4
+                     : (mode == HPVG_CONV_T32_64 || mode == HPVG_CONV_T32_3) ? 32 : 64;
   if (cout > max_co || cin > max_ci || cout <= 0 || cin <= 0)
     return fail(HPVG_E_ARG, "conv_pack_weights: channel counts exceed the kernel variant");
   const char* e = hpvg::conv3d_pack_weights(w, w_cout, w_cin, kt, mode, transpose_flip, cout_off, cout, cin_off, cin,
@@ -216,8 +232,12 @@ int hpvg_conv_cl(int mode, int N, int T, int H, int W, const void* in, int in_pi
   if (out_mode == HPVG_OUT_BF16_CL && ((out_pitch & 7) || (out_coff & 7)))
     return fail(HPVG_E_ARG, "conv_cl: out_pitch/out_coff must be multiples of 8");
   if (g_sm_count == 0) return fail(HPVG_E_ARG, "hpvg_init was not called");
-  if (stats && (mode == HPVG_CONV_64_16 || mode == HPVG_CONV_64_3 || out_mode != HPVG_OUT_BF16_CL))
-    return fail(HPVG_E_ARG, "conv_cl: fused BatchNorm statistics need a 64-channel bf16 output");
+  const bool tf32 = hpvg::conv_mode_is_tf32(mode);
+  if (tf32 != (out_mode == HPVG_OUT_F32_CL) && out_mode != HPVG_OUT_F32_RAW && out_mode != HPVG_OUT_F32_NCDHW)
+    return fail(HPVG_E_ARG, "conv_cl: bf16 kernels write HPVG_OUT_BF16_CL, tf32 kernels HPVG_OUT_F32_CL");
+  if (stats && (mode == HPVG_CONV_64_16 || mode == HPVG_CONV_64_3 || mode == HPVG_CONV_T32_3 ||
+                (out_mode != HPVG_OUT_BF16_CL && out_mode != HPVG_OUT_F32_CL)))
+    return fail(HPVG_E_ARG, "conv_cl: fused BatchNorm statistics need a 64-channel channels-last output");
   hpvg::ConvLaunch L;
   L.mode = mode;
   L.N = N; L.T = T; L.H = H; L.W = W;
@@ -270,7 +290,17 @@ int hpvg_upsample_noise_pack(const float* x, int N, int C, int Ti, int Hi, int W
   if (N <= 0) return HPVG_OK;
   KL(hpvg::ew_upsample_noise_pack(x, N, C, Ti, Hi, Wi, To, Ho, Wo, noise, amp, seed, sample_base,
                                   reinterpret_cast<const unsigned long long*>(d_sample_offset), up,
-                                  static_cast<__nv_bfloat16*>(xin), S(st)), 1);
+                                  static_cast<__nv_bfloat16*>(xin), 0, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_upsample_noise_pack_f32(const float* x, int N, int C, int Ti, int Hi, int Wi, int To, int Ho, int Wo,
+                                 const float* noise, float amp, uint64_t seed, uint64_t sample_base,
+                                 const uint64_t* d_sample_offset, float* up, float* xin, void* st) {
+  if (C < 1 || C > 4) return fail(HPVG_E_ARG, "upsample_noise_pack: 1 <= C <= 4");
+  if (N <= 0) return HPVG_OK;
+  KL(hpvg::ew_upsample_noise_pack(x, N, C, Ti, Hi, Wi, To, Ho, Wo, noise, amp, seed, sample_base,
+                                  reinterpret_cast<const unsigned long long*>(d_sample_offset), up,
+                                  reinterpret_cast<__nv_bfloat16*>(xin), 1, S(st)), 1);
   return HPVG_OK;
 }
 
@@ -428,6 +458,65 @@ int hpvg_conv_wgrad_cl(const void* x, int x_pitch, const void* gy, int gy_pitch,
                                             ci_n, accumulate, scale, g_wgrad_ws, g_sm_count, S(st));
   if (e) return fail(HPVG_E_CUDA, std::string("conv_wgrad_cl: ") + e);
   g_launches += 2;
+  return HPVG_OK;
+}
+int hpvg_conv_wgrad_cl_tf32(const float* x, int x_pitch, const float* gy, int gy_pitch, int N, int T, int H, int W,
+                            float* dw, int w_cin, int kt, int co_off, int co_n, int ci_off, int ci_n, int accumulate,
+                            float scale, void* st) {
+  if (N <= 0 || T <= 0 || H <= 0 || W <= 0) return HPVG_OK;
+  if (!g_wgrad_ws) return fail(HPVG_E_ARG, "hpvg_init was not called");
+  if ((x_pitch & 3) || (gy_pitch & 3) || x_pitch < 4 || gy_pitch < 4 || (x_pitch >= 32 && x_pitch < 64) ||
+      (gy_pitch >= 32 && gy_pitch < 64))
+    return fail(HPVG_E_ARG, "conv_wgrad_cl_tf32: operands are fp32 channels-last tensors of >= 64 channels, or narrow "
+                            "tensors of 4..28 channels");
+  if ((x_pitch < 64 && ci_n > x_pitch) || (gy_pitch < 64 && co_n > gy_pitch))
+    return fail(HPVG_E_ARG, "conv_wgrad_cl_tf32: block extent exceeds the channels of a narrow operand");
+  if (co_n < 1 || co_n > 64 || ci_n < 1 || ci_n > 64 || (kt != 1 && kt != 3))
+    return fail(HPVG_E_ARG, "conv_wgrad_cl_tf32: bad block extents");
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(gy) & 15))
+    return fail(HPVG_E_ARG, "conv_wgrad_cl_tf32: operands must be 16-byte aligned");
+  const char* e = hpvg::conv3d_wgrad_tf32_launch(x, x_pitch, gy, gy_pitch, N, T, H, W, dw, w_cin, kt, co_off, co_n,
+                                                 ci_off, ci_n, accumulate, scale, g_wgrad_ws, g_sm_count, S(st));
+  if (e) return fail(HPVG_E_CUDA, std::string("conv_wgrad_cl_tf32: ") + e);
+  g_launches += 2;
+  return HPVG_OK;
+}
+int hpvg_bn_stats_cl_f32(const float* y, long long voxels, double* sum, double* sumsq, void* st) {
+  if (voxels <= 0) return fail(HPVG_E_ARG, "bn_stats: empty batch");
+  KL(hpvg::ew_bn_stats_cl_f32(y, voxels, sum, sumsq, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_bn_apply_lrelu_cl_f32(const float* y, long long voxels, const float* scale, const float* shift, int act,
+                               float* x, void* st) {
+  if (voxels <= 0) return HPVG_OK;
+  KL(hpvg::ew_bn_apply_cl_f32(y, voxels, scale, shift, act, x, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_bn_train_apply_cl_f32(const float* y, long long voxels, const double* sums, const float* gamma,
+                               const float* beta, float eps, float momentum, float* mm, float* mv, float* saved,
+                               int act, float* x, void* st) {
+  if (voxels <= 0) return fail(HPVG_E_ARG, "bn_train_apply: empty batch");
+  if (!y || !sums || !gamma || !beta || !x) return fail(HPVG_E_ARG, "bn_train_apply: null pointer");
+  KL(hpvg::ew_bn_train_apply_cl_f32(y, voxels, sums, gamma, beta, eps, momentum, mm, mv, saved, act, x, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_lrelu_bwd_cl_f32(const float* ga, const float* a, long long elems, float* gz, void* st) {
+  if (elems <= 0) return HPVG_OK;
+  if (elems & 3) return fail(HPVG_E_ARG, "lrelu_bwd_cl_f32: element count must be a multiple of 4");
+  KL(hpvg::ew_lrelu_bwd_cl_f32(ga, a, elems, gz, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_bn_bwd_cl_f32(const float* ga, const float* y, long long voxels, const float* saved, int act, float* gy,
+                       float* dgamma, float* dbeta, int accumulate, void* st) {
+  if (voxels <= 0) return fail(HPVG_E_ARG, "bn_bwd: empty batch");
+  if (!g_sums) return fail(HPVG_E_ARG, "hpvg_init was not called");
+  KL(hpvg::ew_bn_bwd_cl_f32(ga, y, voxels, saved, act, g_sums, gy, dgamma, dbeta, accumulate, S(st)), 4);
+  return HPVG_OK;
+}
+int hpvg_colsum_cl_f32(const float* g, long long voxels, float* out, int accumulate, void* st) {
+  if (voxels <= 0) return fail(HPVG_E_ARG, "colsum: empty input");
+  if (!g_sums) return fail(HPVG_E_ARG, "hpvg_init was not called");
+  KL(hpvg::ew_colsum_cl_f32(g, voxels, g_sums, out, accumulate, S(st)), 2);
   return HPVG_OK;
 }
 int hpvg_lrelu_bwd_cl(const void* ga, const void* a, long long elems, void* gz, void* st) {

@@ -52,6 +52,9 @@ struct TailParams {
   const float* addend;   // optional fp32 NCDHW residual (added after scale/shift, before the activation)
 };
 
+// TF32: the same kernel over fp32 channels-last activations, 32 input channels per launch (a 128-byte row = 32 tf32
+// channels; K = 8 per MMA): a 64 -> 3 tail is two launches, the second adding the first's output through `addend`.
+template <bool TF32>
 __global__ void __launch_bounds__(T_THREADS, 1)
 conv3d_tail_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ TailParams p) {
   extern __shared__ uint8_t smem_dyn[];
@@ -119,8 +122,8 @@ conv3d_tail_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
     // ======================================================================================= MMA issuer
     if (elect_one()) {
       mbar_wait(w_full, 0);
-      const uint32_t idesc128 = make_idesc_bf16(128, 32);
-      const uint32_t idesc64 = make_idesc_bf16(64, 32);
+      const uint32_t idesc128 = make_idesc<TF32>(128, 32);
+      const uint32_t idesc64 = make_idesc<TF32>(64, 32);
       const uint32_t w_addr = smem_u32(w_sm);
       const uint32_t planes_addr = smem_u32(planes);
       uint32_t j0 = 0, q = 0;
@@ -145,8 +148,8 @@ conv3d_tail_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t bd = make_smem_desc(b_base + k * 32, 16, 1024, 2);
-              umma_bf16(d1, make_smem_desc(a_base + k * 32, 16, 1024, 2), bd, idesc128, accum);
-              umma_bf16(d2, make_smem_desc(a_base + 128 * 128 + k * 32, 16, 1024, 2), bd, idesc64, accum);
+              umma_ss<TF32>(d1, make_smem_desc(a_base + k * 32, 16, 1024, 2), bd, idesc128, accum);
+              umma_ss<TF32>(d2, make_smem_desc(a_base + 128 * 128 + k * 32, 16, 1024, 2), bd, idesc64, accum);
               accum = 1;
             }
           }
@@ -256,18 +259,20 @@ int conv3d_tail_wimg_bytes() { return T_W_BYTES; }
 const char* conv3d_tail_launch(const ConvLaunch& L, int sm_count, cudaStream_t stream) {
   EncodeTiledFn enc = tail_get_encode();
   if (!enc) return "cuTensorMapEncodeTiled entry point not available";
-  if (L.in_pitch < 64 || (L.in_pitch & 7)) return "input pitch must be a multiple of 8 channels and >= 64";
+  const bool tf32 = (L.mode == CONV_MODE_T32_T);
+  const int cbox = tf32 ? 32 : 64, esz = tf32 ? 4 : 2;
+  if (L.in_pitch < cbox || ((L.in_pitch * esz) & 15)) return "input pitch must be a multiple of 16 bytes and >= the box";
   if ((reinterpret_cast<uintptr_t>(L.in) & 15) != 0) return "input not 16-byte aligned";
   if (L.out_mode != CONV_OUT_F32_NCDHW || L.cout_real < 1 || L.cout_real > 3) return "tail conv: 1..3 fp32 NCDHW outputs";
   if (L.act == CONV_ACT_LRELU_MASK) return "tail conv: LRELU_MASK is a bf16-output epilogue";
   CUtensorMap tmap;
-  cuuint64_t gd[5] = {64, static_cast<cuuint64_t>(L.W), static_cast<cuuint64_t>(L.H), static_cast<cuuint64_t>(L.T),
-                      static_cast<cuuint64_t>(L.N)};
-  const cuuint64_t vox = static_cast<cuuint64_t>(L.in_pitch) * 2;
+  cuuint64_t gd[5] = {static_cast<cuuint64_t>(cbox), static_cast<cuuint64_t>(L.W), static_cast<cuuint64_t>(L.H),
+                      static_cast<cuuint64_t>(L.T), static_cast<cuuint64_t>(L.N)};
+  const cuuint64_t vox = static_cast<cuuint64_t>(L.in_pitch) * esz;
   cuuint64_t gs[4] = {vox, vox * L.W, vox * L.W * L.H, vox * L.W * L.H * L.T};
-  cuuint32_t bx[5] = {64, TB_W, TB_H, 1, 1};
+  cuuint32_t bx[5] = {static_cast<cuuint32_t>(cbox), TB_W, TB_H, 1, 1};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(L.in), gd, gs, bx, es,
+  if (enc(&tmap, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(L.in), gd, gs, bx, es,
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return "cuTensorMapEncodeTiled failed";
@@ -284,12 +289,16 @@ const char* conv3d_tail_launch(const ConvLaunch& L, int sm_count, cudaStream_t s
   if (prm.n_units < 1) return nullptr;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv3d_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
+    cudaError_t e =
+        cudaFuncSetAttribute(conv3d_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv3d_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
     if (e != cudaSuccess) return cudaGetErrorString(e);
     configured = true;
   }
   const int grid = prm.n_units < sm_count ? prm.n_units : sm_count;
-  conv3d_tail_kernel<<<grid, T_THREADS, T_SMEM, stream>>>(tmap, prm);
+  if (tf32) conv3d_tail_kernel<true><<<grid, T_THREADS, T_SMEM, stream>>>(tmap, prm);
+  else conv3d_tail_kernel<false><<<grid, T_THREADS, T_SMEM, stream>>>(tmap, prm);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

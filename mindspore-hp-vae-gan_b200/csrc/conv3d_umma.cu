@@ -42,6 +42,7 @@ struct Cfg;
 // MODE 0: Cin 64 -> Cout 64 (SW128 planes, 4 K-steps per tap)
 template <>
 struct Cfg<CONV_MODE_64_64> {
+  static constexpr bool TF32 = false, HEAD = false;
   static constexpr int CIN = 64, NOUT = 64, ROWS_PER_CTA = 32;
   static constexpr int PLANE_BYTES = BOX_H * BOX_W * 128, SLOT_STRIDE = 23552, SLOTS = 4;
   static constexpr int W_BYTES = 27 * ROWS_PER_CTA * 128, DT_BYTES = 9 * ROWS_PER_CTA * 128;
@@ -50,6 +51,7 @@ struct Cfg<CONV_MODE_64_64> {
 // MODE 1: Cin 64 -> Cout <= 16 (tail convs 64->3 / 64->1)
 template <>
 struct Cfg<CONV_MODE_64_16> {
+  static constexpr bool TF32 = false, HEAD = false;
   static constexpr int CIN = 64, NOUT = 16, ROWS_PER_CTA = 8;
   static constexpr int PLANE_BYTES = BOX_H * BOX_W * 128, SLOT_STRIDE = 23552, SLOTS = 6;
   static constexpr int W_BYTES = 27 * ROWS_PER_CTA * 128, DT_BYTES = 9 * ROWS_PER_CTA * 128;
@@ -58,10 +60,25 @@ struct Cfg<CONV_MODE_64_16> {
 // MODE 2: Cin <= 8 -> Cout 64 (head convs 3->64); no-swizzle planes of 16 B per voxel, taps paired through LBO
 template <>
 struct Cfg<CONV_MODE_8_64> {
+  static constexpr bool TF32 = false, HEAD = true;
   static constexpr int CIN = 8, NOUT = 64, ROWS_PER_CTA = 32;
   static constexpr int PLANE_BYTES = BOX_H * BOX_W * 16, SLOT_STRIDE = 3072, SLOTS = 8;
   static constexpr int W_BYTES = 3 * 5 * 1024, DT_BYTES = 5 * 1024;
   static constexpr int ACC_STRIDE = 64, TMEM_COLS = 128;
+};
+// kind::tf32 twins: fp32 operands, the SAME byte layouts with half the channels per row (a 128-byte row = 32 tf32
+// channels, K = 8 per MMA = the same 32 bytes; a 16-byte head voxel = 4 fp32 channels).  A 64 -> 64 layer at tf32 is two
+// launches of the 32 -> 64 variant (second launch adds the first's raw fp32 partial sums): exactly the half-rate of the
+// tf32 tensor pipe, and the full 27-tap filter bank of 32 input channels still fits the shared memory next to the ring.
+template <>
+struct Cfg<CONV_MODE_T32_64> : Cfg<CONV_MODE_64_64> {
+  static constexpr bool TF32 = true;
+  static constexpr int CIN = 32;
+};
+template <>
+struct Cfg<CONV_MODE_T4_64> : Cfg<CONV_MODE_8_64> {
+  static constexpr bool TF32 = true;
+  static constexpr int CIN = 4;
 };
 
 struct Unit {
@@ -196,6 +213,64 @@ __device__ __forceinline__ void epilogue_bf16_dispatch(int act, uint32_t (&r0)[3
   }
 }
 
+// fp32 channels-last twin (tf32 modes): 64 fp32 channels = 256 bytes per voxel, values rounded to tf32 (round to nearest)
+// because the consumer's tensor core would otherwise truncate them (except the statistics variant, see below).
+template <int ACT, bool ADD, bool KEEP>
+__device__ __forceinline__ void epilogue_f32_row(uint32_t (&r0)[32], uint32_t (&r1)[32], const float* scale_sm,
+                                                 const float* shift_sm, const float* __restrict__ add,
+                                                 float* __restrict__ dst) {
+  const float4* sc4 = reinterpret_cast<const float4*>(scale_sm);
+  const float4* sh4 = reinterpret_cast<const float4*>(shift_sm);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t* r = half ? r1 : r0;
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const int cb = half * 32 + c4 * 4;
+      const float4 sa = sc4[cb / 4], ha = sh4[cb / 4];
+      const float sc[4] = {sa.x, sa.y, sa.z, sa.w};
+      const float sh[4] = {ha.x, ha.y, ha.z, ha.w};
+      float ad[4] = {0.f, 0.f, 0.f, 0.f};
+      if constexpr (ADD) {
+        const float4 a0 = *reinterpret_cast<const float4*>(add + cb);
+        ad[0] = a0.x; ad[1] = a0.y; ad[2] = a0.z; ad[3] = a0.w;
+      }
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float a = __uint_as_float(r[c4 * 4 + e]);
+        if constexpr (ADD) a += ad[e];
+        a = fmaf(a, sc[e], sh[e]);
+        if constexpr (ACT == CONV_ACT_LRELU) a = fmaxf(a, 0.2f * a);
+        if constexpr (ACT == CONV_ACT_TANH) a = tanhf(a);
+        // KEEP = the pre-BatchNorm output of a training-mode layer: read by the normalise / backward passes only, never by
+        // a tensor core, and its SIGN after the affine decides the LeakyReLU mask — stored unrounded
+        v[e] = KEEP ? a : round_tf32(a);
+      }
+      *reinterpret_cast<float4*>(dst + cb) = make_float4(v[0], v[1], v[2], v[3]);
+      if constexpr (KEEP) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r[c4 * 4 + e] = __float_as_uint(v[e]);
+      }
+    }
+  }
+}
+
+template <bool KEEP>
+__device__ __forceinline__ void epilogue_f32_dispatch(int act, uint32_t (&r0)[32], uint32_t (&r1)[32],
+                                                      const float* scale_sm, const float* shift_sm,
+                                                      const float* __restrict__ add, float* __restrict__ dst) {
+  if (add) {
+    if (act == CONV_ACT_LRELU) epilogue_f32_row<CONV_ACT_LRELU, true, KEEP>(r0, r1, scale_sm, shift_sm, add, dst);
+    else if (act == CONV_ACT_TANH) epilogue_f32_row<CONV_ACT_TANH, true, KEEP>(r0, r1, scale_sm, shift_sm, add, dst);
+    else epilogue_f32_row<CONV_ACT_NONE, true, KEEP>(r0, r1, scale_sm, shift_sm, add, dst);
+  } else {
+    if (act == CONV_ACT_LRELU) epilogue_f32_row<CONV_ACT_LRELU, false, KEEP>(r0, r1, scale_sm, shift_sm, add, dst);
+    else if (act == CONV_ACT_TANH) epilogue_f32_row<CONV_ACT_TANH, false, KEEP>(r0, r1, scale_sm, shift_sm, add, dst);
+    else epilogue_f32_row<CONV_ACT_NONE, false, KEEP>(r0, r1, scale_sm, shift_sm, add, dst);
+  }
+}
+
 template <int MODE, bool STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ConvParams p) {
@@ -284,8 +359,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
           uint32_t dst_bar = leader_full[0];
 #pragma unroll
           for (int i = 1; i < C::SLOTS; ++i) dst_bar = (slot == static_cast<uint32_t>(i)) ? leader_full[i] : dst_bar;
-          if (MODE == CONV_MODE_8_64 && p.in_merged)   // (C, W) merged into one 160-byte box row
-            tma_load_5d_pair(planes + slot * C::SLOT_STRIDE, &tmap_in, dst_bar, (un.w0 - 1) * 8, un.h0 - 1, t, un.n, 0);
+          if (C::HEAD && p.in_merged)   // (C, W) merged into one 160-byte box row
+            tma_load_5d_pair(planes + slot * C::SLOT_STRIDE, &tmap_in, dst_bar, (un.w0 - 1) * C::CIN, un.h0 - 1, t, un.n, 0);
           else
             tma_load_5d_pair(planes + slot * C::SLOT_STRIDE, &tmap_in, dst_bar, 0, un.w0 - 1, un.h0 - 1, t, un.n);
         }
@@ -305,7 +380,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
     }
     if (rank == 0 && elect_one()) {
       uint32_t w_ready = 0;                      // bit dt: the taps of temporal offset dt are resident in both CTAs
-      const uint32_t idesc = make_idesc_bf16(256, C::NOUT);
+      const uint32_t idesc = make_idesc<C::TF32>(256, C::NOUT);
       const uint32_t w_addr = smem_u32(w_sm);
       const uint32_t planes_addr = smem_u32(planes);
       uint32_t j0 = 0, q = 0;
@@ -339,8 +414,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
             const uint32_t slot = (j0 + static_cast<uint32_t>(tin - tlo)) % C::SLOTS;
             const uint32_t a_base = planes_addr + slot * C::SLOT_STRIDE;
             const uint32_t b_base = w_addr + dt * C::DT_BYTES;
-            if constexpr (MODE == CONV_MODE_8_64) {
+            if constexpr (C::HEAD) {
               // 9 in-plane taps, 8 channels (16 B) each -> 5 MMAs of K=16: (tap0 | zero-weight dummy), (1|2) ... (7|8)
+              // (tf32: 4 channels per 16-byte voxel, K = 8: the same two 16-byte K groups)
 #pragma unroll
               for (int s = 0; s < 5; ++s) {
                 const int ta = (s == 0) ? 0 : 2 * s - 1;
@@ -349,7 +425,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
                 const uint32_t offb = ((tb / 3) * BOX_W + (tb % 3)) * 16;
                 const uint64_t ad = make_smem_desc(a_base + offa, offb - offa, BOX_W * 16, 0);
                 const uint64_t bd = make_smem_desc(b_base + s * 1024, C::ROWS_PER_CTA * 16, 128, 0);
-                umma_bf16_pair(d_tmem, ad, bd, idesc, accum);
+                umma_ss_pair<C::TF32>(d_tmem, ad, bd, idesc, accum);
                 accum = 1;
               }
             } else {
@@ -361,7 +437,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
                 for (int k = 0; k < 4; ++k) {
                   const uint64_t ad = make_smem_desc(a_tap + k * 32, 16, BOX_W * 128, 2);
                   const uint64_t bd = make_smem_desc(b_tap + k * 32, 16, 1024, 2);
-                  umma_bf16_pair(d_tmem, ad, bd, idesc, accum);
+                  umma_ss_pair<C::TF32>(d_tmem, ad, bd, idesc, accum);
                   accum = 1;
                 }
               }
@@ -419,6 +495,23 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
             if (inb) {
               if (p.out_mode == CONV_OUT_F32_RAW) {
                 float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + vox * 64);
+                if constexpr (C::TF32) {
+                  if (p.addend) {   // running fp32 partial sum of a split-Cin layer (may alias the output)
+                    const float4* ad = reinterpret_cast<const float4*>(p.addend + vox * 64);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                      const float4 a0 = ad[c], a1 = ad[8 + c];
+                      r0[4 * c] = __float_as_uint(__uint_as_float(r0[4 * c]) + a0.x);
+                      r0[4 * c + 1] = __float_as_uint(__uint_as_float(r0[4 * c + 1]) + a0.y);
+                      r0[4 * c + 2] = __float_as_uint(__uint_as_float(r0[4 * c + 2]) + a0.z);
+                      r0[4 * c + 3] = __float_as_uint(__uint_as_float(r0[4 * c + 3]) + a0.w);
+                      r1[4 * c] = __float_as_uint(__uint_as_float(r1[4 * c]) + a1.x);
+                      r1[4 * c + 1] = __float_as_uint(__uint_as_float(r1[4 * c + 1]) + a1.y);
+                      r1[4 * c + 2] = __float_as_uint(__uint_as_float(r1[4 * c + 2]) + a1.z);
+                      r1[4 * c + 3] = __float_as_uint(__uint_as_float(r1[4 * c + 3]) + a1.w);
+                    }
+                  }
+                }
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
                   dst[c] = make_float4(__uint_as_float(r0[4 * c]), __uint_as_float(r0[4 * c + 1]),
@@ -427,6 +520,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
                 for (int c = 0; c < 8; ++c)
                   dst[8 + c] = make_float4(__uint_as_float(r1[4 * c]), __uint_as_float(r1[4 * c + 1]),
                                            __uint_as_float(r1[4 * c + 2]), __uint_as_float(r1[4 * c + 3]));
+              } else if constexpr (C::TF32) {
+                const float* add = p.addend ? p.addend + vox * 64 : nullptr;
+                float* dst = static_cast<float*>(p.out) + vox * p.out_pitch + p.out_coff;
+                epilogue_f32_dispatch<false>(p.act, r0, r1, scale_sm, shift_sm, add, dst);
               } else {
                 const float* add = p.addend ? p.addend + vox * 64 : nullptr;
                 __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + vox * p.out_pitch + p.out_coff;
@@ -439,10 +536,15 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
             // bf16 output + BatchNorm batch statistics (sum, sum of squares of the values AS STORED, i.e. bf16-rounded)
             if (inb) {
               const float* add = p.addend ? p.addend + vox * 64 : nullptr;
-              __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + vox * p.out_pitch + p.out_coff;
-              const __nv_bfloat16* mk =
-                  p.mask ? static_cast<const __nv_bfloat16*>(p.mask) + vox * p.mask_pitch : nullptr;
-              epilogue_bf16_dispatch<true>(p.act, r0, r1, scale_sm, shift_sm, add, dst, mk);
+              if constexpr (C::TF32) {
+                float* dst = static_cast<float*>(p.out) + vox * p.out_pitch + p.out_coff;
+                epilogue_f32_dispatch<true>(p.act, r0, r1, scale_sm, shift_sm, add, dst);
+              } else {
+                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + vox * p.out_pitch + p.out_coff;
+                const __nv_bfloat16* mk =
+                    p.mask ? static_cast<const __nv_bfloat16*>(p.mask) + vox * p.mask_pitch : nullptr;
+                epilogue_bf16_dispatch<true>(p.act, r0, r1, scale_sm, shift_sm, add, dst, mk);
+              }
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) r0[i] = r1[i] = 0u;
@@ -575,36 +677,39 @@ cudaError_t launch_mode(const CUtensorMap& tmap, const ConvParams& prm, int n_pa
 }  // namespace
 
 const char* conv3d_umma_launch(const ConvLaunch& L, cudaStream_t stream) {
-  if (L.mode == CONV_MODE_64_T) return conv3d_tail_launch(L, 2 * L.max_pairs, stream);
+  if (L.mode == CONV_MODE_64_T || L.mode == CONV_MODE_T32_T) return conv3d_tail_launch(L, 2 * L.max_pairs, stream);
   EncodeTiledFn enc = get_encode();
   if (!enc) return "cuTensorMapEncodeTiled entry point not available";
-  const int cin_pitch = L.in_pitch;  // channels per voxel row in the input tensor
-  const int cin_box = (L.mode == CONV_MODE_8_64) ? 8 : 64;
-  if (cin_pitch < cin_box || (cin_pitch & 7)) return "input pitch must be a multiple of 8 channels and >= the box";
+  const bool tf32 = conv_mode_is_tf32(L.mode);
+  const bool head = (L.mode == CONV_MODE_8_64 || L.mode == CONV_MODE_T4_64);
+  const int esz = tf32 ? 4 : 2;                      // bytes per activation element
+  const int cin_pitch = L.in_pitch;                  // channels per voxel row in the input tensor
+  const int cin_box = head ? (tf32 ? 4 : 8) : (tf32 ? 32 : 64);   // one 16-byte (head) or 128-byte box row
+  if (cin_pitch < cin_box || ((cin_pitch * esz) & 15)) return "input pitch must be a multiple of 16 bytes and >= the box";
   if ((reinterpret_cast<uintptr_t>(L.in) & 15) != 0) return "input not 16-byte aligned";
   CUtensorMap tmap;
   cuuint64_t gd[5] = {static_cast<cuuint64_t>(cin_box), static_cast<cuuint64_t>(L.W), static_cast<cuuint64_t>(L.H),
                       static_cast<cuuint64_t>(L.T), static_cast<cuuint64_t>(L.N)};
-  const cuuint64_t vox = static_cast<cuuint64_t>(cin_pitch) * 2;
+  const cuuint64_t vox = static_cast<cuuint64_t>(cin_pitch) * esz;
   cuuint64_t gs[4] = {vox, vox * L.W, vox * L.W * L.H, vox * L.W * L.H * L.T};
   cuuint32_t bx[5] = {static_cast<cuuint32_t>(cin_box), BOX_W, BOX_H, 1, 1};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   // head convs on a densely packed 8-channel tensor: voxels of an image row are contiguous, so (C, W) merge into one
   // dimension and every box row becomes ONE 160-byte request instead of ten 16-byte ones
   static const bool no_merge = getenv("HPVG_NO_MERGE") != nullptr;
-  const bool merged = (L.mode == CONV_MODE_8_64 && cin_pitch == 8 && !no_merge);
+  const bool merged = (head && cin_pitch == cin_box && !no_merge);
   if (merged) {
-    gd[0] = 8ull * L.W; gd[1] = L.H; gd[2] = L.T; gd[3] = L.N; gd[4] = 1;
+    gd[0] = static_cast<cuuint64_t>(cin_box) * L.W; gd[1] = L.H; gd[2] = L.T; gd[3] = L.N; gd[4] = 1;
     gs[0] = vox * L.W; gs[1] = vox * L.W * L.H; gs[2] = vox * L.W * L.H * L.T; gs[3] = vox * L.W * L.H * L.T * L.N;
-    bx[0] = 8 * BOX_W; bx[1] = BOX_H; bx[2] = 1; bx[3] = 1; bx[4] = 1;
+    bx[0] = cin_box * BOX_W; bx[1] = BOX_H; bx[2] = 1; bx[3] = 1; bx[4] = 1;
   }
-  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(L.in), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   L.mode == CONV_MODE_8_64 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = enc(&tmap, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
+                   const_cast<void*>(L.in), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   head ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed";
 
-  if (L.act == CONV_ACT_LRELU_MASK && (!L.mask || L.out_mode != CONV_OUT_BF16_NDHWC || (L.mask_pitch & 7) ||
+  if (L.act == CONV_ACT_LRELU_MASK && (tf32 || !L.mask || L.out_mode != CONV_OUT_BF16_NDHWC || (L.mask_pitch & 7) ||
                                        (reinterpret_cast<uintptr_t>(L.mask) & 15)))
     return "LRELU_MASK needs a 16-byte aligned bf16 mask tensor and the bf16 output mode";
   ConvParams prm;
@@ -635,6 +740,14 @@ const char* conv3d_umma_launch(const ConvLaunch& L, cudaStream_t stream) {
   int n_pairs = out_planes < L.max_pairs ? static_cast<int>(out_planes) : L.max_pairs;
   if (n_pairs < 1) return nullptr;
   cudaError_t e;
+  if (tf32) {
+    if (L.out_mode != CONV_OUT_F32_NDHWC && L.out_mode != CONV_OUT_F32_RAW) return "bad out_mode for a tf32 conv";
+    if (L.out_mode == CONV_OUT_F32_NDHWC && ((L.out_pitch & 3) || (L.out_coff & 3) ||
+                                             (reinterpret_cast<uintptr_t>(L.out) & 15)))
+      return "fp32 channels-last output: pitch / offset must be multiples of 4 channels, pointer 16-byte aligned";
+    if (L.addend && (reinterpret_cast<uintptr_t>(L.addend) & 15)) return "addend not 16-byte aligned";
+    if (L.stats && L.out_mode != CONV_OUT_F32_NDHWC) return "fused statistics need the channels-last output mode";
+  }
   switch (L.mode) {
     case CONV_MODE_64_64:
       if (L.out_mode != CONV_OUT_BF16_NDHWC && L.out_mode != CONV_OUT_F32_RAW) return "bad out_mode for 64->64";
@@ -653,6 +766,14 @@ const char* conv3d_umma_launch(const ConvLaunch& L, cudaStream_t stream) {
       e = L.stats ? launch_mode<CONV_MODE_8_64, true>(tmap, prm, n_pairs, stream)
                   : launch_mode<CONV_MODE_8_64, false>(tmap, prm, n_pairs, stream);
       break;
+    case CONV_MODE_T32_64:
+      e = L.stats ? launch_mode<CONV_MODE_T32_64, true>(tmap, prm, n_pairs, stream)
+                  : launch_mode<CONV_MODE_T32_64, false>(tmap, prm, n_pairs, stream);
+      break;
+    case CONV_MODE_T4_64:
+      e = L.stats ? launch_mode<CONV_MODE_T4_64, true>(tmap, prm, n_pairs, stream)
+                  : launch_mode<CONV_MODE_T4_64, false>(tmap, prm, n_pairs, stream);
+      break;
     default:
       return "unknown conv mode";
   }
@@ -665,6 +786,9 @@ int conv3d_umma_wimg_bytes(int mode) {
     case CONV_MODE_64_16: return 2 * Cfg<CONV_MODE_64_16>::W_BYTES;
     case CONV_MODE_8_64: return 2 * Cfg<CONV_MODE_8_64>::W_BYTES;
     case CONV_MODE_64_T: return conv3d_tail_wimg_bytes();
+    case CONV_MODE_T32_64: return 2 * Cfg<CONV_MODE_T32_64>::W_BYTES;
+    case CONV_MODE_T4_64: return 2 * Cfg<CONV_MODE_T4_64>::W_BYTES;
+    case CONV_MODE_T32_T: return conv3d_tail_wimg_bytes();
   }
   return 0;
 }
@@ -772,11 +896,93 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int c
   img[idx] = __float2bfloat16_rn(val);
 }
 
+// The same images for the kind::tf32 variants: fp32 elements rounded to tf32, 32 input channels per 128-byte row
+// (16-byte swizzle chunk = 4 channels), 4 channels per 16-byte head voxel.  One thread per fp32 element.
+__global__ void pack_weights_tf32_kernel(const float* __restrict__ w, int cout, int cin, int kt, int mode,
+                                         int transpose_flip, int cin_off, int cout_off, int w_cin,
+                                         float* __restrict__ img, int total) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int co, ci, dt, dh, dw;
+  bool valid = true;
+  if (mode == CONV_MODE_T32_T) {
+    // [dt 3][row n = (dh*3+dw)*3 + co (32 rows, 27 used)][32 ci], 128B-swizzled rows
+    dt = idx / (32 * 32);
+    const int rem = idx - dt * 32 * 32;
+    const int n = rem / 32, within = rem - n * 32;
+    const int chunk = (within >> 2) ^ (n & 7);
+    ci = chunk * 4 + (within & 3);
+    const int s = n / 3;
+    co = n - s * 3;
+    valid = n < 27;
+    dh = s / 3;
+    dw = s - dh * 3;
+  } else if (mode == CONV_MODE_T32_64) {
+    // [rank 2][tap 27][row 32][32 ci], 128B-swizzled rows
+    const int per_rank = 27 * 32 * 32;
+    const int rank = idx / per_rank;
+    int rem = idx - rank * per_rank;
+    const int tap = rem / (32 * 32);
+    rem -= tap * 32 * 32;
+    const int row = rem / 32, within = rem - row * 32;
+    const int chunk = (within >> 2) ^ (row & 7);
+    ci = chunk * 4 + (within & 3);
+    co = rank * 32 + row;
+    dt = tap / 9; dh = (tap / 3) % 3; dw = tap % 3;
+  } else {
+    // [rank][dt 3][step 5][kg 2][row 32][4]
+    const int per_rank = 3 * 5 * 2 * 32 * 4;
+    const int rank = idx / per_rank;
+    int rem = idx - rank * per_rank;
+    dt = rem / (5 * 256);
+    rem -= dt * 5 * 256;
+    const int step = rem / 256;
+    rem -= step * 256;
+    const int kg = rem / 128;
+    rem -= kg * 128;
+    const int row = rem / 4;
+    ci = rem & 3;
+    int s;
+    if (step == 0) {
+      s = 0;
+      valid = (kg == 0);
+    } else {
+      s = 2 * step - 1 + kg;
+    }
+    co = rank * 32 + row;
+    dh = s / 3; dw = s % 3;
+  }
+  if (kt == 1) {  // 2-D filter: only the centre temporal tap is populated
+    valid = valid && (dt == 1);
+    dt = 0;
+  }
+  float val = 0.f;
+  if (valid && co < cout && ci < cin) {
+    if (!transpose_flip) {
+      const size_t o = ((((static_cast<size_t>(co + cout_off) * w_cin) + (ci + cin_off)) * kt + dt) * 3 + dh) * 3 + dw;
+      val = w[o];
+    } else {
+      const int fdt = (kt == 1) ? 0 : 2 - dt;
+      const size_t o =
+          ((((static_cast<size_t>(ci + cin_off) * w_cin) + (co + cout_off)) * kt + fdt) * 3 + (2 - dh)) * 3 + (2 - dw);
+      val = w[o];
+    }
+  }
+  img[idx] = round_tf32(val);
+}
+
 const char* conv3d_pack_weights(const float* w, int w_cout, int w_cin, int kt, int mode, int transpose_flip,
                                 int cout_off, int cout, int cin_off, int cin, void* img, cudaStream_t stream) {
+  if (kt != 1 && kt != 3) return "kernel depth must be 1 or 3";
+  if (conv_mode_is_tf32(mode)) {
+    const int n = conv3d_umma_wimg_bytes(mode) / 4;
+    pack_weights_tf32_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w, cout, cin, kt, mode, transpose_flip, cin_off,
+                                                                   cout_off, w_cin, static_cast<float*>(img), n);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+  }
   const int total = conv3d_umma_wimg_bytes(mode) / 2;
   if (total == 0) return "unknown conv mode";
-  if (kt != 1 && kt != 3) return "kernel depth must be 1 or 3";
   pack_weights_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w, cout, cin, kt, mode, transpose_flip, cin_off,
                                                                 cout_off, w_cout, w_cin,
                                                                 static_cast<__nv_bfloat16*>(img), total);

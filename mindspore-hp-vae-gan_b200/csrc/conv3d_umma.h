@@ -5,9 +5,16 @@
 
 namespace hpvg {
 
-enum ConvMode { CONV_MODE_64_64 = 0, CONV_MODE_64_16 = 1, CONV_MODE_8_64 = 2, CONV_MODE_64_T = 3 };
+enum ConvMode {
+  CONV_MODE_64_64 = 0, CONV_MODE_64_16 = 1, CONV_MODE_8_64 = 2, CONV_MODE_64_T = 3,
+  // kind::tf32 variants over fp32 channels-last activations.  Byte for byte the shared-memory images of the bf16
+  // variants with half the channels per 128-byte row: 32 -> 64 (a 64 -> 64 layer = two launches, the second adding the
+  // first's fp32 partial sums), <= 4 -> 64 (heads; 16-byte voxels) and 32 -> <= 3 (tails; two launches likewise).
+  CONV_MODE_T32_64 = 4, CONV_MODE_T4_64 = 5, CONV_MODE_T32_T = 6
+};
 enum ConvAct { CONV_ACT_NONE = 0, CONV_ACT_LRELU = 1, CONV_ACT_TANH = 2, CONV_ACT_LRELU_MASK = 3 };
-enum ConvOut { CONV_OUT_BF16_NDHWC = 0, CONV_OUT_F32_NCDHW = 1, CONV_OUT_F32_RAW = 2 };
+enum ConvOut { CONV_OUT_BF16_NDHWC = 0, CONV_OUT_F32_NCDHW = 1, CONV_OUT_F32_RAW = 2, CONV_OUT_F32_NDHWC = 3 };
+inline bool conv_mode_is_tf32(int mode) { return mode >= CONV_MODE_T32_64 && mode <= CONV_MODE_T32_T; }
 
 // device-side parameter block (passed as __grid_constant__)
 struct ConvParams {
@@ -19,10 +26,11 @@ struct ConvParams {
   int act;               // ConvAct
   int out_mode;          // ConvOut
   void* out;
-  int out_pitch;         // channels per voxel of the bf16 output tensor
+  int out_pitch;         // channels per voxel of the channels-last (bf16 / fp32) output tensor
   int out_coff;          // first output channel inside that pitch
   int cout_real;         // CONV_OUT_F32_NCDHW: number of real output channels (<= 4)
-  const float* addend;   // bf16 out: fp32 [V][64] partial sums added before scale/shift (split-Cin);
+  const float* addend;   // cl out: fp32 [V][64] partial sums added before scale/shift (split-Cin); tf32 RAW out: the same,
+                         // added to the raw accumulator (may alias `out`);
                          // NCDHW out: fp32 NCDHW residual added after scale/shift, before the activation
   const void* mask;      // CONV_ACT_LRELU_MASK: bf16 cl tensor (same voxels, 64 channels at `mask`, mask_pitch per voxel)
   int mask_pitch;        //   y = v * LeakyReLU'(mask): the backward of a LeakyReLU fused into the data-gradient conv
@@ -35,8 +43,9 @@ struct ConvParams {
 struct ConvLaunch {
   int mode;              // ConvMode
   int N, T, H, W;
-  const void* in;        // bf16 channels-last; for 64-ch modes may point at a 64-channel slice of a wider tensor
-  int in_pitch;          // channels per voxel of the input tensor (64, 128, ... or 8)
+  const void* in;        // bf16 (fp32 for the tf32 modes) channels-last; may point at a 64- (32-) channel slice of a
+                         // wider tensor
+  int in_pitch;          // channels per voxel of the input tensor (64, 128, ... or 8; tf32: 32k or 4)
   const void* wimg;
   const float* scale;
   const float* shift;
@@ -60,6 +69,13 @@ const char* conv3d_pack_weights(const float* w, int w_cout, int w_cin, int kt, i
 // mode == CONV_MODE_64_T, out_mode == CONV_OUT_F32_NCDHW
 const char* conv3d_tail_launch(const ConvLaunch& L, int sm_count, cudaStream_t stream);
 int conv3d_tail_wimg_bytes();
+
+// the same over fp32 channels-last operands on kind::tf32 (conv3d_wgrad_tf32.cu); pitches in fp32 channels (>= 32, or a
+// narrow tensor of 4k channels)
+const char* conv3d_wgrad_tf32_launch(const void* x, int x_pitch, const void* gy, int gy_pitch, int N, int T, int H,
+                                     int W, float* dw, int w_cin, int kt, int co_off, int co_n, int ci_off, int ci_n,
+                                     int accumulate, float scale, float* workspace, int sm_count, cudaStream_t stream);
+size_t conv3d_wgrad_tf32_workspace_bytes(int sm_count);
 
 // weight gradient (conv3d_wgrad.cu)
 size_t conv3d_wgrad_workspace_bytes(int sm_count);

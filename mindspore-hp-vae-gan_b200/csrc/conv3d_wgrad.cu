@@ -252,6 +252,12 @@ bool make_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, int pitch, in
 
 }  // namespace
 
+void wgrad_reduce_launch(const float* partial, int groups, float* dw, int w_cin, int kt, int co_off, int co_n,
+                         int ci_off, int ci_n, int accumulate, float scale, cudaStream_t stream) {
+  wgrad_reduce_kernel<<<(27 * 4096 + 255) / 256, 256, 0, stream>>>(partial, groups, dw, w_cin, kt, co_off, co_n, ci_off,
+                                                                  ci_n, accumulate, scale);
+}
+
 size_t conv3d_wgrad_workspace_bytes(int sm_count) {
   const int groups = sm_count / 3;
   return static_cast<size_t>(groups) * 27 * 4096 * sizeof(float);

@@ -21,6 +21,19 @@ __device__ __forceinline__ float2 unpack2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
+// one 16-byte block-input voxel: 8 bf16 channels, or (tf32 mode) 4 fp32 channels rounded to tf32
+__device__ __forceinline__ uint4 xin_voxel(const float (&v)[8], int f32) {
+  if (f32) {
+    uint4 r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r.x) : "f"(v[0]));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r.y) : "f"(v[1]));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r.z) : "f"(v[2]));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r.w) : "f"(v[3]));
+    return r;
+  }
+  return make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+}
+
 // ----------------------------------------------------------------------------------------------- pack / unpack
 // thread = (voxel, 8-channel group); consecutive threads walk consecutive voxels so the fp32 side is coalesced.
 __global__ void pack_cl_kernel(const float* __restrict__ x, int C, long long sp /*T*H*W*/, long long voxels,
@@ -483,7 +496,7 @@ __global__ void upsample_noise_pack_tiled_kernel(const float* __restrict__ x, in
                                                  const float* __restrict__ noise, float amp, unsigned long long seed,
                                                  unsigned long long sample_base,
                                                  const unsigned long long* __restrict__ d_sample_offset,
-                                                 float* __restrict__ up, __nv_bfloat16* __restrict__ xin) {
+                                                 float* __restrict__ up, __nv_bfloat16* __restrict__ xin, int xin_f32) {
   extern __shared__ __align__(16) float rs_sm[];
   const ResizeGeom& g = tg.g;
   if (d_sample_offset) sample_base += *d_sample_offset;
@@ -527,8 +540,7 @@ __global__ void upsample_noise_pack_tiled_kernel(const float* __restrict__ x, in
         const float nz = noise ? noise[o] : z[c];
         v[c] = fmaf(nz, amp, u);
       }
-      *reinterpret_cast<uint4*>(xin + (n * spo + sidx) * 8) =
-          make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+      *reinterpret_cast<uint4*>(xin + (n * spo + sidx) * 8) = xin_voxel(v, xin_f32);
     }
   }
 }
@@ -630,7 +642,7 @@ upsample_noise_pack_colwalk_kernel(const float* __restrict__ x, const ResizeGeom
                                    const float* __restrict__ noise, float amp, unsigned long long seed,
                                    unsigned long long sample_base,
                                    const unsigned long long* __restrict__ d_sample_offset, float* __restrict__ up,
-                                   __nv_bfloat16* __restrict__ xin) {
+                                   __nv_bfloat16* __restrict__ xin, int xin_f32) {
   const unsigned plane = g.Ho * g.Wo;
   const unsigned col = blockIdx.x * CW_THREADS + threadIdx.x;
   if (col >= plane) return;
@@ -675,7 +687,7 @@ upsample_noise_pack_colwalk_kernel(const float* __restrict__ x, const ResizeGeom
         up_p[c * spo] = u;
         v[c] = fmaf(z[c], amp, u);
       }
-      *xin_p = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+      *xin_p = xin_voxel(v, xin_f32);
       up_p += plane;
       xin_p += plane;
       sidx += plane;
@@ -1058,7 +1070,7 @@ __global__ void upsample_noise_pack_kernel(const float* __restrict__ x, int N, i
                                            const float* __restrict__ noise, float amp, unsigned long long seed,
                                            unsigned long long sample_base,
                                            const unsigned long long* __restrict__ d_sample_offset,
-                                           float* __restrict__ up, __nv_bfloat16* __restrict__ xin) {
+                                           float* __restrict__ up, __nv_bfloat16* __restrict__ xin, int xin_f32) {
   if (d_sample_offset) sample_base += *d_sample_offset;   // device-resident draw counter (CUDA-graph replays)
   const long long spo = static_cast<long long>(g.To) * g.Ho * g.Wo;
   const long long spi = static_cast<long long>(g.Ti) * g.Hi * g.Wi;
@@ -1091,8 +1103,7 @@ __global__ void upsample_noise_pack_kernel(const float* __restrict__ x, int N, i
       else if (seed != 0ull) nz = z[c];
       v[c] = fmaf(nz, amp, u);
     }
-    *reinterpret_cast<uint4*>(xin + idx * 8) =
-        make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+    *reinterpret_cast<uint4*>(xin + idx * 8) = xin_voxel(v, xin_f32);
   }
 }
 
@@ -2013,7 +2024,7 @@ cudaError_t ew_resize3d_bwd(const float* gy, long long NC, int To, int Ho, int W
 cudaError_t ew_upsample_noise_pack(const float* x, int N, int C, int Ti, int Hi, int Wi, int To, int Ho, int Wo,
                                    const float* noise, float amp, unsigned long long seed,
                                    unsigned long long sample_base, const unsigned long long* d_sample_offset,
-                                   float* up, __nv_bfloat16* xin, cudaStream_t st) {
+                                   float* up, __nv_bfloat16* xin, int xin_f32, cudaStream_t st) {
   const ResizeGeom g = make_geom(Ti, Hi, Wi, To, Ho, Wo, 1);
   TiledGeom tg;
   size_t smem;
@@ -2021,7 +2032,7 @@ cudaError_t ew_upsample_noise_pack(const float* x, int N, int C, int Ti, int Hi,
   if ((C == 1 || C == 3) && colwalk_ok(g, N, C) && make_twalk(g, &tw)) {
     const dim3 grid((Ho * Wo + CW_THREADS - 1) / CW_THREADS, N);
 #define HPVG_CW(C_, T_) upsample_noise_pack_colwalk_kernel<C_, T_><<<grid, CW_THREADS, 0, st>>>( \
-      x, g, tw, noise, amp, seed, sample_base, d_sample_offset, up, xin)
+      x, g, tw, noise, amp, seed, sample_base, d_sample_offset, up, xin, xin_f32)
 #define HPVG_CWT(C_)                       \
     switch (Ti) {                            \
       case 1: HPVG_CW(C_, 1); break;         \
@@ -2041,10 +2052,10 @@ cudaError_t ew_upsample_noise_pack(const float* x, int N, int C, int Ti, int Hi,
     cudaError_t e = rs_allow_smem(upsample_noise_pack_tiled_kernel, &ok);
     if (e != cudaSuccess) return e;
     upsample_noise_pack_tiled_kernel<<<dim3((Ho + tg.band - 1) / tg.band, N), dim3(tg.nx, tg.ny), smem, st>>>(
-        x, C, tg, noise, amp, seed, sample_base, d_sample_offset, up, xin);
+        x, C, tg, noise, amp, seed, sample_base, d_sample_offset, up, xin, xin_f32);
   } else {
     upsample_noise_pack_kernel<<<grid_for(static_cast<long long>(N) * To * Ho * Wo, 256), 256, 0, st>>>(
-        x, N, C, g, noise, amp, seed, sample_base, d_sample_offset, up, xin);
+        x, N, C, g, noise, amp, seed, sample_base, d_sample_offset, up, xin, xin_f32);
   }
   LAUNCH_CHECK();
   return cudaSuccess;

@@ -30,7 +30,7 @@ cudaError_t ew_resize3d_bwd(const float* gy, long long NC, int To, int Ho, int W
 cudaError_t ew_upsample_noise_pack(const float* x, int N, int C, int Ti, int Hi, int Wi, int To, int Ho, int Wo,
                                    const float* noise, float amp, unsigned long long seed,
                                    unsigned long long sample_base, const unsigned long long* d_sample_offset,
-                                   float* up, __nv_bfloat16* xin, cudaStream_t st);
+                                   float* up, __nv_bfloat16* xin, int xin_f32, cudaStream_t st);
 cudaError_t ew_frames_to_clip(const uint8_t* frames, int Hs, int Ws, int bgr, int start, int every, int T, int H, int W,
                               int hflip, float* clip, cudaStream_t st);
 cudaError_t ew_randn(float* z, long long n, unsigned long long seed, unsigned long long offset,
@@ -103,5 +103,23 @@ cudaError_t ew_sn_grad(const float* G, const float* w, const float* u, const flo
 cudaError_t ew_lerp(const float* a, const float* b, float alpha, long long n, float* out, cudaStream_t st);
 cudaError_t ew_gp_grad(const float* g, int N, int C, long long sp, float lambda, float* Gout, float* gp,
                        cudaStream_t st);
+
+
+// ---- fp32 channels-last twins (tf32 precision mode; elementwise_f32.cu)
+cudaError_t ew_pack_cl_f32(const float* x, int N, int C, long long sp, float* y, int c_pitch, int c_off, int c_zero_to,
+                           cudaStream_t st);
+cudaError_t ew_unpack_cl_f32(const float* x, int N, int C, long long sp, int c_pitch, int c_off, float* y,
+                             cudaStream_t st);
+cudaError_t ew_bn_stats_cl_f32(const float* y, long long voxels, double* sum, double* sumsq, cudaStream_t st);
+cudaError_t ew_bn_apply_cl_f32(const float* y, long long voxels, const float* scale, const float* shift, int act,
+                               float* x, cudaStream_t st);
+cudaError_t ew_bn_train_apply_cl_f32(const float* y, long long voxels, const double* sums, const float* gamma,
+                                     const float* beta, float eps, float momentum, float* mm, float* mv, float* saved,
+                                     int act, float* x, cudaStream_t st);
+cudaError_t ew_lrelu_bwd_cl_f32(const float* ga, const float* a, long long elems, float* gz, cudaStream_t st);
+cudaError_t ew_bn_bwd_cl_f32(const float* ga, const float* y, long long voxels, const float* saved, int act,
+                             double* sums, float* gy, float* dgamma, float* dbeta, int accumulate, cudaStream_t st);
+cudaError_t ew_colsum_cl_f32(const float* g, long long voxels, double* scratch, float* out, int accumulate,
+                             cudaStream_t st);
 
 }  // namespace hpvg

@@ -305,4 +305,62 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
       : "memory");
 }
 
+// ---------------------------------------------------------------- TF32 (kind::tf32) variants
+// Operands are 32-bit containers in shared memory; the tensor core reads the upper 19 bits (the low 13 mantissa bits are
+// ignored), so producers round to nearest with round_tf32() before storing an operand.  K = 8 per instruction (32 B).
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+__host__ __device__ __forceinline__ uint32_t make_idesc_tf32(uint32_t M, uint32_t N, uint32_t a_mn_major = 0,
+                                                             uint32_t b_mn_major = 0) {
+  uint32_t d = 0;
+  d |= 1u << 4;   // D format: f32
+  d |= 2u << 7;   // A format: tf32
+  d |= 2u << 10;  // B format: tf32
+  d |= (a_mn_major & 1u) << 15;
+  d |= (b_mn_major & 1u) << 16;
+  d |= ((N >> 3) & 0x3Fu) << 17;
+  d |= ((M >> 4) & 0x1Fu) << 24;
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// compile-time selection between the two operand kinds (same descriptors, same byte layouts)
+template <bool TF32>
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if constexpr (TF32) umma_tf32(d_tmem, a_desc, b_desc, idesc, accumulate);
+  else umma_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+template <bool TF32>
+__device__ __forceinline__ void umma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  if constexpr (TF32) umma_tf32_pair(d_tmem, a_desc, b_desc, idesc, accumulate);
+  else umma_bf16_pair(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+template <bool TF32>
+__host__ __device__ __forceinline__ uint32_t make_idesc(uint32_t M, uint32_t N, uint32_t a_mn = 0, uint32_t b_mn = 0) {
+  return TF32 ? make_idesc_tf32(M, N, a_mn, b_mn) : make_idesc_bf16(M, N, a_mn, b_mn);
+}
+
 }  // namespace hpvg

@@ -95,6 +95,17 @@ _SIGS = {
     "hpvg_sn_grad": ([vp, vp, vp, vp, vp, i, i, i, vp, vp], c_int),
     "hpvg_lerp": ([vp, vp, f, ll, vp, vp], c_int),
     "hpvg_gp_grad": ([vp, i, i, ll, f, vp, vp, vp], c_int),
+    # fp32 channels-last / kind::tf32 twins (tf32 precision mode)
+    "hpvg_pack_cl_f32": ([vp, i, i, i, i, i, vp, i, i, i, vp], c_int),
+    "hpvg_unpack_cl_f32": ([vp, i, i, i, i, i, i, i, vp, vp], c_int),
+    "hpvg_upsample_noise_pack_f32": ([vp, i, i, i, i, i, i, i, i, vp, f, u64, u64, vp, vp, vp, vp], c_int),
+    "hpvg_conv_wgrad_cl_tf32": ([vp, i, vp, i, i, i, i, i, vp, i, i, i, i, i, i, i, f, vp], c_int),
+    "hpvg_bn_stats_cl_f32": ([vp, ll, vp, vp, vp], c_int),
+    "hpvg_bn_apply_lrelu_cl_f32": ([vp, ll, vp, vp, i, vp, vp], c_int),
+    "hpvg_bn_train_apply_cl_f32": ([vp, ll, vp, vp, vp, f, f, vp, vp, vp, i, vp, vp], c_int),
+    "hpvg_lrelu_bwd_cl_f32": ([vp, vp, ll, vp, vp], c_int),
+    "hpvg_bn_bwd_cl_f32": ([vp, vp, ll, vp, i, vp, vp, vp, i, vp], c_int),
+    "hpvg_colsum_cl_f32": ([vp, ll, vp, i, vp], c_int),
     "hpvg_adam_clip_multi": ([i, POINTER(vp), POINTER(vp), POINTER(vp), POINTER(vp), POINTER(ll), POINTER(f), f, f,
                               f, i, f, vp, vp], c_int),
 }

@@ -36,7 +36,7 @@ class RandomFeatures3D:
 
     def __call__(self, x, stream=None):
         """x: fp32 (N,3,T,H,W) or (N,3,H,W) -> bf16 channels-last (N,T,H,W,64)."""
-        return self.layer.forward_cl(ops.pack_cl(as5d(x), c_pitch=8, stream=stream), stream=stream)
+        return self.layer.forward_cl(ops.pack_cl(as5d(x), c_pitch=8, stream=stream, dtype=BF16), stream=stream)
 
 
 def sample_moments(feat_cl, out=None, stream=None):

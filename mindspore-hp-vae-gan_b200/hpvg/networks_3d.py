@@ -11,7 +11,7 @@ import numpy as np
 
 from . import ops
 from .ops import ACT_LRELU, ACT_NONE, ACT_TANH
-from .runtime import BF16, F32, HpvgError, Tensor, from_numpy
+from .runtime import F32, HpvgError, Tensor, from_numpy
 from .utils import images as uimg
 
 
@@ -106,6 +106,7 @@ class ConvLayer(Cell):
             self.p["moving_mean"] = from_numpy(np.zeros(cout, np.float32))
             self.p["moving_variance"] = from_numpy(np.ones(cout, np.float32))
         self._wimgs = None
+        self._wimgs_prec = None
         self._aff = None        # epilogue vectors used by the current forward
         self._aff_bias = None   # cached (1, bias): valid until the parameters change
         self._aff_eval = None   # cached folded eval-mode BatchNorm: valid until parameters / moving stats change
@@ -133,19 +134,13 @@ class ConvLayer(Cell):
         self.invalidate()
 
     # ---- forward
-    def _prepare_wimgs(self, stream=None):
-        """(Re)build the packed filter bank(s) — no side effects on the spectral-norm state."""
-        if self._wimgs is None:
-            w = self.p["weight"]
-            if self.cout <= 4:
-                self._wimgs = [ops.pack_weights(w, ops.tail_mode(self.cout), stream=stream)]
-            else:
-                self._wimgs = []
-                mode = ops.CONV_8_64 if self.cin <= 8 else ops.CONV_64_64
-                for ob in range(self.cout // 64):
-                    for ib in range(1 if self.cin <= 8 else self.cin // 64):
-                        self._wimgs.append(ops.pack_weights(w, mode, cout_off=ob * 64, cout=64, cin_off=ib * 64,
-                                                            cin=min(self.cin, 64), stream=stream))
+    def _prepare_wimgs(self, stream=None, dtype=None):
+        """(Re)build the packed filter bank(s) — no side effects on the spectral-norm state.  The banks are specific
+        to the activation dtype (bf16 -> kind::f16 images, fp32 -> kind::tf32 images), so a switch rebuilds them."""
+        dtype = dtype or ops.cl_dtype()
+        if self._wimgs is None or self._wimgs_prec != dtype:
+            self._wimgs = ops.build_wimgs(self.p["weight"], self.cin, self.cout, dtype=dtype, stream=stream)
+            self._wimgs_prec = dtype
 
     def sn_entry(self, sigma=None, aff=None, u_copy=None, v_copy=None):
         """Table entry for ops.sn_power_iter_multi.  `sigma` / `aff` default to the layer's own persistent buffers;
@@ -162,9 +157,9 @@ class ConvLayer(Cell):
         return {"w": self.p["weight"], "u": self.p["weight_u"], "v": self.p["weight_v"], "sigma": sigma,
                 "bias": self.p["bias"], "aff": aff, "u_copy": u_copy, "v_copy": v_copy}
 
-    def _prepare(self, training, stream):
+    def _prepare(self, training, stream, dtype=None):
         """Filter bank + the epilogue vectors (bias / folded BN / 1/sigma) for this forward."""
-        self._prepare_wimgs(stream)
+        self._prepare_wimgs(stream, dtype)
         if self.sn:
             # Q5: u/v advance on EVERY forward, train or eval (spectral_norm.py:146-148)
             if not self._sn_fresh:
@@ -189,11 +184,12 @@ class ConvLayer(Cell):
         normalise+activation pass.  `stats`: pre-zeroed fp64 (2,64) scratch (allocated here when absent);
         `saved`: dict that receives raw=y and bn=(scale, shift, mean, invstd) for the backward."""
         training = self.training
-        self._prepare(training, stream)
+        self._prepare(training, stream, x_cl.dtype)
         if self.bn and training:
             N, T, H, W, _ = x_cl.shape
             if raw is None:
-                raw = ws.get(tag + ".raw", (N, T, H, W, self.cout), BF16) if ws else Tensor((N, T, H, W, self.cout), BF16)
+                dt = x_cl.dtype
+                raw = ws.get(tag + ".raw", (N, T, H, W, self.cout), dt) if ws else Tensor((N, T, H, W, self.cout), dt)
             if stats is None:
                 stats = Tensor((2, 64), "float64").zero_(stream)
             y = ops.conv3d_cl_any(x_cl, self.p["weight"], self._aff, ACT_NONE, self.cin, self.cout, out=raw,
@@ -340,10 +336,10 @@ class Encode3DVAE(Cell):
             f = l.forward_cl(f, stream=stream)
         return self._mu.forward_cl(f, stream=stream), self._logvar.forward_cl(f, stream=stream), f
 
-    def construct(self, x):
+    def construct(self, x, stream=None):
         nd4 = len(x.shape) == 4
-        mu, logvar, _ = self.construct_cl(ops.pack_cl(as5d(x), c_pitch=8))
-        mu, logvar = ops.unpack_cl(mu), ops.unpack_cl(logvar)
+        mu, logvar, _ = self.construct_cl(ops.pack_cl(as5d(x), c_pitch=ops.narrow_pitch(), stream=stream), stream=stream)
+        mu, logvar = ops.unpack_cl(mu, stream=stream), ops.unpack_cl(logvar, stream=stream)
         return (as4d(mu), as4d(logvar)) if nd4 else (mu, logvar)
 
 
@@ -363,7 +359,7 @@ class WDiscriminator3D(Cell):
     def construct(self, x, stream=None):
         nd4 = len(x.shape) == 4
         sn_prepare_batch([self.head] + self.body.layers, stream)
-        h = self.head.forward_cl(ops.pack_cl(as5d(x), c_pitch=8, stream=stream), stream=stream)
+        h = self.head.forward_cl(ops.pack_cl(as5d(x), c_pitch=ops.narrow_pitch(), stream=stream), stream=stream)
         for l in self.body.layers:
             h = l.forward_cl(h, stream=stream)
         out = self.tail.forward_cl(h, stream=stream)
@@ -429,7 +425,7 @@ class GeneratorHPVAEGAN(Cell):
         N, T, H, W, _ = x_cl.shape
         h = x_cl
         for j, layer in enumerate(block.layers[:-1]):
-            buf = ws.get("%s.act%d" % (tag, j & 1), (N, T, H, W, self.N), BF16)
+            buf = ws.get("%s.act%d" % (tag, j & 1), (N, T, H, W, self.N), x_cl.dtype)
             stats = self.bn_slab.take() if (layer.bn and layer.training) else None
             h = layer.forward_cl(h, out=buf, ws=ws, tag=tag, stream=stream, stats=stats)
         tail = block.layers[-1]
@@ -453,7 +449,7 @@ class GeneratorHPVAEGAN(Cell):
         if self.training:
             self.bn_slab.reset(stream)
         if noise_init is None:
-            mu, logvar = self.encode.construct(video)
+            mu, logvar = self.encode.construct(video, stream=stream)
             if self.is_training:
                 if eps is None:
                     eps = from_numpy(np.random.normal(size=mu.shape).astype(np.float32))   # networks_3d.py:28-30
@@ -464,8 +460,8 @@ class GeneratorHPVAEGAN(Cell):
         else:
             z_vae = noise_init
         N = z_vae.shape[0]
-        z_cl = ops.pack_cl(z_vae, out=self.ws.get("z", (N,) + tuple(z_vae.shape[2:]) + (z_vae.shape[1],), BF16),
-                           stream=stream)
+        z_cl = ops.pack_cl(z_vae, out=self.ws.get("z", (N,) + tuple(z_vae.shape[2:]) + (z_vae.shape[1],),
+                                                  ops.cl_dtype()), stream=stream)
         vae_out = self._run_block(self.decoder, z_cl, None, "dec", stream,
                                   out=self.ws.get("vae_out", (N, self.opt.nc_im) + tuple(z_vae.shape[2:]), F32))
         if sample_init is None:
@@ -488,7 +484,7 @@ class GeneratorHPVAEGAN(Cell):
             size = self.stage_shape(idx + 1)
             N = x_prev_out.shape[0]
             up = self.ws.get("up%d" % idx, (N, opt.nc_im) + size, F32)
-            xin = self.ws.get("xin%d" % idx, (N,) + size + (8,), BF16)
+            xin = self.ws.get("xin%d" % idx, (N,) + size + (ops.narrow_pitch(),), ops.cl_dtype())
             add_noise = self.noise_at(idx + 1, isRandom)
             noise_t, seed, amp = None, 0, 0.0
             if add_noise:

@@ -2,6 +2,7 @@
 (SURVEY.md §2.2).  Tensors are `hpvg.runtime.Tensor` (device memory); fp32 tensors use the reference's
 NCDHW layout, "cl" tensors are the kernels' internal channels-last bf16 layout."""
 import ctypes
+import os
 
 import numpy as np
 
@@ -10,14 +11,48 @@ from ._lib import HpvgError, check, lib
 from .runtime import BF16, F32, F64, I32, Tensor, _s
 
 CONV_64_64, CONV_64_16, CONV_8_64, CONV_64_3 = 0, 1, 2, 3
+CONV_T32_64, CONV_T4_64, CONV_T32_3 = 4, 5, 6      # kind::tf32 variants over fp32 channels-last activations
 ACT_NONE, ACT_LRELU, ACT_TANH, ACT_LRELU_MASK = 0, 1, 2, 3
-OUT_BF16_CL, OUT_F32_NCDHW, OUT_F32_RAW = 0, 1, 2
+OUT_BF16_CL, OUT_F32_NCDHW, OUT_F32_RAW, OUT_F32_CL = 0, 1, 2, 3
 BN_EPS = 1e-5        # mindspore.nn.BatchNorm3d default
 BN_MOMENTUM = 0.9    # mindspore.nn.BatchNorm3d default (moving = 0.9*moving + 0.1*batch)
 
 
 def _p(t):
     return None if t is None else ctypes.c_void_p(t.ptr)
+
+
+# ------------------------------------------------------------------------------------------------ precision mode
+# "bf16": activations between convs are channels-last bf16, tcgen05 kind::f16 (north_star's 1e-2 branch; the fast path).
+# "tf32": activations are channels-last fp32 (values rounded to tf32), tcgen05 kind::tf32 — the fp32-accurate path
+#         (north_star's 1e-3 branch; the reference computes in fp32, networks_3d.py:48-50).
+# The mode decides the dtype of NEW channels-last tensors; every operator dispatches on the dtype of its operands.
+_PRECISION = [os.environ.get("HPVG_PRECISION", "bf16").lower()]
+
+
+def set_precision(mode):
+    mode = str(mode).lower()
+    if mode not in ("bf16", "tf32"):
+        raise HpvgError("precision must be 'bf16' or 'tf32', got %r" % (mode,))
+    _PRECISION[0] = mode
+
+
+def precision():
+    return _PRECISION[0]
+
+
+def cl_dtype():
+    """dtype of channels-last activation tensors in the current precision mode."""
+    return F32 if _PRECISION[0] == "tf32" else BF16
+
+
+def narrow_pitch(dtype=None):
+    """Channels per voxel of a 'narrow' (16-byte) channels-last tensor: block inputs, 3-channel gradients."""
+    return 4 if (dtype or cl_dtype()) == F32 else 8
+
+
+def _isz(t):
+    return 4 if t.dtype == F32 else 2
 
 
 # ------------------------------------------------------------------------------------------------ in-situ kernel timing
@@ -42,27 +77,31 @@ def stop_profile():
 
 
 # ------------------------------------------------------------------------------------------------ layout
-def pack_cl(x, c_pitch=None, c_off=0, zero_to=None, out=None, stream=None):
-    """fp32 (N,C,T,H,W) -> bf16 (N,T,H,W,c_pitch)."""
+def pack_cl(x, c_pitch=None, c_off=0, zero_to=None, out=None, stream=None, dtype=None):
+    """fp32 (N,C,T,H,W) -> channels-last (N,T,H,W,c_pitch) in the current precision's dtype (or `out`'s)."""
     N, C, T, H, W = x.shape
+    dtype = out.dtype if out is not None else (dtype or cl_dtype())
+    g = narrow_pitch(dtype)
     if c_pitch is None:
-        c_pitch = (C + 7) // 8 * 8
+        c_pitch = out.shape[-1] if out is not None else (C + g - 1) // g * g
     if zero_to is None:
-        zero_to = min(c_pitch, (c_off + C + 7) // 8 * 8)
+        zero_to = min(c_pitch, (c_off + C + g - 1) // g * g)
     if out is None:
-        out = Tensor((N, T, H, W, c_pitch), BF16)
-    check(lib.hpvg_pack_cl(_p(x), N, C, T, H, W, _p(out), c_pitch, c_off, zero_to, _s(stream)), "pack_cl")
+        out = Tensor((N, T, H, W, c_pitch), dtype)
+    fn = lib.hpvg_pack_cl_f32 if dtype == F32 else lib.hpvg_pack_cl
+    check(fn(_p(x), N, C, T, H, W, _p(out), c_pitch, c_off, zero_to, _s(stream)), "pack_cl")
     return out
 
 
 def unpack_cl(x_cl, C=None, c_off=0, out=None, stream=None):
-    """bf16 (N,T,H,W,c_pitch) -> fp32 (N,C,T,H,W)."""
+    """channels-last (N,T,H,W,c_pitch) bf16 / fp32 -> fp32 (N,C,T,H,W)."""
     N, T, H, W, pitch = x_cl.shape
     if C is None:
         C = pitch - c_off
     if out is None:
         out = Tensor((N, C, T, H, W), F32)
-    check(lib.hpvg_unpack_cl(_p(x_cl), N, C, T, H, W, pitch, c_off, _p(out), _s(stream)), "unpack_cl")
+    fn = lib.hpvg_unpack_cl_f32 if x_cl.dtype == F32 else lib.hpvg_unpack_cl
+    check(fn(_p(x_cl), N, C, T, H, W, pitch, c_off, _p(out), _s(stream)), "unpack_cl")
     return out
 
 
@@ -84,6 +123,10 @@ def tail_mode(cout):
     return CONV_64_3 if cout <= 3 else CONV_64_16
 
 
+def is_tf32_mode(mode):
+    return mode >= CONV_T32_64
+
+
 def pack_weights(w, mode, transpose_flip=False, cout_off=0, cout=None, cin_off=0, cin=None, out=None, stream=None):
     """w: fp32 (Cout, Cin, [kt,] 3, 3) device tensor -> packed filter-bank image for `mode`."""
     if len(w.shape) == 5:
@@ -94,26 +137,66 @@ def pack_weights(w, mode, transpose_flip=False, cout_off=0, cout=None, cin_off=0
     cout = eff_cout - cout_off if cout is None else cout
     cin = eff_cin - cin_off if cin is None else cin
     if out is None:
-        out = Tensor((lib.hpvg_conv_wimg_bytes(mode) // 2,), BF16)
+        nb = lib.hpvg_conv_wimg_bytes(mode)
+        out = Tensor((nb // 4,), F32) if is_tf32_mode(mode) else Tensor((nb // 2,), BF16)
     check(lib.hpvg_conv_pack_weights(_p(w), w_cout, w_cin, kt, mode, 1 if transpose_flip else 0, cout_off, cout,
                                      cin_off, cin, _p(out), _s(stream)), "conv_pack_weights")
     return out
 
 
-def conv_cl(mode, x_cl, wimg, scale, shift, act=ACT_NONE, out_mode=OUT_BF16_CL, out=None, out_pitch=64, out_coff=0,
+def build_wimgs(w, cin, cout, transpose_flip=False, dtype=None, stream=None):
+    """Packed filter banks of a cin -> cout convolution, in the order conv3d_cl_any consumes them, for activations of
+    `dtype` (default: the current precision mode).  cin / cout are the EFFECTIVE channel counts (for the data-gradient
+    conv, transpose_flip=True, they are the forward layer's cout / cin)."""
+    tf = (dtype or cl_dtype()) == F32
+    if cout <= 4:
+        if cin != 64:
+            raise HpvgError("tail convolutions read 64 channels")
+        if tf:
+            if cout > 3:
+                raise HpvgError("tf32 tail convolutions write at most 3 channels")
+            return [pack_weights(w, CONV_T32_3, transpose_flip, cout=cout, cin_off=32 * ib, cin=32, stream=stream)
+                    for ib in range(2)]
+        return [pack_weights(w, tail_mode(cout), transpose_flip, cout=cout, stream=stream)]
+    imgs = []
+    if cin <= 8:
+        if tf and cin > 4:
+            raise HpvgError("tf32 head convolutions read at most 4 channels")
+        mode = CONV_T4_64 if tf else CONV_8_64
+        for ob in range(cout // 64):
+            imgs.append(pack_weights(w, mode, transpose_flip, cout_off=ob * 64, cout=64, cin=cin, stream=stream))
+        return imgs
+    blk = 32 if tf else 64
+    mode = CONV_T32_64 if tf else CONV_64_64
+    for ob in range(cout // 64):
+        for ib in range(cin // blk):
+            imgs.append(pack_weights(w, mode, transpose_flip, cout_off=ob * 64, cout=64, cin_off=ib * blk, cin=blk,
+                                     stream=stream))
+    return imgs
+
+
+def conv_cl(mode, x_cl, wimg, scale, shift, act=ACT_NONE, out_mode=None, out=None, out_pitch=64, out_coff=0,
             cout_real=64, addend=None, in_coff=0, stats=None, mask=None, mask_coff=0, stream=None):
-    """Raw kernel call.  x_cl: bf16 (N,T,H,W,in_pitch); reads channels [in_coff, in_coff+64|8).
+    """Raw kernel call.  x_cl: channels-last (N,T,H,W,in_pitch), bf16 for the kind::f16 variants, fp32 for the kind::tf32
+    ones; reads channels [in_coff, in_coff + 64|8 (32|4)).
     stats: optional fp64 (2,64) tensor accumulating the per-channel sum / sum of squares of the stored output.
-    mask (act=ACT_LRELU_MASK): bf16 cl tensor of a stored LeakyReLU activation; output = v * LeakyReLU'(mask)."""
+    mask (act=ACT_LRELU_MASK, bf16 only): cl tensor of a stored LeakyReLU activation; output = v * LeakyReLU'(mask)."""
     N, T, H, W, in_pitch = x_cl.shape
+    tf = is_tf32_mode(mode)
+    if tf != (x_cl.dtype == F32):
+        raise HpvgError("conv_cl: kernel variant %d does not read %s activations" % (mode, x_cl.dtype))
+    if out_mode is None:
+        out_mode = OUT_F32_CL if tf else OUT_BF16_CL
     if out is None:
         if out_mode == OUT_BF16_CL:
             out = Tensor((N, T, H, W, out_pitch), BF16)
+        elif out_mode == OUT_F32_CL:
+            out = Tensor((N, T, H, W, out_pitch), F32)
         elif out_mode == OUT_F32_RAW:
             out = Tensor((N, T, H, W, 64), F32)
         else:
             out = Tensor((N, cout_real, T, H, W), F32)
-    in_ptr = ctypes.c_void_p(x_cl.ptr + 2 * in_coff)
+    in_ptr = ctypes.c_void_p(x_cl.ptr + _isz(x_cl) * in_coff)
     timed = _prof is not None and (_prof["mode"] == mode or _prof["mode"] is None)
     if timed:
         e0, e1 = rt.Event(), rt.Event()
@@ -154,42 +237,82 @@ def _sc(aff):
     return aff, aff.view((64,), F32, 256)
 
 
-def conv3d_cl_any(x_cl, w, aff, act, cin, cout, out_mode=OUT_BF16_CL, residual=None, out=None, wimgs=None,
-                  transpose_flip=False, stats=None, mask=None, stream=None):
+_SCRATCH = {}
+
+
+def _zeros64():
+    t = _SCRATCH.get("zeros64")
+    if t is None:
+        t = Tensor((64,), F32).zero_()
+        rt.device_sync()
+        _SCRATCH["zeros64"] = t
+    return t
+
+
+def _partial_buf(shape, stream):
+    """fp32 raw partial sums of a split-Cin layer: one buffer per (stream, shape) — launches on a stream are ordered, so
+    consecutive layers can share it; concurrent streams get their own."""
+    key = ("partial", None if stream is None else stream.handle.value, tuple(shape))
+    t = _SCRATCH.get(key)
+    if t is None:
+        t = Tensor(shape, F32)
+        _SCRATCH[key] = t
+    return t
+
+
+def conv3d_cl_any(x_cl, w, aff, act, cin, cout, out_mode=None, residual=None, out=None, wimgs=None,
+                  transpose_flip=False, stats=None, mask=None, stream=None, scale_shift=None):
     """Convolution for every channel combination on the hot path, composed from the kernel variants:
-    Cin in {<=8, 64, 128}, Cout in {<=4, 64, 128}.  aff: (2,64*ceil(cout/64)) epilogue vectors.
-    Returns bf16 cl (cout 64/128) or fp32 ncdhw (cout <= 4)."""
+    Cin in {<=8, 64, 128}, Cout in {<=4, 64, 128}.  aff: (2,64*ceil(cout/64)) epilogue vectors (or scale_shift = one
+    (scale, shift) pair of 64-vectors used for every output block).  The precision follows x_cl's dtype: bf16 ->
+    kind::f16 kernels, fp32 -> kind::tf32 kernels (a 64-channel input block is consumed in two 32-channel launches).
+    Returns channels-last (cout 64/128, same dtype as x_cl) or fp32 ncdhw (cout <= 4)."""
     N, T, H, W, pitch = x_cl.shape
+    tf = x_cl.dtype == F32
+    if wimgs is None:
+        wimgs = build_wimgs(w, cin, cout, transpose_flip, dtype=x_cl.dtype, stream=stream)
+    if mask is not None and tf:
+        raise HpvgError("the fused LeakyReLU-mask epilogue exists for the bf16 kernels only")
     if cout <= 4:
         assert cin == 64
-        mode = tail_mode(cout)
-        wi = wimgs[0] if wimgs else pack_weights(w, mode, transpose_flip, stream=stream)
-        s, b = _sc(aff)
-        return conv_cl(mode, x_cl, wi, s, b, act, OUT_F32_NCDHW, out=out, cout_real=cout, addend=residual,
-                       stream=stream)
+        s, b = scale_shift if scale_shift is not None else _sc(aff)
+        if not tf:
+            return conv_cl(tail_mode(cout), x_cl, wimgs[0], s, b, act, OUT_F32_NCDHW, out=out, cout_real=cout,
+                           addend=residual, stream=stream)
+        # two 32-channel launches: (conv_lo*scale + residual), then act(conv_hi*scale + shift + that)
+        out = conv_cl(CONV_T32_3, x_cl, wimgs[0], s, _zeros64(), ACT_NONE, OUT_F32_NCDHW, out=out, cout_real=cout,
+                      addend=residual, stream=stream)
+        return conv_cl(CONV_T32_3, x_cl, wimgs[1], s, b, act, OUT_F32_NCDHW, out=out, cout_real=cout, addend=out,
+                       in_coff=32, stream=stream)
     n_ob = cout // 64
-    n_ib = 1 if cin <= 8 else cin // 64
+    blk = 32 if tf else 64
+    n_ib = 1 if cin <= 8 else cin // blk
+    cl_out = OUT_F32_CL if tf else OUT_BF16_CL
     if out is None:
-        out = Tensor((N, T, H, W, cout), BF16)
+        out = Tensor((N, T, H, W, cout), x_cl.dtype)
     k = 0
     for ob in range(n_ob):
-        s = aff.view((64,), F32, ob * 256)
-        b = aff.view((64,), F32, (n_ob + ob) * 256)
+        if scale_shift is not None:
+            s, b = scale_shift
+        else:
+            s = aff.view((64,), F32, ob * 256)
+            b = aff.view((64,), F32, (n_ob + ob) * 256)
         partial = None
         for ib in range(n_ib):
-            mode = CONV_8_64 if cin <= 8 else CONV_64_64
-            if wimgs:
-                wi = wimgs[k]
+            if cin <= 8:
+                mode = CONV_T4_64 if tf else CONV_8_64
             else:
-                wi = pack_weights(w, mode, transpose_flip, cout_off=ob * 64, cout=64, cin_off=ib * 64,
-                                  cin=min(cin, 64), stream=stream)
+                mode = CONV_T32_64 if tf else CONV_64_64
+            wi = wimgs[k]
             k += 1
             last = ib == n_ib - 1
             if not last:
-                partial = conv_cl(mode, x_cl, wi, s, b, ACT_NONE, OUT_F32_RAW, in_coff=ib * 64, stream=stream)
+                buf = _partial_buf((N, T, H, W, 64), stream) if tf else None
+                partial = conv_cl(mode, x_cl, wi, s, b, ACT_NONE, OUT_F32_RAW, out=buf, addend=partial,
+                                  in_coff=ib * blk, stream=stream)
             else:
-                conv_cl(mode, x_cl, wi, s, b, act, OUT_BF16_CL, out=out, out_pitch=cout, out_coff=ob * 64,
-                        addend=partial, in_coff=ib * 64, stats=stats, mask=mask, mask_coff=ob * 64, stream=stream)
+                conv_cl(mode, x_cl, wi, s, b, act, cl_out, out=out, out_pitch=cout, out_coff=ob * 64,
+                        addend=partial, in_coff=ib * blk, stats=stats, mask=mask, mask_coff=ob * 64, stream=stream)
     return out
 
 
@@ -268,14 +391,16 @@ def counter_add(counter, inc=1, stream=None):
 
 def upsample_noise_pack(x, size, noise=None, amp=0.0, seed=0, sample_base=0, up=None, xin=None, stream=None,
                         d_sample_offset=None):
-    """Block input stage (networks_3d.py:440-446).  Returns (up fp32 ncdhw, x_in bf16 cl 8-channel)."""
+    """Block input stage (networks_3d.py:440-446).  Returns (up fp32 ncdhw, x_in narrow channels-last: 8 bf16 channels
+    or, in tf32 mode, 4 fp32 channels per voxel)."""
     N, C, Ti, Hi, Wi = x.shape
     To, Ho, Wo = (int(v) for v in size)
     if up is None:
         up = Tensor((N, C, To, Ho, Wo), F32)
     if xin is None:
-        xin = Tensor((N, To, Ho, Wo, 8), BF16)
-    check(lib.hpvg_upsample_noise_pack(_p(x), N, C, Ti, Hi, Wi, To, Ho, Wo, _p(noise), float(amp), int(seed),
+        xin = Tensor((N, To, Ho, Wo, narrow_pitch()), cl_dtype())
+    fn = lib.hpvg_upsample_noise_pack_f32 if xin.dtype == F32 else lib.hpvg_upsample_noise_pack
+    check(fn(_p(x), N, C, Ti, Hi, Wi, To, Ho, Wo, _p(noise), float(amp), int(seed),
                                        int(sample_base), _p(d_sample_offset), _p(up), _p(xin), _s(stream)),
           "upsample_noise_pack")
     return up, xin
@@ -283,13 +408,15 @@ def upsample_noise_pack(x, size, noise=None, amp=0.0, seed=0, sample_base=0, up=
 
 # ------------------------------------------------------------------------------------------------ batch norm (train)
 def bn_train_cl(y_cl, gamma, beta, moving_mean, moving_var, act=ACT_LRELU, out=None, stats=None, stream=None):
-    """Training-mode BatchNorm + LeakyReLU over a (.., 64) bf16 cl tensor (networks_3d.py:52).  Updates the moving
+    """Training-mode BatchNorm + LeakyReLU over a (.., 64) cl tensor (networks_3d.py:52).  Updates the moving
     statistics in place.  Returns (x_cl, saved) where saved = (scale, shift, mean, invstd) for the backward."""
     voxels = int(np.prod(y_cl.shape[:-1]))
+    f32 = y_cl.dtype == F32
     if stats is None:
         stats = Tensor((2, 64), F64)
     sums, sumsq = stats, stats.view((64,), F64, 512)
-    check(lib.hpvg_bn_stats_cl(_p(y_cl), voxels, _p(sums), _p(sumsq), _s(stream)), "bn_stats")
+    check((lib.hpvg_bn_stats_cl_f32 if f32 else lib.hpvg_bn_stats_cl)(_p(y_cl), voxels, _p(sums), _p(sumsq),
+                                                                       _s(stream)), "bn_stats")
     saved = Tensor((4, 64), F32)
     sc, sh = saved, saved.view((64,), F32, 256)
     mean, invstd = saved.view((64,), F32, 512), saved.view((64,), F32, 768)
@@ -297,8 +424,9 @@ def bn_train_cl(y_cl, gamma, beta, moving_mean, moving_var, act=ACT_LRELU, out=N
                                _p(moving_mean), _p(moving_var), _p(sc), _p(sh), _p(mean), _p(invstd), _s(stream)),
           "bn_finalize")
     if out is None:
-        out = Tensor(y_cl.shape, BF16)
-    check(lib.hpvg_bn_apply_lrelu_cl(_p(y_cl), voxels, _p(sc), _p(sh), act, _p(out), _s(stream)), "bn_apply")
+        out = Tensor(y_cl.shape, y_cl.dtype)
+    check((lib.hpvg_bn_apply_lrelu_cl_f32 if f32 else lib.hpvg_bn_apply_lrelu_cl)(
+        _p(y_cl), voxels, _p(sc), _p(sh), act, _p(out), _s(stream)), "bn_apply")
     return out, saved
 
 
@@ -308,8 +436,9 @@ def bn_train_fused_cl(y_cl, stats, gamma, beta, moving_mean, moving_var, act=ACT
     epilogue (conv_cl(stats=...)).  Updates the moving statistics; `saved` (4,64) receives (scale, shift, mean, invstd)."""
     voxels = int(np.prod(y_cl.shape[:-1]))
     if out is None:
-        out = Tensor(y_cl.shape, BF16)
-    check(lib.hpvg_bn_train_apply_cl(_p(y_cl), voxels, _p(stats), _p(gamma), _p(beta), BN_EPS, BN_MOMENTUM,
+        out = Tensor(y_cl.shape, y_cl.dtype)
+    fn = lib.hpvg_bn_train_apply_cl_f32 if y_cl.dtype == F32 else lib.hpvg_bn_train_apply_cl
+    check(fn(_p(y_cl), voxels, _p(stats), _p(gamma), _p(beta), BN_EPS, BN_MOMENTUM,
                                      _p(moving_mean), _p(moving_var), _p(saved), act, _p(out), _s(stream)),
           "bn_train_apply")
     return out
@@ -404,37 +533,43 @@ def adam_clip_multi(params, grads, ms, vs, lrs, step, beta1=0.5, beta2=0.999, ep
 # ================================================================================================ backward operators
 def conv_wgrad_cl(x_cl, gy_cl, dw, co_off=0, co_n=64, ci_off=0, ci_n=64, x_coff=0, gy_coff=0, accumulate=False,
                   scale=1.0, stream=None):
-    """dW block (+)= scale * sum_v gy[v] (x) x[v+tap].  x_cl / gy_cl: bf16 cl, either >= 64 channels (a 64-channel
-    slice at x_coff / gy_coff) or a narrow tensor (pitch 8..56: all of its channels, the rest read as zero); dw: fp32
-    (Cout, Cin, [kt,] 3, 3)."""
+    """dW block (+)= scale * sum_v gy[v] (x) x[v+tap].  x_cl / gy_cl: cl tensors of the same dtype (bf16 -> kind::f16
+    kernel, fp32 -> kind::tf32 kernel), either >= 64 channels (a 64-channel slice at x_coff / gy_coff) or a narrow
+    tensor (all of its channels, the rest read as zero); dw: fp32 (Cout, Cin, [kt,] 3, 3)."""
     N, T, H, W, xp = x_cl.shape
     gp = gy_cl.shape[-1]
+    if x_cl.dtype != gy_cl.dtype:
+        raise HpvgError("conv_wgrad_cl: operands must have the same dtype")
     if (xp < 64 and x_coff) or (gp < 64 and gy_coff):
         raise HpvgError("conv_wgrad_cl: a narrow operand cannot be sliced")
     kt = dw.shape[2] if len(dw.shape) == 5 else 1
-    check(lib.hpvg_conv_wgrad_cl(ctypes.c_void_p(x_cl.ptr + 2 * x_coff), xp, ctypes.c_void_p(gy_cl.ptr + 2 * gy_coff),
-                                 gp, N, T, H, W, _p(dw), dw.shape[1], kt, co_off, co_n, ci_off, ci_n,
-                                 1 if accumulate else 0, float(scale), _s(stream)), "conv_wgrad_cl")
+    isz = _isz(x_cl)
+    fn = lib.hpvg_conv_wgrad_cl_tf32 if x_cl.dtype == F32 else lib.hpvg_conv_wgrad_cl
+    check(fn(ctypes.c_void_p(x_cl.ptr + isz * x_coff), xp, ctypes.c_void_p(gy_cl.ptr + isz * gy_coff),
+             gp, N, T, H, W, _p(dw), dw.shape[1], kt, co_off, co_n, ci_off, ci_n,
+             1 if accumulate else 0, float(scale), _s(stream)), "conv_wgrad_cl")
     return dw
 
 
 def lrelu_bwd_cl(ga, a, out=None, stream=None):
-    out = out or Tensor(ga.shape, BF16)
-    check(lib.hpvg_lrelu_bwd_cl(_p(ga), _p(a), ga.size, _p(out), _s(stream)), "lrelu_bwd_cl")
+    out = out or Tensor(ga.shape, ga.dtype)
+    fn = lib.hpvg_lrelu_bwd_cl_f32 if ga.dtype == F32 else lib.hpvg_lrelu_bwd_cl
+    check(fn(_p(ga), _p(a), ga.size, _p(out), _s(stream)), "lrelu_bwd_cl")
     return out
 
 
 def bn_bwd_cl(ga, y, saved, act=ACT_LRELU, out=None, dgamma=None, dbeta=None, accumulate=False, stream=None):
     voxels = int(np.prod(ga.shape[:-1]))
-    out = out or Tensor(ga.shape, BF16)
-    check(lib.hpvg_bn_bwd_cl(_p(ga), _p(y), voxels, _p(saved), act, _p(out), _p(dgamma), _p(dbeta),
+    out = out or Tensor(ga.shape, ga.dtype)
+    fn = lib.hpvg_bn_bwd_cl_f32 if ga.dtype == F32 else lib.hpvg_bn_bwd_cl
+    check(fn(_p(ga), _p(y), voxels, _p(saved), act, _p(out), _p(dgamma), _p(dbeta),
                              1 if accumulate else 0, _s(stream)), "bn_bwd_cl")
     return out
 
 
 def colsum_cl(g, out, accumulate=False, stream=None):
-    check(lib.hpvg_colsum_cl(_p(g), int(np.prod(g.shape[:-1])), _p(out), 1 if accumulate else 0, _s(stream)),
-          "colsum_cl")
+    fn = lib.hpvg_colsum_cl_f32 if g.dtype == F32 else lib.hpvg_colsum_cl
+    check(fn(_p(g), int(np.prod(g.shape[:-1])), _p(out), 1 if accumulate else 0, _s(stream)), "colsum_cl")
     return out
 
 

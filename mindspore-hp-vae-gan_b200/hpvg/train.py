@@ -12,8 +12,8 @@ import numpy as np
 
 from . import ops
 from .networks_3d import BnStatsSlab, ConvLayer, Workspace, as5d
-from .ops import ACT_LRELU, ACT_LRELU_MASK, ACT_NONE, ACT_TANH, CONV_64_16, CONV_64_64, CONV_8_64, OUT_BF16_CL, OUT_F32_NCDHW, OUT_F32_RAW
-from .runtime import BF16, F32, U64, Event, Graph, HpvgError, Tensor, device_sync, from_numpy
+from .ops import ACT_LRELU, ACT_LRELU_MASK, ACT_NONE, ACT_TANH
+from .runtime import F32, U64, Event, Graph, HpvgError, Tensor, device_sync, from_numpy
 from .utils import images as uimg
 
 import os as _os
@@ -127,15 +127,15 @@ def layer_forward_train(layer, x_cl, ws, key, stream=None, slab=None, defer=None
     defer: list that receives (saved, moving_mean, moving_var) INSTEAD of updating the moving statistics in the BatchNorm
     kernel — used when several forwards of the network run concurrently (see GraphedIteration)."""
     N, T, H, W, _ = x_cl.shape
-    layer._prepare(True, stream)
+    layer._prepare(True, stream, x_cl.dtype)
     ctx = {"x": x_cl, "layer": layer}
     if layer.bn:
         # conv(+bias) with the batch statistics accumulated in its epilogue, then ONE normalise+LeakyReLU pass
-        y = ws.get(key + ".y", (N, T, H, W, layer.cout), BF16)
+        y = ws.get(key + ".y", (N, T, H, W, layer.cout), x_cl.dtype)
         stats = slab.take() if slab is not None else Tensor((2, 64), "float64").zero_(stream)
         ops.conv3d_cl_any(x_cl, layer.p["weight"], layer._aff, ACT_NONE, layer.cin, layer.cout, out=y,
                           wimgs=layer._wimgs, stats=stats, stream=stream)
-        a = ws.get(key + ".a", (N, T, H, W, layer.cout), BF16)
+        a = ws.get(key + ".a", (N, T, H, W, layer.cout), x_cl.dtype)
         saved = ws.get(key + ".saved", (4, 64), F32)
         if defer is None:
             ops.bn_train_fused_cl(y, stats, layer.p["gamma"], layer.p["beta"], layer.p["moving_mean"],
@@ -161,7 +161,7 @@ def layer_forward_train(layer, x_cl, ws, key, stream=None, slab=None, defer=None
             layer._aff = aff
     if layer.cout <= 4:
         raise HpvgError("tail convs are handled by the block-level code")
-    a = ws.get(key + ".a", (N, T, H, W, layer.cout), BF16)
+    a = ws.get(key + ".a", (N, T, H, W, layer.cout), x_cl.dtype)
     ops.conv3d_cl_any(x_cl, layer.p["weight"], layer._aff, layer.act, layer.cin, layer.cout, out=a,
                       wimgs=layer._wimgs, stream=stream)
     ctx.update(a=a)
@@ -189,18 +189,8 @@ def _dgrad_wimgs(layer, stream=None):
     cached = getattr(layer, "_dgrad_cache", None)
     if cached is not None and layer._wimgs is not None and cached[0] is layer._wimgs:
         return cached[1]
-    w = layer.p["weight"]
-    cin, cout = layer.cin, layer.cout           # forward channels; dgrad maps cout -> cin
-    if cin <= 8:                                 # 64 -> (<=4): tail-type kernel
-        imgs = [ops.pack_weights(w, ops.tail_mode(cin), True, cout=cin, stream=stream)]
-    elif cout <= 4:                              # (<=4, zero padded to 8) -> 64: head-type kernel
-        imgs = [ops.pack_weights(w, CONV_8_64, True, cin=cout, stream=stream)]
-    else:
-        imgs = []
-        for ob in range(cin // 64):              # output blocks of the dgrad = forward input blocks
-            for ib in range(cout // 64):
-                imgs.append(ops.pack_weights(w, CONV_64_64, True, cout_off=ob * 64, cout=64, cin_off=ib * 64, cin=64,
-                                             stream=stream))
+    # forward channels cin -> cout; the data gradient maps cout -> cin with the transposed / mirrored bank
+    imgs = ops.build_wimgs(layer.p["weight"], layer.cout, layer.cin, transpose_flip=True, stream=stream)
     # keyed by the identity of the forward filter-bank list: invalidate() drops that list, so a stale entry can never
     # be returned after a weight update
     if layer._wimgs is not None:
@@ -230,35 +220,22 @@ def conv_backward(layer, ctx, gy_cl, grads, ws, key, need_dx=True, want_dw=True,
         return None
     imgs = _dgrad_wimgs(layer, stream)
     aff = inv_sigma_aff if inv_sigma_aff is not None else _unit_affine(stream)
-    sc, sh = aff.view((64,), F32, 0), _unit_affine(stream).view((64,), F32, 256)
-    if cin <= 8:
+    ss = (aff.view((64,), F32, 0), _unit_affine(stream).view((64,), F32, 256))     # (1 or 1/sigma, 0)
+    dt = gy_cl.dtype
+    if cin <= 8:       # head layer: 64 -> (<= 4) tail-type kernel, fp32 ncdhw result
         out = ws.get(key + ".dx3", (N, cin, T, H, W), F32)
-        return ops.conv_cl(ops.tail_mode(cin), gy_cl, imgs[0], sc, sh, ACT_NONE, OUT_F32_NCDHW, out=out, cout_real=cin,
-                           stream=stream)
-    dx = dx_out if dx_out is not None else ws.get(key + ".dx", (N, T, H, W, cin), BF16)
-    if mask_input and not _MASK_FUSION:     # default: data gradient, then the (bandwidth-bound) lrelu backward pass
-        raw = ws.get(key + ".dxraw", (N, T, H, W, cin), BF16)
+        return ops.conv3d_cl_any(gy_cl, w, None, ACT_NONE, 64, cin, out=out, wimgs=imgs, stream=stream, scale_shift=ss)
+    dx = dx_out if dx_out is not None else ws.get(key + ".dx", (N, T, H, W, cin), dt)
+    fuse_mask = mask_input and _MASK_FUSION and dt != F32
+    if mask_input and not fuse_mask:     # default: data gradient, then the (bandwidth-bound) lrelu backward pass
+        raw = ws.get(key + ".dxraw", (N, T, H, W, cin), dt)
         conv_backward(layer, ctx, gy_cl, grads, ws, key, True, False, inv_sigma_aff, stream, None, False, raw)
         return ops.lrelu_bwd_cl(raw, x_cl, out=dx, stream=stream)
-    act = ACT_LRELU_MASK if mask_input else ACT_NONE
-    mask = x_cl if mask_input else None
-    if cout <= 4:
-        return ops.conv_cl(CONV_8_64, gy_cl, imgs[0], sc, sh, act, OUT_BF16_CL, out=dx, out_pitch=cin,
-                           mask=mask, stream=stream)
-    k = 0
-    for ob in range(cin // 64):
-        partial = None
-        n_ib = cout // 64
-        for ib in range(n_ib):
-            if ib < n_ib - 1:
-                partial = ops.conv_cl(CONV_64_64, gy_cl, imgs[k], sc, sh, ACT_NONE, OUT_F32_RAW, in_coff=ib * 64,
-                                      out=ws.get(key + ".dxp", (N, T, H, W, 64), F32), stream=stream)
-            else:
-                ops.conv_cl(CONV_64_64, gy_cl, imgs[k], sc, sh, act, OUT_BF16_CL, out=dx, out_pitch=cin,
-                            out_coff=ob * 64, addend=partial, in_coff=ib * 64, mask=mask, mask_coff=ob * 64,
-                            stream=stream)
-            k += 1
-    return dx
+    act = ACT_LRELU_MASK if fuse_mask else ACT_NONE
+    mask = x_cl if fuse_mask else None
+    # tail layer (cout <= 4): gy is a narrow tensor -> head-type kernel; otherwise 64-channel blocks
+    return ops.conv3d_cl_any(gy_cl, w, None, act, cout if cout > 4 else gy_cl.shape[-1], cin, out=dx, wimgs=imgs,
+                             mask=mask, stream=stream, scale_shift=ss)
 
 
 def layer_backward(layer, ctx, ga_cl, grads, ws, key, need_dx=True, trainable=True, stream=None, ga_masked=False,
@@ -269,14 +246,14 @@ def layer_backward(layer, ctx, ga_cl, grads, ws, key, need_dx=True, trainable=Tr
     if layer.bn:
         dg = grads.of(layer.p["gamma"]) if trainable else None
         db = grads.of(layer.p["beta"]) if trainable else None
-        gy = ops.bn_bwd_cl(ga_cl, ctx["y"], ctx["saved"], layer.act, out=ws.get(key + ".gy", ga_cl.shape, BF16),
+        gy = ops.bn_bwd_cl(ga_cl, ctx["y"], ctx["saved"], layer.act, out=ws.get(key + ".gy", ga_cl.shape, ga_cl.dtype),
                            dgamma=dg, dbeta=db, accumulate=True, stream=stream)
         if trainable:
             ops.colsum_cl(gy, grads.of(layer.p["bias"]), accumulate=True, stream=stream)
         return conv_backward(layer, ctx, gy, grads, ws, key, need_dx, trainable, stream=stream)
     gz = ga_cl
     if layer.act == ACT_LRELU and not ga_masked:
-        gz = ops.lrelu_bwd_cl(ga_cl, ctx["a"], out=ws.get(key + ".gz", ga_cl.shape, BF16), stream=stream)
+        gz = ops.lrelu_bwd_cl(ga_cl, ctx["a"], out=ws.get(key + ".gz", ga_cl.shape, ga_cl.dtype), stream=stream)
     if trainable:
         if layer.cout == 64:
             ops.colsum_cl(gz, grads.of(layer.p["bias"]), accumulate=True, stream=stream)
@@ -327,7 +304,7 @@ def block_backward(block, ctxs, g_out, grads, ws, tag, need_dx, trainable=True, 
     g_pre = ops.tanh_bwd(g_out, o, gpre=ws.get(tag + ".gpre", o.shape, F32), stream=stream)
     if trainable:
         ops.channel_sum(g_pre, grads.of(tail.p["bias"]), accumulate=True, stream=stream)
-    gy = ops.pack_cl(g_pre, c_pitch=8, out=ws.get(tag + ".gtail", (N, T, H, W, 8), BF16), stream=stream)
+    gy = ops.pack_cl(g_pre, out=ws.get(tag + ".gtail", (N, T, H, W, ops.narrow_pitch()), ops.cl_dtype()), stream=stream)
     ga = conv_backward(tail, tail_ctx, gy, grads, ws, tag + ".t", True, trainable, stream=stream)
     dx = None
     for j in range(len(block.layers) - 2, -1, -1):
@@ -369,7 +346,7 @@ class GeneratorTrainer:
         size = net.stage_shape(idx + 1)
         N = x_prev.shape[0]
         up = self.ws.get("up%d" % idx, (N, opt.nc_im) + size, F32)
-        xin = self.ws.get("xin%d" % idx, (N,) + size + (8,), BF16)
+        xin = self.ws.get("xin%d" % idx, (N,) + size + (ops.narrow_pitch(),), ops.cl_dtype())
         add_noise = net.noise_at(idx + 1, is_random)
         noise_t, seed, amp = None, 0, 0.0
         if add_noise:
@@ -413,7 +390,7 @@ class GeneratorTrainer:
         if noise_init is None:
             enc = net.encode
             sn_tape_prepare(enc._features.layers, ws, "enc", stream)
-            x_cl = ops.pack_cl(video, c_pitch=8, stream=stream)
+            x_cl = ops.pack_cl(video, c_pitch=ops.narrow_pitch(), stream=stream)
             ectx = []
             h = x_cl
             xw = None
@@ -438,7 +415,7 @@ class GeneratorTrainer:
         else:
             z = noise_init
         N = z.shape[0]
-        z_cl = ops.pack_cl(z, out=ws.get("z", (N,) + tuple(z.shape[2:]) + (z.shape[1],), BF16), stream=stream)
+        z_cl = ops.pack_cl(z, out=ws.get("z", (N,) + tuple(z.shape[2:]) + (z.shape[1],), ops.cl_dtype()), stream=stream)
         vae_out, dctx = block_forward_train(net.decoder, z_cl, None, ws, "dec", stream, slab=slab, defer=defer,
                                             out=ws.get("vae_out", (N, opt.nc_im) + tuple(z.shape[2:]), F32))
         out.update(vae_out=vae_out, dec_ctx=dctx, mu=mu, logvar=logvar)
@@ -584,7 +561,8 @@ class DWithLoss:
     def _forward(self, x, tag, stream):
         D, ws = self._netD, self.ws
         N = x.shape[0]
-        x8 = ops.pack_cl(x, c_pitch=8, out=ws.get(tag + ".x8", (N,) + tuple(x.shape[2:]) + (8,), BF16), stream=stream)
+        x8 = ops.pack_cl(x, out=ws.get(tag + ".x8", (N,) + tuple(x.shape[2:]) + (ops.narrow_pitch(),), ops.cl_dtype()),
+                         stream=stream)
         xw = x8       # narrow operand of the head conv's weight gradient
         ctxs = []
         sn_tape_prepare(self._layers(), ws, tag, stream)
@@ -610,7 +588,7 @@ class DWithLoss:
         N, _, T, H, W = out.shape
         go = ops.fill(ws.get(tag + ".go", out.shape, F32), coef, stream)
         ops.channel_sum(go, g.of(D.tail.p["bias"]), accumulate=True, stream=stream)
-        gy = ops.pack_cl(go, c_pitch=8, out=ws.get(tag + ".gyt", (N, T, H, W, 8), BF16), stream=stream)
+        gy = ops.pack_cl(go, out=ws.get(tag + ".gyt", (N, T, H, W, ops.narrow_pitch()), ops.cl_dtype()), stream=stream)
         # every D layer is SN-conv + LeakyReLU (no BatchNorm): each data-gradient conv applies the LeakyReLU' of the
         # layer below in its epilogue, so no separate lrelu-backward pass runs
         ga = conv_backward(D.tail, ctxs[-1], gy, g, ws, tag + ".t", True, True, stream=stream, mask_input=True)
@@ -627,11 +605,12 @@ class DWithLoss:
         N, _, T, H, W = out.shape
         # (1) input gradient of sum D(xhat): deltas[j] = grad wrt the pre-activation of layer j
         ones = ops.fill(ws.get(tag + ".ones", out.shape, F32), 1.0, stream)
-        d_out = ops.pack_cl(ones, c_pitch=8, out=ws.get(tag + ".dout", (N, T, H, W, 8), BF16), stream=stream)
+        d_out = ops.pack_cl(ones, out=ws.get(tag + ".dout", (N, T, H, W, ops.narrow_pitch()), ops.cl_dtype()),
+                            stream=stream)
         # LeakyReLU' of the layer below is applied in each data-gradient conv's epilogue: its output IS delta[j-1]
         nl = len(layers)
         dshape = ctxs[-1]["x"].shape
-        deltas = [ws.get("%s.delta%d" % (tag, j), dshape, BF16) for j in range(nl)]
+        deltas = [ws.get("%s.delta%d" % (tag, j), dshape, ops.cl_dtype()) for j in range(nl)]
         conv_backward(D.tail, ctxs[-1], d_out, g, ws, tag + ".gt", True, False, stream=stream, mask_input=True,
                       dx_out=deltas[nl - 1])
         ga = None
@@ -643,7 +622,7 @@ class DWithLoss:
         Gx, gp = ops.gp_grad(grad_x, self.lambda_grad, Gout=ws.get(tag + ".G", grad_x.shape, F32),
                              gp=self.terms.slot(1.0), stream=stream)
         # (2) d GP / d W: push G forward through the SAME linear maps, masked by the LeakyReLU pattern of xhat
-        xi8 = ops.pack_cl(Gx, c_pitch=8, out=ws.get(tag + ".xi8", (N, T, H, W, 8), BF16), stream=stream)
+        xi8 = ops.pack_cl(Gx, out=ws.get(tag + ".xi8", (N, T, H, W, ops.narrow_pitch()), ops.cl_dtype()), stream=stream)
         xi_wide = xi8
         unit = _unit_affine(stream)
         zero_shift = unit.view((64,), F32, 256)
@@ -657,15 +636,15 @@ class DWithLoss:
             # eta = conv(xi; W/sigma) (no bias, no activation); xi_next = eta * LeakyReLU'(a_j)
             layer._prepare_wimgs(stream)
             so = _scale_only(ctxs[j]["aff"], zero_shift, ws, tag, j, stream)
-            if _MASK_FUSION:   # the mask of this layer's own LeakyReLU applied in the conv epilogue
+            if _MASK_FUSION and xi.dtype != F32:   # the mask of this layer's own LeakyReLU applied in the conv epilogue
                 xi = ops.conv3d_cl_any(xi, layer.p["weight"], so, ACT_LRELU_MASK, layer.cin, 64,
-                                       out=ws.get("%s.xi%d" % (tag, j), deltas[j].shape, BF16), wimgs=layer._wimgs,
+                                       out=ws.get("%s.xi%d" % (tag, j), deltas[j].shape, xi.dtype), wimgs=layer._wimgs,
                                        mask=ctxs[j]["a"], stream=stream)
             else:
                 eta = ops.conv3d_cl_any(xi, layer.p["weight"], so, ACT_NONE, layer.cin, 64,
-                                        out=ws.get("%s.eta%d" % (tag, j), deltas[j].shape, BF16), wimgs=layer._wimgs,
+                                        out=ws.get("%s.eta%d" % (tag, j), deltas[j].shape, xi.dtype), wimgs=layer._wimgs,
                                         stream=stream)
-                xi = ops.lrelu_bwd_cl(eta, ctxs[j]["a"], out=ws.get("%s.xi%d" % (tag, j), eta.shape, BF16),
+                xi = ops.lrelu_bwd_cl(eta, ctxs[j]["a"], out=ws.get("%s.xi%d" % (tag, j), eta.shape, eta.dtype),
                                       stream=stream)
         ops.conv_wgrad_cl(xi, d_out, g.of(D.tail.p["weight"]), co_n=1, ci_n=64, accumulate=True, stream=stream)
         return gp
