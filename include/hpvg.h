@@ -244,6 +244,11 @@ int hpvg_lrelu_bwd_cl_f32(const float* d_ga, const float* d_a, long long elems, 
 int hpvg_bn_bwd_cl_f32(const float* d_ga, const float* d_y, long long voxels, const float* d_saved, int act,
                        float* d_gy, float* d_dgamma, float* d_dbeta, int accumulate, void* stream);
 int hpvg_colsum_cl_f32(const float* d_g, long long voxels, float* d_out, int accumulate, void* stream);
+/* out[n,t,ho,wo,:] = act(in[n,t,h0+ho*sh,w0+wo*sw,:]) on bf16 channels-last tensors (C % 8 == 0; relu != 0 applies ReLU):
+ * crop / stride-2 sub-sampling / ReLU of the sinFID feature networks (src/sinFID/inception.py:66-72, c3d.py:63-66),
+ * whose convolutions run on the stride-1 zero-padded kernels above. NT = N*T planes of Hi x Wi voxels. */
+int hpvg_slice_act_cl(const void* d_in, int NT, int Hi, int Wi, int C, int Ho, int Wo, int h0, int w0, int sh, int sw,
+                      int relu, void* d_out, void* stream);
 /* gz = ga * LeakyReLU'(a), a = stored activation (bf16 cl, elems % 8 == 0) */
 int hpvg_lrelu_bwd_cl(const void* d_ga, const void* d_a, long long elems, void* d_gz, void* stream);
 /* BatchNorm(train)+act backward on (voxels, 64) bf16: d_saved = (scale, shift, mean, invstd) from the forward

@@ -519,6 +519,16 @@ int hpvg_colsum_cl_f32(const float* g, long long voxels, float* out, int accumul
   KL(hpvg::ew_colsum_cl_f32(g, voxels, g_sums, out, accumulate, S(st)), 2);
   return HPVG_OK;
 }
+int hpvg_slice_act_cl(const void* in, int NT, int Hi, int Wi, int C, int Ho, int Wo, int h0, int w0, int sh, int sw,
+                      int relu, void* out, void* st) {
+  if (NT <= 0 || Ho <= 0 || Wo <= 0) return HPVG_OK;
+  if (!in || !out || (C & 7) || sh < 1 || sw < 1 || h0 < 0 || w0 < 0 || h0 + (Ho - 1) * sh >= Hi ||
+      w0 + (Wo - 1) * sw >= Wi)
+    return fail(HPVG_E_ARG, "slice_act_cl: window outside the input, or channels not a multiple of 8");
+  KL(hpvg::ew_slice_act_cl(static_cast<const __nv_bfloat16*>(in), NT, Hi, Wi, C, Ho, Wo, h0, w0, sh, sw, relu,
+                           static_cast<__nv_bfloat16*>(out), S(st)), 1);
+  return HPVG_OK;
+}
 int hpvg_lrelu_bwd_cl(const void* ga, const void* a, long long elems, void* gz, void* st) {
   if (elems <= 0) return HPVG_OK;
   if (elems & 7) return fail(HPVG_E_ARG, "lrelu_bwd_cl: element count must be a multiple of 8");

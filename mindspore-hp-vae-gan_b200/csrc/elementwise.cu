@@ -2294,4 +2294,41 @@ cudaError_t ew_gp_grad(const float* g, int N, int C, long long sp, float lambda,
   return cudaSuccess;
 }
 
+// ----------------------------------------------------------------------------------------------- strided window (+ ReLU)
+// out[n][t][ho][wo][:] = act(in[n][t][h0 + ho*sh][w0 + wo*sw][:]) on bf16 channels-last tensors of C channels (C % 8 == 0):
+// the crop of a "valid" convolution computed as a zero-padded one, the stride-2 sub-sampling of a strided convolution
+// computed at stride 1, and the ReLU of the sinFID feature networks (src/sinFID/inception.py:66-72 Conv2d_1a/2a/2b are
+// conv(no pad / stride 2) + BN + ReLU; the conv kernels here are stride-1 "same" convolutions with LeakyReLU epilogues).
+__global__ void slice_act_cl_kernel(const uint4* __restrict__ in, int T, int Hi, int Wi, int Ho, int Wo, int h0, int w0,
+                                    int sh, int sw, int c8, int relu, long long total, uint4* __restrict__ out) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % c8);
+    long long v = i / c8;
+    const int wo = static_cast<int>(v % Wo); v /= Wo;
+    const int ho = static_cast<int>(v % Ho); v /= Ho;      // v = n*T + t
+    const long long src = ((v * Hi + (h0 + ho * sh)) * Wi + (w0 + wo * sw)) * c8 + g;
+    uint4 q = __ldg(in + src);
+    if (relu) {
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&q);
+      const __nv_bfloat162 z = __float2bfloat162_rn(0.f);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h2[e] = __hmax2(h2[e], z);
+    }
+    out[i] = q;
+  }
+}
+
+cudaError_t ew_slice_act_cl(const __nv_bfloat16* in, int NT, int Hi, int Wi, int C, int Ho, int Wo, int h0, int w0, int sh,
+                            int sw, int relu, __nv_bfloat16* out, cudaStream_t st) {
+  const int c8 = C / 8;
+  const long long total = static_cast<long long>(NT) * Ho * Wo * c8;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  slice_act_cl_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(reinterpret_cast<const uint4*>(in), NT, Hi, Wi, Ho, Wo,
+                                                                      h0, w0, sh, sw, c8, relu, total,
+                                                                      reinterpret_cast<uint4*>(out));
+  return cudaGetLastError();
+}
+
 }  // namespace hpvg

@@ -57,22 +57,40 @@ def _isz(t):
 
 # ------------------------------------------------------------------------------------------------ in-situ kernel timing
 _prof = None
+_flops = None
 
 
 def start_profile(mode):
-    """Record a CUDA-event pair around every conv launch of kernel variant `mode` (bench.py's roofline leg)."""
+    """Record a CUDA-event pair around every conv launch of kernel variant `mode` (bench.py's roofline leg).
+    mode="all": every convolution AND weight-gradient launch, tagged (see stop_profile)."""
     global _prof
     _prof = {"mode": mode, "items": []}
 
 
 def stop_profile():
-    """-> [(voxels, milliseconds)] for the launches recorded since start_profile()."""
+    """-> [(voxels, milliseconds)] for the launches recorded since start_profile(mode);
+    for mode="all": [(kind, mode, voxels, milliseconds)] with kind in {"conv", "wgrad"}."""
     global _prof
-    items, _prof = (_prof["items"] if _prof else []), None
+    items, tagged = (_prof["items"] if _prof else []), bool(_prof and _prof["mode"] == "all")
+    _prof = None
     out = []
-    for vox, e0, e1 in items:
+    for tag, e0, e1 in items:
         e1.sync()
-        out.append((vox, e0.elapsed_ms(e1)))
+        out.append(tag + (e0.elapsed_ms(e1),) if tagged else (tag, e0.elapsed_ms(e1)))
+    return out
+
+
+def start_flop_count():
+    """Count the ALGORITHMIC FLOP of every convolution / data-gradient / weight-gradient call from here on:
+    2 * taps * Cin * Cout per output voxel with the layer's real channel counts (3 for the clip-side convs, not the
+    padded 8 / 64) and taps = 27 (3-D) or 9 (2-D)."""
+    global _flops
+    _flops = {"conv": 0, "wgrad": 0, "conv_calls": 0, "wgrad_calls": 0}
+
+
+def stop_flop_count():
+    global _flops
+    out, _flops = _flops, None
     return out
 
 
@@ -197,7 +215,7 @@ def conv_cl(mode, x_cl, wimg, scale, shift, act=ACT_NONE, out_mode=None, out=Non
         else:
             out = Tensor((N, cout_real, T, H, W), F32)
     in_ptr = ctypes.c_void_p(x_cl.ptr + _isz(x_cl) * in_coff)
-    timed = _prof is not None and (_prof["mode"] == mode or _prof["mode"] is None)
+    timed = _prof is not None and (_prof["mode"] == mode or _prof["mode"] is None or _prof["mode"] == "all")
     if timed:
         e0, e1 = rt.Event(), rt.Event()
         e0.record(stream)
@@ -207,7 +225,11 @@ def conv_cl(mode, x_cl, wimg, scale, shift, act=ACT_NONE, out_mode=None, out=Non
                            0 if mask is None else mask.shape[-1], _s(stream)), "conv_cl")
     if timed:
         e1.record(stream)
-        _prof["items"].append((N * T * H * W, e0, e1) if _prof["mode"] is not None else ((mode, N * T * H * W), e0, e1))
+        if _prof["mode"] == "all":
+            _prof["items"].append((("conv", mode, N * T * H * W), e0, e1))
+        else:
+            _prof["items"].append((N * T * H * W, e0, e1) if _prof["mode"] is not None
+                                  else ((mode, N * T * H * W), e0, e1))
     return out
 
 
@@ -269,6 +291,10 @@ def conv3d_cl_any(x_cl, w, aff, act, cin, cout, out_mode=None, residual=None, ou
     Returns channels-last (cout 64/128, same dtype as x_cl) or fp32 ncdhw (cout <= 4)."""
     N, T, H, W, pitch = x_cl.shape
     tf = x_cl.dtype == F32
+    if _flops is not None and w is not None:
+        taps = 27 if (len(w.shape) == 5 and w.shape[2] == 3) else 9
+        _flops["conv"] += 2 * taps * w.shape[0] * w.shape[1] * N * T * H * W
+        _flops["conv_calls"] += 1
     if wimgs is None:
         wimgs = build_wimgs(w, cin, cout, transpose_flip, dtype=x_cl.dtype, stream=stream)
     if mask is not None and tf:
@@ -545,10 +571,34 @@ def conv_wgrad_cl(x_cl, gy_cl, dw, co_off=0, co_n=64, ci_off=0, ci_n=64, x_coff=
     kt = dw.shape[2] if len(dw.shape) == 5 else 1
     isz = _isz(x_cl)
     fn = lib.hpvg_conv_wgrad_cl_tf32 if x_cl.dtype == F32 else lib.hpvg_conv_wgrad_cl
+    if _flops is not None:
+        _flops["wgrad"] += 2 * (27 if kt == 3 else 9) * min(co_n, dw.shape[0]) * min(ci_n, dw.shape[1]) * N * T * H * W
+        _flops["wgrad_calls"] += 1
+    timed = _prof is not None and _prof["mode"] == "all"
+    if timed:
+        e0, e1 = rt.Event(), rt.Event()
+        e0.record(stream)
     check(fn(ctypes.c_void_p(x_cl.ptr + isz * x_coff), xp, ctypes.c_void_p(gy_cl.ptr + isz * gy_coff),
              gp, N, T, H, W, _p(dw), dw.shape[1], kt, co_off, co_n, ci_off, ci_n,
              1 if accumulate else 0, float(scale), _s(stream)), "conv_wgrad_cl")
+    if timed:
+        e1.record(stream)
+        _prof["items"].append((("wgrad", None, N * T * H * W), e0, e1))
     return dw
+
+
+def slice_act_cl(x_cl, h0=0, w0=0, sh=1, sw=1, out_hw=None, relu=False, out=None, stream=None):
+    """Strided window of a bf16 channels-last tensor (N,T,H,W,C), optionally with ReLU:
+    out[..., ho, wo, :] = act(x[..., h0 + ho*sh, w0 + wo*sw, :])."""
+    N, T, H, W, C = x_cl.shape
+    if x_cl.dtype != BF16:
+        raise HpvgError("slice_act_cl works on bf16 channels-last tensors")
+    Ho, Wo = out_hw if out_hw is not None else ((H - h0 + sh - 1) // sh, (W - w0 + sw - 1) // sw)
+    if out is None:
+        out = Tensor((N, T, Ho, Wo, C), BF16)
+    check(lib.hpvg_slice_act_cl(_p(x_cl), N * T, H, W, C, Ho, Wo, h0, w0, sh, sw, 1 if relu else 0, _p(out), _s(stream)),
+          "slice_act_cl")
+    return out
 
 
 def lrelu_bwd_cl(ga, a, out=None, stream=None):

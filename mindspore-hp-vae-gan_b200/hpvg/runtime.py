@@ -108,6 +108,12 @@ def _pool_free(ptr, size):
         _POOL.setdefault(size, []).append(ptr)
 
 
+def _sync_unless_capturing():
+    """cudaDeviceSynchronize is illegal while a stream is being captured into a graph."""
+    if _CAPTURE_HOLD[0] is None:
+        device_sync()
+
+
 def empty_cache():
     device_sync()
     for lst in _POOL.values():
@@ -149,21 +155,37 @@ class Tensor:
     def view(self, shape, dtype=None, byte_offset=0):
         return Tensor(shape, dtype or self.dtype, ptr=self.ptr + byte_offset, owner=self)
 
+    # Stream contract of the data-movement methods.  hpvg.Stream objects are cudaStreamNonBlocking: they do NOT order
+    # against the legacy NULL stream.  `stream=None` therefore means "synchronous with respect to the whole device":
+    # the call first waits for everything queued on every stream (so it sees the results of kernels a caller enqueued on
+    # its own stream — e.g. checkpoint.state_dict() after driver.train_scale(stream=st)) and returns only when its own
+    # copy has completed (so kernels enqueued afterwards on any stream see the data).  With an explicit stream the call
+    # is ordered on that stream only.
     def zero_(self, stream=None):
+        if stream is None:
+            _sync_unless_capturing()
         check(lib.hpvg_memset(self.ptr, 0, self.nbytes, _s(stream)), "memset")
+        if stream is None:
+            _sync_unless_capturing()
         return self
 
     def copy_from_host(self, arr, stream=None):
         a = np.ascontiguousarray(arr, dtype=_NP[self.dtype])
         if a.nbytes != self.nbytes:
             raise HpvgError("copy_from_host: size mismatch %d vs %d" % (a.nbytes, self.nbytes))
+        if stream is None:
+            _sync_unless_capturing()
         check(lib.hpvg_h2d(self.ptr, a.ctypes.data, self.nbytes, _s(stream)), "h2d")
         if stream is not None:
             stream.sync()   # pageable source must stay alive until the copy is done
+        else:
+            _sync_unless_capturing()
         return self
 
     def numpy(self, stream=None):
         out = np.empty(self.shape, dtype=_NP[self.dtype])
+        if stream is None:
+            device_sync()   # producers may sit on any (non-blocking) stream
         check(lib.hpvg_d2h(out.ctypes.data, self.ptr, self.nbytes, _s(stream)), "d2h")
         if stream is not None:
             stream.sync()
@@ -174,7 +196,11 @@ class Tensor:
     def copy_(self, other, stream=None):
         if other.nbytes != self.nbytes:
             raise HpvgError("copy_: size mismatch")
+        if stream is None:
+            _sync_unless_capturing()
         check(lib.hpvg_d2d(self.ptr, other.ptr, self.nbytes, _s(stream)), "d2d")
+        if stream is None:
+            _sync_unless_capturing()
         return self
 
 

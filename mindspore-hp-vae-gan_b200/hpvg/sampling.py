@@ -3,6 +3,8 @@
 One "sampled clip" = one random-mode generator forward from `Z_init_size` noise through the whole pyramid
 (SURVEY §8 a16).  Samples are independent in eval mode (BatchNorm uses moving statistics), so sample i goes to rank
 `i mod world` and each rank batches its local samples; no collective is needed during generation."""
+import os
+
 import numpy as np
 
 from . import ops
@@ -26,24 +28,159 @@ def local_chunks(num_samples, batch, rank, world):
     return chunks
 
 
-def host_noise_for_sample(seed, index, shape):
-    """Counter-based host draw: z of sample `index` does not depend on the number of ranks."""
-    return np.random.default_rng([int(seed), int(index)]).standard_normal(shape).astype(np.float32)
+def host_noise_for_sample(seed, index, shape, out=None):
+    """Counter-based host draw (numpy Philox-free PCG64 keyed by [seed, sample index], float32 ziggurat): z of sample
+    `index` does not depend on the number of ranks, the batch size or the drawing thread.  The reference draws z on the
+    host with numpy too (eval_video.py:67 -> utils.generate_noise_ref), from the global generator."""
+    g = np.random.default_rng([int(seed), int(index)])
+    if out is None:
+        return g.standard_normal(shape, dtype=np.float32)
+    g.standard_normal(dtype=np.float32, out=out)
+    return out
 
 
-def generate(netG, noise_amps, num_samples, rank=0, world=1, batch=8, seed=0, stream=None, keep=True):
-    """Returns (indices, clips) for this rank: clips is a float32 array (n_local, 3, T, H, W) when keep=True."""
-    opt = netG.opt
-    shp = z_init_size(opt, 1)[1:]
-    idxs, outs = [], []
-    for chunk in local_chunks(num_samples, batch, rank, world):
-        z = np.stack([host_noise_for_sample(seed, i, shp) for i in chunk])
-        tz = from_numpy(z, stream=stream)
-        netG.sample_counter = chunk[0]       # device Philox noise is keyed by (seed, global sample index, element)
-        x, _ = netG(tz, noise_amps, noise_init=tz, isRandom=True, stream=stream)
-        idxs += chunk
-        if keep:
-            outs.append(x.numpy(stream))
+def fold_seed(netG, seed):
+    """The device Philox key of the refinement noise follows `seed` (opt.manualSeed) as well: different seeds must not
+    reuse the same refinement noise per sample index."""
+    base = getattr(netG, "_noise_seed_base", None)
+    if base is None:
+        base = netG._noise_seed_base = int(netG.noise_seed)
+    x = (int(seed) + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF          # splitmix64 finaliser
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    netG.noise_seed = (base ^ x ^ (x >> 31)) & 0x7FFFFFFFFFFFFFFF
+
+
+class SamplePipeline:
+    """eval_video.py:53-82 as a stream: per chunk of `batch` samples
+         host z draw (worker threads, straight into pinned memory)  ->  H2D on a copy stream
+         ->  generator forward on `stream`  ->  D2H of the clips on a second copy stream into pinned memory  ->  sink.
+    `depth` z buffers and two clip buffers are in flight, so the draw / copies of chunk i+1 overlap the generation of
+    chunk i.  noise="device": z is drawn by the device Philox generator keyed by (seed, sample index) instead — no host
+    draw, no H2D (the clips differ from the host-noise ones; stated wherever it is used)."""
+
+    def __init__(self, netG, noise_amps, batch, seed=0, stream=None, threads=None, noise="host", depth=3):
+        from concurrent.futures import ThreadPoolExecutor
+        from .runtime import Event, PinnedBuffer, Stream
+        if noise not in ("host", "device"):
+            raise ValueError("noise must be 'host' or 'device'")
+        self.net, self.amps, self.batch, self.seed, self.noise = netG, list(noise_amps), int(batch), int(seed), noise
+        self.opt = netG.opt
+        self.st = stream or Stream()
+        self.cp_in, self.cp_out = Stream(), Stream()
+        self.zshape = z_init_size(self.opt, self.batch)
+        self.depth = int(depth)
+        zbytes = int(np.prod(self.zshape)) * 4
+        self.z_dev = [Tensor(self.zshape, F32) for _ in range(self.depth)]
+        self.z_host = [PinnedBuffer(zbytes) for _ in range(self.depth)] if noise == "host" else None
+        self.gen_done = [None] * self.depth          # device z buffer k may be overwritten once its consumer has run
+        self.h2d_done = [None] * self.depth          # pinned z buffer k may be redrawn once its upload has completed
+        self.out_host, self.d2h_done = [None, None], [None, None]
+        self._Event, self._Pinned = Event, PinnedBuffer
+        self.pool = ThreadPoolExecutor(max_workers=threads or max(1, min(8, (os.cpu_count() or 2) // 2))) \
+            if noise == "host" else None
+        self.h2d_bytes = self.d2h_bytes = 0
+        fold_seed(netG, seed)
+
+    def _draw_async(self, k, chunk):
+        """Fill pinned z buffer k with the draws of `chunk` on the worker threads -> list of futures."""
+        arr = self.z_host[k].as_array(self.zshape)
+        shp = self.zshape[1:]
+        return [self.pool.submit(host_noise_for_sample, self.seed, i, shp, arr[j]) for j, i in enumerate(chunk)]
+
+    def run(self, chunks, sink=None):
+        """chunks: list of lists of global sample indices (each <= batch long).  sink(chunk, clips_view) is called with a
+        numpy VIEW of the pinned clip buffer (valid until the next-but-one chunk); returns the number of clips."""
+        Event = self._Event
+        st, n_done = self.st, 0
+        pending = []                                  # (chunk, out slot, d2h event)
+        futs = {}
+        if self.noise == "host":
+            for k in range(min(self.depth - 1, len(chunks))):      # prefetch
+                if self.h2d_done[k % self.depth] is not None:
+                    self.h2d_done[k % self.depth].sync()
+                futs[k] = self._draw_async(k % self.depth, chunks[k])
+        for c, chunk in enumerate(chunks):
+            k, o = c % self.depth, c & 1
+            n = len(chunk)
+            zd = self.z_dev[k] if n == self.batch else self.z_dev[k].view((n,) + self.zshape[1:], F32, 0)
+            if self.noise == "host":
+                for f in futs.pop(c):
+                    f.result()
+                nb = n * int(np.prod(self.zshape[1:])) * 4
+                if self.gen_done[k] is not None:
+                    self.cp_in.wait_event(self.gen_done[k])        # device-side: the previous reader of z_dev[k] is done
+                check_h2d(zd.ptr, self.z_host[k].ptr, nb, self.cp_in)
+                self.h2d_bytes += nb
+                ev = Event(); ev.record(self.cp_in)
+                self.h2d_done[k] = ev
+                st.wait_event(ev)
+                nxt = c + self.depth - 1
+                if nxt < len(chunks):                 # next draw goes into the pinned buffer uploaded longest ago
+                    kk = nxt % self.depth
+                    if self.h2d_done[kk] is not None:
+                        self.h2d_done[kk].sync()
+                    futs[nxt] = self._draw_async(kk, chunks[nxt])
+            else:
+                per = int(np.prod(self.zshape[1:]))
+                for j, i in enumerate(chunk):
+                    ops.randn((per,), self.seed ^ 0x5A17, offset=i, out=zd.view((per,), F32, j * per * 4), stream=st)
+            if self.d2h_done[o] is not None:
+                st.wait_event(self.d2h_done[o])       # clip tensor / pinned buffer o is free again
+            self.net.sample_counter = chunk[0]        # device Philox noise keyed by (seed, GLOBAL sample index, element)
+            self.net.out_slot = o
+            x, _ = self.net(zd, self.amps, noise_init=zd, isRandom=True, stream=st)
+            ev = Event(); ev.record(st); self.gen_done[k] = ev
+            if self.out_host[o] is None or self.out_host[o].nbytes < x.nbytes:
+                self.out_host[o] = self._Pinned(int(np.prod((self.batch,) + tuple(x.shape[1:]))) * 4)
+            self.cp_out.wait_event(ev)
+            check_d2h(self.out_host[o].ptr, x.ptr, x.nbytes, self.cp_out)
+            self.d2h_bytes += x.nbytes
+            ev2 = Event(); ev2.record(self.cp_out); self.d2h_done[o] = ev2
+            pending.append((chunk, o, ev2, tuple(x.shape)))
+            while len(pending) > 1:                   # hand the previous chunk to the sink while this one runs
+                n_done += self._deliver(pending.pop(0), sink)
+        while pending:
+            n_done += self._deliver(pending.pop(0), sink)
+        return n_done
+
+    def _deliver(self, item, sink):
+        chunk, o, ev, shape = item
+        ev.sync()
+        if sink is not None:
+            sink(chunk, self.out_host[o].as_array(shape))
+        return len(chunk)
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.shutdown(wait=True)
+            self.pool = None
+        self.net.out_slot = 0
+
+
+def check_h2d(dst, src, nbytes, stream):
+    from ._lib import check, lib
+    check(lib.hpvg_h2d(dst, src, nbytes, stream.handle), "h2d")
+
+
+def check_d2h(dst, src, nbytes, stream):
+    from ._lib import check, lib
+    check(lib.hpvg_d2h(dst, src, nbytes, stream.handle), "d2h")
+
+
+def generate(netG, noise_amps, num_samples, rank=0, world=1, batch=8, seed=0, stream=None, keep=True, noise="host",
+             threads=None):
+    """Returns (indices, clips) for this rank: clips is a float32 array (n_local, 3, T, H, W) when keep=True.
+    The loop runs as a SamplePipeline (host draw / copies overlapped with the generation)."""
+    chunks = local_chunks(num_samples, batch, rank, world)
+    idxs = [i for c in chunks for i in c]
+    outs = []
+    pipe = SamplePipeline(netG, noise_amps, batch, seed=seed, stream=stream, threads=threads, noise=noise)
+    try:
+        pipe.run(chunks, (lambda chunk, clips: outs.append(np.array(clips))) if keep else None)
+        pipe.st.sync()
+    finally:
+        pipe.close()
     return idxs, (np.concatenate(outs) if outs and keep else None)
 
 
@@ -57,6 +194,7 @@ def generate_moments(netG, noise_amps, num_samples, features, comm=None, batch=8
     comm = comm or SingleProcess()
     opt = netG.opt
     shp = z_init_size(opt, 1)[1:]
+    fold_seed(netG, seed)
     idx = shard_rows(num_samples, batch, comm.rank, comm.world)
     rows = Tensor((len(idx), fid.MOMENT_FLOATS), F32).zero_(stream)
     clips = []

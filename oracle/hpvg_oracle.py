@@ -87,6 +87,8 @@ def scale_shape(opt, index):
     """(T, H, W) of pyramid level `index`: images.py:96-103 (3D) — [td, int(s*ar), s]."""
     s = get_scales_by_index(index, opt.scale_factor, opt.stop_scale, opt.img_size)
     _, td, _ = get_fps_td_by_index(index, opt.stop_scale_time, opt.sampling_rates, opt.org_fps, opt.fps_lcm)
+    # synthetic benchmark clips may pin the time depth of a level (BASELINE.json config 3: 16 frames at the finest scale)
+    td = getattr(opt, "td_override", {}).get(index, td)
     return (td, int(s * opt.ar), s)
 
 
@@ -632,3 +634,69 @@ def g_loss(real, real_zero, noise_init, noise_amps, pg, pd, opt, is_vae, z_pred=
                                 noises=noises, nd=nd)
     fake = fake.detach()                                                          # Q1 (losses.py:94)
     return total + (-discriminator(fake, pd, opt).mean() * opt.disc_loss_weight)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# sinFID                                                                    (src/sinFID/c3d.py, inception.py, fid_score.py)
+# ----------------------------------------------------------------------------------------------------------------
+def c3d_block0(x, w, b, normalize_input=False):
+    """C3D block 0 (c3d.py:62-66): conv1 = Conv3d(3, 64, 3x3x3, pad 1, bias), no activation inside the block;
+    c3d.py:129-130: inputs in (0, 1) are scaled to (-1, 1) first when normalize_input."""
+    x = torch.as_tensor(x)
+    if normalize_input:
+        x = 2 * x - 1
+    return F.conv3d(x, torch.as_tensor(w), torch.as_tensor(b), padding=1)
+
+
+INCEPTION_BN_EPS = 1e-3     # BasicConv2d's BatchNorm2d(eps=0.001) in InceptionV3
+
+
+def inception_block0(x, params, normalize_input=False):
+    """InceptionV3 block 0 (inception.py:66-72): Conv2d_1a_3x3 (3->32, k3, stride 2, no pad), Conv2d_2a_3x3 (32->32, k3,
+    no pad), Conv2d_2b_3x3 (32->64, k3, pad 1); each conv(no bias) + BatchNorm(eval, eps 1e-3) + ReLU."""
+    x = torch.as_tensor(x)
+    if normalize_input:
+        x = 2 * x - 1
+    for name, stride, pad in (("Conv2d_1a", 2, 0), ("Conv2d_2a", 1, 0), ("Conv2d_2b", 1, 1)):
+        x = F.conv2d(x, torch.as_tensor(params[name + ".conv.weight"]), None, stride=stride, padding=pad)
+        g, b = torch.as_tensor(params[name + ".bn.gamma"]), torch.as_tensor(params[name + ".bn.beta"])
+        m, v = torch.as_tensor(params[name + ".bn.moving_mean"]), torch.as_tensor(params[name + ".bn.moving_variance"])
+        x = (x - m.reshape(1, -1, 1, 1)) / torch.sqrt(v.reshape(1, -1, 1, 1) + INCEPTION_BN_EPS) * g.reshape(1, -1, 1, 1) \
+            + b.reshape(1, -1, 1, 1)
+        x = F.relu(x)
+    return x
+
+
+def activation_statistics(feat):
+    """fid_score.py:92-93,160-178 for ONE sample: positions are the observations — pred.transpose(0,2,3,1).reshape(-1, C),
+    mu = mean, sigma = np.cov(rowvar=False).  feat: (1, C, [T,] H, W)."""
+    f = np.asarray(feat, np.float64)
+    act = np.moveaxis(f[0], 0, -1).reshape(-1, f.shape[1])
+    return act.mean(axis=0), np.cov(act, rowvar=False)
+
+
+def frechet_distance(mu1, sigma1, mu2, sigma2, eps=1e-6):
+    """fid_score.py:105-159 (Sutherland's stable form)."""
+    from scipy import linalg
+    diff = mu1 - mu2
+    try:
+        covmean, _ = linalg.sqrtm(sigma1.dot(sigma2), disp=False)
+    except TypeError:       # scipy >= 1.16 dropped `disp` (and the error-estimate return value)
+        covmean = linalg.sqrtm(sigma1.dot(sigma2))
+    if not np.isfinite(covmean).all():
+        offset = np.eye(sigma1.shape[0]) * eps
+        covmean = linalg.sqrtm((sigma1 + offset).dot(sigma2 + offset))
+    if np.iscomplexobj(covmean):
+        covmean = covmean.real
+    return float(diff.dot(diff) + np.trace(sigma1) + np.trace(sigma2) - 2 * np.trace(covmean))
+
+
+def svfid(real, fakes, feature_fn):
+    """calculate_SVFID / calculate_SIFID (fid_score.py:181-242): per fake sample the Fréchet distance between its
+    position statistics and the real sample's, averaged in float32.  real: (1,3,...); fakes: (n,3,...)."""
+    m1, s1 = activation_statistics(feature_fn(real))
+    vals = []
+    for i in range(len(fakes)):
+        m2, s2 = activation_statistics(feature_fn(fakes[i:i + 1]))
+        vals.append(frechet_distance(m1, s1, m2, s2))
+    return float(np.asarray(vals, np.float32).mean()), vals

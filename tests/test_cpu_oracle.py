@@ -264,3 +264,51 @@ def test_frames_to_clip_argument_errors():
     assert hpvg.lib.hpvg_frames_to_clip(buf, 3, 2, 2, 0, 1, 2, 2, 2, 2, 0, out, None) == -2
     assert b"past the decoded frames" in hpvg.lib.hpvg_last_error()
     assert hpvg.lib.hpvg_frames_to_clip(buf, 3, 2, 2, 0, 0, 0, 2, 2, 2, 0, out, None) == -2      # every == 0
+
+
+def test_sinfid_restatement_shapes_and_identities():
+    """src/sinFID: block-0 shapes (c3d.py:62-66 keeps the clip's size at 64 channels; inception.py:66-72 halves and crops),
+    position statistics (fid_score.py:160-178) and the Fréchet distance (fid_score.py:105-159)."""
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((1, 3, 4, 17, 21)).astype(np.float32)
+    w, b = rng.standard_normal((64, 3, 3, 3, 3)).astype(np.float32) * 0.1, rng.standard_normal(64).astype(np.float32)
+    f = orc.c3d_block0(x, w, b)
+    assert tuple(f.shape) == (1, 64, 4, 17, 21)
+    assert np.allclose(orc.c3d_block0((x + 1) / 2, w, b, normalize_input=True).numpy(), f.numpy(), atol=1e-4)
+    params = {}
+    for name, cin, cout in (("Conv2d_1a", 3, 32), ("Conv2d_2a", 32, 32), ("Conv2d_2b", 32, 64)):
+        params[name + ".conv.weight"] = rng.standard_normal((cout, cin, 3, 3)).astype(np.float32) * 0.1
+        params[name + ".bn.gamma"] = np.ones(cout, np.float32)
+        params[name + ".bn.beta"] = np.zeros(cout, np.float32)
+        params[name + ".bn.moving_mean"] = np.zeros(cout, np.float32)
+        params[name + ".bn.moving_variance"] = np.ones(cout, np.float32)
+    g = orc.inception_block0(rng.standard_normal((2, 3, 65, 81)).astype(np.float32), params)
+    assert tuple(g.shape) == (2, 64, (65 - 3) // 2 + 1 - 2, (81 - 3) // 2 + 1 - 2) and float(g.min()) >= 0.0
+    mu, sigma = orc.activation_statistics(f.numpy())
+    assert mu.shape == (64,) and sigma.shape == (64, 64)
+    act = f.numpy()[0].reshape(64, -1).T
+    assert np.allclose(mu, act.mean(0)) and np.allclose(sigma, np.cov(act, rowvar=False))
+    assert abs(orc.frechet_distance(mu, sigma, mu, sigma)) < 1e-3
+    # 1-D Gaussians: d^2 = (m1-m2)^2 + (s1-s2)^2
+    d = orc.frechet_distance(np.array([1.0]), np.array([[4.0]]), np.array([3.0]), np.array([[9.0]]))
+    assert abs(d - (4.0 + 1.0)) < 1e-9
+    v, per = orc.svfid(x, np.concatenate([x, x * 0.5]), lambda c: orc.c3d_block0(c, w, b).numpy())
+    assert abs(per[0]) < 1e-3 and per[1] > 0 and abs(v - np.mean(per)) < 1e-6
+
+
+def test_host_noise_is_counter_based_and_seed_folding_changes_the_device_key():
+    from hpvg import sampling
+    a = sampling.host_noise_for_sample(3, 17, (4, 5))
+    buf = np.empty((4, 5), np.float32)
+    assert sampling.host_noise_for_sample(3, 17, (4, 5), out=buf) is buf and np.array_equal(a, buf)
+    assert a.dtype == np.float32 and not np.array_equal(a, sampling.host_noise_for_sample(4, 17, (4, 5)))
+
+    class Net:
+        noise_seed = 0x9E3779B97F4A7C15
+    n = Net()
+    sampling.fold_seed(n, 1)
+    k1 = n.noise_seed
+    sampling.fold_seed(n, 2)
+    k2 = n.noise_seed
+    sampling.fold_seed(n, 1)
+    assert k1 != k2 and n.noise_seed == k1 and 0 <= k1 < 2 ** 63
