@@ -91,18 +91,28 @@ def _pool_alloc(nbytes):
     lst = _POOL.get(size)
     if lst:
         _POOL_STATS["reuse"] += 1
-        return lst.pop(), size
-    h = ctypes.c_void_p()
-    check(lib.hpvg_malloc(ctypes.byref(h), size), "malloc")
-    _POOL_STATS["malloc"] += 1
-    return h.value, size
+        ptr = lst.pop()
+    else:
+        h = ctypes.c_void_p()
+        check(lib.hpvg_malloc(ctypes.byref(h), size), "malloc")
+        _POOL_STATS["malloc"] += 1
+        ptr = h.value
+    if _CAPTURE_HOLD[0] is not None:
+        # allocated while a graph is being captured: the address is baked into captured kernel arguments, so the block
+        # belongs to that graph until it is destroyed — whenever its Python owner lets go of it
+        _GRAPH_OWNED[ptr] = _CAPTURE_HOLD[0]
+    return ptr, size
 
 
 _CAPTURE_HOLD = [None]   # while a CUDA graph is being captured: blocks freed meanwhile stay reserved for the graph
+_GRAPH_OWNED = {}        # ptr -> held-list of the live graph whose capture allocated it
 
 
 def _pool_free(ptr, size):
-    if _CAPTURE_HOLD[0] is not None:
+    held = _GRAPH_OWNED.get(ptr)
+    if held is not None:
+        held.append((ptr, size))         # stays reserved for its graph (returned to the pool by Graph.destroy)
+    elif _CAPTURE_HOLD[0] is not None:
         _CAPTURE_HOLD[0].append((ptr, size))
     else:
         _POOL.setdefault(size, []).append(ptr)
@@ -236,7 +246,10 @@ class Graph:
             self.stream.sync()
             lib.hpvg_graph_destroy(self.exec)
             self.exec = None
-        for ptr, size in self._held:
+        held = self._held
+        for ptr in [q for q, h in _GRAPH_OWNED.items() if h is held]:
+            del _GRAPH_OWNED[ptr]        # blocks still alive simply return to the pool when their owner frees them
+        for ptr, size in held:
             _POOL.setdefault(size, []).append(ptr)
         self._held = []
 

@@ -442,11 +442,22 @@ class GWithLoss:
         self.grads = GradBook()
         self.terms = LossTerms()
 
-    def recon_forward_args(self, isVAE, trainable_body):
+    def recon_forward_args(self, isVAE, trainable_body, train_codec=False):
         """Keyword arguments of the reconstruction forward that grad() runs (for callers that run it themselves)."""
+        _, enc_bw, save_from = self._plan(isVAE, trainable_body, train_codec)
+        return dict(is_random=False, save_from=save_from, save_encoder=enc_bw)
+
+    def _plan(self, isVAE, trainable_body, train_codec):
+        """Which parts of the tape the backward walks.  GAN phase (losses.py:93-103): the reconstruction loss reaches every
+        stage of body[-train_depth:] (train_video.py:78-86) — the chain runs down to the lowest trainable stage and stops
+        only at the reference's stop_gradient (networks_3d.py:437-438); with --train-all and fewer stages than
+        train_depth (train_video.py:95-103) encode / decoder are optimised too, and the chain continues into the decoder
+        (and, with is_training=True, through the reparameterised z into the encoder)."""
         nb = len(self._netG.body)
-        save_from = 0 if isVAE else (min(trainable_body) if trainable_body else nb)
-        return dict(is_random=False, save_from=save_from, save_encoder=isVAE)
+        codec_bw = bool(isVAE or train_codec)
+        enc_bw = bool(isVAE or (train_codec and self._netG.is_training))
+        save_from = 0 if codec_bw else (min(trainable_body) if trainable_body else nb)
+        return codec_bw, enc_bw, save_from
 
     def grad(self, real, real_zero, noise_init, noise_amps, isVAE=False, trainable_body=(), train_codec=False,
              noises=None, z_pred=None, eps=None, stream=None, finish=True, recon_fw=None, random_x=None,
@@ -462,13 +473,10 @@ class GWithLoss:
         g = self.grads
         g.zero(stream)
         nb = len(net.body)
-        if isVAE:
-            save_from = 0
-        else:
-            save_from = min(trainable_body) if trainable_body else nb
+        codec_bw, enc_bw, save_from = self._plan(isVAE, trainable_body, train_codec)
         if recon_fw is None:
             fw = tr.forward(real_zero, noise_amps, is_random=False, z_pred=z_pred, eps=eps, save_from=save_from,
-                            save_encoder=isVAE, stream=stream)
+                            save_encoder=enc_bw, stream=stream)
         else:
             fw = recon_fw
             if wait_recon is not None:
@@ -488,7 +496,7 @@ class GWithLoss:
         lowest = save_from
         for idx in range(nb - 1, lowest - 1, -1):
             stop_here = (opt.vae_levels == idx + 1 and not opt.train_all)      # stop_gradient on the stage input
-            need_prev = isVAE and not stop_here
+            need_prev = (not stop_here) and (codec_bw or idx > lowest)
             g_pre, dx = block_backward(net.body[idx], fw["body_ctx"][idx], g_cur, g, ws, "s%d" % idx,
                                        need_dx=need_prev, trainable=idx in trainable_body, stream=stream)
             if not need_prev:
@@ -498,6 +506,7 @@ class GWithLoss:
             ops.axpby(1.0, g_pre, 1.0, dx, stream=stream)
             prev_shape = (vae_out if idx == 0 else fw["ups"][idx - 1]).shape
             g_cur = ops.resize3d_bwd(dx, prev_shape[2:], out=ws.get("g_prev%d" % idx, prev_shape, F32), stream=stream)
+        g_z_cl = None
         if isVAE:
             # ---- decoder: grad = chain from the stages + rec_weight*MSE(vae_out, real_zero)
             if nb == 0 or g_cur is None:
@@ -510,10 +519,17 @@ class GWithLoss:
                                    stream=stream)
             _, g_z_cl = block_backward(net.decoder, fw["dec_ctx"], g_v, g, ws, "dec", need_dx=net.is_training,
                                        trainable=train_codec, stream=stream)
-            # ---- encoder: the KL term always reaches it; the reconstruction terms only through the reparameterised z,
-            # i.e. only with is_training=True (Q2: the reference's drivers leave it False, then z is pure noise)
+        elif codec_bw and (g_cur is not None or nb == 0):
+            # ---- GAN phase with encode / decoder in the optimiser (--train-all, train_video.py:95-103): only the
+            # reconstruction term rec_weight*MSE(x, real) reaches the decoder, through the whole refinement chain
+            _, g_z_cl = block_backward(net.decoder, fw["dec_ctx"], g_cur if nb else g_x, g, ws, "dec",
+                                       need_dx=net.is_training, trainable=True, stream=stream)
+        if enc_bw and (isVAE or g_z_cl is not None):
+            # ---- encoder: the KL term (VAE phase) always reaches it; the reconstruction terms only through the
+            # reparameterised z, i.e. only with is_training=True (Q2: the reference's drivers leave it False, then z is
+            # pure noise)
             mu, lv = fw["mu"], fw["logvar"]
-            gmu, glv = ops.kl_grad(mu, lv, self.kl_weight / mu.size, stream=stream)
+            gmu, glv = ops.kl_grad(mu, lv, (self.kl_weight / mu.size) if isVAE else 0.0, stream=stream)
             if net.is_training:
                 g_z = ops.unpack_cl(g_z_cl, stream=stream)
                 ops.reparam_bwd(g_z, fw["eps"], lv, gmu, glv, stream=stream)
@@ -525,7 +541,7 @@ class GWithLoss:
             for i in range(len(enc._features.layers) - 1, -1, -1):
                 ga = layer_backward(enc._features.layers[i], fw["enc_ctx"][i], ga, g, ws, "enc.%d" % i, i > 0,
                                     train_codec, stream)
-        else:
+        if not isVAE:
             # ---- adversarial term: value only, no gradient reaches G (Q1, losses.py:93-98)
             if random_x is None:
                 random_x = tr.forward(None, noise_amps, noise_init=noise_init, is_random=True, noises=noises,
@@ -801,7 +817,8 @@ class GraphedIteration:
                 s.wait_event(fork)
         fake = d_loss.trainer.forward(None, self.amps, noise_init=self.noise_init, is_random=True, stream=s1,
                                       defer_bn=True)
-        rkw = g_loss.recon_forward_args(self.g_kwargs.get("isVAE", False), self.g_kwargs.get("trainable_body", ()))
+        rkw = g_loss.recon_forward_args(self.g_kwargs.get("isVAE", False), self.g_kwargs.get("trainable_body", ()),
+                                        self.g_kwargs.get("train_codec", False))
         recon = g_loss.trainer.forward(self.real_zero, self.amps, stream=s2, defer_bn=True, **rkw)
         rand = self.trainer3.forward(None, self.amps, noise_init=self.noise_init, is_random=True, stream=s3,
                                      defer_bn=True)

@@ -88,8 +88,10 @@ def test_frechet_distance_known_answers():
     assert np.allclose(mu2, f.mean(0)) and np.allclose(sig2, np.cov(f, rowvar=False))
 
 
-def test_pytorch_key_map_produces_reference_names():
-    """src/tools/pt2ms.py:129-188 documents the parameter-name contract; our map must land on the same names."""
+def test_pytorch_key_map_and_reference_name_translation():
+    """src/tools/pt2ms.py:129-188: our map lands on THIS PACKAGE's positional names; the reference's MindSpore names differ
+    for generator stages >= 1 (`body.0.0.N.`, pt2ms.py:156-157) and discriminator blocks >= 1 (`body.0.j.`, :112-113) and
+    are translated both ways."""
     from hpvg import checkpoint as ck
     z = np.zeros
     state = {"encode.features.conv_block_0.conv.weight_orig": z((64, 3, 3, 3, 3)),
@@ -113,6 +115,24 @@ def test_pytorch_key_map_produces_reference_names():
     assert got["encode._features.0.0.weight_u"].shape == (64, 1)
     got2 = ck.p2m_HPVAEGAN_2d(state)
     assert "decoder.0.1.moving_mean" in got2 and "decoder.4.1.gamma" in got2
+    # the names pt2ms.py itself produces for the same PyTorch keys (its string substitutions restated literally)
+    ref_names = ck.to_reference_names(got)
+    assert "body.0.0.2.1.0.bias" in ref_names and "body.0.0.2.0.1.bn2d.moving_variance" in ref_names \
+        and "body.0.0.2.6.bias" in ref_names and "decoder.0.0.weight" in ref_names
+    assert ck.from_reference_names(ref_names).keys() == got.keys()
+    assert ck.from_reference_names(got).keys() == got.keys()              # idempotent on our names
+    # stage 0 keys are identical in both namings and must not be mistaken for a later stage
+    s0 = {"body.0.0.0.weight": 1, "body.0.0.1.bn2d.gamma": 2, "body.0.6.weight": 3, "body.0.0.1.0.0.weight": 4}
+    assert ck.from_reference_names(s0) == {"body.0.0.0.weight": 1, "body.0.0.1.bn2d.gamma": 2, "body.0.6.weight": 3,
+                                           "body.1.0.0.weight": 4}
+    # discriminator (pt2ms.py:105-126)
+    dstate = {"head.conv.weight_orig": z((64, 3, 3, 3, 3)), "head.conv.weight_u": z((64,)), "body.block0.conv.bias": z((64,)),
+              "body.block3.conv.weight_orig": z((64, 64, 3, 3, 3)), "tail.weight": z((1, 64, 3, 3, 3)), "tail.bias": z((1,))}
+    dgot = ck.p2m_WDiscriminator_3d({"state_dict": dstate})
+    assert set(dgot) == {"head.0.weight", "head.0.weight_u", "body.0.0.bias", "body.3.0.weight", "tail.weight", "tail.bias"}
+    dref = ck.to_reference_names(dgot)
+    assert set(dref) == {"head.0.weight", "head.0.weight_u", "body.0.0.bias", "body.0.3.0.weight", "tail.weight", "tail.bias"}
+    assert set(ck.from_reference_names(dref)) == set(dgot)
 
 
 def test_product_package_does_not_import_torch_or_oracle():

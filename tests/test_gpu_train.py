@@ -381,3 +381,145 @@ def test_vae_phase_with_reparameterised_z_is_training_true(hpvg_gpu):
     # the chain is the longest in the model (body BN x6 + decoder BN x6 before reaching the encoder): conditioning-
     # limited like the other BatchNorm-path gradients (see the note above), measured rel-L2 0.15-0.21, cos 0.98-0.99
     _report(got, ref, 0.30, "VAE phase, is_training=True / encoder through the reparameterisation", min_cos=0.97)
+
+
+def test_gan_phase_train_depth_2_reaches_both_stages(hpvg_gpu):
+    """--train-depth 2 (train_video.py:78-86): the optimiser holds body[-2:], and the reconstruction loss must reach BOTH
+    stages — the backward chain runs from the top stage through the resize adjoint into the stage below and stops at
+    the lowest trainable one (round-1 advisor finding: only the top stage received a gradient)."""
+    hp = hpvg_gpu
+    from hpvg import train as T
+    nb = 5
+    G, D, opt, oopt, pg, pd, rng = _setup(hp, nb, seed=11)
+    s0, st = orc.scale_shape(oopt, 0), orc.scale_shape(oopt, nb)
+    real = np.tanh(rng.standard_normal((1, 3) + st)).astype(np.float32)
+    real_zero = np.tanh(rng.standard_normal((1, 3) + s0)).astype(np.float32)
+    z_pred = rng.standard_normal((1, 128) + s0).astype(np.float32)
+    noise_init = rng.standard_normal((1, 128) + s0).astype(np.float32)
+    nz = {s: rng.standard_normal((1, 3) + orc.scale_shape(oopt, s)).astype(np.float32) for s in range(3, nb + 1)}
+    amps = [1.0, 0.0, 0.0, 0.3, 0.25, 0.2]
+    G.set_train(True)
+    D.set_train(True)
+    tg = orc.to_torch(pg, requires_grad=("body.3.", "body.4."))
+    td = orc.to_torch(pd)
+    with orc.bf16_emulation():
+        gloss_ref = orc.g_loss(torch.from_numpy(real), torch.from_numpy(real_zero), torch.from_numpy(noise_init), amps,
+                               tg, td, oopt, False, z_pred=torch.from_numpy(z_pred),
+                               noises={k: torch.from_numpy(v) for k, v in nz.items()})
+    gloss_ref.backward()
+    names = [k for k, t in tg.items() if t.requires_grad]
+    ref = {k: tg[k].grad.numpy() for k in names}
+    assert np.linalg.norm(ref["body.3.2.0.weight"]) > 0
+    gl = T.GWithLoss(opt, D, G)
+    loss, book = gl.grad(hp.from_numpy(real), hp.from_numpy(real_zero), hp.from_numpy(noise_init), amps, isVAE=False,
+                         trainable_body=(3, 4), z_pred=hp.from_numpy(z_pred),
+                         noises={k: hp.from_numpy(v) for k, v in nz.items()})
+    assert abs(float(loss) - float(gloss_ref)) < 2e-2 * abs(float(gloss_ref))
+    got = _grads_by_name(G, book, names)
+    assert np.linalg.norm(got["body.3.2.0.weight"]) > 0, "the lower trainable stage received no gradient"
+    _report(got, ref, E2E_BN_TOL, "G step, GAN phase, train_depth 2", min_cos=E2E_BN_COS)
+
+
+def test_gan_phase_train_all_reaches_the_decoder(hpvg_gpu):
+    """--train-all with fewer stages than train_depth (train_video.py:95-103): encode / decoder / every stage are in the
+    optimiser in the GAN phase too, there is no stop_gradient (networks_3d.py:437), and the reconstruction term flows
+    through the whole chain into the decoder; the encoder sees nothing (z is pure noise, Q2; no KL term in this phase)."""
+    hp = hpvg_gpu
+    from hpvg import networks_3d as n3, train as T
+    from hpvg.utils import images as uimg
+    nb = 3
+    opt, oopt = uimg.default_opt(train_all=True, train_depth=5), orc.default_opt(train_all=True, train_depth=5)
+    pg = orc.init_generator_params(oopt, nb, seed=13)
+    pd = orc.init_discriminator_params(oopt, seed=13)
+    rng = np.random.default_rng(13)
+    G = n3.GeneratorHPVAEGAN(opt)
+    for _ in range(nb):
+        G.init_next_stage()
+    G.load_parameters(pg)
+    D = n3.WDiscriminator3D(opt)
+    D.load_parameters(pd)
+    s0, st = orc.scale_shape(oopt, 0), orc.scale_shape(oopt, nb)
+    real = np.tanh(rng.standard_normal((1, 3) + st)).astype(np.float32)
+    real_zero = np.tanh(rng.standard_normal((1, 3) + s0)).astype(np.float32)
+    z_pred = rng.standard_normal((1, 128) + s0).astype(np.float32)
+    noise_init = rng.standard_normal((1, 128) + s0).astype(np.float32)
+    nz = {3: rng.standard_normal((1, 3) + st).astype(np.float32)}
+    amps = [1.0, 0.0, 0.0, 0.3]
+    G.set_train(True)
+    D.set_train(True)
+    tg = orc.to_torch(pg, requires_grad=("encode.", "decoder.", "body."))
+    td = orc.to_torch(pd)
+    with orc.bf16_emulation():
+        gloss_ref = orc.g_loss(torch.from_numpy(real), torch.from_numpy(real_zero), torch.from_numpy(noise_init), amps,
+                               tg, td, oopt, False, z_pred=torch.from_numpy(z_pred),
+                               noises={k: torch.from_numpy(v) for k, v in nz.items()})
+    gloss_ref.backward()
+    names = [k for k, t in tg.items() if t.requires_grad and t.grad is not None and not k.startswith("encode.")]
+    ref = {k: tg[k].grad.numpy() for k in names}
+    assert np.linalg.norm(ref["decoder.0.0.weight"]) > 0
+    gl = T.GWithLoss(opt, D, G)
+    loss, book = gl.grad(hp.from_numpy(real), hp.from_numpy(real_zero), hp.from_numpy(noise_init), amps, isVAE=False,
+                         trainable_body=(0, 1, 2), train_codec=True, z_pred=hp.from_numpy(z_pred),
+                         noises={k: hp.from_numpy(v) for k, v in nz.items()})
+    assert abs(float(loss) - float(gloss_ref)) < 2e-2 * abs(float(gloss_ref))
+    got = _grads_by_name(G, book, names)
+    assert np.linalg.norm(got["decoder.0.0.weight"]) > 0, "the decoder received no gradient"
+    # the longest BatchNorm chain in the model (3 stages + decoder = 24 BN layers): conditioning-limited like the VAE test
+    _report(got, ref, 0.30, "G step, GAN phase, --train-all (decoder + 3 stages)", min_cos=0.95)
+
+
+def test_cuda_graph_vae_iteration_matches_eager_iteration(hpvg_gpu):
+    """The VAE-phase iteration (d_step None: encoder + decoder + refinement stage, resize backward, KL / MSE terms,
+    ClippedAdam with per-group learning rates) captured as a CUDA graph evolves the weights like the eager sequence.
+    The capture allocates temporaries and the layers' packed filter banks; between replays the test churns the caching
+    allocator — memory baked into the graph must stay reserved for it (runtime: _GRAPH_OWNED)."""
+    hp = hpvg_gpu
+    from hpvg import driver, train as T
+
+    def run(graphed, iters=4):
+        scale_idx = 2
+        G, D, opt, oopt, pg, pd, rng = _setup(hp, scale_idx, seed=21)
+        G.noise_seed = 0x7654321
+        st = hp.Stream()
+        real = hp.from_numpy(np.tanh(rng.standard_normal((1, 3) + orc.scale_shape(oopt, scale_idx))).astype(np.float32))
+        real_zero = hp.from_numpy(np.tanh(rng.standard_normal((1, 3) + orc.scale_shape(oopt, 0))).astype(np.float32))
+        noise = hp.from_numpy(rng.standard_normal((1, 128) + orc.scale_shape(oopt, 0)).astype(np.float32))
+        amps = [1.0, 0.0, 0.0]
+        groups, body_idx, codec = driver.generator_param_groups(opt, G, scale_idx)
+        optG = T.ClippedAdam(opt, groups, opt.lr_g, beta1=0.5, beta2=0.999, device_step=True)
+        cells = [G.body[i] for i in body_idx] + [G.encode, G.decoder]
+        g_step = T.TrainOneStepCell(T.GWithLoss(opt, None, G, device_rng=True), optG, cells_to_invalidate=cells)
+        G.set_train(True)
+        it = T.GraphedIteration(st, g_step, None, real, real_zero, noise, amps,
+                                dict(isVAE=True, trainable_body=body_idx, train_codec=codec))
+        it.warmup(1)
+        losses = []
+        if graphed:
+            it.capture()
+            assert it.kernels_per_launch > 100
+            for _ in range(iters):
+                junk = [hp.Tensor((n,), hp.F32).zero_(st) for n in (64, 4096, 27 * 64 * 64 * 2, 16384)]   # allocator churn
+                del junk
+                for c in cells:
+                    c.invalidate()
+                losses.append(float(it()[1]))
+        else:
+            for _ in range(iters):
+                losses.append(float(it._body(True)[1]))
+        st.sync()
+        out = {k: t.numpy() for k, t in G.parameters_dict().items()}
+        if graphed:
+            it.destroy()
+        return out, losses
+
+    p_e, l_e = run(False)
+    p_g, l_g = run(True)
+    for a, b in zip(l_e, l_g):
+        assert abs(a - b) < 2e-3 * max(1.0, abs(a)), (l_e, l_g)
+    assert l_e[0] != l_e[1]
+    for k in p_e:
+        if k.endswith(".0.bias") and (k.startswith("body.") or k.startswith("decoder.")) and ".6." not in k:
+            # conv bias in front of a BatchNorm: analytically zero gradient, Adam amplifies rounding noise (see above)
+            assert np.abs(p_g[k] - p_e[k]).max() <= 2 * 4 * 5e-4 + 1e-6, k
+            continue
+        assert rel_l2(p_g[k], p_e[k]) < 2e-3, k
