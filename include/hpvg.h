@@ -9,6 +9,8 @@
  * Conventions
  *   - every pointer named d_* / "device" is a CUDA device pointer owned by the caller; the library never frees it.
  *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Nothing synchronises inside.
+ *   - thread safety: every entry point may be called concurrently from several host threads provided each uses its own
+ *     stream (all internal scratch — reduction buffers, weight-gradient partials, AOT staging — is per stream).
  *   - return value: 0 on success, negative HPVG_E_* on failure; hpvg_last_error() gives a thread-local message.
  *   - "cl" tensors are channels-last bf16: (N, T, H, W, Cpitch); "ncdhw" tensors are fp32 (N, C, T, H, W) — the
  *     layout of the reference's Tensors.  2-D (N, C, H, W) data is the T == 1 case.
@@ -64,6 +66,11 @@ int hpvg_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);
 int hpvg_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
 int hpvg_d2d(void* d_dst, const void* d_src, size_t bytes, void* stream);
 int hpvg_stream_create(void** stream);
+/* Scratch memory is per stream.  hpvg_stream_create registers its stream; a stream created elsewhere (MindSpore's) is
+ * registered on first use, or explicitly with hpvg_stream_attach — required before that stream is first used INSIDE a
+ * CUDA-graph capture (registration allocates).  hpvg_stream_detach releases the scratch of a foreign stream. */
+int hpvg_stream_attach(void* stream);
+int hpvg_stream_detach(void* stream);
 int hpvg_stream_destroy(void* stream);
 int hpvg_stream_sync(void* stream);
 int hpvg_device_sync(void);
@@ -280,13 +287,27 @@ int hpvg_gp_grad(const float* d_g, int N, int C, long long spatial, float lambda
 
 /* ---------------------------------------------------------------- MindSpore ops.Custom(func_type="aot") entry points
  * int Name(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes, void* stream, void* extra)
- * params = device pointers, inputs then outputs, pre-allocated by the framework. */
-int HpvgUpsampleTrilinear3D(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
-                            void* stream, void* extra); /* x -> y, align_corners=True */
-int HpvgUpsampleTrilinear3DGrad(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
-                                void* stream, void* extra); /* (dy, x) -> dx */
-int HpvgConv3dBiasLRelu(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes, void* stream,
-                        void* extra); /* (x ncdhw f32 C=64, w (64,64,3,3,3), b) -> y */
+ * params = fp32 device pointers in the reference's layouts, inputs then outputs, pre-allocated by the framework.
+ * No allocation per call and no synchronisation inside: staging buffers live in the calling stream's grow-only
+ * workspace (the first call at a new size grows it).  0 = success, anything else makes MindSpore raise.
+ * Each entry replaces the MindSpore library op named next to it. */
+#define HPVG_AOT(name) \
+  int name(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes, void* stream, void* extra)
+HPVG_AOT(HpvgUpsampleTrilinear3D);       /* x -> y, align_corners=True            (src/tools/trilinear.py:171-254)  */
+HPVG_AOT(HpvgUpsampleTrilinear3DGrad);   /* (dy, x) -> dx                          (its bprop)                       */
+HPVG_AOT(HpvgConv3dBias);                /* (x, w, b) -> conv(x, w) + b            (nn.Conv3d, networks_3d.py:48-50)  */
+HPVG_AOT(HpvgConv3dBiasLRelu);           /* ... -> LeakyReLU(0.2)                  (ConvBlock3DSN, :57-73)            */
+HPVG_AOT(HpvgConv3dBiasTanh);            /* ... -> tanh (Cout <= 3 tails)          (networks_3d.py:399,450)           */
+/*   channel shapes: (Cin <= 8 | 64) -> 64 and 64 -> (<= 3); x (N,Cin,T,H,W), w (Cout,Cin,3,3,3), b (Cout)          */
+HPVG_AOT(HpvgConv3dBiasLReluGrad);       /* (x, w, y, dy) -> (dx, dw, db), 64 -> 64 (autodiff of the above)          */
+HPVG_AOT(HpvgBatchNorm3dLReluTrain);     /* (x, gamma, beta, moving_mean, moving_var) -> (y, saved[4,64]); moving
+                                            statistics updated in place           (nn.BatchNorm3d train, :52-53)    */
+HPVG_AOT(HpvgBatchNorm3dLReluTrainGrad); /* (dy, x, saved) -> (dx, dgamma, dbeta)                                    */
+HPVG_AOT(HpvgSpectralNormIter);          /* (w, u, v) -> (sigma2[2] = sigma, 1/sigma; u'; v') (spectral_norm.py:146-151) */
+HPVG_AOT(HpvgClipAdam);                  /* (param, grad, m, v, hyper[6] = lr, beta1, beta2, eps, clip, step) ->
+                                            (param', m', v')                      (optimizers.py:41-43, nn.Adam)    */
+HPVG_AOT(HpvgMSELoss);                   /* (a, b) -> loss[1]                      (nn.MSELoss)                      */
+HPVG_AOT(HpvgKLLoss);                    /* (mu, logvar) -> loss[1]                (losses.py:5-7)                   */
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 
 #include "../../include/hpvg.h"
 #include "conv3d_umma.h"
@@ -17,11 +19,28 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
-float* g_adam_norms = nullptr;
-float* g_wgrad_ws = nullptr;   // [sm/3][27][64][64] partial weight gradients
-double* g_sums = nullptr;      // [128] reduction scratch (BatchNorm backward, column sums)
-float* g_fscratch = nullptr;   // [256] fp32 scratch (spectral-norm gradient partial dots)
 int g_sm_count = 0;
+
+// Scratch memory is PER STREAM: two host threads (or two branches of a captured graph) driving different streams never
+// share a reduction buffer, so every entry point is safe to call concurrently as long as each caller uses its own
+// stream.  A stream's context is created by hpvg_stream_create / hpvg_stream_attach (or lazily on first
+// use, which allocates and therefore must not happen while that stream is being captured into a graph).
+struct StreamCtx {
+  float* adam_norms = nullptr;   // [ADAM_MAX_TENSORS] per-tensor gradient norms
+  float* wgrad_ws = nullptr;     // [sm/3][27][64][64] partial weight gradients
+  double* sums = nullptr;        // [128] reduction scratch (BatchNorm backward, column sums)
+  float* fscratch = nullptr;     // [256] fp32 scratch (spectral-norm gradient partial dots)
+  void* arena = nullptr;         // grow-only workspace of the ops.Custom(aot) entry points
+  size_t arena_cap = 0;
+};
+std::mutex g_ctx_mu;
+std::unordered_map<void*, StreamCtx*> g_ctx;
+
+void ctx_free(StreamCtx* c) {
+  if (!c) return;
+  cudaFree(c->adam_norms); cudaFree(c->wgrad_ws); cudaFree(c->sums); cudaFree(c->fscratch); cudaFree(c->arena);
+  delete c;
+}
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -45,6 +64,58 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
+// The scratch context of `stream` (nullptr + g_err on failure).
+StreamCtx* ctx_for(void* stream) {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  auto it = g_ctx.find(stream);
+  if (it != g_ctx.end()) return it->second;
+  if (g_sm_count == 0) {
+    g_err = "hpvg_init was not called";
+    return nullptr;
+  }
+  StreamCtx* c = new StreamCtx();
+  size_t wg = hpvg::conv3d_wgrad_workspace_bytes(g_sm_count);
+  const size_t wg32 = hpvg::conv3d_wgrad_tf32_workspace_bytes(g_sm_count);
+  if (wg32 > wg) wg = wg32;
+  cudaError_t e = cudaMalloc(&c->adam_norms, hpvg::ADAM_MAX_TENSORS * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->wgrad_ws, wg);
+  if (e == cudaSuccess) e = cudaMalloc(&c->sums, 128 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&c->fscratch, 256 * sizeof(float));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    g_err = std::string("scratch allocation for a new stream failed (") + cudaGetErrorString(e) +
+            "); a stream first used inside a graph capture must be registered with hpvg_stream_attach before";
+    ctx_free(c);
+    return nullptr;
+  }
+  g_ctx[stream] = c;
+  return c;
+}
+
+// `bytes` of 256-byte aligned workspace on `stream` (grow-only; growing synchronises that stream once).
+void* arena_for(void* stream, size_t bytes) {
+  StreamCtx* c = ctx_for(stream);
+  if (!c) return nullptr;
+  if (bytes <= c->arena_cap) return c->arena;
+  if (c->arena) {
+    if (cudaStreamSynchronize(S(stream)) != cudaSuccess) return nullptr;
+    cudaFree(c->arena);
+    c->arena = nullptr;
+    c->arena_cap = 0;
+  }
+  const size_t cap = (bytes + (1u << 20) - 1) & ~static_cast<size_t>((1u << 20) - 1);
+  if (cudaMalloc(&c->arena, cap) != cudaSuccess) {
+    cudaGetLastError();
+    g_err = "workspace allocation failed";
+    return nullptr;
+  }
+  c->arena_cap = cap;
+  return c->arena;
+}
+#define CTX(c, st)                        \
+  StreamCtx* c = ctx_for(st);             \
+  if (!c) return HPVG_E_ARG
+
 }  // namespace
 
 extern "C" {
@@ -67,10 +138,7 @@ int hpvg_init(int device) {
   CU(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail(HPVG_E_UNSUPPORTED, "libhpvg needs an sm_100a (B200) device");
   g_sm_count = prop.multiProcessorCount;
-  if (!g_adam_norms) CU(cudaMalloc(&g_adam_norms, hpvg::ADAM_MAX_TENSORS * sizeof(float)));
-  if (!g_wgrad_ws) CU(cudaMalloc(&g_wgrad_ws, hpvg::conv3d_wgrad_workspace_bytes(g_sm_count)));
-  if (!g_sums) CU(cudaMalloc(&g_sums, 128 * sizeof(double)));
-  if (!g_fscratch) CU(cudaMalloc(&g_fscratch, 256 * sizeof(float)));
+  if (!ctx_for(nullptr)) return HPVG_E_CUDA;      // the legacy default stream's scratch
   return HPVG_OK;
 }
 int hpvg_sm_count(void) { return g_sm_count; }
@@ -110,9 +178,25 @@ int hpvg_stream_create(void** st) {
   cudaStream_t s;
   CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   *st = s;
+  if (!ctx_for(s)) return HPVG_E_CUDA;
+  return HPVG_OK;
+}
+int hpvg_stream_attach(void* st) { return ctx_for(st) ? HPVG_OK : HPVG_E_CUDA; }
+int hpvg_stream_detach(void* st) {
+  StreamCtx* c = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    auto it = g_ctx.find(st);
+    if (it == g_ctx.end()) return HPVG_OK;
+    c = it->second;
+    g_ctx.erase(it);
+  }
+  CU(cudaStreamSynchronize(S(st)));
+  ctx_free(c);
   return HPVG_OK;
 }
 int hpvg_stream_destroy(void* st) {
+  hpvg_stream_detach(st);
   CU(cudaStreamDestroy(S(st)));
   return HPVG_OK;
 }
@@ -421,7 +505,7 @@ int hpvg_adam_clip_multi(int n_tensors, float* const* params, const float* const
                          float eps, int step, float clip, const uint64_t* d_step, void* st) {
   if (step < 1 && !d_step) return fail(HPVG_E_ARG, "adam: step is 1-based");
   if (step < 1) step = 1;
-  if (!g_adam_norms) return fail(HPVG_E_ARG, "hpvg_init was not called");
+  CTX(cx, st);
   const float bc = static_cast<float>(std::sqrt(1.0 - std::pow(static_cast<double>(beta2), step)) /
                                       (1.0 - std::pow(static_cast<double>(beta1), step)));
   for (int base = 0; base < n_tensors; base += hpvg::ADAM_MAX_TENSORS) {
@@ -436,8 +520,8 @@ int hpvg_adam_clip_multi(int n_tensors, float* const* params, const float* const
       tab.n[cnt] = sizes[i];
       tab.lr[cnt] = lrs[i];
     }
-    KL(hpvg::ew_adam_clip(tab, cnt, g_adam_norms, beta1, beta2, eps, bc, clip,
-                          reinterpret_cast<const unsigned long long*>(d_step), S(st)), clip > 0.f ? 2 : 1);
+    KL(hpvg::ew_adam_clip(tab, cnt, cx->adam_norms, beta1, beta2, eps, bc, clip,
+                          reinterpret_cast<const unsigned long long*>(d_step), S(st), nullptr), clip > 0.f ? 2 : 1);
   }
   return HPVG_OK;
 }
@@ -447,7 +531,7 @@ int hpvg_conv_wgrad_cl(const void* x, int x_pitch, const void* gy, int gy_pitch,
                        float* dw, int w_cin, int kt, int co_off, int co_n, int ci_off, int ci_n, int accumulate,
                        float scale, void* st) {
   if (N <= 0 || T <= 0 || H <= 0 || W <= 0) return HPVG_OK;
-  if (!g_wgrad_ws) return fail(HPVG_E_ARG, "hpvg_init was not called");
+  CTX(cx, st);
   if ((x_pitch & 7) || (gy_pitch & 7) || x_pitch < 8 || gy_pitch < 8)
     return fail(HPVG_E_ARG, "conv_wgrad_cl: operands must be bf16 channels-last tensors with a pitch of 8k channels");
   if ((x_pitch < 64 && ci_n > x_pitch) || (gy_pitch < 64 && co_n > gy_pitch))
@@ -455,7 +539,7 @@ int hpvg_conv_wgrad_cl(const void* x, int x_pitch, const void* gy, int gy_pitch,
   if (co_n < 1 || co_n > 64 || ci_n < 1 || ci_n > 64 || (kt != 1 && kt != 3))
     return fail(HPVG_E_ARG, "conv_wgrad_cl: bad block extents");
   const char* e = hpvg::conv3d_wgrad_launch(x, x_pitch, gy, gy_pitch, N, T, H, W, dw, w_cin, kt, co_off, co_n, ci_off,
-                                            ci_n, accumulate, scale, g_wgrad_ws, g_sm_count, S(st));
+                                            ci_n, accumulate, scale, cx->wgrad_ws, g_sm_count, S(st));
   if (e) return fail(HPVG_E_CUDA, std::string("conv_wgrad_cl: ") + e);
   g_launches += 2;
   return HPVG_OK;
@@ -464,7 +548,7 @@ int hpvg_conv_wgrad_cl_tf32(const float* x, int x_pitch, const float* gy, int gy
                             float* dw, int w_cin, int kt, int co_off, int co_n, int ci_off, int ci_n, int accumulate,
                             float scale, void* st) {
   if (N <= 0 || T <= 0 || H <= 0 || W <= 0) return HPVG_OK;
-  if (!g_wgrad_ws) return fail(HPVG_E_ARG, "hpvg_init was not called");
+  CTX(cx, st);
   if ((x_pitch & 3) || (gy_pitch & 3) || x_pitch < 4 || gy_pitch < 4 || (x_pitch >= 32 && x_pitch < 64) ||
       (gy_pitch >= 32 && gy_pitch < 64))
     return fail(HPVG_E_ARG, "conv_wgrad_cl_tf32: operands are fp32 channels-last tensors of >= 64 channels, or narrow "
@@ -476,7 +560,7 @@ int hpvg_conv_wgrad_cl_tf32(const float* x, int x_pitch, const float* gy, int gy
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(gy) & 15))
     return fail(HPVG_E_ARG, "conv_wgrad_cl_tf32: operands must be 16-byte aligned");
   const char* e = hpvg::conv3d_wgrad_tf32_launch(x, x_pitch, gy, gy_pitch, N, T, H, W, dw, w_cin, kt, co_off, co_n,
-                                                 ci_off, ci_n, accumulate, scale, g_wgrad_ws, g_sm_count, S(st));
+                                                 ci_off, ci_n, accumulate, scale, cx->wgrad_ws, g_sm_count, S(st));
   if (e) return fail(HPVG_E_CUDA, std::string("conv_wgrad_cl_tf32: ") + e);
   g_launches += 2;
   return HPVG_OK;
@@ -509,14 +593,14 @@ int hpvg_lrelu_bwd_cl_f32(const float* ga, const float* a, long long elems, floa
 int hpvg_bn_bwd_cl_f32(const float* ga, const float* y, long long voxels, const float* saved, int act, float* gy,
                        float* dgamma, float* dbeta, int accumulate, void* st) {
   if (voxels <= 0) return fail(HPVG_E_ARG, "bn_bwd: empty batch");
-  if (!g_sums) return fail(HPVG_E_ARG, "hpvg_init was not called");
-  KL(hpvg::ew_bn_bwd_cl_f32(ga, y, voxels, saved, act, g_sums, gy, dgamma, dbeta, accumulate, S(st)), 4);
+  CTX(cx, st);
+  KL(hpvg::ew_bn_bwd_cl_f32(ga, y, voxels, saved, act, cx->sums, gy, dgamma, dbeta, accumulate, S(st)), 4);
   return HPVG_OK;
 }
 int hpvg_colsum_cl_f32(const float* g, long long voxels, float* out, int accumulate, void* st) {
   if (voxels <= 0) return fail(HPVG_E_ARG, "colsum: empty input");
-  if (!g_sums) return fail(HPVG_E_ARG, "hpvg_init was not called");
-  KL(hpvg::ew_colsum_cl_f32(g, voxels, g_sums, out, accumulate, S(st)), 2);
+  CTX(cx, st);
+  KL(hpvg::ew_colsum_cl_f32(g, voxels, cx->sums, out, accumulate, S(st)), 2);
   return HPVG_OK;
 }
 int hpvg_slice_act_cl(const void* in, int NT, int Hi, int Wi, int C, int Ho, int Wo, int h0, int w0, int sh, int sw,
@@ -539,15 +623,15 @@ int hpvg_lrelu_bwd_cl(const void* ga, const void* a, long long elems, void* gz, 
 int hpvg_bn_bwd_cl(const void* ga, const void* y, long long voxels, const float* saved, int act, void* gy,
                    float* dgamma, float* dbeta, int accumulate, void* st) {
   if (voxels <= 0) return fail(HPVG_E_ARG, "bn_bwd: empty batch");
-  if (!g_sums) return fail(HPVG_E_ARG, "hpvg_init was not called");
+  CTX(cx, st);
   KL(hpvg::ew_bn_bwd_cl(static_cast<const __nv_bfloat16*>(ga), static_cast<const __nv_bfloat16*>(y), voxels, saved,
-                        act, g_sums, static_cast<__nv_bfloat16*>(gy), dgamma, dbeta, accumulate, S(st)), 4);
+                        act, cx->sums, static_cast<__nv_bfloat16*>(gy), dgamma, dbeta, accumulate, S(st)), 4);
   return HPVG_OK;
 }
 int hpvg_colsum_cl(const void* g, long long voxels, float* out, int accumulate, void* st) {
   if (voxels <= 0) return fail(HPVG_E_ARG, "colsum: empty input");
-  if (!g_sums) return fail(HPVG_E_ARG, "hpvg_init was not called");
-  KL(hpvg::ew_colsum_cl(static_cast<const __nv_bfloat16*>(g), voxels, g_sums, out, accumulate, S(st)), 2);
+  CTX(cx, st);
+  KL(hpvg::ew_colsum_cl(static_cast<const __nv_bfloat16*>(g), voxels, cx->sums, out, accumulate, S(st)), 2);
   return HPVG_OK;
 }
 int hpvg_mse_grad(const float* out, const float* target, long long n, float coef, int accumulate, float* g, void* st) {
@@ -599,9 +683,9 @@ int hpvg_gather_strided(const float* src, long long n, long long stride, long lo
 }
 int hpvg_channel_sum(const float* g, int N, int C, long long sp, int accumulate, float* out, void* st) {
   if (N <= 0 || C <= 0 || sp <= 0) return fail(HPVG_E_ARG, "channel_sum: empty input");
-  if (!g_sums) return fail(HPVG_E_ARG, "hpvg_init was not called");
+  CTX(cx, st);
   if (C > 128) return fail(HPVG_E_ARG, "channel_sum: at most 128 channels");
-  KL(hpvg::ew_channel_sum_ncdhw(g, N, C, sp, accumulate, g_sums, out, S(st)), 2);
+  KL(hpvg::ew_channel_sum_ncdhw(g, N, C, sp, accumulate, cx->sums, out, S(st)), 2);
   return HPVG_OK;
 }
 int hpvg_kl_grad(const float* mu, const float* lv, long long n, float coef, float* gmu, float* glv, void* st) {
@@ -612,8 +696,8 @@ int hpvg_kl_grad(const float* mu, const float* lv, long long n, float coef, floa
 int hpvg_sn_grad(const float* G, const float* w, const float* u, const float* v, const float* sigma, int cout, int k,
                  int accumulate, float* gw, void* st) {
   if (cout <= 0 || k <= 0) return fail(HPVG_E_ARG, "sn_grad: empty matrix");
-  if (!g_fscratch) return fail(HPVG_E_ARG, "hpvg_init was not called");
-  KL(hpvg::ew_sn_grad(G, w, u, v, sigma, cout, k, accumulate, g_fscratch, gw, S(st)), 2);
+  CTX(cx, st);
+  KL(hpvg::ew_sn_grad(G, w, u, v, sigma, cout, k, accumulate, cx->fscratch, gw, S(st)), 2);
   return HPVG_OK;
 }
 int hpvg_lerp(const float* a, const float* b, float alpha, long long n, float* out, void* st) {
@@ -628,7 +712,83 @@ int hpvg_gp_grad(const float* g, int N, int C, long long sp, float lambda, float
 }
 
 // ------------------------------------------------------------------------------------------------ MindSpore AOT
-static bool is_f32(const char* s) { return s && std::strcmp(s, "float32") == 0; }
+// Entry points with the signature MindSpore's ops.Custom(func_type="aot") calls:
+//     int f(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes, void* stream, void* extra)
+// params = inputs then outputs, all fp32 device tensors in the reference's layouts (NCDHW / parameter shapes), all
+// owned by the caller.  Nothing allocates per call and nothing synchronises: the bf16 channels-last staging buffers,
+// packed filter banks and epilogue vectors live in the calling stream's grow-only workspace (arena_for) — the first
+// call at a new size grows it (one stream synchronise), every later call reuses it.  0 = success; any other value makes
+// MindSpore raise (hpvg_last_error() has the reason).  Where the reference's cell updates a Parameter in place
+// (BatchNorm moving statistics) the entry point writes through the corresponding INPUT pointer, as the MindSpore kernel
+// does.  INTEGRATION.md lists each entry with the Custom(...) declaration that binds it.
+}  // extern "C" (helpers with C++ linkage follow)
+
+namespace {
+bool is_f32(const char* s) { return s && std::strcmp(s, "float32") == 0; }
+struct Carver {     // sequential 256-byte aligned sub-buffers of one workspace
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base(static_cast<char*>(b)) {}
+  template <typename T>
+  T* take(size_t bytes) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off += (bytes + 255) & ~static_cast<size_t>(255);
+    return p;
+  }
+};
+inline size_t al(size_t b) { return (b + 255) & ~static_cast<size_t>(255); }
+bool all_f32(int n, const char** dtypes) {
+  for (int i = 0; i < n; ++i)
+    if (!is_f32(dtypes[i])) return false;
+  return true;
+}
+int aot_bad(const char* msg) {
+  g_err = msg;
+  return 1;
+}
+
+// y = act(conv3x3x3(x, w) + b): (Cin <= 8 | 64) -> 64 with fp32 NCDHW in/out, or 64 -> (<= 3) (tail; tanh/none)
+int aot_conv(int act, int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes, void* stream) {
+  if (nparam != 4 || !all_f32(4, dtypes) || ndims[0] != 5 || ndims[1] != 5 || ndims[2] != 1 || ndims[3] != 5)
+    return aot_bad("conv: expects (x[N,Cin,T,H,W], w[Cout,Cin,3,3,3], b[Cout]) -> y[N,Cout,T,H,W], all float32");
+  const int64_t* a = shapes[0];
+  const int64_t* ws = shapes[1];
+  const int N = (int)a[0], Cin = (int)a[1], T = (int)a[2], H = (int)a[3], W = (int)a[4];
+  const int Cout = (int)ws[0];
+  if (ws[1] != Cin || ws[2] != 3 || ws[3] != 3 || ws[4] != 3 || shapes[2][0] != Cout || shapes[3][1] != Cout ||
+      shapes[3][0] != N || shapes[3][2] != T || shapes[3][3] != H || shapes[3][4] != W)
+    return aot_bad("conv: inconsistent shapes");
+  const bool head = Cin <= 8 && Cout == 64, body = Cin == 64 && Cout == 64, tail = Cin == 64 && Cout <= 3;
+  if (!head && !body && !tail) return aot_bad("conv: supported channel shapes are (<=8|64)->64 and 64->(<=3)");
+  const size_t vox = (size_t)N * T * H * W;
+  const int mode = head ? HPVG_CONV_8_64 : (body ? HPVG_CONV_64_64 : HPVG_CONV_64_3);
+  const int in_pitch = head ? 8 : 64;
+  const size_t need = al(vox * in_pitch * 2) + al(tail ? 0 : vox * 128) + al(hpvg_conv_wimg_bytes(mode)) + al(512);
+  void* wsp = arena_for(stream, need);
+  if (!wsp) return 3;
+  Carver cv(wsp);
+  void* xcl = cv.take<void>(vox * in_pitch * 2);
+  void* ycl = cv.take<void>(tail ? 0 : vox * 128);
+  void* wimg = cv.take<void>(hpvg_conv_wimg_bytes(mode));
+  float* aff = cv.take<float>(512);
+  int rc = hpvg_pack_cl(static_cast<const float*>(params[0]), N, Cin, T, H, W, xcl, in_pitch, 0, in_pitch, stream);
+  if (!rc) rc = hpvg_conv_pack_weights(static_cast<const float*>(params[1]), Cout, Cin, 3, mode, 0, 0, Cout, 0, Cin, wimg,
+                                       stream);
+  if (!rc) rc = hpvg_memset(aff, 0, 512, stream);
+  if (!rc) rc = hpvg_affine_from_bias(static_cast<const float*>(params[2]), nullptr, Cout, aff, aff + 64, stream);
+  if (tail) {
+    if (!rc) rc = hpvg_conv_cl(mode, N, T, H, W, xcl, 64, wimg, aff, aff + 64, act, HPVG_OUT_F32_NCDHW, params[3], 64, 0,
+                               Cout, nullptr, nullptr, nullptr, 0, stream);
+  } else {
+    if (!rc) rc = hpvg_conv_cl(mode, N, T, H, W, xcl, in_pitch, wimg, aff, aff + 64, act, HPVG_OUT_BF16_CL, ycl, 64, 0, 64,
+                               nullptr, nullptr, nullptr, 0, stream);
+    if (!rc) rc = hpvg_unpack_cl(ycl, N, 64, T, H, W, 64, 0, static_cast<float*>(params[3]), stream);
+  }
+  return rc;
+}
+}  // namespace
+
+extern "C" {
 
 int HpvgUpsampleTrilinear3D(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
                             void* stream, void* /*extra*/) {
@@ -648,32 +808,171 @@ int HpvgUpsampleTrilinear3DGrad(int nparam, void** params, int* ndims, int64_t**
   return hpvg_resize3d_bwd(static_cast<const float*>(params[0]), (int)a[0], (int)a[1], (int)a[2], (int)a[3],
                            (int)a[4], static_cast<float*>(params[2]), (int)b[2], (int)b[3], (int)b[4], 1, stream);
 }
-int HpvgConv3dBiasLRelu(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes, void* stream,
-                        void* /*extra*/) {
-  // x (N,64,T,H,W) f32, w (64,64,3,3,3) f32, b (64) f32 -> y (N,64,T,H,W) f32 ; workspace is allocated per call here
-  // (a production binding passes a workspace through `extra`)
-  if (nparam != 4 || ndims[0] != 5 || !is_f32(dtypes[0])) return 1;
+
+// nn.Conv3d(+bias) [+ LeakyReLU(0.2) | tanh] of networks_3d.py:48-53, 380, 399: (x, w, b) -> y
+int HpvgConv3dBias(int n, void** p, int* nd, int64_t** sh, const char** dt, void* st, void*) {
+  return aot_conv(HPVG_ACT_NONE, n, p, nd, sh, dt, st);
+}
+int HpvgConv3dBiasLRelu(int n, void** p, int* nd, int64_t** sh, const char** dt, void* st, void*) {
+  return aot_conv(HPVG_ACT_LRELU, n, p, nd, sh, dt, st);
+}
+int HpvgConv3dBiasTanh(int n, void** p, int* nd, int64_t** sh, const char** dt, void* st, void*) {
+  return aot_conv(HPVG_ACT_TANH, n, p, nd, sh, dt, st);
+}
+
+// bprop of y = LeakyReLU(conv(x, w) + b) for the 64 -> 64 layer: (x, w, y, dy) -> (dx, dw, db).
+// The data gradient is the forward kernel on the transposed / mirrored bank (dgrad), the weight gradient the tcgen05
+// wgrad kernel, the bias gradient a column sum; y (the stored activation) supplies the LeakyReLU mask.
+int HpvgConv3dBiasLReluGrad(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes, void* stream,
+                            void* /*extra*/) {
+  if (nparam != 7 || !all_f32(7, dtypes) || ndims[0] != 5 || ndims[1] != 5 || ndims[2] != 5 || ndims[3] != 5)
+    return aot_bad("conv grad: expects (x, w, y, dy) -> (dx, dw, db), float32");
   const int64_t* a = shapes[0];
-  if (a[1] != 64 || shapes[1][0] != 64 || shapes[1][1] != 64) return 2;
+  if (a[1] != 64 || shapes[1][0] != 64 || shapes[1][1] != 64 || shapes[2][1] != 64 || shapes[3][1] != 64 ||
+      shapes[4][1] != 64 || shapes[5][0] != 64 || shapes[6][0] != 64)
+    return aot_bad("conv grad: the 64 -> 64 layer only");
+  const int N = (int)a[0], T = (int)a[2], H = (int)a[3], W = (int)a[4];
+  const size_t vox = (size_t)N * T * H * W, act_b = vox * 128;
+  const size_t need = 4 * al(act_b) + al(hpvg_conv_wimg_bytes(HPVG_CONV_64_64)) + al(512);
+  void* wsp = arena_for(stream, need);
+  if (!wsp) return 3;
+  Carver cv(wsp);
+  void* xcl = cv.take<void>(act_b);
+  void* ycl = cv.take<void>(act_b);
+  void* gcl = cv.take<void>(act_b);      // dy, then gz = dy * LeakyReLU'(y) in place
+  void* dxcl = cv.take<void>(act_b);
+  void* wimg = cv.take<void>(hpvg_conv_wimg_bytes(HPVG_CONV_64_64));
+  float* aff = cv.take<float>(512);
+  const float* x = static_cast<const float*>(params[0]);
+  const float* w = static_cast<const float*>(params[1]);
+  int rc = hpvg_pack_cl(x, N, 64, T, H, W, xcl, 64, 0, 64, stream);
+  if (!rc) rc = hpvg_pack_cl(static_cast<const float*>(params[2]), N, 64, T, H, W, ycl, 64, 0, 64, stream);
+  if (!rc) rc = hpvg_pack_cl(static_cast<const float*>(params[3]), N, 64, T, H, W, gcl, 64, 0, 64, stream);
+  if (!rc) rc = hpvg_lrelu_bwd_cl(gcl, ycl, (long long)vox * 64, gcl, stream);
+  if (!rc) rc = hpvg_colsum_cl(gcl, (long long)vox, static_cast<float*>(params[6]), 0, stream);
+  if (!rc) rc = hpvg_conv_wgrad_cl(xcl, 64, gcl, 64, N, T, H, W, static_cast<float*>(params[5]), 64, 3, 0, 64, 0, 64, 0,
+                                   1.0f, stream);
+  if (!rc) rc = hpvg_conv_pack_weights(w, 64, 64, 3, HPVG_CONV_64_64, 1, 0, 64, 0, 64, wimg, stream);
+  if (!rc) rc = hpvg_fill(aff, 1.0f, 64, stream);
+  if (!rc) rc = hpvg_memset(aff + 64, 0, 256, stream);
+  if (!rc) rc = hpvg_conv_cl(HPVG_CONV_64_64, N, T, H, W, gcl, 64, wimg, aff, aff + 64, HPVG_ACT_NONE, HPVG_OUT_BF16_CL,
+                             dxcl, 64, 0, 64, nullptr, nullptr, nullptr, 0, stream);
+  if (!rc) rc = hpvg_unpack_cl(dxcl, N, 64, T, H, W, 64, 0, static_cast<float*>(params[4]), stream);
+  return rc;
+}
+
+// Training-mode nn.BatchNorm3d(64) + LeakyReLU (networks_3d.py:52-53):
+//   (x, gamma, beta, moving_mean, moving_var) -> (y, saved[4,64] = scale, shift, mean, invstd)
+// moving_mean / moving_var are updated IN PLACE (momentum 0.9), like the Parameters of the reference's cell.
+int HpvgBatchNorm3dLReluTrain(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes, void* stream,
+                              void* /*extra*/) {
+  if (nparam != 7 || !all_f32(7, dtypes) || ndims[0] != 5 || ndims[5] != 5 || shapes[0][1] != 64 || shapes[1][0] != 64 ||
+      ndims[6] != 2 || shapes[6][0] != 4 || shapes[6][1] != 64)
+    return aot_bad("batchnorm train: expects (x[N,64,T,H,W], gamma, beta, moving_mean, moving_var) -> (y, saved[4,64])");
+  const int64_t* a = shapes[0];
   const int N = (int)a[0], T = (int)a[2], H = (int)a[3], W = (int)a[4];
   const size_t vox = (size_t)N * T * H * W;
-  void *xcl = nullptr, *ycl = nullptr, *wimg = nullptr;
-  float *scale = nullptr;
-  int rc = 0;
-  if (cudaMalloc(&xcl, vox * 128) != cudaSuccess || cudaMalloc(&ycl, vox * 128) != cudaSuccess ||
-      cudaMalloc(&wimg, hpvg_conv_wimg_bytes(HPVG_CONV_64_64)) != cudaSuccess ||
-      cudaMalloc(&scale, 128 * sizeof(float)) != cudaSuccess)
-    rc = 3;
-  if (!rc) rc = hpvg_pack_cl(static_cast<const float*>(params[0]), N, 64, T, H, W, xcl, 64, 0, 64, stream);
-  if (!rc) rc = hpvg_conv_pack_weights(static_cast<const float*>(params[1]), 64, 64, 3, HPVG_CONV_64_64, 0, 0, 64, 0,
-                                       64, wimg, stream);
-  if (!rc) rc = hpvg_affine_from_bias(static_cast<const float*>(params[2]), nullptr, 64, scale, scale + 64, stream);
-  if (!rc) rc = hpvg_conv_cl(HPVG_CONV_64_64, N, T, H, W, xcl, 64, wimg, scale, scale + 64, HPVG_ACT_LRELU,
-                             HPVG_OUT_BF16_CL, ycl, 64, 0, 64, nullptr, nullptr, nullptr, 0, stream);
-  if (!rc) rc = hpvg_unpack_cl(ycl, N, 64, T, H, W, 64, 0, static_cast<float*>(params[3]), stream);
-  cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
-  cudaFree(xcl); cudaFree(ycl); cudaFree(wimg); cudaFree(scale);
+  void* wsp = arena_for(stream, 2 * al(vox * 128) + al(1024));
+  if (!wsp) return 3;
+  Carver cv(wsp);
+  void* xcl = cv.take<void>(vox * 128);
+  void* ycl = cv.take<void>(vox * 128);
+  double* sums = cv.take<double>(1024);
+  int rc = hpvg_pack_cl(static_cast<const float*>(params[0]), N, 64, T, H, W, xcl, 64, 0, 64, stream);
+  if (!rc) rc = hpvg_bn_stats_cl(xcl, (long long)vox, sums, sums + 64, stream);
+  if (!rc) rc = hpvg_bn_train_apply_cl(xcl, (long long)vox, sums, static_cast<const float*>(params[1]),
+                                       static_cast<const float*>(params[2]), 1e-5f, 0.9f, static_cast<float*>(params[3]),
+                                       static_cast<float*>(params[4]), static_cast<float*>(params[6]), HPVG_ACT_LRELU, ycl,
+                                       stream);
+  if (!rc) rc = hpvg_unpack_cl(ycl, N, 64, T, H, W, 64, 0, static_cast<float*>(params[5]), stream);
   return rc;
+}
+// its bprop: (dy, x, saved) -> (dx, dgamma, dbeta)
+int HpvgBatchNorm3dLReluTrainGrad(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes,
+                                  void* stream, void* /*extra*/) {
+  if (nparam != 6 || !all_f32(6, dtypes) || ndims[0] != 5 || ndims[1] != 5 || shapes[0][1] != 64 || shapes[1][1] != 64 ||
+      ndims[2] != 2 || shapes[2][0] != 4 || shapes[2][1] != 64 || shapes[4][0] != 64 || shapes[5][0] != 64)
+    return aot_bad("batchnorm grad: expects (dy, x, saved[4,64]) -> (dx, dgamma[64], dbeta[64])");
+  const int64_t* a = shapes[0];
+  const int N = (int)a[0], T = (int)a[2], H = (int)a[3], W = (int)a[4];
+  const size_t vox = (size_t)N * T * H * W;
+  void* wsp = arena_for(stream, 3 * al(vox * 128));
+  if (!wsp) return 3;
+  Carver cv(wsp);
+  void* gcl = cv.take<void>(vox * 128);
+  void* xcl = cv.take<void>(vox * 128);
+  void* dxcl = cv.take<void>(vox * 128);
+  int rc = hpvg_pack_cl(static_cast<const float*>(params[0]), N, 64, T, H, W, gcl, 64, 0, 64, stream);
+  if (!rc) rc = hpvg_pack_cl(static_cast<const float*>(params[1]), N, 64, T, H, W, xcl, 64, 0, 64, stream);
+  if (!rc) rc = hpvg_bn_bwd_cl(gcl, xcl, (long long)vox, static_cast<const float*>(params[2]), HPVG_ACT_LRELU, dxcl,
+                               static_cast<float*>(params[4]), static_cast<float*>(params[5]), 0, stream);
+  if (!rc) rc = hpvg_unpack_cl(dxcl, N, 64, T, H, W, 64, 0, static_cast<float*>(params[3]), stream);
+  return rc;
+}
+
+// One power iteration of SpectualNormConv3d (spectral_norm.py:146-151): (w, u, v) -> (sigma2 = [sigma, 1/sigma], u', v')
+int HpvgSpectralNormIter(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes, void* stream,
+                         void* /*extra*/) {
+  if (nparam != 6 || !all_f32(6, dtypes) || ndims[0] < 2) return aot_bad("sn iter: expects (w, u, v) -> (sigma2, u', v')");
+  const int cout = (int)shapes[0][0];
+  long long k = 1;
+  for (int i = 1; i < ndims[0]; ++i) k *= shapes[0][i];
+  long long nu = 1, nv = 1;
+  for (int i = 0; i < ndims[1]; ++i) nu *= shapes[1][i];
+  for (int i = 0; i < ndims[2]; ++i) nv *= shapes[2][i];
+  if (nu != cout || nv != k || shapes[3][0] != 2) return aot_bad("sn iter: u must have Cout, v Cin*taps, sigma2 2 elements");
+  float* s2 = static_cast<float*>(params[3]);
+  int rc = hpvg_d2d(params[4], params[1], (size_t)nu * 4, stream);
+  if (!rc) rc = hpvg_d2d(params[5], params[2], (size_t)nv * 4, stream);
+  if (!rc) rc = hpvg_sn_power_iter(static_cast<const float*>(params[0]), cout, (int)k, static_cast<float*>(params[4]),
+                                   static_cast<float*>(params[5]), s2, s2 + 1, stream);
+  return rc;
+}
+
+// ClippedAdam step of ONE parameter tensor (optimizers.py:41-43 + mindspore.nn.Adam):
+//   (param, grad, m, v, hyper[6] = lr, beta1, beta2, eps, clip (0 = none), step (1-based)) -> (param', m', v')
+// hyper is a DEVICE tensor (MindSpore keeps the learning rate and the global step as Tensors).
+int HpvgClipAdam(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes, void* stream,
+                 void* /*extra*/) {
+  if (nparam != 8 || !all_f32(8, dtypes) || ndims[4] != 1 || shapes[4][0] != 6)
+    return aot_bad("clip adam: expects (param, grad, m, v, hyper[6]) -> (param', m', v'), float32");
+  long long n = 1;
+  for (int i = 0; i < ndims[0]; ++i) n *= shapes[0][i];
+  CTX(cx, stream);
+  int rc = hpvg_d2d(params[5], params[0], (size_t)n * 4, stream);
+  if (!rc) rc = hpvg_d2d(params[6], params[2], (size_t)n * 4, stream);
+  if (!rc) rc = hpvg_d2d(params[7], params[3], (size_t)n * 4, stream);
+  if (rc) return rc;
+  hpvg::AdamTable tab;
+  std::memset(&tab, 0, sizeof(tab));
+  tab.p[0] = static_cast<float*>(params[5]);
+  tab.g[0] = static_cast<const float*>(params[1]);
+  tab.m[0] = static_cast<float*>(params[6]);
+  tab.v[0] = static_cast<float*>(params[7]);
+  tab.n[0] = n;
+  KL(hpvg::ew_adam_clip(tab, 1, cx->adam_norms, 0.f, 0.f, 0.f, 1.f, 1.f, nullptr, S(stream),
+                        static_cast<const float*>(params[4])), 2);
+  return HPVG_OK;
+}
+
+// losses (losses.py:5-7, nn.MSELoss): (a, b) -> loss[1] ; (mu, logvar) -> loss[1]
+int HpvgMSELoss(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes, void* stream, void*) {
+  if (nparam != 3 || !all_f32(3, dtypes)) return aot_bad("mse: expects (a, b) -> loss[1]");
+  long long n = 1, m = 1;
+  for (int i = 0; i < ndims[0]; ++i) n *= shapes[0][i];
+  for (int i = 0; i < ndims[1]; ++i) m *= shapes[1][i];
+  if (n != m) return aot_bad("mse: operand sizes differ");
+  return hpvg_mse(static_cast<const float*>(params[0]), static_cast<const float*>(params[1]), n,
+                  static_cast<float*>(params[2]), stream);
+}
+int HpvgKLLoss(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes, void* stream, void*) {
+  if (nparam != 3 || !all_f32(3, dtypes)) return aot_bad("kl: expects (mu, logvar) -> loss[1]");
+  long long n = 1, m = 1;
+  for (int i = 0; i < ndims[0]; ++i) n *= shapes[0][i];
+  for (int i = 0; i < ndims[1]; ++i) m *= shapes[1][i];
+  if (n != m) return aot_bad("kl: operand sizes differ");
+  return hpvg_kl(static_cast<const float*>(params[0]), static_cast<const float*>(params[1]), n,
+                 static_cast<float*>(params[2]), stream);
 }
 
 }  // extern "C"

@@ -1455,10 +1455,18 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
   p = p - lr_t * m / (sqrtf(v) + eps);
 }
 
-__global__ void adam_apply_kernel(const AdamTable tab, const float* __restrict__ norms, float beta1, float beta2,
+__global__ void adam_apply_kernel(AdamTable tab, const float* __restrict__ norms, float beta1, float beta2,
                                   float eps, float bc /* sqrt(1-b2^t)/(1-b1^t) */, float clip,
-                                  const unsigned long long* __restrict__ d_step) {
-  if (d_step) {   // 1-based step lives on the device (CUDA-graph replays): same formula as the host path, in fp64
+                                  const unsigned long long* __restrict__ d_step, const float* __restrict__ d_hyper) {
+  if (d_hyper) {   // every hyper-parameter lives on the device (ops.Custom binding): lr, beta1, beta2, eps, clip, step
+    beta1 = d_hyper[1];
+    beta2 = d_hyper[2];
+    eps = d_hyper[3];
+    clip = d_hyper[4];
+    const double t = static_cast<double>(d_hyper[5]);
+    bc = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), t)) / (1.0 - pow(static_cast<double>(beta1), t)));
+    tab.lr[blockIdx.y] = d_hyper[0];
+  } else if (d_step) {   // 1-based step lives on the device (CUDA-graph replays): same formula as the host path, in fp64
     const double t = static_cast<double>(*d_step);
     bc = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), t)) / (1.0 - pow(static_cast<double>(beta1), t)));
   }
@@ -2150,7 +2158,8 @@ cudaError_t ew_reparam_bwd(const float* gz, const float* eps, const float* lv, l
   return cudaSuccess;
 }
 cudaError_t ew_adam_clip(const AdamTable& tab, int n_tensors, float* norms_scratch, float beta1, float beta2,
-                         float eps, float bias_corr, float clip, const unsigned long long* d_step, cudaStream_t st) {
+                         float eps, float bias_corr, float clip, const unsigned long long* d_step, cudaStream_t st,
+                         const float* d_hyper) {
   // blocks per tensor: enough to cover the largest tensor with ~2 float4 per thread, and to fill the 148 SMs
   long long nmax = 1;
   for (int i = 0; i < n_tensors; ++i) nmax = tab.n[i] > nmax ? tab.n[i] : nmax;
@@ -2165,7 +2174,7 @@ cudaError_t ew_adam_clip(const AdamTable& tab, int n_tensors, float* norms_scrat
     LAUNCH_CHECK();
   }
   adam_apply_kernel<<<dim3(gx, n_tensors), 256, 0, st>>>(tab, norms_scratch, beta1, beta2, eps, bias_corr, clip,
-                                                         d_step);
+                                                         d_step, d_hyper);
   LAUNCH_CHECK();
   return cudaSuccess;
 }

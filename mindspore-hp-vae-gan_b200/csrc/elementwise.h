@@ -78,7 +78,8 @@ cudaError_t ew_reparam_bwd(const float* gz, const float* eps, const float* lv, l
                            cudaStream_t st);
 cudaError_t ew_reparam(const float* mu, const float* lv, const float* eps, long long n, float* z, cudaStream_t st);
 cudaError_t ew_adam_clip(const AdamTable& tab, int n_tensors, float* norms_scratch, float beta1, float beta2,
-                         float eps, float bias_corr, float clip, const unsigned long long* d_step, cudaStream_t st);
+                         float eps, float bias_corr, float clip, const unsigned long long* d_step, cudaStream_t st,
+                         const float* d_hyper = nullptr /* device (lr, beta1, beta2, eps, clip, step) overriding all */);
 
 cudaError_t ew_lrelu_bwd_cl(const __nv_bfloat16* ga, const __nv_bfloat16* a, long long elems, __nv_bfloat16* gz,
                             cudaStream_t st);

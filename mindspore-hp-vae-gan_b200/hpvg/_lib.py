@@ -39,6 +39,8 @@ _SIGS = {
     "hpvg_d2h": ([vp, vp, c_size_t, vp], c_int),
     "hpvg_d2d": ([vp, vp, c_size_t, vp], c_int),
     "hpvg_stream_create": ([POINTER(vp)], c_int),
+    "hpvg_stream_attach": ([vp], c_int),
+    "hpvg_stream_detach": ([vp], c_int),
     "hpvg_stream_destroy": ([vp], c_int),
     "hpvg_stream_sync": ([vp], c_int),
     "hpvg_device_sync": ([], c_int),
@@ -111,7 +113,9 @@ _SIGS = {
                               f, i, f, vp, vp], c_int),
 }
 # MindSpore ops.Custom(func_type="aot") entry points
-_AOT = ["HpvgUpsampleTrilinear3D", "HpvgUpsampleTrilinear3DGrad", "HpvgConv3dBiasLRelu"]
+_AOT = ["HpvgUpsampleTrilinear3D", "HpvgUpsampleTrilinear3DGrad", "HpvgConv3dBias", "HpvgConv3dBiasLRelu",
+        "HpvgConv3dBiasTanh", "HpvgConv3dBiasLReluGrad", "HpvgBatchNorm3dLReluTrain", "HpvgBatchNorm3dLReluTrainGrad",
+        "HpvgSpectralNormIter", "HpvgClipAdam", "HpvgMSELoss", "HpvgKLLoss"]
 
 EXPORTED = list(_SIGS) + _AOT
 
