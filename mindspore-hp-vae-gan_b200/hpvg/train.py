@@ -198,6 +198,48 @@ def _dgrad_wimgs(layer, stream=None):
     return imgs
 
 
+# ------------------------------------------------------------------------------------------------ backward branches
+# Inside one layer's backward the weight gradient (wgrad kernel [+ the spectral-norm chain rule]) and the data gradient
+# (dgrad conv -> the layer below) only share their INPUTS.  At the coarse scales every kernel is a few microseconds and
+# the iteration is one long dependency chain (BASELINE config 2: 329 launches), so the weight-gradient work is issued on
+# side streams — captured as parallel branches of the iteration's CUDA graph — and the chain that remains is
+# BN-backward -> dgrad per layer.  A layer always maps to the same side stream, so repeated accumulations into one
+# weight gradient stay ordered; the library's reduction scratch is per stream (csrc/api.cu).  The branch set is joined
+# before the optimiser reads the gradients (GWithLoss.grad).
+class WgradBranches:
+    def __init__(self, main, sides):
+        self.main, self.sides, self._slot, self._keep, self._used = main, list(sides), {}, [], set()
+
+    def stream_for(self, layer):
+        """Side stream of `layer`, made to wait for everything enqueued on the main stream so far."""
+        i = self._slot.setdefault(id(layer), len(self._slot) % len(self.sides))
+        side = self.sides[i]
+        ev = Event()
+        ev.record(self.main)
+        side.wait_event(ev)
+        self._keep.append(ev)
+        self._used.add(i)
+        return side
+
+    def join(self):
+        for i in sorted(self._used):
+            ev = Event()
+            ev.record(self.sides[i])
+            self.main.wait_event(ev)
+            self._keep.append(ev)
+        self._used = set()
+
+
+_BRANCHES = [None]
+
+
+def _wgrad_stream(layer, stream):
+    br = _BRANCHES[0]
+    if br is None or stream is not br.main:
+        return stream
+    return br.stream_for(layer)
+
+
 def conv_backward(layer, ctx, gy_cl, grads, ws, key, need_dx=True, want_dw=True, inv_sigma_aff=None, stream=None,
                   dw_target=None, mask_input=False, dx_out=None):
     """Backward of the convolution of `layer` given gy (bf16 cl, Cout channels [zero padded to 64 for tails]).
@@ -212,10 +254,11 @@ def conv_backward(layer, ctx, gy_cl, grads, ws, key, need_dx=True, want_dw=True,
     if want_dw:
         dw = dw_target if dw_target is not None else grads.of(w)
         xw = ctx.get("x_wide", x_cl)             # head convs: the 64-channel zero-padded copy of the 8-channel input
+        wst = ctx["wg_stream"] = _wgrad_stream(layer, stream)
         for ob in range(max(1, cout // 64)):
             for ib in range(max(1, cin // 64)):
                 ops.conv_wgrad_cl(xw, gy_cl, dw, co_off=ob * 64, co_n=min(cout, 64), ci_off=ib * 64,
-                                  ci_n=min(cin, 64), x_coff=ib * 64, gy_coff=ob * 64, accumulate=True, stream=stream)
+                                  ci_n=min(cin, 64), x_coff=ib * 64, gy_coff=ob * 64, accumulate=True, stream=wst)
     if not need_dx:
         return None
     imgs = _dgrad_wimgs(layer, stream)
@@ -263,9 +306,9 @@ def layer_backward(layer, ctx, ga_cl, grads, ws, key, need_dx=True, trainable=Tr
         ghat = ws.get(key + ".ghat", layer.p["weight"].shape, F32).zero_(stream)
         dx = conv_backward(layer, ctx, gz, grads, ws, key, need_dx, trainable, inv_sigma_aff=ctx["aff"],
                            stream=stream, dw_target=ghat, mask_input=mask_input)
-        if trainable:
+        if trainable:     # on the stream that produced ghat (a side branch when branches are active)
             ops.sn_grad(ghat, layer.p["weight"], ctx["u"], ctx["v"], ctx["sigma"], grads.of(layer.p["weight"]),
-                        accumulate=True, stream=stream)
+                        accumulate=True, stream=ctx.get("wg_stream", stream))
         return dx
     return conv_backward(layer, ctx, gz, grads, ws, key, need_dx, trainable, stream=stream, mask_input=mask_input)
 
@@ -372,7 +415,7 @@ class GeneratorTrainer:
                 layer._prepare(True, stream)
 
     def forward(self, video, noise_amp, noise_init=None, is_random=False, noises=None, eps=None, z_pred=None,
-                save_from=None, save_decoder=False, save_encoder=False, stream=None, defer_bn=False):
+                save_from=None, save_decoder=False, save_encoder=False, stream=None, defer_bn=False, enc_stream=None):
         """networks_3d.py:406-451 in set_train() mode.  Contexts are kept for the encoder / decoder when asked and
         for body stages with index >= save_from.  Returns dict(x, vae_out, mu, logvar, ctx...).
         defer_bn: do not touch the BatchNorm moving statistics; out["bn_deferred"] lists the pending updates."""
@@ -388,23 +431,38 @@ class GeneratorTrainer:
         if self.device_rng:
             ops.counter_add(self.draws, n_draw, stream)
         if noise_init is None:
+            # enc_stream: with is_training=False (the reference's drivers, Q2) z is pure noise, so the encoder pass is
+            # independent of the decoder / refinement pass and may run next to it on its own stream; the caller joins
+            es = stream
+            if enc_stream is not None and enc_stream is not stream:
+                es = enc_stream
+                fork = Event()
+                fork.record(stream)
+                es.wait_event(fork)
+                out["enc_events"] = [fork]
+            out["enc_stream"] = es
             enc = net.encode
-            sn_tape_prepare(enc._features.layers, ws, "enc", stream)
-            x_cl = ops.pack_cl(video, c_pitch=ops.narrow_pitch(), stream=stream)
+            sn_tape_prepare(enc._features.layers, ws, "enc", es)
+            x_cl = ops.pack_cl(video, c_pitch=ops.narrow_pitch(), stream=es)
             ectx = []
             h = x_cl
             xw = None
             if save_encoder:
                 xw = x_cl
             for i, l in enumerate(enc._features.layers):
-                h, c = layer_forward_train(l, h, ws, "enc.%d" % i, stream)
+                h, c = layer_forward_train(l, h, ws, "enc.%d" % i, es)
                 if i == 0 and xw is not None:
                     c["x_wide"] = xw
                 ectx.append(c)
-            mu_cl, cm = layer_forward_train(enc._mu, h, ws, "enc.mu", stream)
-            lv_cl, cl = layer_forward_train(enc._logvar, h, ws, "enc.lv", stream)
-            mu, logvar = ops.unpack_cl(mu_cl, stream=stream), ops.unpack_cl(lv_cl, stream=stream)
+            mu_cl, cm = layer_forward_train(enc._mu, h, ws, "enc.mu", es)
+            lv_cl, cl = layer_forward_train(enc._logvar, h, ws, "enc.lv", es)
+            mu, logvar = ops.unpack_cl(mu_cl, stream=es), ops.unpack_cl(lv_cl, stream=es)
             out.update(enc_ctx=ectx, mu_ctx=cm, lv_ctx=cl)
+            if es is not stream and net.is_training:      # z = eps*exp(.5 logvar)+mu needs the encoder's result
+                ev = Event()
+                ev.record(es)
+                stream.wait_event(ev)
+                out["enc_events"].append(ev)
             if net.is_training:
                 if eps is None:
                     eps = self._draw(mu.shape, stream)
@@ -441,6 +499,8 @@ class GWithLoss:
         self.trainer = GeneratorTrainer(netG, device_rng, salt=1)
         self.grads = GradBook()
         self.terms = LossTerms()
+        self.wgrad_sides = None      # side streams for the weight-gradient branches (set by GraphedIteration.capture)
+        self.enc_side = None         # side stream for the VAE-phase encoder pass (forward, KL term, backward)
 
     def recon_forward_args(self, isVAE, trainable_body, train_codec=False):
         """Keyword arguments of the reconstruction forward that grad() runs (for callers that run it themselves)."""
@@ -473,10 +533,24 @@ class GWithLoss:
         g = self.grads
         g.zero(stream)
         nb = len(net.body)
+        if self.wgrad_sides and stream is not None:
+            _BRANCHES[0] = WgradBranches(stream, self.wgrad_sides)
+        try:
+            return self._grad(real, real_zero, noise_init, noise_amps, isVAE, trainable_body, train_codec, noises,
+                              z_pred, eps, stream, finish, recon_fw, random_x, wait_recon, wait_random)
+        finally:
+            _BRANCHES[0] = None
+
+    def _grad(self, real, real_zero, noise_init, noise_amps, isVAE, trainable_body, train_codec, noises, z_pred, eps,
+              stream, finish, recon_fw, random_x, wait_recon, wait_random):
+        net, opt, tr = self._netG, self.opt, self.trainer
+        g = self.grads
+        nb = len(net.body)
         codec_bw, enc_bw, save_from = self._plan(isVAE, trainable_body, train_codec)
         if recon_fw is None:
             fw = tr.forward(real_zero, noise_amps, is_random=False, z_pred=z_pred, eps=eps, save_from=save_from,
-                            save_encoder=enc_bw, stream=stream)
+                            save_encoder=enc_bw, stream=stream,
+                            enc_stream=self.enc_side if (isVAE and stream is not None) else None)
         else:
             fw = recon_fw
             if wait_recon is not None:
@@ -490,7 +564,7 @@ class GWithLoss:
         g_x = ops.mse_grad(x, real, self.rec_weight * 2.0 / n, g=ws.get("g_x", x.shape, F32), stream=stream)
         if isVAE:
             ops.mse(vae_out, real_zero, out=terms.slot(self.rec_weight), stream=stream)
-            ops.kl_criterion(fw["mu"], fw["logvar"], out=terms.slot(self.kl_weight), stream=stream)
+            ops.kl_criterion(fw["mu"], fw["logvar"], out=terms.slot(self.kl_weight), stream=fw.get("enc_stream", stream))
         # ---- backward through the refinement stages (networks_3d.py:434-451)
         g_cur = g_x
         lowest = save_from
@@ -529,18 +603,30 @@ class GWithLoss:
             # reparameterised z, i.e. only with is_training=True (Q2: the reference's drivers leave it False, then z is
             # pure noise)
             mu, lv = fw["mu"], fw["logvar"]
-            gmu, glv = ops.kl_grad(mu, lv, (self.kl_weight / mu.size) if isVAE else 0.0, stream=stream)
+            es = fw.get("enc_stream", stream) or stream      # the encoder's own branch when it ran on a side stream
+            if es is not stream and net.is_training:          # the reparameterisation gradient comes from the decoder
+                ev = Event()
+                ev.record(stream)
+                es.wait_event(ev)
+                fw["enc_events"].append(ev)
+            gmu, glv = ops.kl_grad(mu, lv, (self.kl_weight / mu.size) if isVAE else 0.0, stream=es)
             if net.is_training:
-                g_z = ops.unpack_cl(g_z_cl, stream=stream)
-                ops.reparam_bwd(g_z, fw["eps"], lv, gmu, glv, stream=stream)
-            gmu_cl, glv_cl = ops.pack_cl(gmu, stream=stream), ops.pack_cl(glv, stream=stream)
+                g_z = ops.unpack_cl(g_z_cl, stream=es)
+                ops.reparam_bwd(g_z, fw["eps"], lv, gmu, glv, stream=es)
+            gmu_cl, glv_cl = ops.pack_cl(gmu, stream=es), ops.pack_cl(glv, stream=es)
             enc = net.encode
-            d1 = layer_backward(enc._mu, fw["mu_ctx"], gmu_cl, g, ws, "enc.mu", True, train_codec, stream)
-            d2 = layer_backward(enc._logvar, fw["lv_ctx"], glv_cl, g, ws, "enc.lv", True, train_codec, stream)
-            ga = _add_cl(d1, d2, ws, stream)
+            d1 = layer_backward(enc._mu, fw["mu_ctx"], gmu_cl, g, ws, "enc.mu", True, train_codec, es)
+            d2 = layer_backward(enc._logvar, fw["lv_ctx"], glv_cl, g, ws, "enc.lv", True, train_codec, es)
+            ga = _add_cl(d1, d2, ws, es)
             for i in range(len(enc._features.layers) - 1, -1, -1):
                 ga = layer_backward(enc._features.layers[i], fw["enc_ctx"][i], ga, g, ws, "enc.%d" % i, i > 0,
-                                    train_codec, stream)
+                                    train_codec, es)
+            if es is not stream:      # join: the loss terms and the optimiser read what the encoder branch wrote
+                ev = Event()
+                ev.record(es)
+                stream.wait_event(ev)
+                fw["enc_events"].append(ev)
+                self._enc_keep = fw["enc_events"]
         if not isVAE:
             # ---- adversarial term: value only, no gradient reaches G (Q1, losses.py:93-98)
             if random_x is None:
@@ -550,6 +636,9 @@ class GWithLoss:
                 stream.wait_event(wait_random)
             d_out = self._netD(random_x, stream=stream)
             ops.mean(d_out, out=terms.slot(-self.disc_loss_weight), stream=stream)
+        if _BRANCHES[0] is not None:
+            self._branch_keep = _BRANCHES[0]      # events stay alive as long as a graph captured from this call
+            _BRANCHES[0].join()                   # the optimiser reads the gradients next
         return (terms.finish(stream) if finish else terms), g
 
 
@@ -844,12 +933,18 @@ class GraphedIteration:
         self.stream.sync()
         return out
 
-    def capture(self, concurrent=True):
+    def capture(self, concurrent=True, wgrad_branches=2):
+        """wgrad_branches: number of side streams the G step's weight-gradient kernels are spread over (0 = all on the
+        main stream)."""
         from ._lib import lib
         from .runtime import Stream
         n0 = lib.hpvg_launch_count()
         if concurrent and self.d_step is not None and self.side is None:
             self.side = (Stream(), Stream(), Stream())
+        if self.d_step is None and concurrent and self.g_step.network.enc_side is None:
+            self.g_step.network.enc_side = Stream()
+        if wgrad_branches and self.g_step.network.wgrad_sides is None:
+            self.g_step.network.wgrad_sides = tuple(Stream() for _ in range(int(wgrad_branches)))
         self.graph = Graph(self.stream)
         with self.graph:
             self._terms = self._body(False, concurrent=concurrent and self.d_step is not None)
