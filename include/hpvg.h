@@ -110,6 +110,11 @@ int hpvg_conv_wimg_bytes(int mode);
  * transpose_flip = 1 packs the data-gradient filter (roles of cin/cout swapped, taps mirrored). */
 int hpvg_conv_pack_weights(const float* d_w, int w_cout, int w_cin, int kt, int mode, int transpose_flip,
                            int cout_off, int cout, int cin_off, int cin, void* d_wimg, void* stream);
+/* n banks in ONE launch (arrays of length n on the host; bf16 variants only).  mode[i] < 0 marks an epilogue-vector
+ * entry instead of a filter bank: d_w[i] = bias (cout[i] values, nullable), d_wimg[i] = fp32 [2][64] := (1, bias). */
+int hpvg_conv_pack_weights_multi(int n, const float* const* d_w, const int* w_cout, const int* w_cin, const int* kt,
+                                 const int* mode, const int* transpose_flip, const int* cout_off, const int* cout,
+                                 const int* cin_off, const int* cin, void* const* d_wimg, void* stream);
 /* y = act((conv(x) [+ addend_raw]) * scale + shift [+ residual]) ; see HPVG_OUT_* for the output layouts.
  *  d_in     bf16 cl, in_pitch channels per voxel (the kernel reads 64 — or 8 — channels starting at d_in)
  *  d_scale/d_shift fp32 [Cout]: bias, folded BatchNorm, 1/sigma of spectral norm

@@ -10,6 +10,7 @@
 #include <mutex>
 #include <string>
 #include <unordered_map>
+#include <vector>
 
 #include "../../include/hpvg.h"
 #include "conv3d_umma.h"
@@ -307,6 +308,23 @@ int hpvg_conv_pack_weights(const float* w, int w_cout, int w_cin, int kt, int mo
   return HPVG_OK;
 }
 
+int hpvg_conv_pack_weights_multi(int n, const float* const* w, const int* w_cout, const int* w_cin, const int* kt,
+                                 const int* mode, const int* transpose_flip, const int* cout_off, const int* cout,
+                                 const int* cin_off, const int* cin, void* const* wimg, void* st) {
+  if (n <= 0) return HPVG_OK;
+  std::vector<hpvg::PackEntry> es(n);
+  for (int i = 0; i < n; ++i) {
+    hpvg::PackEntry& e = es[i];
+    e.w = w[i]; e.img = wimg[i]; e.cout = cout[i]; e.cin = cin[i]; e.kt = kt[i]; e.mode = mode[i];
+    e.flip = transpose_flip[i]; e.cin_off = cin_off[i]; e.cout_off = cout_off[i]; e.w_cout = w_cout[i];
+    e.w_cin = w_cin[i]; e.total = 0;
+    if (!e.img || (e.mode >= 0 && !e.w)) return fail(HPVG_E_ARG, "conv_pack_weights_multi: null pointer");
+  }
+  const char* err = hpvg::conv3d_pack_weights_multi(es.data(), n, S(st));
+  if (err) return fail(HPVG_E_CUDA, std::string("conv_pack_weights_multi: ") + err);
+  g_launches += (n + hpvg::PACK_MAX_ENTRIES - 1) / hpvg::PACK_MAX_ENTRIES;
+  return HPVG_OK;
+}
 int hpvg_conv_cl(int mode, int N, int T, int H, int W, const void* in, int in_pitch, const void* wimg,
                  const float* scale, const float* shift, int act, int out_mode, void* out, int out_pitch,
                  int out_coff, int cout_real, const float* addend, double* stats, const void* mask, int mask_pitch,
@@ -594,7 +612,7 @@ int hpvg_bn_bwd_cl_f32(const float* ga, const float* y, long long voxels, const 
                        float* dgamma, float* dbeta, int accumulate, void* st) {
   if (voxels <= 0) return fail(HPVG_E_ARG, "bn_bwd: empty batch");
   CTX(cx, st);
-  KL(hpvg::ew_bn_bwd_cl_f32(ga, y, voxels, saved, act, cx->sums, gy, dgamma, dbeta, accumulate, S(st)), 4);
+  KL(hpvg::ew_bn_bwd_cl_f32(ga, y, voxels, saved, act, cx->sums, gy, dgamma, dbeta, accumulate, S(st)), 2);
   return HPVG_OK;
 }
 int hpvg_colsum_cl_f32(const float* g, long long voxels, float* out, int accumulate, void* st) {
@@ -625,7 +643,7 @@ int hpvg_bn_bwd_cl(const void* ga, const void* y, long long voxels, const float*
   if (voxels <= 0) return fail(HPVG_E_ARG, "bn_bwd: empty batch");
   CTX(cx, st);
   KL(hpvg::ew_bn_bwd_cl(static_cast<const __nv_bfloat16*>(ga), static_cast<const __nv_bfloat16*>(y), voxels, saved,
-                        act, cx->sums, static_cast<__nv_bfloat16*>(gy), dgamma, dbeta, accumulate, S(st)), 4);
+                        act, cx->sums, static_cast<__nv_bfloat16*>(gy), dgamma, dbeta, accumulate, S(st)), 2);
   return HPVG_OK;
 }
 int hpvg_colsum_cl(const void* g, long long voxels, float* out, int accumulate, void* st) {

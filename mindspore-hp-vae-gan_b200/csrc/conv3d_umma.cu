@@ -797,12 +797,10 @@ int conv3d_umma_wimg_bytes(int mode) {
 // Filter-bank packing: fp32 (Cout, Cin, 3,3,3) [or (Cout,Cin,3,3) with kt==1] -> the per-CTA shared-memory image the
 // conv kernel bulk-copies.  transpose_flip=1 packs the data-gradient filter (Cin<->Cout swapped, taps mirrored).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin, int kt, int mode,
-                                    int transpose_flip, int cin_off, int cout_off, int w_cout, int w_cin,
-                                    __nv_bfloat16* __restrict__ img, int total) {
+__device__ __forceinline__ void pack_weights_element(const float* __restrict__ w, int cout, int cin, int kt, int mode,
+                                                     int transpose_flip, int cin_off, int cout_off, int w_cout,
+                                                     int w_cin, __nv_bfloat16* __restrict__ img, int idx) {
   // one thread per bf16 element of the image
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
   int rank, tap, row, ci;
   float val = 0.f;
   bool valid = true;
@@ -894,6 +892,31 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int c
   }
   (void)w_cout;
   img[idx] = __float2bfloat16_rn(val);
+}
+
+__global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin, int kt, int mode,
+                                    int transpose_flip, int cin_off, int cout_off, int w_cout, int w_cin,
+                                    __nv_bfloat16* __restrict__ img, int total) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < total)
+    pack_weights_element(w, cout, cin, kt, mode, transpose_flip, cin_off, cout_off, w_cout, w_cin, img, idx);
+}
+
+// Many banks (and epilogue-vector pairs) in ONE launch: at the coarse scales of the pyramid an iteration repacks ~45
+// filter banks of its trainable layers, each a 3-4 us launch on the critical path of a launch-latency-bound step.
+// blockIdx.y selects the table entry; mode < 0 marks an "affine" entry: img = fp32 [2][64] = (1 | 1/sigma, bias).
+__global__ void pack_weights_multi_kernel(const __grid_constant__ PackTable tab) {
+  const PackEntry& e = tab.e[blockIdx.y];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= e.total) return;
+  if (e.mode < 0) {
+    float* out = static_cast<float*>(e.img);
+    const int c = idx & 63;
+    out[idx] = (idx < 64) ? 1.0f : ((c < e.cout && e.w) ? e.w[c] : 0.f);
+    return;
+  }
+  pack_weights_element(e.w, e.cout, e.cin, e.kt, e.mode, e.flip, e.cin_off, e.cout_off, e.w_cout, e.w_cin,
+                       static_cast<__nv_bfloat16*>(e.img), idx);
 }
 
 // The same images for the kind::tf32 variants: fp32 elements rounded to tf32, 32 input channels per 128-byte row
@@ -988,6 +1011,31 @@ const char* conv3d_pack_weights(const float* w, int w_cout, int w_cin, int kt, i
                                                                 static_cast<__nv_bfloat16*>(img), total);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+const char* conv3d_pack_weights_multi(const PackEntry* entries, int n, cudaStream_t stream) {
+  for (int base = 0; base < n; base += PACK_MAX_ENTRIES) {
+    PackTable tab;
+    const int cnt = (n - base < PACK_MAX_ENTRIES) ? n - base : PACK_MAX_ENTRIES;
+    int max_total = 0;
+    for (int i = 0; i < cnt; ++i) {
+      tab.e[i] = entries[base + i];
+      PackEntry& e = tab.e[i];
+      if (e.mode < 0) {
+        e.total = 128;
+      } else {
+        if (conv_mode_is_tf32(e.mode)) return "pack_weights_multi: bf16 kernel variants only";
+        if (e.kt != 1 && e.kt != 3) return "kernel depth must be 1 or 3";
+        e.total = conv3d_umma_wimg_bytes(e.mode) / 2;
+        if (e.total == 0) return "unknown conv mode";
+      }
+      max_total = e.total > max_total ? e.total : max_total;
+    }
+    pack_weights_multi_kernel<<<dim3((max_total + 255) / 256, cnt), 256, 0, stream>>>(tab);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+  }
+  return nullptr;
 }
 
 }  // namespace hpvg

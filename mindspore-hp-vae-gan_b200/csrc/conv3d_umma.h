@@ -67,6 +67,18 @@ const char* conv3d_pack_weights(const float* w, int w_cout, int w_cin, int kt, i
 
 // 64 -> (<= 3) tail convolution with the in-plane taps folded into N (conv3d_tail.cu); uses ConvLaunch with
 // mode == CONV_MODE_64_T, out_mode == CONV_OUT_F32_NCDHW
+// table-driven packing of many filter banks in one launch (bf16 variants); mode < 0: an (1, bias) epilogue-vector pair
+struct PackEntry {
+  const float* w;      // weights (Cout, Cin, kt, 3, 3) — or the bias vector for an affine entry
+  void* img;           // packed image (bf16) — or fp32 [2][64] for an affine entry
+  int cout, cin, kt, mode, flip, cin_off, cout_off, w_cout, w_cin, total;
+};
+constexpr int PACK_MAX_ENTRIES = 64;
+struct PackTable {
+  PackEntry e[PACK_MAX_ENTRIES];
+};
+const char* conv3d_pack_weights_multi(const PackEntry* entries, int n, cudaStream_t stream);
+
 const char* conv3d_tail_launch(const ConvLaunch& L, int sm_count, cudaStream_t stream);
 int conv3d_tail_wimg_bytes();
 

@@ -1455,7 +1455,7 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
   p = p - lr_t * m / (sqrtf(v) + eps);
 }
 
-__global__ void adam_apply_kernel(AdamTable tab, const float* __restrict__ norms, float beta1, float beta2,
+__global__ void adam_apply_kernel(const AdamTable tab, const float* __restrict__ norms, float beta1, float beta2,
                                   float eps, float bc /* sqrt(1-b2^t)/(1-b1^t) */, float clip,
                                   const unsigned long long* __restrict__ d_step, const float* __restrict__ d_hyper) {
   if (d_hyper) {   // every hyper-parameter lives on the device (ops.Custom binding): lr, beta1, beta2, eps, clip, step
@@ -1465,7 +1465,6 @@ __global__ void adam_apply_kernel(AdamTable tab, const float* __restrict__ norms
     clip = d_hyper[4];
     const double t = static_cast<double>(d_hyper[5]);
     bc = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), t)) / (1.0 - pow(static_cast<double>(beta1), t)));
-    tab.lr[blockIdx.y] = d_hyper[0];
   } else if (d_step) {   // 1-based step lives on the device (CUDA-graph replays): same formula as the host path, in fp64
     const double t = static_cast<double>(*d_step);
     bc = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), t)) / (1.0 - pow(static_cast<double>(beta1), t)));
@@ -1476,7 +1475,8 @@ __global__ void adam_apply_kernel(AdamTable tab, const float* __restrict__ norms
   float* __restrict__ m = tab.m[t];
   float* __restrict__ v = tab.v[t];
   const long long n = tab.n[t];
-  const float lr_t = tab.lr[t] * bc;
+  // (the table is a kernel PARAMETER: it is only ever read — a dynamic write would force a per-thread local copy of it)
+  const float lr_t = (d_hyper ? d_hyper[0] : tab.lr[t]) * bc;
   float coef = 1.0f;
   if (clip > 0.f) coef = clip / fmaxf(sqrtf(norms[t]), clip);   // ClipByNorm: g*c / max(||g||, c)
   const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
@@ -1606,7 +1606,8 @@ __device__ __forceinline__ uint32_t pack2_sr(float lo, float hi, uint32_t key) {
 __global__ void bn_bwd_apply_cl_kernel(const __nv_bfloat16* __restrict__ ga, const __nv_bfloat16* __restrict__ y,
                                        long long groups, const float* __restrict__ saved, int act,
                                        const double* __restrict__ sums, double inv_count,
-                                       __nv_bfloat16* __restrict__ gy) {
+                                       __nv_bfloat16* __restrict__ gy, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, int accumulate) {
   __shared__ float sc[64], sh[64], mu[64], is[64], m0[64], m1[64];
   if (threadIdx.x < 64) {
     const int c = threadIdx.x;
@@ -1616,6 +1617,10 @@ __global__ void bn_bwd_apply_cl_kernel(const __nv_bfloat16* __restrict__ ga, con
     is[c] = saved[192 + c];
     m0[c] = static_cast<float>(sums[c] * inv_count);
     m1[c] = static_cast<float>(sums[64 + c] * inv_count);
+    if (blockIdx.x == 0) {   // dbeta = sum gz, dgamma = sum gz*xhat: written here instead of by two more launches
+      if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + static_cast<float>(sums[c]);
+      if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + static_cast<float>(sums[64 + c]);
+    }
   }
   __syncthreads();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < groups;
@@ -2193,16 +2198,9 @@ cudaError_t ew_bn_bwd_cl(const __nv_bfloat16* ga, const __nv_bfloat16* y, long l
   bn_bwd_reduce_cl_kernel<<<grid_for(voxels, 32, 148 * 8), 256, 0, st>>>(ga, y, voxels, saved, act, sums);
   LAUNCH_CHECK();
   bn_bwd_apply_cl_kernel<<<grid_for(voxels * 8, 256), 256, 0, st>>>(ga, y, voxels * 8, saved, act, sums,
-                                                                    1.0 / static_cast<double>(voxels), gy);
+                                                                    1.0 / static_cast<double>(voxels), gy, dgamma, dbeta,
+                                                                    accumulate);
   LAUNCH_CHECK();
-  if (dbeta) {
-    d2f_kernel<<<1, 64, 0, st>>>(sums, 64, 1.f, accumulate, dbeta);
-    LAUNCH_CHECK();
-  }
-  if (dgamma) {
-    d2f_kernel<<<1, 64, 0, st>>>(sums + 64, 64, 1.f, accumulate, dgamma);
-    LAUNCH_CHECK();
-  }
   return cudaSuccess;
 }
 cudaError_t ew_colsum_cl(const __nv_bfloat16* g, long long voxels, double* scratch, float* out, int accumulate,

@@ -283,7 +283,8 @@ __device__ __forceinline__ float tf32_sr(float v, uint32_t key) {
 // pass 2: gy = gamma*invstd*(gz - mean(gz) - xhat*mean(gz*xhat))
 __global__ void bn_bwd_apply_cl_f32_kernel(const float* __restrict__ ga, const float* __restrict__ y, long long groups,
                                            const float* __restrict__ saved, int act, const double* __restrict__ sums,
-                                           double inv_count, float* __restrict__ gy) {
+                                           double inv_count, float* __restrict__ gy, float* __restrict__ dgamma,
+                                           float* __restrict__ dbeta, int accumulate) {
   __shared__ float sc[64], sh[64], mu[64], is[64], m0[64], m1[64];
   if (threadIdx.x < 64) {
     const int c = threadIdx.x;
@@ -293,6 +294,10 @@ __global__ void bn_bwd_apply_cl_f32_kernel(const float* __restrict__ ga, const f
     is[c] = saved[192 + c];
     m0[c] = static_cast<float>(sums[c] * inv_count);
     m1[c] = static_cast<float>(sums[64 + c] * inv_count);
+    if (blockIdx.x == 0) {
+      if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + static_cast<float>(sums[c]);
+      if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + static_cast<float>(sums[64 + c]);
+    }
   }
   __syncthreads();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < groups;
@@ -389,16 +394,9 @@ cudaError_t ew_bn_bwd_cl_f32(const float* ga, const float* y, long long voxels, 
   bn_bwd_reduce_cl_f32_kernel<<<grid_for(voxels, 16, 148 * 8), 256, 0, st>>>(ga, y, voxels, saved, act, sums);
   LAUNCH_CHECK();
   bn_bwd_apply_cl_f32_kernel<<<grid_for(voxels * 16, 256), 256, 0, st>>>(ga, y, voxels * 16, saved, act, sums,
-                                                                         1.0 / static_cast<double>(voxels), gy);
+                                                                         1.0 / static_cast<double>(voxels), gy, dgamma,
+                                                                         dbeta, accumulate);
   LAUNCH_CHECK();
-  if (dbeta) {
-    d2f_f32_kernel<<<1, 64, 0, st>>>(sums, 64, 1.f, accumulate, dbeta);
-    LAUNCH_CHECK();
-  }
-  if (dgamma) {
-    d2f_f32_kernel<<<1, 64, 0, st>>>(sums + 64, 64, 1.f, accumulate, dgamma);
-    LAUNCH_CHECK();
-  }
   return cudaSuccess;
 }
 cudaError_t ew_colsum_cl_f32(const float* g, long long voxels, double* scratch, float* out, int accumulate,

@@ -59,6 +59,8 @@ _SIGS = {
     "hpvg_unpack_cl": ([vp, i, i, i, i, i, i, i, vp, vp], c_int),
     "hpvg_conv_wimg_bytes": ([i], c_int),
     "hpvg_conv_pack_weights": ([vp, i, i, i, i, i, i, i, i, i, vp, vp], c_int),
+    "hpvg_conv_pack_weights_multi": ([i, POINTER(vp), POINTER(i), POINTER(i), POINTER(i), POINTER(i), POINTER(i), POINTER(i),
+                                      POINTER(i), POINTER(i), POINTER(i), POINTER(vp), vp], c_int),
     "hpvg_conv_cl": ([i, i, i, i, i, vp, i, vp, vp, vp, i, i, vp, i, i, i, vp, vp, vp, i, vp], c_int),
     "hpvg_linear_taps": ([i, i, i, POINTER(c_int32), POINTER(c_int32), POINTER(f), POINTER(f)], c_int),
     "hpvg_linear_taps_dev": ([i, i, i, vp, vp, vp, vp, vp], c_int),

@@ -11,7 +11,7 @@ import numpy as np
 
 from . import ops
 from .ops import ACT_LRELU, ACT_NONE, ACT_TANH
-from .runtime import F32, HpvgError, Tensor, from_numpy
+from .runtime import BF16, F32, HpvgError, Tensor, from_numpy
 from .utils import images as uimg
 
 
@@ -78,6 +78,53 @@ class Cell:
 
     def __call__(self, *a, **k):
         return self.construct(*a, **k)
+
+
+def conv_layers_of(cell):
+    """Every ConvLayer under `cell`, depth first."""
+    if isinstance(cell, ConvLayer):
+        return [cell]
+    out = []
+    for c in cell.cells().values():
+        out += conv_layers_of(c)
+    return out
+
+
+def prepack(cells, stream=None, dgrad=True):
+    """Rebuild, in ONE launch, everything the coming forward / backward derives from the weights of `cells`' layers: the
+    packed forward filter banks, the data-gradient banks (transposed / mirrored) and the (1, bias) epilogue vectors.
+    Equivalent to what ConvLayer._prepare / train._dgrad_wimgs do lazily, layer by layer, one launch per bank — at the
+    coarse scales those ~45 small launches sit on the critical path of a launch-latency-bound iteration.  bf16 kernel
+    variants only (the tf32 mode keeps the lazy path)."""
+    if ops.cl_dtype() != BF16:
+        return 0
+    entries = []
+    seen = set()
+    for cell in cells:
+        for l in conv_layers_of(cell):
+            if id(l) in seen or l._wimgs is not None:
+                continue
+            seen.add(id(l))
+            w = l.p["weight"]
+            imgs = []
+            for kw in ops.plan_wimgs(l.cin, l.cout, BF16):
+                t = ops.wimg_tensor(kw["mode"])
+                imgs.append(t)
+                entries.append(dict(w=w, out=t, **kw))
+            l._wimgs, l._wimgs_prec = imgs, BF16
+            if dgrad:
+                dimgs = []
+                for kw in ops.plan_wimgs(l.cout, l.cin, BF16):      # roles of Cin / Cout swapped
+                    t = ops.wimg_tensor(kw["mode"])
+                    dimgs.append(t)
+                    entries.append(dict(w=w, out=t, transpose_flip=True, **kw))
+                l._dgrad_cache = (imgs, dimgs)
+            if not l.sn and (l.cout == 64 or l.cout <= 4) and l._aff_bias is None:
+                aff = Tensor((2, 64), F32)
+                entries.append(dict(bias=l.p["bias"], cout=l.cout, out=aff))
+                l._aff_bias = aff
+    ops.pack_weights_multi(entries, stream=stream)
+    return len(entries)
 
 
 class ConvLayer(Cell):

@@ -162,10 +162,10 @@ def pack_weights(w, mode, transpose_flip=False, cout_off=0, cout=None, cin_off=0
     return out
 
 
-def build_wimgs(w, cin, cout, transpose_flip=False, dtype=None, stream=None):
-    """Packed filter banks of a cin -> cout convolution, in the order conv3d_cl_any consumes them, for activations of
-    `dtype` (default: the current precision mode).  cin / cout are the EFFECTIVE channel counts (for the data-gradient
-    conv, transpose_flip=True, they are the forward layer's cout / cin)."""
+def plan_wimgs(cin, cout, dtype=None):
+    """The filter banks of a cin -> cout convolution, in the order conv3d_cl_any consumes them, for activations of `dtype`
+    (default: the current precision mode): a list of pack_weights keyword dicts (mode, cout_off, cout, cin_off, cin).
+    cin / cout are the EFFECTIVE channel counts (for the data-gradient conv they are the forward layer's cout / cin)."""
     tf = (dtype or cl_dtype()) == F32
     if cout <= 4:
         if cin != 64:
@@ -173,24 +173,62 @@ def build_wimgs(w, cin, cout, transpose_flip=False, dtype=None, stream=None):
         if tf:
             if cout > 3:
                 raise HpvgError("tf32 tail convolutions write at most 3 channels")
-            return [pack_weights(w, CONV_T32_3, transpose_flip, cout=cout, cin_off=32 * ib, cin=32, stream=stream)
-                    for ib in range(2)]
-        return [pack_weights(w, tail_mode(cout), transpose_flip, cout=cout, stream=stream)]
-    imgs = []
+            return [dict(mode=CONV_T32_3, cout=cout, cin_off=32 * ib, cin=32) for ib in range(2)]
+        return [dict(mode=tail_mode(cout), cout=cout)]
+    plan = []
     if cin <= 8:
         if tf and cin > 4:
             raise HpvgError("tf32 head convolutions read at most 4 channels")
         mode = CONV_T4_64 if tf else CONV_8_64
-        for ob in range(cout // 64):
-            imgs.append(pack_weights(w, mode, transpose_flip, cout_off=ob * 64, cout=64, cin=cin, stream=stream))
-        return imgs
+        return [dict(mode=mode, cout_off=ob * 64, cout=64, cin=cin) for ob in range(cout // 64)]
     blk = 32 if tf else 64
     mode = CONV_T32_64 if tf else CONV_64_64
     for ob in range(cout // 64):
         for ib in range(cin // blk):
-            imgs.append(pack_weights(w, mode, transpose_flip, cout_off=ob * 64, cout=64, cin_off=ib * blk, cin=blk,
-                                     stream=stream))
-    return imgs
+            plan.append(dict(mode=mode, cout_off=ob * 64, cout=64, cin_off=ib * blk, cin=blk))
+    return plan
+
+
+def build_wimgs(w, cin, cout, transpose_flip=False, dtype=None, stream=None):
+    """Packed filter banks of a cin -> cout convolution (see plan_wimgs), one launch per bank."""
+    return [pack_weights(w, transpose_flip=transpose_flip, stream=stream, **kw) for kw in plan_wimgs(cin, cout, dtype)]
+
+
+def wimg_tensor(mode):
+    nb = lib.hpvg_conv_wimg_bytes(mode)
+    return Tensor((nb // 4,), F32) if is_tf32_mode(mode) else Tensor((nb // 2,), BF16)
+
+
+def pack_weights_multi(entries, stream=None):
+    """Many filter banks (bf16 kernel variants) and (1, bias) epilogue-vector pairs in ONE launch.
+    entries: dicts with `out` plus either (w, mode, transpose_flip, cout_off, cout, cin_off, cin) or (bias, cout) —
+    the latter writes fp32 [2][64] = (1, bias)."""
+    n = len(entries)
+    if not n:
+        return
+    vp = ctypes.c_void_p
+    ws, outs = (vp * n)(), (vp * n)()
+    cols = {k: (ctypes.c_int * n)() for k in ("w_cout", "w_cin", "kt", "mode", "flip", "cout_off", "cout", "cin_off", "cin")}
+    for i, e in enumerate(entries):
+        outs[i] = e["out"].ptr
+        if "bias" in e:
+            ws[i] = e["bias"].ptr if e["bias"] is not None else None
+            cols["mode"][i], cols["cout"][i], cols["kt"][i] = -1, int(e["cout"]), 3
+            continue
+        w = e["w"]
+        kt = w.shape[2] if len(w.shape) == 5 else 1
+        w_cout, w_cin = w.shape[0], w.shape[1]
+        flip = 1 if e.get("transpose_flip") else 0
+        eff_cout, eff_cin = (w_cin, w_cout) if flip else (w_cout, w_cin)
+        co_off, ci_off = int(e.get("cout_off", 0)), int(e.get("cin_off", 0))
+        ws[i] = w.ptr
+        cols["w_cout"][i], cols["w_cin"][i], cols["kt"][i], cols["mode"][i], cols["flip"][i] = w_cout, w_cin, kt, e["mode"], flip
+        cols["cout_off"][i], cols["cin_off"][i] = co_off, ci_off
+        cols["cout"][i] = int(e["cout"]) if e.get("cout") is not None else eff_cout - co_off
+        cols["cin"][i] = int(e["cin"]) if e.get("cin") is not None else eff_cin - ci_off
+    check(lib.hpvg_conv_pack_weights_multi(n, ws, cols["w_cout"], cols["w_cin"], cols["kt"], cols["mode"], cols["flip"],
+                                           cols["cout_off"], cols["cout"], cols["cin_off"], cols["cin"], outs,
+                                           _s(stream)), "conv_pack_weights_multi")
 
 
 def conv_cl(mode, x_cl, wimg, scale, shift, act=ACT_NONE, out_mode=None, out=None, out_pitch=64, out_coff=0,

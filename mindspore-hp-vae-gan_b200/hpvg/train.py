@@ -254,11 +254,14 @@ def conv_backward(layer, ctx, gy_cl, grads, ws, key, need_dx=True, want_dw=True,
     if want_dw:
         dw = dw_target if dw_target is not None else grads.of(w)
         xw = ctx.get("x_wide", x_cl)             # head convs: the 64-channel zero-padded copy of the 8-channel input
-        wst = ctx["wg_stream"] = _wgrad_stream(layer, stream)
+        wst = ctx.get("wg_stream") or _wgrad_stream(layer, stream)
+        ctx["wg_stream"] = wst
         for ob in range(max(1, cout // 64)):
             for ib in range(max(1, cin // 64)):
                 ops.conv_wgrad_cl(xw, gy_cl, dw, co_off=ob * 64, co_n=min(cout, 64), ci_off=ib * 64,
                                   ci_n=min(cin, 64), x_coff=ib * 64, gy_coff=ob * 64, accumulate=True, stream=wst)
+        ctx["wg_last"] = wst          # where this layer's weight gradient was produced (the sigma chain rule follows it)
+    ctx["wg_stream"] = None           # a preset is valid for one call only (contexts persist across iterations)
     if not need_dx:
         return None
     imgs = _dgrad_wimgs(layer, stream)
@@ -291,24 +294,29 @@ def layer_backward(layer, ctx, ga_cl, grads, ws, key, need_dx=True, trainable=Tr
         db = grads.of(layer.p["beta"]) if trainable else None
         gy = ops.bn_bwd_cl(ga_cl, ctx["y"], ctx["saved"], layer.act, out=ws.get(key + ".gy", ga_cl.shape, ga_cl.dtype),
                            dgamma=dg, dbeta=db, accumulate=True, stream=stream)
-        if trainable:
-            ops.colsum_cl(gy, grads.of(layer.p["bias"]), accumulate=True, stream=stream)
+        ctx["wg_stream"] = None
+        if trainable:     # parameter-gradient work (bias column sum, then the weight gradient) leaves the main chain
+            wst = ctx["wg_stream"] = _wgrad_stream(layer, stream)
+            ops.colsum_cl(gy, grads.of(layer.p["bias"]), accumulate=True, stream=wst)
         return conv_backward(layer, ctx, gy, grads, ws, key, need_dx, trainable, stream=stream)
     gz = ga_cl
     if layer.act == ACT_LRELU and not ga_masked:
         gz = ops.lrelu_bwd_cl(ga_cl, ctx["a"], out=ws.get(key + ".gz", ga_cl.shape, ga_cl.dtype), stream=stream)
+    ctx["wg_stream"] = None
     if trainable:
         if layer.cout == 64:
-            ops.colsum_cl(gz, grads.of(layer.p["bias"]), accumulate=True, stream=stream)
+            wst = ctx["wg_stream"] = _wgrad_stream(layer, stream)
+            ops.colsum_cl(gz, grads.of(layer.p["bias"]), accumulate=True, stream=wst)
         else:   # 128-channel outputs (mu / logvar): column sums per 64-channel half via an fp32 view
             _colsum_wide(gz, grads.of(layer.p["bias"]), stream)
     if layer.sn:
-        ghat = ws.get(key + ".ghat", layer.p["weight"].shape, F32).zero_(stream)
+        # zeroed on the stream that will accumulate into it (the side branch forked above, when there is one)
+        ghat = ws.get(key + ".ghat", layer.p["weight"].shape, F32).zero_(ctx.get("wg_stream") or stream)
         dx = conv_backward(layer, ctx, gz, grads, ws, key, need_dx, trainable, inv_sigma_aff=ctx["aff"],
                            stream=stream, dw_target=ghat, mask_input=mask_input)
         if trainable:     # on the stream that produced ghat (a side branch when branches are active)
             ops.sn_grad(ghat, layer.p["weight"], ctx["u"], ctx["v"], ctx["sigma"], grads.of(layer.p["weight"]),
-                        accumulate=True, stream=ctx.get("wg_stream", stream))
+                        accumulate=True, stream=ctx.get("wg_last") or stream)
         return dx
     return conv_backward(layer, ctx, gz, grads, ws, key, need_dx, trainable, stream=stream, mask_input=mask_input)
 
@@ -881,10 +889,14 @@ class GraphedIteration:
         # make the iteration CLOSED: packed filter banks / epilogue vectors derived from trainable weights must be
         # rebuilt inside the iteration, never carried over from the previous one through a Python-side cache (a
         # replayed graph would keep reading the buffer that was current at capture time)
+        cells = []
         for cell in (self.d_step, self.g_step):
             if cell is not None:
                 for c in cell.cells:
                     c.invalidate()
+                    cells.append(c)
+        from .networks_3d import prepack
+        prepack(cells, st)     # every filter bank / epilogue vector of the trainable layers in one launch
         if self.d_step is None:      # VAE phase: one forward, nothing to overlap
             return None, self.g_step(self.real, self.real_zero, self.noise_init, self.amps, stream=st, finish=finish,
                                      **self.g_kwargs)
