@@ -524,6 +524,7 @@ def test_cuda_graph_vae_iteration_matches_eager_iteration(hpvg_gpu):
         return out, losses
 
     p_e, l_e = run(False)
+    p_e2, _ = run(False)
     p_g, l_g = run(True)
     for a, b in zip(l_e, l_g):
         assert abs(a - b) < 2e-3 * max(1.0, abs(a)), (l_e, l_g)
@@ -533,4 +534,8 @@ def test_cuda_graph_vae_iteration_matches_eager_iteration(hpvg_gpu):
             # conv bias in front of a BatchNorm: analytically zero gradient, Adam amplifies rounding noise (see above)
             assert np.abs(p_g[k] - p_e[k]).max() <= 2 * 4 * 5e-4 + 1e-6, k
             continue
-        assert rel_l2(p_g[k], p_e[k]) < 2e-3, k
+        # Adam divides by sqrt(v): where a gradient element is tiny its +-lr step follows rounding noise (fp64 atomics in
+        # the BatchNorm statistics are order-dependent at 1e-16), so two EAGER runs already differ slightly; the graph
+        # must be no further from an eager run than eager runs are from each other (plus float32 round-off)
+        noise = rel_l2(p_e2[k], p_e[k])
+        assert rel_l2(p_g[k], p_e[k]) < 1e-3 + 2 * noise, (k, rel_l2(p_g[k], p_e[k]), noise)

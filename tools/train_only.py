@@ -14,4 +14,5 @@ st = hpvg.Stream()
 opt = uimg.default_opt()
 graph = not (len(sys.argv) > 3 and sys.argv[3] == 'eager')
 frames = int(sys.argv[4]) if len(sys.argv) > 4 else None
-print(json.dumps(bench.train_iter_bench(hpvg, opt, steps, warm, st, graph=graph, frames=frames)))
+peaks, kind = bench.load_peaks()
+print(json.dumps(bench.train_iter_bench(hpvg, opt, steps, warm, st, peaks, kind, graph=graph, frames=frames)))
