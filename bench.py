@@ -790,6 +790,26 @@ def run_ours(args):
         for k in ("e2e", "roofline", "cpu_baseline", "dtype"):
             if k in o:
                 line[k] = o[k]
+    # compact digest of the extra objects LAST on the line (a log tail keeps the end of a long line)
+    digest = {}
+    for k in ("train", "train_vae", "train_image", "tf32", "fid"):
+        o = line.get(k)
+        if not o:
+            continue
+        e = {"value": round(o["value"], 2), "unit": o["unit"]}
+        r = o.get("roofline", {})
+        for kk in ("frac", "iteration_frac"):
+            if kk in r:
+                e["roofline_" + kk] = round(r[kk], 3)
+        if "cpu_baseline" in o:
+            e["cpu"] = round(o["cpu_baseline"]["value"], 4)
+        if "gpu_launches_per_iter" in o:
+            e["launches"] = o["gpu_launches_per_iter"]
+        digest[k] = e
+    if "hbm_kernels" in line:
+        digest["hbm_frac"] = {r["kernel"].split(" (")[0][:28]: r["frac"] for r in line["hbm_kernels"]}
+    if digest:
+        line["digest"] = digest
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:

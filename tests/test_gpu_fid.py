@@ -11,7 +11,7 @@ from util import rel_l2
 pytestmark = pytest.mark.gpu
 
 # stated deltas on the mean per-sample Fréchet distance (relative to the oracle's value)
-SVFID_DELTA = {"bf16": 5e-2, "tf32": 5e-3}
+SVFID_DELTA = {"bf16": 2e-2, "tf32": 1e-3}      # measured: 1.7e-3 / 6.9e-3 (bf16, 5 / 10 scales), 6e-5 (tf32)
 
 
 def _ncdhw(feat_cl_tensor, ops):
