@@ -47,6 +47,7 @@ struct Cfg<CONV_MODE_64_64> {
   static constexpr int PLANE_BYTES = BOX_H * BOX_W * 128, SLOT_STRIDE = 23552, SLOTS = 4;
   static constexpr int W_BYTES = 27 * ROWS_PER_CTA * 128, DT_BYTES = 9 * ROWS_PER_CTA * 128;
   static constexpr int ACC_STRIDE = 64, TMEM_COLS = 128;
+  static constexpr int STAGES = 1;   // 16 KB output staging tiles for the TMA-store epilogue (what the 227 KB leave)
 };
 // MODE 1: Cin 64 -> Cout <= 16 (tail convs 64->3 / 64->1)
 template <>
@@ -56,6 +57,7 @@ struct Cfg<CONV_MODE_64_16> {
   static constexpr int PLANE_BYTES = BOX_H * BOX_W * 128, SLOT_STRIDE = 23552, SLOTS = 6;
   static constexpr int W_BYTES = 27 * ROWS_PER_CTA * 128, DT_BYTES = 9 * ROWS_PER_CTA * 128;
   static constexpr int ACC_STRIDE = 32, TMEM_COLS = 64;
+  static constexpr int STAGES = 0;
 };
 // MODE 2: Cin <= 8 -> Cout 64 (head convs 3->64); no-swizzle planes of 16 B per voxel, taps paired through LBO
 template <>
@@ -65,6 +67,9 @@ struct Cfg<CONV_MODE_8_64> {
   static constexpr int PLANE_BYTES = BOX_H * BOX_W * 16, SLOT_STRIDE = 3072, SLOTS = 8;
   static constexpr int W_BYTES = 3 * 5 * 1024, DT_BYTES = 5 * 1024;
   static constexpr int ACC_STRIDE = 64, TMEM_COLS = 128;
+  static constexpr int STAGES = 0;   // measured: the head conv is 14 % SLOWER through the staged TMA store (0.359 vs 0.316 ms
+                                     // at 8 x 13x192x257) although its L2 write requests drop 8x — its epilogue warps are
+                                     // latency-bound on ld -> math -> store per plane, and the two CTA barriers add to that
 };
 // kind::tf32 twins: fp32 operands, the SAME byte layouts with half the channels per row (a 128-byte row = 32 tf32
 // channels, K = 8 per MMA = the same 32 bytes; a 16-byte head voxel = 4 fp32 channels).  A 64 -> 64 layer at tf32 is two
@@ -80,6 +85,8 @@ struct Cfg<CONV_MODE_T4_64> : Cfg<CONV_MODE_8_64> {
   static constexpr bool TF32 = true;
   static constexpr int CIN = 4;
 };
+
+constexpr int STAGE_BYTES = TILE_H * TILE_W * 128;   // one CTA's output tile: 128 voxels x 64 bf16 channels
 
 struct Unit {
   int n, h0, w0;
@@ -135,7 +142,8 @@ template <int ACT, bool ADD, bool KEEP>
 __device__ __forceinline__ void epilogue_bf16_row(uint32_t (&r0)[32], uint32_t (&r1)[32], const float* scale_sm,
                                                   const float* shift_sm, const float* __restrict__ add,
                                                   __nv_bfloat16* __restrict__ dst,
-                                                  const __nv_bfloat16* __restrict__ mask = nullptr) {
+                                                  const __nv_bfloat16* __restrict__ mask = nullptr, int swz = 0) {
+  // swz: 0 for a global row; (row & 7) for a row of the 128B-swizzled shared-memory staging tile of the TMA store
   const float4* sc4 = reinterpret_cast<const float4*>(scale_sm);
   const float4* sh4 = reinterpret_cast<const float4*>(shift_sm);
 #pragma unroll
@@ -179,7 +187,7 @@ __device__ __forceinline__ void epilogue_bf16_row(uint32_t (&r0)[32], uint32_t (
       pk.y = pack_bf16x2(v[2], v[3]);
       pk.z = pack_bf16x2(v[4], v[5]);
       pk.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(dst + cb) = pk;
+      *reinterpret_cast<uint4*>(dst + ((((cb >> 3) ^ swz)) << 3)) = pk;
       if constexpr (KEEP) {
         const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
@@ -196,20 +204,20 @@ template <bool KEEP>
 __device__ __forceinline__ void epilogue_bf16_dispatch(int act, uint32_t (&r0)[32], uint32_t (&r1)[32],
                                                        const float* scale_sm, const float* shift_sm,
                                                        const float* __restrict__ add, __nv_bfloat16* __restrict__ dst,
-                                                       const __nv_bfloat16* __restrict__ mask) {
+                                                       const __nv_bfloat16* __restrict__ mask, int swz = 0) {
   if (act == CONV_ACT_LRELU_MASK) {
-    if (add) epilogue_bf16_row<CONV_ACT_LRELU_MASK, true, KEEP>(r0, r1, scale_sm, shift_sm, add, dst, mask);
-    else epilogue_bf16_row<CONV_ACT_LRELU_MASK, false, KEEP>(r0, r1, scale_sm, shift_sm, add, dst, mask);
+    if (add) epilogue_bf16_row<CONV_ACT_LRELU_MASK, true, KEEP>(r0, r1, scale_sm, shift_sm, add, dst, mask, swz);
+    else epilogue_bf16_row<CONV_ACT_LRELU_MASK, false, KEEP>(r0, r1, scale_sm, shift_sm, add, dst, mask, swz);
     return;
   }
   if (add) {   // split-Cin accumulation (128 -> 64 layers): rare
-    if (act == CONV_ACT_LRELU) epilogue_bf16_row<CONV_ACT_LRELU, true, KEEP>(r0, r1, scale_sm, shift_sm, add, dst);
-    else if (act == CONV_ACT_TANH) epilogue_bf16_row<CONV_ACT_TANH, true, KEEP>(r0, r1, scale_sm, shift_sm, add, dst);
-    else epilogue_bf16_row<CONV_ACT_NONE, true, KEEP>(r0, r1, scale_sm, shift_sm, add, dst);
+    if (act == CONV_ACT_LRELU) epilogue_bf16_row<CONV_ACT_LRELU, true, KEEP>(r0, r1, scale_sm, shift_sm, add, dst, nullptr, swz);
+    else if (act == CONV_ACT_TANH) epilogue_bf16_row<CONV_ACT_TANH, true, KEEP>(r0, r1, scale_sm, shift_sm, add, dst, nullptr, swz);
+    else epilogue_bf16_row<CONV_ACT_NONE, true, KEEP>(r0, r1, scale_sm, shift_sm, add, dst, nullptr, swz);
   } else {
-    if (act == CONV_ACT_LRELU) epilogue_bf16_row<CONV_ACT_LRELU, false, KEEP>(r0, r1, scale_sm, shift_sm, add, dst);
-    else if (act == CONV_ACT_TANH) epilogue_bf16_row<CONV_ACT_TANH, false, KEEP>(r0, r1, scale_sm, shift_sm, add, dst);
-    else epilogue_bf16_row<CONV_ACT_NONE, false, KEEP>(r0, r1, scale_sm, shift_sm, add, dst);
+    if (act == CONV_ACT_LRELU) epilogue_bf16_row<CONV_ACT_LRELU, false, KEEP>(r0, r1, scale_sm, shift_sm, add, dst, nullptr, swz);
+    else if (act == CONV_ACT_TANH) epilogue_bf16_row<CONV_ACT_TANH, false, KEEP>(r0, r1, scale_sm, shift_sm, add, dst, nullptr, swz);
+    else epilogue_bf16_row<CONV_ACT_NONE, false, KEEP>(r0, r1, scale_sm, shift_sm, add, dst, nullptr, swz);
   }
 }
 
@@ -273,7 +281,8 @@ __device__ __forceinline__ void epilogue_f32_dispatch(int act, uint32_t (&r0)[32
 
 template <int MODE, bool STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ConvParams p) {
+conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
+                   const __grid_constant__ ConvParams p) {
   using C = Cfg<MODE>;
   extern __shared__ uint8_t smem_dyn[];
   // carve (identical in both CTAs of the pair): [weights | plane ring | scale | shift | barriers | tmem ptr]
@@ -281,7 +290,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
   uint8_t* sm = smem_dyn + (((base_u32 + 1023u) & ~1023u) - base_u32);
   uint8_t* w_sm = sm;
   uint8_t* planes = sm + ((C::W_BYTES + 1023) & ~1023);
-  float* scale_sm = reinterpret_cast<float*>(planes + C::SLOTS * C::SLOT_STRIDE);
+  uint8_t* stage = planes + C::SLOTS * C::SLOT_STRIDE;     // [STAGES][128 rows][128 B], 1024-byte aligned, 128B-swizzled
+  float* scale_sm = reinterpret_cast<float*>(stage + C::STAGES * STAGE_BYTES);
   float* shift_sm = scale_sm + 64;
   uint64_t* bars = reinterpret_cast<uint64_t*>(shift_sm + 64);
   uint64_t* a_full = bars;                    // [SLOTS]  (used in the leader CTA; tx from both CTAs)
@@ -468,6 +478,32 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
     leader_empty[0] = map_to_cta(smem_u32(&acc_empty[0]), 0);
     leader_empty[1] = map_to_cta(smem_u32(&acc_empty[1]), 0);
     uint32_t q = 0;
+    // ---- TMA-store epilogue (bf16 channels-last output): the four epilogue warps write their 128 rows (128 B each) into
+    // a 128B-swizzled shared-memory tile — conflict-free 16-byte stores — and ONE bulk tensor store moves the tile out:
+    // full 128-byte lines instead of 32 partial-line store streams per warp instruction, and the tile's out-of-range
+    // rows / columns are clipped by the tensor map instead of being predicated per voxel.
+    const bool tma_out = C::STAGES > 0 && !C::TF32 && p.tma_out != 0;
+    uint32_t stage_n = 0;                      // tiles staged so far by this CTA
+    const bool store_thread = (warp == 2 && lane == 0);
+    auto stage_ptr = [&]() { return stage + (C::STAGES > 1 ? (stage_n & 1u) : 0u) * STAGE_BYTES; };
+    auto stage_row = [&]() { return reinterpret_cast<__nv_bfloat16*>(stage_ptr() + row * 128); };
+    auto stage_row_begin = [&]() {
+      // the tile about to be overwritten must have been read by the bulk store issued STAGES tiles ago
+      if (store_thread) {
+        if constexpr (C::STAGES > 1) tma_store_wait_read<1>();
+        else tma_store_wait_read<0>();
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+    };
+    auto stage_row_end = [&](const Unit& u, int plane) {
+      fence_proxy_async();                     // generic-proxy writes -> visible to the async proxy (TMA)
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (store_thread) {
+        tma_store_5d(&tmap_out, stage_ptr(), 0, u.w0, u.h0, plane, u.n);
+        tma_store_commit();
+      }
+      ++stage_n;
+    };
     float st_s0 = 0.f, st_s1 = 0.f, st_q0 = 0.f, st_q1 = 0.f;   // BatchNorm partial sums of channels 2*lane, 2*lane+1
     int g0, g1;
     work_range(pair, n_pairs, p, g0, g1);
@@ -524,7 +560,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
                 const float* add = p.addend ? p.addend + vox * 64 : nullptr;
                 float* dst = static_cast<float*>(p.out) + vox * p.out_pitch + p.out_coff;
                 epilogue_f32_dispatch<false>(p.act, r0, r1, scale_sm, shift_sm, add, dst);
-              } else {
+              } else if (!tma_out) {
                 const float* add = p.addend ? p.addend + vox * 64 : nullptr;
                 __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + vox * p.out_pitch + p.out_coff;
                 const __nv_bfloat16* mk =
@@ -532,22 +568,49 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
                 epilogue_bf16_dispatch<false>(p.act, r0, r1, scale_sm, shift_sm, add, dst, mk);
               }
             }
+            if constexpr (C::STAGES > 0 && !C::TF32) {
+              if (tma_out) {
+                stage_row_begin();
+                if (inb) {
+                  const float* add = p.addend ? p.addend + vox * 64 : nullptr;
+                  const __nv_bfloat16* mk =
+                      p.mask ? static_cast<const __nv_bfloat16*>(p.mask) + vox * p.mask_pitch : nullptr;
+                  epilogue_bf16_dispatch<false>(p.act, r0, r1, scale_sm, shift_sm, add, stage_row(), mk, row & 7);
+                }
+                stage_row_end(un, pl);
+              }
+            }
           } else {
             // bf16 output + BatchNorm batch statistics (sum, sum of squares of the values AS STORED, i.e. bf16-rounded)
+            if constexpr (C::STAGES > 0 && !C::TF32) {
+              if (tma_out) stage_row_begin();      // (a CTA barrier: outside the per-voxel `inb` divergence)
+            }
             if (inb) {
               const float* add = p.addend ? p.addend + vox * 64 : nullptr;
               if constexpr (C::TF32) {
                 float* dst = static_cast<float*>(p.out) + vox * p.out_pitch + p.out_coff;
                 epilogue_f32_dispatch<true>(p.act, r0, r1, scale_sm, shift_sm, add, dst);
               } else {
-                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + vox * p.out_pitch + p.out_coff;
                 const __nv_bfloat16* mk =
                     p.mask ? static_cast<const __nv_bfloat16*>(p.mask) + vox * p.mask_pitch : nullptr;
-                epilogue_bf16_dispatch<true>(p.act, r0, r1, scale_sm, shift_sm, add, dst, mk);
+                if constexpr (C::STAGES > 0) {
+                  if (tma_out) {
+                    epilogue_bf16_dispatch<true>(p.act, r0, r1, scale_sm, shift_sm, add, stage_row(), mk, row & 7);
+                  } else {
+                    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + vox * p.out_pitch + p.out_coff;
+                    epilogue_bf16_dispatch<true>(p.act, r0, r1, scale_sm, shift_sm, add, dst, mk);
+                  }
+                } else {
+                  __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + vox * p.out_pitch + p.out_coff;
+                  epilogue_bf16_dispatch<true>(p.act, r0, r1, scale_sm, shift_sm, add, dst, mk);
+                }
               }
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) r0[i] = r1[i] = 0u;
+            }
+            if constexpr (C::STAGES > 0 && !C::TF32) {
+              if (tma_out) stage_row_end(un, pl);
             }
             // per-channel sums over the 32 voxels of this warp: a butterfly that halves the channel set at every
             // step (62 shuffles per statistic instead of 320); lane L ends up with channels 2L, 2L+1.
@@ -617,6 +680,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
         }
       }
     }
+    if (tma_out && store_thread) tma_store_wait_all<0>();   // the staged tiles have reached global memory
     if constexpr (STATS) {
       {
         // all MMAs of this pair have completed (the last acc_full fired), so the plane ring is free: use it to combine
@@ -642,7 +706,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
 template <int MODE>
 constexpr int smem_bytes_for() {
   using C = Cfg<MODE>;
-  return 1024 + ((C::W_BYTES + 1023) & ~1023) + C::SLOTS * C::SLOT_STRIDE + 512 + (2 * C::SLOTS + 10) * 8 + 16;
+  static_assert((C::SLOTS * C::SLOT_STRIDE) % 1024 == 0, "the staging tiles must stay 1024-byte aligned");
+  return 1024 + ((C::W_BYTES + 1023) & ~1023) + C::SLOTS * C::SLOT_STRIDE + C::STAGES * STAGE_BYTES + 512 +
+         (2 * C::SLOTS + 10) * 8 + 16;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -661,7 +727,8 @@ EncodeTiledFn get_encode() {
 }
 
 template <int MODE, bool STATS>
-cudaError_t launch_mode(const CUtensorMap& tmap, const ConvParams& prm, int n_pairs, cudaStream_t stream) {
+cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& tmap_out, const ConvParams& prm, int n_pairs,
+                        cudaStream_t stream) {
   static bool configured = false;
   constexpr int smem = smem_bytes_for<MODE>();
   if (!configured) {
@@ -670,7 +737,7 @@ cudaError_t launch_mode(const CUtensorMap& tmap, const ConvParams& prm, int n_pa
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  conv3d_umma_kernel<MODE, STATS><<<dim3(2 * n_pairs), dim3(NUM_THREADS), smem, stream>>>(tmap, prm);
+  conv3d_umma_kernel<MODE, STATS><<<dim3(2 * n_pairs), dim3(NUM_THREADS), smem, stream>>>(tmap, tmap_out, prm);
   return cudaGetLastError();
 }
 
@@ -733,6 +800,25 @@ const char* conv3d_umma_launch(const ConvLaunch& L, cudaStream_t stream) {
   prm.addend = L.addend;
   prm.stats = L.stats;
   prm.mask = L.mask;
+  // output tensor map of the TMA-store epilogue: (C = 64 channels at out_coff, W, H, T, N) over the channels-last bf16
+  // output, box = one CTA tile (64 x TILE_W x TILE_H), 128B swizzle; rows / columns past H / W are clipped by the store
+  CUtensorMap tmap_out = tmap;
+  prm.tma_out = 0;
+  static const bool no_tma_store = getenv("HPVG_NO_TMA_STORE") != nullptr;
+  if (!tf32 && !no_tma_store && L.out_mode == CONV_OUT_BF16_NDHWC && L.mode == CONV_MODE_64_64 &&
+      (L.out_pitch & 7) == 0 && (L.out_coff & 7) == 0 && (reinterpret_cast<uintptr_t>(L.out) & 15) == 0) {
+    const cuuint64_t ovox = static_cast<cuuint64_t>(L.out_pitch) * 2;
+    cuuint64_t ogd[5] = {64, static_cast<cuuint64_t>(L.W), static_cast<cuuint64_t>(L.H), static_cast<cuuint64_t>(L.T),
+                         static_cast<cuuint64_t>(L.N)};
+    cuuint64_t ogs[4] = {ovox, ovox * L.W, ovox * L.W * L.H, ovox * L.W * L.H * L.T};
+    cuuint32_t obx[5] = {64, TILE_W, TILE_H, 1, 1};
+    void* obase = static_cast<char*>(L.out) + static_cast<size_t>(L.out_coff) * 2;
+    CUresult ro = enc(&tmap_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, obase, ogd, ogs, obx, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (ro != CUDA_SUCCESS) return "cuTensorMapEncodeTiled (output) failed";
+    prm.tma_out = 1;
+  }
   prm.mask_pitch = L.mask_pitch;
   prm.in_merged = merged ? 1 : 0;
   const long long out_planes = static_cast<long long>(prm.n_units) * L.T;   // work items of one plane each
@@ -752,27 +838,27 @@ const char* conv3d_umma_launch(const ConvLaunch& L, cudaStream_t stream) {
     case CONV_MODE_64_64:
       if (L.out_mode != CONV_OUT_BF16_NDHWC && L.out_mode != CONV_OUT_F32_RAW) return "bad out_mode for 64->64";
       if (L.stats && L.out_mode != CONV_OUT_BF16_NDHWC) return "fused statistics need the bf16 output mode";
-      e = L.stats ? launch_mode<CONV_MODE_64_64, true>(tmap, prm, n_pairs, stream)
-                  : launch_mode<CONV_MODE_64_64, false>(tmap, prm, n_pairs, stream);
+      e = L.stats ? launch_mode<CONV_MODE_64_64, true>(tmap, tmap_out, prm, n_pairs, stream)
+                  : launch_mode<CONV_MODE_64_64, false>(tmap, tmap_out, prm, n_pairs, stream);
       break;
     case CONV_MODE_64_16:
       if (L.out_mode != CONV_OUT_F32_NCDHW || L.cout_real > 4) return "bad out_mode for 64->16";
       if (L.stats) return "fused statistics need a 64-channel output";
-      e = launch_mode<CONV_MODE_64_16, false>(tmap, prm, n_pairs, stream);
+      e = launch_mode<CONV_MODE_64_16, false>(tmap, tmap_out, prm, n_pairs, stream);
       break;
     case CONV_MODE_8_64:
       if (L.out_mode != CONV_OUT_BF16_NDHWC && L.out_mode != CONV_OUT_F32_RAW) return "bad out_mode for 8->64";
       if (L.stats && L.out_mode != CONV_OUT_BF16_NDHWC) return "fused statistics need the bf16 output mode";
-      e = L.stats ? launch_mode<CONV_MODE_8_64, true>(tmap, prm, n_pairs, stream)
-                  : launch_mode<CONV_MODE_8_64, false>(tmap, prm, n_pairs, stream);
+      e = L.stats ? launch_mode<CONV_MODE_8_64, true>(tmap, tmap_out, prm, n_pairs, stream)
+                  : launch_mode<CONV_MODE_8_64, false>(tmap, tmap_out, prm, n_pairs, stream);
       break;
     case CONV_MODE_T32_64:
-      e = L.stats ? launch_mode<CONV_MODE_T32_64, true>(tmap, prm, n_pairs, stream)
-                  : launch_mode<CONV_MODE_T32_64, false>(tmap, prm, n_pairs, stream);
+      e = L.stats ? launch_mode<CONV_MODE_T32_64, true>(tmap, tmap_out, prm, n_pairs, stream)
+                  : launch_mode<CONV_MODE_T32_64, false>(tmap, tmap_out, prm, n_pairs, stream);
       break;
     case CONV_MODE_T4_64:
-      e = L.stats ? launch_mode<CONV_MODE_T4_64, true>(tmap, prm, n_pairs, stream)
-                  : launch_mode<CONV_MODE_T4_64, false>(tmap, prm, n_pairs, stream);
+      e = L.stats ? launch_mode<CONV_MODE_T4_64, true>(tmap, tmap_out, prm, n_pairs, stream)
+                  : launch_mode<CONV_MODE_T4_64, false>(tmap, tmap_out, prm, n_pairs, stream);
       break;
     default:
       return "unknown conv mode";

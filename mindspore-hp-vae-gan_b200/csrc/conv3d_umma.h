@@ -28,6 +28,7 @@ struct ConvParams {
   void* out;
   int out_pitch;         // channels per voxel of the channels-last (bf16 / fp32) output tensor
   int out_coff;          // first output channel inside that pitch
+  int tma_out;           // bf16 channels-last output through the TMA-store epilogue (tensor map passed to the kernel)
   int cout_real;         // CONV_OUT_F32_NCDHW: number of real output channels (<= 4)
   const float* addend;   // cl out: fp32 [V][64] partial sums added before scale/shift (split-Cin); tf32 RAW out: the same,
                          // added to the raw accumulator (may alias `out`);
