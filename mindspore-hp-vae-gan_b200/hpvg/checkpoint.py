@@ -2,9 +2,9 @@
 
 The reference saves one `netG_{i}.ckpt` / `netD_{i}.ckpt` per scale plus `intermediate.json`
 (`train_video.py:224-227`, `src/utils/saver.py:55-76`) and can import the original PyTorch `.pth` through the key map of
-`src/tools/pt2ms.py:129-188`.  MindSpore's `.ckpt` is a protobuf that only MindSpore can parse, so the container here
-is `.npz` — ONE array per parameter.  A maintainer converts a reference checkpoint with
-`np.savez(path, **{k: v.asnumpy() for k, v in mindspore.load_checkpoint(f).items()})`.
+`src/tools/pt2ms.py:129-188`.  The native container here is `.npz` — ONE array per parameter; MindSpore's `.ckpt` (a small
+protobuf schema) is read and written directly by `load_mindspore_ckpt` / `save_mindspore_ckpt` at the bottom of this file,
+so a reference checkpoint loads as it is: `load_param_into_net(netG, load_checkpoint("netG_9.ckpt"))`.
 
 Parameter names.  This package names parameters by their position in the graph: `body.<stage>.<layer>.<module>.<param>`
 for the generator (`body.2.1.0.bias`), `body.<block>.0.<param>` for the discriminator.  The reference's MindSpore
@@ -89,7 +89,10 @@ def save_checkpoint(cell, filename, reference_names=False, stream=None):
 
 
 def load_checkpoint(filename):
-    """saver.py:59-63 -> {name: array}."""
+    """saver.py:59-63 -> {name: array}.  A file ending in .ckpt that exists is read as a MindSpore checkpoint
+    (load_mindspore_ckpt); everything else is this package's .npz container."""
+    if filename.endswith(".ckpt") and os.path.exists(filename):
+        return load_mindspore_ckpt(filename)
     with np.load(_npz(filename)) as f:
         return {k: f[k] for k in f.files}
 
@@ -225,3 +228,135 @@ def p2m_WDiscriminator(state):
 
 p2m_WDiscriminator_3d = p2m_WDiscriminator
 p2m_WDiscriminator_2d = p2m_WDiscriminator
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# MindSpore `.ckpt` container without MindSpore (eval_video.py:162-170 `mindspore.load_checkpoint`).
+# A .ckpt is a protobuf (mindspore/ccsrc/utils/checkpoint.proto, proto2, unchanged across 1.x / 2.x):
+#     message Checkpoint  { repeated Value value = 1; }
+#     message Value       { required string tag = 1; required TensorProto tensor = 2; }
+#     message TensorProto { repeated int64 dims = 1; required string tensor_type = 2; required bytes tensor_content = 3; }
+# `tensor_type` is the MindSpore dtype name ("Float32", "Float16", "Int32", ...).  mindspore.save_checkpoint splits a
+# large tensor over several consecutive Values with the same tag (the dims are those of the whole tensor); their
+# contents are concatenated here.  The wire format is restated by hand (varints, length-delimited fields) — MindSpore is
+# not installable offline and the reference ships no .ckpt, so this reader is checked against an independent encoder of
+# the same schema (tests/test_cpu_dist.py), not against a file written by MindSpore ("parity unpinned").
+# ---------------------------------------------------------------------------------------------------------------------
+_MS_DTYPES = {"Float32": np.float32, "Float16": np.float16, "Float64": np.float64, "Int32": np.int32, "Int64": np.int64,
+              "Int8": np.int8, "UInt8": np.uint8, "Bool": np.bool_}
+
+
+def _varint(buf, pos):
+    val, shift = 0, 0
+    while True:
+        b = buf[pos]
+        pos += 1
+        val |= (b & 0x7F) << shift
+        if not b & 0x80:
+            return val, pos
+        shift += 7
+        if shift > 70:
+            raise HpvgError("corrupt varint in checkpoint")
+
+
+def _fields(buf, pos, end):
+    """Yield (field number, wire type, value) of one protobuf message; value = int (varint / fixed) or a memoryview."""
+    while pos < end:
+        key, pos = _varint(buf, pos)
+        num, wt = key >> 3, key & 7
+        if wt == 0:
+            v, pos = _varint(buf, pos)
+        elif wt == 2:
+            n, pos = _varint(buf, pos)
+            v = buf[pos:pos + n]
+            pos += n
+        elif wt == 1:
+            v = int.from_bytes(buf[pos:pos + 8], "little")
+            pos += 8
+        elif wt == 5:
+            v = int.from_bytes(buf[pos:pos + 4], "little")
+            pos += 4
+        else:
+            raise HpvgError("unsupported protobuf wire type %d in checkpoint" % wt)
+        if pos > end:
+            raise HpvgError("truncated checkpoint")
+        yield num, wt, v
+
+
+def load_mindspore_ckpt(filename):
+    """A MindSpore .ckpt -> {parameter name: numpy array} (the reference's names; see from_reference_names)."""
+    with open(filename, "rb") as f:
+        buf = memoryview(f.read())
+    chunks, dims_of, type_of, order = {}, {}, {}, []
+    for num, wt, value in _fields(buf, 0, len(buf)):
+        if num != 1 or wt != 2:
+            continue
+        tag, tensor = None, None
+        for n2, w2, v2 in _fields(value, 0, len(value)):
+            if n2 == 1 and w2 == 2:
+                tag = bytes(v2).decode("utf-8")
+            elif n2 == 2 and w2 == 2:
+                tensor = v2
+        if tag is None or tensor is None:
+            raise HpvgError("checkpoint Value without tag / tensor")
+        dims, ttype, content = [], None, b""
+        for n3, w3, v3 in _fields(tensor, 0, len(tensor)):
+            if n3 == 1 and w3 == 0:
+                dims.append(v3 if v3 < (1 << 63) else v3 - (1 << 64))
+            elif n3 == 1 and w3 == 2:          # packed encoding of the repeated field
+                p = 0
+                while p < len(v3):
+                    d, p = _varint(v3, p)
+                    dims.append(d)
+            elif n3 == 2 and w3 == 2:
+                ttype = bytes(v3).decode("utf-8")
+            elif n3 == 3 and w3 == 2:
+                content = v3
+        if tag not in chunks:
+            chunks[tag], dims_of[tag], type_of[tag] = [], dims, ttype
+            order.append(tag)
+        chunks[tag].append(bytes(content))
+    out = {}
+    for tag in order:
+        dt = _MS_DTYPES.get(type_of[tag])
+        if dt is None:
+            raise HpvgError("checkpoint tensor %s has unsupported dtype %r" % (tag, type_of[tag]))
+        arr = np.frombuffer(b"".join(chunks[tag]), dtype=dt)
+        shape = tuple(int(d) for d in dims_of[tag])
+        if int(np.prod(shape, dtype=np.int64)) != arr.size:
+            raise HpvgError("checkpoint tensor %s: %d elements for dims %s" % (tag, arr.size, shape))
+        out[tag] = arr.reshape(shape).copy()
+    return out
+
+
+def _enc_varint(v):
+    v &= (1 << 64) - 1
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        if v:
+            out.append(b | 0x80)
+        else:
+            out.append(b)
+            return bytes(out)
+
+
+def _enc_field(num, payload):
+    return _enc_varint((num << 3) | 2) + _enc_varint(len(payload)) + payload
+
+
+def save_mindspore_ckpt(params, filename, slice_bytes=None):
+    """{name: array} -> a file in MindSpore's .ckpt wire format (float32 tensors), so weights trained here can be handed
+    back to the reference's `mindspore.load_checkpoint`.  slice_bytes: split tensor contents like save_checkpoint does."""
+    names = {np.dtype(v): k for k, v in _MS_DTYPES.items()}
+    with open(filename, "wb") as f:
+        for tag, arr in params.items():
+            a = np.ascontiguousarray(arr)
+            raw = a.tobytes()
+            step = slice_bytes or max(len(raw), 1)
+            for off in range(0, max(len(raw), 1), step):
+                tensor = b"".join(_enc_varint((1 << 3) | 0) + _enc_varint(int(d)) for d in a.shape)
+                tensor += _enc_field(2, names[a.dtype].encode()) + _enc_field(3, raw[off:off + step])
+                f.write(_enc_field(1, _enc_field(1, tag.encode("utf-8")) + _enc_field(2, tensor)))
+    return filename

@@ -16,22 +16,22 @@ rng = np.random.default_rng(0)
 
 
 def bench(mode_name, cin, cout, shape, iters=10, stats=False):
+    """Precision follows HPVG_PRECISION (bf16: one kind::f16 launch; tf32: the two 32-channel kind::tf32 launches)."""
     N, T, H, W = shape
-    cpad = 8 if cin <= 8 else cin
-    x_cl = hpvg.Tensor((N, T, H, W, cpad), hpvg.BF16).zero_()
+    dt = ops.cl_dtype()
+    cpad = ops.narrow_pitch() if cin <= 8 else cin
+    x_cl = hpvg.Tensor((N, T, H, W, cpad), dt).zero_()
     w = hpvg.from_numpy((rng.standard_normal((cout, cin, 3, 3, 3)) * 0.05).astype(np.float32))
     aff = ops.affine_from_bias(hpvg.from_numpy(np.zeros(max(cout, 1), np.float32)))
-    mode = ops.conv_mode_for(cin, cout)
-    wi = ops.pack_weights(w, mode)
+    wimgs = ops.build_wimgs(w, cin, cout)
+    mode_name += "" if dt == hpvg.BF16 else "[tf32]"
     if cout <= 4:
         out = hpvg.Tensor((N, cout, T, H, W), hpvg.F32)
-        run = lambda: ops.conv_cl(mode, x_cl, wi, aff, aff.view((64,), hpvg.F32, 256), ops.ACT_TANH, ops.OUT_F32_NCDHW,
-                                  out=out, cout_real=cout, stream=st)
+        run = lambda: ops.conv3d_cl_any(x_cl, w, aff, ops.ACT_TANH, cin, cout, out=out, wimgs=wimgs, stream=st)
     else:
-        out = hpvg.Tensor((N, T, H, W, 64), hpvg.BF16)
+        out = hpvg.Tensor((N, T, H, W, 64), dt)
         stt = hpvg.Tensor((2, 64), hpvg.F64).zero_() if stats else None
-        run = lambda: ops.conv_cl(mode, x_cl, wi, aff, aff.view((64,), hpvg.F32, 256), ops.ACT_LRELU, ops.OUT_BF16_CL,
-                                  out=out, stats=stt, stream=st)
+        run = lambda: ops.conv3d_cl_any(x_cl, w, aff, ops.ACT_LRELU, cin, cout, out=out, wimgs=wimgs, stats=stt, stream=st)
     for _ in range(3):
         run()
     st.sync()

@@ -4,7 +4,7 @@ launch-list shares, a one-line-per-kernel table of the `ncu --set full` captures
 import csv, json, os, subprocess, sys, collections, re, shutil
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
 src = os.path.join(ROOT, "gpurun_out", "prof_" + tag)
 dst = os.path.join(ROOT, "profiles")
 os.makedirs(dst, exist_ok=True)
@@ -57,8 +57,9 @@ def full_rows(rep):
 
 
 def main():
-    for name, title in (("launches_sample.csv", "bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train --no-hbm (sampling, 16 clips/step)"),
-                        ("launches_train.csv", "tools/train_only.py 1 1 eager (2 GAN-phase train iterations at the finest scale)")):
+    for name, title in (("launches_sample.csv", "bench.py --steps 2 --warmup 3 --no-extras (sampling, 16 clips/step)"),
+                        ("launches_train.csv", "tools/train_only.py 1 1 eager 16 (GAN-phase train iterations at the 16-frame finest scale)"),
+                        ("launches_train_vae.csv", "tools/train_vae_only.py 1 0 eager (VAE-phase train iterations at scale 2, BASELINE config 2)")):
         p = os.path.join(src, name)
         if os.path.exists(p):
             open(os.path.join(dst, "%s_%s_summary.txt" % (tag, name[:-4])), "w").write(launch_summary(p, title))
