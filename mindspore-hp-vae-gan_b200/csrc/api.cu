@@ -33,6 +33,7 @@ struct StreamCtx {
   float* fscratch = nullptr;     // [256] fp32 scratch (spectral-norm gradient partial dots)
   void* arena = nullptr;         // grow-only workspace of the ops.Custom(aot) entry points
   size_t arena_cap = 0;
+  hpvg::DetScratch det{nullptr, nullptr};   // block partials + ticket counter of the deterministic reductions
 };
 std::mutex g_ctx_mu;
 std::unordered_map<void*, StreamCtx*> g_ctx;
@@ -40,6 +41,7 @@ std::unordered_map<void*, StreamCtx*> g_ctx;
 void ctx_free(StreamCtx* c) {
   if (!c) return;
   cudaFree(c->adam_norms); cudaFree(c->wgrad_ws); cudaFree(c->sums); cudaFree(c->fscratch); cudaFree(c->arena);
+  cudaFree(c->det.partials); cudaFree(c->det.counter);
   delete c;
 }
 
@@ -78,7 +80,10 @@ StreamCtx* ctx_for(void* stream) {
   size_t wg = hpvg::conv3d_wgrad_workspace_bytes(g_sm_count);
   const size_t wg32 = hpvg::conv3d_wgrad_tf32_workspace_bytes(g_sm_count);
   if (wg32 > wg) wg = wg32;
-  cudaError_t e = cudaMalloc(&c->adam_norms, hpvg::ADAM_MAX_TENSORS * sizeof(float));
+  cudaError_t e = cudaMalloc(&c->adam_norms, hpvg::ADAM_MAX_TENSORS * hpvg::ADAM_NORM_BLOCKS * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->det.partials, static_cast<size_t>(hpvg::DET_MAX_BLOCKS) * 128 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&c->det.counter, 256);
+  if (e == cudaSuccess) e = cudaMemset(c->det.counter, 0, 256);
   if (e == cudaSuccess) e = cudaMalloc(&c->wgrad_ws, wg);
   if (e == cudaSuccess) e = cudaMalloc(&c->sums, 128 * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&c->fscratch, 256 * sizeof(float));
@@ -349,6 +354,10 @@ int hpvg_conv_cl(int mode, int N, int T, int H, int W, const void* in, int in_pi
   L.out = out; L.out_pitch = out_pitch; L.out_coff = out_coff; L.cout_real = cout_real;
   L.addend = addend;
   L.stats = stats;
+  if (stats) {
+    CTX(cx, st);
+    L.det = cx->det;
+  }
   L.mask = mask;
   L.mask_pitch = mask_pitch;
   L.max_pairs = g_sm_count / 2;
@@ -409,7 +418,8 @@ int hpvg_upsample_noise_pack_f32(const float* x, int N, int C, int Ti, int Hi, i
 // ------------------------------------------------------------------------------------------------ batch norm
 int hpvg_bn_stats_cl(const void* y, long long voxels, double* sum, double* sumsq, void* st) {
   if (voxels <= 0) return fail(HPVG_E_ARG, "bn_stats: empty batch");
-  KL(hpvg::ew_bn_stats_cl(static_cast<const __nv_bfloat16*>(y), voxels, sum, sumsq, S(st)), 1);
+  CTX(cx, st);
+  KL(hpvg::ew_bn_stats_cl(static_cast<const __nv_bfloat16*>(y), voxels, sum, sumsq, cx->det, S(st)), 1);
   return HPVG_OK;
 }
 int hpvg_bn_finalize(const double* sum, const double* sumsq, long long count, const float* gamma, const float* beta,
@@ -492,17 +502,20 @@ int hpvg_affine_from_bias(const float* bias, const float* inv_sigma, int C, floa
 }
 int hpvg_mse(const float* a, const float* b, long long n, float* out, void* st) {
   if (n <= 0) return fail(HPVG_E_ARG, "mse: empty input");
-  KL(hpvg::ew_reduce(0, a, b, n, out, S(st)), 1);
+  CTX(cx, st);
+  KL(hpvg::ew_reduce(0, a, b, n, out, cx->det, S(st)), 1);
   return HPVG_OK;
 }
 int hpvg_mean(const float* a, long long n, float* out, void* st) {
   if (n <= 0) return fail(HPVG_E_ARG, "mean: empty input");
-  KL(hpvg::ew_reduce(1, a, nullptr, n, out, S(st)), 1);
+  CTX(cx, st);
+  KL(hpvg::ew_reduce(1, a, nullptr, n, out, cx->det, S(st)), 1);
   return HPVG_OK;
 }
 int hpvg_kl(const float* mu, const float* lv, long long n, float* out, void* st) {
   if (n <= 0) return fail(HPVG_E_ARG, "kl: empty input");
-  KL(hpvg::ew_reduce(2, mu, lv, n, out, S(st)), 1);
+  CTX(cx, st);
+  KL(hpvg::ew_reduce(2, mu, lv, n, out, cx->det, S(st)), 1);
   return HPVG_OK;
 }
 int hpvg_reparam(const float* mu, const float* lv, const float* eps, long long n, float* z, void* st) {
@@ -585,7 +598,8 @@ int hpvg_conv_wgrad_cl_tf32(const float* x, int x_pitch, const float* gy, int gy
 }
 int hpvg_bn_stats_cl_f32(const float* y, long long voxels, double* sum, double* sumsq, void* st) {
   if (voxels <= 0) return fail(HPVG_E_ARG, "bn_stats: empty batch");
-  KL(hpvg::ew_bn_stats_cl_f32(y, voxels, sum, sumsq, S(st)), 1);
+  CTX(cx, st);
+  KL(hpvg::ew_bn_stats_cl_f32(y, voxels, sum, sumsq, cx->det, S(st)), 1);
   return HPVG_OK;
 }
 int hpvg_bn_apply_lrelu_cl_f32(const float* y, long long voxels, const float* scale, const float* shift, int act,
@@ -612,13 +626,13 @@ int hpvg_bn_bwd_cl_f32(const float* ga, const float* y, long long voxels, const 
                        float* dgamma, float* dbeta, int accumulate, void* st) {
   if (voxels <= 0) return fail(HPVG_E_ARG, "bn_bwd: empty batch");
   CTX(cx, st);
-  KL(hpvg::ew_bn_bwd_cl_f32(ga, y, voxels, saved, act, cx->sums, gy, dgamma, dbeta, accumulate, S(st)), 2);
+  KL(hpvg::ew_bn_bwd_cl_f32(ga, y, voxels, saved, act, cx->sums, cx->det, gy, dgamma, dbeta, accumulate, S(st)), 2);
   return HPVG_OK;
 }
 int hpvg_colsum_cl_f32(const float* g, long long voxels, float* out, int accumulate, void* st) {
   if (voxels <= 0) return fail(HPVG_E_ARG, "colsum: empty input");
   CTX(cx, st);
-  KL(hpvg::ew_colsum_cl_f32(g, voxels, cx->sums, out, accumulate, S(st)), 2);
+  KL(hpvg::ew_colsum_cl_f32(g, voxels, cx->sums, cx->det, out, accumulate, S(st)), 2);
   return HPVG_OK;
 }
 int hpvg_slice_act_cl(const void* in, int NT, int Hi, int Wi, int C, int Ho, int Wo, int h0, int w0, int sh, int sw,
@@ -643,13 +657,13 @@ int hpvg_bn_bwd_cl(const void* ga, const void* y, long long voxels, const float*
   if (voxels <= 0) return fail(HPVG_E_ARG, "bn_bwd: empty batch");
   CTX(cx, st);
   KL(hpvg::ew_bn_bwd_cl(static_cast<const __nv_bfloat16*>(ga), static_cast<const __nv_bfloat16*>(y), voxels, saved,
-                        act, cx->sums, static_cast<__nv_bfloat16*>(gy), dgamma, dbeta, accumulate, S(st)), 2);
+                        act, cx->sums, cx->det, static_cast<__nv_bfloat16*>(gy), dgamma, dbeta, accumulate, S(st)), 2);
   return HPVG_OK;
 }
 int hpvg_colsum_cl(const void* g, long long voxels, float* out, int accumulate, void* st) {
   if (voxels <= 0) return fail(HPVG_E_ARG, "colsum: empty input");
   CTX(cx, st);
-  KL(hpvg::ew_colsum_cl(static_cast<const __nv_bfloat16*>(g), voxels, cx->sums, out, accumulate, S(st)), 2);
+  KL(hpvg::ew_colsum_cl(static_cast<const __nv_bfloat16*>(g), voxels, cx->sums, cx->det, out, accumulate, S(st)), 2);
   return HPVG_OK;
 }
 int hpvg_mse_grad(const float* out, const float* target, long long n, float coef, int accumulate, float* g, void* st) {
@@ -703,7 +717,7 @@ int hpvg_channel_sum(const float* g, int N, int C, long long sp, int accumulate,
   if (N <= 0 || C <= 0 || sp <= 0) return fail(HPVG_E_ARG, "channel_sum: empty input");
   CTX(cx, st);
   if (C > 128) return fail(HPVG_E_ARG, "channel_sum: at most 128 channels");
-  KL(hpvg::ew_channel_sum_ncdhw(g, N, C, sp, accumulate, cx->sums, out, S(st)), 2);
+  KL(hpvg::ew_channel_sum_ncdhw(g, N, C, sp, accumulate, cx->det.partials, out, S(st)), 2);
   return HPVG_OK;
 }
 int hpvg_kl_grad(const float* mu, const float* lv, long long n, float coef, float* gmu, float* glv, void* st) {
@@ -725,7 +739,8 @@ int hpvg_lerp(const float* a, const float* b, float alpha, long long n, float* o
 }
 int hpvg_gp_grad(const float* g, int N, int C, long long sp, float lambda, float* Gout, float* gp, void* st) {
   if (N <= 0 || C <= 0 || sp <= 0) return fail(HPVG_E_ARG, "gp_grad: empty input");
-  KL(hpvg::ew_gp_grad(g, N, C, sp, lambda, Gout, gp, S(st)), 1);
+  CTX(cx, st);
+  KL(hpvg::ew_gp_grad(g, N, C, sp, lambda, Gout, gp, cx->det, S(st)), 1);
   return HPVG_OK;
 }
 

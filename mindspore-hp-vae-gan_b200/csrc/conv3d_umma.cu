@@ -25,6 +25,7 @@
 #include <cstdlib>
 
 #include "conv3d_umma.h"
+#include "det_reduce.cuh"
 #include "ptx.cuh"
 
 namespace hpvg {
@@ -693,7 +694,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int t = threadIdx.x - 64;   // 0..127 : statistic (t >> 6), channel (t & 63)
         const float tot = red[t] + red[128 + t] + red[256 + t] + red[384 + t];
-        atomicAdd(p.stats + t, static_cast<double>(tot));
+        // CTA partials are summed in CTA order by whichever CTA finishes last: bitwise reproducible statistics
+        det_reduce_128<true>(static_cast<double>(tot), t, true, blockIdx.x, gridDim.x, p.det, p.stats, p.stats + 64, true);
       }
     }
   }
@@ -799,6 +801,8 @@ const char* conv3d_umma_launch(const ConvLaunch& L, cudaStream_t stream) {
   prm.cout_real = L.cout_real;
   prm.addend = L.addend;
   prm.stats = L.stats;
+  prm.det = L.det;
+  if (L.stats && (!L.det.partials || !L.det.counter)) return "fused statistics need the stream's reduction scratch";
   prm.mask = L.mask;
   // output tensor map of the TMA-store epilogue: (C = 64 channels at out_coff, W, H, T, N) over the channels-last bf16
   // output, box = one CTA tile (64 x TILE_W x TILE_H), 128B swizzle; rows / columns past H / W are clipped by the store

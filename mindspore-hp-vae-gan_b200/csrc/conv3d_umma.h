@@ -3,6 +3,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "det_reduce.cuh"
+
 namespace hpvg {
 
 enum ConvMode {
@@ -28,6 +30,7 @@ struct ConvParams {
   void* out;
   int out_pitch;         // channels per voxel of the channels-last (bf16 / fp32) output tensor
   int out_coff;          // first output channel inside that pitch
+  DetScratch det;        // stats: block partials + ticket counter of the deterministic cross-CTA sum
   int tma_out;           // bf16 channels-last output through the TMA-store epilogue (tensor map passed to the kernel)
   int cout_real;         // CONV_OUT_F32_NCDHW: number of real output channels (<= 4)
   const float* addend;   // cl out: fp32 [V][64] partial sums added before scale/shift (split-Cin); tf32 RAW out: the same,
@@ -55,6 +58,7 @@ struct ConvLaunch {
   int out_pitch, out_coff, cout_real;
   const float* addend;
   double* stats;
+  DetScratch det{nullptr, nullptr};   // required with stats: the calling stream's reduction scratch
   const void* mask;
   int mask_pitch;
   int max_pairs;         // CTA pairs to launch (<= 74 on a 148-SM B200)

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#include "det_reduce.cuh"
 #include "elementwise.h"
 
 namespace hpvg {
@@ -1110,7 +1111,7 @@ __global__ void upsample_noise_pack_kernel(const float* __restrict__ x, int N, i
 // ----------------------------------------------------------------------------------------------- BatchNorm (train)
 // y: (voxels, 64) bf16.  thread -> one 16 B channel group; 8 groups per voxel; block = 256 threads = 32 voxels/iter.
 __global__ void bn_stats_cl_kernel(const __nv_bfloat16* __restrict__ y, long long voxels, double* __restrict__ sum,
-                                   double* __restrict__ sumsq) {
+                                   double* __restrict__ sumsq, const DetScratch det) {
   const int g = threadIdx.x & 7;         // channel group
   const int vl = threadIdx.x >> 3;       // voxel lane 0..31
   float a[8], b[8];
@@ -1148,13 +1149,13 @@ __global__ void bn_stats_cl_kernel(const __nv_bfloat16* __restrict__ y, long lon
     }
   }
   __syncthreads();
+  double acc = 0.0;
   if (threadIdx.x < 128) {
     const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
-    double acc = 0.0;
 #pragma unroll
     for (int wv = 0; wv < 8; ++wv) acc += static_cast<double>(red[wv][which][c]);
-    atomicAdd((which ? sumsq : sum) + c, acc);
   }
+  det_reduce_128<false>(acc, threadIdx.x, threadIdx.x < 128, blockIdx.x, gridDim.x, det, sum, sumsq, false);
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, double count,
@@ -1383,7 +1384,7 @@ __global__ void affine_from_bias_kernel(const float* bias, const float* inv_sigm
 // ----------------------------------------------------------------------------------------------- reductions
 template <int OP>  // 0: sum (a-b)^2 ; 1: sum a ; 2: sum -0.5(1+lv-mu^2-exp(lv))
 __global__ void reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float inv_n,
-                              float* __restrict__ out) {
+                              float* __restrict__ out, const DetScratch det) {
   __shared__ float red[32];
   float acc = 0.f;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -1399,7 +1400,7 @@ __global__ void reduce_kernel(const float* __restrict__ a, const float* __restri
     }
   }
   const float t = block_sum(acc, red);
-  if (threadIdx.x == 0) atomicAdd(out, t * inv_n);
+  det_reduce_scalar(t, blockIdx.x, gridDim.x, det, inv_n, out);
 }
 
 __global__ void reparam_kernel(const float* __restrict__ mu, const float* __restrict__ lv,
@@ -1444,7 +1445,7 @@ __global__ void adam_norm_kernel(const AdamTable tab, float* __restrict__ norms)
   }
   for (long long i = (n4 << 2) + tid; i < n; i += nth) acc = fmaf(g[i], g[i], acc);
   const float s = block_sum(acc, red);
-  if (threadIdx.x == 0 && s != 0.f) atomicAdd(norms + t, s);
+  if (threadIdx.x == 0) norms[t * gridDim.x + blockIdx.x] = s;     // block partial; summed in block order by the apply kernel
 }
 
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float coef, float beta1, float beta2,
@@ -1457,7 +1458,8 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 
 __global__ void adam_apply_kernel(const AdamTable tab, const float* __restrict__ norms, float beta1, float beta2,
                                   float eps, float bc /* sqrt(1-b2^t)/(1-b1^t) */, float clip,
-                                  const unsigned long long* __restrict__ d_step, const float* __restrict__ d_hyper) {
+                                  const unsigned long long* __restrict__ d_step, const float* __restrict__ d_hyper,
+                                  int norm_blocks) {
   if (d_hyper) {   // every hyper-parameter lives on the device (ops.Custom binding): lr, beta1, beta2, eps, clip, step
     beta1 = d_hyper[1];
     beta2 = d_hyper[2];
@@ -1478,7 +1480,11 @@ __global__ void adam_apply_kernel(const AdamTable tab, const float* __restrict__
   // (the table is a kernel PARAMETER: it is only ever read — a dynamic write would force a per-thread local copy of it)
   const float lr_t = (d_hyper ? d_hyper[0] : tab.lr[t]) * bc;
   float coef = 1.0f;
-  if (clip > 0.f) coef = clip / fmaxf(sqrtf(norms[t]), clip);   // ClipByNorm: g*c / max(||g||, c)
+  if (clip > 0.f) {   // ClipByNorm: g*c / max(||g||, c); ||g||^2 = the norm kernel's block partials in block order
+    float nrm2 = 0.f;
+    for (int b = 0; b < norm_blocks; ++b) nrm2 += norms[t * norm_blocks + b];
+    coef = clip / fmaxf(sqrtf(nrm2), clip);
+  }
   const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                      reinterpret_cast<uintptr_t>(v)) & 15) == 0;
   const long long n4 = vec ? n >> 2 : 0;
@@ -1528,7 +1534,7 @@ __global__ void lrelu_bwd_cl_kernel(const __nv_bfloat16* __restrict__ ga, const 
 //   z = y*scale+shift (mask), xhat = (y-mean)*invstd, gz = ga*lrelu'(z)
 __global__ void bn_bwd_reduce_cl_kernel(const __nv_bfloat16* __restrict__ ga, const __nv_bfloat16* __restrict__ y,
                                         long long voxels, const float* __restrict__ saved /*[4][64]*/, int act,
-                                        double* __restrict__ sums) {
+                                        double* __restrict__ sums, const DetScratch det) {
   const int g = threadIdx.x & 7, vl = threadIdx.x >> 3;
   float sc[8], sh[8], mu[8], is[8], s0[8], s1[8];
 #pragma unroll
@@ -1575,13 +1581,13 @@ __global__ void bn_bwd_reduce_cl_kernel(const __nv_bfloat16* __restrict__ ga, co
     }
   }
   __syncthreads();
+  double acc = 0.0;
   if (threadIdx.x < 128) {
     const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
-    double acc = 0.0;
 #pragma unroll
     for (int wv = 0; wv < 8; ++wv) acc += static_cast<double>(red[wv][which][c]);
-    atomicAdd(sums + which * 64 + c, acc);
   }
+  det_reduce_128<false>(acc, threadIdx.x, threadIdx.x < 128, blockIdx.x, gridDim.x, det, sums, sums + 64, false);
 }
 
 // fp32 pair -> bf16 pair with STOCHASTIC rounding (16 hashed dither bits per value, keyed by the element index, so the
@@ -1701,7 +1707,16 @@ __global__ void channel_sum_ncdhw_kernel(const float* __restrict__ g, int N, int
       acc += p[i];
   }
   const float t = block_sum(acc, red);
-  if (threadIdx.x == 0) atomicAdd(scratch + c, static_cast<double>(t));
+  if (threadIdx.x == 0) scratch[static_cast<size_t>(c) * gridDim.x + blockIdx.x] = static_cast<double>(t);
+}
+// out[c] (+)= sum of the nblk block partials of channel c, in block order (deterministic)
+__global__ void channel_sum_final_kernel(const double* __restrict__ partials, int nblk, int C, int accumulate,
+                                         float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double acc = 0.0;
+  for (int b = 0; b < nblk; ++b) acc += partials[static_cast<size_t>(c) * nblk + b];
+  out[c] = (accumulate ? out[c] : 0.f) + static_cast<float>(acc);
 }
 // KL gradient (losses.py:5-7): d/dmu = coef*mu ; d/dlogvar = coef*0.5*(exp(lv)-1) ; coef = kl_weight/n
 __global__ void kl_grad_kernel(const float* __restrict__ mu, const float* __restrict__ lv, long long n, float coef,
@@ -1748,7 +1763,7 @@ __global__ void lerp_kernel(const float* __restrict__ a, const float* __restrict
 }
 // per voxel: nrm = ||g[:, v]||_2 over C channels ; gp += lambda*(nrm-1)^2/V ; G[c] = lambda*2*(nrm-1)/nrm*g[c]/V
 __global__ void gp_grad_kernel(const float* __restrict__ g, int N, int C, long long sp, float lambda,
-                               float* __restrict__ Gout, float* __restrict__ gp) {
+                               float* __restrict__ Gout, float* __restrict__ gp, const DetScratch det) {
   __shared__ float red[32];
   const long long V = static_cast<long long>(N) * sp;
   const float invV = 1.0f / static_cast<float>(V);
@@ -1767,7 +1782,7 @@ __global__ void gp_grad_kernel(const float* __restrict__ g, int N, int C, long l
     for (int c = 0; c < C; ++c) Gout[(n * C + c) * sp + s] = coef * g[(n * C + c) * sp + s];
   }
   const float t = block_sum(acc, red);
-  if (threadIdx.x == 0) atomicAdd(gp, t * lambda * invV);
+  det_reduce_scalar(t, blockIdx.x, gridDim.x, det, lambda * invV, gp);
 }
 
 inline int grid_for(long long n, int block, int cap = 148 * 16) {
@@ -2073,12 +2088,9 @@ cudaError_t ew_upsample_noise_pack(const float* x, int N, int C, int Ti, int Hi,
   LAUNCH_CHECK();
   return cudaSuccess;
 }
-cudaError_t ew_bn_stats_cl(const __nv_bfloat16* y, long long voxels, double* sum, double* sumsq, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(sum, 0, 64 * sizeof(double), st);
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(sumsq, 0, 64 * sizeof(double), st);
-  if (e != cudaSuccess) return e;
-  bn_stats_cl_kernel<<<grid_for(voxels, 32, 148 * 8), 256, 0, st>>>(y, voxels, sum, sumsq);
+cudaError_t ew_bn_stats_cl(const __nv_bfloat16* y, long long voxels, double* sum, double* sumsq, DetScratch det,
+                           cudaStream_t st) {
+  bn_stats_cl_kernel<<<grid_for(voxels, 32, DET_MAX_BLOCKS), 256, 0, st>>>(y, voxels, sum, sumsq, det);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -2140,14 +2152,13 @@ cudaError_t ew_affine_from_bias(const float* bias, const float* inv_sigma, int C
   LAUNCH_CHECK();
   return cudaSuccess;
 }
-cudaError_t ew_reduce(int op, const float* a, const float* b, long long n, float* out, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float), st);
-  if (e != cudaSuccess) return e;
+cudaError_t ew_reduce(int op, const float* a, const float* b, long long n, float* out, DetScratch det,
+                      cudaStream_t st) {
   const int grid = grid_for(n, 256, 148 * 4);
   const float inv = 1.0f / static_cast<float>(n);
-  if (op == 0) reduce_kernel<0><<<grid, 256, 0, st>>>(a, b, n, inv, out);
-  else if (op == 1) reduce_kernel<1><<<grid, 256, 0, st>>>(a, b, n, inv, out);
-  else reduce_kernel<2><<<grid, 256, 0, st>>>(a, b, n, inv, out);
+  if (op == 0) reduce_kernel<0><<<grid, 256, 0, st>>>(a, b, n, inv, out, det);
+  else if (op == 1) reduce_kernel<1><<<grid, 256, 0, st>>>(a, b, n, inv, out, det);
+  else reduce_kernel<2><<<grid, 256, 0, st>>>(a, b, n, inv, out, det);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -2172,14 +2183,13 @@ cudaError_t ew_adam_clip(const AdamTable& tab, int n_tensors, float* norms_scrat
   const long long cap = (148LL * 16 + n_tensors - 1) / n_tensors;
   if (want > cap) want = cap;
   const int gx = static_cast<int>(want < 1 ? 1 : want);
+  const int nb = gx < ADAM_NORM_BLOCKS ? gx : ADAM_NORM_BLOCKS;
   if (clip > 0.f) {
-    cudaError_t e = cudaMemsetAsync(norms_scratch, 0, ADAM_MAX_TENSORS * sizeof(float), st);
-    if (e != cudaSuccess) return e;
-    adam_norm_kernel<<<dim3(gx, n_tensors), 256, 0, st>>>(tab, norms_scratch);
+    adam_norm_kernel<<<dim3(nb, n_tensors), 256, 0, st>>>(tab, norms_scratch);
     LAUNCH_CHECK();
   }
   adam_apply_kernel<<<dim3(gx, n_tensors), 256, 0, st>>>(tab, norms_scratch, beta1, beta2, eps, bias_corr, clip,
-                                                         d_step, d_hyper);
+                                                         d_step, d_hyper, nb);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -2191,11 +2201,9 @@ cudaError_t ew_lrelu_bwd_cl(const __nv_bfloat16* ga, const __nv_bfloat16* a, lon
   return cudaSuccess;
 }
 cudaError_t ew_bn_bwd_cl(const __nv_bfloat16* ga, const __nv_bfloat16* y, long long voxels, const float* saved, int act,
-                         double* sums, __nv_bfloat16* gy, float* dgamma, float* dbeta, int accumulate,
+                         double* sums, DetScratch det, __nv_bfloat16* gy, float* dgamma, float* dbeta, int accumulate,
                          cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(sums, 0, 128 * sizeof(double), st);
-  if (e != cudaSuccess) return e;
-  bn_bwd_reduce_cl_kernel<<<grid_for(voxels, 32, 148 * 8), 256, 0, st>>>(ga, y, voxels, saved, act, sums);
+  bn_bwd_reduce_cl_kernel<<<grid_for(voxels, 32, DET_MAX_BLOCKS), 256, 0, st>>>(ga, y, voxels, saved, act, sums, det);
   LAUNCH_CHECK();
   bn_bwd_apply_cl_kernel<<<grid_for(voxels * 8, 256), 256, 0, st>>>(ga, y, voxels * 8, saved, act, sums,
                                                                     1.0 / static_cast<double>(voxels), gy, dgamma, dbeta,
@@ -2203,9 +2211,9 @@ cudaError_t ew_bn_bwd_cl(const __nv_bfloat16* ga, const __nv_bfloat16* y, long l
   LAUNCH_CHECK();
   return cudaSuccess;
 }
-cudaError_t ew_colsum_cl(const __nv_bfloat16* g, long long voxels, double* scratch, float* out, int accumulate,
-                         cudaStream_t st) {
-  cudaError_t e = ew_bn_stats_cl(g, voxels, scratch, scratch + 64, st);
+cudaError_t ew_colsum_cl(const __nv_bfloat16* g, long long voxels, double* scratch, DetScratch det, float* out,
+                         int accumulate, cudaStream_t st) {
+  cudaError_t e = ew_bn_stats_cl(g, voxels, scratch, scratch + 64, det, st);
   if (e != cudaSuccess) return e;
   d2f_kernel<<<1, 64, 0, st>>>(scratch, 64, 1.f, accumulate, out);
   LAUNCH_CHECK();
@@ -2264,11 +2272,10 @@ cudaError_t ew_fill(float* y, float v, long long n, cudaStream_t st) {
 cudaError_t ew_channel_sum_ncdhw(const float* g, int N, int C, long long sp, int accumulate, double* scratch,
                                  float* out, cudaStream_t st) {
   if (C > 128) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(scratch, 0, C * sizeof(double), st);
-  if (e != cudaSuccess) return e;
-  channel_sum_ncdhw_kernel<<<dim3(grid_for(sp, 512, 128), C), 512, 0, st>>>(g, N, C, sp, scratch);
+  const int nblk = grid_for(sp, 512, 128);        // scratch: [C <= 128][nblk <= 128] doubles (the DetScratch partials)
+  channel_sum_ncdhw_kernel<<<dim3(nblk, C), 512, 0, st>>>(g, N, C, sp, scratch);
   LAUNCH_CHECK();
-  d2f_kernel<<<(C + 63) / 64, 64, 0, st>>>(scratch, C, 1.f, accumulate, out);
+  channel_sum_final_kernel<<<(C + 63) / 64, 64, 0, st>>>(scratch, nblk, C, accumulate, out);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -2293,10 +2300,9 @@ cudaError_t ew_lerp(const float* a, const float* b, float alpha, long long n, fl
   return cudaSuccess;
 }
 cudaError_t ew_gp_grad(const float* g, int N, int C, long long sp, float lambda, float* Gout, float* gp,
-                       cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(gp, 0, sizeof(float), st);
-  if (e != cudaSuccess) return e;
-  gp_grad_kernel<<<grid_for(static_cast<long long>(N) * sp, 256, 148 * 4), 256, 0, st>>>(g, N, C, sp, lambda, Gout, gp);
+                       DetScratch det, cudaStream_t st) {
+  gp_grad_kernel<<<grid_for(static_cast<long long>(N) * sp, 256, 148 * 4), 256, 0, st>>>(g, N, C, sp, lambda, Gout, gp,
+                                                                                         det);
   LAUNCH_CHECK();
   return cudaSuccess;
 }

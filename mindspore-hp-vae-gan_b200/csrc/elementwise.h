@@ -2,11 +2,14 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+
+#include "det_reduce.cuh"
 #include <cstdint>
 
 namespace hpvg {
 
 constexpr int ADAM_MAX_TENSORS = 64;
+constexpr int ADAM_NORM_BLOCKS = 64;   // block partials per tensor of the gradient-norm pass (scratch: 64 x 64 floats)
 struct AdamTable {
   float* p[ADAM_MAX_TENSORS];
   const float* g[ADAM_MAX_TENSORS];
@@ -36,7 +39,8 @@ cudaError_t ew_frames_to_clip(const uint8_t* frames, int Hs, int Ws, int bgr, in
 cudaError_t ew_randn(float* z, long long n, unsigned long long seed, unsigned long long offset,
                      const unsigned long long* d_offset, cudaStream_t st);
 cudaError_t ew_counter_add(unsigned long long* c, unsigned long long inc, cudaStream_t st);
-cudaError_t ew_bn_stats_cl(const __nv_bfloat16* y, long long voxels, double* sum, double* sumsq, cudaStream_t st);
+cudaError_t ew_bn_stats_cl(const __nv_bfloat16* y, long long voxels, double* sum, double* sumsq, DetScratch det,
+                           cudaStream_t st);
 cudaError_t ew_bn_finalize(const double* sum, const double* sumsq, long long count, const float* gamma,
                            const float* beta, float eps, float momentum, float* mm, float* mv, float* scale,
                            float* shift, float* mean, float* invstd, cudaStream_t st);
@@ -73,7 +77,7 @@ cudaError_t ew_bn_fold_eval(const float* gamma, const float* beta, const float* 
                             const float* bias, int C, float* scale, float* shift, cudaStream_t st);
 cudaError_t ew_affine_from_bias(const float* bias, const float* inv_sigma, int C, float* scale, float* shift,
                                 cudaStream_t st);
-cudaError_t ew_reduce(int op, const float* a, const float* b, long long n, float* out, cudaStream_t st);
+cudaError_t ew_reduce(int op, const float* a, const float* b, long long n, float* out, DetScratch det, cudaStream_t st);
 cudaError_t ew_reparam_bwd(const float* gz, const float* eps, const float* lv, long long n, float* gmu, float* glv,
                            cudaStream_t st);
 cudaError_t ew_reparam(const float* mu, const float* lv, const float* eps, long long n, float* z, cudaStream_t st);
@@ -84,10 +88,10 @@ cudaError_t ew_adam_clip(const AdamTable& tab, int n_tensors, float* norms_scrat
 cudaError_t ew_lrelu_bwd_cl(const __nv_bfloat16* ga, const __nv_bfloat16* a, long long elems, __nv_bfloat16* gz,
                             cudaStream_t st);
 cudaError_t ew_bn_bwd_cl(const __nv_bfloat16* ga, const __nv_bfloat16* y, long long voxels, const float* saved, int act,
-                         double* sums, __nv_bfloat16* gy, float* dgamma, float* dbeta, int accumulate,
+                         double* sums, DetScratch det, __nv_bfloat16* gy, float* dgamma, float* dbeta, int accumulate,
                          cudaStream_t st);
-cudaError_t ew_colsum_cl(const __nv_bfloat16* g, long long voxels, double* scratch, float* out, int accumulate,
-                         cudaStream_t st);
+cudaError_t ew_colsum_cl(const __nv_bfloat16* g, long long voxels, double* scratch, DetScratch det, float* out,
+                         int accumulate, cudaStream_t st);
 cudaError_t ew_diff_scale(const float* a, const float* b, long long n, float coef, int accumulate, float* g,
                           cudaStream_t st);
 cudaError_t ew_tanh_bwd(const float* g, const float* out, long long n, float* gpre, cudaStream_t st);
@@ -103,7 +107,7 @@ cudaError_t ew_sn_grad(const float* G, const float* w, const float* u, const flo
                        int k, int accumulate, float* scratch, float* gw, cudaStream_t st);
 cudaError_t ew_lerp(const float* a, const float* b, float alpha, long long n, float* out, cudaStream_t st);
 cudaError_t ew_gp_grad(const float* g, int N, int C, long long sp, float lambda, float* Gout, float* gp,
-                       cudaStream_t st);
+                       DetScratch det, cudaStream_t st);
 
 
 // ---- fp32 channels-last twins (tf32 precision mode; elementwise_f32.cu)
@@ -111,7 +115,8 @@ cudaError_t ew_pack_cl_f32(const float* x, int N, int C, long long sp, float* y,
                            cudaStream_t st);
 cudaError_t ew_unpack_cl_f32(const float* x, int N, int C, long long sp, int c_pitch, int c_off, float* y,
                              cudaStream_t st);
-cudaError_t ew_bn_stats_cl_f32(const float* y, long long voxels, double* sum, double* sumsq, cudaStream_t st);
+cudaError_t ew_bn_stats_cl_f32(const float* y, long long voxels, double* sum, double* sumsq, DetScratch det,
+                               cudaStream_t st);
 cudaError_t ew_bn_apply_cl_f32(const float* y, long long voxels, const float* scale, const float* shift, int act,
                                float* x, cudaStream_t st);
 cudaError_t ew_bn_train_apply_cl_f32(const float* y, long long voxels, const double* sums, const float* gamma,
@@ -119,9 +124,10 @@ cudaError_t ew_bn_train_apply_cl_f32(const float* y, long long voxels, const dou
                                      int act, float* x, cudaStream_t st);
 cudaError_t ew_lrelu_bwd_cl_f32(const float* ga, const float* a, long long elems, float* gz, cudaStream_t st);
 cudaError_t ew_bn_bwd_cl_f32(const float* ga, const float* y, long long voxels, const float* saved, int act,
-                             double* sums, float* gy, float* dgamma, float* dbeta, int accumulate, cudaStream_t st);
-cudaError_t ew_colsum_cl_f32(const float* g, long long voxels, double* scratch, float* out, int accumulate,
+                             double* sums, DetScratch det, float* gy, float* dgamma, float* dbeta, int accumulate,
                              cudaStream_t st);
+cudaError_t ew_colsum_cl_f32(const float* g, long long voxels, double* scratch, DetScratch det, float* out,
+                             int accumulate, cudaStream_t st);
 
 // strided window of a bf16 channels-last tensor (+ optional ReLU): out = act(in[.., h0 + ho*sh, w0 + wo*sw, :])
 cudaError_t ew_slice_act_cl(const __nv_bfloat16* in, int NT, int Hi, int Wi, int C, int Ho, int Wo, int h0, int w0, int sh,

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#include "det_reduce.cuh"
 #include "elementwise.h"
 
 namespace hpvg {
@@ -103,7 +104,7 @@ unpack_cl_f32_tiled_kernel(const float* __restrict__ x, int C, long long sp, lon
 // y: (voxels, 64) fp32.  thread -> one float4 channel group; 16 groups per voxel; block = 256 threads = 16 voxels/iter.
 // sums[0][c] += sum y, sums[1][c] += sum y^2
 __global__ void bn_stats_cl_f32_kernel(const float* __restrict__ y, long long voxels, double* __restrict__ sum,
-                                       double* __restrict__ sumsq) {
+                                       double* __restrict__ sumsq, const DetScratch det) {
   const int g = threadIdx.x & 15, vl = threadIdx.x >> 4;
   float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
   for (long long v = static_cast<long long>(blockIdx.x) * 16 + vl; v < voxels;
@@ -127,13 +128,13 @@ __global__ void bn_stats_cl_f32_kernel(const float* __restrict__ y, long long vo
     }
   }
   __syncthreads();
+  double acc = 0.0;
   if (threadIdx.x < 128) {
     const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
-    double acc = 0.0;
 #pragma unroll
     for (int wv = 0; wv < 8; ++wv) acc += static_cast<double>(red[wv][which][c]);
-    atomicAdd((which ? sumsq : sum) + c, acc);
   }
+  det_reduce_128<false>(acc, threadIdx.x, threadIdx.x < 128, blockIdx.x, gridDim.x, det, sum, sumsq, false);
 }
 
 __device__ __forceinline__ float4 affine_act(float4 f, const float* sc, const float* sh, int c, int act) {
@@ -220,7 +221,7 @@ __global__ void lrelu_bwd_cl_f32_kernel(const float* __restrict__ ga, const floa
 // BatchNorm(train)+LeakyReLU backward, pass 1: sums[0][c] = sum gz, sums[1][c] = sum gz*xhat
 __global__ void bn_bwd_reduce_cl_f32_kernel(const float* __restrict__ ga, const float* __restrict__ y,
                                             long long voxels, const float* __restrict__ saved /*[4][64]*/, int act,
-                                            double* __restrict__ sums) {
+                                            double* __restrict__ sums, const DetScratch det) {
   const int g = threadIdx.x & 15, vl = threadIdx.x >> 4;
   float sc[4], sh[4], mu[4], is[4], s0[4], s1[4];
 #pragma unroll
@@ -259,13 +260,13 @@ __global__ void bn_bwd_reduce_cl_f32_kernel(const float* __restrict__ ga, const 
     }
   }
   __syncthreads();
+  double acc = 0.0;
   if (threadIdx.x < 128) {
     const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
-    double acc = 0.0;
 #pragma unroll
     for (int wv = 0; wv < 8; ++wv) acc += static_cast<double>(red[wv][which][c]);
-    atomicAdd(sums + which * 64 + c, acc);
   }
+  det_reduce_128<false>(acc, threadIdx.x, threadIdx.x < 128, blockIdx.x, gridDim.x, det, sums, sums + 64, false);
 }
 
 // fp32 -> tf32 with STOCHASTIC rounding (13 hashed dither bits, keyed by the element index: reproducible): the stored
@@ -359,12 +360,9 @@ cudaError_t ew_unpack_cl_f32(const float* x, int N, int C, long long sp, int c_p
   LAUNCH_CHECK();
   return cudaSuccess;
 }
-cudaError_t ew_bn_stats_cl_f32(const float* y, long long voxels, double* sum, double* sumsq, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(sum, 0, 64 * sizeof(double), st);
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(sumsq, 0, 64 * sizeof(double), st);
-  if (e != cudaSuccess) return e;
-  bn_stats_cl_f32_kernel<<<grid_for(voxels, 16, 148 * 8), 256, 0, st>>>(y, voxels, sum, sumsq);
+cudaError_t ew_bn_stats_cl_f32(const float* y, long long voxels, double* sum, double* sumsq, DetScratch det,
+                               cudaStream_t st) {
+  bn_stats_cl_f32_kernel<<<grid_for(voxels, 16, DET_MAX_BLOCKS), 256, 0, st>>>(y, voxels, sum, sumsq, det);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -388,10 +386,9 @@ cudaError_t ew_lrelu_bwd_cl_f32(const float* ga, const float* a, long long elems
   return cudaSuccess;
 }
 cudaError_t ew_bn_bwd_cl_f32(const float* ga, const float* y, long long voxels, const float* saved, int act,
-                             double* sums, float* gy, float* dgamma, float* dbeta, int accumulate, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(sums, 0, 128 * sizeof(double), st);
-  if (e != cudaSuccess) return e;
-  bn_bwd_reduce_cl_f32_kernel<<<grid_for(voxels, 16, 148 * 8), 256, 0, st>>>(ga, y, voxels, saved, act, sums);
+                             double* sums, DetScratch det, float* gy, float* dgamma, float* dbeta, int accumulate,
+                             cudaStream_t st) {
+  bn_bwd_reduce_cl_f32_kernel<<<grid_for(voxels, 16, DET_MAX_BLOCKS), 256, 0, st>>>(ga, y, voxels, saved, act, sums, det);
   LAUNCH_CHECK();
   bn_bwd_apply_cl_f32_kernel<<<grid_for(voxels * 16, 256), 256, 0, st>>>(ga, y, voxels * 16, saved, act, sums,
                                                                          1.0 / static_cast<double>(voxels), gy, dgamma,
@@ -399,9 +396,9 @@ cudaError_t ew_bn_bwd_cl_f32(const float* ga, const float* y, long long voxels, 
   LAUNCH_CHECK();
   return cudaSuccess;
 }
-cudaError_t ew_colsum_cl_f32(const float* g, long long voxels, double* scratch, float* out, int accumulate,
-                             cudaStream_t st) {
-  cudaError_t e = ew_bn_stats_cl_f32(g, voxels, scratch, scratch + 64, st);
+cudaError_t ew_colsum_cl_f32(const float* g, long long voxels, double* scratch, DetScratch det, float* out,
+                             int accumulate, cudaStream_t st) {
+  cudaError_t e = ew_bn_stats_cl_f32(g, voxels, scratch, scratch + 64, det, st);
   if (e != cudaSuccess) return e;
   d2f_f32_kernel<<<1, 64, 0, st>>>(scratch, 64, 1.f, accumulate, out);
   LAUNCH_CHECK();

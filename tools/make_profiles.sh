@@ -24,10 +24,6 @@ $NCU --set full --import-source on -k regex:conv3d_umma -s 3 -c 1 -o $OUT/conv64
     python tools/perf_conv.py 64 64 8,13,192,257 > $OUT/ncu_conv64.log 2>&1
 $NCU --set full --import-source on -k regex:conv3d_umma -s 3 -c 1 -o $OUT/conv64_bnstats -f \
     python tools/perf_conv.py 64 64 8,13,192,257 stats > $OUT/ncu_conv64s.log 2>&1
-$NCU --set full --import-source on -k regex:conv3d_tail -s 3 -c 1 -o $OUT/conv_tail -f \
-    python tools/perf_conv.py 64 3 8,13,192,257 > $OUT/ncu_tail.log 2>&1
-$NCU --set full --import-source on -k regex:conv3d_umma -s 3 -c 1 -o $OUT/conv_head -f \
-    python tools/perf_conv.py 3 64 8,13,192,257 > $OUT/ncu_head.log 2>&1
 $NCU --set full -k regex:conv3d_wgrad_kernel -s 40 -c 1 -o $OUT/wgrad -f \
     python tools/train_only.py 1 1 eager 16 > $OUT/ncu_wgrad.log 2>&1
 # train-path kernels at the 16-frame finest scale (the last launches of an iteration are the finest scale's)
@@ -43,5 +39,7 @@ HPVG_PRECISION=tf32 $NCU --set full --import-source on -k regex:conv3d_umma -s 3
 $NCU --section SpeedOfLight --section MemoryWorkloadAnalysis --section LaunchStats --section Occupancy \
     -k regex:"colwalk|frames_to_clip|bn_train_apply|adam_apply|adam_norm|bn_bwd_apply|bn_bwd_reduce|reduce_kernel" -c 14 \
     -o $OUT/hbm_kernels -f python tools/bench_hbm.py --iters 1 --warm 0 > $OUT/ncu_hbm.log 2>&1
-du -sh $OUT; find $OUT -size +30M -name "*.ncu-rep" -delete
-ls -la $OUT
+# digest ON THE BOX (gpurun copies back at most 64 MiB): tables into $OUT/summary, then drop the raw reports
+HPVG_PROF_DST=$OUT/summary python tools/summarize_profiles.py $TAG > $OUT/summarize.log 2>&1
+du -sh $OUT; find $OUT -name "*.ncu-rep" -delete
+ls -la $OUT $OUT/summary

@@ -6,7 +6,7 @@ import csv, json, os, subprocess, sys, collections, re, shutil
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
 src = os.path.join(ROOT, "gpurun_out", "prof_" + tag)
-dst = os.path.join(ROOT, "profiles")
+dst = os.environ.get("HPVG_PROF_DST") or os.path.join(ROOT, "profiles")
 os.makedirs(dst, exist_ok=True)
 
 
