@@ -43,17 +43,17 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
 
 
 def full_rows(rep):
+    """One row per profiled launch with the FIXED column set KEYS (captures made with different options expose different
+    raw columns; a metric a capture does not have stays empty)."""
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(txt.splitlines()))
     if len(r) < 3:
         return [], []
-    h = r[0]
-    cols = [("Kernel Name", h.index("Kernel Name"))] + [(k, h.index(k)) for k in KEYS if k in h]
-    units = r[1]
-    rows = []
-    for row in r[2:]:
-        rows.append([row[i] for _, i in cols])
-    return [c + (" [%s]" % units[i] if units[i] else "") for c, i in cols], rows
+    h, units = r[0], r[1]
+    idx = {k: h.index(k) for k in ["Kernel Name"] + KEYS if k in h}
+    header = ["Kernel Name"] + [k + (" [%s]" % units[idx[k]] if k in idx and units[idx[k]] else "") for k in KEYS]
+    rows = [[row[idx["Kernel Name"]]] + [row[idx[k]] if k in idx else "" for k in KEYS] for row in r[2:]]
+    return header, rows
 
 
 def main():
@@ -86,8 +86,6 @@ def main():
             continue
         if hdr is None:
             hdr = h
-        if h != hdr:
-            continue
         table.append([rep] + rows[0])
         if rep == "conv64.ncu-rep":
             d = dict(zip(h, rows[0]))
