@@ -9,7 +9,8 @@ forward through the full 10-scale pyramid (13 x 192 x 257 at the finest scale), 
 on the data path.  ONE JSON line on rank 0:
   value      device-resident throughput (noise already in HBM), CUDA events, max over ranks
   e2e        the same through the public API `hpvg.sampling.SamplePipeline` (what `sampling.generate` runs): per-sample
-             z drawn ON THE HOST (numpy, worker threads) into pinned memory, H2D, generation, D2H of every clip
+             random numbers of z drawn ON THE HOST (numpy, worker threads) into pinned memory, H2D, Box-Muller +
+             generation on the device, D2H of every clip
   roofline   the dominant kernel (tcgen05 conv 64->64), per-launch CUDA events live in this run
   extras (objects in the same line): `tf32` (the fp32-accurate precision mode), `train` (config 3), `train_vae`
   (config 2), `train_image` (config 1, 2-D), `fid` (config 5: moments + NCCL all-gather, every N), `hbm_kernels`,
@@ -657,8 +658,9 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(e2e_info["d2h"]), "ms_per_step": ms_e2e / args.steps,
                 "api": "hpvg.sampling.SamplePipeline.run (the loop inside sampling.generate)",
                 "host_draw_threads": e2e_info["threads"],
-                "note": "per-sample z drawn on the host (numpy, worker threads) into pinned memory, H2D, generation, D2H "
-                        "of every clip; wall clock between device-wide barriers, the last clip on the host",
+                "note": "per-sample random numbers of z drawn on the host (numpy uniforms, worker threads) into pinned "
+                        "memory, H2D, Box-Muller + generation on the device, D2H of every clip; wall clock between "
+                        "device-wide barriers, the last clip on the host",
                 "device_noise": {"value": clips / (ms_e2e_dev / 1000.0), "unit": UNIT, "h2d_bytes_per_step": 0,
                                  "d2h_bytes_per_step": int(e2e_dev_info["d2h"]),
                                  "note": "same call with noise='device': z from the device Philox generator keyed by "
@@ -676,7 +678,8 @@ def run_ours(args):
             n_fid = world * B * 2
 
             def fid_pass(seed):
-                return sampling.generate_moments(net, amps, n_fid, feats, comm, batch=B, seed=seed, stream=st)
+                return sampling.generate_moments(net, amps, n_fid, feats, comm, batch=B, seed=seed, stream=st,
+                                                 threads=max(1, min(8, (os.cpu_count() or 2) // max(local_world, 1))))
 
             fid_pass(1)
             barrier()

@@ -164,6 +164,9 @@ int hpvg_frames_to_clip(const uint8_t* d_frames, int F, int Hs, int Ws, int bgr,
                         int W, int hflip, float* d_clip, void* stream);
 /* z ~ N(0,1) on the device (Philox4x32-10 + Box-Muller), keyed by (seed, offset [+ *d_offset], element): stand-in for
  * the reference's host numpy draws (images.py:17-21, networks_3d.py:28-34) inside CUDA-graph replays */
+/* z <- N(0,1) in place from host-drawn uniforms u in [0,1) (pairs (u[2i], u[2i+1]) -> Box-Muller): the device half of
+ * the sampling pipeline's host noise (utils.generate_noise_ref, eval_video.py:67, drawn on the host there too). */
+int hpvg_box_muller_inplace(float* d_z, long long n, void* stream);
 int hpvg_randn(float* d_z, long long n, uint64_t seed, uint64_t offset, const uint64_t* d_offset, void* stream);
 int hpvg_counter_add(uint64_t* d_counter, uint64_t inc, void* stream);
 

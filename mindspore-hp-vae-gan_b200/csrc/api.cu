@@ -696,6 +696,12 @@ int hpvg_frames_to_clip(const uint8_t* frames, int F, int Hs, int Ws, int bgr, i
   KL(hpvg::ew_frames_to_clip(frames, Hs, Ws, bgr ? 1 : 0, start, every, T, H, W, hflip ? 1 : 0, clip, S(st)), 1);
   return HPVG_OK;
 }
+int hpvg_box_muller_inplace(float* z, long long n, void* st) {
+  if (n <= 0) return HPVG_OK;
+  if (!z) return fail(HPVG_E_ARG, "box_muller_inplace: null pointer");
+  KL(hpvg::ew_box_muller_inplace(z, n, S(st)), 1);
+  return HPVG_OK;
+}
 int hpvg_randn(float* z, long long n, uint64_t seed, uint64_t offset, const uint64_t* d_offset, void* st) {
   if (n <= 0) return HPVG_OK;
   if (!z) return fail(HPVG_E_ARG, "randn: null pointer");

@@ -2344,4 +2344,28 @@ cudaError_t ew_slice_act_cl(const __nv_bfloat16* in, int NT, int Hi, int Wi, int
   return cudaGetLastError();
 }
 
+// ----------------------------------------------------------------------------------------------- host-drawn noise
+// z <- N(0,1) from UNIFORMS drawn on the host: the host draws the random numbers (numpy, counter-based per sample —
+// the reference draws its z on the host too, eval_video.py:67), 3.9x cheaper per value as uniforms than as ziggurat
+// normals, and this kernel applies Box-Muller in place after the H2D copy: (u[2i], u[2i+1]) -> (z[2i], z[2i+1]).
+// u in [0, 1) with 24 bits: 1 - u is exact and in (0, 1], so the logarithm is finite.
+__global__ void box_muller_inplace_kernel(float* __restrict__ z, long long n) {
+  const long long pairs = (n + 1) >> 1;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < pairs;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const bool two = 2 * i + 1 < n;
+    const float u1 = 1.0f - z[2 * i], u2 = two ? z[2 * i + 1] : 0.5f;
+    const float r = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    z[2 * i] = r * cs;
+    if (two) z[2 * i + 1] = r * sn;
+  }
+}
+
+cudaError_t ew_box_muller_inplace(float* z, long long n, cudaStream_t st) {
+  box_muller_inplace_kernel<<<grid_for((n + 1) / 2, 256), 256, 0, st>>>(z, n);
+  return cudaGetLastError();
+}
+
 }  // namespace hpvg

@@ -133,4 +133,7 @@ cudaError_t ew_colsum_cl_f32(const float* g, long long voxels, double* scratch, 
 cudaError_t ew_slice_act_cl(const __nv_bfloat16* in, int NT, int Hi, int Wi, int C, int Ho, int Wo, int h0, int w0, int sh,
                             int sw, int relu, __nv_bfloat16* out, cudaStream_t st);
 
+// Box-Muller in place over host-drawn uniforms (see elementwise.cu)
+cudaError_t ew_box_muller_inplace(float* z, long long n, cudaStream_t st);
+
 }  // namespace hpvg

@@ -68,6 +68,7 @@ _SIGS = {
     "hpvg_resize3d_bwd": ([vp, i, i, i, i, i, vp, i, i, i, i, vp], c_int),
     "hpvg_upsample_noise_pack": ([vp, i, i, i, i, i, i, i, i, vp, f, u64, u64, vp, vp, vp, vp], c_int),
     "hpvg_frames_to_clip": ([vp, i, i, i, i, i, i, i, i, i, i, vp, vp], c_int),
+    "hpvg_box_muller_inplace": ([vp, ll, vp], c_int),
     "hpvg_randn": ([vp, ll, u64, u64, vp, vp], c_int),
     "hpvg_counter_add": ([vp, u64, vp], c_int),
     "hpvg_bn_stats_cl": ([vp, ll, vp, vp, vp], c_int),

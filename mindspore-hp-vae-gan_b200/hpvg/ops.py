@@ -448,6 +448,12 @@ def randn(shape, seed, offset=0, d_offset=None, out=None, stream=None):
     return out
 
 
+def box_muller_(z, stream=None):
+    """In place: host-drawn uniforms in [0, 1) -> N(0, 1) (pairs of consecutive elements, Box-Muller)."""
+    check(lib.hpvg_box_muller_inplace(_p(z), z.size, _s(stream)), "box_muller_inplace")
+    return z
+
+
 def counter_add(counter, inc=1, stream=None):
     check(lib.hpvg_counter_add(_p(counter), int(inc), _s(stream)), "counter_add")
     return counter

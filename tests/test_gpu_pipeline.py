@@ -161,3 +161,22 @@ def test_nccl_communicator_world1(hpvg_gpu):
     out = comm.all_gather_rows(rows, stream=st)
     assert np.array_equal(out, np.arange(12, dtype=np.float32).reshape(3, 4))
     comm.close()
+
+
+def test_host_uniform_noise_becomes_standard_normal_on_the_device(hpvg_gpu):
+    """SamplePipeline's z: uniforms drawn on the host per sample, Box-Muller on the device (ops.box_muller_): N(0,1)
+    statistics, no infinities at u = 0, the documented pairing, and reproducible per (seed, index)."""
+    hp, ops = hpvg_gpu, hpvg_gpu.ops
+    from hpvg import sampling
+    u = sampling.host_uniform_for_sample(11, 5, (128, 4, 24, 33))
+    assert u.dtype == np.float32 and u.min() >= 0.0 and u.max() < 1.0
+    assert np.array_equal(u, sampling.host_uniform_for_sample(11, 5, (128, 4, 24, 33)))
+    z = ops.box_muller_(hp.from_numpy(u)).numpy()
+    assert np.isfinite(z).all() and abs(z.mean()) < 5e-3 and abs(z.std() - 1.0) < 5e-3
+    assert abs(np.mean(z ** 3)) < 2e-2 and abs(np.mean(z ** 4) - 3.0) < 5e-2
+    f = u.ravel().astype(np.float64)
+    r = np.sqrt(-2.0 * np.log(1.0 - f[0::2]))
+    ref = np.stack([r * np.cos(2 * np.pi * f[1::2]), r * np.sin(2 * np.pi * f[1::2])], axis=1).ravel()
+    assert np.max(np.abs(z.ravel() - ref)) < 1e-4
+    edge = ops.box_muller_(hp.from_numpy(np.array([0.0, 0.0, 0.99999994, 0.25, 0.5], np.float32))).numpy()
+    assert np.isfinite(edge).all() and edge[0] == 0.0 and abs(edge[4]) < 1e-6 + 2.0   # odd tail element pairs with u2 = 0.5
