@@ -66,9 +66,18 @@ def calibrate_noise_amp(opt, netG, real, real_zero, noise_amps, scale_idx, strea
 
 
 def train_scale(opt, netG, D_cls, scale_idx, real, real_zero, noise_amps, niter, save_dir=None, prev_D_state=None,
-                z_init_size=None, stream=None, on_iter=None):
+                z_init_size=None, stream=None, on_iter=None, graph=False):
     """One call of the reference's `train(opt, netG)` for `scale_idx` (netG already has `scale_idx` body stages).
-    real / real_zero: float32 numpy clips of this scale / of scale 0.  Returns (D or None, losses list, D state)."""
+    real / real_zero: float32 numpy clips of this scale / of scale 0.  Returns (D or None, losses list, D state).
+
+    graph=False: every iteration is launched kernel by kernel; all N(0,1) draws come from numpy on the host exactly
+    where the reference makes them (Q7).
+    graph=True: the first two iterations run the same way, then the iteration (D step + G step + both Adam updates, or
+    the VAE-phase G step) is captured ONCE as a CUDA graph and replayed — what bench.py measures: at the coarse scales an
+    iteration is launch-latency bound and replays 6-8x faster than it can be launched from Python.  `noise_init` is
+    still drawn by numpy on the host every iteration and uploaded before each replay; the refinement noise inside the
+    forwards comes from the device Philox generator keyed by a device-resident draw counter (the host cannot inject
+    draws into a replayed graph), and the Adam step counter lives on the device."""
     vae_phase = opt.vae_levels >= scale_idx + 1
     D = None
     d_step = None
@@ -76,12 +85,12 @@ def train_scale(opt, netG, D_cls, scale_idx, real, real_zero, noise_amps, niter,
         D = D_cls(opt, rng=np.random.default_rng(1000 + scale_idx))
         if prev_D_state is not None and opt.vae_levels < scale_idx:        # warm start (:59-62)
             checkpoint.load_param_into_net(D, prev_D_state)
-        optD = T.Adam(T.trainable_params(D), opt.lr_d, beta1=opt.beta1, beta2=0.999)
-        d_step = T.TrainOneStepCell(T.DWithLoss(opt, D, netG), optD, cells_to_invalidate=[D])
+        optD = T.Adam(T.trainable_params(D), opt.lr_d, beta1=opt.beta1, beta2=0.999, device_step=graph)
+        d_step = T.TrainOneStepCell(T.DWithLoss(opt, D, netG, device_rng=graph), optD, cells_to_invalidate=[D])
     groups, body_idx, codec = generator_param_groups(opt, netG, scale_idx)
-    optG = T.ClippedAdam(opt, groups, opt.lr_g, beta1=opt.beta1, beta2=0.999)
+    optG = T.ClippedAdam(opt, groups, opt.lr_g, beta1=opt.beta1, beta2=0.999, device_step=graph)
     to_invalidate = [netG.body[s] for s in body_idx] + ([netG.encode, netG.decoder] if codec else [])
-    g_step = T.TrainOneStepCell(T.GWithLoss(opt, D, netG), optG, cells_to_invalidate=to_invalidate)
+    g_step = T.TrainOneStepCell(T.GWithLoss(opt, D, netG, device_rng=graph), optG, cells_to_invalidate=to_invalidate)
     netG.set_train(True)
     if D is not None:
         D.set_train(True)
@@ -89,6 +98,10 @@ def train_scale(opt, netG, D_cls, scale_idx, real, real_zero, noise_amps, niter,
     if z_init_size is None:
         z_init_size = (1, opt.latent_dim) + tuple(netG.stage_shape(0)[(0 if netG.KT == 3 else 1):])
     losses = []
+    if graph:
+        losses = _train_scale_graphed(opt, netG, scale_idx, g_step, d_step, t_real, t_zero, noise_amps, niter,
+                                      z_init_size, body_idx, codec, vae_phase, stream, on_iter)
+        niter = 0
     for it in range(niter):
         noise_init = from_numpy(np.random.normal(size=z_init_size).astype(np.float32))      # images.py:17-21 (Q7)
         if it == 0:
@@ -114,8 +127,53 @@ def train_scale(opt, netG, D_cls, scale_idx, real, real_zero, noise_amps, niter,
     return D, losses, d_state
 
 
+def _train_scale_graphed(opt, netG, scale_idx, g_step, d_step, t_real, t_zero, noise_amps, niter, z_init_size,
+                         body_idx, codec, vae_phase, stream, on_iter):
+    """The iteration loop of train_scale as CUDA-graph replays (see train_scale)."""
+    from .runtime import PinnedBuffer, Stream
+    from ._lib import check, lib
+    st = stream or Stream()
+    t_real, t_zero = as5d(t_real), as5d(t_zero)
+    z5 = tuple(z_init_size) if len(z_init_size) == 5 else (z_init_size[0], z_init_size[1], 1) + tuple(z_init_size[2:])
+    noise_dev = Tensor(z5, F32)
+    pinned = [PinnedBuffer(noise_dev.nbytes), PinnedBuffer(noise_dev.nbytes)]
+    uploaded = [None, None]
+
+    def upload(it):
+        k = it & 1
+        if uploaded[k] is not None:
+            uploaded[k].sync()          # the copy that last read this pinned buffer has completed
+        pinned[k].as_array(z5)[...] = np.random.normal(size=z5).astype(np.float32)          # images.py:17-21 (Q7)
+        check(lib.hpvg_h2d(noise_dev.ptr, pinned[k].ptr, noise_dev.nbytes, st.handle), "h2d")
+        ev = T.Event()
+        ev.record(st)
+        uploaded[k] = ev
+
+    kw = dict(isVAE=vae_phase, trainable_body=body_idx, train_codec=codec)
+    losses, graphed = [], None
+    for it in range(niter):
+        upload(it)
+        if it == 0:
+            calibrate_noise_amp(opt, netG, t_real, t_zero, noise_amps, scale_idx, st)
+            graphed = T.GraphedIteration(st, g_step, d_step, t_real, t_zero, noise_dev, noise_amps, kw)
+        if it < 2:
+            dl, gl = graphed._body(True)        # eager: first-use allocations, caches — and two real iterations
+        else:
+            if graphed.graph is None:
+                st.sync()
+                graphed.capture()
+            dl, gl = graphed()
+        losses.append((dl, gl))
+        if on_iter is not None:
+            on_iter(scale_idx, it, losses[-1])
+    st.sync()
+    if graphed is not None:
+        graphed.destroy()
+    return losses
+
+
 def train_pyramid(opt, netG, D_cls, real_at, niter, start_scale=0, stop_scale=None, noise_amps=None, save_dir=None,
-                  stream=None, on_iter=None):
+                  stream=None, on_iter=None, graph=False):
     """The `while opt.scale_idx < opt.stop_scale + 1` loop of train_video.py:413-419."""
     noise_amps = [] if noise_amps is None else noise_amps
     stop_scale = opt.stop_scale if stop_scale is None else stop_scale
@@ -126,6 +184,7 @@ def train_pyramid(opt, netG, D_cls, real_at, niter, start_scale=0, stop_scale=No
             netG.init_next_stage()
         real = real_at(scale_idx)
         _, losses, d_state = train_scale(opt, netG, D_cls, scale_idx, real, real_zero if scale_idx > 0 else real,
-                                         noise_amps, niter, save_dir, d_state, stream=stream, on_iter=on_iter)
+                                         noise_amps, niter, save_dir, d_state, stream=stream, on_iter=on_iter,
+                                         graph=graph)
         history.append(losses)
     return noise_amps, history
