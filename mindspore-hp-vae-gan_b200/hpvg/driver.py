@@ -74,10 +74,11 @@ def train_scale(opt, netG, D_cls, scale_idx, real, real_zero, noise_amps, niter,
     where the reference makes them (Q7).
     graph=True: the first two iterations run the same way, then the iteration (D step + G step + both Adam updates, or
     the VAE-phase G step) is captured ONCE as a CUDA graph and replayed — what bench.py measures: at the coarse scales an
-    iteration is launch-latency bound and replays 6-8x faster than it can be launched from Python.  `noise_init` is
-    still drawn by numpy on the host every iteration and uploaded before each replay; the refinement noise inside the
-    forwards comes from the device Philox generator keyed by a device-resident draw counter (the host cannot inject
-    draws into a replayed graph), and the Adam step counter lives on the device."""
+    iteration is launch-latency bound and replays several times faster than it can be launched from Python.  In the GAN
+    phase the random numbers of `noise_init` are still drawn by numpy on the host every iteration (on a worker thread,
+    one iteration ahead) and uploaded before each replay; the refinement noise inside the forwards comes from the device
+    Philox generator keyed by a device-resident draw counter (the host cannot inject draws into a replayed graph), and
+    the Adam step counter lives on the device."""
     vae_phase = opt.vae_levels >= scale_idx + 1
     D = None
     d_step = None
@@ -135,19 +136,37 @@ def _train_scale_graphed(opt, netG, scale_idx, g_step, d_step, t_real, t_zero, n
     st = stream or Stream()
     t_real, t_zero = as5d(t_real), as5d(t_zero)
     z5 = tuple(z_init_size) if len(z_init_size) == 5 else (z_init_size[0], z_init_size[1], 1) + tuple(z_init_size[2:])
-    noise_dev = Tensor(z5, F32)
+    noise_dev = Tensor(z5, F32).zero_(st)
     pinned = [PinnedBuffer(noise_dev.nbytes), PinnedBuffer(noise_dev.nbytes)]
     uploaded = [None, None]
+    # noise_init is consumed by the GAN phase only (the fake clip of the D step, the random clip of the G step); the VAE
+    # phase never reads it (losses.py:77-91), so nothing is drawn there.  GAN phase: the host draws the random numbers of
+    # iteration i+1 on a worker thread while the GPU replays iteration i — uniforms from a numpy Generator seeded from the
+    # global numpy state (the reference draws from that state, images.py:17-21), turned into N(0,1) on the device after
+    # the upload (ops.box_muller_: a quarter of the host cost of drawing normals)
+    from concurrent.futures import ThreadPoolExecutor
+    gen = np.random.default_rng(int(np.random.randint(0, 2 ** 31 - 1)))
+    pool = ThreadPoolExecutor(max_workers=1) if not vae_phase else None
+    drawn = {}
 
-    def upload(it):
+    def draw(it):
         k = it & 1
         if uploaded[k] is not None:
             uploaded[k].sync()          # the copy that last read this pinned buffer has completed
-        pinned[k].as_array(z5)[...] = np.random.normal(size=z5).astype(np.float32)          # images.py:17-21 (Q7)
+        gen.random(dtype=np.float32, out=pinned[k].as_array(z5))
+        return k
+
+    def upload(it):
+        if vae_phase:
+            return
+        k = drawn.pop(it).result() if it in drawn else draw(it)
         check(lib.hpvg_h2d(noise_dev.ptr, pinned[k].ptr, noise_dev.nbytes, st.handle), "h2d")
         ev = T.Event()
         ev.record(st)
         uploaded[k] = ev
+        ops.box_muller_(noise_dev, stream=st)
+        if it + 1 < niter:
+            drawn[it + 1] = pool.submit(draw, it + 1)
 
     kw = dict(isVAE=vae_phase, trainable_body=body_idx, train_codec=codec)
     losses, graphed = [], None
@@ -167,6 +186,8 @@ def _train_scale_graphed(opt, netG, scale_idx, g_step, d_step, t_real, t_zero, n
         if on_iter is not None:
             on_iter(scale_idx, it, losses[-1])
     st.sync()
+    if pool is not None:
+        pool.shutdown(wait=True)
     if graphed is not None:
         graphed.destroy()
     return losses
