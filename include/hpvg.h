@@ -184,16 +184,28 @@ int hpvg_bn_apply_lrelu_cl(const void* d_y, long long voxels, const float* d_sca
 
 /* one-pass training-mode BatchNorm: d_sums = the fp64 [2][64] statistics produced by hpvg_conv_cl(d_stats=...);
  * finalises (scale, shift), updates the moving statistics, writes d_saved = (scale, shift, mean, invstd) [4][64]
- * (nullable) and x = act(y*scale + shift) in a single launch. */
+ * (nullable) and x = act(y*scale + shift) in a single launch.  d_center (nullable): y was stored minus this per-channel
+ * offset (hpvg_bn_center_multi); d_saved stays in that centred frame, the moving mean gets the offset added back. */
 int hpvg_bn_train_apply_cl(const void* d_y, long long voxels, const double* d_sums, const float* d_gamma,
                            const float* d_beta, float eps, float momentum, float* d_moving_mean, float* d_moving_var,
-                           float* d_saved, int act, void* d_x, void* stream);
+                           float* d_saved, int act, void* d_x, const float* d_center, void* stream);
 
 /* deferred moving-statistics update of many BatchNorm layers in one launch (pointer arrays on the host): pass
  * d_moving_mean = d_moving_var = NULL to hpvg_bn_train_apply_cl, keep its d_saved, and replay the updates later in the
  * reference's order — needed when training-mode forwards of one network run concurrently on several streams */
 int hpvg_bn_moving_update_multi(int n_layers, const float* const* d_saved, float* const* d_moving_mean,
-                                float* const* d_moving_var, float eps, float momentum, void* stream);
+                                float* const* d_moving_var, const float* const* d_center /* nullable (array / entries) */,
+                                float eps, float momentum, void* stream);
+/* Kink-centred bf16 storage of the pre-BatchNorm activation (training mode): for every layer i, from the layer's gamma,
+ * beta, moving mean / variance and conv bias (64 floats each) compute center = moving_mean - beta*sqrt(moving_var+eps)/gamma
+ * — the estimated position of the LeakyReLU kink in units of the conv output — and the conv epilogue vectors
+ * aff[2][64] = (1, bias - center).  The conv then stores y - center (bf16 resolution is finest where the mask of the
+ * backward is decided); hpvg_bn_train_apply_cl / hpvg_bn_moving_update_multi take d_center to keep the MOVING mean that
+ * of the un-centred output.  BatchNorm being shift invariant, nothing else changes. */
+int hpvg_bn_center_multi(int n_layers, const float* const* d_gamma, const float* const* d_beta,
+                         const float* const* d_moving_mean, const float* const* d_moving_var,
+                         const float* const* d_bias, float* const* d_center, float* const* d_aff, float eps,
+                         void* stream);
 
 /* ---------------------------------------------------------------- spectral norm (spectral_norm.py:142-151)
  * One power iteration on W viewed (Cout, K): v <- l2n(W^T u); u <- l2n(W v); sigma = u^T W v.
@@ -254,7 +266,7 @@ int hpvg_bn_apply_lrelu_cl_f32(const float* d_y, long long voxels, const float* 
                                float* d_x, void* stream);
 int hpvg_bn_train_apply_cl_f32(const float* d_y, long long voxels, const double* d_sums, const float* d_gamma,
                                const float* d_beta, float eps, float momentum, float* d_moving_mean,
-                               float* d_moving_var, float* d_saved, int act, float* d_x, void* stream);
+                               float* d_moving_var, float* d_saved, int act, float* d_x, const float* d_center, void* stream);
 int hpvg_lrelu_bwd_cl_f32(const float* d_ga, const float* d_a, long long elems, float* d_gz, void* stream);
 int hpvg_bn_bwd_cl_f32(const float* d_ga, const float* d_y, long long voxels, const float* d_saved, int act,
                        float* d_gy, float* d_dgamma, float* d_dbeta, int accumulate, void* stream);

@@ -437,16 +437,36 @@ int hpvg_bn_apply_lrelu_cl(const void* y, long long voxels, const float* scale, 
 }
 
 int hpvg_bn_train_apply_cl(const void* y, long long voxels, const double* sums, const float* gamma, const float* beta,
-                           float eps, float momentum, float* mm, float* mv, float* saved, int act, void* x, void* st) {
+                           float eps, float momentum, float* mm, float* mv, float* saved, int act, void* x,
+                           const float* center, void* st) {
   if (voxels <= 0) return fail(HPVG_E_ARG, "bn_train_apply: empty batch");
   if (!y || !sums || !gamma || !beta || !x) return fail(HPVG_E_ARG, "bn_train_apply: null pointer");
   KL(hpvg::ew_bn_train_apply_cl(static_cast<const __nv_bfloat16*>(y), voxels, sums, gamma, beta, eps, momentum, mm, mv,
-                                saved, act, static_cast<__nv_bfloat16*>(x), S(st)), 1);
+                                saved, act, static_cast<__nv_bfloat16*>(x), center, S(st)), 1);
+  return HPVG_OK;
+}
+int hpvg_bn_center_multi(int n_layers, const float* const* gamma, const float* const* beta, const float* const* mm,
+                         const float* const* mv, const float* const* bias, float* const* center, float* const* aff,
+                         float eps, void* st) {
+  if (n_layers < 0 || !gamma || !beta || !mm || !mv || !bias || !center || !aff)
+    return fail(HPVG_E_ARG, "bn_center_multi: bad arguments");
+  for (int base = 0; base < n_layers; base += hpvg::BN_MOVING_MAX_LAYERS) {
+    hpvg::BnCenterTable tab;
+    std::memset(&tab, 0, sizeof(tab));
+    int cnt = 0;
+    for (int i = base; i < n_layers && cnt < hpvg::BN_MOVING_MAX_LAYERS; ++i, ++cnt) {
+      if (!gamma[i] || !beta[i] || !mm[i] || !mv[i] || !bias[i] || !center[i] || !aff[i])
+        return fail(HPVG_E_ARG, "bn_center_multi: null pointer");
+      tab.gamma[cnt] = gamma[i]; tab.beta[cnt] = beta[i]; tab.mm[cnt] = mm[i]; tab.mv[cnt] = mv[i];
+      tab.bias[cnt] = bias[i]; tab.center[cnt] = center[i]; tab.aff[cnt] = aff[i];
+    }
+    KL(hpvg::ew_bn_center_multi(tab, cnt, eps, S(st)), 1);
+  }
   return HPVG_OK;
 }
 
-int hpvg_bn_moving_update_multi(int n_layers, const float* const* saved, float* const* mm, float* const* mv, float eps,
-                                float momentum, void* st) {
+int hpvg_bn_moving_update_multi(int n_layers, const float* const* saved, float* const* mm, float* const* mv,
+                                const float* const* center, float eps, float momentum, void* st) {
   if (n_layers < 0 || !saved || !mm || !mv) return fail(HPVG_E_ARG, "bn_moving_update_multi: bad arguments");
   for (int base = 0; base < n_layers; base += hpvg::BN_MOVING_MAX_LAYERS) {
     hpvg::BnMovingTable tab;
@@ -455,6 +475,7 @@ int hpvg_bn_moving_update_multi(int n_layers, const float* const* saved, float* 
     for (int i = base; i < n_layers && cnt < hpvg::BN_MOVING_MAX_LAYERS; ++i, ++cnt) {
       if (!saved[i] || !mm[i] || !mv[i]) return fail(HPVG_E_ARG, "bn_moving_update_multi: null pointer");
       tab.saved[cnt] = saved[i]; tab.mm[cnt] = mm[i]; tab.mv[cnt] = mv[i];
+      tab.center[cnt] = center ? center[i] : nullptr;
     }
     KL(hpvg::ew_bn_moving_update_multi(tab, cnt, eps, momentum, S(st)), 1);
   }
@@ -610,10 +631,10 @@ int hpvg_bn_apply_lrelu_cl_f32(const float* y, long long voxels, const float* sc
 }
 int hpvg_bn_train_apply_cl_f32(const float* y, long long voxels, const double* sums, const float* gamma,
                                const float* beta, float eps, float momentum, float* mm, float* mv, float* saved,
-                               int act, float* x, void* st) {
+                               int act, float* x, const float* center, void* st) {
   if (voxels <= 0) return fail(HPVG_E_ARG, "bn_train_apply: empty batch");
   if (!y || !sums || !gamma || !beta || !x) return fail(HPVG_E_ARG, "bn_train_apply: null pointer");
-  KL(hpvg::ew_bn_train_apply_cl_f32(y, voxels, sums, gamma, beta, eps, momentum, mm, mv, saved, act, x, S(st)), 1);
+  KL(hpvg::ew_bn_train_apply_cl_f32(y, voxels, sums, gamma, beta, eps, momentum, mm, mv, saved, act, x, center, S(st)), 1);
   return HPVG_OK;
 }
 int hpvg_lrelu_bwd_cl_f32(const float* ga, const float* a, long long elems, float* gz, void* st) {
@@ -922,7 +943,7 @@ int HpvgBatchNorm3dLReluTrain(int nparam, void** params, int* ndims, int64_t** s
   if (!rc) rc = hpvg_bn_train_apply_cl(xcl, (long long)vox, sums, static_cast<const float*>(params[1]),
                                        static_cast<const float*>(params[2]), 1e-5f, 0.9f, static_cast<float*>(params[3]),
                                        static_cast<float*>(params[4]), static_cast<float*>(params[6]), HPVG_ACT_LRELU, ycl,
-                                       stream);
+                                       nullptr, stream);
   if (!rc) rc = hpvg_unpack_cl(ycl, N, 64, T, H, W, 64, 0, static_cast<float*>(params[5]), stream);
   return rc;
 }

@@ -1217,7 +1217,10 @@ __global__ void bn_train_apply_cl_kernel(const __nv_bfloat16* __restrict__ y, lo
                                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                          float momentum, float* __restrict__ mm, float* __restrict__ mv,
                                          float* __restrict__ saved /*[4][64], nullable*/, int act,
-                                         __nv_bfloat16* __restrict__ x) {
+                                         __nv_bfloat16* __restrict__ x, const float* __restrict__ center) {
+  // center (nullable): the per-channel offset the producing conv subtracted from y before storing it (kink-centred
+  // storage, see bn_center_multi_kernel).  Everything here and in the backward works in the centred frame — BatchNorm
+  // is shift invariant — except the MOVING mean, which tracks the true mean = centred mean + center.
   __shared__ float sc[64], sh[64];
   if (threadIdx.x < 64) {
     const int c = threadIdx.x;
@@ -1236,7 +1239,7 @@ __global__ void bn_train_apply_cl_kernel(const __nv_bfloat16* __restrict__ y, lo
         saved[128 + c] = static_cast<float>(mean);
         saved[192 + c] = invstd;
       }
-      if (mm) mm[c] = momentum * mm[c] + (1.f - momentum) * static_cast<float>(mean);
+      if (mm) mm[c] = momentum * mm[c] + (1.f - momentum) * (static_cast<float>(mean) + (center ? center[c] : 0.f));
       if (mv) mv[c] = momentum * mv[c] + (1.f - momentum) * static_cast<float>(var);
     }
   }
@@ -1270,10 +1273,29 @@ __global__ void bn_train_apply_cl_kernel(const __nv_bfloat16* __restrict__ y, lo
 __global__ void bn_moving_update_multi_kernel(const BnMovingTable tab, float eps, float momentum) {
   const int b = blockIdx.x, c = threadIdx.x;
   const float* sv = tab.saved[b];
-  const float mean = sv[128 + c], invstd = sv[192 + c];
+  const float mean = sv[128 + c] + (tab.center[b] ? tab.center[b][c] : 0.f), invstd = sv[192 + c];
   const float var = fmaxf(1.0f / (invstd * invstd) - eps, 0.f);
   tab.mm[b][c] = momentum * tab.mm[b][c] + (1.f - momentum) * mean;
   tab.mv[b][c] = momentum * tab.mv[b][c] + (1.f - momentum) * var;
+}
+
+// Kink-centred storage of the pre-BatchNorm activation (bf16 mode).  A training-mode layer stores y = conv(x) + bias in
+// bf16 and its backward recomputes the LeakyReLU mask from that stored y; bf16 rounding of y moves ~1e-3 of the
+// pre-activations across the kink relative to fp32 arithmetic (the rounding error is relative to |y|, and the kink of
+// channel c sits at y = mean_c - beta_c / (gamma_c * invstd_c), usually far from 0).  Storing y - center_c with
+// center_c = the ESTIMATED kink (moving statistics and the current gamma / beta: all known before the conv runs) puts
+// bf16's finest resolution exactly where the mask is decided.  BatchNorm is shift invariant, so the statistics, the
+// normalise pass and the backward simply run in the centred frame; only the moving mean needs center added back.
+// One block per layer: center[c] and the conv's epilogue vectors aff = (1, bias - center).
+__global__ void bn_center_multi_kernel(const BnCenterTable tab, float eps) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  const float g = tab.gamma[b][c];
+  float cen = tab.mm[b][c];
+  if (fabsf(g) > 1e-3f) cen -= tab.beta[b][c] * sqrtf(tab.mv[b][c] + eps) / g;
+  cen = __bfloat162float(__float2bfloat16_rn(cen));     // a bf16 value: exactly representable in every frame
+  tab.center[b][c] = cen;
+  tab.aff[b][c] = 1.0f;
+  tab.aff[b][64 + c] = tab.bias[b][c] - cen;
 }
 
 // ----------------------------------------------------------------------------------------------- spectral norm
@@ -2131,12 +2153,17 @@ cudaError_t ew_bn_moving_update_multi(const BnMovingTable& tab, int n_layers, fl
   LAUNCH_CHECK();
   return cudaSuccess;
 }
+cudaError_t ew_bn_center_multi(const BnCenterTable& tab, int n_layers, float eps, cudaStream_t st) {
+  bn_center_multi_kernel<<<n_layers, 64, 0, st>>>(tab, eps);
+  LAUNCH_CHECK();
+  return cudaSuccess;
+}
 cudaError_t ew_bn_train_apply_cl(const __nv_bfloat16* y, long long voxels, const double* sums, const float* gamma,
                                  const float* beta, float eps, float momentum, float* mm, float* mv, float* saved,
-                                 int act, __nv_bfloat16* x, cudaStream_t st) {
+                                 int act, __nv_bfloat16* x, const float* center, cudaStream_t st) {
   bn_train_apply_cl_kernel<<<grid_for(voxels * 8, 256), 256, 0, st>>>(y, voxels * 8, sums,
                                                                       static_cast<double>(voxels), gamma, beta, eps,
-                                                                      momentum, mm, mv, saved, act, x);
+                                                                      momentum, mm, mv, saved, act, x, center);
   LAUNCH_CHECK();
   return cudaSuccess;
 }

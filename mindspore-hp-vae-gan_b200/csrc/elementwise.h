@@ -67,12 +67,24 @@ struct BnMovingTable {
   const float* saved[BN_MOVING_MAX_LAYERS];
   float* mm[BN_MOVING_MAX_LAYERS];
   float* mv[BN_MOVING_MAX_LAYERS];
+  const float* center[BN_MOVING_MAX_LAYERS];   // nullable entries: offset of the centred frame `saved` lives in
 };
+struct BnCenterTable {     // per layer: inputs gamma, beta, moving mean / variance, conv bias; outputs center[64], aff[2][64]
+  const float* gamma[BN_MOVING_MAX_LAYERS];
+  const float* beta[BN_MOVING_MAX_LAYERS];
+  const float* mm[BN_MOVING_MAX_LAYERS];
+  const float* mv[BN_MOVING_MAX_LAYERS];
+  const float* bias[BN_MOVING_MAX_LAYERS];
+  float* center[BN_MOVING_MAX_LAYERS];
+  float* aff[BN_MOVING_MAX_LAYERS];
+};
+cudaError_t ew_bn_center_multi(const BnCenterTable& tab, int n_layers, float eps, cudaStream_t st);
 cudaError_t ew_bn_moving_update_multi(const BnMovingTable& tab, int n_layers, float eps, float momentum,
                                       cudaStream_t st);
 cudaError_t ew_bn_train_apply_cl(const __nv_bfloat16* y, long long voxels, const double* sums, const float* gamma,
                                  const float* beta, float eps, float momentum, float* mm, float* mv, float* saved,
-                                 int act, __nv_bfloat16* x, cudaStream_t st);
+                                 int act, __nv_bfloat16* x, const float* center,
+                                 cudaStream_t st);
 cudaError_t ew_bn_fold_eval(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                             const float* bias, int C, float* scale, float* shift, cudaStream_t st);
 cudaError_t ew_affine_from_bias(const float* bias, const float* inv_sigma, int C, float* scale, float* shift,
@@ -121,7 +133,7 @@ cudaError_t ew_bn_apply_cl_f32(const float* y, long long voxels, const float* sc
                                float* x, cudaStream_t st);
 cudaError_t ew_bn_train_apply_cl_f32(const float* y, long long voxels, const double* sums, const float* gamma,
                                      const float* beta, float eps, float momentum, float* mm, float* mv, float* saved,
-                                     int act, float* x, cudaStream_t st);
+                                     int act, float* x, const float* center, cudaStream_t st);
 cudaError_t ew_lrelu_bwd_cl_f32(const float* ga, const float* a, long long elems, float* gz, cudaStream_t st);
 cudaError_t ew_bn_bwd_cl_f32(const float* ga, const float* y, long long voxels, const float* saved, int act,
                              double* sums, DetScratch det, float* gy, float* dgamma, float* dbeta, int accumulate,

@@ -171,7 +171,7 @@ __global__ void bn_train_apply_cl_f32_kernel(const float* __restrict__ y, long l
                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                              float eps, float momentum, float* __restrict__ mm,
                                              float* __restrict__ mv, float* __restrict__ saved, int act,
-                                             float* __restrict__ x) {
+                                             float* __restrict__ x, const float* __restrict__ center) {
   __shared__ float sc[64], sh[64];
   if (threadIdx.x < 64) {
     const int c = threadIdx.x;
@@ -190,7 +190,7 @@ __global__ void bn_train_apply_cl_f32_kernel(const float* __restrict__ y, long l
         saved[128 + c] = static_cast<float>(mean);
         saved[192 + c] = invstd;
       }
-      if (mm) mm[c] = momentum * mm[c] + (1.f - momentum) * static_cast<float>(mean);
+      if (mm) mm[c] = momentum * mm[c] + (1.f - momentum) * (static_cast<float>(mean) + (center ? center[c] : 0.f));
       if (mv) mv[c] = momentum * mv[c] + (1.f - momentum) * static_cast<float>(var);
     }
   }
@@ -374,9 +374,9 @@ cudaError_t ew_bn_apply_cl_f32(const float* y, long long voxels, const float* sc
 }
 cudaError_t ew_bn_train_apply_cl_f32(const float* y, long long voxels, const double* sums, const float* gamma,
                                      const float* beta, float eps, float momentum, float* mm, float* mv, float* saved,
-                                     int act, float* x, cudaStream_t st) {
+                                     int act, float* x, const float* center, cudaStream_t st) {
   bn_train_apply_cl_f32_kernel<<<grid_for(voxels * 16, 256), 256, 0, st>>>(
-      y, voxels * 16, sums, static_cast<double>(voxels), gamma, beta, eps, momentum, mm, mv, saved, act, x);
+      y, voxels * 16, sums, static_cast<double>(voxels), gamma, beta, eps, momentum, mm, mv, saved, act, x, center);
   LAUNCH_CHECK();
   return cudaSuccess;
 }

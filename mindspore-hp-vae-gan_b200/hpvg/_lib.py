@@ -74,8 +74,10 @@ _SIGS = {
     "hpvg_bn_stats_cl": ([vp, ll, vp, vp, vp], c_int),
     "hpvg_bn_finalize": ([vp, vp, ll, vp, vp, f, f, vp, vp, vp, vp, vp, vp, vp], c_int),
     "hpvg_bn_apply_lrelu_cl": ([vp, ll, vp, vp, i, vp, vp], c_int),
-    "hpvg_bn_train_apply_cl": ([vp, ll, vp, vp, vp, f, f, vp, vp, vp, i, vp, vp], c_int),
-    "hpvg_bn_moving_update_multi": ([i, POINTER(vp), POINTER(vp), POINTER(vp), f, f, vp], c_int),
+    "hpvg_bn_train_apply_cl": ([vp, ll, vp, vp, vp, f, f, vp, vp, vp, i, vp, vp, vp], c_int),
+    "hpvg_bn_moving_update_multi": ([i, POINTER(vp), POINTER(vp), POINTER(vp), POINTER(vp), f, f, vp], c_int),
+    "hpvg_bn_center_multi": ([i, POINTER(vp), POINTER(vp), POINTER(vp), POINTER(vp), POINTER(vp), POINTER(vp), POINTER(vp),
+                              f, vp], c_int),
     "hpvg_sn_power_iter": ([vp, i, i, vp, vp, vp, vp, vp], c_int),
     "hpvg_sn_power_iter_multi": ([i, POINTER(vp), POINTER(i), POINTER(i), POINTER(vp), POINTER(vp), POINTER(vp),
                                   POINTER(vp), POINTER(vp), POINTER(vp), POINTER(vp), vp], c_int),
@@ -108,7 +110,7 @@ _SIGS = {
     "hpvg_conv_wgrad_cl_tf32": ([vp, i, vp, i, i, i, i, i, vp, i, i, i, i, i, i, i, f, vp], c_int),
     "hpvg_bn_stats_cl_f32": ([vp, ll, vp, vp, vp], c_int),
     "hpvg_bn_apply_lrelu_cl_f32": ([vp, ll, vp, vp, i, vp, vp], c_int),
-    "hpvg_bn_train_apply_cl_f32": ([vp, ll, vp, vp, vp, f, f, vp, vp, vp, i, vp, vp], c_int),
+    "hpvg_bn_train_apply_cl_f32": ([vp, ll, vp, vp, vp, f, f, vp, vp, vp, i, vp, vp, vp], c_int),
     "hpvg_lrelu_bwd_cl_f32": ([vp, vp, ll, vp, vp], c_int),
     "hpvg_bn_bwd_cl_f32": ([vp, vp, ll, vp, i, vp, vp, vp, i, vp], c_int),
     "hpvg_colsum_cl_f32": ([vp, ll, vp, i, vp], c_int),

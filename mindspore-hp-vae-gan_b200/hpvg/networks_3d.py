@@ -80,6 +80,12 @@ class Cell:
         return self.construct(*a, **k)
 
 
+# Kink-centred bf16 storage of the pre-BatchNorm activation in training mode (csrc/elementwise.cu: bn_center_multi_kernel).
+# HPVG_CENTRED_BN=0 stores the plain conv output (round-1 behaviour; kept for the A/B numbers of DESIGN.md §5.1).
+import os as _os
+CENTRED_BN_STORAGE = [_os.environ.get("HPVG_CENTRED_BN", "1") != "0"]
+
+
 def conv_layers_of(cell):
     """Every ConvLayer under `cell`, depth first."""
     if isinstance(cell, ConvLayer):
@@ -98,7 +104,7 @@ def prepack(cells, stream=None, dgrad=True):
     variants only (the tf32 mode keeps the lazy path)."""
     if ops.cl_dtype() != BF16:
         return 0
-    entries = []
+    entries, centres = [], []
     seen = set()
     for cell in cells:
         for l in conv_layers_of(cell):
@@ -119,12 +125,16 @@ def prepack(cells, stream=None, dgrad=True):
                     dimgs.append(t)
                     entries.append(dict(w=w, out=t, transpose_flip=True, **kw))
                 l._dgrad_cache = (imgs, dimgs)
-            if not l.sn and (l.cout == 64 or l.cout <= 4) and l._aff_bias is None:
+            if l.centred(BF16) and l.training:
+                if l._aff_center is None:
+                    centres.append(l.center_entry())
+            elif not l.sn and (l.cout == 64 or l.cout <= 4) and l._aff_bias is None:
                 aff = Tensor((2, 64), F32)
                 entries.append(dict(bias=l.p["bias"], cout=l.cout, out=aff))
                 l._aff_bias = aff
     ops.pack_weights_multi(entries, stream=stream)
-    return len(entries)
+    ops.bn_center_multi(centres, stream=stream)
+    return len(entries) + len(centres)
 
 
 class ConvLayer(Cell):
@@ -156,6 +166,9 @@ class ConvLayer(Cell):
         self._wimgs_prec = None
         self._aff = None        # epilogue vectors used by the current forward
         self._aff_bias = None   # cached (1, bias): valid until the parameters change
+        self._aff_center = None  # cached (1, bias - center) of the kink-centred training forward (bf16 mode)
+        self._center = None      # (64,) the offset itself (persistent buffer, rewritten when _aff_center is rebuilt)
+        self._center_used = None  # the offset of the CURRENT forward's stored y (None: not centred)
         self._aff_eval = None   # cached folded eval-mode BatchNorm: valid until parameters / moving stats change
         self._aff_sn = None     # (1/sigma, bias) written by the power-iteration kernel
         self._sigma = None      # (sigma, 1/sigma)
@@ -173,6 +186,7 @@ class ConvLayer(Cell):
         self._wimgs = None
         self._aff = None
         self._aff_bias = None
+        self._aff_center = None
         self._aff_eval = None
 
     def copy_from(self, other):
@@ -219,10 +233,32 @@ class ConvLayer(Cell):
                 self._aff_eval = ops.bn_fold_eval(self.p["gamma"], self.p["beta"], self.p["moving_mean"],
                                                   self.p["moving_variance"], self.p["bias"], stream=stream)
             self._aff = self._aff_eval
+        elif self.centred(dtype):
+            # training-mode BatchNorm, bf16 storage of y: store y minus the estimated LeakyReLU kink (bn_center_multi)
+            if self._aff_center is None:
+                ops.bn_center_multi([self.center_entry()], stream=stream)
+            self._aff = self._aff_center
+            self._center_used = self._center
         else:
             if self._aff_bias is None:
                 self._aff_bias = ops.affine_from_bias(self.p["bias"], None, stream=stream)
             self._aff = self._aff_bias
+        if not (self.bn and training and self.centred(dtype)):
+            self._center_used = None
+
+    def centred(self, dtype=None):
+        """Does the training-mode forward store its pre-BatchNorm output kink-centred?  (bf16 activations only: the
+        tf32 mode stores y unrounded, and the eval path folds BatchNorm into the conv epilogue and stores no y.)"""
+        return self.bn and self.cout == 64 and (dtype or ops.cl_dtype()) == BF16 and CENTRED_BN_STORAGE[0]
+
+    def center_entry(self):
+        """Allocate (once) the offset / epilogue-vector buffers and return this layer's row for ops.bn_center_multi."""
+        if self._center is None:
+            self._center = Tensor((64,), F32)
+        if self._aff_center is None:
+            self._aff_center = Tensor((2, 64), F32)
+        return (self.p["gamma"], self.p["beta"], self.p["moving_mean"], self.p["moving_variance"], self.p["bias"],
+                self._center, self._aff_center)
 
     def forward_cl(self, x_cl, residual=None, out=None, ws=None, tag="", stream=None, saved=None, stats=None,
                    raw=None):
@@ -243,7 +279,8 @@ class ConvLayer(Cell):
                                   wimgs=self._wimgs, stats=stats, stream=stream)
             sv = Tensor((4, 64), F32) if saved is not None else None
             x = ops.bn_train_fused_cl(y, stats, self.p["gamma"], self.p["beta"], self.p["moving_mean"],
-                                      self.p["moving_variance"], self.act, out=out, saved=sv, stream=stream)
+                                      self.p["moving_variance"], self.act, out=out, saved=sv, stream=stream,
+                                      center=self._center_used)
             self._aff_eval = None   # moving stats changed: a later eval-mode fold must be rebuilt
             if saved is not None:
                 saved.update(raw=y, bn=sv)

@@ -501,28 +501,44 @@ def bn_train_cl(y_cl, gamma, beta, moving_mean, moving_var, act=ACT_LRELU, out=N
 
 
 def bn_train_fused_cl(y_cl, stats, gamma, beta, moving_mean, moving_var, act=ACT_LRELU, out=None, saved=None,
-                      stream=None):
-    """One-pass training-mode BatchNorm (+LeakyReLU): `stats` is the fp64 (2,64) tensor filled by the producing conv's
-    epilogue (conv_cl(stats=...)).  Updates the moving statistics; `saved` (4,64) receives (scale, shift, mean, invstd)."""
+                      stream=None, center=None):
+    """One-pass training-mode BatchNorm + activation whose batch statistics were accumulated by the producing conv's
+    epilogue (conv_cl(stats=...)).  Updates the moving statistics; `saved` (4,64) receives (scale, shift, mean, invstd).
+    center: the per-channel offset the conv subtracted from y (kink-centred storage, bn_center_multi) — `saved` stays
+    in that centred frame, the moving mean gets it added back."""
     voxels = int(np.prod(y_cl.shape[:-1]))
     if out is None:
         out = Tensor(y_cl.shape, y_cl.dtype)
     fn = lib.hpvg_bn_train_apply_cl_f32 if y_cl.dtype == F32 else lib.hpvg_bn_train_apply_cl
     check(fn(_p(y_cl), voxels, _p(stats), _p(gamma), _p(beta), BN_EPS, BN_MOMENTUM,
-                                     _p(moving_mean), _p(moving_var), _p(saved), act, _p(out), _s(stream)),
+             _p(moving_mean), _p(moving_var), _p(saved), act, _p(out), _p(center), _s(stream)),
           "bn_train_apply")
     return out
 
 
+def bn_center_multi(layers, stream=None):
+    """layers: [(gamma, beta, moving_mean, moving_var, bias, center_out (64,), aff_out (2,64))] -> one launch computing
+    every layer's kink estimate and its conv epilogue vectors (1, bias - center)."""
+    n = len(layers)
+    if n == 0:
+        return
+    VP = ctypes.c_void_p * n
+    cols = [VP(*[t[i].ptr for t in layers]) for i in range(7)]
+    check(lib.hpvg_bn_center_multi(n, *cols, BN_EPS, _s(stream)), "bn_center_multi")
+
+
 def bn_moving_update_multi(items, stream=None):
-    """items: [(saved (4,64), moving_mean, moving_var)] in the order the forwards ran: moving = 0.9*moving + 0.1*batch."""
+    """items: [(saved (4,64), moving_mean, moving_var[, center or None])] in the order the forwards ran:
+    moving = 0.9*moving + 0.1*batch (the batch mean = saved mean + center when the layer's y was stored centred)."""
     n = len(items)
     if n == 0:
         return
     VP = ctypes.c_void_p * n
-    check(lib.hpvg_bn_moving_update_multi(n, VP(*[a.ptr for a, _, _ in items]), VP(*[b.ptr for _, b, _ in items]),
-                                          VP(*[c.ptr for _, _, c in items]), BN_EPS, BN_MOMENTUM, _s(stream)),
-          "bn_moving_update_multi")
+    cen = [it[3] if len(it) > 3 else None for it in items]
+    check(lib.hpvg_bn_moving_update_multi(n, VP(*[it[0].ptr for it in items]), VP(*[it[1].ptr for it in items]),
+                                          VP(*[it[2].ptr for it in items]),
+                                          VP(*[None if c is None else c.ptr for c in cen]), BN_EPS, BN_MOMENTUM,
+                                          _s(stream)), "bn_moving_update_multi")
 
 
 # ------------------------------------------------------------------------------------------------ spectral norm

@@ -137,13 +137,14 @@ def layer_forward_train(layer, x_cl, ws, key, stream=None, slab=None, defer=None
                           wimgs=layer._wimgs, stats=stats, stream=stream)
         a = ws.get(key + ".a", (N, T, H, W, layer.cout), x_cl.dtype)
         saved = ws.get(key + ".saved", (4, 64), F32)
+        cen = layer._center_used       # y is stored minus this offset (kink-centred bf16 storage), or None
         if defer is None:
             ops.bn_train_fused_cl(y, stats, layer.p["gamma"], layer.p["beta"], layer.p["moving_mean"],
-                                  layer.p["moving_variance"], layer.act, out=a, saved=saved, stream=stream)
+                                  layer.p["moving_variance"], layer.act, out=a, saved=saved, stream=stream, center=cen)
         else:
             ops.bn_train_fused_cl(y, stats, layer.p["gamma"], layer.p["beta"], None, None, layer.act, out=a, saved=saved,
-                                  stream=stream)
-            defer.append((saved, layer.p["moving_mean"], layer.p["moving_variance"]))
+                                  stream=stream, center=cen)
+            defer.append((saved, layer.p["moving_mean"], layer.p["moving_variance"], cen))
         layer._aff_eval = None
         ctx.update(y=y, a=a, saved=saved)
         return a, ctx

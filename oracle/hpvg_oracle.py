@@ -477,8 +477,19 @@ def conv_block(x, p, prefix, pad, training, bn=True, act=True, taps=None):
     if taps is not None:
         taps[prefix + "conv"] = y
     if bn:
-        if training:
-            y = _q(y)       # training mode stores the raw conv output in bf16 before the statistics pass
+        if training and _QUANT[0]:
+            # training mode stores the raw conv output in bf16 before the statistics pass — MINUS the estimated position
+            # of the LeakyReLU kink (kink-centred storage, csrc/elementwise.cu bn_center_multi_kernel): the offset comes
+            # from the moving statistics BEFORE this forward's update and the current gamma / beta, and is itself a
+            # bf16 value
+            nd = y.dim() - 2
+            pre = prefix + "1." + ("bn2d." if nd == 3 else "")
+            g, b = p[pre + "gamma"].detach(), p[pre + "beta"].detach()
+            cen = p[pre + "moving_mean"].detach().clone()
+            ok = g.abs() > 1e-3
+            cen[ok] = cen[ok] - (b[ok] * torch.sqrt(p[pre + "moving_variance"].detach()[ok] + BN_EPS) / g[ok])
+            cen = cen.to(torch.bfloat16).to(torch.float32).reshape([1, -1] + [1] * nd)
+            y = _q(y - cen) + cen
         y = batchnorm(y, p, prefix + "1.", training)
     if act:
         y = lrelu(y)

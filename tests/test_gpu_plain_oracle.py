@@ -16,16 +16,18 @@ from oracle import hpvg_oracle as orc
 from util import rel_l2
 
 pytestmark = pytest.mark.gpu
+import os
+CENTRED = os.environ.get("HPVG_CENTRED_BN", "1") != "0"
 # per precision mode: north_star's per-layer tolerance, then the stated tolerances of the multi-layer quantities
 # (measured values are printed by every test and tabulated in DESIGN.md §5.1)
 TOLS = {
     "tf32": dict(layer=1e-3, layer_bwd=1e-3, stage=2e-3, vae_out=2e-3, sample5=5e-3, net_fwd=2e-3, chain=2e-3, loss=1e-3, enc=2e-3,
                  e2e=1e-1, dloss=2e-3),
-    # bf16 "layer_bwd": a BatchNorm layer's backward reads the pre-BN activation y in its STORAGE precision; rounding y to
-    # bf16 moves ~2e-4 of the pre-activations across the LeakyReLU kink relative to the oracle's fp32 y (0.8 x the
-    # gradient on each): 1.3-3.3e-2 rel-L2 on the layer's gradients, measured.  With the same bf16 y on both sides the
-    # same kernels are within 4e-3 (tests/test_gpu_train.py, orc.bf16_emulation()).
-    "bf16": dict(layer=1e-2, layer_bwd=5e-2, stage=1e-2, vae_out=1e-2, sample5=5e-2, net_fwd=1e-2, chain=6e-2, loss=2e-2, enc=1e-2,
+    # bf16 "layer_bwd": a BatchNorm layer's backward reads the pre-BN activation y in its STORAGE precision.  Plain bf16
+    # storage moves ~1e-3 of the pre-activations across the LeakyReLU kink relative to the oracle's fp32 y (1.3-3.3e-2
+    # rel-L2 on the layer's gradients, measured with HPVG_CENTRED_BN=0); the kink-centred storage (y minus the estimated
+    # kink position, bn_center_multi) puts bf16's resolution where the mask is decided — north_star's 1e-2 holds.
+    "bf16": dict(layer=1e-2, layer_bwd=1e-2 if CENTRED else 5e-2, stage=1e-2, vae_out=1e-2, sample5=5e-2, net_fwd=1e-2, chain=2e-2 if CENTRED else 6e-2, loss=2e-2, enc=1e-2,
                  e2e=3e-1, dloss=2e-2),
 }
 
@@ -44,6 +46,27 @@ def _y_upload(hp, y):
     if ops.precision() == "tf32":
         return hp.from_numpy(np.ascontiguousarray(np.moveaxis(np.asarray(y, np.float32), 1, -1)))
     return ops.pack_cl(hp.from_numpy(y))
+
+
+def _steady_state(layer, y_ref):
+    """Moving statistics := the batch statistics of this forward — where they sit after a few training iterations on the
+    single video (momentum 0.9).  The kink-centred bf16 storage of y derives its offset from them."""
+    layer.p["moving_mean"].copy_from_host(y_ref.astype(np.float64).mean(axis=(0, 2, 3, 4)).astype(np.float32))
+    layer.p["moving_variance"].copy_from_host(y_ref.astype(np.float64).var(axis=(0, 2, 3, 4)).astype(np.float32))
+    layer.invalidate()
+
+
+def _bn_ctx_from_oracle(hp, layer, y_ref, gamma, beta):
+    """What the layer's own forward would have kept for its backward, built from the ORACLE's conv output: y in the
+    layer's storage frame and precision (bf16 mode: minus the layer's offset, rounded to bf16; tf32 mode: plain fp32) and
+    saved = (scale, shift, mean, invstd) in that frame."""
+    cen = layer._center_used.numpy().astype(np.float64) if layer._center_used is not None else np.zeros(64)
+    mean = y_ref.astype(np.float64).mean(axis=(0, 2, 3, 4)) - cen
+    invstd = 1.0 / np.sqrt(y_ref.astype(np.float64).var(axis=(0, 2, 3, 4)) + 1e-5)
+    g, b = gamma.astype(np.float64), beta.astype(np.float64)
+    y_c = (y_ref.astype(np.float64) - cen.reshape(1, -1, 1, 1, 1)).astype(np.float32)
+    saved = hp.from_numpy(np.stack([g * invstd, b - mean * g * invstd, mean, invstd]).astype(np.float32))
+    return _y_upload(hp, y_c), saved
 
 
 def _setup(hp, n_body, seed=3):
@@ -186,18 +209,14 @@ def test_per_layer_backward_teacher_forced(prec, shape):
         pre_n = "body.0.%d." % j
         xin = x3 if j == 0 else taps["body.0.%d.out" % (j - 1)].detach().numpy()
         x_cl = ops.pack_cl(hp.from_numpy(xin), c_pitch=ops.narrow_pitch() if j == 0 else 64)
+        y_ref = taps[pre_n + "conv"].detach().numpy()
+        _steady_state(layer, y_ref)
         a, ctx = T.layer_forward_train(layer, x_cl, ws, "tf%d" % j)
         e = rel_l2(ops.unpack_cl(a).numpy(), taps[pre_n + "out"].detach().numpy())
         worst_f = max(worst_f, e)
         assert e < tol["layer"], "layer %d forward (conv + batch statistics + BN + LeakyReLU) rel-L2 %.3e" % (j, e)
         # backward from the oracle's own forward tensors
-        y_ref = taps[pre_n + "conv"].detach().numpy()
-        mean = y_ref.astype(np.float64).mean(axis=(0, 2, 3, 4))
-        var = y_ref.astype(np.float64).var(axis=(0, 2, 3, 4))
-        invstd = 1.0 / np.sqrt(var + 1e-5)
-        gam, bet = pg[pre_n + "1.bn2d.gamma"].astype(np.float64), pg[pre_n + "1.bn2d.beta"].astype(np.float64)
-        ctx["y"] = _y_upload(hp, y_ref)
-        ctx["saved"] = hp.from_numpy(np.stack([gam * invstd, bet - mean * gam * invstd, mean, invstd]).astype(np.float32))
+        ctx["y"], ctx["saved"] = _bn_ctx_from_oracle(hp, layer, y_ref, pg[pre_n + "1.bn2d.gamma"], pg[pre_n + "1.bn2d.beta"])
         ga = taps[pre_n + "out"].grad.numpy()
         book = T.GradBook()
         dx = T.layer_backward(layer, ctx, ops.pack_cl(hp.from_numpy(ga)), book, ws, "tf%d" % j, need_dx=True)
@@ -363,14 +382,12 @@ def test_block_backward_chain_on_oracle_forward(prec):
         pre_n = "body.0.%d." % j
         xin = x3 if j == 0 else taps["body.0.%d.out" % (j - 1)].detach().numpy()
         y_ref = taps[pre_n + "conv"].detach().numpy()
-        mean = y_ref.astype(np.float64).mean(axis=(0, 2, 3, 4))
-        invstd = 1.0 / np.sqrt(y_ref.astype(np.float64).var(axis=(0, 2, 3, 4)) + 1e-5)
-        gam, bet = pg[pre_n + "1.bn2d.gamma"].astype(np.float64), pg[pre_n + "1.bn2d.beta"].astype(np.float64)
-        block.layers[j]._prepare_wimgs()
-        ctxs.append({"x": ops.pack_cl(hp.from_numpy(xin), c_pitch=ops.narrow_pitch() if j == 0 else 64), "layer": block.layers[j],
-                     "y": _y_upload(hp, y_ref),
-                     "saved": hp.from_numpy(np.stack([gam * invstd, bet - mean * gam * invstd, mean,
-                                                      invstd]).astype(np.float32))})
+        layer = block.layers[j]
+        _steady_state(layer, y_ref)
+        layer._prepare(True, None)            # filter banks + this forward's storage offset
+        y_st, saved = _bn_ctx_from_oracle(hp, layer, y_ref, pg[pre_n + "1.bn2d.gamma"], pg[pre_n + "1.bn2d.beta"])
+        ctxs.append({"x": ops.pack_cl(hp.from_numpy(xin), c_pitch=ops.narrow_pitch() if j == 0 else 64), "layer": layer,
+                     "y": y_st, "saved": saved})
     jt = opt.num_layer + 1
     tail = block.layers[jt]
     tail._prepare_wimgs()
