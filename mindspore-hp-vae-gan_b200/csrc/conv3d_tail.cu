@@ -15,12 +15,16 @@
 //
 // One CTA per SM (cta_group::1), 16h x 8w output tile walking along T.  Haloed plane = 18 x 10 = 180 voxels = 180 rows
 // of 128 B (64 bf16 channels, 128B swizzle): rows 0..127 -> MMA M=128, rows 128..191 -> MMA M=64 (rows >= 180 are
-// never gathered).  Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue.
+// never gathered).  Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 / 6..9 epilogue of the
+// even / odd output planes (accumulator stage and partial-sum buffer 0 / 1).  The kernel runs at the pace of its
+// epilogue (24 small MMAs per plane), and one group alone is a single warp per SM sub-partition walking a dependent
+// chain TMEM load -> shared store -> barrier -> 27 shared loads -> global store; the second group overlaps it.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include "conv3d_umma.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace hpvg {
@@ -36,7 +40,7 @@ constexpr int T_SLOTS = 6;
 constexpr int T_W_BYTES = 3 * 32 * 128;           // [dt][n = (dh*3+dw)*3+co (32 rows)][64 ci]  = 12288
 constexpr int T_PS = 27;                          // floats per voxel in the partial-sum buffer (odd: conflict-free)
 constexpr int T_PBUF_FLOATS = T_ROWS * T_PS;      // 4860
-constexpr int T_THREADS = 192;
+constexpr int T_THREADS = 320;                      // TMA warp, MMA warp, 2 groups of 4 epilogue warps
 constexpr int T_TMEM_COLS = 128;                  // 2 buffers x (32 cols M=128 tile + 32 cols M=64 tile)
 constexpr int T_SMEM = 1024 + T_W_BYTES + T_SLOTS * T_SLOT_STRIDE + 2 * T_PBUF_FLOATS * 4 + 64 + (2 * T_SLOTS + 5) * 8 + 16;
 
@@ -50,6 +54,7 @@ struct TailParams {
   float* out;            // fp32 NCDHW, cout_real channels
   int cout_real;
   const float* addend;   // optional fp32 NCDHW residual (added after scale/shift, before the activation)
+  int dbg;
 };
 
 // TF32: the same kernel over fp32 channels-last activations, 32 input channels per launch (a 128-byte row = 32 tf32
@@ -88,11 +93,12 @@ conv3d_tail_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
     mbar_init(w_full, 1);
     fence_mbar_init();
   }
+  if (warp == 1) tmem_alloc(tmem_ptr_sm, T_TMEM_COLS);
+  pdl_grid_sync();   // launch.cuh: global memory only from here on
   if (threadIdx.x < 4) {
     scale_sm[threadIdx.x] = threadIdx.x < p.cout_real ? p.scale[threadIdx.x] : 0.f;
     shift_sm[threadIdx.x] = threadIdx.x < p.cout_real ? p.shift[threadIdx.x] : 0.f;
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_sm, T_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -112,6 +118,7 @@ conv3d_tail_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
         for (int t = 0; t < T; ++t, ++j) {
           const uint32_t slot = j % T_SLOTS, ph = (j / T_SLOTS) & 1u;
           mbar_wait(&a_empty[slot], ph ^ 1u);
+          if (p.dbg & 8) { mbar_arrive(&a_full[slot]); continue; }
           mbar_expect_tx(&a_full[slot], T_PLANE_BYTES);
           tma_load_5d(planes + slot * T_SLOT_STRIDE, &tmap_in, &a_full[slot], 0, w0 - 1, h0 - 1, t, n);
         }
@@ -127,32 +134,40 @@ conv3d_tail_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
       const uint32_t w_addr = smem_u32(w_sm);
       const uint32_t planes_addr = smem_u32(planes);
       uint32_t j0 = 0, q = 0;
+      const uint32_t my_units = (static_cast<uint32_t>(p.n_units) - blockIdx.x + gridDim.x - 1u) / gridDim.x;
+      const uint32_t q_end = my_units * static_cast<uint32_t>(T);
+      // the tensor pipe idles while this thread waits between two planes (conv3d_umma.cu): the waits for the plane
+      // the dt = 2 taps read and for the NEXT plane's accumulator stage sit behind the MMAs of dt = 0, 1
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
         for (int pl = 0; pl < T; ++pl, ++q) {
           const uint32_t ab = q & 1u;
-          mbar_wait(&acc_empty[ab], ((q >> 1) & 1u) ^ 1u);
+          const uint32_t d1 = tmem_base + ab * 64, d2 = d1 + 32;
+          uint32_t accum = 0;
+          auto issue_dt = [&](int dt) {
+            const uint32_t a_base = planes_addr + ((j0 + pl + dt - 1) % T_SLOTS) * T_SLOT_STRIDE;
+            const uint32_t b_base = w_addr + dt * (32 * 128);
+            const uint64_t a0 = make_smem_desc(a_base, 16, 1024, 2);   // descriptors: one add per MMA (ptx.cuh)
+            const uint64_t b0 = make_smem_desc(b_base, 16, 1024, 2);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t bd = desc_add_lo(b0, desc_lo_delta(k * 32));
+              umma_ss<TF32>(d1, desc_add_lo(a0, desc_lo_delta(k * 32)), bd, idesc128, accum);
+              umma_ss<TF32>(d2, desc_add_lo(a0, desc_lo_delta(128 * 128 + k * 32)), bd, idesc64, accum);
+              accum = 1;
+            }
+          };
           if (pl == 0) mbar_wait(&a_full[j0 % T_SLOTS], (j0 / T_SLOTS) & 1u);
+          if (q < 2) mbar_wait(&acc_empty[ab], 1u);
+          tc_fence_after();
+          if (pl >= 1) issue_dt(0);
+          issue_dt(1);
           if (pl + 1 < T) {
             const uint32_t jj = j0 + pl + 1;
             mbar_wait(&a_full[jj % T_SLOTS], (jj / T_SLOTS) & 1u);
           }
+          if (q + 1 < q_end && q + 1 >= 2) mbar_wait(&acc_empty[ab ^ 1u], (((q + 1) >> 1) & 1u) ^ 1u);
           tc_fence_after();
-          const uint32_t d1 = tmem_base + ab * 64, d2 = d1 + 32;
-          uint32_t accum = 0;
-#pragma unroll 1
-          for (int dt = 0; dt < 3; ++dt) {
-            const int tin = pl + dt - 1;
-            if (tin < 0 || tin >= T) continue;
-            const uint32_t a_base = planes_addr + ((j0 + tin) % T_SLOTS) * T_SLOT_STRIDE;
-            const uint32_t b_base = w_addr + dt * (32 * 128);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t bd = make_smem_desc(b_base + k * 32, 16, 1024, 2);
-              umma_ss<TF32>(d1, make_smem_desc(a_base + k * 32, 16, 1024, 2), bd, idesc128, accum);
-              umma_ss<TF32>(d2, make_smem_desc(a_base + 128 * 128 + k * 32, 16, 1024, 2), bd, idesc64, accum);
-              accum = 1;
-            }
-          }
+          if (pl + 1 < T) issue_dt(2);
           umma_commit(&acc_full[ab]);
           if (pl >= 1) umma_commit(&a_empty[(j0 + pl - 1) % T_SLOTS]);
           if (pl == T - 1) umma_commit(&a_empty[(j0 + pl) % T_SLOTS]);
@@ -162,8 +177,9 @@ conv3d_tail_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
     }
     __syncwarp();
   } else {
-    // ======================================================================================= epilogue (4 warps)
+    // ======================================================================================= epilogue (2 x 4 warps)
     const int quad = warp & 3;
+    const uint32_t grp = static_cast<uint32_t>(warp - 2) >> 2;
     const int row = quad * 32 + lane;          // TMEM lane == P row (M=128 tile) == output voxel of the tile
     const int hh = row >> 3, ww = row & 7;
     // M=64 tile: P row 128 + i sits in lane (i/16)*32 + i%16
@@ -178,17 +194,22 @@ conv3d_tail_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
       const bool inb = (h < p.H) && (w < p.W);
       for (int pl = 0; pl < T; ++pl, ++q) {
         const uint32_t ab = q & 1u;
+        if (ab != grp) continue;
         float* pb = pbuf + ab * T_PBUF_FLOATS;
         mbar_wait(&acc_full[ab], (q >> 1) & 1u);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + ab * 64;
         uint32_t r1[32], r2[32];
+        if (!(p.dbg & 2)) {
         tmem_ld32(taddr, r1);
         tmem_ld32(taddr + 32, r2);
         tmem_ld_wait();
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_relaxed(&acc_empty[ab]);
+        if (p.dbg & 1) continue;
+        if (p.dbg & 16) { if (inb) p.out[(static_cast<size_t>(n) * p.cout_real) * chan_sz + (static_cast<size_t>(pl) * p.H + h) * p.W + w] = __uint_as_float(r1[0]); continue; }
         {
           float* dst = pb + row * T_PS;
 #pragma unroll
@@ -199,7 +220,8 @@ conv3d_tail_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
             for (int i = 0; i < T_PS; ++i) dst2[i] = __uint_as_float(r2[i]);
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // all 180 partial-sum rows of this plane are in shared memory
+        // all 180 partial-sum rows of this plane are in shared memory (one named barrier per group)
+        asm volatile("bar.sync %0, 128;" ::"r"(1u + grp) : "memory");
         float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
         for (int s = 0; s < 9; ++s) {
@@ -229,7 +251,7 @@ conv3d_tail_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
           for (int c = 0; c < 3; ++c)
             if (c < p.cout_real) p.out[idx[c]] = v[c];
         }
-        // no second barrier: the partial-sum buffer is double buffered and the next plane's barrier orders the reuse
+        asm volatile("bar.sync %0, 128;" ::"r"(3u + grp) : "memory");   // the gather is done before the buffer is rewritten
       }
     }
   }
@@ -286,6 +308,7 @@ const char* conv3d_tail_launch(const ConvLaunch& L, int sm_count, cudaStream_t s
   prm.out = static_cast<float*>(L.out);
   prm.cout_real = L.cout_real;
   prm.addend = L.addend;
+  { const char* e_ = getenv("HPVG_CONV_DBG"); prm.dbg = e_ ? atoi(e_) : 0; }
   if (prm.n_units < 1) return nullptr;
   static bool configured = false;
   if (!configured) {
@@ -297,8 +320,8 @@ const char* conv3d_tail_launch(const ConvLaunch& L, int sm_count, cudaStream_t s
     configured = true;
   }
   const int grid = prm.n_units < sm_count ? prm.n_units : sm_count;
-  if (tf32) conv3d_tail_kernel<true><<<grid, T_THREADS, T_SMEM, stream>>>(tmap, prm);
-  else conv3d_tail_kernel<false><<<grid, T_THREADS, T_SMEM, stream>>>(tmap, prm);
+  if (tf32) launch(conv3d_tail_kernel<true>, grid, T_THREADS, T_SMEM, stream, tmap, prm);
+  else launch(conv3d_tail_kernel<false>, grid, T_THREADS, T_SMEM, stream, tmap, prm);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

@@ -26,6 +26,7 @@
 
 #include "conv3d_umma.h"
 #include "det_reduce.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace hpvg {
@@ -36,7 +37,6 @@ constexpr int TILE_W = 8;
 constexpr int TILE_H = 16;
 constexpr int BOX_W = TILE_W + 2;
 constexpr int BOX_H = TILE_H + 2;
-constexpr int NUM_THREADS = 192;
 
 template <int MODE>
 struct Cfg;
@@ -48,6 +48,7 @@ struct Cfg<CONV_MODE_64_64> {
   static constexpr int PLANE_BYTES = BOX_H * BOX_W * 128, SLOT_STRIDE = 23552, SLOTS = 4;
   static constexpr int W_BYTES = 27 * ROWS_PER_CTA * 128, DT_BYTES = 9 * ROWS_PER_CTA * 128;
   static constexpr int ACC_STRIDE = 64, TMEM_COLS = 128;
+  static constexpr int EPI_GROUPS = 1;   // groups of 4 epilogue warps (the epilogue hides under the 108 MMAs of a plane)
   static constexpr int STAGES = 1;   // 16 KB output staging tiles for the TMA-store epilogue (what the 227 KB leave)
 };
 // MODE 1: Cin 64 -> Cout <= 16 (tail convs 64->3 / 64->1)
@@ -58,6 +59,7 @@ struct Cfg<CONV_MODE_64_16> {
   static constexpr int PLANE_BYTES = BOX_H * BOX_W * 128, SLOT_STRIDE = 23552, SLOTS = 6;
   static constexpr int W_BYTES = 27 * ROWS_PER_CTA * 128, DT_BYTES = 9 * ROWS_PER_CTA * 128;
   static constexpr int ACC_STRIDE = 32, TMEM_COLS = 64;
+  static constexpr int EPI_GROUPS = 1;
   static constexpr int STAGES = 0;
 };
 // MODE 2: Cin <= 8 -> Cout 64 (head convs 3->64); no-swizzle planes of 16 B per voxel, taps paired through LBO
@@ -68,6 +70,11 @@ struct Cfg<CONV_MODE_8_64> {
   static constexpr int PLANE_BYTES = BOX_H * BOX_W * 16, SLOT_STRIDE = 3072, SLOTS = 8;
   static constexpr int W_BYTES = 3 * 5 * 1024, DT_BYTES = 5 * 1024;
   static constexpr int ACC_STRIDE = 64, TMEM_COLS = 128;
+  // The head conv issues 15 MMAs per output plane against 108 for the 64 -> 64 layer, so it runs at the pace of its
+  // epilogue: one warp per SM sub-partition walking ld -> 64 x (affine, activation, pack) -> 8 stores per plane at an
+  // issue rate of 0.22 (profiles/r2_ncu_head_conv_store_experiment.csv).  Two groups of 4 epilogue warps, one per
+  // accumulator stage, put two warps on every sub-partition and overlap one plane's TMEM load with the other's stores.
+  static constexpr int EPI_GROUPS = 2;
   static constexpr int STAGES = 0;   // measured: the head conv is 14 % SLOWER through the staged TMA store (0.359 vs 0.316 ms
                                      // at 8 x 13x192x257) although its L2 write requests drop 8x — its epilogue warps are
                                      // latency-bound on ld -> math -> store per plane, and the two CTA barriers add to that
@@ -86,6 +93,9 @@ struct Cfg<CONV_MODE_T4_64> : Cfg<CONV_MODE_8_64> {
   static constexpr bool TF32 = true;
   static constexpr int CIN = 4;
 };
+
+template <int MODE>
+constexpr int num_threads() { return 64 + 128 * Cfg<MODE>::EPI_GROUPS; }   // TMA warp, MMA warp, epilogue warps
 
 constexpr int STAGE_BYTES = TILE_H * TILE_W * 128;   // one CTA's output tile: 128 voxels x 64 bf16 channels
 
@@ -281,7 +291,7 @@ __device__ __forceinline__ void epilogue_f32_dispatch(int act, uint32_t (&r0)[32
 }
 
 template <int MODE, bool STATS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(num_threads<MODE>(), 1)
 conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
                    const __grid_constant__ ConvParams p) {
   using C = Cfg<MODE>;
@@ -325,11 +335,13 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
     }
     fence_mbar_init();
   }
+  if (warp == 1) tmem_alloc_pair(tmem_ptr_sm, C::TMEM_COLS);
+  // barriers and TMEM are set up while the previous kernel of the stream drains (launch.cuh); global memory from here on
+  pdl_grid_sync();
   if (threadIdx.x < 64) {
     scale_sm[threadIdx.x] = threadIdx.x < C::NOUT ? p.scale[threadIdx.x] : 0.f;
     shift_sm[threadIdx.x] = threadIdx.x < C::NOUT ? p.shift[threadIdx.x] : 0.f;
   }
-  if (warp == 1) tmem_alloc_pair(tmem_ptr_sm, C::TMEM_COLS);
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -366,6 +378,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
           const uint32_t slot = j % C::SLOTS;
           const uint32_t ph = (j / C::SLOTS) & 1u;
           mbar_wait(&a_empty[slot], ph ^ 1u);
+          if (p.dbg & 8) { if (rank == 0) mbar_arrive(&a_full[slot]); continue; }
           if (rank == 0) mbar_expect_tx(&a_full[slot], 2u * C::PLANE_BYTES);
           uint32_t dst_bar = leader_full[0];
 #pragma unroll
@@ -397,69 +410,85 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
       uint32_t j0 = 0, q = 0;
       int g0, g1;
       work_range(pair, n_pairs, p, g0, g1);
+      const uint32_t q_end = static_cast<uint32_t>(g1 - g0);   // output planes of this pair
+      // The tensor pipe runs only a few MMAs behind this thread, so whatever the thread does BETWEEN the last MMA of
+      // one plane and the first MMA of the next is idle time of the pipe (measured: ~1100 cycles per plane when every
+      // wait sat there — a third of the 64 -> 64 layer's time and two thirds of the head conv's).  Hence the order:
+      //   taps of dt = 0, 1 (planes pl-1, pl: waited for during the previous plane)
+      //   -> wait for plane pl+1 AND for the next plane's accumulator stage, behind the MMAs just queued
+      //   -> taps of dt = 2 -> commits.
       for (int g = g0; g < g1;) {
         const Item it = next_item(g, g1, T);
         g += it.t1 - it.t0;
         const int tlo = max(it.t0 - 1, 0), thi = min(it.t1, T - 1);
         int arrived = tlo;                       // input planes [tlo, arrived) of this item have been waited for
-        for (int pl = it.t0; pl < it.t1; ++pl, ++q) {
-          const uint32_t ab = q & 1u;
-          mbar_wait(&acc_empty[ab], ((q >> 1) & 1u) ^ 1u);
-          for (const int need = min(pl + 1, T - 1); arrived <= need; ++arrived) {
+        auto plane_slot = [&](int t) { return (j0 + static_cast<uint32_t>(t - tlo)) % C::SLOTS; };
+        auto wait_planes = [&](int need) {
+          for (; arrived <= need; ++arrived) {
             const uint32_t jj = j0 + static_cast<uint32_t>(arrived - tlo);
             mbar_wait(&a_full[jj % C::SLOTS], (jj / C::SLOTS) & 1u);
           }
-          tc_fence_after();
+        };
+        for (int pl = it.t0; pl < it.t1; ++pl, ++q) {
+          const uint32_t ab = q & 1u;
           const uint32_t d_tmem = tmem_base + ab * C::ACC_STRIDE;
           uint32_t accum = 0;
-#pragma unroll 1
-          for (int dt = 0; dt < 3; ++dt) {
-            const int tin = pl + dt - 1;
-            if (tin < 0 || tin >= T) continue;
+          auto issue_dt = [&](int dt) {
             if (!(w_ready & (1u << dt))) {
               mbar_wait(&w_full[dt], 0);
               mbar_wait(&w_peer[dt], 0);
               tc_fence_after();
               w_ready |= 1u << dt;
             }
-            const uint32_t slot = (j0 + static_cast<uint32_t>(tin - tlo)) % C::SLOTS;
-            const uint32_t a_base = planes_addr + slot * C::SLOT_STRIDE;
+            const uint32_t a_base = planes_addr + plane_slot(pl + dt - 1) * C::SLOT_STRIDE;
             const uint32_t b_base = w_addr + dt * C::DT_BYTES;
             if constexpr (C::HEAD) {
               // 9 in-plane taps, 8 channels (16 B) each -> 5 MMAs of K=16: (tap0 | zero-weight dummy), (1|2) ... (7|8)
               // (tf32: 4 channels per 16-byte voxel, K = 8: the same two 16-byte K groups)
+              const uint64_t a0 = make_smem_desc(a_base, 0, BOX_W * 16, 0);   // LBO chosen per tap pair below
+              const uint64_t b0 = make_smem_desc(b_base, C::ROWS_PER_CTA * 16, 128, 0);
 #pragma unroll
               for (int s = 0; s < 5; ++s) {
                 const int ta = (s == 0) ? 0 : 2 * s - 1;
                 const int tb = (s == 0) ? 1 : 2 * s;
                 const uint32_t offa = ((ta / 3) * BOX_W + (ta % 3)) * 16;
                 const uint32_t offb = ((tb / 3) * BOX_W + (tb % 3)) * 16;
-                const uint64_t ad = make_smem_desc(a_base + offa, offb - offa, BOX_W * 16, 0);
-                const uint64_t bd = make_smem_desc(b_base + s * 1024, C::ROWS_PER_CTA * 16, 128, 0);
-                umma_ss_pair<C::TF32>(d_tmem, ad, bd, idesc, accum);
+                umma_ss_pair<C::TF32>(d_tmem, desc_add_lo(a0, desc_lo_delta(offa, offb - offa)),
+                                      desc_add_lo(b0, desc_lo_delta(s * 1024)), idesc, accum);
                 accum = 1;
               }
             } else {
+              const uint64_t a0 = make_smem_desc(a_base, 16, BOX_W * 128, 2);
+              const uint64_t b0 = make_smem_desc(b_base, 16, 1024, 2);
 #pragma unroll
               for (int s = 0; s < 9; ++s) {
-                const uint32_t a_tap = a_base + ((s / 3) * BOX_W + (s % 3)) * 128;
-                const uint32_t b_tap = b_base + s * (C::ROWS_PER_CTA * 128);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  const uint64_t ad = make_smem_desc(a_tap + k * 32, 16, BOX_W * 128, 2);
-                  const uint64_t bd = make_smem_desc(b_tap + k * 32, 16, 1024, 2);
-                  umma_ss_pair<C::TF32>(d_tmem, ad, bd, idesc, accum);
+                  umma_ss_pair<C::TF32>(d_tmem, desc_add_lo(a0, desc_lo_delta(((s / 3) * BOX_W + (s % 3)) * 128 + k * 32)),
+                                        desc_add_lo(b0, desc_lo_delta(s * (C::ROWS_PER_CTA * 128) + k * 32)), idesc,
+                                        accum);
                   accum = 1;
                 }
               }
             }
-          }
+          };
+          // (steady state: nothing to wait for here — see below; the first plane of an item waits for its own planes,
+          // the first two planes of the pair find their accumulator stages free)
+          wait_planes(pl);
+          if (q < 2) mbar_wait(&acc_empty[ab], 1u);
+          tc_fence_after();
+          if (pl - 1 >= 0) issue_dt(0);
+          issue_dt(1);
+          if (pl + 1 < T) wait_planes(pl + 1);
+          if (q + 1 < q_end && q + 1 >= 2) mbar_wait(&acc_empty[ab ^ 1u], (((q + 1) >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          if (pl + 1 < T) issue_dt(2);
           umma_commit_pair(&acc_full[ab], 3);
           // plane pl-1 has fed its last output plane; the item's last output also frees planes pl and pl+1
-          if (pl - 1 >= tlo) umma_commit_pair(&a_empty[(j0 + static_cast<uint32_t>(pl - 1 - tlo)) % C::SLOTS], 3);
+          if (pl - 1 >= tlo) umma_commit_pair(&a_empty[plane_slot(pl - 1)], 3);
           if (pl == it.t1 - 1) {
-            umma_commit_pair(&a_empty[(j0 + static_cast<uint32_t>(pl - tlo)) % C::SLOTS], 3);
-            if (pl + 1 <= thi) umma_commit_pair(&a_empty[(j0 + static_cast<uint32_t>(pl + 1 - tlo)) % C::SLOTS], 3);
+            umma_commit_pair(&a_empty[plane_slot(pl)], 3);
+            if (pl + 1 <= thi) umma_commit_pair(&a_empty[plane_slot(pl + 1)], 3);
           }
         }
         j0 += static_cast<uint32_t>(thi - tlo + 1);
@@ -471,8 +500,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
     }
     __syncwarp();
   } else {
-    // =========================================================================== epilogue (both CTAs, 4 warps)
+    // =========================================================================== epilogue (both CTAs, 4 warps per group)
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const uint32_t grp = static_cast<uint32_t>(warp - 2) >> 2;   // EPI_GROUPS == 2: group g owns accumulator stage g
     const int row = quad * 32 + lane;          // accumulator row == voxel of this CTA's tile
     const int hh = row >> 3, ww = row & 7;
     uint32_t leader_empty[2];
@@ -516,18 +546,22 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
       const bool inb = (h < p.H) && (w < p.W);
       for (int pl = it.t0; pl < it.t1; ++pl, ++q) {
         const uint32_t ab = q & 1u;
+        if (C::EPI_GROUPS == 2 && ab != grp) continue;
         mbar_wait(&acc_full[ab], (q >> 1) & 1u);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + ab * C::ACC_STRIDE;
         const size_t vox = ((static_cast<size_t>(un.n) * T + pl) * p.H + h) * p.W + w;
         if constexpr (C::NOUT == 64) {
           uint32_t r0[32], r1[32];
+          if (!(p.dbg & 2)) {
           tmem_ld32(taddr, r0);
           tmem_ld32(taddr + 32, r1);
           tmem_ld_wait();
+          }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster_relaxed(leader_empty[ab]);
+          if (p.dbg & 1) continue;
           if constexpr (!STATS) {
             if (inb) {
               if (p.out_mode == CONV_OUT_F32_RAW) {
@@ -686,16 +720,22 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
       {
         // all MMAs of this pair have completed (the last acc_full fired), so the plane ring is free: use it to combine
         // the 4 epilogue warps, then one fp64 atomic per channel and statistic per CTA.
-        float* red = reinterpret_cast<float*>(planes);   // [4 warps][2 stats][64 ch]
-        red[(quad * 2 + 0) * 64 + 2 * lane] = st_s0;
-        red[(quad * 2 + 0) * 64 + 2 * lane + 1] = st_s1;
-        red[(quad * 2 + 1) * 64 + 2 * lane] = st_q0;
-        red[(quad * 2 + 1) * 64 + 2 * lane + 1] = st_q1;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int t = threadIdx.x - 64;   // 0..127 : statistic (t >> 6), channel (t & 63)
-        const float tot = red[t] + red[128 + t] + red[256 + t] + red[384 + t];
-        // CTA partials are summed in CTA order by whichever CTA finishes last: bitwise reproducible statistics
-        det_reduce_128<true>(static_cast<double>(tot), t, true, blockIdx.x, gridDim.x, p.det, p.stats, p.stats + 64, true);
+        float* red = reinterpret_cast<float*>(planes);   // [epilogue warps][2 stats][64 ch]
+        const int ew = warp - 2;
+        red[(ew * 2 + 0) * 64 + 2 * lane] = st_s0;
+        red[(ew * 2 + 0) * 64 + 2 * lane + 1] = st_s1;
+        red[(ew * 2 + 1) * 64 + 2 * lane] = st_q0;
+        red[(ew * 2 + 1) * 64 + 2 * lane + 1] = st_q1;
+        if constexpr (C::EPI_GROUPS == 2) asm volatile("bar.sync 3, 256;" ::: "memory");
+        else asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (ew < 4) {
+          const int t = threadIdx.x - 64;   // 0..127 : statistic (t >> 6), channel (t & 63)
+          float tot = red[t] + red[128 + t] + red[256 + t] + red[384 + t];
+          if constexpr (C::EPI_GROUPS == 2) tot += red[512 + t] + red[640 + t] + red[768 + t] + red[896 + t];
+          // CTA partials are summed in CTA order by whichever CTA finishes last: bitwise reproducible statistics
+          det_reduce_128<true>(static_cast<double>(tot), t, true, blockIdx.x, gridDim.x, p.det, p.stats, p.stats + 64,
+                               true);
+        }
       }
     }
   }
@@ -739,7 +779,7 @@ cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& tmap_out, co
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  conv3d_umma_kernel<MODE, STATS><<<dim3(2 * n_pairs), dim3(NUM_THREADS), smem, stream>>>(tmap, tmap_out, prm);
+  launch(conv3d_umma_kernel<MODE, STATS>, dim3(2 * n_pairs), dim3(num_threads<MODE>()), smem, stream, tmap, tmap_out, prm);
   return cudaGetLastError();
 }
 
@@ -782,6 +822,7 @@ const char* conv3d_umma_launch(const ConvLaunch& L, cudaStream_t stream) {
                                        (reinterpret_cast<uintptr_t>(L.mask) & 15)))
     return "LRELU_MASK needs a 16-byte aligned bf16 mask tensor and the bf16 output mode";
   ConvParams prm;
+  { const char* e_ = getenv("HPVG_CONV_DBG"); prm.dbg = e_ ? atoi(e_) : 0; }
   prm.N = L.N;
   prm.T = L.T;
   prm.H = L.H;
@@ -987,6 +1028,7 @@ __device__ __forceinline__ void pack_weights_element(const float* __restrict__ w
 __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin, int kt, int mode,
                                     int transpose_flip, int cin_off, int cout_off, int w_cout, int w_cin,
                                     __nv_bfloat16* __restrict__ img, int total) {
+  pdl_grid_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < total)
     pack_weights_element(w, cout, cin, kt, mode, transpose_flip, cin_off, cout_off, w_cout, w_cin, img, idx);
@@ -996,6 +1038,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int c
 // filter banks of its trainable layers, each a 3-4 us launch on the critical path of a launch-latency-bound step.
 // blockIdx.y selects the table entry; mode < 0 marks an "affine" entry: img = fp32 [2][64] = (1 | 1/sigma, bias).
 __global__ void pack_weights_multi_kernel(const __grid_constant__ PackTable tab) {
+  pdl_grid_sync();
   const PackEntry& e = tab.e[blockIdx.y];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= e.total) return;
@@ -1014,6 +1057,7 @@ __global__ void pack_weights_multi_kernel(const __grid_constant__ PackTable tab)
 __global__ void pack_weights_tf32_kernel(const float* __restrict__ w, int cout, int cin, int kt, int mode,
                                          int transpose_flip, int cin_off, int cout_off, int w_cin,
                                          float* __restrict__ img, int total) {
+  pdl_grid_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   int co, ci, dt, dh, dw;
@@ -1089,14 +1133,14 @@ const char* conv3d_pack_weights(const float* w, int w_cout, int w_cin, int kt, i
   if (kt != 1 && kt != 3) return "kernel depth must be 1 or 3";
   if (conv_mode_is_tf32(mode)) {
     const int n = conv3d_umma_wimg_bytes(mode) / 4;
-    pack_weights_tf32_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w, cout, cin, kt, mode, transpose_flip, cin_off,
+    launch(pack_weights_tf32_kernel, (n + 255) / 256, 256, 0, stream, w, cout, cin, kt, mode, transpose_flip, cin_off,
                                                                    cout_off, w_cin, static_cast<float*>(img), n);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
   }
   const int total = conv3d_umma_wimg_bytes(mode) / 2;
   if (total == 0) return "unknown conv mode";
-  pack_weights_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w, cout, cin, kt, mode, transpose_flip, cin_off,
+  launch(pack_weights_kernel, (total + 255) / 256, 256, 0, stream, w, cout, cin, kt, mode, transpose_flip, cin_off,
                                                                 cout_off, w_cout, w_cin,
                                                                 static_cast<__nv_bfloat16*>(img), total);
   cudaError_t e = cudaGetLastError();
@@ -1121,7 +1165,7 @@ const char* conv3d_pack_weights_multi(const PackEntry* entries, int n, cudaStrea
       }
       max_total = e.total > max_total ? e.total : max_total;
     }
-    pack_weights_multi_kernel<<<dim3((max_total + 255) / 256, cnt), 256, 0, stream>>>(tab);
+    launch(pack_weights_multi_kernel, dim3((max_total + 255) / 256, cnt), 256, 0, stream, tab);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cudaGetErrorString(e);
   }

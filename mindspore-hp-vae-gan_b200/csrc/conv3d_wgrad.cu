@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include "conv3d_umma.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace hpvg {
@@ -67,6 +68,7 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_sm, 512);
+  pdl_grid_sync();   // launch.cuh: global memory only from here on
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -116,24 +118,28 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         tc_fence_after();
         const uint32_t xs = smem_u32(sm + s * WG_STAGE);
         const uint32_t gs = xs + WG_X_STRIDE;
+        const uint64_t x0 = make_smem_desc(xs, 0, 1024, 2);    // descriptors: one add per MMA (ptx.cuh); LBO per tap pair
+        const uint64_t g0 = make_smem_desc(gs, 16, 1024, 2);
 #pragma unroll 1
         for (int hh = 0; hh < WG_NH; ++hh) {
+          const uint64_t xh = desc_add_lo(x0, static_cast<uint32_t>(hh * WG_XP * 128) >> 4);
+          const uint64_t gh = desc_add_lo(g0, static_cast<uint32_t>(hh * WG_WS * 128) >> 4);
 #pragma unroll
           for (int ks = 0; ks < WG_WS / 16; ++ks) {
             if (ks >= nks) break;
-            const uint64_t bd = make_smem_desc(gs + (hh * WG_WS + ks * 16) * 128, 16, 1024, 2);
+            const uint64_t bd = desc_add_lo(gh, desc_lo_delta(ks * 16 * 128));
             // nine taps in five MMAs: any two taps whose A tiles differ by a CONSTANT byte offset stack along M through
             // the descriptor's leading-dimension offset (second 64-channel block = first + LBO).
             //   acc 0..2: (dh 0, dw) + (dh 1, dw)   LBO = one x row      acc 3: (dh 2, dw 0) + (dh 2, dw 1)   LBO = one voxel
             //   acc 4   : (dh 2, dw 2) alone (M = 64)
-            const uint32_t a_row0 = xs + ((hh * WG_XP) + ks * 16) * 128;
 #pragma unroll
             for (int dw = 0; dw < 3; ++dw)
-              umma_bf16(tmem_base + dw * 64, make_smem_desc(a_row0 + dw * 128, WG_XP * 128, 1024, 2), bd, idesc128,
-                        accum);
-            const uint32_t a_row2 = a_row0 + 2 * WG_XP * 128;
-            umma_bf16(tmem_base + 3 * 64, make_smem_desc(a_row2, 128, 1024, 2), bd, idesc128, accum);
-            umma_bf16(tmem_base + 4 * 64, make_smem_desc(a_row2 + 2 * 128, WG_XP * 128, 1024, 2), bd, idesc64, accum);
+              umma_bf16(tmem_base + dw * 64, desc_add_lo(xh, desc_lo_delta((ks * 16 + dw) * 128, WG_XP * 128)), bd,
+                        idesc128, accum);
+            constexpr uint32_t ROW2 = 2 * WG_XP * 128;
+            umma_bf16(tmem_base + 3 * 64, desc_add_lo(xh, desc_lo_delta(ROW2 + ks * 16 * 128, 128)), bd, idesc128, accum);
+            umma_bf16(tmem_base + 4 * 64, desc_add_lo(xh, desc_lo_delta(ROW2 + (ks * 16 + 2) * 128, WG_XP * 128)), bd,
+                      idesc64, accum);
             accum = 1;
           }
         }
@@ -206,6 +212,7 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 // dW[(co+co_off)][(ci+ci_off)][tap] (+)= sum_g partial[g][tap][ci][co]    (tap stride = 1; layout (Cout, Cin, kt,3,3))
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int groups, float* __restrict__ dw, int w_cin,
                                     int kt, int co_off, int co_n, int ci_off, int ci_n, int accumulate, float scale) {
+  pdl_grid_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over 27*64*64, co fastest (coalesced partial reads)
   if (idx >= 27 * 4096) return;
   const int co = idx & 63, ci = (idx >> 6) & 63, tap = idx >> 12;
@@ -254,7 +261,7 @@ bool make_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, int pitch, in
 
 void wgrad_reduce_launch(const float* partial, int groups, float* dw, int w_cin, int kt, int co_off, int co_n,
                          int ci_off, int ci_n, int accumulate, float scale, cudaStream_t stream) {
-  wgrad_reduce_kernel<<<(27 * 4096 + 255) / 256, 256, 0, stream>>>(partial, groups, dw, w_cin, kt, co_off, co_n, ci_off,
+  launch(wgrad_reduce_kernel, (27 * 4096 + 255) / 256, 256, 0, stream, partial, groups, dw, w_cin, kt, co_off, co_n, ci_off,
                                                                   ci_n, accumulate, scale);
 }
 
@@ -291,10 +298,10 @@ const char* conv3d_wgrad_launch(const void* x, int x_pitch, const void* gy, int 
     if (e != cudaSuccess) return cudaGetErrorString(e);
     configured = true;
   }
-  conv3d_wgrad_kernel<<<3 * groups, WG_THREADS, WG_SMEM, stream>>>(mx, mg, p);
+  launch(conv3d_wgrad_kernel, 3 * groups, WG_THREADS, WG_SMEM, stream, mx, mg, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cudaGetErrorString(e);
-  wgrad_reduce_kernel<<<(27 * 4096 + 255) / 256, 256, 0, stream>>>(workspace, groups, dw, w_cin, kt, co_off, co_n,
+  launch(wgrad_reduce_kernel, (27 * 4096 + 255) / 256, 256, 0, stream, workspace, groups, dw, w_cin, kt, co_off, co_n,
                                                                   ci_off, ci_n, accumulate, scale);
   e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

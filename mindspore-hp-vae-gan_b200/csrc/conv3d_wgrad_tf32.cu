@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include "conv3d_umma.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace hpvg {
@@ -77,6 +78,7 @@ conv3d_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_sm, 256);
+  pdl_grid_sync();   // launch.cuh: global memory only from here on
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -125,19 +127,21 @@ conv3d_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
         tc_fence_after();
         const uint32_t xs = smem_u32(sm + s * WT_STAGE);
         const uint32_t gs = xs + WT_X_STRIDE;
+        const uint64_t x0 = make_smem_desc(xs, 128, 512, WT_LAYOUT);   // descriptors: one add per MMA (ptx.cuh)
+        const uint64_t g0 = make_smem_desc(gs, WT_GH_BYTES, 512, WT_LAYOUT);
 #pragma unroll 1
         for (int hh = 0; hh < WT_NH; ++hh) {
+          const uint64_t xh = desc_add_lo(x0, static_cast<uint32_t>(hh * WT_XP * 128) >> 4);
+          const uint64_t gh = desc_add_lo(g0, static_cast<uint32_t>(hh * WT_WS * 128) >> 4);
 #pragma unroll
           for (int ks = 0; ks < WT_WS / 8; ++ks) {
             if (ks >= nks) break;
             // B: gy row hh, voxels [8ks, 8ks+8): N = 64 = two 32-channel atoms WT_GH_BYTES apart, K = two 4-voxel atoms
-            const uint64_t bd = make_smem_desc(gs + (hh * WT_WS + ks * 8) * 128, WT_GH_BYTES, 512, WT_LAYOUT);
+            const uint64_t bd = desc_add_lo(gh, desc_lo_delta(ks * 8 * 128));
             // A: x rows hh + dh, the same voxels shifted by dw = 0..3 (atom stride = one voxel); accumulator dh
 #pragma unroll
-            for (int dh = 0; dh < 3; ++dh) {
-              const uint32_t a_addr = xs + ((hh + dh) * WT_XP + ks * 8) * 128;
-              umma_tf32(tmem_base + dh * 64, make_smem_desc(a_addr, 128, 512, WT_LAYOUT), bd, idesc, accum);
-            }
+            for (int dh = 0; dh < 3; ++dh)
+              umma_tf32(tmem_base + dh * 64, desc_add_lo(xh, desc_lo_delta((dh * WT_XP + ks * 8) * 128)), bd, idesc, accum);
             accum = 1;
           }
         }
@@ -255,7 +259,7 @@ const char* conv3d_wgrad_tf32_launch(const void* x, int x_pitch, const void* gy,
     if (e != cudaSuccess) return cudaGetErrorString(e);
     configured = true;
   }
-  conv3d_wgrad_tf32_kernel<<<3 * p.halves * groups, WT_THREADS, WT_SMEM, stream>>>(mx, mg, p);
+  launch(conv3d_wgrad_tf32_kernel, 3 * p.halves * groups, WT_THREADS, WT_SMEM, stream, mx, mg, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cudaGetErrorString(e);
   wgrad_reduce_launch(workspace, groups, dw, w_cin, kt, co_off, co_n, ci_off, ci_n, accumulate, scale, stream);

@@ -7,6 +7,7 @@
 #include <cstdint>
 
 #include "det_reduce.cuh"
+#include "launch.cuh"
 #include "elementwise.h"
 
 namespace hpvg {
@@ -39,6 +40,7 @@ __device__ __forceinline__ uint4 xin_voxel(const float (&v)[8], int f32) {
 // thread = (voxel, 8-channel group); consecutive threads walk consecutive voxels so the fp32 side is coalesced.
 __global__ void pack_cl_kernel(const float* __restrict__ x, int C, long long sp /*T*H*W*/, long long voxels,
                                __nv_bfloat16* __restrict__ y, int c_pitch, int c_off, int groups) {
+  pdl_grid_sync();
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= voxels * groups) return;
   const int g = static_cast<int>(gid / voxels);
@@ -59,6 +61,7 @@ __global__ void pack_cl_kernel(const float* __restrict__ x, int C, long long sp 
 // would write 16 bytes out of every 128); only group 0 reads anything.
 __global__ void pack_cl_skinny_kernel(const float* __restrict__ x, int C, long long sp, long long voxels,
                                       __nv_bfloat16* __restrict__ y, int c_pitch, int c_off, int groups) {
+  pdl_grid_sync();
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= voxels * groups) return;
   const long long v = gid / groups;
@@ -76,6 +79,7 @@ __global__ void pack_cl_skinny_kernel(const float* __restrict__ x, int C, long l
 
 __global__ void unpack_cl_kernel(const __nv_bfloat16* __restrict__ x, int C, long long sp, long long voxels,
                                  int c_pitch, int c_off, float* __restrict__ y, int groups) {
+  pdl_grid_sync();
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= voxels * groups) return;
   const int g = static_cast<int>(gid / voxels);
@@ -101,6 +105,7 @@ constexpr int PK_VOX = 64, PK_PITCH = 33;
 __global__ void __launch_bounds__(256)
 pack_cl_tiled_kernel(const float* __restrict__ x, int C, long long sp, long long voxels, __nv_bfloat16* __restrict__ y,
                      int c_pitch, int c_off, int groups) {
+  pdl_grid_sync();
   __shared__ uint32_t tile[PK_VOX * PK_PITCH];
   const int cb = blockIdx.y * 64;                      // first channel of this block's 64-channel slab
   const long long v0 = static_cast<long long>(blockIdx.x) * PK_VOX;
@@ -135,6 +140,7 @@ pack_cl_tiled_kernel(const float* __restrict__ x, int C, long long sp, long long
 __global__ void __launch_bounds__(256)
 unpack_cl_tiled_kernel(const __nv_bfloat16* __restrict__ x, int C, long long sp, long long voxels, int c_pitch, int c_off,
                        float* __restrict__ y, int groups) {
+  pdl_grid_sync();
   __shared__ uint32_t tile[PK_VOX * PK_PITCH];
   const int cb = blockIdx.y * 64;
   const long long v0 = static_cast<long long>(blockIdx.x) * PK_VOX;
@@ -236,6 +242,7 @@ struct ResizeGeom {
 };
 
 __global__ void resize3d_fwd_kernel(const float* __restrict__ x, long long NC, ResizeGeom g, float* __restrict__ y) {
+  pdl_grid_sync();
   const long long total = NC * g.To * g.Ho * g.Wo;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -268,6 +275,7 @@ __device__ __forceinline__ void cand_range(int i, int n_out, float scale, int al
 
 __global__ void resize3d_bwd_kernel(const float* __restrict__ gy, long long NC, ResizeGeom g,
                                     float* __restrict__ gx) {
+  pdl_grid_sync();
   const long long total = NC * g.Ti * g.Hi * g.Wi;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -306,6 +314,7 @@ __global__ void resize3d_bwd_kernel(const float* __restrict__ gy, long long NC, 
 
 __global__ void linear_taps_kernel(int n_in, int n_out, float scale, int align, int* i0, int* i1, float* l0,
                                    float* l1) {
+  pdl_grid_sync();
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= n_out) return;
   const Tap t = linear_tap(o, n_in, scale, align);
@@ -476,6 +485,7 @@ __device__ __forceinline__ void build_th_taps(const TiledGeom& tg, const FwdTile
 }
 
 __global__ void resize3d_fwd_tiled_kernel(const float* __restrict__ x, const TiledGeom tg, float* __restrict__ y) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) float rs_sm[];
   const ResizeGeom& g = tg.g;
   const FwdTile f = carve_fwd(rs_sm, tg);
@@ -498,6 +508,7 @@ __global__ void upsample_noise_pack_tiled_kernel(const float* __restrict__ x, in
                                                  unsigned long long sample_base,
                                                  const unsigned long long* __restrict__ d_sample_offset,
                                                  float* __restrict__ up, __nv_bfloat16* __restrict__ xin, int xin_f32) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) float rs_sm[];
   const ResizeGeom& g = tg.g;
   if (d_sample_offset) sample_base += *d_sample_offset;
@@ -610,6 +621,7 @@ template <int TI>
 __global__ void __launch_bounds__(CW_THREADS)
 resize3d_fwd_colwalk_kernel(const float* __restrict__ x, const ResizeGeom g, const __grid_constant__ TWalk w,
                             float* __restrict__ y) {
+  pdl_grid_sync();
   const unsigned plane = g.Ho * g.Wo;
   const unsigned col = blockIdx.x * CW_THREADS + threadIdx.x;
   if (col >= plane) return;
@@ -644,6 +656,7 @@ upsample_noise_pack_colwalk_kernel(const float* __restrict__ x, const ResizeGeom
                                    unsigned long long sample_base,
                                    const unsigned long long* __restrict__ d_sample_offset, float* __restrict__ up,
                                    __nv_bfloat16* __restrict__ xin, int xin_f32) {
+  pdl_grid_sync();
   const unsigned plane = g.Ho * g.Wo;
   const unsigned col = blockIdx.x * CW_THREADS + threadIdx.x;
   if (col >= plane) return;
@@ -746,6 +759,7 @@ template <int NH, int NW, int TI, int NK>   // bounds: contributing rows / colum
 __global__ void __launch_bounds__(BW_TX * BW_TY)
 resize3d_bwd_colwalk_kernel(const float* __restrict__ gy, const ResizeGeom g, const __grid_constant__ TWalk w,
                             const BwdWin win, float* __restrict__ gx) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) float bw_sm[];          // [TI][win.rows][win.cols]
   __shared__ InvTap htab[BW_TY], wtab[BW_TX];
   const int tid = threadIdx.y * BW_TX + threadIdx.x;
@@ -828,6 +842,7 @@ resize3d_bwd_colwalk_kernel(const float* __restrict__ gy, const ResizeGeom g, co
 // backward: a thread owns (source row hs, column wo) and walks along T_out with register accumulators for the (at
 // most two) source frames currently being fed — no shared-memory read-modify-write, fixed order => deterministic.
 __global__ void resize3d_bwd_tiled_kernel(const float* __restrict__ gy, const TiledGeom tg, float* __restrict__ gx) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) float rs_sm[];
   const ResizeGeom& g = tg.g;
   const int hs0 = blockIdx.x * tg.band;
@@ -978,6 +993,7 @@ __device__ __forceinline__ float cv_coord(int d, double scale, int& s) {
 constexpr int FC_ROWS = 4;      // output rows per block: a thread keeps its column coefficients for FC_ROWS x T pixels
 __global__ void __launch_bounds__(256)
 frames_to_clip_kernel(const uint8_t* __restrict__ frames, const FrameGeom g, float* __restrict__ clip) {
+  pdl_grid_sync();
   // ((v / 255) - 0.5) / 0.5 for the 256 possible pixel values, each with the reference's correctly rounded fp32
   // operations, once per block: the per-pixel epilogue becomes three shared-memory lookups instead of six divisions
   __shared__ float lut[256];
@@ -1049,6 +1065,7 @@ frames_to_clip_kernel(const uint8_t* __restrict__ frames, const FrameGeom g, flo
 // the reference's host numpy draws (images.py:17-21, networks_3d.py:28-34) when the step is replayed as a CUDA graph.
 __global__ void randn_kernel(float* __restrict__ z, long long n, unsigned long long seed, unsigned long long offset,
                              const unsigned long long* __restrict__ d_offset) {
+  pdl_grid_sync();
   if (d_offset) offset += *d_offset;
   const long long n4 = (n + 3) >> 2;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
@@ -1064,7 +1081,8 @@ __global__ void randn_kernel(float* __restrict__ z, long long n, unsigned long l
       if (4 * i + e < n) z[4 * i + e] = v[e];
   }
 }
-__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) { *c += inc; }
+__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) {
+  pdl_grid_sync(); *c += inc; }
 
 // block input stage (networks_3d.py:440-446): up = resize(x_prev) ; x_in = up + noise*amp ; C <= 4
 __global__ void upsample_noise_pack_kernel(const float* __restrict__ x, int N, int C, ResizeGeom g,
@@ -1072,6 +1090,7 @@ __global__ void upsample_noise_pack_kernel(const float* __restrict__ x, int N, i
                                            unsigned long long sample_base,
                                            const unsigned long long* __restrict__ d_sample_offset,
                                            float* __restrict__ up, __nv_bfloat16* __restrict__ xin, int xin_f32) {
+  pdl_grid_sync();
   if (d_sample_offset) sample_base += *d_sample_offset;   // device-resident draw counter (CUDA-graph replays)
   const long long spo = static_cast<long long>(g.To) * g.Ho * g.Wo;
   const long long spi = static_cast<long long>(g.Ti) * g.Hi * g.Wi;
@@ -1112,6 +1131,7 @@ __global__ void upsample_noise_pack_kernel(const float* __restrict__ x, int N, i
 // y: (voxels, 64) bf16.  thread -> one 16 B channel group; 8 groups per voxel; block = 256 threads = 32 voxels/iter.
 __global__ void bn_stats_cl_kernel(const __nv_bfloat16* __restrict__ y, long long voxels, double* __restrict__ sum,
                                    double* __restrict__ sumsq, const DetScratch det) {
+  pdl_grid_sync();
   const int g = threadIdx.x & 7;         // channel group
   const int vl = threadIdx.x >> 3;       // voxel lane 0..31
   float a[8], b[8];
@@ -1163,6 +1183,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
                                    float momentum, float* __restrict__ mm, float* __restrict__ mv,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_o,
                                    float* __restrict__ invstd_o) {
+  pdl_grid_sync();
   const int c = threadIdx.x;
   if (c >= 64) return;
   const double mean = sum[c] / count;
@@ -1181,6 +1202,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
 __global__ void bn_apply_cl_kernel(const __nv_bfloat16* __restrict__ y, long long groups /*voxels*8*/,
                                    const float* __restrict__ scale, const float* __restrict__ shift, int act,
                                    __nv_bfloat16* __restrict__ x) {
+  pdl_grid_sync();
   __shared__ float sc[64], sh[64];
   if (threadIdx.x < 64) {
     sc[threadIdx.x] = scale[threadIdx.x];
@@ -1218,6 +1240,7 @@ __global__ void bn_train_apply_cl_kernel(const __nv_bfloat16* __restrict__ y, lo
                                          float momentum, float* __restrict__ mm, float* __restrict__ mv,
                                          float* __restrict__ saved /*[4][64], nullable*/, int act,
                                          __nv_bfloat16* __restrict__ x, const float* __restrict__ center) {
+  pdl_grid_sync();
   // center (nullable): the per-channel offset the producing conv subtracted from y before storing it (kink-centred
   // storage, see bn_center_multi_kernel).  Everything here and in the backward works in the centred frame — BatchNorm
   // is shift invariant — except the MOVING mean, which tracks the true mean = centred mean + center.
@@ -1271,6 +1294,7 @@ __global__ void bn_train_apply_cl_kernel(const __nv_bfloat16* __restrict__ y, lo
 // of the shared moving statistics is taken out of the forwards and replayed afterwards, forward by forward, in the
 // reference's order.  saved = (scale, shift, mean, invstd) of bn_train_apply_cl; var = 1/invstd^2 - eps.
 __global__ void bn_moving_update_multi_kernel(const BnMovingTable tab, float eps, float momentum) {
+  pdl_grid_sync();
   const int b = blockIdx.x, c = threadIdx.x;
   const float* sv = tab.saved[b];
   const float mean = sv[128 + c] + (tab.center[b] ? tab.center[b][c] : 0.f), invstd = sv[192 + c];
@@ -1288,6 +1312,7 @@ __global__ void bn_moving_update_multi_kernel(const BnMovingTable tab, float eps
 // normalise pass and the backward simply run in the centred frame; only the moving mean needs center added back.
 // One block per layer: center[c] and the conv's epilogue vectors aff = (1, bias - center).
 __global__ void bn_center_multi_kernel(const BnCenterTable tab, float eps) {
+  pdl_grid_sync();
   const int b = blockIdx.x, c = threadIdx.x;
   const float g = tab.gamma[b][c];
   float cen = tab.mm[b][c];
@@ -1373,6 +1398,7 @@ __device__ void sn_power_iter_body(const float* __restrict__ w, int cout, int k,
 __global__ void sn_power_iter_kernel(const float* __restrict__ w, int cout, int k, float* __restrict__ u,
                                      float* __restrict__ v, float* __restrict__ sigma,
                                      float* __restrict__ inv_sigma) {
+  pdl_grid_sync();
   extern __shared__ float sm[];
   __shared__ float red[32];
   sn_power_iter_body(w, cout, k, u, v, sigma, inv_sigma, nullptr, nullptr, nullptr, nullptr, sm, red);
@@ -1380,6 +1406,7 @@ __global__ void sn_power_iter_kernel(const float* __restrict__ w, int cout, int 
 
 // all spectrally normalised layers of a network in one launch: block b = layer b
 __global__ void sn_power_iter_multi_kernel(const SnTable tab) {
+  pdl_grid_sync();
   extern __shared__ float sm[];
   __shared__ float red[32];
   const int b = blockIdx.x;
@@ -1390,6 +1417,7 @@ __global__ void sn_power_iter_multi_kernel(const SnTable tab) {
 // ----------------------------------------------------------------------------------------------- epilogue vectors
 __global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const float* mean, const float* var,
                                     float eps, const float* bias, int C, float* scale, float* shift) {
+  pdl_grid_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float sc = gamma[c] / sqrtf(var[c] + eps);
@@ -1397,6 +1425,7 @@ __global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const
   shift[c] = (bias[c] - mean[c]) * sc + beta[c];
 }
 __global__ void affine_from_bias_kernel(const float* bias, const float* inv_sigma, int C, float* scale, float* shift) {
+  pdl_grid_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   scale[c] = inv_sigma ? inv_sigma[0] : 1.0f;
@@ -1407,6 +1436,7 @@ __global__ void affine_from_bias_kernel(const float* bias, const float* inv_sigm
 template <int OP>  // 0: sum (a-b)^2 ; 1: sum a ; 2: sum -0.5(1+lv-mu^2-exp(lv))
 __global__ void reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float inv_n,
                               float* __restrict__ out, const DetScratch det) {
+  pdl_grid_sync();
   __shared__ float red[32];
   float acc = 0.f;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -1427,6 +1457,7 @@ __global__ void reduce_kernel(const float* __restrict__ a, const float* __restri
 
 __global__ void reparam_kernel(const float* __restrict__ mu, const float* __restrict__ lv,
                                const float* __restrict__ eps, long long n, float* __restrict__ z) {
+  pdl_grid_sync();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     z[i] = fmaf(eps[i], expf(0.5f * lv[i]), mu[i]);
@@ -1436,6 +1467,7 @@ __global__ void reparam_kernel(const float* __restrict__ mu, const float* __rest
 __global__ void reparam_bwd_kernel(const float* __restrict__ gz, const float* __restrict__ eps,
                                    const float* __restrict__ lv, long long n, float* __restrict__ gmu,
                                    float* __restrict__ glv) {
+  pdl_grid_sync();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float g = gz[i];
@@ -1448,6 +1480,7 @@ __global__ void reparam_bwd_kernel(const float* __restrict__ gz, const float* __
 // grid (blocks, tensors); 16-byte vector accesses on the aligned body, scalar tail.  cudaMalloc'd tensors are
 // 256-byte aligned; a misaligned view falls back to the scalar loop (vec = 0).
 __global__ void adam_norm_kernel(const AdamTable tab, float* __restrict__ norms) {
+  pdl_grid_sync();
   __shared__ float red[32];
   const int t = blockIdx.y;
   const float* __restrict__ g = tab.g[t];
@@ -1482,6 +1515,7 @@ __global__ void adam_apply_kernel(const AdamTable tab, const float* __restrict__
                                   float eps, float bc /* sqrt(1-b2^t)/(1-b1^t) */, float clip,
                                   const unsigned long long* __restrict__ d_step, const float* __restrict__ d_hyper,
                                   int norm_blocks) {
+  pdl_grid_sync();
   if (d_hyper) {   // every hyper-parameter lives on the device (ops.Custom binding): lr, beta1, beta2, eps, clip, step
     beta1 = d_hyper[1];
     beta2 = d_hyper[2];
@@ -1534,6 +1568,7 @@ __global__ void adam_apply_kernel(const AdamTable tab, const float* __restrict__
 // gz = ga * lrelu'(a)  (a = the stored activation; sign(a) == sign(pre-activation))          bf16 cl, any width
 __global__ void lrelu_bwd_cl_kernel(const __nv_bfloat16* __restrict__ ga, const __nv_bfloat16* __restrict__ a,
                                     long long groups, __nv_bfloat16* __restrict__ gz) {
+  pdl_grid_sync();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < groups;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const uint4 g4 = *reinterpret_cast<const uint4*>(ga + i * 8);
@@ -1557,6 +1592,7 @@ __global__ void lrelu_bwd_cl_kernel(const __nv_bfloat16* __restrict__ ga, const 
 __global__ void bn_bwd_reduce_cl_kernel(const __nv_bfloat16* __restrict__ ga, const __nv_bfloat16* __restrict__ y,
                                         long long voxels, const float* __restrict__ saved /*[4][64]*/, int act,
                                         double* __restrict__ sums, const DetScratch det) {
+  pdl_grid_sync();
   const int g = threadIdx.x & 7, vl = threadIdx.x >> 3;
   float sc[8], sh[8], mu[8], is[8], s0[8], s1[8];
 #pragma unroll
@@ -1636,6 +1672,7 @@ __global__ void bn_bwd_apply_cl_kernel(const __nv_bfloat16* __restrict__ ga, con
                                        const double* __restrict__ sums, double inv_count,
                                        __nv_bfloat16* __restrict__ gy, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, int accumulate) {
+  pdl_grid_sync();
   __shared__ float sc[64], sh[64], mu[64], is[64], m0[64], m1[64];
   if (threadIdx.x < 64) {
     const int c = threadIdx.x;
@@ -1679,6 +1716,7 @@ __global__ void bn_bwd_apply_cl_kernel(const __nv_bfloat16* __restrict__ ga, con
 
 // out[c] (+)= scale * in[c]  (double -> float), used for dgamma / dbeta / bias gradients
 __global__ void d2f_kernel(const double* __restrict__ in, int n, float scale, int accumulate, float* __restrict__ out) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (accumulate ? out[i] : 0.f) + scale * static_cast<float>(in[i]);
 }
@@ -1686,6 +1724,7 @@ __global__ void d2f_kernel(const double* __restrict__ in, int n, float scale, in
 // g (+)= coef*(a - b)                                               (MSE gradient, coef = weight*2/n)
 __global__ void diff_scale_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float coef,
                                   int accumulate, float* __restrict__ g) {
+  pdl_grid_sync();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     g[i] = (accumulate ? g[i] : 0.f) + coef * (a[i] - b[i]);
@@ -1693,12 +1732,14 @@ __global__ void diff_scale_kernel(const float* __restrict__ a, const float* __re
 // gpre = g*(1 - out^2)
 __global__ void tanh_bwd_kernel(const float* __restrict__ g, const float* __restrict__ out, long long n,
                                 float* __restrict__ gpre) {
+  pdl_grid_sync();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     gpre[i] = g[i] * (1.f - out[i] * out[i]);
 }
 // y = a*x + b*y
 __global__ void axpby_kernel(float a, const float* __restrict__ x, float b, float* __restrict__ y, long long n) {
+  pdl_grid_sync();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     y[i] = a * x[i] + (b == 0.f ? 0.f : b * y[i]);
@@ -1706,11 +1747,13 @@ __global__ void axpby_kernel(float a, const float* __restrict__ x, float b, floa
 // dst[i] = src[i*stride + offset]   (e.g. one tap of a (Cout,Cin,27) weight-gradient tensor)
 __global__ void gather_strided_kernel(const float* __restrict__ src, long long n, long long stride, long long offset,
                                       float* __restrict__ dst) {
+  pdl_grid_sync();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     dst[i] = src[i * stride + offset];
 }
 __global__ void fill_kernel(float* __restrict__ y, float v, long long n) {
+  pdl_grid_sync();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     y[i] = v;
@@ -1719,6 +1762,7 @@ __global__ void fill_kernel(float* __restrict__ y, float v, long long n) {
 // grid (blocks, C): fp32 block partials -> fp64 atomics into scratch[c]; a d2f pass writes the result.
 __global__ void channel_sum_ncdhw_kernel(const float* __restrict__ g, int N, int C, long long sp,
                                          double* __restrict__ scratch) {
+  pdl_grid_sync();
   __shared__ float red[32];
   const int c = blockIdx.y;
   float acc = 0.f;
@@ -1734,6 +1778,7 @@ __global__ void channel_sum_ncdhw_kernel(const float* __restrict__ g, int N, int
 // out[c] (+)= sum of the nblk block partials of channel c, in block order (deterministic)
 __global__ void channel_sum_final_kernel(const double* __restrict__ partials, int nblk, int C, int accumulate,
                                          float* __restrict__ out) {
+  pdl_grid_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double acc = 0.0;
@@ -1743,6 +1788,7 @@ __global__ void channel_sum_final_kernel(const double* __restrict__ partials, in
 // KL gradient (losses.py:5-7): d/dmu = coef*mu ; d/dlogvar = coef*0.5*(exp(lv)-1) ; coef = kl_weight/n
 __global__ void kl_grad_kernel(const float* __restrict__ mu, const float* __restrict__ lv, long long n, float coef,
                                float* __restrict__ gmu, float* __restrict__ glv) {
+  pdl_grid_sync();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     gmu[i] = coef * mu[i];
@@ -1754,6 +1800,7 @@ __global__ void kl_grad_kernel(const float* __restrict__ mu, const float* __rest
 constexpr int SN_GRAD_BLOCKS = 64;
 __global__ void sn_grad_dot_kernel(const float* __restrict__ G, const float* __restrict__ w, int n,
                                    float* __restrict__ partial) {
+  pdl_grid_sync();
   __shared__ float red[32];
   float part = 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -1765,6 +1812,7 @@ __global__ void sn_grad_apply_kernel(const float* __restrict__ G, const float* _
                                      const float* __restrict__ u, const float* __restrict__ v,
                                      const float* __restrict__ sigma, int cout, int k, int accumulate,
                                      float* __restrict__ gw) {
+  pdl_grid_sync();
   const float sg = sigma[0];
   float dot = 0.f;
   for (int i = 0; i < SN_GRAD_BLOCKS; ++i) dot += partial[i];
@@ -1779,6 +1827,7 @@ __global__ void sn_grad_apply_kernel(const float* __restrict__ G, const float* _
 // WGAN-GP (losses.py:47-52): xhat = alpha*real + (1-alpha)*fake
 __global__ void lerp_kernel(const float* __restrict__ a, const float* __restrict__ b, float alpha, long long n,
                             float* __restrict__ out) {
+  pdl_grid_sync();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     out[i] = alpha * a[i] + (1.f - alpha) * b[i];
@@ -1786,6 +1835,7 @@ __global__ void lerp_kernel(const float* __restrict__ a, const float* __restrict
 // per voxel: nrm = ||g[:, v]||_2 over C channels ; gp += lambda*(nrm-1)^2/V ; G[c] = lambda*2*(nrm-1)/nrm*g[c]/V
 __global__ void gp_grad_kernel(const float* __restrict__ g, int N, int C, long long sp, float lambda,
                                float* __restrict__ Gout, float* __restrict__ gp, const DetScratch det) {
+  pdl_grid_sync();
   __shared__ float red[32];
   const long long V = static_cast<long long>(N) * sp;
   const float invV = 1.0f / static_cast<float>(V);
@@ -1829,13 +1879,13 @@ cudaError_t ew_pack_cl(const float* x, int N, int C, long long sp, __nv_bfloat16
   const int groups = (c_zero_to - c_off > C ? c_zero_to - c_off : C) + 7 >> 3;
   const long long total = voxels * groups;
   if (C <= 8 && groups > 1)
-    pack_cl_skinny_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, C, sp, voxels, y, c_pitch,
+    launch(pack_cl_skinny_kernel, static_cast<unsigned>((total + 255) / 256), 256, 0, st, x, C, sp, voxels, y, c_pitch,
                                                                                      c_off, groups);
   else if (C > 8 && (voxels + PK_VOX - 1) / PK_VOX < (1LL << 31))
-    pack_cl_tiled_kernel<<<dim3(static_cast<unsigned>((voxels + PK_VOX - 1) / PK_VOX), (groups + 7) / 8), 256, 0, st>>>(
+    launch(pack_cl_tiled_kernel, dim3(static_cast<unsigned>((voxels + PK_VOX - 1) / PK_VOX), (groups + 7) / 8), 256, 0, st, 
         x, C, sp, voxels, y, c_pitch, c_off, groups);
   else
-    pack_cl_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, C, sp, voxels, y, c_pitch, c_off,
+    launch(pack_cl_kernel, static_cast<unsigned>((total + 255) / 256), 256, 0, st, x, C, sp, voxels, y, c_pitch, c_off,
                                                                               groups);
   LAUNCH_CHECK();
   return cudaSuccess;
@@ -1846,10 +1896,10 @@ cudaError_t ew_unpack_cl(const __nv_bfloat16* x, int N, int C, long long sp, int
   const int groups = (C + 7) >> 3;
   const long long total = voxels * groups;
   if (C > 8 && (voxels + PK_VOX - 1) / PK_VOX < (1LL << 31))
-    unpack_cl_tiled_kernel<<<dim3(static_cast<unsigned>((voxels + PK_VOX - 1) / PK_VOX), (groups + 7) / 8), 256, 0, st>>>(
+    launch(unpack_cl_tiled_kernel, dim3(static_cast<unsigned>((voxels + PK_VOX - 1) / PK_VOX), (groups + 7) / 8), 256, 0, st, 
         x, C, sp, voxels, c_pitch, c_off, y, groups);
   else
-    unpack_cl_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, C, sp, voxels, c_pitch, c_off, y,
+    launch(unpack_cl_kernel, static_cast<unsigned>((total + 255) / 256), 256, 0, st, x, C, sp, voxels, c_pitch, c_off, y,
                                                                                 groups);
   LAUNCH_CHECK();
   return cudaSuccess;
@@ -1878,7 +1928,7 @@ void ew_linear_taps_host(int n_in, int n_out, int align, int32_t* i0, int32_t* i
 }
 cudaError_t ew_linear_taps_dev(int n_in, int n_out, int align, int32_t* i0, int32_t* i1, float* l0, float* l1,
                                cudaStream_t st) {
-  linear_taps_kernel<<<(n_out + 127) / 128, 128, 0, st>>>(n_in, n_out, axis_scale(n_in, n_out, align), align, i0, i1,
+  launch(linear_taps_kernel, (n_out + 127) / 128, 128, 0, st, n_in, n_out, axis_scale(n_in, n_out, align), align, i0, i1,
                                                          l0, l1);
   LAUNCH_CHECK();
   return cudaSuccess;
@@ -1967,7 +2017,7 @@ cudaError_t ew_resize3d_fwd(const float* x, long long NC, int Ti, int Hi, int Wi
   TWalk tw;
   if (colwalk_ok(g, NC) && make_twalk(g, &tw)) {
     const dim3 grid((Ho * Wo + CW_THREADS - 1) / CW_THREADS, static_cast<unsigned>(NC));
-#define HPVG_CWF(T_) resize3d_fwd_colwalk_kernel<T_><<<grid, CW_THREADS, 0, st>>>(x, g, tw, y)
+#define HPVG_CWF(T_) launch(resize3d_fwd_colwalk_kernel<T_>, grid, CW_THREADS, 0, st, x, g, tw, y)
     switch (Ti) {   // the frame count is a template parameter: no per-frame predicates in the unrolled body
       case 1: HPVG_CWF(1); break;
       case 2: HPVG_CWF(2); break;
@@ -1983,10 +2033,10 @@ cudaError_t ew_resize3d_fwd(const float* x, long long NC, int Ti, int Hi, int Wi
     static bool ok = false;
     cudaError_t e = rs_allow_smem(resize3d_fwd_tiled_kernel, &ok);
     if (e != cudaSuccess) return e;
-    resize3d_fwd_tiled_kernel<<<dim3((Ho + tg.band - 1) / tg.band, static_cast<unsigned>(NC)), dim3(tg.nx, tg.ny), smem, st>>>(
+    launch(resize3d_fwd_tiled_kernel, dim3((Ho + tg.band - 1) / tg.band, static_cast<unsigned>(NC)), dim3(tg.nx, tg.ny), smem, st, 
         x, tg, y);
   } else {
-    resize3d_fwd_kernel<<<grid_for(NC * To * Ho * Wo, 256), 256, 0, st>>>(x, NC, g, y);
+    launch(resize3d_fwd_kernel, grid_for(NC * To * Ho * Wo, 256), 256, 0, st, x, NC, g, y);
   }
   LAUNCH_CHECK();
   return cudaSuccess;
@@ -2039,7 +2089,7 @@ cudaError_t ew_resize3d_bwd(const float* gy, long long NC, int To, int Ho, int W
       if (e_ != cudaSuccess) return e_;                                                                            \
       ok_ = true;                                                                                                  \
     }                                                                                                              \
-    resize3d_bwd_colwalk_kernel<H_, W_, T_, K_><<<grid, block, bw_smem, st>>>(gy, g, tw, win, gx);                 \
+    launch(resize3d_bwd_colwalk_kernel<H_, W_, T_, K_>, grid, block, bw_smem, st, gy, g, tw, win, gx);                 \
   }
 #define HPVG_BWT(H_, W_, K_)                    \
     switch (Ti) {                                 \
@@ -2063,10 +2113,10 @@ cudaError_t ew_resize3d_bwd(const float* gy, long long NC, int To, int Ho, int W
     static bool ok = false;
     cudaError_t e = rs_allow_smem(resize3d_bwd_tiled_kernel, &ok);
     if (e != cudaSuccess) return e;
-    resize3d_bwd_tiled_kernel<<<dim3((Hi + tg.band - 1) / tg.band, static_cast<unsigned>(NC)), dim3(tg.nx, tg.ny), smem, st>>>(
+    launch(resize3d_bwd_tiled_kernel, dim3((Hi + tg.band - 1) / tg.band, static_cast<unsigned>(NC)), dim3(tg.nx, tg.ny), smem, st, 
         gy, tg, gx);
   } else {
-    resize3d_bwd_kernel<<<grid_for(NC * Ti * Hi * Wi, 128), 128, 0, st>>>(gy, NC, g, gx);
+    launch(resize3d_bwd_kernel, grid_for(NC * Ti * Hi * Wi, 128), 128, 0, st, gy, NC, g, gx);
   }
   LAUNCH_CHECK();
   return cudaSuccess;
@@ -2081,7 +2131,7 @@ cudaError_t ew_upsample_noise_pack(const float* x, int N, int C, int Ti, int Hi,
   TWalk tw;
   if ((C == 1 || C == 3) && colwalk_ok(g, N, C) && make_twalk(g, &tw)) {
     const dim3 grid((Ho * Wo + CW_THREADS - 1) / CW_THREADS, N);
-#define HPVG_CW(C_, T_) upsample_noise_pack_colwalk_kernel<C_, T_><<<grid, CW_THREADS, 0, st>>>( \
+#define HPVG_CW(C_, T_) launch(upsample_noise_pack_colwalk_kernel<C_, T_>, grid, CW_THREADS, 0, st,  \
       x, g, tw, noise, amp, seed, sample_base, d_sample_offset, up, xin, xin_f32)
 #define HPVG_CWT(C_)                       \
     switch (Ti) {                            \
@@ -2101,10 +2151,10 @@ cudaError_t ew_upsample_noise_pack(const float* x, int N, int C, int Ti, int Hi,
     static bool ok = false;
     cudaError_t e = rs_allow_smem(upsample_noise_pack_tiled_kernel, &ok);
     if (e != cudaSuccess) return e;
-    upsample_noise_pack_tiled_kernel<<<dim3((Ho + tg.band - 1) / tg.band, N), dim3(tg.nx, tg.ny), smem, st>>>(
+    launch(upsample_noise_pack_tiled_kernel, dim3((Ho + tg.band - 1) / tg.band, N), dim3(tg.nx, tg.ny), smem, st, 
         x, C, tg, noise, amp, seed, sample_base, d_sample_offset, up, xin, xin_f32);
   } else {
-    upsample_noise_pack_kernel<<<grid_for(static_cast<long long>(N) * To * Ho * Wo, 256), 256, 0, st>>>(
+    launch(upsample_noise_pack_kernel, grid_for(static_cast<long long>(N) * To * Ho * Wo, 256), 256, 0, st, 
         x, N, C, g, noise, amp, seed, sample_base, d_sample_offset, up, xin, xin_f32);
   }
   LAUNCH_CHECK();
@@ -2112,28 +2162,28 @@ cudaError_t ew_upsample_noise_pack(const float* x, int N, int C, int Ti, int Hi,
 }
 cudaError_t ew_bn_stats_cl(const __nv_bfloat16* y, long long voxels, double* sum, double* sumsq, DetScratch det,
                            cudaStream_t st) {
-  bn_stats_cl_kernel<<<grid_for(voxels, 32, DET_MAX_BLOCKS), 256, 0, st>>>(y, voxels, sum, sumsq, det);
+  launch(bn_stats_cl_kernel, grid_for(voxels, 32, DET_MAX_BLOCKS), 256, 0, st, y, voxels, sum, sumsq, det);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_bn_finalize(const double* sum, const double* sumsq, long long count, const float* gamma,
                            const float* beta, float eps, float momentum, float* mm, float* mv, float* scale,
                            float* shift, float* mean, float* invstd, cudaStream_t st) {
-  bn_finalize_kernel<<<1, 64, 0, st>>>(sum, sumsq, static_cast<double>(count), gamma, beta, eps, momentum, mm, mv,
+  launch(bn_finalize_kernel, 1, 64, 0, st, sum, sumsq, static_cast<double>(count), gamma, beta, eps, momentum, mm, mv,
                                        scale, shift, mean, invstd);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_bn_apply_cl(const __nv_bfloat16* y, long long voxels, const float* scale, const float* shift, int act,
                            __nv_bfloat16* x, cudaStream_t st) {
-  bn_apply_cl_kernel<<<grid_for(voxels * 8, 256), 256, 0, st>>>(y, voxels * 8, scale, shift, act, x);
+  launch(bn_apply_cl_kernel, grid_for(voxels * 8, 256), 256, 0, st, y, voxels * 8, scale, shift, act, x);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_sn_power_iter(const float* w, int cout, int k, float* u, float* v, float* sigma, float* inv_sigma,
                              cudaStream_t st) {
   const size_t smem = (2 * static_cast<size_t>(cout) + k) * sizeof(float);
-  sn_power_iter_kernel<<<1, 512, smem, st>>>(w, cout, k, u, v, sigma, inv_sigma);
+  launch(sn_power_iter_kernel, 1, 512, smem, st, w, cout, k, u, v, sigma, inv_sigma);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -2143,25 +2193,25 @@ cudaError_t ew_sn_power_iter_multi(const SnTable& tab, int n_layers, cudaStream_
     const size_t b = (2 * static_cast<size_t>(tab.cout[i]) + tab.k[i]) * sizeof(float);
     if (b > smem) smem = b;
   }
-  sn_power_iter_multi_kernel<<<n_layers, 512, smem, st>>>(tab);
+  launch(sn_power_iter_multi_kernel, n_layers, 512, smem, st, tab);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_bn_moving_update_multi(const BnMovingTable& tab, int n_layers, float eps, float momentum,
                                       cudaStream_t st) {
-  bn_moving_update_multi_kernel<<<n_layers, 64, 0, st>>>(tab, eps, momentum);
+  launch(bn_moving_update_multi_kernel, n_layers, 64, 0, st, tab, eps, momentum);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_bn_center_multi(const BnCenterTable& tab, int n_layers, float eps, cudaStream_t st) {
-  bn_center_multi_kernel<<<n_layers, 64, 0, st>>>(tab, eps);
+  launch(bn_center_multi_kernel, n_layers, 64, 0, st, tab, eps);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_bn_train_apply_cl(const __nv_bfloat16* y, long long voxels, const double* sums, const float* gamma,
                                  const float* beta, float eps, float momentum, float* mm, float* mv, float* saved,
                                  int act, __nv_bfloat16* x, const float* center, cudaStream_t st) {
-  bn_train_apply_cl_kernel<<<grid_for(voxels * 8, 256), 256, 0, st>>>(y, voxels * 8, sums,
+  launch(bn_train_apply_cl_kernel, grid_for(voxels * 8, 256), 256, 0, st, y, voxels * 8, sums,
                                                                       static_cast<double>(voxels), gamma, beta, eps,
                                                                       momentum, mm, mv, saved, act, x, center);
   LAUNCH_CHECK();
@@ -2169,13 +2219,13 @@ cudaError_t ew_bn_train_apply_cl(const __nv_bfloat16* y, long long voxels, const
 }
 cudaError_t ew_bn_fold_eval(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                             const float* bias, int C, float* scale, float* shift, cudaStream_t st) {
-  bn_fold_eval_kernel<<<(C + 63) / 64, 64, 0, st>>>(gamma, beta, mean, var, eps, bias, C, scale, shift);
+  launch(bn_fold_eval_kernel, (C + 63) / 64, 64, 0, st, gamma, beta, mean, var, eps, bias, C, scale, shift);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_affine_from_bias(const float* bias, const float* inv_sigma, int C, float* scale, float* shift,
                                 cudaStream_t st) {
-  affine_from_bias_kernel<<<(C + 63) / 64, 64, 0, st>>>(bias, inv_sigma, C, scale, shift);
+  launch(affine_from_bias_kernel, (C + 63) / 64, 64, 0, st, bias, inv_sigma, C, scale, shift);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -2183,20 +2233,20 @@ cudaError_t ew_reduce(int op, const float* a, const float* b, long long n, float
                       cudaStream_t st) {
   const int grid = grid_for(n, 256, 148 * 4);
   const float inv = 1.0f / static_cast<float>(n);
-  if (op == 0) reduce_kernel<0><<<grid, 256, 0, st>>>(a, b, n, inv, out, det);
-  else if (op == 1) reduce_kernel<1><<<grid, 256, 0, st>>>(a, b, n, inv, out, det);
-  else reduce_kernel<2><<<grid, 256, 0, st>>>(a, b, n, inv, out, det);
+  if (op == 0) launch(reduce_kernel<0>, grid, 256, 0, st, a, b, n, inv, out, det);
+  else if (op == 1) launch(reduce_kernel<1>, grid, 256, 0, st, a, b, n, inv, out, det);
+  else launch(reduce_kernel<2>, grid, 256, 0, st, a, b, n, inv, out, det);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_reparam(const float* mu, const float* lv, const float* eps, long long n, float* z, cudaStream_t st) {
-  reparam_kernel<<<grid_for(n, 256), 256, 0, st>>>(mu, lv, eps, n, z);
+  launch(reparam_kernel, grid_for(n, 256), 256, 0, st, mu, lv, eps, n, z);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_reparam_bwd(const float* gz, const float* eps, const float* lv, long long n, float* gmu, float* glv,
                            cudaStream_t st) {
-  reparam_bwd_kernel<<<grid_for(n, 256), 256, 0, st>>>(gz, eps, lv, n, gmu, glv);
+  launch(reparam_bwd_kernel, grid_for(n, 256), 256, 0, st, gz, eps, lv, n, gmu, glv);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -2212,10 +2262,10 @@ cudaError_t ew_adam_clip(const AdamTable& tab, int n_tensors, float* norms_scrat
   const int gx = static_cast<int>(want < 1 ? 1 : want);
   const int nb = gx < ADAM_NORM_BLOCKS ? gx : ADAM_NORM_BLOCKS;
   if (clip > 0.f) {
-    adam_norm_kernel<<<dim3(nb, n_tensors), 256, 0, st>>>(tab, norms_scratch);
+    launch(adam_norm_kernel, dim3(nb, n_tensors), 256, 0, st, tab, norms_scratch);
     LAUNCH_CHECK();
   }
-  adam_apply_kernel<<<dim3(gx, n_tensors), 256, 0, st>>>(tab, norms_scratch, beta1, beta2, eps, bias_corr, clip,
+  launch(adam_apply_kernel, dim3(gx, n_tensors), 256, 0, st, tab, norms_scratch, beta1, beta2, eps, bias_corr, clip,
                                                          d_step, d_hyper, nb);
   LAUNCH_CHECK();
   return cudaSuccess;
@@ -2223,16 +2273,16 @@ cudaError_t ew_adam_clip(const AdamTable& tab, int n_tensors, float* norms_scrat
 
 cudaError_t ew_lrelu_bwd_cl(const __nv_bfloat16* ga, const __nv_bfloat16* a, long long elems, __nv_bfloat16* gz,
                             cudaStream_t st) {
-  lrelu_bwd_cl_kernel<<<grid_for(elems / 8, 256), 256, 0, st>>>(ga, a, elems / 8, gz);
+  launch(lrelu_bwd_cl_kernel, grid_for(elems / 8, 256), 256, 0, st, ga, a, elems / 8, gz);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_bn_bwd_cl(const __nv_bfloat16* ga, const __nv_bfloat16* y, long long voxels, const float* saved, int act,
                          double* sums, DetScratch det, __nv_bfloat16* gy, float* dgamma, float* dbeta, int accumulate,
                          cudaStream_t st) {
-  bn_bwd_reduce_cl_kernel<<<grid_for(voxels, 32, DET_MAX_BLOCKS), 256, 0, st>>>(ga, y, voxels, saved, act, sums, det);
+  launch(bn_bwd_reduce_cl_kernel, grid_for(voxels, 32, DET_MAX_BLOCKS), 256, 0, st, ga, y, voxels, saved, act, sums, det);
   LAUNCH_CHECK();
-  bn_bwd_apply_cl_kernel<<<grid_for(voxels * 8, 256), 256, 0, st>>>(ga, y, voxels * 8, saved, act, sums,
+  launch(bn_bwd_apply_cl_kernel, grid_for(voxels * 8, 256), 256, 0, st, ga, y, voxels * 8, saved, act, sums,
                                                                     1.0 / static_cast<double>(voxels), gy, dgamma, dbeta,
                                                                     accumulate);
   LAUNCH_CHECK();
@@ -2242,29 +2292,29 @@ cudaError_t ew_colsum_cl(const __nv_bfloat16* g, long long voxels, double* scrat
                          int accumulate, cudaStream_t st) {
   cudaError_t e = ew_bn_stats_cl(g, voxels, scratch, scratch + 64, det, st);
   if (e != cudaSuccess) return e;
-  d2f_kernel<<<1, 64, 0, st>>>(scratch, 64, 1.f, accumulate, out);
+  launch(d2f_kernel, 1, 64, 0, st, scratch, 64, 1.f, accumulate, out);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_diff_scale(const float* a, const float* b, long long n, float coef, int accumulate, float* g,
                           cudaStream_t st) {
-  diff_scale_kernel<<<grid_for(n, 256), 256, 0, st>>>(a, b, n, coef, accumulate, g);
+  launch(diff_scale_kernel, grid_for(n, 256), 256, 0, st, a, b, n, coef, accumulate, g);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_tanh_bwd(const float* g, const float* out, long long n, float* gpre, cudaStream_t st) {
-  tanh_bwd_kernel<<<grid_for(n, 256), 256, 0, st>>>(g, out, n, gpre);
+  launch(tanh_bwd_kernel, grid_for(n, 256), 256, 0, st, g, out, n, gpre);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_axpby(float a, const float* x, float b, float* y, long long n, cudaStream_t st) {
-  axpby_kernel<<<grid_for(n, 256), 256, 0, st>>>(a, x, b, y, n);
+  launch(axpby_kernel, grid_for(n, 256), 256, 0, st, a, x, b, y, n);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_gather_strided(const float* src, long long n, long long stride, long long offset, float* dst,
                               cudaStream_t st) {
-  gather_strided_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, n, stride, offset, dst);
+  launch(gather_strided_kernel, grid_for(n, 256), 256, 0, st, src, n, stride, offset, dst);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -2276,23 +2326,23 @@ cudaError_t ew_frames_to_clip(const uint8_t* frames, int Hs, int Ws, int bgr, in
   g.sy = static_cast<double>(Hs) / H;
   if ((H + FC_ROWS - 1) / FC_ROWS > 65535 || static_cast<long long>(Hs) * Ws * 3 >= (1LL << 31))
     return cudaErrorInvalidValue;
-  frames_to_clip_kernel<<<dim3((W + 255) / 256, (H + FC_ROWS - 1) / FC_ROWS), 256, 0, st>>>(frames, g, clip);
+  launch(frames_to_clip_kernel, dim3((W + 255) / 256, (H + FC_ROWS - 1) / FC_ROWS), 256, 0, st, frames, g, clip);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_randn(float* z, long long n, unsigned long long seed, unsigned long long offset,
                      const unsigned long long* d_offset, cudaStream_t st) {
-  randn_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(z, n, seed, offset, d_offset);
+  launch(randn_kernel, grid_for((n + 3) / 4, 256), 256, 0, st, z, n, seed, offset, d_offset);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_counter_add(unsigned long long* c, unsigned long long inc, cudaStream_t st) {
-  counter_add_kernel<<<1, 1, 0, st>>>(c, inc);
+  launch(counter_add_kernel, 1, 1, 0, st, c, inc);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_fill(float* y, float v, long long n, cudaStream_t st) {
-  fill_kernel<<<grid_for(n, 256), 256, 0, st>>>(y, v, n);
+  launch(fill_kernel, grid_for(n, 256), 256, 0, st, y, v, n);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -2300,35 +2350,35 @@ cudaError_t ew_channel_sum_ncdhw(const float* g, int N, int C, long long sp, int
                                  float* out, cudaStream_t st) {
   if (C > 128) return cudaErrorInvalidValue;
   const int nblk = grid_for(sp, 512, 128);        // scratch: [C <= 128][nblk <= 128] doubles (the DetScratch partials)
-  channel_sum_ncdhw_kernel<<<dim3(nblk, C), 512, 0, st>>>(g, N, C, sp, scratch);
+  launch(channel_sum_ncdhw_kernel, dim3(nblk, C), 512, 0, st, g, N, C, sp, scratch);
   LAUNCH_CHECK();
-  channel_sum_final_kernel<<<(C + 63) / 64, 64, 0, st>>>(scratch, nblk, C, accumulate, out);
+  launch(channel_sum_final_kernel, (C + 63) / 64, 64, 0, st, scratch, nblk, C, accumulate, out);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_kl_grad(const float* mu, const float* lv, long long n, float coef, float* gmu, float* glv,
                        cudaStream_t st) {
-  kl_grad_kernel<<<grid_for(n, 256), 256, 0, st>>>(mu, lv, n, coef, gmu, glv);
+  launch(kl_grad_kernel, grid_for(n, 256), 256, 0, st, mu, lv, n, coef, gmu, glv);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_sn_grad(const float* G, const float* w, const float* u, const float* v, const float* sigma, int cout,
                        int k, int accumulate, float* scratch /*[SN_GRAD_BLOCKS]*/, float* gw, cudaStream_t st) {
   const int n = cout * k;
-  sn_grad_dot_kernel<<<SN_GRAD_BLOCKS, 256, 0, st>>>(G, w, n, scratch);
+  launch(sn_grad_dot_kernel, SN_GRAD_BLOCKS, 256, 0, st, G, w, n, scratch);
   LAUNCH_CHECK();
-  sn_grad_apply_kernel<<<grid_for(n, 256, 148 * 2), 256, 0, st>>>(G, scratch, u, v, sigma, cout, k, accumulate, gw);
+  launch(sn_grad_apply_kernel, grid_for(n, 256, 148 * 2), 256, 0, st, G, scratch, u, v, sigma, cout, k, accumulate, gw);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_lerp(const float* a, const float* b, float alpha, long long n, float* out, cudaStream_t st) {
-  lerp_kernel<<<grid_for(n, 256), 256, 0, st>>>(a, b, alpha, n, out);
+  launch(lerp_kernel, grid_for(n, 256), 256, 0, st, a, b, alpha, n, out);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_gp_grad(const float* g, int N, int C, long long sp, float lambda, float* Gout, float* gp,
                        DetScratch det, cudaStream_t st) {
-  gp_grad_kernel<<<grid_for(static_cast<long long>(N) * sp, 256, 148 * 4), 256, 0, st>>>(g, N, C, sp, lambda, Gout, gp,
+  launch(gp_grad_kernel, grid_for(static_cast<long long>(N) * sp, 256, 148 * 4), 256, 0, st, g, N, C, sp, lambda, Gout, gp,
                                                                                          det);
   LAUNCH_CHECK();
   return cudaSuccess;
@@ -2341,6 +2391,7 @@ cudaError_t ew_gp_grad(const float* g, int N, int C, long long sp, float lambda,
 // conv(no pad / stride 2) + BN + ReLU; the conv kernels here are stride-1 "same" convolutions with LeakyReLU epilogues).
 __global__ void slice_act_cl_kernel(const uint4* __restrict__ in, int T, int Hi, int Wi, int Ho, int Wo, int h0, int w0,
                                     int sh, int sw, int c8, int relu, long long total, uint4* __restrict__ out) {
+  pdl_grid_sync();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int g = static_cast<int>(i % c8);
@@ -2365,7 +2416,7 @@ cudaError_t ew_slice_act_cl(const __nv_bfloat16* in, int NT, int Hi, int Wi, int
   const long long total = static_cast<long long>(NT) * Ho * Wo * c8;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  slice_act_cl_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(reinterpret_cast<const uint4*>(in), NT, Hi, Wi, Ho, Wo,
+  launch(slice_act_cl_kernel, static_cast<unsigned>(blocks), 256, 0, st, reinterpret_cast<const uint4*>(in), NT, Hi, Wi, Ho, Wo,
                                                                       h0, w0, sh, sw, c8, relu, total,
                                                                       reinterpret_cast<uint4*>(out));
   return cudaGetLastError();
@@ -2377,6 +2428,7 @@ cudaError_t ew_slice_act_cl(const __nv_bfloat16* in, int NT, int Hi, int Wi, int
 // normals, and this kernel applies Box-Muller in place after the H2D copy: (u[2i], u[2i+1]) -> (z[2i], z[2i+1]).
 // u in [0, 1) with 24 bits: 1 - u is exact and in (0, 1], so the logarithm is finite.
 __global__ void box_muller_inplace_kernel(float* __restrict__ z, long long n) {
+  pdl_grid_sync();
   const long long pairs = (n + 1) >> 1;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < pairs;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -2391,7 +2443,7 @@ __global__ void box_muller_inplace_kernel(float* __restrict__ z, long long n) {
 }
 
 cudaError_t ew_box_muller_inplace(float* z, long long n, cudaStream_t st) {
-  box_muller_inplace_kernel<<<grid_for((n + 1) / 2, 256), 256, 0, st>>>(z, n);
+  launch(box_muller_inplace_kernel, grid_for((n + 1) / 2, 256), 256, 0, st, z, n);
   return cudaGetLastError();
 }
 

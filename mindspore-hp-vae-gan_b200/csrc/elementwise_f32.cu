@@ -8,6 +8,7 @@
 #include <cstdint>
 
 #include "det_reduce.cuh"
+#include "launch.cuh"
 #include "elementwise.h"
 
 namespace hpvg {
@@ -32,6 +33,7 @@ inline int grid_for(long long n, int block, int cap = 148 * 16) {
 // Narrow source (C <= 4: clips, 3-channel gradients) -> one 16-byte voxel (channels >= C zero).
 __global__ void pack_cl_f32_skinny_kernel(const float* __restrict__ x, int C, long long sp, long long voxels,
                                           float* __restrict__ y, int c_pitch, int c_off, int groups) {
+  pdl_grid_sync();
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= voxels * groups) return;
   const long long v = gid / groups;
@@ -52,6 +54,7 @@ __global__ void pack_cl_f32_skinny_kernel(const float* __restrict__ x, int C, lo
 __global__ void __launch_bounds__(256)
 pack_cl_f32_tiled_kernel(const float* __restrict__ x, int C, long long sp, long long voxels, float* __restrict__ y,
                          int c_pitch, int c_off, int c_fill /* channels [c_off, c_off + c_fill) are written */) {
+  pdl_grid_sync();
   __shared__ float tile[32][33];
   const int cb = blockIdx.y * 32;
   const long long v0 = static_cast<long long>(blockIdx.x) * 32;
@@ -79,6 +82,7 @@ pack_cl_f32_tiled_kernel(const float* __restrict__ x, int C, long long sp, long 
 __global__ void __launch_bounds__(256)
 unpack_cl_f32_tiled_kernel(const float* __restrict__ x, int C, long long sp, long long voxels, int c_pitch, int c_off,
                            float* __restrict__ y) {
+  pdl_grid_sync();
   __shared__ float tile[32][33];
   const int cb = blockIdx.y * 32;
   const long long v0 = static_cast<long long>(blockIdx.x) * 32;
@@ -105,6 +109,7 @@ unpack_cl_f32_tiled_kernel(const float* __restrict__ x, int C, long long sp, lon
 // sums[0][c] += sum y, sums[1][c] += sum y^2
 __global__ void bn_stats_cl_f32_kernel(const float* __restrict__ y, long long voxels, double* __restrict__ sum,
                                        double* __restrict__ sumsq, const DetScratch det) {
+  pdl_grid_sync();
   const int g = threadIdx.x & 15, vl = threadIdx.x >> 4;
   float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
   for (long long v = static_cast<long long>(blockIdx.x) * 16 + vl; v < voxels;
@@ -151,6 +156,7 @@ __device__ __forceinline__ float4 affine_act(float4 f, const float* sc, const fl
 __global__ void bn_apply_cl_f32_kernel(const float* __restrict__ y, long long groups /*voxels*16*/,
                                        const float* __restrict__ scale, const float* __restrict__ shift, int act,
                                        float* __restrict__ x) {
+  pdl_grid_sync();
   __shared__ float sc[64], sh[64];
   if (threadIdx.x < 64) {
     sc[threadIdx.x] = scale[threadIdx.x];
@@ -172,6 +178,7 @@ __global__ void bn_train_apply_cl_f32_kernel(const float* __restrict__ y, long l
                                              float eps, float momentum, float* __restrict__ mm,
                                              float* __restrict__ mv, float* __restrict__ saved, int act,
                                              float* __restrict__ x, const float* __restrict__ center) {
+  pdl_grid_sync();
   __shared__ float sc[64], sh[64];
   if (threadIdx.x < 64) {
     const int c = threadIdx.x;
@@ -206,6 +213,7 @@ __global__ void bn_train_apply_cl_f32_kernel(const float* __restrict__ y, long l
 // ----------------------------------------------------------------------------------------------- backward pieces
 __global__ void lrelu_bwd_cl_f32_kernel(const float* __restrict__ ga, const float* __restrict__ a, long long groups,
                                         float* __restrict__ gz) {
+  pdl_grid_sync();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < groups;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float4 g = *reinterpret_cast<const float4*>(ga + i * 4);
@@ -222,6 +230,7 @@ __global__ void lrelu_bwd_cl_f32_kernel(const float* __restrict__ ga, const floa
 __global__ void bn_bwd_reduce_cl_f32_kernel(const float* __restrict__ ga, const float* __restrict__ y,
                                             long long voxels, const float* __restrict__ saved /*[4][64]*/, int act,
                                             double* __restrict__ sums, const DetScratch det) {
+  pdl_grid_sync();
   const int g = threadIdx.x & 15, vl = threadIdx.x >> 4;
   float sc[4], sh[4], mu[4], is[4], s0[4], s1[4];
 #pragma unroll
@@ -286,6 +295,7 @@ __global__ void bn_bwd_apply_cl_f32_kernel(const float* __restrict__ ga, const f
                                            const float* __restrict__ saved, int act, const double* __restrict__ sums,
                                            double inv_count, float* __restrict__ gy, float* __restrict__ dgamma,
                                            float* __restrict__ dbeta, int accumulate) {
+  pdl_grid_sync();
   __shared__ float sc[64], sh[64], mu[64], is[64], m0[64], m1[64];
   if (threadIdx.x < 64) {
     const int c = threadIdx.x;
@@ -322,6 +332,7 @@ __global__ void bn_bwd_apply_cl_f32_kernel(const float* __restrict__ ga, const f
 
 __global__ void d2f_f32_kernel(const double* __restrict__ in, int n, float scale, int accumulate,
                                float* __restrict__ out) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (accumulate ? out[i] : 0.f) + scale * static_cast<float>(in[i]);
 }
@@ -341,11 +352,11 @@ cudaError_t ew_pack_cl_f32(const float* x, int N, int C, long long sp, float* y,
   if (C <= 4) {
     const int groups = (fill + 3) >> 2;
     const long long total = voxels * groups;
-    pack_cl_f32_skinny_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, C, sp, voxels, y, c_pitch,
+    launch(pack_cl_f32_skinny_kernel, static_cast<unsigned>((total + 255) / 256), 256, 0, st, x, C, sp, voxels, y, c_pitch,
                                                                                          c_off, groups);
   } else {
     if ((voxels + 31) / 32 >= (1LL << 31)) return cudaErrorInvalidValue;
-    pack_cl_f32_tiled_kernel<<<dim3(static_cast<unsigned>((voxels + 31) / 32), (fill + 31) / 32), 256, 0, st>>>(
+    launch(pack_cl_f32_tiled_kernel, dim3(static_cast<unsigned>((voxels + 31) / 32), (fill + 31) / 32), 256, 0, st, 
         x, C, sp, voxels, y, c_pitch, c_off, fill);
   }
   LAUNCH_CHECK();
@@ -355,42 +366,42 @@ cudaError_t ew_unpack_cl_f32(const float* x, int N, int C, long long sp, int c_p
                              cudaStream_t st) {
   const long long voxels = static_cast<long long>(N) * sp;
   if ((voxels + 31) / 32 >= (1LL << 31)) return cudaErrorInvalidValue;
-  unpack_cl_f32_tiled_kernel<<<dim3(static_cast<unsigned>((voxels + 31) / 32), (C + 31) / 32), 256, 0, st>>>(
+  launch(unpack_cl_f32_tiled_kernel, dim3(static_cast<unsigned>((voxels + 31) / 32), (C + 31) / 32), 256, 0, st, 
       x, C, sp, voxels, c_pitch, c_off, y);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_bn_stats_cl_f32(const float* y, long long voxels, double* sum, double* sumsq, DetScratch det,
                                cudaStream_t st) {
-  bn_stats_cl_f32_kernel<<<grid_for(voxels, 16, DET_MAX_BLOCKS), 256, 0, st>>>(y, voxels, sum, sumsq, det);
+  launch(bn_stats_cl_f32_kernel, grid_for(voxels, 16, DET_MAX_BLOCKS), 256, 0, st, y, voxels, sum, sumsq, det);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_bn_apply_cl_f32(const float* y, long long voxels, const float* scale, const float* shift, int act,
                                float* x, cudaStream_t st) {
-  bn_apply_cl_f32_kernel<<<grid_for(voxels * 16, 256), 256, 0, st>>>(y, voxels * 16, scale, shift, act, x);
+  launch(bn_apply_cl_f32_kernel, grid_for(voxels * 16, 256), 256, 0, st, y, voxels * 16, scale, shift, act, x);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_bn_train_apply_cl_f32(const float* y, long long voxels, const double* sums, const float* gamma,
                                      const float* beta, float eps, float momentum, float* mm, float* mv, float* saved,
                                      int act, float* x, const float* center, cudaStream_t st) {
-  bn_train_apply_cl_f32_kernel<<<grid_for(voxels * 16, 256), 256, 0, st>>>(
+  launch(bn_train_apply_cl_f32_kernel, grid_for(voxels * 16, 256), 256, 0, st, 
       y, voxels * 16, sums, static_cast<double>(voxels), gamma, beta, eps, momentum, mm, mv, saved, act, x, center);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_lrelu_bwd_cl_f32(const float* ga, const float* a, long long elems, float* gz, cudaStream_t st) {
-  lrelu_bwd_cl_f32_kernel<<<grid_for(elems / 4, 256), 256, 0, st>>>(ga, a, elems / 4, gz);
+  launch(lrelu_bwd_cl_f32_kernel, grid_for(elems / 4, 256), 256, 0, st, ga, a, elems / 4, gz);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
 cudaError_t ew_bn_bwd_cl_f32(const float* ga, const float* y, long long voxels, const float* saved, int act,
                              double* sums, DetScratch det, float* gy, float* dgamma, float* dbeta, int accumulate,
                              cudaStream_t st) {
-  bn_bwd_reduce_cl_f32_kernel<<<grid_for(voxels, 16, DET_MAX_BLOCKS), 256, 0, st>>>(ga, y, voxels, saved, act, sums, det);
+  launch(bn_bwd_reduce_cl_f32_kernel, grid_for(voxels, 16, DET_MAX_BLOCKS), 256, 0, st, ga, y, voxels, saved, act, sums, det);
   LAUNCH_CHECK();
-  bn_bwd_apply_cl_f32_kernel<<<grid_for(voxels * 16, 256), 256, 0, st>>>(ga, y, voxels * 16, saved, act, sums,
+  launch(bn_bwd_apply_cl_f32_kernel, grid_for(voxels * 16, 256), 256, 0, st, ga, y, voxels * 16, saved, act, sums,
                                                                          1.0 / static_cast<double>(voxels), gy, dgamma,
                                                                          dbeta, accumulate);
   LAUNCH_CHECK();
@@ -400,7 +411,7 @@ cudaError_t ew_colsum_cl_f32(const float* g, long long voxels, double* scratch, 
                              int accumulate, cudaStream_t st) {
   cudaError_t e = ew_bn_stats_cl_f32(g, voxels, scratch, scratch + 64, det, st);
   if (e != cudaSuccess) return e;
-  d2f_f32_kernel<<<1, 64, 0, st>>>(scratch, 64, 1.f, accumulate, out);
+  launch(d2f_f32_kernel, 1, 64, 0, st, scratch, 64, 1.f, accumulate, out);
   LAUNCH_CHECK();
   return cudaSuccess;
 }

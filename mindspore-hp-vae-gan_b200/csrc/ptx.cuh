@@ -221,6 +221,20 @@ __host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, 
   return d;
 }
 
+// Descriptor arithmetic for the MMA-issuing thread.  The low word of a descriptor is
+//   start address (16-byte units, bits 0..13) | LBO (16-byte units, bits 16..29)
+// and shared memory ends below 256 KB, so moving the start address (and, for the no-swizzle head layout, choosing the
+// LBO) is ONE 32-bit add of a compile-time constant to the low word of a descriptor built once per plane.  Building
+// every descriptor from scratch cost ~20 uniform-datapath instructions (shift / mask / or, plus uniform-register
+// spills) per tcgen05.mma: the issuing thread, not the tensor pipe, set the pace of the kernels (27 cycles per MMA
+// measured against a 16-cycle floor).
+__device__ __forceinline__ uint64_t desc_add_lo(uint64_t desc, uint32_t add_lo) {
+  return (desc & 0xFFFFFFFF00000000ull) | static_cast<uint64_t>(static_cast<uint32_t>(desc) + add_lo);
+}
+__host__ __device__ constexpr uint32_t desc_lo_delta(uint32_t byte_offset, uint32_t lbo_bytes = 0) {
+  return (byte_offset >> 4) | ((lbo_bytes >> 4) << 16);
+}
+
 // Instruction descriptor for kind::f16 with BF16 A/B and FP32 accumulate.
 //   a_mn_major / b_mn_major: 0 = K-major operand, 1 = MN-major operand.
 __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major = 0,
