@@ -54,7 +54,6 @@ struct TailParams {
   float* out;            // fp32 NCDHW, cout_real channels
   int cout_real;
   const float* addend;   // optional fp32 NCDHW residual (added after scale/shift, before the activation)
-  int dbg;
 };
 
 // TF32: the same kernel over fp32 channels-last activations, 32 input channels per launch (a 128-byte row = 32 tf32
@@ -118,7 +117,6 @@ conv3d_tail_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
         for (int t = 0; t < T; ++t, ++j) {
           const uint32_t slot = j % T_SLOTS, ph = (j / T_SLOTS) & 1u;
           mbar_wait(&a_empty[slot], ph ^ 1u);
-          if (p.dbg & 8) { mbar_arrive(&a_full[slot]); continue; }
           mbar_expect_tx(&a_full[slot], T_PLANE_BYTES);
           tma_load_5d(planes + slot * T_SLOT_STRIDE, &tmap_in, &a_full[slot], 0, w0 - 1, h0 - 1, t, n);
         }
@@ -127,27 +125,38 @@ conv3d_tail_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
     __syncwarp();
   } else if (warp == 1) {
     // ======================================================================================= MMA issuer
-    if (elect_one()) {
+    // The WHOLE warp walks the loop, so counters, barrier addresses and descriptors are warp-uniform and live in the
+    // uniform datapath; one elected lane (always the same one: tcgen05.commit tracks the MMAs of its own thread)
+    // issues.  Ring positions rotate (no modulo), descriptors are one add away from two built before the loop.
+    {
       mbar_wait(w_full, 0);
       const uint32_t idesc128 = make_idesc<TF32>(128, 32);
       const uint32_t idesc64 = make_idesc<TF32>(64, 32);
-      const uint32_t w_addr = smem_u32(w_sm);
-      const uint32_t planes_addr = smem_u32(planes);
-      uint32_t j0 = 0, q = 0;
+      const uint64_t a_desc0 = make_smem_desc(smem_u32(planes), 16, 1024, 2);   // slot 0; one add per slot / MMA
+      const uint64_t b_desc0 = make_smem_desc(smem_u32(w_sm), 16, 1024, 2);
+      constexpr uint32_t SLOT16 = T_SLOT_STRIDE >> 4;
+      uint32_t q = 0;
       const uint32_t my_units = (static_cast<uint32_t>(p.n_units) - blockIdx.x + gridDim.x - 1u) / gridDim.x;
       const uint32_t q_end = my_units * static_cast<uint32_t>(T);
-      // the tensor pipe idles while this thread waits between two planes (conv3d_umma.cu): the waits for the plane
+      // ring position of plane pl-1 / pl / pl+1 and the phase parity of plane pl+1's slot
+      uint32_t s_prev = 0, s_cur = 0, s_next = 0, ph_next = 0;
+      auto advance = [&]() {   // (s_prev, s_cur, s_next) <- (s_cur, s_next, s_next + 1)
+        s_prev = s_cur;
+        s_cur = s_next;
+        if (++s_next == T_SLOTS) {
+          s_next = 0;
+          ph_next ^= 1u;
+        }
+      };
+      // the tensor pipe idles while this warp waits between two planes (conv3d_umma.cu): the waits for the plane
       // the dt = 2 taps read and for the NEXT plane's accumulator stage sit behind the MMAs of dt = 0, 1
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      for (uint32_t u = 0; u < my_units; ++u) {
         for (int pl = 0; pl < T; ++pl, ++q) {
           const uint32_t ab = q & 1u;
           const uint32_t d1 = tmem_base + ab * 64, d2 = d1 + 32;
-          uint32_t accum = 0;
-          auto issue_dt = [&](int dt) {
-            const uint32_t a_base = planes_addr + ((j0 + pl + dt - 1) % T_SLOTS) * T_SLOT_STRIDE;
-            const uint32_t b_base = w_addr + dt * (32 * 128);
-            const uint64_t a0 = make_smem_desc(a_base, 16, 1024, 2);   // descriptors: one add per MMA (ptx.cuh)
-            const uint64_t b0 = make_smem_desc(b_base, 16, 1024, 2);
+          auto issue_dt = [&](int dt, uint32_t slot, uint32_t accum) {
+            const uint64_t a0 = desc_add_lo(a_desc0, slot * SLOT16);
+            const uint64_t b0 = desc_add_lo(b_desc0, desc_lo_delta(dt * (32 * 128)));
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t bd = desc_add_lo(b0, desc_lo_delta(k * 32));
@@ -156,26 +165,31 @@ conv3d_tail_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
               accum = 1;
             }
           };
-          if (pl == 0) mbar_wait(&a_full[j0 % T_SLOTS], (j0 / T_SLOTS) & 1u);
+          if (pl == 0) {   // a new unit: its plane 0 is the next ring position
+            mbar_wait(&a_full[s_next], ph_next);
+            advance();     // s_cur = plane 0, s_next = plane 1
+          }
           if (q < 2) mbar_wait(&acc_empty[ab], 1u);
           tc_fence_after();
-          if (pl >= 1) issue_dt(0);
-          issue_dt(1);
-          if (pl + 1 < T) {
-            const uint32_t jj = j0 + pl + 1;
-            mbar_wait(&a_full[jj % T_SLOTS], (jj / T_SLOTS) & 1u);
+          if (elect_one()) {
+            if (pl >= 1) issue_dt(0, s_prev, 0);
+            issue_dt(1, s_cur, pl >= 1 ? 1u : 0u);
           }
+          __syncwarp();
+          if (pl + 1 < T) mbar_wait(&a_full[s_next], ph_next);
           if (q + 1 < q_end && q + 1 >= 2) mbar_wait(&acc_empty[ab ^ 1u], (((q + 1) >> 1) & 1u) ^ 1u);
           tc_fence_after();
-          if (pl + 1 < T) issue_dt(2);
-          umma_commit(&acc_full[ab]);
-          if (pl >= 1) umma_commit(&a_empty[(j0 + pl - 1) % T_SLOTS]);
-          if (pl == T - 1) umma_commit(&a_empty[(j0 + pl) % T_SLOTS]);
+          if (elect_one()) {
+            if (pl + 1 < T) issue_dt(2, s_next, 1);
+            umma_commit(&acc_full[ab]);
+            if (pl >= 1) umma_commit(&a_empty[s_prev]);
+            if (pl == T - 1) umma_commit(&a_empty[s_cur]);
+          }
+          __syncwarp();
+          if (pl + 1 < T) advance();
         }
-        j0 += T;
       }
     }
-    __syncwarp();
   } else {
     // ======================================================================================= epilogue (2 x 4 warps)
     const int quad = warp & 3;
@@ -200,16 +214,12 @@ conv3d_tail_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + ab * 64;
         uint32_t r1[32], r2[32];
-        if (!(p.dbg & 2)) {
         tmem_ld32(taddr, r1);
         tmem_ld32(taddr + 32, r2);
         tmem_ld_wait();
-        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_relaxed(&acc_empty[ab]);
-        if (p.dbg & 1) continue;
-        if (p.dbg & 16) { if (inb) p.out[(static_cast<size_t>(n) * p.cout_real) * chan_sz + (static_cast<size_t>(pl) * p.H + h) * p.W + w] = __uint_as_float(r1[0]); continue; }
         {
           float* dst = pb + row * T_PS;
 #pragma unroll
@@ -308,7 +318,6 @@ const char* conv3d_tail_launch(const ConvLaunch& L, int sm_count, cudaStream_t s
   prm.out = static_cast<float*>(L.out);
   prm.cout_real = L.cout_real;
   prm.addend = L.addend;
-  { const char* e_ = getenv("HPVG_CONV_DBG"); prm.dbg = e_ ? atoi(e_) : 0; }
   if (prm.n_units < 1) return nullptr;
   static bool configured = false;
   if (!configured) {

@@ -75,9 +75,10 @@ struct Cfg<CONV_MODE_8_64> {
   // issue rate of 0.22 (profiles/r2_ncu_head_conv_store_experiment.csv).  Two groups of 4 epilogue warps, one per
   // accumulator stage, put two warps on every sub-partition and overlap one plane's TMEM load with the other's stores.
   static constexpr int EPI_GROUPS = 2;
-  static constexpr int STAGES = 0;   // measured: the head conv is 14 % SLOWER through the staged TMA store (0.359 vs 0.316 ms
-                                     // at 8 x 13x192x257) although its L2 write requests drop 8x — its epilogue warps are
-                                     // latency-bound on ld -> math -> store per plane, and the two CTA barriers add to that
+  // One staging tile per epilogue group.  (With ONE group the staged TMA store was 14 % slower than direct stores,
+  // 0.359 vs 0.316 ms at 8 x 13x192x257, although the L2 write requests dropped 8x: the lone group waited on its own
+  // store's read-out.  With direct stores the kernel sits at 79 % L1TEX throughput — 32 partial-line streams per store.)
+  static constexpr int STAGES = 2;
 };
 // kind::tf32 twins: fp32 operands, the SAME byte layouts with half the channels per row (a 128-byte row = 32 tf32
 // channels, K = 8 per MMA = the same 32 bytes; a 16-byte head voxel = 4 fp32 channels).  A 64 -> 64 layer at tf32 is two
@@ -378,7 +379,6 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
           const uint32_t slot = j % C::SLOTS;
           const uint32_t ph = (j / C::SLOTS) & 1u;
           mbar_wait(&a_empty[slot], ph ^ 1u);
-          if (p.dbg & 8) { if (rank == 0) mbar_arrive(&a_full[slot]); continue; }
           if (rank == 0) mbar_expect_tx(&a_full[slot], 2u * C::PLANE_BYTES);
           uint32_t dst_bar = leader_full[0];
 #pragma unroll
@@ -515,20 +515,24 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
     // rows / columns are clipped by the tensor map instead of being predicated per voxel.
     const bool tma_out = C::STAGES > 0 && !C::TF32 && p.tma_out != 0;
     uint32_t stage_n = 0;                      // tiles staged so far by this CTA
-    const bool store_thread = (warp == 2 && lane == 0);
-    auto stage_ptr = [&]() { return stage + (C::STAGES > 1 ? (stage_n & 1u) : 0u) * STAGE_BYTES; };
+    // EPI_GROUPS == 2: group g stages into tile g and synchronises on its own named barrier
+    const bool store_thread = (warp == 2 + 4 * static_cast<int>(grp) && lane == 0);
+    const uint32_t stage_bar = 4u + grp;
+    auto stage_ptr = [&]() {
+      return stage + (C::EPI_GROUPS == 2 ? grp : (C::STAGES > 1 ? (stage_n & 1u) : 0u)) * STAGE_BYTES;
+    };
     auto stage_row = [&]() { return reinterpret_cast<__nv_bfloat16*>(stage_ptr() + row * 128); };
     auto stage_row_begin = [&]() {
       // the tile about to be overwritten must have been read by the bulk store issued STAGES tiles ago
       if (store_thread) {
-        if constexpr (C::STAGES > 1) tma_store_wait_read<1>();
+        if constexpr (C::STAGES > 1 && C::EPI_GROUPS == 1) tma_store_wait_read<1>();
         else tma_store_wait_read<0>();
       }
-      asm volatile("bar.sync 2, 128;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(stage_bar) : "memory");
     };
     auto stage_row_end = [&](const Unit& u, int plane) {
       fence_proxy_async();                     // generic-proxy writes -> visible to the async proxy (TMA)
-      asm volatile("bar.sync 2, 128;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(stage_bar) : "memory");
       if (store_thread) {
         tma_store_5d(&tmap_out, stage_ptr(), 0, u.w0, u.h0, plane, u.n);
         tma_store_commit();
@@ -553,15 +557,12 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
         const size_t vox = ((static_cast<size_t>(un.n) * T + pl) * p.H + h) * p.W + w;
         if constexpr (C::NOUT == 64) {
           uint32_t r0[32], r1[32];
-          if (!(p.dbg & 2)) {
           tmem_ld32(taddr, r0);
           tmem_ld32(taddr + 32, r1);
           tmem_ld_wait();
-          }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster_relaxed(leader_empty[ab]);
-          if (p.dbg & 1) continue;
           if constexpr (!STATS) {
             if (inb) {
               if (p.out_mode == CONV_OUT_F32_RAW) {
@@ -722,6 +723,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
         // the 4 epilogue warps, then one fp64 atomic per channel and statistic per CTA.
         float* red = reinterpret_cast<float*>(planes);   // [epilogue warps][2 stats][64 ch]
         const int ew = warp - 2;
+        // (two groups: the other group's last plane may still be feeding the tensor pipe from the ring)
+        if constexpr (C::EPI_GROUPS == 2) asm volatile("bar.sync 3, 256;" ::: "memory");
         red[(ew * 2 + 0) * 64 + 2 * lane] = st_s0;
         red[(ew * 2 + 0) * 64 + 2 * lane + 1] = st_s1;
         red[(ew * 2 + 1) * 64 + 2 * lane] = st_q0;
@@ -822,7 +825,6 @@ const char* conv3d_umma_launch(const ConvLaunch& L, cudaStream_t stream) {
                                        (reinterpret_cast<uintptr_t>(L.mask) & 15)))
     return "LRELU_MASK needs a 16-byte aligned bf16 mask tensor and the bf16 output mode";
   ConvParams prm;
-  { const char* e_ = getenv("HPVG_CONV_DBG"); prm.dbg = e_ ? atoi(e_) : 0; }
   prm.N = L.N;
   prm.T = L.T;
   prm.H = L.H;
@@ -850,7 +852,8 @@ const char* conv3d_umma_launch(const ConvLaunch& L, cudaStream_t stream) {
   CUtensorMap tmap_out = tmap;
   prm.tma_out = 0;
   static const bool no_tma_store = getenv("HPVG_NO_TMA_STORE") != nullptr;
-  if (!tf32 && !no_tma_store && L.out_mode == CONV_OUT_BF16_NDHWC && L.mode == CONV_MODE_64_64 &&
+  if (!tf32 && !no_tma_store && L.out_mode == CONV_OUT_BF16_NDHWC &&
+      (L.mode == CONV_MODE_64_64 || L.mode == CONV_MODE_8_64) &&
       (L.out_pitch & 7) == 0 && (L.out_coff & 7) == 0 && (reinterpret_cast<uintptr_t>(L.out) & 15) == 0) {
     const cuuint64_t ovox = static_cast<cuuint64_t>(L.out_pitch) * 2;
     cuuint64_t ogd[5] = {64, static_cast<cuuint64_t>(L.W), static_cast<cuuint64_t>(L.H), static_cast<cuuint64_t>(L.T),

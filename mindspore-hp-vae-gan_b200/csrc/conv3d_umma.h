@@ -39,7 +39,6 @@ struct ConvParams {
   const void* mask;      // CONV_ACT_LRELU_MASK: bf16 cl tensor (same voxels, 64 channels at `mask`, mask_pitch per voxel)
   int mask_pitch;        //   y = v * LeakyReLU'(mask): the backward of a LeakyReLU fused into the data-gradient conv
   int in_merged;         // head variant: the tensor map has (C, W) merged (densely packed 8-channel input)
-  int dbg;               // TEMP
   double* stats;         // bf16 out, Cout 64: optional [2][64] fp64 accumulators (+= sum y, sum y^2 over all voxels of
                          // the stored output): the training-mode BatchNorm statistics, fused into the epilogue
 };
