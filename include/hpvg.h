@@ -87,6 +87,10 @@ int hpvg_graph_launch(void* graph_exec, void* stream);
 int hpvg_graph_destroy(void* graph_exec);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 long long hpvg_launch_count(void);
+/* programmatic dependent launch for every kernel of the library (default on; environment HPVG_PDL=0 turns it off):
+   returns the previous setting.  Kernels launched with it start their prologue while their predecessor in the
+   stream drains and block in griddepcontrol.wait before touching global memory (csrc/launch.cuh) */
+int hpvg_set_pdl(int on);
 
 /* ---------------------------------------------------------------- layout changes at the API edge */
 /* fp32 (N,C,T,H,W) -> bf16 (N,T,H,W,c_pitch) channels [c_off, c_off+C); channels [c_off+C, c_off+c_zero_to) := 0 */

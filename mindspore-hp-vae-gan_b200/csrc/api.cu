@@ -15,11 +15,17 @@
 #include "../../include/hpvg.h"
 #include "conv3d_umma.h"
 #include "elementwise.h"
+#include "launch.cuh"
 
 namespace {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
+}  // namespace
+namespace hpvg {
+int g_pdl_mode = -1;
+}
+namespace {
 int g_sm_count = 0;
 
 // Scratch memory is PER STREAM: two host threads (or two branches of a captured graph) driving different streams never
@@ -129,6 +135,11 @@ extern "C" {
 int hpvg_version(void) { return 100; }
 const char* hpvg_last_error(void) { return g_err.c_str(); }
 long long hpvg_launch_count(void) { return g_launches.load(); }
+int hpvg_set_pdl(int on) {
+  const int before = hpvg::pdl_enabled() ? 1 : 0;
+  hpvg::g_pdl_mode = on ? 1 : 0;
+  return before;
+}
 
 int hpvg_device_count(void) {
   int n = 0;

@@ -31,16 +31,26 @@ __device__ __forceinline__ void det_reduce_128(double value, int t, bool active,
   else __syncthreads();
   if (s_last && active) {
     __threadfence();
-    const volatile double* p = s.partials + t;
-    double acc = 0.0;
-    for (unsigned int b = 0; b < nblocks; ++b) acc += p[static_cast<size_t>(b) * 128];
+    // four interleaved chains (rows b % 4), combined in a fixed order: the loads of a chain step are independent, so
+    // the tail of a launch-latency-bound kernel is nblocks / 4 dependent adds instead of nblocks dependent L2 loads
+    const double* p = s.partials + t;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    unsigned int b = 0;
+    for (; b + 4 <= nblocks; b += 4) {
+      a0 += __ldcg(p + static_cast<size_t>(b) * 128);
+      a1 += __ldcg(p + static_cast<size_t>(b + 1) * 128);
+      a2 += __ldcg(p + static_cast<size_t>(b + 2) * 128);
+      a3 += __ldcg(p + static_cast<size_t>(b + 3) * 128);
+    }
+    for (; b < nblocks; ++b) a0 += __ldcg(p + static_cast<size_t>(b) * 128);
+    const double acc = (a0 + a1) + (a2 + a3);
     double* o = (t < 64) ? out_lo + t : out_hi + (t - 64);
     *o = accumulate ? *o + acc : acc;
     if (t == 0) *s.counter = 0u;
   }
 }
 
-// Scalar twin: every block contributes one value (thread 0); the last block writes out = scale * sum in block order.
+// Scalar twin: every block contributes one value (thread 0); the last block writes out = scale * sum (fixed order).
 __device__ __forceinline__ void det_reduce_scalar(float value, unsigned int block_id, unsigned int nblocks, DetScratch s,
                                                   float scale, float* out) {
   __shared__ unsigned int s_last1;
@@ -50,13 +60,23 @@ __device__ __forceinline__ void det_reduce_scalar(float value, unsigned int bloc
     s_last1 = (atomicAdd(s.counter, 1u) == nblocks - 1u) ? 1u : 0u;
   }
   __syncthreads();
-  if (s_last1 && threadIdx.x == 0) {
+  if (s_last1) {
+    // the whole (last) block: thread i sums partials i, i + blockDim, ... ; a fixed-order tree over shared memory
+    // finishes — same result whatever block happens to be last
+    __shared__ double s_tree[256];
     __threadfence();
-    const volatile double* p = s.partials;
     double acc = 0.0;
-    for (unsigned int b = 0; b < nblocks; ++b) acc += p[b];
-    *out = static_cast<float>(acc) * scale;
-    *s.counter = 0u;
+    for (unsigned int b = threadIdx.x; b < nblocks; b += blockDim.x) acc += __ldcg(s.partials + b);
+    if (threadIdx.x < 256) s_tree[threadIdx.x] = acc;
+    __syncthreads();
+    for (unsigned int w = 128; w >= 1; w >>= 1) {
+      if (threadIdx.x < w && threadIdx.x + w < blockDim.x) s_tree[threadIdx.x] += s_tree[threadIdx.x + w];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      *out = static_cast<float>(s_tree[0]) * scale;
+      *s.counter = 0u;
+    }
   }
 }
 

@@ -26,12 +26,14 @@ __device__ __forceinline__ void pdl_grid_sync() {
   pdl_launch_dependents();
 }
 
+// -1: not decided yet (environment HPVG_PDL, default on); 0 / 1: off / on (hpvg_set_pdl).  Defined in api.cu.
+extern int g_pdl_mode;
 inline bool pdl_enabled() {
-  static const bool on = [] {
+  if (g_pdl_mode < 0) {
     const char* e = std::getenv("HPVG_PDL");
-    return !(e && e[0] == '0');
-  }();
-  return on;
+    g_pdl_mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl_mode != 0;
 }
 
 // launch(kernel, grid, block, dynamic smem, stream, args...) — the <<<>>> of this library

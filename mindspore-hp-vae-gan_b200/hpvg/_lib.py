@@ -55,6 +55,7 @@ _SIGS = {
     "hpvg_graph_launch": ([vp, vp], c_int),
     "hpvg_graph_destroy": ([vp], c_int),
     "hpvg_launch_count": ([], ll),
+    "hpvg_set_pdl": ([i], c_int),
     "hpvg_pack_cl": ([vp, i, i, i, i, i, vp, i, i, i, vp], c_int),
     "hpvg_unpack_cl": ([vp, i, i, i, i, i, i, i, vp, vp], c_int),
     "hpvg_conv_wimg_bytes": ([i], c_int),

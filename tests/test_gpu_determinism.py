@@ -121,3 +121,15 @@ def test_train_iterations_are_bitwise_reproducible(hpvg_gpu):
     assert l1 == l2
     diff = [k for k in p1 if not _same(p1[k], p2[k])]
     assert not diff, "parameters differ between two runs: %s" % diff[:5]
+    # ... and the same bits with programmatic dependent launch switched off (csrc/launch.cuh): a kernel that touched
+    # global memory before its griddepcontrol.wait, or overwrote a buffer its still-running predecessor reads, would
+    # show up here as a difference
+    before = hp.lib.hpvg_set_pdl(0)
+    try:
+        p3, l3 = run()
+    finally:
+        hp.lib.hpvg_set_pdl(before)
+    assert before == 1, "programmatic dependent launch is the default"
+    assert l1 == l3
+    diff = [k for k in p1 if not _same(p1[k], p3[k])]
+    assert not diff, "parameters differ between PDL on / off: %s" % diff[:5]
