@@ -25,14 +25,21 @@ namespace hpvg {
 
 namespace {
 
-constexpr int WG_NH = 4;                 // gy rows per tile
+#ifndef HPVG_WG_NH
+#define HPVG_WG_NH 4
+#endif
+#ifndef HPVG_WG_STAGES
+#define HPVG_WG_STAGES 2
+#endif
+constexpr int WG_NH = HPVG_WG_NH;        // gy rows per tile
 constexpr int WG_WS = 64;                // gy voxels per row per tile
 constexpr int WG_XP = WG_WS + 2;         // x row pitch (voxels)
-constexpr int WG_X_BYTES = (WG_NH + 2) * WG_XP * 128;   // 50688
-constexpr int WG_X_STRIDE = 51200;                      // 1024-aligned
-constexpr int WG_GY_BYTES = WG_NH * WG_WS * 128;        // 32768
-constexpr int WG_STAGE = WG_X_STRIDE + WG_GY_BYTES;     // 83968
-constexpr int WG_STAGES = 2;
+constexpr int WG_X_BYTES = (WG_NH + 2) * WG_XP * 128;
+constexpr int WG_X_STRIDE = (WG_X_BYTES + 1023) & ~1023;   // 1024-aligned
+constexpr int WG_GY_BYTES = WG_NH * WG_WS * 128;
+constexpr int WG_STAGE = WG_X_STRIDE + WG_GY_BYTES;
+constexpr int WG_STAGES = HPVG_WG_STAGES;
+static_assert(1024 + WG_STAGES * WG_STAGE + 64 <= 227 * 1024, "wgrad ring exceeds the shared memory of an SM");
 constexpr int WG_THREADS = 192;
 constexpr int WG_SMEM = 1024 + WG_STAGES * WG_STAGE + 64;
 
