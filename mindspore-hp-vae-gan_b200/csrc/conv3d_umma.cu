@@ -339,31 +339,39 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
   if (warp == 1) tmem_alloc_pair(tmem_ptr_sm, C::TMEM_COLS);
   // barriers and TMEM are set up while the previous kernel of the stream drains (launch.cuh); global memory from here on
   pdl_grid_sync();
-  if (threadIdx.x < 64) {
-    scale_sm[threadIdx.x] = threadIdx.x < C::NOUT ? p.scale[threadIdx.x] : 0.f;
-    shift_sm[threadIdx.x] = threadIdx.x < C::NOUT ? p.shift[threadIdx.x] : 0.f;
-  }
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_sm;
+  // Order in which the temporal thirds of the filter bank are fetched = the order this pair's FIRST output plane consumes
+  // them: dt = 1, 2, 0 when it is the first plane of a strip (no dt = 0 tap), else dt = 0, 1, 2.  (Measured with
+  // clock64 stamps at 4x38x51, one plane per pair: the three pairs out of four that start mid-strip waited for the
+  // whole 110 KB bank before their first MMA.)
+  int w_first = 1;
+  {
+    int g0w, g1w;
+    work_range(pair, n_pairs, p, g0w, g1w);
+    if (g1w > g0w && next_item(g0w, g1w, T).t0 > 0) w_first = 0;
+  }
 
   if (warp == 0) {
     // =========================================================================== TMA producer (both CTAs)
     if (elect_one()) {
       tma_prefetch_desc(&tmap_in);
       // resident filter bank: this CTA's half of Cout, all taps — one barrier per temporal offset, so the first MMAs
-      // start after a third of the bank (dt = 1 first: the strip's first plane has no dt = 0 tap)
+      // start after a third of the bank.  The first third goes out now, the other two behind the first two input planes
+      // (what the first MMAs need is one third of the bank and two planes, not the whole bank).
       const uint8_t* wsrc = p.wimg + static_cast<size_t>(rank) * C::W_BYTES;
       constexpr int CHUNK = (C::DT_BYTES % 3 == 0 && C::DT_BYTES / 3 >= 1024) ? C::DT_BYTES / 3 : C::DT_BYTES;
       static_assert(C::W_BYTES == 3 * C::DT_BYTES && C::DT_BYTES % CHUNK == 0 && CHUNK % 16 == 0, "filter bank layout");
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int dt = (i + 1) % 3;   // 1, 2, 0
+      auto load_bank_third = [&](int i) {
+        const int dt = (w_first + i) % 3;
         mbar_expect_tx(&w_full[dt], C::DT_BYTES);
         for (int off = dt * C::DT_BYTES; off < (dt + 1) * C::DT_BYTES; off += CHUNK)
           bulk_load(w_sm + off, wsrc + off, CHUNK, &w_full[dt]);
-      }
+      };
+      load_bank_third(0);
+      bool bank_complete = false;
       uint32_t leader_full[C::SLOTS];
 #pragma unroll
       for (int i = 0; i < C::SLOTS; ++i) leader_full[i] = map_to_cta(smem_u32(&a_full[i]), 0);
@@ -387,7 +395,16 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
             tma_load_5d_pair(planes + slot * C::SLOT_STRIDE, &tmap_in, dst_bar, (un.w0 - 1) * C::CIN, un.h0 - 1, t, un.n, 0);
           else
             tma_load_5d_pair(planes + slot * C::SLOT_STRIDE, &tmap_in, dst_bar, 0, un.w0 - 1, un.h0 - 1, t, un.n);
+          if (!bank_complete && j >= 1) {
+            load_bank_third(1);
+            load_bank_third(2);
+            bank_complete = true;
+          }
         }
+      }
+      if (!bank_complete) {   // (a pair with at most one input plane; every third is waited for before the kernel ends)
+        load_bank_third(1);
+        load_bank_third(2);
       }
     }
     __syncwarp();
@@ -397,7 +414,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
       // tell the leader as each third of this CTA's half of the filter bank becomes resident
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        const int dt = (i + 1) % 3;
+        const int dt = (w_first + i) % 3;   // the order of arrival (see w_first)
         mbar_wait(&w_full[dt], 0);
         mbar_arrive_cluster(map_to_cta(smem_u32(&w_peer[dt]), 0));
       }
@@ -508,6 +525,14 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
     uint32_t leader_empty[2];
     leader_empty[0] = map_to_cta(smem_u32(&acc_empty[0]), 0);
     leader_empty[1] = map_to_cta(smem_u32(&acc_empty[1]), 0);
+    // epilogue vectors: fetched by the warps that use them, off the critical path of the prologue (they have nothing to
+    // do until the first accumulator is complete)
+    if (threadIdx.x - 64 < 64) {
+      const int c = threadIdx.x - 64;
+      scale_sm[c] = c < C::NOUT ? p.scale[c] : 0.f;
+      shift_sm[c] = c < C::NOUT ? p.shift[c] : 0.f;
+    }
+    asm volatile("bar.sync 6, %0;" ::"n"(128 * C::EPI_GROUPS) : "memory");
     uint32_t q = 0;
     // ---- TMA-store epilogue (bf16 channels-last output): the four epilogue warps write their 128 rows (128 B each) into
     // a 128B-swizzled shared-memory tile — conflict-free 16-byte stores — and ONE bulk tensor store moves the tile out:
