@@ -2203,7 +2203,7 @@ cudaError_t ew_upsample_noise_pack(const float* x, int N, int C, int Ti, int Hi,
 }
 cudaError_t ew_bn_stats_cl(const __nv_bfloat16* y, long long voxels, double* sum, double* sumsq, DetScratch det,
                            cudaStream_t st) {
-  launch(bn_stats_cl_kernel, grid_for(voxels, 32, DET_STREAM_BLOCKS), 256, 0, st, y, voxels, sum, sumsq, det);
+  launch(bn_stats_cl_kernel, grid_for(voxels, 128, DET_STREAM_BLOCKS), 256, 0, st, y, voxels, sum, sumsq, det);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -2321,7 +2321,7 @@ cudaError_t ew_lrelu_bwd_cl(const __nv_bfloat16* ga, const __nv_bfloat16* a, lon
 cudaError_t ew_bn_bwd_cl(const __nv_bfloat16* ga, const __nv_bfloat16* y, long long voxels, const float* saved, int act,
                          double* sums, DetScratch det, __nv_bfloat16* gy, float* dgamma, float* dbeta, int accumulate,
                          cudaStream_t st) {
-  launch(bn_bwd_reduce_cl_kernel, grid_for(voxels, 32, DET_STREAM_BLOCKS), 256, 0, st, ga, y, voxels, saved, act, sums, det);
+  launch(bn_bwd_reduce_cl_kernel, grid_for(voxels, 128, DET_STREAM_BLOCKS), 256, 0, st, ga, y, voxels, saved, act, sums, det);
   LAUNCH_CHECK();
   launch(bn_bwd_apply_cl_kernel, grid_for(voxels * 8, 256), 256, 0, st, ga, y, voxels * 8, saved, act, sums,
                                                                     1.0 / static_cast<double>(voxels), gy, dgamma, dbeta,

@@ -373,7 +373,7 @@ cudaError_t ew_unpack_cl_f32(const float* x, int N, int C, long long sp, int c_p
 }
 cudaError_t ew_bn_stats_cl_f32(const float* y, long long voxels, double* sum, double* sumsq, DetScratch det,
                                cudaStream_t st) {
-  launch(bn_stats_cl_f32_kernel, grid_for(voxels, 16, DET_STREAM_BLOCKS), 256, 0, st, y, voxels, sum, sumsq, det);
+  launch(bn_stats_cl_f32_kernel, grid_for(voxels, 64, DET_STREAM_BLOCKS), 256, 0, st, y, voxels, sum, sumsq, det);
   LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -399,7 +399,7 @@ cudaError_t ew_lrelu_bwd_cl_f32(const float* ga, const float* a, long long elems
 cudaError_t ew_bn_bwd_cl_f32(const float* ga, const float* y, long long voxels, const float* saved, int act,
                              double* sums, DetScratch det, float* gy, float* dgamma, float* dbeta, int accumulate,
                              cudaStream_t st) {
-  launch(bn_bwd_reduce_cl_f32_kernel, grid_for(voxels, 16, DET_STREAM_BLOCKS), 256, 0, st, ga, y, voxels, saved, act, sums, det);
+  launch(bn_bwd_reduce_cl_f32_kernel, grid_for(voxels, 64, DET_STREAM_BLOCKS), 256, 0, st, ga, y, voxels, saved, act, sums, det);
   LAUNCH_CHECK();
   launch(bn_bwd_apply_cl_f32_kernel, grid_for(voxels * 16, 256), 256, 0, st, ga, y, voxels * 16, saved, act, sums,
                                                                          1.0 / static_cast<double>(voxels), gy, dgamma,
