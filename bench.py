@@ -594,11 +594,11 @@ def run_ours(args):
         barrier()
         return max_over_ranks(ms), launches, prof
 
-    def timed_pipeline(noise, steps):
+    def timed_pipeline(noise, steps, fused=False):
         """`steps` chunks of B clips through sampling.SamplePipeline (the public API): wall-clock of pipe.run() between
         two device-wide barriers — host draws, H2D, generation, D2H of every clip, the last clip on the host."""
         threads = max(1, min(8, (os.cpu_count() or 2) // max(local_world, 1)))
-        pipe = sampling.SamplePipeline(net, amps, B, seed=7 + rank, stream=st, threads=threads, noise=noise)
+        pipe = sampling.SamplePipeline(net, amps, B, seed=7 + rank, stream=st, threads=threads, noise=noise, fused=fused)
         base = rank * 1000000
         warm = [[base + c * B + i for i in range(B)] for c in range(W)]
         chunks = [[base + (W + c) * B + i for i in range(B)] for c in range(steps)]
@@ -627,6 +627,7 @@ def run_ours(args):
     ms_dev, launches, prof = timed_device(step_device, args.steps, profile_mode=ops.CONV_64_64)
     ms_e2e, e2e_info = timed_pipeline("host", args.steps)
     ms_e2e_dev, e2e_dev_info = timed_pipeline("device", args.steps)
+    ms_e2e_fused, e2e_fused_info = timed_pipeline("host", args.steps, fused=True)
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
@@ -664,7 +665,13 @@ def run_ours(args):
                 "device_noise": {"value": clips / (ms_e2e_dev / 1000.0), "unit": UNIT, "h2d_bytes_per_step": 0,
                                  "d2h_bytes_per_step": int(e2e_dev_info["d2h"]),
                                  "note": "same call with noise='device': z from the device Philox generator keyed by "
-                                         "(seed, sample index) — no host draw, clips still copied to the host"}},
+                                         "(seed, sample index) — no host draw, clips still copied to the host"},
+                "fused_entry": {"value": clips / (ms_e2e_fused / 1000.0), "unit": UNIT,
+                                "h2d_bytes_per_step": int(e2e_fused_info["h2d"]),
+                                "d2h_bytes_per_step": int(e2e_fused_info["d2h"]),
+                                "note": "the same pipeline (host draw included) with the generation issued as ONE C call "
+                                        "per chunk, hpvg_generator_sample (include/hpvg.h), instead of one call per "
+                                        "layer from Python; bit-identical clips"}},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": roofline,

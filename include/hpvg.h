@@ -309,6 +309,39 @@ int hpvg_lerp(const float* d_a, const float* d_b, float alpha, long long n, floa
 int hpvg_gp_grad(const float* d_g, int N, int C, long long spatial, float lambda, float* d_G, float* d_gp,
                  void* stream);
 
+/* ---------------------------------------------------------------- fused sampling entry (SURVEY.md §8b "granularity")
+ * One call = GeneratorHPVAEGAN.construct(noise_init=z, isRandom=True) in eval mode for a batch of N samples
+ * (reference networks_3d.py:406-451 as driven by eval_video.py:53-82): decoder block on z, then for every refinement
+ * stage  up = trilinear(x_prev) ; x_in = up + noise * amp ; x = tanh(block(x_in) + up).
+ * bf16 precision mode.  The description holds what the host prepared once per checkpoint: packed filter banks
+ * (hpvg_conv_pack_weights*) and epilogue vectors (hpvg_bn_fold_eval: eval-mode BatchNorm folded into the conv) of
+ * every layer.  No allocation, no synchronisation: everything is enqueued on `stream`; activations live in the
+ * caller's workspace of hpvg_generator_sample_workspace() bytes. */
+#define HPVG_MAX_LEVELS 16
+#define HPVG_BLOCK_LAYERS 8
+typedef struct {
+  int n_layers;                             /* conv layers of the block; the last one is the 64 -> nc_im tail */
+  int cin[HPVG_BLOCK_LAYERS];               /* nc_im (head of a refinement block), 64, or 128 (decoder head) */
+  const void* wimg[HPVG_BLOCK_LAYERS][2];   /* packed banks; [l][1] is the second 64-channel half of a 128-channel input */
+  const float* scale[HPVG_BLOCK_LAYERS];    /* [64] epilogue multiplier (tail: [nc_im]) */
+  const float* shift[HPVG_BLOCK_LAYERS];    /* [64] epilogue offset */
+} HpvgBlock;
+typedef struct {
+  int n_stages;                             /* refinement blocks = pyramid levels - 1 */
+  int nc_im, latent_dim;
+  int T[HPVG_MAX_LEVELS], H[HPVG_MAX_LEVELS], W[HPVG_MAX_LEVELS];   /* level 0 (z, decoder) .. n_stages */
+  float noise_amp[HPVG_MAX_LEVELS];         /* level l: amplitude of the refinement noise; 0 = none (VAE levels) */
+  uint64_t noise_seed[HPVG_MAX_LEVELS];     /* level l: Philox key of that noise */
+  HpvgBlock decoder;
+  HpvgBlock body[HPVG_MAX_LEVELS];          /* body[s] produces level s + 1 */
+} HpvgGenerator;
+size_t hpvg_generator_sample_workspace(const HpvgGenerator* g, int N);
+/* d_z: fp32 (N, latent_dim, T0, H0, W0); d_out: fp32 (N, nc_im, T, H, W) of the finest level; d_vae_out: optional fp32
+ * (N, nc_im, T0, H0, W0) decoder output; sample_base: index of the batch's first sample (keys the device noise, so a
+ * sample's noise does not depend on how samples are batched or sharded) */
+int hpvg_generator_sample(const HpvgGenerator* g, const float* d_z, int N, uint64_t sample_base, float* d_out,
+                          float* d_vae_out, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- MindSpore ops.Custom(func_type="aot") entry points
  * int Name(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes, void* stream, void* extra)
  * params = fp32 device pointers in the reference's layouts, inputs then outputs, pre-allocated by the framework.

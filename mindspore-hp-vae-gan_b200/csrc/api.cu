@@ -782,6 +782,121 @@ int hpvg_gp_grad(const float* g, int N, int C, long long sp, float lambda, float
   return HPVG_OK;
 }
 
+}  // extern "C"
+// ------------------------------------------------------------------------------------------------ fused sampling entry
+// GeneratorHPVAEGAN.construct(noise_init=z, isRandom=True) in eval mode as ONE call (include/hpvg.h): the launches the
+// Python layer (hpvg/networks_3d.py: construct / refinement_layers / _run_block) makes, in the same order with the same
+// arguments — so the result is bit-identical to that path — without a host round trip per launch.
+namespace {
+struct SampleWs {
+  size_t zcl, raw, act[2], up, xin, lvl[2], total;
+};
+inline size_t al256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+SampleWs sample_ws_layout(const HpvgGenerator* g, int N) {
+  size_t vmax = 0;
+  for (int l = 0; l <= g->n_stages; ++l) {
+    const size_t v = static_cast<size_t>(g->T[l]) * g->H[l] * g->W[l];
+    if (v > vmax) vmax = v;
+  }
+  const size_t v0 = static_cast<size_t>(g->T[0]) * g->H[0] * g->W[0], n = static_cast<size_t>(N);
+  SampleWs w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off += al256(bytes);
+    return o;
+  };
+  w.zcl = take(n * v0 * g->latent_dim * 2);
+  w.raw = take(n * v0 * 64 * 4);
+  w.act[0] = take(n * vmax * 64 * 2);
+  w.act[1] = take(n * vmax * 64 * 2);
+  w.up = take(n * vmax * g->nc_im * 4);
+  w.xin = take(n * vmax * 16);
+  w.lvl[0] = take(n * vmax * g->nc_im * 4);
+  w.lvl[1] = take(n * vmax * g->nc_im * 4);
+  w.total = off;
+  return w;
+}
+// one block: hidden layers (conv + folded BN + LeakyReLU, bf16 channels-last ping-pong) and the tail
+// (64 -> nc_im, + residual, tanh, fp32 ncdhw)
+int sample_block(const HpvgBlock& b, int nc_im, int N, int T, int H, int W, const void* x, int x_pitch, char* act0,
+                 char* act1, float* raw, const float* residual, float* out, void* st) {
+  if (b.n_layers < 2 || b.n_layers > HPVG_BLOCK_LAYERS) return fail(HPVG_E_ARG, "generator_sample: 2..8 layers per block");
+  const void* h = x;
+  int pitch = x_pitch;
+  for (int l = 0; l < b.n_layers - 1; ++l) {
+    char* o = (l & 1) ? act1 : act0;
+    int rc;
+    if (b.cin[l] == 128) {   // two 64-channel halves: the first leaves raw fp32 partial sums, the second adds them
+      rc = hpvg_conv_cl(HPVG_CONV_64_64, N, T, H, W, h, pitch, b.wimg[l][0], b.scale[l], b.shift[l], HPVG_ACT_NONE,
+                        HPVG_OUT_F32_RAW, raw, 64, 0, 64, nullptr, nullptr, nullptr, 0, st);
+      if (rc != HPVG_OK) return rc;
+      rc = hpvg_conv_cl(HPVG_CONV_64_64, N, T, H, W, static_cast<const char*>(h) + 64 * 2, pitch, b.wimg[l][1],
+                        b.scale[l], b.shift[l], HPVG_ACT_LRELU, HPVG_OUT_BF16_CL, o, 64, 0, 64, raw, nullptr, nullptr, 0,
+                        st);
+    } else if (b.cin[l] == 64 || b.cin[l] <= 8) {
+      rc = hpvg_conv_cl(b.cin[l] == 64 ? HPVG_CONV_64_64 : HPVG_CONV_8_64, N, T, H, W, h, pitch, b.wimg[l][0],
+                        b.scale[l], b.shift[l], HPVG_ACT_LRELU, HPVG_OUT_BF16_CL, o, 64, 0, 64, nullptr, nullptr,
+                        nullptr, 0, st);
+    } else {
+      return fail(HPVG_E_ARG, "generator_sample: layer input channels must be <= 8, 64 or 128");
+    }
+    if (rc != HPVG_OK) return rc;
+    h = o;
+    pitch = 64;
+  }
+  const int t = b.n_layers - 1;
+  return hpvg_conv_cl(nc_im <= 3 ? HPVG_CONV_64_3 : HPVG_CONV_64_16, N, T, H, W, h, pitch, b.wimg[t][0], b.scale[t],
+                      b.shift[t], HPVG_ACT_TANH, HPVG_OUT_F32_NCDHW, out, 64, 0, nc_im, residual, nullptr, nullptr, 0,
+                      st);
+}
+}  // namespace
+extern "C" {
+size_t hpvg_generator_sample_workspace(const HpvgGenerator* g, int N) {
+  if (!g || N <= 0 || g->n_stages < 0 || g->n_stages >= HPVG_MAX_LEVELS) return 0;
+  return sample_ws_layout(g, N).total;
+}
+int hpvg_generator_sample(const HpvgGenerator* g, const float* z, int N, uint64_t sample_base, float* out,
+                          float* vae_out, void* workspace, size_t workspace_bytes, void* st) {
+  if (!g || !z || !out || !workspace) return fail(HPVG_E_ARG, "generator_sample: null argument");
+  if (N <= 0) return HPVG_OK;
+  if (g->n_stages < 0 || g->n_stages >= HPVG_MAX_LEVELS) return fail(HPVG_E_ARG, "generator_sample: 0..15 stages");
+  if (g->nc_im < 1 || g->nc_im > 4 || (g->latent_dim != 64 && g->latent_dim != 128))
+    return fail(HPVG_E_ARG, "generator_sample: nc_im 1..4, latent_dim 64 or 128");
+  const SampleWs w = sample_ws_layout(g, N);
+  if (workspace_bytes < w.total) return fail(HPVG_E_ARG, "generator_sample: workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(HPVG_E_ARG, "generator_sample: workspace not 256-byte aligned");
+  char* ws = static_cast<char*>(workspace);
+  // ---- decoder on z (networks_3d.py:419-423)
+  int rc = hpvg_pack_cl(z, N, g->latent_dim, g->T[0], g->H[0], g->W[0], ws + w.zcl, g->latent_dim, 0, g->latent_dim, st);
+  if (rc != HPVG_OK) return rc;
+  float* lvl[2] = {reinterpret_cast<float*>(ws + w.lvl[0]), reinterpret_cast<float*>(ws + w.lvl[1])};
+  float* prev = (g->n_stages == 0) ? out : (vae_out ? vae_out : lvl[0]);
+  rc = sample_block(g->decoder, g->nc_im, N, g->T[0], g->H[0], g->W[0], ws + w.zcl, g->latent_dim, ws + w.act[0],
+                    ws + w.act[1], reinterpret_cast<float*>(ws + w.raw), nullptr, prev, st);
+  if (rc != HPVG_OK) return rc;
+  if (g->n_stages == 0 && vae_out) {
+    const size_t bytes = static_cast<size_t>(N) * g->nc_im * g->T[0] * g->H[0] * g->W[0] * 4;
+    CU(cudaMemcpyAsync(vae_out, out, bytes, cudaMemcpyDeviceToDevice, S(st)));
+  }
+  // ---- refinement stages (networks_3d.py:434-451)
+  float* up = reinterpret_cast<float*>(ws + w.up);
+  for (int s = 0; s < g->n_stages; ++s) {
+    const int l = s + 1;
+    const float amp = g->noise_amp[l];
+    rc = hpvg_upsample_noise_pack(prev, N, g->nc_im, g->T[s], g->H[s], g->W[s], g->T[l], g->H[l], g->W[l], nullptr, amp,
+                                  amp != 0.f ? g->noise_seed[l] : 0, sample_base, nullptr, up, ws + w.xin, st);
+    if (rc != HPVG_OK) return rc;
+    float* o = (s == g->n_stages - 1) ? out : lvl[l & 1];
+    rc = sample_block(g->body[s], g->nc_im, N, g->T[l], g->H[l], g->W[l], ws + w.xin, 8, ws + w.act[0], ws + w.act[1],
+                      nullptr, up, o, st);
+    if (rc != HPVG_OK) return rc;
+    prev = o;
+  }
+  return HPVG_OK;
+}
+}  // extern "C"
+extern "C" {
 // ------------------------------------------------------------------------------------------------ MindSpore AOT
 // Entry points with the signature MindSpore's ops.Custom(func_type="aot") calls:
 //     int f(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes, void* stream, void* extra)

@@ -24,6 +24,25 @@ def _load():
 lib = _load()
 
 vp, i, f, ll, u64 = c_void_p, c_int, c_float, c_longlong, c_uint64
+
+HPVG_MAX_LEVELS, HPVG_BLOCK_LAYERS = 16, 8
+
+
+class HpvgBlock(ctypes.Structure):
+    """include/hpvg.h: HpvgBlock."""
+    _fields_ = [("n_layers", c_int), ("cin", c_int * HPVG_BLOCK_LAYERS),
+                ("wimg", (c_void_p * 2) * HPVG_BLOCK_LAYERS), ("scale", c_void_p * HPVG_BLOCK_LAYERS),
+                ("shift", c_void_p * HPVG_BLOCK_LAYERS)]
+
+
+class HpvgGenerator(ctypes.Structure):
+    """include/hpvg.h: HpvgGenerator (description of a prepared generator for hpvg_generator_sample)."""
+    _fields_ = [("n_stages", c_int), ("nc_im", c_int), ("latent_dim", c_int),
+                ("T", c_int * HPVG_MAX_LEVELS), ("H", c_int * HPVG_MAX_LEVELS), ("W", c_int * HPVG_MAX_LEVELS),
+                ("noise_amp", c_float * HPVG_MAX_LEVELS), ("noise_seed", c_uint64 * HPVG_MAX_LEVELS),
+                ("decoder", HpvgBlock), ("body", HpvgBlock * HPVG_MAX_LEVELS)]
+
+
 _SIGS = {
     "hpvg_version": ([], c_int),
     "hpvg_last_error": ([], c_char_p),
@@ -56,6 +75,8 @@ _SIGS = {
     "hpvg_graph_destroy": ([vp], c_int),
     "hpvg_launch_count": ([], ll),
     "hpvg_set_pdl": ([i], c_int),
+    "hpvg_generator_sample_workspace": ([POINTER(HpvgGenerator), i], c_size_t),
+    "hpvg_generator_sample": ([POINTER(HpvgGenerator), vp, i, u64, vp, vp, vp, c_size_t, vp], c_int),
     "hpvg_pack_cl": ([vp, i, i, i, i, i, vp, i, i, i, vp], c_int),
     "hpvg_unpack_cl": ([vp, i, i, i, i, i, i, i, vp, vp], c_int),
     "hpvg_conv_wimg_bytes": ([i], c_int),

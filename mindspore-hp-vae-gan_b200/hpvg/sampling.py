@@ -63,6 +63,80 @@ def fold_seed(netG, seed):
     netG.noise_seed = (base ^ x ^ (x >> 31)) & 0x7FFFFFFFFFFFFFFF
 
 
+class FusedSampler:
+    """The generator's random-mode forward (eval_video.py:67-76 -> networks_3d.py:406-451) as ONE C call per batch:
+    `hpvg_generator_sample` (include/hpvg.h) enqueues exactly the launches `GeneratorHPVAEGAN.construct(noise_init=z,
+    isRandom=True)` makes, with the same arguments — the clips are bit-identical to that path — from a description of
+    the prepared network (packed filter banks, folded-BatchNorm epilogue vectors) built here once.  bf16 precision
+    mode, eval-mode BatchNorm.  This is the entry a maintainer binds when the per-layer cells are not needed
+    (INTEGRATION.md, "one call per batch")."""
+
+    def __init__(self, netG, noise_amps, batch, stream=None):
+        import ctypes
+        from ._lib import HPVG_BLOCK_LAYERS, HPVG_MAX_LEVELS, HpvgGenerator, HpvgError, lib
+        if ops.cl_dtype() != BF16:
+            raise HpvgError("FusedSampler: bf16 precision mode only")
+        if netG.training:
+            raise HpvgError("FusedSampler: the generator must be in eval mode (set_train(False))")
+        opt = netG.opt
+        n_stages = len(netG.body)
+        if n_stages + 1 > HPVG_MAX_LEVELS:
+            raise HpvgError("FusedSampler: at most %d pyramid levels" % HPVG_MAX_LEVELS)
+        self.net, self.batch = netG, int(batch)
+        g = HpvgGenerator()
+        g.n_stages, g.nc_im, g.latent_dim = n_stages, int(opt.nc_im), int(opt.latent_dim)
+        for l in range(n_stages + 1):
+            g.T[l], g.H[l], g.W[l] = (int(v) for v in netG.stage_shape(l))
+            add = l >= 1 and netG.noise_at(l, True)
+            g.noise_amp[l] = float(noise_amps[l]) if add else 0.0
+            g.noise_seed[l] = ((netG.noise_seed + 0x632BE59BD9B4E019 * l) & 0xFFFFFFFFFFFFFFFF) if add else 0
+        self._keep = []                               # tensors the description points at
+
+        def fill(dst, block):
+            layers = block.layers
+            if len(layers) > HPVG_BLOCK_LAYERS:
+                raise HpvgError("FusedSampler: at most %d layers per block" % HPVG_BLOCK_LAYERS)
+            dst.n_layers = len(layers)
+            for j, layer in enumerate(layers):
+                layer._prepare(False, stream)         # filter bank(s) + (scale, shift) with eval-mode BatchNorm folded in
+                if layer.sn:
+                    raise HpvgError("FusedSampler: spectrally normalised layers are not part of the generator")
+                dst.cin[j] = int(layer.cin)
+                for h, img in enumerate(layer._wimgs):
+                    dst.wimg[j][h] = img.ptr
+                dst.scale[j] = layer._aff.ptr
+                dst.shift[j] = layer._aff.ptr + 256
+                self._keep += list(layer._wimgs) + [layer._aff]
+
+        fill(g.decoder, netG.decoder)
+        for sidx in range(n_stages):
+            fill(g.body[sidx], netG.body[sidx])
+        self.desc = g
+        nbytes = int(lib.hpvg_generator_sample_workspace(ctypes.byref(g), self.batch))
+        if nbytes <= 0:
+            raise HpvgError("FusedSampler: bad generator description")
+        self.ws = Tensor(((nbytes + 3) // 4,), F32)
+        self.ws_bytes = nbytes
+        self.out_shape = (int(opt.nc_im),) + tuple(int(v) for v in netG.stage_shape(n_stages))
+
+    def __call__(self, z, sample_base=None, out=None, vae_out=None, stream=None):
+        """z: fp32 (n <= batch, latent_dim, T0, H0, W0) device tensor -> fp32 (n, nc_im, T, H, W)."""
+        import ctypes
+        from ._lib import check, lib
+        n = int(z.shape[0])
+        if n > self.batch:
+            raise ValueError("FusedSampler built for batches of %d" % self.batch)
+        if sample_base is None:
+            sample_base = self.net.sample_counter
+        if out is None:
+            out = Tensor((n,) + self.out_shape, F32)
+        check(lib.hpvg_generator_sample(ctypes.byref(self.desc), z.ptr, n, int(sample_base), out.ptr,
+                                        None if vae_out is None else vae_out.ptr, self.ws.ptr, self.ws_bytes,
+                                        None if stream is None else stream.handle), "generator_sample")
+        self.net.sample_counter = int(sample_base) + n
+        return out
+
+
 class SamplePipeline:
     """eval_video.py:53-82 as a stream: per chunk of `batch` samples
          host draw of z's random numbers (uniforms; worker threads, straight into pinned memory)  ->  H2D on a copy
@@ -71,7 +145,7 @@ class SamplePipeline:
     chunk i.  noise="device": z is drawn by the device Philox generator keyed by (seed, sample index) instead — no host
     draw, no H2D (the clips differ from the host-noise ones; stated wherever it is used)."""
 
-    def __init__(self, netG, noise_amps, batch, seed=0, stream=None, threads=None, noise="host", depth=3):
+    def __init__(self, netG, noise_amps, batch, seed=0, stream=None, threads=None, noise="host", depth=3, fused=False):
         from concurrent.futures import ThreadPoolExecutor
         from .runtime import Event, PinnedBuffer, Stream
         if noise not in ("host", "device"):
@@ -93,6 +167,9 @@ class SamplePipeline:
             if noise == "host" else None
         self.h2d_bytes = self.d2h_bytes = 0
         fold_seed(netG, seed)
+        # fused=True: one C call per chunk (FusedSampler) instead of the per-layer launches from Python; same clips
+        self.fused = FusedSampler(netG, self.amps, self.batch, stream=self.st) if fused else None
+        self.fused_out = [None, None]
 
     def _draw_async(self, k, chunk):
         """Fill pinned z buffer k with the draws of `chunk` on the worker threads -> list of futures."""
@@ -142,7 +219,13 @@ class SamplePipeline:
                 st.wait_event(self.d2h_done[o])       # clip tensor / pinned buffer o is free again
             self.net.sample_counter = chunk[0]        # device Philox noise keyed by (seed, GLOBAL sample index, element)
             self.net.out_slot = o
-            x, _ = self.net(zd, self.amps, noise_init=zd, isRandom=True, stream=st)
+            if self.fused is not None:
+                if self.fused_out[o] is None:
+                    self.fused_out[o] = Tensor((self.batch,) + self.fused.out_shape, F32)
+                xo = self.fused_out[o] if n == self.batch else self.fused_out[o].view((n,) + self.fused.out_shape, F32, 0)
+                x = self.fused(zd, sample_base=chunk[0], out=xo, stream=st)
+            else:
+                x, _ = self.net(zd, self.amps, noise_init=zd, isRandom=True, stream=st)
             ev = Event(); ev.record(st); self.gen_done[k] = ev
             if self.out_host[o] is None or self.out_host[o].nbytes < x.nbytes:
                 self.out_host[o] = self._Pinned(int(np.prod((self.batch,) + tuple(x.shape[1:]))) * 4)
