@@ -335,6 +335,12 @@ typedef struct {
   HpvgBlock decoder;
   HpvgBlock body[HPVG_MAX_LEVELS];          /* body[s] produces level s + 1 */
 } HpvgGenerator;
+/* One block in eval mode (ConvBlock3D x (n_layers - 1) + the 64 -> nc_im tail, networks_3d.py:377-381,395-401):
+ * d_out = tanh(block(x) [+ d_residual]).  d_x_cl: bf16 channels-last (N,T,H,W,x_pitch): x_pitch = 8 for a refinement
+ * block's padded input, 64 or 128 for the decoder.  Workspace: hpvg_block_fwd_eval_workspace() bytes. */
+size_t hpvg_block_fwd_eval_workspace(const HpvgBlock* b, int N, int T, int H, int W);
+int hpvg_block_fwd_eval(const HpvgBlock* b, int nc_im, int N, int T, int H, int W, const void* d_x_cl, int x_pitch,
+                        const float* d_residual, float* d_out, void* d_workspace, size_t workspace_bytes, void* stream);
 size_t hpvg_generator_sample_workspace(const HpvgGenerator* g, int N);
 /* d_z: fp32 (N, latent_dim, T0, H0, W0); d_out: fp32 (N, nc_im, T, H, W) of the finest level; d_vae_out: optional fp32
  * (N, nc_im, T0, H0, W0) decoder output; sample_base: index of the batch's first sample (keys the device noise, so a

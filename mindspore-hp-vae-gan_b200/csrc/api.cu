@@ -852,6 +852,23 @@ int sample_block(const HpvgBlock& b, int nc_im, int N, int T, int H, int W, cons
 }
 }  // namespace
 extern "C" {
+size_t hpvg_block_fwd_eval_workspace(const HpvgBlock* b, int N, int T, int H, int W) {
+  if (!b || N <= 0 || T <= 0 || H <= 0 || W <= 0) return 0;
+  const size_t v = static_cast<size_t>(N) * T * H * W;
+  return 2 * al256(v * 64 * 2) + (b->cin[0] == 128 ? al256(v * 64 * 4) : 0);
+}
+int hpvg_block_fwd_eval(const HpvgBlock* b, int nc_im, int N, int T, int H, int W, const void* x, int x_pitch,
+                        const float* residual, float* out, void* workspace, size_t workspace_bytes, void* st) {
+  if (!b || !x || !out || !workspace) return fail(HPVG_E_ARG, "block_fwd_eval: null argument");
+  if (N <= 0) return HPVG_OK;
+  if (nc_im < 1 || nc_im > 4) return fail(HPVG_E_ARG, "block_fwd_eval: nc_im 1..4");
+  if (workspace_bytes < hpvg_block_fwd_eval_workspace(b, N, T, H, W)) return fail(HPVG_E_ARG, "block_fwd_eval: workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(HPVG_E_ARG, "block_fwd_eval: workspace not 256-byte aligned");
+  const size_t a = al256(static_cast<size_t>(N) * T * H * W * 64 * 2);
+  char* ws = static_cast<char*>(workspace);
+  return sample_block(*b, nc_im, N, T, H, W, x, x_pitch, ws, ws + a, reinterpret_cast<float*>(ws + 2 * a), residual, out,
+                      st);
+}
 size_t hpvg_generator_sample_workspace(const HpvgGenerator* g, int N) {
   if (!g || N <= 0 || g->n_stages < 0 || g->n_stages >= HPVG_MAX_LEVELS) return 0;
   return sample_ws_layout(g, N).total;

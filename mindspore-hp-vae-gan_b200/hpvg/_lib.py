@@ -75,6 +75,8 @@ _SIGS = {
     "hpvg_graph_destroy": ([vp], c_int),
     "hpvg_launch_count": ([], ll),
     "hpvg_set_pdl": ([i], c_int),
+    "hpvg_block_fwd_eval_workspace": ([POINTER(HpvgBlock), i, i, i, i], c_size_t),
+    "hpvg_block_fwd_eval": ([POINTER(HpvgBlock), i, i, i, i, i, vp, i, vp, vp, vp, c_size_t, vp], c_int),
     "hpvg_generator_sample_workspace": ([POINTER(HpvgGenerator), i], c_size_t),
     "hpvg_generator_sample": ([POINTER(HpvgGenerator), vp, i, u64, vp, vp, vp, c_size_t, vp], c_int),
     "hpvg_pack_cl": ([vp, i, i, i, i, i, vp, i, i, i, vp], c_int),

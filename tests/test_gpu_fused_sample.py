@@ -91,3 +91,29 @@ def test_fused_entry_rejects_bad_arguments(hpvg_gpu):
     with pytest.raises(hp.HpvgError):
         sampling.FusedSampler(net, [1.0, 0.0, 0.0], batch=2)
     net.set_train(False)
+
+
+def test_block_fwd_eval_is_bit_identical_to_the_layer_path(hpvg_gpu):
+    """hpvg_block_fwd_eval: one refinement block (head 3->64, 3 x 64->64, tail 64->3 + residual, tanh) as one C call."""
+    import ctypes
+    hp = hpvg_gpu
+    from hpvg import ops, sampling
+    net, opt = _build(hp, {}, 4, seed=8)
+    fused = sampling.FusedSampler(net, [1.0, 0.0, 0.0, 0.3, 0.2], batch=2)
+    rng = np.random.default_rng(9)
+    size = net.stage_shape(4)
+    prev = hp.from_numpy(np.tanh(rng.standard_normal((2, 3) + tuple(net.stage_shape(3)))).astype(np.float32))
+    up, xin = ops.upsample_noise_pack(prev, size, amp=0.2, seed=1234, sample_base=3)
+    ref = net._run_block(net.body[3], xin, up, "t", None).numpy().copy()
+    blk = fused.desc.body[3]
+    nb = int(hp.lib.hpvg_block_fwd_eval_workspace(ctypes.byref(blk), 2, *size))
+    ws = hp.Tensor((nb // 4 + 1,), hp.F32)
+    out = hp.Tensor(ref.shape, hp.F32)
+    rc = hp.lib.hpvg_block_fwd_eval(ctypes.byref(blk), 3, 2, size[0], size[1], size[2], xin.ptr, 8, up.ptr, out.ptr, ws.ptr,
+                                    nb, None)
+    assert rc == 0, hp.lib.hpvg_last_error()
+    hp.device_sync()
+    assert np.array_equal(out.numpy(), ref)
+    # too small a workspace is refused before any launch
+    assert hp.lib.hpvg_block_fwd_eval(ctypes.byref(blk), 3, 2, size[0], size[1], size[2], xin.ptr, 8, up.ptr, out.ptr,
+                                      ws.ptr, 16, None) != 0
