@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """SASS evidence without a GPU: per kernel of the built objects, the count of the Blackwell-specific opcodes
 (UTCHMMA = tcgen05.mma, UTMALDG / UTMASTG = TMA tensor load / store, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit,
-UBLKCP = bulk copy, SYNCS = mbarrier) plus the classic ones a recompiled sm_90 kernel would show instead (HMMA, LDGSTS).
+UBLKCP = bulk copy, SYNCS = mbarrier, ACQBULK / PREEXIT = griddepcontrol.wait / launch_dependents of the programmatic
+dependent launch) plus the classic ones a recompiled sm_90 kernel would show instead (HMMA, LDGSTS).
 usage: tools/sass_histogram.py > profiles/r2_sass_histogram.txt"""
 import collections
 import glob
@@ -11,6 +12,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WATCH = ["UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UTMAPF", "LDTM", "STTM", "UTCBAR", "UBLKCP", "SYNCS", "UTCATOMSWS",
+         "ACQBULK", "PREEXIT",
          "HMMA", "IMMA", "LDGSTS", "LDG", "STG", "LDS", "STS", "ATOM", "RED", "BAR", "MUFU", "FFMA", "DFMA"]
 
 for obj in sorted(glob.glob(os.path.join(ROOT, "mindspore-hp-vae-gan_b200", "build", "*.o"))):
