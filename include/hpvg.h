@@ -280,6 +280,12 @@ int hpvg_colsum_cl_f32(const float* d_g, long long voxels, float* d_out, int acc
  * whose convolutions run on the stride-1 zero-padded kernels above. NT = N*T planes of Hi x Wi voxels. */
 int hpvg_slice_act_cl(const void* d_in, int NT, int Hi, int Wi, int C, int Ho, int Wo, int h0, int w0, int sh, int sw,
                       int relu, void* d_out, void* stream);
+/* nn.Pad(mode='REFLECT') of a channels-last tensor (N,T,H,W,voxel_bytes) by pad_t frames and pad_hw rows / columns on
+ * both sides (reference networks_3d.py:65-68, networks_2d.py: the bias-free `bn=False` branch of ConvBlock3DSN / 2DSN):
+ * d_out is (N, T+2*pad_t, H+2*pad_hw, W+2*pad_hw, voxel_bytes).  The reference's pad_mode='valid' convolution of the
+ * padded tensor is then hpvg_conv_cl on it followed by the interior crop hpvg_slice_act_cl(h0 = w0 = 1). */
+int hpvg_reflect_pad_cl(const void* d_in, int N, int T, int H, int W, int voxel_bytes, int pad_t, int pad_hw, void* d_out,
+                        void* stream);
 /* gz = ga * LeakyReLU'(a), a = stored activation (bf16 cl, elems % 8 == 0) */
 int hpvg_lrelu_bwd_cl(const void* d_ga, const void* d_a, long long elems, void* d_gz, void* stream);
 /* BatchNorm(train)+act backward on (voxels, 64) bf16: d_saved = (scale, shift, mean, invstd) from the forward

@@ -677,6 +677,15 @@ int hpvg_slice_act_cl(const void* in, int NT, int Hi, int Wi, int C, int Ho, int
                            static_cast<__nv_bfloat16*>(out), S(st)), 1);
   return HPVG_OK;
 }
+int hpvg_reflect_pad_cl(const void* in, int N, int T, int H, int W, int voxel_bytes, int pad_t, int pad_hw, void* out,
+                        void* st) {
+  if (N <= 0) return HPVG_OK;
+  if (!in || !out || T < 1 || H < 1 || W < 1 || voxel_bytes < 16 || (voxel_bytes & 15) || pad_t < 0 || pad_hw < 0)
+    return fail(HPVG_E_ARG, "reflect_pad_cl: bad geometry (voxels are multiples of 16 bytes)");
+  if (pad_t >= T || pad_hw >= H || pad_hw >= W) return fail(HPVG_E_ARG, "reflect_pad_cl: padding must be smaller than the axis");
+  KL(hpvg::ew_reflect_pad_cl(in, N, T, H, W, voxel_bytes, pad_t, pad_hw, out, S(st)), 1);
+  return HPVG_OK;
+}
 int hpvg_lrelu_bwd_cl(const void* ga, const void* a, long long elems, void* gz, void* st) {
   if (elems <= 0) return HPVG_OK;
   if (elems & 7) return fail(HPVG_E_ARG, "lrelu_bwd_cl: element count must be a multiple of 8");

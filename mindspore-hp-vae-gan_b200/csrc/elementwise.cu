@@ -2463,6 +2463,34 @@ cudaError_t ew_slice_act_cl(const __nv_bfloat16* in, int NT, int Hi, int Wi, int
   return cudaGetLastError();
 }
 
+// nn.Pad(mode='REFLECT') on a channels-last tensor (reference networks_3d.py:65-68, the bias-free `bn=False` branch of
+// ConvBlock3DSN): out[n, t, h, w, :] = in[n, r(t - pt, T), r(h - ph, H), r(w - ph, W), :], r = mirror without repeating
+// the edge.  One 16-byte group per thread (any element type: q16 = 16-byte groups per voxel).
+__device__ __forceinline__ int reflect_index(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+__global__ void reflect_pad_cl_kernel(const uint4* __restrict__ in, int T, int H, int W, int q16, int pt, int ph,
+                                      long long total, uint4* __restrict__ out) {
+  pdl_grid_sync();
+  const int To = T + 2 * pt, Ho = H + 2 * ph, Wo = W + 2 * ph;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % q16);
+    long long v = i / q16;
+    const int wo = static_cast<int>(v % Wo); v /= Wo;
+    const int ho = static_cast<int>(v % Ho); v /= Ho;
+    const int to = static_cast<int>(v % To); v /= To;      // v = n
+    const int t = reflect_index(to - pt, T), h = reflect_index(ho - ph, H), w = reflect_index(wo - ph, W);
+    out[i] = __ldg(in + (((v * T + t) * H + h) * W + w) * q16 + g);
+  }
+}
+cudaError_t ew_reflect_pad_cl(const void* in, int N, int T, int H, int W, int voxel_bytes, int pt, int ph, void* out,
+                              cudaStream_t st) {
+  const int q16 = voxel_bytes / 16;
+  const long long total = static_cast<long long>(N) * (T + 2 * pt) * (H + 2 * ph) * (W + 2 * ph) * q16;
+  launch(reflect_pad_cl_kernel, grid_for(total, 256), 256, 0, st, reinterpret_cast<const uint4*>(in), T, H, W, q16, pt, ph,
+         total, reinterpret_cast<uint4*>(out));
+  return cudaGetLastError();
+}
+
 // ----------------------------------------------------------------------------------------------- host-drawn noise
 // z <- N(0,1) from UNIFORMS drawn on the host: the host draws the random numbers (numpy, counter-based per sample —
 // the reference draws its z on the host too, eval_video.py:67), 3.9x cheaper per value as uniforms than as ziggurat

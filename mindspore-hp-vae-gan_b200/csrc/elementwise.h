@@ -142,6 +142,8 @@ cudaError_t ew_colsum_cl_f32(const float* g, long long voxels, double* scratch, 
                              int accumulate, cudaStream_t st);
 
 // strided window of a bf16 channels-last tensor (+ optional ReLU): out = act(in[.., h0 + ho*sh, w0 + wo*sw, :])
+cudaError_t ew_reflect_pad_cl(const void* in, int N, int T, int H, int W, int voxel_bytes, int pt, int ph, void* out,
+                              cudaStream_t st);
 cudaError_t ew_slice_act_cl(const __nv_bfloat16* in, int NT, int Hi, int Wi, int C, int Ho, int Wo, int h0, int w0, int sh,
                             int sw, int relu, __nv_bfloat16* out, cudaStream_t st);
 

@@ -114,6 +114,7 @@ _SIGS = {
     "hpvg_reparam_bwd": ([vp, vp, vp, ll, vp, vp, vp], c_int),
     "hpvg_conv_wgrad_cl": ([vp, i, vp, i, i, i, i, i, vp, i, i, i, i, i, i, i, f, vp], c_int),
     "hpvg_lrelu_bwd_cl": ([vp, vp, ll, vp, vp], c_int),
+    "hpvg_reflect_pad_cl": ([vp, i, i, i, i, i, i, i, vp, vp], c_int),
     "hpvg_slice_act_cl": ([vp, i, i, i, i, i, i, i, i, i, i, i, vp, vp], c_int),
     "hpvg_bn_bwd_cl": ([vp, vp, ll, vp, i, vp, vp, vp, i, vp], c_int),
     "hpvg_colsum_cl": ([vp, ll, vp, i, vp], c_int),

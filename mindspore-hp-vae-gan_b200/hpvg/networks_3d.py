@@ -289,6 +289,45 @@ class ConvLayer(Cell):
                                  residual=residual, out=out, wimgs=self._wimgs, stream=stream)
 
 
+class ReflectConvLayer(ConvLayer):
+    """The `bn=False` branch of ConvBlock3DSN / ConvBlock2DSN (networks_3d.py:64-71): nn.Pad(REFLECT) by one voxel on
+    every spatial (and temporal) side, then a plain bias-free convolution with pad_mode='valid' [+ activation].  Computed
+    as reflect pad -> the zero-padded conv kernel on the padded tensor -> its interior (the interior of a 'same'
+    convolution never touches the zero padding, so it IS the valid convolution).  Unreachable from the reference's
+    drivers (only FeatureExtractor(return_linear=True) builds it): forward only.  In the SequentialCell the conv is
+    cell 1 (after the Pad), hence the parameter name `1.weight`; the 3-D cell has no bias, the 2-D one has."""
+
+    def __init__(self, cin, cout, act=None, kt=3, rng=None):
+        super().__init__(cin, cout, act=act, conv_prefix="1.", kt=kt, rng=rng)
+        self.has_bias = kt == 1      # networks_3d.py:70 has_bias=False ; networks_2d.py:68 has_bias=True
+
+    def parameters_dict(self, prefix=""):
+        out = {prefix + self.conv_prefix + "weight": self.p["weight"]}
+        if self.has_bias:
+            out[prefix + self.conv_prefix + "bias"] = self.p["bias"]
+        return out
+
+    def forward_cl(self, x_cl, residual=None, out=None, ws=None, tag="", stream=None, saved=None, stats=None, raw=None):
+        if saved is not None:
+            raise HpvgError("ReflectConvLayer has no backward (the branch is unreachable from the reference's trainers)")
+        if x_cl.dtype != BF16 or self.cout != 64:
+            raise HpvgError("ReflectConvLayer: bf16 precision mode, 64 output channels")
+        N, T, H, W, _ = x_cl.shape
+        pt = 1 if self.kt == 3 else 0
+        xp = ops.reflect_pad_cl(x_cl, pad_t=pt, pad_hw=1, stream=stream)
+        self._prepare(False, stream, x_cl.dtype)          # filter bank + (1, 0) epilogue vectors (the bias stays zero)
+        yp = ops.conv3d_cl_any(xp, self.p["weight"], self._aff, self.act, self.cin, self.cout, wimgs=self._wimgs,
+                               stream=stream)
+        if out is None:
+            out = Tensor((N, T, H, W, self.cout), BF16)
+        plane = (H + 2) * (W + 2) * self.cout * 2
+        for n in range(N):                                 # frames pt .. pt+T-1 of sample n, rows / columns 1 .. H / W
+            src = yp.view((1, T, H + 2, W + 2, self.cout), BF16, (n * (T + 2 * pt) + pt) * plane)
+            dst = out.view((1, T, H, W, self.cout), BF16, n * T * H * W * self.cout * 2)
+            ops.slice_act_cl(src, h0=1, w0=1, out_hw=(H, W), out=dst, stream=stream)
+        return out
+
+
 def sn_prepare_batch(layers, stream=None, entries=None):
     """Run the power iteration of every spectrally normalised layer in `layers` in one launch and mark them fresh."""
     sn = [l for l in layers if l.sn]
@@ -333,8 +372,7 @@ def ConvBlock3DSN(in_channel, out_channel, ker_size=3, padding=1, stride=1, bn=T
     """networks_3d.py:57-73: `bn=True` selects the spectrally normalised conv (there is no BatchNorm in it)."""
     _check_geometry(ker_size, padding, stride)
     if not bn:
-        raise HpvgError("ConvBlock3DSN(bn=False) (reflect-pad, bias-free) is unreachable in the reference's default "
-                        "path and is not implemented")
+        return ReflectConvLayer(in_channel, out_channel, act=act, rng=rng, kt=kt)
     return ConvLayer(in_channel, out_channel, sn=True, act=act, rng=rng, kt=kt)
 
 
@@ -367,13 +405,18 @@ class FeatureExtractor(Sequential):
 
     def __init__(self, in_channel, out_channel, ker_size, padding, stride, num_blocks=2, return_linear=False, rng=None,
                  kt=3):
-        if return_linear:
-            raise HpvgError("FeatureExtractor(return_linear=True) is never used by the reference; not implemented")
         layers = [ConvBlock3DSN(in_channel, out_channel, ker_size, padding, stride, rng=rng, kt=kt)]
         for _ in range(num_blocks - 1):
             layers.append(ConvBlock3DSN(out_channel, out_channel, ker_size, padding, stride, rng=rng, kt=kt))
-        layers.append(ConvBlock3DSN(out_channel, out_channel, ker_size, padding, stride, rng=rng, kt=kt))
+        # return_linear (networks_3d.py:83-84): the last block is the bias-free reflect-padded conv without activation
+        layers.append(ConvBlock3DSN(out_channel, out_channel, ker_size, padding, stride, rng=rng, kt=kt,
+                                    bn=not return_linear, act=None if return_linear else "lrelu"))
         super().__init__(layers)
+
+    def construct_cl(self, x_cl, stream=None):
+        for layer in self.layers:
+            x_cl = layer.forward_cl(x_cl, stream=stream)
+        return x_cl
 
 
 class _Wrap(Sequential):

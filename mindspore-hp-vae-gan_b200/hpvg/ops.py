@@ -661,6 +661,16 @@ def slice_act_cl(x_cl, h0=0, w0=0, sh=1, sw=1, out_hw=None, relu=False, out=None
     return out
 
 
+def reflect_pad_cl(x_cl, pad_t=1, pad_hw=1, out=None, stream=None):
+    """nn.Pad(mode='REFLECT') of a channels-last tensor (N,T,H,W,C) (reference networks_3d.py:65-68)."""
+    N, T, H, W, C = x_cl.shape
+    if out is None:
+        out = Tensor((N, T + 2 * pad_t, H + 2 * pad_hw, W + 2 * pad_hw, C), x_cl.dtype)
+    check(lib.hpvg_reflect_pad_cl(_p(x_cl), N, T, H, W, C * _isz(x_cl), int(pad_t), int(pad_hw), _p(out), _s(stream)),
+          "reflect_pad_cl")
+    return out
+
+
 def lrelu_bwd_cl(ga, a, out=None, stream=None):
     out = out or Tensor(ga.shape, ga.dtype)
     fn = lib.hpvg_lrelu_bwd_cl_f32 if ga.dtype == F32 else lib.hpvg_lrelu_bwd_cl

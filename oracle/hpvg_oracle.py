@@ -427,6 +427,15 @@ def lrelu(x):
     return F.leaky_relu(x, LRELU_SLOPE)
 
 
+def reflect_conv(x, w, b=None, act=False):
+    """The `bn=False` branch of ConvBlock3DSN / ConvBlock2DSN (reference networks_3d.py:64-73, networks_2d.py:63-72):
+    nn.Pad(mode='REFLECT') by one voxel on every spatial (and temporal) side, then a pad_mode='valid' convolution
+    (bias-free in 3-D, with bias in 2-D) [+ LeakyReLU(0.2)]."""
+    nd = w.dim() - 2
+    y = F.conv3d(F.pad(x, (1,) * 6, mode="reflect"), w, b) if nd == 3 else F.conv2d(F.pad(x, (1,) * 4, mode="reflect"), w, b)
+    return lrelu(y) if act else y
+
+
 def sn_power_iteration(w, u, v, eps=1e-12):
     """spectral_norm.py:142-151: one power iteration; returns (sigma, u_new, v_new).  u, v are constants for
     autodiff (they are re-assigned onto non-trainable Parameters, spectral_norm.py:147-148)."""

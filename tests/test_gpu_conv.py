@@ -7,6 +7,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from oracle import hpvg_oracle as orc
 from util import bf16_round, rel_l2
 
 pytestmark = pytest.mark.gpu
@@ -223,3 +224,44 @@ def test_conv2d_is_t1(hpvg_gpu):
 def test_conv_empty_input_is_noop(hpvg_gpu):
     hp = hpvg_gpu
     assert hp.lib.hpvg_conv_cl(0, 0, 4, 8, 8, None, 64, None, None, None, 0, 0, None, 64, 0, 64, None, None, None, 0, None) == 0
+
+
+@pytest.mark.parametrize("nd", [3, 2])
+def test_reflect_pad_branch_of_convblock_sn(hpvg_gpu, nd):
+    """ConvBlock3DSN / ConvBlock2DSN(bn=False): nn.Pad(REFLECT) + pad_mode='valid' conv (reference networks_3d.py:64-73,
+    networks_2d.py:63-72; reached through FeatureExtractor(return_linear=True)).  Pad bit-exact, conv within the bf16
+    tolerance of the fp32 oracle."""
+    hp = hpvg_gpu
+    import torch
+    from hpvg import networks_2d as n2, networks_3d as n3, ops
+    rng = np.random.default_rng(21 + nd)
+    N, T, H, W = (2, 4, 11, 13) if nd == 3 else (2, 1, 14, 9)
+    x = rng.standard_normal((N, 64, T, H, W)).astype(np.float32)
+    x_cl = ops.pack_cl(hp.from_numpy(x))
+    # the pad itself, against numpy
+    xp = ops.reflect_pad_cl(x_cl, pad_t=1 if nd == 3 else 0, pad_hw=1)
+    got = ops.unpack_cl(xp).numpy()
+    pads = ((0, 0), (0, 0), (1, 1) if nd == 3 else (0, 0), (1, 1), (1, 1))
+    ref = np.pad(ops.unpack_cl(x_cl).numpy(), pads, mode="reflect")
+    assert np.array_equal(got, ref)
+    # the cell
+    mk = n3.ConvBlock3DSN if nd == 3 else n2.ConvBlock2DSN
+    cell = mk(64, 64, 3, 1, 1, bn=False, act="lrelu", rng=rng)
+    names = sorted(cell.parameters_dict())
+    assert names == (["1.weight"] if nd == 3 else ["1.bias", "1.weight"])
+    w = cell.p["weight"].numpy()
+    b = rng.standard_normal(64).astype(np.float32) * 0.1 if nd == 2 else None
+    if b is not None:
+        cell.load_parameters({"1.weight": w, "1.bias": b})
+    y = ops.unpack_cl(cell.forward_cl(x_cl)).numpy()
+    xt = torch.from_numpy(x if nd == 3 else x[:, :, 0])
+    with torch.no_grad():
+        yr = orc.reflect_conv(xt, torch.from_numpy(w), None if b is None else torch.from_numpy(b), act=True).numpy()
+    if nd == 2:
+        yr = yr[:, :, None]
+    assert y.shape == yr.shape
+    assert rel_l2(y, yr) < 1e-2, rel_l2(y, yr)
+    # FeatureExtractor(return_linear=True): last block is that cell without activation
+    fe = (n3.FeatureExtractor if nd == 3 else n2.FeatureExtractor)(64, 64, 3, 1, 1, num_blocks=2, return_linear=True, rng=rng)
+    assert isinstance(fe.layers[-1], n3.ReflectConvLayer) and fe.layers[-1].act == ops.ACT_NONE
+    assert fe.construct_cl(x_cl).shape == x_cl.shape
