@@ -17,7 +17,12 @@
 //   * FP32 accumulators in TMEM, double buffered: the epilogue of plane p (TMEM -> registers -> per-channel
 //     scale/shift (+bias, folded BN, 1/sigma of spectral norm) -> LeakyReLU/tanh -> bf16/f32 store) overlaps the
 //     MMAs of plane p+1.
-//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only) + TMEM owner, warps 2..5 = epilogue.
+//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only) + TMEM owner, warps 2..5 = epilogue
+//     (the head variant has a second epilogue group, warps 6..9, one group per accumulator stage: Cfg::EPI_GROUPS).
+//   * the MMA-issuing thread is on the critical path (the tensor pipe runs only a few MMAs behind it): descriptors are
+//     one add away from two built per plane, and the mbarrier waits sit behind already queued MMAs (see the issuer).
+//   * every launch is a programmatic dependent launch (launch.cuh): barrier init and TMEM allocation overlap the tail
+//     of the previous kernel of the stream; global memory is touched only after pdl_grid_sync().
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
