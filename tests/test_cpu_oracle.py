@@ -312,3 +312,36 @@ def test_host_noise_is_counter_based_and_seed_folding_changes_the_device_key():
     k2 = n.noise_seed
     sampling.fold_seed(n, 1)
     assert k1 != k2 and n.noise_seed == k1 and 0 <= k1 < 2 ** 63
+
+
+def test_generator_description_layout_matches_the_c_struct():
+    """include/hpvg.h HpvgGenerator / HpvgBlock against their ctypes mirrors (hpvg/_lib.py): the workspace size the C side
+    computes from a description filled through ctypes must be the documented sum — which it only is when every field
+    sits where the C struct has it (no compute, no GPU)."""
+    import ctypes
+    import hpvg
+    from hpvg._lib import HpvgBlock, HpvgGenerator
+    assert ctypes.sizeof(HpvgBlock) == 4 + 4 * 8 + 4 + 8 * 16 + 8 * 8 + 8 * 8      # int, int[8], pad, ptr[8][2], ptr[8], ptr[8]
+    g = HpvgGenerator()
+    g.n_stages, g.nc_im, g.latent_dim = 2, 3, 128
+    shapes = [(4, 24, 33), (4, 30, 41), (4, 38, 51)]
+    for l, (t, h, w) in enumerate(shapes):
+        g.T[l], g.H[l], g.W[l] = t, h, w
+    g.noise_amp[2] = 0.5
+    g.noise_seed[2] = 0xFFFFFFFFFFFFFFFF
+    g.body[1].n_layers = 5          # a field far into the struct
+    N = 3
+    al = lambda b: (b + 255) // 256 * 256                                       # noqa: E731
+    v0, vmax = 4 * 24 * 33, 4 * 38 * 51
+    want = (al(N * v0 * 128 * 2) + al(N * v0 * 64 * 4) + 2 * al(N * vmax * 64 * 2) + al(N * vmax * 3 * 4) +
+            al(N * vmax * 16) + 2 * al(N * vmax * 3 * 4))
+    assert hpvg.lib.hpvg_generator_sample_workspace(ctypes.byref(g), N) == want
+    assert hpvg.lib.hpvg_generator_sample_workspace(ctypes.byref(g), 0) == 0
+    g.n_stages = 16
+    assert hpvg.lib.hpvg_generator_sample_workspace(ctypes.byref(g), N) == 0     # more levels than HPVG_MAX_LEVELS
+    # argument errors are reported before any launch
+    g.n_stages = 2
+    assert hpvg.lib.hpvg_generator_sample(ctypes.byref(g), None, N, 0, None, None, None, 0, None) == -2
+    blk = HpvgBlock()
+    blk.cin[0] = 128
+    assert hpvg.lib.hpvg_block_fwd_eval_workspace(ctypes.byref(blk), 2, 4, 24, 33) == 2 * al(2 * v0 * 64 * 2) + al(2 * v0 * 64 * 4)
