@@ -350,9 +350,12 @@ int hpvg_block_fwd_eval(const HpvgBlock* b, int nc_im, int N, int T, int H, int 
 size_t hpvg_generator_sample_workspace(const HpvgGenerator* g, int N);
 /* d_z: fp32 (N, latent_dim, T0, H0, W0); d_out: fp32 (N, nc_im, T, H, W) of the finest level; d_vae_out: optional fp32
  * (N, nc_im, T0, H0, W0) decoder output; sample_base: index of the batch's first sample (keys the device noise, so a
- * sample's noise does not depend on how samples are batched or sharded) */
-int hpvg_generator_sample(const HpvgGenerator* g, const float* d_z, int N, uint64_t sample_base, float* d_out,
-                          float* d_vae_out, void* d_workspace, size_t workspace_bytes, void* stream);
+ * sample's noise does not depend on how samples are batched or sharded); d_sample_offset: optional device counter
+ * added to sample_base when the kernels run — the call can then be captured ONCE into a CUDA graph (hpvg_graph_begin /
+ * _end) and replayed for every batch with only that counter and d_z rewritten */
+int hpvg_generator_sample(const HpvgGenerator* g, const float* d_z, int N, uint64_t sample_base,
+                          const uint64_t* d_sample_offset, float* d_out, float* d_vae_out, void* d_workspace,
+                          size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- MindSpore ops.Custom(func_type="aot") entry points
  * int Name(int nparam, void** params, int* ndims, int64_t** shapes, const char** dtypes, void* stream, void* extra)

@@ -882,8 +882,9 @@ size_t hpvg_generator_sample_workspace(const HpvgGenerator* g, int N) {
   if (!g || N <= 0 || g->n_stages < 0 || g->n_stages >= HPVG_MAX_LEVELS) return 0;
   return sample_ws_layout(g, N).total;
 }
-int hpvg_generator_sample(const HpvgGenerator* g, const float* z, int N, uint64_t sample_base, float* out,
-                          float* vae_out, void* workspace, size_t workspace_bytes, void* st) {
+int hpvg_generator_sample(const HpvgGenerator* g, const float* z, int N, uint64_t sample_base,
+                          const uint64_t* d_sample_offset, float* out, float* vae_out, void* workspace,
+                          size_t workspace_bytes, void* st) {
   if (!g || !z || !out || !workspace) return fail(HPVG_E_ARG, "generator_sample: null argument");
   if (N <= 0) return HPVG_OK;
   if (g->n_stages < 0 || g->n_stages >= HPVG_MAX_LEVELS) return fail(HPVG_E_ARG, "generator_sample: 0..15 stages");
@@ -911,7 +912,7 @@ int hpvg_generator_sample(const HpvgGenerator* g, const float* z, int N, uint64_
     const int l = s + 1;
     const float amp = g->noise_amp[l];
     rc = hpvg_upsample_noise_pack(prev, N, g->nc_im, g->T[s], g->H[s], g->W[s], g->T[l], g->H[l], g->W[l], nullptr, amp,
-                                  amp != 0.f ? g->noise_seed[l] : 0, sample_base, nullptr, up, ws + w.xin, st);
+                                  amp != 0.f ? g->noise_seed[l] : 0, sample_base, d_sample_offset, up, ws + w.xin, st);
     if (rc != HPVG_OK) return rc;
     float* o = (s == g->n_stages - 1) ? out : lvl[l & 1];
     rc = sample_block(g->body[s], g->nc_im, N, g->T[l], g->H[l], g->W[l], ws + w.xin, 8, ws + w.act[0], ws + w.act[1],

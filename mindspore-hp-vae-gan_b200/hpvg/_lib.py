@@ -78,7 +78,7 @@ _SIGS = {
     "hpvg_block_fwd_eval_workspace": ([POINTER(HpvgBlock), i, i, i, i], c_size_t),
     "hpvg_block_fwd_eval": ([POINTER(HpvgBlock), i, i, i, i, i, vp, i, vp, vp, vp, c_size_t, vp], c_int),
     "hpvg_generator_sample_workspace": ([POINTER(HpvgGenerator), i], c_size_t),
-    "hpvg_generator_sample": ([POINTER(HpvgGenerator), vp, i, u64, vp, vp, vp, c_size_t, vp], c_int),
+    "hpvg_generator_sample": ([POINTER(HpvgGenerator), vp, i, u64, vp, vp, vp, vp, c_size_t, vp], c_int),
     "hpvg_pack_cl": ([vp, i, i, i, i, i, vp, i, i, i, vp], c_int),
     "hpvg_unpack_cl": ([vp, i, i, i, i, i, i, i, vp, vp], c_int),
     "hpvg_conv_wimg_bytes": ([i], c_int),

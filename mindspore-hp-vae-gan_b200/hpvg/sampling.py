@@ -71,7 +71,11 @@ class FusedSampler:
     mode, eval-mode BatchNorm.  This is the entry a maintainer binds when the per-layer cells are not needed
     (INTEGRATION.md, "one call per batch")."""
 
-    def __init__(self, netG, noise_amps, batch, stream=None):
+    def __init__(self, netG, noise_amps, batch, stream=None, graph=False):
+        """graph=True: the call is captured once per batch size into a CUDA graph (z and the clip live in buffers of the
+        sampler, the sample index in a device counter) and replayed — for small batches, where the ~80 launches of a
+        forward cost more than their kernels (the reference's eval loop generates one sample at a time,
+        eval_video.py:62-76)."""
         import ctypes
         from ._lib import HPVG_BLOCK_LAYERS, HPVG_MAX_LEVELS, HpvgGenerator, HpvgError, lib
         if ops.cl_dtype() != BF16:
@@ -118,6 +122,12 @@ class FusedSampler:
         self.ws = Tensor(((nbytes + 3) // 4,), F32)
         self.ws_bytes = nbytes
         self.out_shape = (int(opt.nc_im),) + tuple(int(v) for v in netG.stage_shape(n_stages))
+        self.graph = bool(graph)
+        self._graphs = {}            # n -> (Graph, z buffer, clip buffer)
+        if self.graph:
+            from .runtime import U64
+            self._offset = Tensor((1,), U64).zero_()   # device counter: first sample index of the batch being generated
+            self._offset_val = 0
 
     def __call__(self, z, sample_base=None, out=None, vae_out=None, stream=None):
         """z: fp32 (n <= batch, latent_dim, T0, H0, W0) device tensor -> fp32 (n, nc_im, T, H, W)."""
@@ -128,13 +138,50 @@ class FusedSampler:
             raise ValueError("FusedSampler built for batches of %d" % self.batch)
         if sample_base is None:
             sample_base = self.net.sample_counter
+        if self.graph:
+            return self._replay(z, n, int(sample_base), out, vae_out, stream)
         if out is None:
             out = Tensor((n,) + self.out_shape, F32)
-        check(lib.hpvg_generator_sample(ctypes.byref(self.desc), z.ptr, n, int(sample_base), out.ptr,
+        check(lib.hpvg_generator_sample(ctypes.byref(self.desc), z.ptr, n, int(sample_base), None, out.ptr,
                                         None if vae_out is None else vae_out.ptr, self.ws.ptr, self.ws_bytes,
                                         None if stream is None else stream.handle), "generator_sample")
         self.net.sample_counter = int(sample_base) + n
         return out
+
+    def _replay(self, z, n, sample_base, out, vae_out, stream):
+        import ctypes
+        from ._lib import HpvgError, check, lib
+        from .runtime import Graph
+        if stream is None:
+            raise HpvgError("FusedSampler(graph=True) needs an explicit stream")
+        if vae_out is not None:
+            raise HpvgError("FusedSampler(graph=True) does not return vae_out")
+        ent = self._graphs.get(n)
+        if ent is None or ent[0].stream is not stream:
+            zbuf = Tensor(tuple(z.shape), F32)
+            obuf = Tensor((n,) + self.out_shape, F32)
+            g = Graph(stream)
+            with g:
+                check(lib.hpvg_generator_sample(ctypes.byref(self.desc), zbuf.ptr, n, 0, self._offset.ptr, obuf.ptr, None,
+                                                self.ws.ptr, self.ws_bytes, stream.handle), "generator_sample")
+            ent = self._graphs[n] = (g, zbuf, obuf)
+        g, zbuf, obuf = ent
+        check(lib.hpvg_d2d(zbuf.ptr, z.ptr, z.nbytes, stream.handle), "d2d")
+        # advance the device counter to this batch's first sample index (a kernel argument: nothing on the host has to
+        # stay unchanged until the stream gets there; uint64 wrap-around makes a step backwards an addition too)
+        check(lib.hpvg_counter_add(self._offset.ptr, (sample_base - self._offset_val) & 0xFFFFFFFFFFFFFFFF,
+                                   stream.handle), "counter_add")
+        self._offset_val = sample_base
+        g.launch()
+        if out is not None:
+            check(lib.hpvg_d2d(out.ptr, obuf.ptr, obuf.nbytes, stream.handle), "d2d")
+        self.net.sample_counter = sample_base + n
+        return out if out is not None else obuf
+
+    def close(self):
+        for g, _, _ in self._graphs.values():
+            g.destroy()
+        self._graphs = {}
 
 
 class SamplePipeline:

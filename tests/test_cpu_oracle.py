@@ -341,7 +341,7 @@ def test_generator_description_layout_matches_the_c_struct():
     assert hpvg.lib.hpvg_generator_sample_workspace(ctypes.byref(g), N) == 0     # more levels than HPVG_MAX_LEVELS
     # argument errors are reported before any launch
     g.n_stages = 2
-    assert hpvg.lib.hpvg_generator_sample(ctypes.byref(g), None, N, 0, None, None, None, 0, None) == -2
+    assert hpvg.lib.hpvg_generator_sample(ctypes.byref(g), None, N, 0, None, None, None, None, 0, None) == -2
     blk = HpvgBlock()
     blk.cin[0] = 128
     assert hpvg.lib.hpvg_block_fwd_eval_workspace(ctypes.byref(blk), 2, 4, 24, 33) == 2 * al(2 * v0 * 64 * 2) + al(2 * v0 * 64 * 4)

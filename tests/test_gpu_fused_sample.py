@@ -117,3 +117,30 @@ def test_block_fwd_eval_is_bit_identical_to_the_layer_path(hpvg_gpu):
     # too small a workspace is refused before any launch
     assert hp.lib.hpvg_block_fwd_eval(ctypes.byref(blk), 3, 2, size[0], size[1], size[2], xin.ptr, 8, up.ptr, out.ptr,
                                       ws.ptr, 16, None) != 0
+
+
+def test_fused_entry_replayed_as_a_cuda_graph(hpvg_gpu):
+    """FusedSampler(graph=True): one capture per batch size, then every batch is a D2D of z, a counter update and a
+    graph launch — the same bits as the direct call, for changing z and sample indices (forwards and backwards)."""
+    hp = hpvg_gpu
+    from hpvg import sampling
+    net, opt = _build(hp, {}, 4, seed=10)
+    amps = [1.0, 0.0, 0.0, 0.3, 0.2]
+    st = hp.Stream()
+    direct = sampling.FusedSampler(net, amps, batch=2, stream=st)
+    graphed = sampling.FusedSampler(net, amps, batch=2, stream=st, graph=True)
+    rng = np.random.default_rng(12)
+    for base in (0, 6, 2, 100):
+        z = hp.from_numpy(rng.standard_normal(sampling.z_init_size(opt, 2)).astype(np.float32))
+        want = direct(z, sample_base=base, stream=st).numpy().copy()
+        got = graphed(z, sample_base=base, stream=st)
+        st.sync()
+        assert np.array_equal(got.numpy(), want), "sample_base %d" % base
+    z1 = hp.from_numpy(rng.standard_normal(sampling.z_init_size(opt, 1)).astype(np.float32))
+    want = direct(z1, sample_base=7, stream=st).numpy().copy()          # a second batch size: a second capture
+    out = hp.Tensor(want.shape, hp.F32)
+    graphed(z1, sample_base=7, out=out, stream=st)
+    st.sync()
+    assert np.array_equal(out.numpy(), want)
+    assert len(graphed._graphs) == 2
+    graphed.close()
