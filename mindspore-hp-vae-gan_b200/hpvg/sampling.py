@@ -312,13 +312,14 @@ def check_d2h(dst, src, nbytes, stream):
 
 
 def generate(netG, noise_amps, num_samples, rank=0, world=1, batch=8, seed=0, stream=None, keep=True, noise="host",
-             threads=None):
+             threads=None, fused=False):
     """Returns (indices, clips) for this rank: clips is a float32 array (n_local, 3, T, H, W) when keep=True.
-    The loop runs as a SamplePipeline (host draw / copies overlapped with the generation)."""
+    The loop runs as a SamplePipeline (host draw / copies overlapped with the generation); fused=True issues every
+    chunk's forward as one C call (hpvg_generator_sample) — the same clips."""
     chunks = local_chunks(num_samples, batch, rank, world)
     idxs = [i for c in chunks for i in c]
     outs = []
-    pipe = SamplePipeline(netG, noise_amps, batch, seed=seed, stream=stream, threads=threads, noise=noise)
+    pipe = SamplePipeline(netG, noise_amps, batch, seed=seed, stream=stream, threads=threads, noise=noise, fused=fused)
     try:
         pipe.run(chunks, (lambda chunk, clips: outs.append(np.array(clips))) if keep else None)
         pipe.st.sync()

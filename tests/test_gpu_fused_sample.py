@@ -77,6 +77,10 @@ def test_pipeline_with_the_fused_entry_gives_the_same_clips(hpvg_gpu):
     assert sorted(got[True]) == [0, 1, 2, 3, 4]
     for i in range(5):
         assert np.array_equal(got[True][i], got[False][i]), "sample %d" % i
+    idx, clips = sampling.generate(net, amps, 5, batch=2, seed=3, fused=True)      # the public loop, fused
+    assert idx == [0, 1, 2, 3, 4]
+    for i in range(5):
+        assert np.array_equal(clips[i], got[False][i])
 
 
 def test_fused_entry_rejects_bad_arguments(hpvg_gpu):
