@@ -265,3 +265,53 @@ def test_reflect_pad_branch_of_convblock_sn(hpvg_gpu, nd):
     fe = (n3.FeatureExtractor if nd == 3 else n2.FeatureExtractor)(64, 64, 3, 1, 1, num_blocks=2, return_linear=True, rng=rng)
     assert isinstance(fe.layers[-1], n3.ReflectConvLayer) and fe.layers[-1].act == ops.ACT_NONE
     assert fe.construct_cl(x_cl).shape == x_cl.shape
+
+
+def _random_shapes(seed, n):
+    """Shapes between the tiny cases above and the full size: several output planes per CTA pair, work ranges that start
+    and end inside a strip, ragged last tiles, T from 1 up."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        out.append((int(rng.integers(1, 4)), int(rng.integers(1, 8)), int(rng.integers(8, 97)), int(rng.integers(8, 120))))
+    return out
+
+
+@pytest.mark.parametrize("shape", _random_shapes(2024, 10) + [(1, 2, 160, 200), (5, 3, 64, 64)])
+def test_conv_variants_on_mid_sized_random_shapes(hpvg_gpu, shape):
+    """64->64 (with and without the fused BatchNorm statistics), head 3->64 and tail 64->3 against the torch-CPU oracle
+    on shapes where a CTA pair owns several output planes (the work partition cuts strips mid-way; the MMA issuer's
+    wait-behind-the-MMAs order, the filter-bank fetch order and the two epilogue groups all see that case)."""
+    hp, ops = hpvg_gpu, hpvg_gpu.ops
+    N, T, H, W = shape
+    rng = np.random.default_rng(abs(hash(shape)) % (2 ** 31))
+    x = bf16_round(rng.standard_normal((N, 64, T, H, W)))
+    w = bf16_round(rng.standard_normal((64, 64, 3, 3, 3)) * 0.05)
+    b = rng.standard_normal(64).astype(np.float32) * 0.1
+    x_cl = ops.pack_cl(hp.from_numpy(x))
+    aff = ops.affine_from_bias(hp.from_numpy(b))
+    ref = _conv_ref(x, w, b, "lrelu")
+    y = ops.unpack_cl(ops.conv3d_cl_any(x_cl, hp.from_numpy(w), aff, ops.ACT_LRELU, 64, 64)).numpy()
+    assert rel_l2(y, ref) < TOL, "conv 64->64 %s rel-L2 %.3e" % (shape, rel_l2(y, ref))
+    # the statistics variant: same output, sums of the values as stored
+    stats = hp.Tensor((2, 64), hp.F64).zero_()
+    y_cl = ops.conv3d_cl_any(x_cl, hp.from_numpy(w), aff, ops.ACT_NONE, 64, 64, stats=stats)
+    ys = ops.unpack_cl(y_cl).numpy()
+    s = stats.numpy()
+    assert np.allclose(s[0], ys.sum(axis=(0, 2, 3, 4), dtype=np.float64), rtol=1e-6, atol=1e-3)
+    assert np.allclose(s[1], (ys.astype(np.float64) ** 2).sum(axis=(0, 2, 3, 4)), rtol=1e-6, atol=1e-3)
+    assert rel_l2(ys, _conv_ref(x, w, b)) < TOL
+    # head 3 -> 64
+    x3 = bf16_round(rng.standard_normal((N, 3, T, H, W)))
+    w3 = bf16_round(rng.standard_normal((64, 3, 3, 3, 3)) * 0.1)
+    x3_cl = ops.pack_cl(hp.from_numpy(x3))
+    y3 = ops.unpack_cl(ops.conv3d_cl_any(x3_cl, hp.from_numpy(w3), aff, ops.ACT_LRELU, 3, 64)).numpy()
+    assert rel_l2(y3, _conv_ref(x3, w3, b, "lrelu")) < TOL, "head %s" % (shape,)
+    # tail 64 -> 3 (+ residual, tanh)
+    wt = bf16_round(rng.standard_normal((3, 64, 3, 3, 3)) * 0.05)
+    bt = rng.standard_normal(3).astype(np.float32) * 0.1
+    res = rng.standard_normal((N, 3, T, H, W)).astype(np.float32) * 0.3
+    yt = ops.conv3d_cl_any(x_cl, hp.from_numpy(wt), ops.affine_from_bias(hp.from_numpy(bt)), ops.ACT_TANH, 64, 3,
+                           residual=hp.from_numpy(res)).numpy()
+    reft = np.tanh(_conv_ref(x, wt, bt) + res)
+    assert rel_l2(yt, reft) < TOL, "tail %s" % (shape,)
