@@ -17,11 +17,13 @@ from .runtime import F32, U64, Event, Graph, HpvgError, Tensor, device_sync, fro
 from .utils import images as uimg
 
 import os as _os
-# The LeakyReLU backward CAN be fused into the producing data-gradient conv (HPVG_ACT_LRELU_MASK), but measured on the
-# same B200 (A/B, finest scale, batch 1) the fused iteration is 0.6 ms SLOWER: at batch 1 the conv is paced by its
-# epilogue, and the extra 128 B/voxel mask load there costs more than the separate pass, which streams at 97 % of the
-# HBM copy bandwidth.  So the fusion is opt-in.
-_MASK_FUSION = bool(_os.environ.get("HPVG_MASK_FUSION"))
+# The LeakyReLU backward is fused into the producing data-gradient conv (HPVG_ACT_LRELU_MASK: the epilogue multiplies by
+# LeakyReLU'(stored activation)) instead of running as a separate pass.  Round 1 measured the fused iteration 0.6 ms
+# SLOWER (the conv was paced by its epilogue and the extra 128 B/voxel mask load cost more than the separate pass at
+# 97 % of the copy bandwidth); with the TMA-store epilogue and the cheaper MMA-issue loop the A/B flipped: 47.2 against
+# 46.4 iter/s for the GAN-phase iteration at 16x192x257 (same box, alternating runs).  HPVG_MASK_FUSION=0 restores the
+# separate pass.
+_MASK_FUSION = _os.environ.get("HPVG_MASK_FUSION", "1") != "0"
 NON_TRAINABLE = ("weight_u", "weight_v", "moving_mean", "moving_variance")
 
 
