@@ -1279,18 +1279,23 @@ __global__ void bn_train_apply_cl_kernel(const __nv_bfloat16* __restrict__ y, lo
     }
   }
   __syncthreads();
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < groups;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(i & 7);
-    const uint4 pk = *reinterpret_cast<const uint4*>(y + i * 8);
+  // a thread's channel group is fixed (block size and grid stride are multiples of 8 groups): its 8 (scale, shift)
+  // pairs live in registers instead of 16 shared-memory reads per 16-byte group; two groups in flight per thread
+  const int g = threadIdx.x & 7;
+  float csc[8], csh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    csc[e] = sc[g * 8 + e];
+    csh[e] = sh[g * 8 + e];
+  }
+  auto one = [&](long long i, const uint4& pk) {
     const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
     uint32_t o[4];
 #pragma unroll
     for (int e2 = 0; e2 < 4; ++e2) {
       float2 f = unpack2(w[e2]);
-      const int c = g * 8 + 2 * e2;
-      f.x = fmaf(f.x, sc[c], sh[c]);
-      f.y = fmaf(f.y, sc[c + 1], sh[c + 1]);
+      f.x = fmaf(f.x, csc[2 * e2], csh[2 * e2]);
+      f.y = fmaf(f.y, csc[2 * e2 + 1], csh[2 * e2 + 1]);
       if (act == 1) {
         f.x = f.x > 0.f ? f.x : 0.2f * f.x;
         f.y = f.y > 0.f ? f.y : 0.2f * f.y;
@@ -1298,7 +1303,16 @@ __global__ void bn_train_apply_cl_kernel(const __nv_bfloat16* __restrict__ y, lo
       o[e2] = pack2(f.x, f.y);
     }
     *reinterpret_cast<uint4*>(x + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + stride < groups; i += 2 * stride) {
+    const uint4 p0 = *reinterpret_cast<const uint4*>(y + i * 8);
+    const uint4 p1 = *reinterpret_cast<const uint4*>(y + (i + stride) * 8);
+    one(i, p0);
+    one(i + stride, p1);
   }
+  if (i < groups) one(i, *reinterpret_cast<const uint4*>(y + i * 8));
 }
 
 // Deferred moving-statistics update for many BatchNorm layers in one launch (block b = layer b): when several
